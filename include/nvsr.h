@@ -1,0 +1,214 @@
+/*
+ * nvsr.h — C-ABI of libnvsr_b200.so: the B200 (sm_100a) ray-rendering hot path of
+ * Neural-Volume-Super-Resolution.
+ *
+ * The reference has no FFI / plugin registry: its seams are module-level Python functions
+ * (SURVEY.md §8b).  Every entry point below therefore names the reference *Python* interface it
+ * replaces (file:line under the reference checkout) — the Python host side in
+ * `neural-volume-super-resolution_b200/` binds these with ctypes and mirrors the reference signatures.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = OK, <0 = NVSR_ERR_*, >0 = cudaError_t.
+ *   - no exceptions, no allocation, no global state: every buffer is a caller-owned DEVICE pointer
+ *     (except where a parameter is documented "host"), every call takes the caller's cudaStream_t
+ *     (as void*) and is asynchronous on that stream.
+ *   - all floating-point tensors are fp32 and row-major unless stated; index tensors are int64.
+ *   - "tile image" = the bf16 feature layout the tcgen05 decoder consumes with one bulk copy per
+ *     128-row tile:  [tile][K/8][128 rows][8 bf16]   (UMMA K-major, no-swizzle canonical layout).
+ */
+#ifndef NVSR_H_
+#define NVSR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVSR_ABI_VERSION 1
+
+#define NVSR_OK 0
+#define NVSR_ERR_INVALID_ARG (-1)
+#define NVSR_ERR_UNSUPPORTED (-2)
+#define NVSR_ERR_ALIGNMENT (-3)
+#define NVSR_ERR_RESOURCE (-4)
+
+#define NVSR_F32 0
+#define NVSR_BF16 1
+
+#define NVSR_TILE_ROWS 128
+#define NVSR_MAX_LAYERS 8
+#define NVSR_MAX_SAMPLES 1024 /* samples per ray handled by the warp-per-ray kernels */
+
+int32_t nvsr_abi_version(void);
+const char* nvsr_status_string(int32_t status);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1  get_ray_bundle            nerf_helpers.py:507-549 (+ meshgrid_xy :396-406, get_focal :432-437)
+ * Rays of image rows [row_begin,row_end) of the (H+2p)x(W+2p) pixel grid, written as
+ * ro, rd : [(row_end-row_begin), W+2p, 3].  Ray index = r*W + c (row-major) — the ordering to keep.
+ * focal_x divides the x term, focal_y the y term (the reference's get_focal quirk is resolved by
+ * the Python caller).  c2w_host: 16 floats, row-major 4x4, HOST memory (copied by value).
+ */
+int32_t nvsr_ray_bundle(int32_t height, int32_t width, float focal_x, float focal_y,
+                        const float* c2w_host, int32_t padding, float offset, int32_t row_begin,
+                        int32_t row_end, float* ro, float* rd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a2/a3  ray preparation of run_one_iter_of_nerf      train_utils.py:210-226, ndc_rays
+ * nerf_helpers.py:578-605.  viewdirs = rd/|rd| (computed from the pre-NDC directions); when
+ * use_ndc != 0, (ro,rd) are mapped to NDC with near plane `ndc_near` (the call site passes 1.0).
+ * Any output may alias nothing; viewdirs may be NULL.
+ */
+int32_t nvsr_prepare_rays(const float* ro_in, const float* rd_in, int64_t n_rays, int32_t use_ndc,
+                          int32_t height, int32_t width, double focal, double ndc_near, float* ro_out,
+                          float* rd_out, float* viewdirs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * plane re-pack (once per scene / per SR inference): reference planes are NCHW fp32 [1,C,Rh,Rw]
+ * (models.py:436-439); the gather reads channels-last [Rh][Rw][C] in fp32 or bf16.
+ */
+int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int32_t rw, void* dst,
+                        int32_t dst_dtype, void* stream);
+
+/* nn.Linear weight [n_out, k] (row stride ldw, fp32) -> bf16 UMMA image [k_pad/8][n_out][8],
+ * zero-padded for k <= kk < k_pad.  k_pad % 16 == 0. */
+int32_t nvsr_pack_weight_bf16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
+                              void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a4 + a5  stratified sampler (train_utils.py:95-111) fused with the tri-plane bilinear gather of
+ * TwoDimPlanesModel.forward (models.py:261-268 normalize_coords, :495-497 CoordProjector,
+ * :289-310 project_xyz = F.grid_sample(bilinear, align_corners=True, padding_mode='border'),
+ * :355-361 combine_pos_planes('avg')).
+ */
+typedef struct nvsr_planes {
+  const void* plane[3];   /* channels-last [rh][rw][channels] */
+  int32_t rh[3], rw[3];
+  int32_t channels;       /* multiple of 8, <= 64 */
+  int32_t dtype;          /* NVSR_F32 | NVSR_BF16 */
+  float box_lo[3];        /* fp32(box_coords[scene][0,:3]) */
+  float box_rng[3];       /* fp32(box[1,:3] - box[0,:3]) with the difference taken in fp64 */
+  float proj[3][6];       /* rot_mats[d][:,1:] row-major [3][2]: grid = n_xyz @ proj[d] */
+} nvsr_planes_t;
+
+typedef struct nvsr_sampler {
+  int64_t n_rays;
+  int32_t n_samples;      /* S */
+  const float* ro;        /* [n,3] */
+  const float* rd;        /* [n,3] */
+  float near_, far_;
+  int32_t lindisp;
+  const float* t_vals;    /* [S]   coarse pass: torch.linspace(0,1,S) made by the caller */
+  const float* t_rand;    /* [n,S] caller-supplied uniforms (perturb) or NULL */
+  const float* z_in;      /* [n,S] fine pass: merged depths; when non-NULL t_vals/t_rand unused */
+} nvsr_sampler_t;
+
+#define NVSR_FEAT_ROWMAJOR_F32 0 /* featP [rows,3C] fp32, featM [rows,C] fp32                  */
+#define NVSR_FEAT_TILE_BF16 1    /* featP [tiles][3C/8][128][8] bf16, featM [tiles][C/8][128][8] */
+
+/* rows = n_rays*n_samples, row = ray*S + s.  Tile-image outputs must be sized for
+ * ceil(rows/128) tiles; rows past the end are written as zeros.  z_out [n,S] may be NULL. */
+int32_t nvsr_sample_gather(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes,
+                           int32_t feat_layout, void* feat_p, void* feat_m, float* z_out,
+                           void* stream);
+
+/* a5 view-direction half: cart2az_el (nerf_helpers.py:492-496) + normalize + project_viewdir
+ * (models.py:312-326) — hoisted per ray (the reference recomputes it per sample).
+ * vplane: channels-last fp32 [rh][rw][channels].  vfeat: [n,channels] fp32.
+ * (lo, rng) = fp32(box[0,3:5]), fp32(box[1,3:5]-box[0,3:5]) as in nvsr_planes_t. */
+int32_t nvsr_viewdir_gather(const float* viewdirs, int64_t n_rays, const float* vplane, int32_t rh,
+                            int32_t rw, int32_t channels, float az_lo, float az_rng, float el_lo,
+                            float el_rng, float* vfeat, void* stream);
+
+/* per-ray bias of a decoder layer whose input is concat(per-sample, per-ray) features:
+ * out[ray,n] = b[n] + sum_k w[n*ldw + k] * vin[ray,k]     (the per-ray columns of rgb_dec[0],
+ * models.py:186 / layers_dir[0], models.py:68) */
+int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, const float* w, int32_t ldw,
+                      const float* b, int32_t n_out, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a6 / a6'  decoder MLP as a chain of dense layers   models.py:168-197,393-421 (planes decoder),
+ * models.py:14-108 (FlexibleNeRFModel).  One call evaluates one chain over `rows` rows and
+ * writes its heads into planar raw[ch][raw_stride].
+ */
+typedef struct nvsr_layer {
+  const void* w;         /* F32: [n_out,k] row-major;  BF16: UMMA image [k/8][n_out][8] */
+  const float* bias;     /* [n_out]; ignored when row_bias != NULL */
+  const float* row_bias; /* [n_rays,n_out] per-ray bias (already includes bias) or NULL */
+  const float* head_w;   /* [head_n,n_out] fp32 head tapped on this layer's output, or NULL */
+  const float* head_b;   /* [head_n] */
+  int32_t k, n_out, relu;
+  int32_t head_n, head_ch; /* head writes raw channels head_ch .. head_ch+head_n-1 */
+} nvsr_layer_t;
+
+typedef struct nvsr_mlp {
+  int32_t precision;     /* NVSR_F32: SIMT fp32 kernel, input row-major fp32 [rows,k0];
+                            NVSR_BF16: tcgen05 kernel, input tile image bf16 */
+  int32_t n_layers;
+  nvsr_layer_t layer[NVSR_MAX_LAYERS];
+  const void* in;
+  int64_t rows;
+  int32_t samples_per_ray; /* row -> ray = row / samples_per_ray (for row_bias) */
+  int64_t n_rays;
+  float* raw;            /* planar [4][raw_stride] */
+  int64_t raw_stride;
+} nvsr_mlp_t;
+
+int32_t nvsr_mlp_chain(const nvsr_mlp_t* mlp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a7 + a8  volume_render_radiance_field (volume_rendering_utils.py:6-51, cumprod_exclusive
+ * nerf_helpers.py:409-430) and, on the coarse pass, sample_pdf_2 (nerf_helpers.py:668-702) with
+ * the call-site prep and sort-merge of train_utils.py:144-156.  One warp per ray.
+ */
+typedef struct nvsr_composite {
+  int64_t n_rays;
+  int32_t n_samples;       /* S: radiance samples per ray */
+  const float* raw;        /* planar [4][raw_stride]: r,g,b,sigma of row = ray*S + s */
+  int64_t raw_stride;
+  const float* z;          /* [n,S]  (mip: [n,S+1] interval edges) */
+  const float* rd;         /* [n,3] */
+  const float* noise;      /* [n,S] noise already scaled by radiance_field_noise_std, or NULL */
+  int32_t white_bkgd;
+  int32_t mip;
+  float* rgb;              /* [n,3] */
+  float* disp;             /* [n] */
+  float* acc;              /* [n] */
+  float* depth;            /* [n] */
+  float* weights;          /* [n,S] or NULL */
+  /* hierarchical resampling; n_fine == 0 disables (fine pass) */
+  int32_t n_fine;          /* samples to draw (mip: caller passes num_fine+1) */
+  const float* u;          /* [n_fine] (u_per_ray==0, sorted/deterministic) or [n,n_fine] */
+  int32_t u_per_ray;
+  int64_t* inds;           /* [n,n_fine] searchsorted(right) indices or NULL */
+  float* z_samples;        /* [n,n_fine] or NULL */
+  float* z_merged;         /* [n, S(+1 if mip) + n_fine] sorted */
+} nvsr_composite_t;
+
+int32_t nvsr_composite(const nvsr_composite_t* args, void* stream);
+
+/* a8 stand-alone: sample_pdf(bins[n,B], weights[n,B-1], num_samples, det) nerf_helpers.py:668.
+ * cdf_in [n,B] (optional): skip the pdf/cdf construction and search this cdf instead (stage test:
+ * identical cdf,u => bit-exact inds). */
+int32_t nvsr_sample_pdf(const float* bins, const float* weights, const float* cdf_in, int64_t n_rays,
+                        int32_t n_bins, const float* u, int32_t u_per_ray, int32_t n_samples,
+                        int64_t* inds, float* samples, float* cdf_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a9  mip path: cast_rays + conical_frustum_to_gaussian + lift_gaussian (mip.py:9-43) fused with
+ * IntegratedPositionalEncoding (mip.py:154-199).  z: [n,S+1] interval edges; out: [n*S, 6*n_freqs]
+ * (row-major fp32, out_layout 0) or bf16 tile image padded to k_pad columns (out_layout 1).
+ */
+int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, int64_t n_rays, int32_t n_intervals,
+                 float radius, int32_t n_freqs, int32_t out_layout, int32_t k_pad, void* out,
+                 void* stream);
+
+/* positional_encoding(viewdirs, n_freqs, include_input) nerf_helpers.py:552-575, per ray. */
+int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, int32_t include_input,
+                          float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVSR_H_ */

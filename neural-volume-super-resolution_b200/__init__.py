@@ -1,0 +1,26 @@
+"""nvsr_b200 — B200 (sm_100a) ray-rendering hot path of Neural-Volume-Super-Resolution.
+
+The directory is named after the reference (`neural-volume-super-resolution_b200`); because of the
+hyphens import it as `nvsr_b200` (the alias module at the repo root) or through importlib.
+
+Public surface = the reference's own call surface for this path:
+    get_ray_bundle, run_one_iter_of_nerf, eval_nerf, volume_render_radiance_field, sample_pdf,
+    install(train_utils)   and the stage-level ops in `ops`.
+Host code is Python; every kernel is hand-written CUDA behind the C-ABI of include/nvsr.h.
+There is no CPU fallback: without libnvsr_b200.so (or without a GPU) every entry point raises.
+"""
+from . import _lib, build, ops, render, scene  # noqa: F401
+from ._lib import NVSR_BF16, NVSR_F32, NvsrError  # noqa: F401
+from .ops import (get_ray_bundle, sample_pdf, volume_render_radiance_field)  # noqa: F401
+from .render import (eval_nerf, get_precision, install, render_frame, run_one_iter_of_nerf, set_precision,  # noqa: F401
+                     set_ray_chunk, uninstall)
+
+
+class IntegratedPositionalEncoding:
+    """Handle with the reference's constructor (mip.py:155-161).  The encoding itself is fused with
+    cast_rays into one kernel (`ops.ipe`), which `run_one_iter_of_nerf` calls when it is given this
+    object (or the reference's own module — only `.max_freq` is read) as `encode_position_fn`."""
+
+    def __init__(self, input_dims=3, multires=10, include_input=False):
+        self.out_dims = input_dims * 2 * (multires - 1)
+        self.max_freq = multires - 1

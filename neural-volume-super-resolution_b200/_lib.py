@@ -1,0 +1,163 @@
+"""ctypes binding of libnvsr_b200.so — the C-ABI declared in include/nvsr.h.
+
+There is NO fallback: if the CUDA library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+NVSR_F32, NVSR_BF16 = 0, 1
+FEAT_ROWMAJOR_F32, FEAT_TILE_BF16 = 0, 1
+TILE_ROWS = 128
+MAX_LAYERS = 8
+MAX_SAMPLES = 1024
+
+c_f = C.c_float
+c_i32 = C.c_int32
+c_i64 = C.c_int64
+c_p = C.c_void_p
+
+
+class Planes(C.Structure):
+    _fields_ = [
+        ("plane", c_p * 3),
+        ("rh", c_i32 * 3),
+        ("rw", c_i32 * 3),
+        ("channels", c_i32),
+        ("dtype", c_i32),
+        ("box_lo", c_f * 3),
+        ("box_rng", c_f * 3),
+        ("proj", (c_f * 6) * 3),
+    ]
+
+
+class Sampler(C.Structure):
+    _fields_ = [
+        ("n_rays", c_i64),
+        ("n_samples", c_i32),
+        ("ro", c_p),
+        ("rd", c_p),
+        ("near_", c_f),
+        ("far_", c_f),
+        ("lindisp", c_i32),
+        ("t_vals", c_p),
+        ("t_rand", c_p),
+        ("z_in", c_p),
+    ]
+
+
+class Layer(C.Structure):
+    _fields_ = [
+        ("w", c_p),
+        ("bias", c_p),
+        ("row_bias", c_p),
+        ("head_w", c_p),
+        ("head_b", c_p),
+        ("k", c_i32),
+        ("n_out", c_i32),
+        ("relu", c_i32),
+        ("head_n", c_i32),
+        ("head_ch", c_i32),
+    ]
+
+
+class Mlp(C.Structure):
+    _fields_ = [
+        ("precision", c_i32),
+        ("n_layers", c_i32),
+        ("layer", Layer * MAX_LAYERS),
+        ("in_", c_p),
+        ("rows", c_i64),
+        ("samples_per_ray", c_i32),
+        ("n_rays", c_i64),
+        ("raw", c_p),
+        ("raw_stride", c_i64),
+    ]
+
+
+class Composite(C.Structure):
+    _fields_ = [
+        ("n_rays", c_i64),
+        ("n_samples", c_i32),
+        ("raw", c_p),
+        ("raw_stride", c_i64),
+        ("z", c_p),
+        ("rd", c_p),
+        ("noise", c_p),
+        ("white_bkgd", c_i32),
+        ("mip", c_i32),
+        ("rgb", c_p),
+        ("disp", c_p),
+        ("acc", c_p),
+        ("depth", c_p),
+        ("weights", c_p),
+        ("n_fine", c_i32),
+        ("u", c_p),
+        ("u_per_ray", c_i32),
+        ("inds", c_p),
+        ("z_samples", c_p),
+        ("z_merged", c_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/nvsr.h declares
+SIGNATURES = {
+    "nvsr_abi_version": (c_i32, []),
+    "nvsr_status_string": (C.c_char_p, [c_i32]),
+    "nvsr_ray_bundle": (c_i32, [c_i32, c_i32, c_f, c_f, C.POINTER(c_f), c_i32, c_f, c_i32, c_i32, c_p, c_p, c_p]),
+    "nvsr_prepare_rays": (c_i32, [c_p, c_p, c_i64, c_i32, c_i32, c_i32, C.c_double, C.c_double, c_p, c_p, c_p, c_p]),
+    "nvsr_pack_plane": (c_i32, [c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),
+    "nvsr_pack_weight_bf16": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),
+    "nvsr_sample_gather": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_i32, c_p, c_p, c_p, c_p]),
+    "nvsr_viewdir_gather": (c_i32, [c_p, c_i64, c_p, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p]),
+    "nvsr_row_bias": (c_i32, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p]),
+    "nvsr_mlp_chain": (c_i32, [C.POINTER(Mlp), c_p]),
+    "nvsr_composite": (c_i32, [C.POINTER(Composite), c_p]),
+    "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
+    "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),
+    "nvsr_dir_encoding": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_p]),
+}
+
+_LIB = None
+
+
+class NvsrError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load the shared library (building it in-tree first when absent/stale and nvcc is present)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if build_if_missing:
+        try:
+            _build.build_library()
+        except FileNotFoundError:
+            pass  # no nvcc on this box: use the prebuilt .so that travelled with the tree
+    if not os.path.exists(path):
+        raise NvsrError(
+            f"{path} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
+            "There is no CPU / PyTorch fallback for the nvsr_b200 render path."
+        )
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nvsr_abi_version() != 1:
+        raise NvsrError("libnvsr_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().nvsr_status_string(status).decode()
+        raise NvsrError(f"{what} failed: status {status} ({msg})")

@@ -1,0 +1,155 @@
+// a9: mip-NeRF conical-frustum Gaussians + integrated positional encoding, fused (mip.py:9-43,
+// 154-199), and the per-ray direction encoding (nerf_helpers.py:552-575).  The reference
+// materialises means/covs/[N*S,63] in HBM; here one thread turns (t0,t1,o,d) straight into the
+// encoded row.
+#include "common.cuh"
+
+namespace nvsr {
+
+constexpr int kIpeMaxFreqs = 16;
+
+struct IpeRow {
+  float mean[3], cov[3];
+};
+
+__device__ __forceinline__ IpeRow ipe_gaussian(float t0, float t1, const float o[3], const float d[3], float radius) {
+  // conical_frustum_to_gaussian (mip.py:21-29); python-double scalars are cast to fp32 by torch
+  float mu = (t0 + t1) / 2.f;
+  float hw = (t1 - t0) / 2.f;
+  float mu2 = mu * mu, hw2 = hw * hw, hw4 = hw2 * hw2;
+  float den = 3.f * mu2 + hw2;
+  float t_mean = mu + (2.f * mu * hw2) / den;
+  float t_var = hw2 / 3.f - (float)(4.0 / 15.0) * ((hw4 * (12.f * mu2 - hw2)) / (den * den));
+  float r_var = (radius * radius) * (mu2 / 4.f + (float)(5.0 / 12.0) * hw2 - (float)(4.0 / 15.0) * hw4 / den);
+  // lift_gaussian (mip.py:32-43)
+  float dmag = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  IpeRow g;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float dd = d[c] * d[c];
+    g.mean[c] = d[c] * t_mean + o[c];
+    g.cov[c] = t_var * dd + r_var * (1.f - dd / dmag);
+  }
+  return g;
+}
+
+// out index: [sin block: i*3+c | shifted block: 3*nf + i*3+c]
+__device__ __forceinline__ float ipe_value(const IpeRow& g, int nf, int j) {
+  int blk = j >= 3 * nf;
+  int jj = j - blk * 3 * nf;
+  int i = jj / 3, c = jj - i * 3;
+  float sc = (float)(1 << i);
+  float y = g.mean[c] * sc;
+  float yv = g.cov[c] * (sc * sc);
+  if (blk) y = y + (float)(0.5 * 3.14159265358979323846);
+  return expf(-0.5f * yv) * sinf(y);
+}
+
+__global__ void ipe_rowmajor_kernel(const float* __restrict__ z, const float* __restrict__ ro, const float* __restrict__ rd,
+                                    int64_t n_rays, int S, float radius, int nf, float* __restrict__ out) {
+  const int D = 6 * nf;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rays * S * D) return;
+  int64_t row = idx / D;
+  int j = (int)(idx - row * D);
+  int64_t ray = row / S;
+  int s = (int)(row - ray * S);
+  float o[3] = {__ldg(ro + ray * 3), __ldg(ro + ray * 3 + 1), __ldg(ro + ray * 3 + 2)};
+  float d[3] = {__ldg(rd + ray * 3), __ldg(rd + ray * 3 + 1), __ldg(rd + ray * 3 + 2)};
+  IpeRow g = ipe_gaussian(__ldg(z + ray * (S + 1) + s), __ldg(z + ray * (S + 1) + s + 1), o, d, radius);
+  out[idx] = ipe_value(g, nf, j);
+}
+
+// bf16 tile image [tile][k_pad/8][128][8]: one thread per (row, 8-column chunk)
+__global__ void ipe_tile_kernel(const float* __restrict__ z, const float* __restrict__ ro, const float* __restrict__ rd,
+                                int64_t n_rays, int S, float radius, int nf, int k_pad, uint4* __restrict__ out,
+                                int64_t n_tiles) {
+  const int chunks = k_pad / 8;
+  const int D = 6 * nf;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tiles * chunks * kTileRows) return;
+  int r = (int)(idx % kTileRows);
+  int c = (int)((idx / kTileRows) % chunks);
+  int64_t tile = idx / ((int64_t)kTileRows * chunks);
+  int64_t row = tile * kTileRows + r;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (row < n_rays * S) {
+    int64_t ray = row / S;
+    int s = (int)(row - ray * S);
+    float o[3] = {__ldg(ro + ray * 3), __ldg(ro + ray * 3 + 1), __ldg(ro + ray * 3 + 2)};
+    float d[3] = {__ldg(rd + ray * 3), __ldg(rd + ray * 3 + 1), __ldg(rd + ray * 3 + 2)};
+    IpeRow g = ipe_gaussian(__ldg(z + ray * (S + 1) + s), __ldg(z + ray * (S + 1) + s + 1), o, d, radius);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int j = c * 8 + e;
+      if (j < D) f[e] = ipe_value(g, nf, j);
+    }
+  }
+  uint4 o4;
+  o4.x = pack_bf16x2(f[0], f[1]), o4.y = pack_bf16x2(f[2], f[3]);
+  o4.z = pack_bf16x2(f[4], f[5]), o4.w = pack_bf16x2(f[6], f[7]);
+  out[idx] = o4;  // idx == (tile*chunks + c)*128 + r
+}
+
+// positional_encoding(d, nf, include_input): [d, sin(2^0 d), cos(2^0 d), sin(2^1 d), ...]
+__global__ void dir_encoding_kernel(const float* __restrict__ dirs, int64_t n, int nf, int include_input,
+                                    float* __restrict__ out) {
+  const int D = (include_input ? 3 : 0) + 6 * nf;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * D) return;
+  int64_t ray = idx / D;
+  int j = (int)(idx - ray * D);
+  float v;
+  if (include_input && j < 3) {
+    v = __ldg(dirs + ray * 3 + j);
+  } else {
+    int jj = j - (include_input ? 3 : 0);
+    int i = jj / 6, rem = jj - i * 6;
+    int c = rem % 3;
+    float x = (float)(1 << i) * __ldg(dirs + ray * 3 + c);
+    v = rem < 3 ? sinf(x) : cosf(x);
+  }
+  out[idx] = v;
+}
+
+}  // namespace nvsr
+
+using namespace nvsr;
+
+extern "C" int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, int64_t n_rays, int32_t n_intervals,
+                            float radius, int32_t n_freqs, int32_t out_layout, int32_t k_pad, void* out,
+                            void* stream) {
+  NVSR_CHECK_ARG(z && ro && rd && out && n_rays >= 0 && n_intervals > 0 && n_freqs > 0 && n_freqs <= kIpeMaxFreqs);
+  if (n_rays == 0) return NVSR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_layout == NVSR_FEAT_ROWMAJOR_F32) {
+    int64_t total = n_rays * n_intervals * 6 * n_freqs;
+    int64_t blocks = ceil_div64(total, 256);
+    NVSR_CHECK_ARG(blocks < ((int64_t)1 << 31));
+    ipe_rowmajor_kernel<<<(unsigned)blocks, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, n_freqs, (float*)out);
+    NVSR_RETURN_LAST_ERROR();
+  }
+  if (out_layout == NVSR_FEAT_TILE_BF16) {
+    NVSR_CHECK_ARG(k_pad >= 6 * n_freqs && k_pad % 16 == 0);
+    if (!aligned16(out)) return NVSR_ERR_ALIGNMENT;
+    int64_t n_tiles = ceil_div64(n_rays * n_intervals, kTileRows);
+    int64_t total = n_tiles * (k_pad / 8) * kTileRows;
+    int64_t blocks = ceil_div64(total, 256);
+    NVSR_CHECK_ARG(blocks < ((int64_t)1 << 31));
+    ipe_tile_kernel<<<(unsigned)blocks, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, n_freqs, k_pad,
+                                                     (uint4*)out, n_tiles);
+    NVSR_RETURN_LAST_ERROR();
+  }
+  return NVSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, int32_t include_input,
+                                     float* out, void* stream) {
+  NVSR_CHECK_ARG(dirs && out && n_rays >= 0 && n_freqs >= 0 && n_freqs <= kIpeMaxFreqs);
+  if (n_rays == 0) return NVSR_OK;
+  int D = (include_input ? 3 : 0) + 6 * n_freqs;
+  int64_t total = n_rays * D;
+  dir_encoding_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(dirs, n_rays, n_freqs,
+                                                                                         include_input, out);
+  NVSR_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,264 @@
+// Ray generation / preparation, plane + weight re-packing, per-ray view-direction features.
+// Small elementwise kernels: one launch each instead of the reference's ~10 ATen kernels per call.
+#include "common.cuh"
+#include "bilinear.cuh"
+
+namespace nvsr {
+
+struct Mat4 {
+  float m[16];
+};
+
+// a1: nerf_helpers.py:530-549.  No FMA contraction: the reference rounds every op separately.
+__global__ void ray_bundle_kernel(int H, int W, float fx, float fy, Mat4 c2w, int padding, float offset,
+                                  int row_begin, int n_rows, int Wp, float* __restrict__ ro,
+                                  float* __restrict__ rd) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)n_rows * Wp;
+  if (idx >= total) return;
+  int r = (int)(idx / Wp) + row_begin;
+  int c = (int)(idx % Wp);
+  // ii = (arange(W+2p) + offset) - p ; jj likewise
+  float ii = __fadd_rn((float)c, offset);
+  float jj = __fadd_rn((float)r, offset);
+  if (padding > 0) {
+    ii = __fsub_rn(ii, (float)padding);
+    jj = __fsub_rn(jj, (float)padding);
+  }
+  float dx = __fdiv_rn(__fsub_rn(ii, (float)W * 0.5f), fx);
+  float dy = -__fdiv_rn(__fsub_rn(jj, (float)H * 0.5f), fy);
+  float dz = -1.0f;
+  float* o = ro + idx * 3;
+  float* d = rd + idx * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w.m[k * 4 + 0]), __fmul_rn(dy, c2w.m[k * 4 + 1])),
+                        __fmul_rn(dz, c2w.m[k * 4 + 2]));
+    d[k] = s;
+    o[k] = c2w.m[k * 4 + 3];
+  }
+}
+
+// a2/a3: train_utils.py:210-226 + nerf_helpers.py:578-605
+__global__ void prepare_rays_kernel(const float* __restrict__ ro_in, const float* __restrict__ rd_in,
+                                    int64_t n, int use_ndc, float c0, float c1, float near_f,
+                                    float two_near, float neg_two_near, float* __restrict__ ro_out,
+                                    float* __restrict__ rd_out, float* __restrict__ viewdirs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ox = ro_in[i * 3 + 0], oy = ro_in[i * 3 + 1], oz = ro_in[i * 3 + 2];
+  float dx = rd_in[i * 3 + 0], dy = rd_in[i * 3 + 1], dz = rd_in[i * 3 + 2];
+  if (viewdirs) {
+    float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    viewdirs[i * 3 + 0] = __fdiv_rn(dx, nrm);
+    viewdirs[i * 3 + 1] = __fdiv_rn(dy, nrm);
+    viewdirs[i * 3 + 2] = __fdiv_rn(dz, nrm);
+  }
+  if (use_ndc) {
+    float t = __fdiv_rn(-__fadd_rn(near_f, oz), dz);
+    ox = __fadd_rn(ox, __fmul_rn(t, dx));
+    oy = __fadd_rn(oy, __fmul_rn(t, dy));
+    oz = __fadd_rn(oz, __fmul_rn(t, dz));
+    float o0 = __fdiv_rn(__fmul_rn(c0, ox), oz);
+    float o1 = __fdiv_rn(__fmul_rn(c1, oy), oz);
+    float o2 = __fadd_rn(1.0f, __fdiv_rn(two_near, oz));
+    float d0 = __fmul_rn(c0, __fsub_rn(__fdiv_rn(dx, dz), __fdiv_rn(ox, oz)));
+    float d1 = __fmul_rn(c1, __fsub_rn(__fdiv_rn(dy, dz), __fdiv_rn(oy, oz)));
+    float d2 = __fdiv_rn(neg_two_near, oz);
+    ox = o0, oy = o1, oz = o2, dx = d0, dy = d1, dz = d2;
+  }
+  ro_out[i * 3 + 0] = ox, ro_out[i * 3 + 1] = oy, ro_out[i * 3 + 2] = oz;
+  rd_out[i * 3 + 0] = dx, rd_out[i * 3 + 1] = dy, rd_out[i * 3 + 2] = dz;
+}
+
+// NCHW fp32 -> HWC (fp32|bf16) through a 32x33 smem transpose: coalesced on both sides.
+template <typename OutT>
+__global__ void pack_plane_kernel(const float* __restrict__ src, int C, int64_t HW, OutT* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  int64_t p0 = (int64_t)blockIdx.x * 32;
+  int c0 = blockIdx.y * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j;
+    int64_t p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? src[(int64_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int64_t p = p0 + j;
+    int c = c0 + tx;
+    if (c < C && p < HW) {
+      float v = tile[tx][j];
+      if constexpr (sizeof(OutT) == 2) dst[p * C + c] = __float2bfloat16_rn(v);
+      else dst[p * C + c] = v;
+    }
+  }
+}
+
+// W [n_out,k] (ld) fp32 -> bf16 image [k_pad/8][n_out][8]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int k, int ldw, int k_pad,
+                                   __nv_bfloat16* __restrict__ dst) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = n_out * k_pad;
+  if (idx >= total) return;
+  int e = idx & 7;
+  int n = (idx >> 3) % n_out;
+  int chunk = (idx >> 3) / n_out;
+  int kk = chunk * 8 + e;
+  float v = kk < k ? w[(int64_t)n * ldw + kk] : 0.f;
+  dst[idx] = __float2bfloat16_rn(v);
+}
+
+// a5 (view half): one thread per (ray, 4-channel chunk)
+__global__ void viewdir_gather_kernel(const float* __restrict__ viewdirs, int64_t n, const float* __restrict__ vplane,
+                                      int rh, int rw, int C, float az_lo, float az_rng, float el_lo, float el_rng,
+                                      float* __restrict__ vfeat) {
+  int chunks = C / 4;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * chunks) return;
+  int64_t ray = idx / chunks;
+  int ch = (int)(idx % chunks) * 4;
+  float dx = viewdirs[ray * 3 + 0], dy = viewdirs[ray * 3 + 1], dz = viewdirs[ray * 3 + 2];
+  // cart2az_el: el = atan2(z, sqrt(x^2+y^2)), az = atan2(y,x)
+  float el = atan2f(dz, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+  float az = atan2f(dy, dx);
+  // normalize_coords: 2*(c-lo)/(hi-lo)-1
+  float gaz = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(az, az_lo)), az_rng), 1.f);
+  float gel = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(el, el_lo)), el_rng), 1.f);
+  Bilin b = bilinear_setup(gaz, gel, rw, rh);
+  const float4 v00 = *reinterpret_cast<const float4*>(vplane + ((int64_t)b.y0 * rw + b.x0) * C + ch);
+  const float4 v01 = *reinterpret_cast<const float4*>(vplane + ((int64_t)b.y0 * rw + b.x1) * C + ch);
+  const float4 v10 = *reinterpret_cast<const float4*>(vplane + ((int64_t)b.y1 * rw + b.x0) * C + ch);
+  const float4 v11 = *reinterpret_cast<const float4*>(vplane + ((int64_t)b.y1 * rw + b.x1) * C + ch);
+  float4 o;
+  o.x = v00.x * b.w00 + v01.x * b.w01 + v10.x * b.w10 + v11.x * b.w11;
+  o.y = v00.y * b.w00 + v01.y * b.w01 + v10.y * b.w10 + v11.y * b.w11;
+  o.z = v00.z * b.w00 + v01.z * b.w01 + v10.z * b.w10 + v11.z * b.w11;
+  o.w = v00.w * b.w00 + v01.w * b.w01 + v10.w * b.w10 + v11.w * b.w11;
+  *reinterpret_cast<float4*>(vfeat + ray * C + ch) = o;
+}
+
+// out[ray,n] = b[n] + sum_k w[n,k]*vin[ray,k]; block = (n_out threads) x rays-per-block rows
+__global__ void row_bias_kernel(const float* __restrict__ vin, int64_t n_rays, int K, const float* __restrict__ w,
+                                int ldw, const float* __restrict__ b, int n_out, float* __restrict__ out) {
+  extern __shared__ float sw[];  // [K][n_out] transposed weights
+  for (int i = threadIdx.x; i < K * n_out; i += blockDim.x) {
+    int n = i % n_out, k = i / n_out;
+    sw[i] = w[(int64_t)n * ldw + k];
+  }
+  __syncthreads();
+  const int rays_per_block = 64;
+  int64_t r0 = (int64_t)blockIdx.x * rays_per_block;
+  for (int i = threadIdx.x; i < rays_per_block * n_out; i += blockDim.x) {
+    int n = i % n_out;
+    int64_t ray = r0 + i / n_out;
+    if (ray >= n_rays) break;
+    float acc = b ? b[n] : 0.f;
+    const float* v = vin + ray * K;
+    for (int k = 0; k < K; ++k) acc = fmaf(sw[k * n_out + n], __ldg(v + k), acc);
+    out[ray * n_out + n] = acc;
+  }
+}
+
+}  // namespace nvsr
+
+using namespace nvsr;
+
+extern "C" int32_t nvsr_ray_bundle(int32_t height, int32_t width, float focal_x, float focal_y,
+                                   const float* c2w_host, int32_t padding, float offset, int32_t row_begin,
+                                   int32_t row_end, float* ro, float* rd, void* stream) {
+  NVSR_CHECK_ARG(height > 0 && width > 0 && c2w_host && ro && rd && padding >= 0);
+  NVSR_CHECK_ARG(row_begin >= 0 && row_end >= row_begin && row_end <= height + 2 * padding);
+  int n_rows = row_end - row_begin;
+  if (n_rows == 0) return NVSR_OK;
+  Mat4 m;
+  for (int i = 0; i < 16; ++i) m.m[i] = c2w_host[i];
+  int Wp = width + 2 * padding;
+  int64_t total = (int64_t)n_rows * Wp;
+  int threads = 256;
+  int64_t blocks = ceil_div64(total, threads);
+  ray_bundle_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(height, width, focal_x, focal_y, m, padding,
+                                                                          offset, row_begin, n_rows, Wp, ro, rd);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_prepare_rays(const float* ro_in, const float* rd_in, int64_t n_rays, int32_t use_ndc,
+                                     int32_t height, int32_t width, double focal, double ndc_near, float* ro_out,
+                                     float* rd_out, float* viewdirs, void* stream) {
+  NVSR_CHECK_ARG(ro_in && rd_in && ro_out && rd_out && n_rays >= 0);
+  if (n_rays == 0) return NVSR_OK;
+  // python-side scalars are evaluated in double then cast to fp32 by the tensor op
+  float c0 = 0.f, c1 = 0.f;
+  if (use_ndc) {
+    NVSR_CHECK_ARG(focal != 0.0 && height > 0 && width > 0);
+    c0 = (float)(-1.0 / ((double)width / (2.0 * focal)));
+    c1 = (float)(-1.0 / ((double)height / (2.0 * focal)));
+  }
+  int threads = 256;
+  int64_t blocks = ceil_div64(n_rays, threads);
+  prepare_rays_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      ro_in, rd_in, n_rays, use_ndc, c0, c1, (float)ndc_near, (float)(2.0 * ndc_near), (float)(-2.0 * ndc_near),
+      ro_out, rd_out, viewdirs);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int32_t rw, void* dst,
+                                   int32_t dst_dtype, void* stream) {
+  NVSR_CHECK_ARG(src_nchw && dst && channels > 0 && rh > 0 && rw > 0);
+  NVSR_CHECK_ARG(dst_dtype == NVSR_F32 || dst_dtype == NVSR_BF16);
+  int64_t HW = (int64_t)rh * rw;
+  dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)((channels + 31) / 32));
+  dim3 block(32, 8);
+  if (dst_dtype == NVSR_F32)
+    pack_plane_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (float*)dst);
+  else
+    pack_plane_kernel<__nv_bfloat16>
+        <<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (__nv_bfloat16*)dst);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_pack_weight_bf16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
+                                         void* dst, void* stream) {
+  NVSR_CHECK_ARG(w && dst && n_out > 0 && k > 0 && ldw >= k && k_pad >= k && (k_pad % 16) == 0);
+  int total = n_out * k_pad;
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, ldw, k_pad,
+                                                                            (__nv_bfloat16*)dst);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_viewdir_gather(const float* viewdirs, int64_t n_rays, const float* vplane, int32_t rh,
+                                       int32_t rw, int32_t channels, float az_lo, float az_rng, float el_lo,
+                                       float el_rng, float* vfeat, void* stream) {
+  NVSR_CHECK_ARG(viewdirs && vplane && vfeat && n_rays >= 0 && rh > 0 && rw > 0);
+  NVSR_CHECK_ARG(channels > 0 && channels % 4 == 0);
+  if (!aligned16(vplane) || !aligned16(vfeat)) return NVSR_ERR_ALIGNMENT;
+  if (n_rays == 0) return NVSR_OK;
+  int64_t total = n_rays * (channels / 4);
+  viewdir_gather_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      viewdirs, n_rays, vplane, rh, rw, channels, az_lo, az_rng, el_lo, el_rng, vfeat);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, const float* w, int32_t ldw,
+                                 const float* b, int32_t n_out, float* out, void* stream) {
+  NVSR_CHECK_ARG(vin && w && out && n_rays >= 0 && k > 0 && n_out > 0 && ldw >= k);
+  NVSR_CHECK_ARG((size_t)k * n_out * sizeof(float) <= 48 * 1024);
+  if (n_rays == 0) return NVSR_OK;
+  size_t smem = (size_t)k * n_out * sizeof(float);
+  row_bias_kernel<<<(unsigned)ceil_div64(n_rays, 64), 256, smem, (cudaStream_t)stream>>>(vin, n_rays, k, w, ldw, b,
+                                                                                        n_out, out);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_abi_version(void) { return NVSR_ABI_VERSION; }
+
+extern "C" const char* nvsr_status_string(int32_t status) {
+  switch (status) {
+    case NVSR_OK: return "ok";
+    case NVSR_ERR_INVALID_ARG: return "invalid argument";
+    case NVSR_ERR_UNSUPPORTED: return "unsupported configuration";
+    case NVSR_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
+    case NVSR_ERR_RESOURCE: return "resource limit (shared memory / samples per ray)";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown nvsr status";
+  }
+}

@@ -1,0 +1,410 @@
+"""Stage-level host wrappers over the C-ABI (include/nvsr.h).
+
+Every function takes/returns torch CUDA tensors, launches on torch's current stream and raises
+`NvsrError` on a non-zero status.  torch is plumbing here (device memory + streams); all arithmetic
+happens in libnvsr_b200.so.  Signatures mirror the reference functions they replace; the reference
+file:line for each is in include/nvsr.h.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, NVSR_BF16, NVSR_F32, TILE_ROWS
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32c(t, device=None):
+    """contiguous fp32 CUDA tensor (no copy when already so)"""
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.NvsrError(f"{name} must be a CUDA tensor: nvsr_b200 has no CPU path")
+
+
+# ---------------------------------------------------------------------------------------------
+# a1  get_ray_bundle
+def get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size=0, downsampling_offset=0,
+                   row_range=None):
+    """Drop-in for nerf_helpers.get_ray_bundle (nerf_helpers.py:507-549).
+
+    Returns (ray_origins, ray_directions), each [H+2p, W+2p, 3] (or the [row_begin,row_end) band when
+    `row_range` is given — the multi-GPU row-band sharding).  `focal_length` may be a scalar or an
+    [fx?, fy?] list; the reference divides x by get_focal(f,'H') and y by get_focal(f,'W')
+    (nerf_helpers.py:432-437, 540-541), which is mirrored here.
+    """
+    lib = _lib.load()
+    _require_cuda(tform_cam2world, "tform_cam2world")
+    if isinstance(focal_length, (list, tuple)):
+        fx, fy = float(focal_length[1]), float(focal_length[0])  # get_focal(.,'H') / get_focal(.,'W')
+    else:
+        fx = fy = float(focal_length)
+    hp, wp = height + 2 * padding_size, width + 2 * padding_size
+    r0, r1 = (0, hp) if row_range is None else row_range
+    c2w = tform_cam2world.detach().to(torch.float32).cpu().contiguous().view(-1)
+    if c2w.numel() != 16:
+        raise _lib.NvsrError("tform_cam2world must be 4x4")
+    c2w_arr = (C.c_float * 16)(*c2w.tolist())
+    dev = tform_cam2world.device
+    ro = torch.empty((r1 - r0, wp, 3), dtype=torch.float32, device=dev)
+    rd = torch.empty_like(ro)
+    with torch.cuda.device(dev):
+        st = lib.nvsr_ray_bundle(height, width, fx, fy, c2w_arr, padding_size, float(downsampling_offset), r0, r1,
+                                 _ptr(ro), _ptr(rd), _stream())
+    _lib.check(st, "nvsr_ray_bundle")
+    return ro, rd
+
+
+# a2/a3
+def prepare_rays(ray_origins, ray_directions, use_ndc=False, height=0, width=0, focal=1.0, ndc_near=1.0,
+                 want_viewdirs=True):
+    """viewdirs = rd/|rd| and optional ndc_rays (train_utils.py:210-221, nerf_helpers.py:578-605)."""
+    lib = _lib.load()
+    ro = _f32c(ray_origins.reshape(-1, 3))
+    rd = _f32c(ray_directions.reshape(-1, 3))
+    _require_cuda(ro, "ray_origins")
+    n = ro.shape[0]
+    ro_o = torch.empty_like(ro)
+    rd_o = torch.empty_like(rd)
+    vd = torch.empty_like(rd) if want_viewdirs else None
+    if isinstance(focal, (list, tuple)):
+        raise _lib.NvsrError("ndc_rays needs a scalar focal (as in the reference)")
+    with torch.cuda.device(ro.device):
+        st = lib.nvsr_prepare_rays(_ptr(ro), _ptr(rd), n, int(bool(use_ndc)), int(height), int(width), float(focal),
+                                   float(ndc_near), _ptr(ro_o), _ptr(rd_o), _ptr(vd), _stream())
+    _lib.check(st, "nvsr_prepare_rays")
+    return ro_o, rd_o, vd
+
+
+# ---------------------------------------------------------------------------------------------
+def pack_plane(plane_nchw, dtype=NVSR_F32):
+    """[1,C,Rh,Rw] fp32 (models.py:436-439) -> channels-last [Rh,Rw,C] fp32|bf16."""
+    lib = _lib.load()
+    p = _f32c(plane_nchw.detach())
+    _require_cuda(p, "plane")
+    if p.dim() == 4:
+        assert p.shape[0] == 1
+        p = p[0]
+    c, rh, rw = p.shape
+    out = torch.empty((rh, rw, c), dtype=torch.float32 if dtype == NVSR_F32 else torch.bfloat16, device=p.device)
+    with torch.cuda.device(p.device):
+        st = lib.nvsr_pack_plane(_ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
+    _lib.check(st, "nvsr_pack_plane")
+    return out
+
+
+def pack_weight_bf16(weight, k_pad=None):
+    """nn.Linear weight [n_out,k] (may be a column-slice view) -> UMMA image [k_pad/8, n_out, 8] bf16."""
+    lib = _lib.load()
+    w = weight.detach()
+    _require_cuda(w, "weight")
+    if w.dtype != torch.float32 or w.stride(1) != 1:
+        w = w.float().contiguous()
+    n_out, k = w.shape
+    ldw = w.stride(0)
+    if k_pad is None:
+        k_pad = (k + 15) // 16 * 16
+    out = torch.empty((k_pad // 8, n_out, 8), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        st = lib.nvsr_pack_weight_bf16(_ptr(w), n_out, k, ldw, k_pad, _ptr(out), _stream())
+    _lib.check(st, "nvsr_pack_weight_bf16")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+class PackedPlanes:
+    """Device-resident, channels-last position planes of one scene + box + projection matrices."""
+
+    def __init__(self, planes, dtype, box_lo, box_rng, proj, vplane=None, view_lo_rng=None):
+        self.planes = planes            # list of 3 tensors [Rh,Rw,C]
+        self.dtype = dtype
+        self.box_lo = [float(v) for v in box_lo]
+        self.box_rng = [float(v) for v in box_rng]
+        self.proj = proj                # 3 x [3][2] nested lists
+        self.vplane = vplane            # [Rh,Rw,C] fp32 view-direction plane or None
+        self.view_lo_rng = view_lo_rng  # (az_lo, az_rng, el_lo, el_rng)
+        self.channels = planes[0].shape[-1]
+
+    def cstruct(self):
+        s = _lib.Planes()
+        for d in range(3):
+            s.plane[d] = self.planes[d].data_ptr()
+            s.rh[d], s.rw[d] = self.planes[d].shape[0], self.planes[d].shape[1]
+            s.box_lo[d], s.box_rng[d] = self.box_lo[d], self.box_rng[d]
+            for i in range(3):
+                for j in range(2):
+                    s.proj[d][i * 2 + j] = float(self.proj[d][i][j])
+        s.channels = self.channels
+        s.dtype = self.dtype
+        return s
+
+
+def feature_buffers(rows, channels, layout, device):
+    """Allocate (featP, featM) for `rows` rows in the given layout."""
+    if layout == FEAT_ROWMAJOR_F32:
+        return (torch.empty((rows, 3 * channels), dtype=torch.float32, device=device),
+                torch.empty((rows, channels), dtype=torch.float32, device=device))
+    tiles = (rows + TILE_ROWS - 1) // TILE_ROWS
+    return (torch.empty((tiles, 3 * channels // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=device),
+            torch.empty((tiles, channels // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=device))
+
+
+def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_rand=None, lindisp=False,
+                  n_samples=None, out=None, want_z=True):
+    """Fused stratified sampler + tri-plane gather (train_utils.py:95-111 + models.py:381-391 xyz half).
+
+    Returns (featP, featM, z_vals[n,S] or None)."""
+    lib = _lib.load()
+    n = ro.shape[0]
+    if z_in is not None:
+        S = z_in.shape[1]
+        z_in = _f32c(z_in)
+    else:
+        S = t_vals.numel() if n_samples is None else n_samples
+        t_vals = _f32c(t_vals)
+    rows = n * S
+    if out is None:
+        out = feature_buffers(rows, packed.channels, layout, ro.device)
+    feat_p, feat_m = out
+    z_out = torch.empty((n, S), dtype=torch.float32, device=ro.device) if (want_z and z_in is None) else None
+    s = _lib.Sampler()
+    s.n_rays, s.n_samples = n, S
+    s.ro, s.rd = ro.data_ptr(), rd.data_ptr()
+    s.near_, s.far_, s.lindisp = float(near), float(far), int(bool(lindisp))
+    s.t_vals = 0 if t_vals is None else t_vals.data_ptr()
+    s.t_rand = 0 if t_rand is None else t_rand.data_ptr()
+    s.z_in = 0 if z_in is None else z_in.data_ptr()
+    pl = packed.cstruct()
+    with torch.cuda.device(ro.device):
+        st = lib.nvsr_sample_gather(C.byref(s), C.byref(pl), layout, _ptr(feat_p), _ptr(feat_m), _ptr(z_out), _stream())
+    _lib.check(st, "nvsr_sample_gather")
+    return feat_p, feat_m, (z_out if z_in is None else z_in)
+
+
+def viewdir_gather(viewdirs, packed):
+    """cart2az_el + normalize + project_viewdir per ray (nerf_helpers.py:492-496, models.py:312-326)."""
+    lib = _lib.load()
+    vd = _f32c(viewdirs)
+    n = vd.shape[0]
+    vp = packed.vplane
+    out = torch.empty((n, vp.shape[-1]), dtype=torch.float32, device=vd.device)
+    az_lo, az_rng, el_lo, el_rng = packed.view_lo_rng
+    with torch.cuda.device(vd.device):
+        st = lib.nvsr_viewdir_gather(_ptr(vd), n, _ptr(vp), vp.shape[0], vp.shape[1], vp.shape[2], az_lo, az_rng,
+                                     el_lo, el_rng, _ptr(out), _stream())
+    _lib.check(st, "nvsr_viewdir_gather")
+    return out
+
+
+def row_bias(vin, weight_cols, bias):
+    """out[ray] = bias + weight_cols @ vin[ray]; weight_cols may be a column-slice view of a Linear weight."""
+    lib = _lib.load()
+    vin = _f32c(vin)
+    w = weight_cols.detach()
+    if w.dtype != torch.float32 or w.stride(1) != 1:
+        w = w.float().contiguous()
+    n, k = vin.shape
+    n_out = w.shape[0]
+    assert w.shape[1] == k
+    b = None if bias is None else _f32c(bias.detach())
+    out = torch.empty((n, n_out), dtype=torch.float32, device=vin.device)
+    with torch.cuda.device(vin.device):
+        st = lib.nvsr_row_bias(_ptr(vin), n, k, _ptr(w), w.stride(0), _ptr(b), n_out, _ptr(out), _stream())
+    _lib.check(st, "nvsr_row_bias")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+class ChainLayer:
+    """One dense layer of a decoder chain (+ optional fp32 output head tapped on its output)."""
+
+    def __init__(self, w, bias, k, n_out, relu, row_bias=None, head_w=None, head_b=None, head_ch=0):
+        self.w, self.bias, self.k, self.n_out, self.relu = w, bias, k, n_out, relu
+        self.row_bias, self.head_w, self.head_b, self.head_ch = row_bias, head_w, head_b, head_ch
+
+
+def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1):
+    """Evaluate one decoder chain (models.py:393-421 / :85-108) over `rows` rows into planar raw [4,stride]."""
+    lib = _lib.load()
+    m = _lib.Mlp()
+    m.precision = precision
+    m.n_layers = len(layers)
+    keep = []
+    for i, ly in enumerate(layers):
+        c = m.layer[i]
+        c.w = ly.w.data_ptr()
+        c.bias = 0 if ly.bias is None else ly.bias.data_ptr()
+        c.row_bias = 0 if ly.row_bias is None else ly.row_bias.data_ptr()
+        c.head_w = 0 if ly.head_w is None else ly.head_w.data_ptr()
+        c.head_b = 0 if ly.head_b is None else ly.head_b.data_ptr()
+        c.k, c.n_out, c.relu = ly.k, ly.n_out, int(bool(ly.relu))
+        c.head_n = 0 if ly.head_w is None else ly.head_w.shape[0]
+        c.head_ch = ly.head_ch
+        keep.append(ly)
+    m.in_ = inp.data_ptr()
+    m.rows = rows
+    m.samples_per_ray = samples_per_ray
+    m.n_rays = n_rays
+    m.raw = raw.data_ptr()
+    m.raw_stride = raw.stride(0)
+    with torch.cuda.device(raw.device):
+        st = lib.nvsr_mlp_chain(C.byref(m), _stream())
+    _lib.check(st, "nvsr_mlp_chain")
+    return raw
+
+
+# ---------------------------------------------------------------------------------------------
+def composite(raw, z, rd, n_samples, noise=None, white_background=False, mip=False, n_fine=0, u=None,
+              want_weights=False, want_inds=False, want_samples=False):
+    """volume_render_radiance_field (+ sample_pdf and the sort-merge on the coarse pass).
+
+    raw: planar [4, stride] (r,g,b,sigma).  Returns a dict with rgb/disp/acc/depth and, optionally,
+    weights / inds / z_samples / z_merged."""
+    lib = _lib.load()
+    n = rd.shape[0]
+    dev = rd.device
+    c = _lib.Composite()
+    c.n_rays, c.n_samples = n, n_samples
+    c.raw, c.raw_stride = raw.data_ptr(), raw.stride(0)
+    z = _f32c(z)
+    rd = _f32c(rd)
+    c.z, c.rd = z.data_ptr(), rd.data_ptr()
+    noise = None if noise is None else _f32c(noise)
+    c.noise = 0 if noise is None else noise.data_ptr()
+    c.white_bkgd, c.mip = int(bool(white_background)), int(bool(mip))
+    out = {
+        "rgb": torch.empty((n, 3), dtype=torch.float32, device=dev),
+        "disp": torch.empty((n,), dtype=torch.float32, device=dev),
+        "acc": torch.empty((n,), dtype=torch.float32, device=dev),
+        "depth": torch.empty((n,), dtype=torch.float32, device=dev),
+    }
+    if want_weights:
+        out["weights"] = torch.empty((n, n_samples), dtype=torch.float32, device=dev)
+    c.rgb, c.disp, c.acc, c.depth = (out[k].data_ptr() for k in ("rgb", "disp", "acc", "depth"))
+    c.weights = out["weights"].data_ptr() if want_weights else 0
+    c.n_fine = int(n_fine)
+    if n_fine > 0:
+        u = _f32c(u)
+        c.u = u.data_ptr()
+        c.u_per_ray = int(u.dim() == 2)
+        s1 = n_samples + (1 if mip else 0)
+        out["z_merged"] = torch.empty((n, s1 + n_fine), dtype=torch.float32, device=dev)
+        c.z_merged = out["z_merged"].data_ptr()
+        if want_inds:
+            out["inds"] = torch.empty((n, n_fine), dtype=torch.int64, device=dev)
+            c.inds = out["inds"].data_ptr()
+        if want_samples:
+            out["z_samples"] = torch.empty((n, n_fine), dtype=torch.float32, device=dev)
+            c.z_samples = out["z_samples"].data_ptr()
+    with torch.cuda.device(dev):
+        st = lib.nvsr_composite(C.byref(c), _stream())
+    _lib.check(st, "nvsr_composite")
+    return out
+
+
+def raw_to_planar(radiance_field):
+    """[N,S,4] (reference layout, train_utils.py:57-60) -> planar [4, N*S]."""
+    n, s, _ = radiance_field.shape
+    return radiance_field.reshape(n * s, 4).t().contiguous()
+
+
+def volume_render_radiance_field(radiance_field, depth_values, ray_directions, radiance_field_noise_std=0.0,
+                                 white_background=False, mip_nerf=False, noise=None):
+    """Drop-in for volume_rendering_utils.volume_render_radiance_field (:6-51).
+
+    When radiance_field_noise_std > 0 the reference draws CPU randn (:32); pass the same draw as
+    `noise` ([N,S], unscaled) for parity, otherwise it is drawn here with torch.randn on CPU."""
+    rf = _f32c(radiance_field)
+    n, s, _ = rf.shape
+    nz = None
+    if radiance_field_noise_std > 0.0:
+        if noise is None:
+            noise = torch.randn(rf[..., 3].shape)
+        nz = (noise * radiance_field_noise_std).to(rf)
+    o = composite(raw_to_planar(rf), depth_values, ray_directions, s, noise=nz, white_background=white_background,
+                  mip=mip_nerf, want_weights=True)
+    return o["rgb"], o["disp"], o["acc"], o["weights"], o["depth"]
+
+
+def sample_pdf(bins, weights, num_samples, det=False, u=None, cdf=None, return_all=False):
+    """Drop-in for nerf_helpers.sample_pdf_2 (:668-702), bound as sample_pdf at train_utils.py:4.
+
+    `u` overrides the uniform draws (the reference draws them on the CPU); `cdf` bypasses the
+    pdf/cdf construction (stage test: identical cdf,u => bit-exact indices)."""
+    lib = _lib.load()
+    bins = _f32c(bins)
+    _require_cuda(bins, "bins")
+    n, nb = bins.shape
+    dev = bins.device
+    if u is None:
+        u = torch.linspace(0.0, 1.0, steps=num_samples) if det else torch.rand([n, num_samples])
+    u = _f32c(u, dev)
+    w = None if weights is None else _f32c(weights)
+    cdf = None if cdf is None else _f32c(cdf)
+    inds = torch.empty((n, num_samples), dtype=torch.int64, device=dev)
+    samples = torch.empty((n, num_samples), dtype=torch.float32, device=dev)
+    cdf_out = torch.empty((n, nb), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.nvsr_sample_pdf(_ptr(bins), _ptr(w), _ptr(cdf), n, nb, _ptr(u), int(u.dim() == 2), num_samples,
+                                 _ptr(inds), _ptr(samples), _ptr(cdf_out), _stream())
+    _lib.check(st, "nvsr_sample_pdf")
+    if return_all:
+        return samples, inds, cdf_out
+    return samples
+
+
+# ---------------------------------------------------------------------------------------------
+def ipe(z_edges, ro, rd, radius, n_freqs, layout=FEAT_ROWMAJOR_F32, k_pad=None):
+    """cast_rays + IntegratedPositionalEncoding (mip.py:9-43,154-199): z_edges [n,S+1] -> [n*S, 6*n_freqs]."""
+    lib = _lib.load()
+    z = _f32c(z_edges)
+    n, s1 = z.shape
+    S = s1 - 1
+    dev = z.device
+    if layout == FEAT_ROWMAJOR_F32:
+        out = torch.empty((n * S, 6 * n_freqs), dtype=torch.float32, device=dev)
+        k_pad = 0
+    else:
+        k_pad = k_pad or (6 * n_freqs + 15) // 16 * 16
+        tiles = (n * S + TILE_ROWS - 1) // TILE_ROWS
+        out = torch.empty((tiles, k_pad // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.nvsr_ipe(_ptr(z), _ptr(_f32c(ro)), _ptr(_f32c(rd)), n, S, float(radius), n_freqs, layout, k_pad,
+                          _ptr(out), _stream())
+    _lib.check(st, "nvsr_ipe")
+    return out
+
+
+def dir_encoding(dirs, n_freqs, include_input=True):
+    """positional_encoding(dirs, n_freqs, include_input) per ray (nerf_helpers.py:552-575)."""
+    lib = _lib.load()
+    d = _f32c(dirs)
+    n = d.shape[0]
+    out = torch.empty((n, (3 if include_input else 0) + 6 * n_freqs), dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        st = lib.nvsr_dir_encoding(_ptr(d), n, n_freqs, int(bool(include_input)), _ptr(out), _stream())
+    _lib.check(st, "nvsr_dir_encoding")
+    return out
+
+
+def mip_radius(scene_id):
+    """radii of train_utils.py:21-23: DS parsed from the scene id suffix `_DS<k>`."""
+    import re
+    m = re.search(r"(?<=_DS)(\d)+(?=$)", scene_id)
+    if m is None:
+        raise _lib.NvsrError(f"mip path needs a scene id ending in _DS<k>, got {scene_id!r}")
+    return int(m.group(0)) * 0.00135 * 2 / math.sqrt(12.0)

@@ -1,0 +1,349 @@
+"""Drop-in render path: same call surface as the reference's train_utils.py, kernels underneath.
+
+    run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, ...)
+    eval_nerf(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions, ...)
+    install(train_utils_module)     rebinds train_utils.run_one_iter_of_nerf
+
+Per ray chunk the pipeline is 5 launches per pass instead of the reference's few hundred ATen ops:
+  viewdir gather -> [coarse] row-bias, sampler+gather, density chain, rgb chain, composite+resample
+                 -> [fine]   row-bias, sampler+gather, density chain, rgb chain, composite
+Nothing of pts / embedded / hidden activations is materialised in HBM; the only intermediates are
+the feature tiles (gather -> decoder) and raw [4, rows] (decoder -> composite).
+
+Engagement rule: forward-only.  Under autograd (training) the kernels are not engaged: `install`
+keeps calling the reference's own function there; calling this module's functions directly with
+grad enabled raises.  Unsupported model configurations raise NotImplementedError — no fallback.
+"""
+import os
+
+import torch
+
+from . import _lib, ops, scene
+from ._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, NVSR_BF16, NVSR_F32
+
+_PRECISION = {"bf16": NVSR_BF16, "fp32": NVSR_F32}
+_state = {
+    "precision": _PRECISION[os.environ.get("NVSR_PRECISION", "bf16")],
+    "ray_chunk": int(os.environ.get("NVSR_RAY_CHUNK", "32768")),
+}
+
+
+def set_precision(name):
+    """'bf16': tcgen05 decoder + bf16 planes/features (fp32 accumulate) — the performance contract;
+    'fp32': SIMT fp32 everywhere — the 1e-3 parity contract."""
+    _state["precision"] = _PRECISION[name]
+
+
+def get_precision():
+    return "bf16" if _state["precision"] == NVSR_BF16 else "fp32"
+
+
+def set_ray_chunk(n):
+    _state["ray_chunk"] = int(n)
+
+
+def _is_planes_model(m):
+    return hasattr(m, "planes_") or hasattr(m, "coord_projector")
+
+
+def _t_vals(n, device):
+    # torch.linspace has its own rounding rule; take it from torch itself
+    return torch.linspace(0.0, 1.0, n).to(device=device, dtype=torch.float32)
+
+
+def _raw_buffer(rows, device):
+    stride = (rows + 127) // 128 * 128
+    return torch.empty((4, stride), dtype=torch.float32, device=device)
+
+
+def _slice(t, i0, i1):
+    return None if t is None else t[i0:i1]
+
+
+_pass_cache = {}
+
+
+def _params_sig(model):
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+def _planes_pass(model, scene_id, precision):
+    """Cached _PlanesPass: rebuilt only when a plane tensor or a decoder weight changed."""
+    model.set_cur_scene_id(scene_id)
+    sig = tuple(scene._Cache.key_of(scene._source_plane(model, d)) for d in range(4)) + _params_sig(model)
+    key = (id(model), scene_id, precision)
+    hit = _pass_cache.get(key)
+    if hit is None or hit[0] != sig:
+        hit = (sig, _PlanesPass(model, scene_id, precision))
+        _pass_cache[key] = hit
+    return hit[1]
+
+
+def _mip_pass(model, precision):
+    sig = _params_sig(model)
+    key = (id(model), "mip", precision)
+    hit = _pass_cache.get(key)
+    if hit is None or hit[0] != sig:
+        hit = (sig, _MipPass(model, precision))
+        _pass_cache[key] = hit
+    return hit[1]
+
+
+class _PlanesPass:
+    """Everything one (model, scene) pair needs on the device, packed once and cached."""
+
+    def __init__(self, model, scene_id, precision):
+        scene.check_supported_planes_model(model)
+        self.precision = precision
+        self.layout = FEAT_TILE_BF16 if precision == NVSR_BF16 else FEAT_ROWMAJOR_F32
+        self.planes = scene.pack_scene_planes(model, scene_id, precision)
+        self.dec = scene.pack_planes_decoder(model, precision)
+
+    def radiance(self, ro, rd, vfeat, near, far, lindisp, S, t_vals=None, z_in=None, t_rand=None):
+        """-> (raw planar [4,stride], z [n,S])"""
+        n = ro.shape[0]
+        rows = n * S
+        fp, fm, z = ops.sample_gather(ro, rd, near, far, self.planes, self.layout, t_vals=t_vals, z_in=z_in,
+                                      t_rand=t_rand, lindisp=lindisp)
+        rbias = ops.row_bias(vfeat, self.dec.view_w, self.dec.view_b)
+        raw = _raw_buffer(rows, ro.device)
+        ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n)
+        ops.mlp_chain(fp, self.dec.rgb_chain(rbias), rows, raw, self.precision, S, n)
+        return raw, z
+
+
+def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
+    n = ro.shape[0]
+    dev = ro.device
+    Nc, Nf = cfg.num_coarse, cfg.num_fine
+    vfeat = ops.viewdir_gather(vd, pc.planes)
+    t_rand = randoms.get("t_rand") if cfg.perturb else None
+    if cfg.perturb and t_rand is None:
+        t_rand = torch.rand([n, Nc]).to(dev)  # CPU RNG like train_utils.py:108
+    raw, z = pc.radiance(ro, rd, vfeat, near, far, cfg.lindisp, Nc, t_vals=_t_vals(Nc, dev), t_rand=t_rand)
+    u = None
+    if Nf > 0:
+        u = randoms.get("u")
+        if u is None:
+            u = _t_vals(Nf, dev) if cfg.perturb == 0.0 else torch.rand([n, Nf]).to(dev)
+    noise_c = _noise(randoms.get("noise_c"), cfg, n, Nc, dev)
+    co = ops.composite(raw, z, rd, Nc, noise=noise_c, white_background=cfg.white_background, n_fine=Nf, u=u,
+                       want_weights=trace is not None, want_inds=trace is not None, want_samples=trace is not None)
+    if trace is not None:
+        trace.update(z_coarse=z, raw_coarse=raw[:, :n * Nc].t().reshape(n, Nc, 4), weights_coarse=co["weights"],
+                     depth_coarse=co["depth"])
+    fo = None
+    if Nf > 0:
+        zf = co["z_merged"]
+        # fine model may read different (super-resolved) planes but shares the view-direction plane
+        vfeat_f = vfeat if pf.planes.vplane is pc.planes.vplane else ops.viewdir_gather(vd, pf.planes)
+        raw_f, _ = pf.radiance(ro, rd, vfeat_f, near, far, cfg.lindisp, Nc + Nf, z_in=zf)
+        noise_f = _noise(randoms.get("noise_f"), cfg, n, Nc + Nf, dev)
+        fo = ops.composite(raw_f, zf, rd, Nc + Nf, noise=noise_f, white_background=cfg.white_background)
+        if trace is not None:
+            trace.update(inds=co["inds"], z_samples=co["z_samples"], z_fine=zf,
+                         raw_fine=raw_f[:, :n * (Nc + Nf)].t().reshape(n, Nc + Nf, 4), depth_fine=fo["depth"])
+    return co, fo
+
+
+def _noise(given, cfg, n, S, dev):
+    std = cfg.radiance_field_noise_std
+    if not std or std <= 0.0:
+        return None
+    if given is None:
+        given = torch.randn([n, S])  # CPU RNG like volume_rendering_utils.py:32
+    return (given * std).to(device=dev, dtype=torch.float32)
+
+
+class _MipPass:
+    def __init__(self, model, precision):
+        self.precision = precision
+        self.layout = FEAT_TILE_BF16 if precision == NVSR_BF16 else FEAT_ROWMAJOR_F32
+        self.dec = scene.pack_mip_decoder(model, precision)
+
+    def radiance(self, z_edges, ro, rd, denc, radius, n_freqs):
+        n, s1 = z_edges.shape
+        S = s1 - 1
+        rows = n * S
+        enc = ops.ipe(z_edges, ro, rd, radius, n_freqs, self.layout, self.dec.k0 if self.precision == NVSR_BF16 else None)
+        rbias = ops.row_bias(denc, self.dec.dir_w, self.dec.dir_b)
+        raw = _raw_buffer(rows, ro.device)
+        ops.mlp_chain(enc, self.dec.chain(rbias), rows, raw, self.precision, S, n)
+        return raw
+
+
+def _render_mip_chunk(mc, mf, ro, rd, vd, near, far, cfg, radius, n_freqs, n_dir_freqs, randoms, trace):
+    n, dev = ro.shape[0], ro.device
+    Nc, Nf = cfg.num_coarse, cfg.num_fine
+    # z edges [n, Nc+1] (train_utils.py:95-109).  Elementwise on [n,65]: plumbing, kept in torch so the
+    # rounding is torch's own.
+    t = _t_vals(Nc + 1, dev)
+    nr = torch.full((n, 1), float(near), device=dev)
+    fr = torch.full((n, 1), float(far), device=dev)
+    z = nr * (1.0 - t) + fr * t if not cfg.lindisp else 1.0 / (1.0 / nr * (1.0 - t) + 1.0 / fr * t)
+    if cfg.perturb:
+        mids = 0.5 * (z[..., 1:] + z[..., :-1])
+        upper, lower = torch.cat((mids, z[..., -1:]), -1), torch.cat((z[..., :1], mids), -1)
+        t_rand = randoms.get("t_rand")
+        t_rand = torch.rand(z.shape).to(dev) if t_rand is None else t_rand
+        z = lower + (upper - lower) * t_rand
+    z = z.contiguous()
+    denc = ops.dir_encoding(vd, n_dir_freqs, True)
+    raw = mc.radiance(z, ro, rd, denc, radius, n_freqs)
+    u = None
+    if Nf > 0:
+        u = randoms.get("u")
+        if u is None:
+            u = _t_vals(Nf + 1, dev) if cfg.perturb == 0.0 else torch.rand([n, Nf + 1]).to(dev)
+    co = ops.composite(raw, z, rd, Nc, noise=_noise(randoms.get("noise_c"), cfg, n, Nc, dev),
+                       white_background=cfg.white_background, mip=True, n_fine=(Nf + 1 if Nf > 0 else 0), u=u,
+                       want_weights=trace is not None, want_inds=trace is not None, want_samples=trace is not None)
+    if trace is not None:
+        trace.update(z_coarse=z, raw_coarse=raw[:, :n * Nc].t().reshape(n, Nc, 4), weights_coarse=co["weights"])
+    fo = None
+    if Nf > 0:
+        zf = co["z_merged"]
+        Sf = zf.shape[1] - 1
+        raw_f = mf.radiance(zf, ro, rd, denc, radius, n_freqs)
+        fo = ops.composite(raw_f, zf, rd, Sf, noise=_noise(randoms.get("noise_f"), cfg, n, Sf, dev),
+                           white_background=cfg.white_background, mip=True)
+        if trace is not None:
+            trace.update(inds=co["inds"], z_samples=co["z_samples"], z_fine=zf,
+                         raw_fine=raw_f[:, :n * Sf].t().reshape(n, Sf, 4))
+    return co, fo
+
+
+def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode="train",
+                         encode_position_fn=None, encode_direction_fn=None, scene_config={}, randoms=None,
+                         trace=None):
+    """Drop-in for train_utils.run_one_iter_of_nerf (train_utils.py:185-282): same arguments, same
+    9-tuple (rgb_coarse, disp_coarse, acc_coarse, rgb_fine, disp_fine, acc_fine, None, None, None).
+
+    Extra keyword-only extensions (not in the reference): `randoms` supplies the uniform/normal draws
+    the reference takes from the CPU RNG (keys t_rand [N,Nc], u [N,Nf], noise_c, noise_f), `trace`
+    (a dict) receives per-stage tensors for parity tests."""
+    if torch.is_grad_enabled():
+        raise RuntimeError("nvsr_b200.run_one_iter_of_nerf is forward-only: call it under torch.no_grad() "
+                           "(training keeps the reference's autograd path; see install())")
+    precision = _state["precision"]
+    cfg = getattr(options.nerf, mode)
+    mip = getattr(options.nerf, "encode_position_fn", None) == "mip"
+    if not options.nerf.use_viewdirs:
+        raise NotImplementedError("nvsr_b200: use_viewdirs=False is not supported")
+    ro_in, rd_in = batch_rays[0], batch_rays[1]
+    if not ro_in.is_cuda:
+        raise _lib.NvsrError("batch_rays must be CUDA tensors: nvsr_b200 has no CPU path")
+    use_ndc = scene_config.no_ndc is False
+    ro, rd, vd = ops.prepare_rays(ro_in, rd_in, use_ndc, H, W, focal if use_ndc else 1.0, 1.0)
+    n_total = ro.shape[0]
+    near, far = float(scene_config.near), float(scene_config.far)
+    randoms = randoms or {}
+
+    if _is_planes_model(model_coarse):
+        if mip:
+            raise NotImplementedError("nvsr_b200: IPE feeds FlexibleNeRFModel only (train_nerf.py:290-291)")
+        model_coarse.set_cur_scene_id(scene_id)
+        model_fine.set_cur_scene_id(scene_id)
+        pc = _planes_pass(model_coarse, scene_id, precision)
+        pf = _planes_pass(model_fine, scene_id, precision) if cfg.num_fine > 0 else None
+        runner = lambda a, b, c, rnd, tr: _render_planes_chunk(pc, pf, a, b, c, near, far, cfg, rnd, tr)
+    else:
+        if not mip:
+            raise NotImplementedError("nvsr_b200: FlexibleNeRFModel is supported with the mip/IPE encoding only")
+        n_freqs = getattr(encode_position_fn, "max_freq", None)
+        if n_freqs is None:
+            raise NotImplementedError("nvsr_b200: encode_position_fn must be an IntegratedPositionalEncoding")
+        if model_coarse.dim_xyz != 6 * n_freqs:
+            raise _lib.NvsrError("IPE width does not match the model's dim_xyz")
+        n_dir = (model_coarse.dim_dir - 3) // 6
+        radius = ops.mip_radius(scene_id)
+        mc = _mip_pass(model_coarse, precision)
+        mf = _mip_pass(model_fine, precision) if cfg.num_fine > 0 else None
+        runner = lambda a, b, c, rnd, tr: _render_mip_chunk(mc, mf, a, b, c, near, far, cfg, radius, n_freqs, n_dir,
+                                                            rnd, tr)
+
+    chunk = _state["ray_chunk"]
+    outs_c, outs_f, traces = [], [], []
+    for i0 in range(0, n_total, chunk):
+        i1 = min(n_total, i0 + chunk)
+        rnd = {k: (v[i0:i1] if (torch.is_tensor(v) and v.dim() == 2 and v.shape[0] == n_total) else v)
+               for k, v in randoms.items()}
+        rnd = {k: (v.to(ro.device) if torch.is_tensor(v) else v) for k, v in rnd.items()}
+        tr = {} if trace is not None else None
+        co, fo = runner(ro[i0:i1], rd[i0:i1], vd[i0:i1], rnd, tr)
+        outs_c.append(co)
+        outs_f.append(fo)
+        if tr is not None:
+            traces.append(tr)
+    if trace is not None and traces:
+        for k in traces[0]:
+            trace[k] = torch.cat([t[k] for t in traces], 0)
+
+    def cat(outs, key):
+        if outs[0] is None:
+            return None
+        return outs[0][key] if len(outs) == 1 else torch.cat([o[key] for o in outs], 0)
+
+    return (cat(outs_c, "rgb"), cat(outs_c, "disp"), cat(outs_c, "acc"),
+            cat(outs_f, "rgb"), cat(outs_f, "disp"), cat(outs_f, "acc"), None, None, None)
+
+
+def eval_nerf(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions, options, scene_id,
+              mode="validation", encode_position_fn=None, encode_direction_fn=None, scene_config={}):
+    """Drop-in for train_utils.eval_nerf (train_utils.py:285-331): full-image synthesis; like the
+    reference it returns only the rgb images (disp/acc slots are None)."""
+    batch = torch.stack((ray_origins.reshape(-1, 3), ray_directions.reshape(-1, 3)), 0)
+    rgb_c, _, _, rgb_f, _, _, _, _, _ = run_one_iter_of_nerf(
+        height, width, focal_length, model_coarse, model_fine, batch, options, scene_id, mode="validation",
+        encode_position_fn=encode_position_fn, encode_direction_fn=encode_direction_fn, scene_config=scene_config)
+    rgb_c = rgb_c.reshape([height, width, -1])
+    if rgb_f is not None:
+        rgb_f = rgb_f.reshape([height, width, -1])
+    return rgb_c, None, None, rgb_f, None, None, None, None, None
+
+
+def render_frame(height, width, focal, pose, model_coarse, model_fine, options, scene_id, scene_config,
+                 downsampling_offset=0.0, row_range=None, encode_position_fn=None, encode_direction_fn=None):
+    """get_ray_bundle + run_one_iter_of_nerf for image rows `row_range` (default: all).  Returns the
+    9-tuple for that row band (ray order = row-major within the band)."""
+    ro, rd = ops.get_ray_bundle(height, width, focal, pose, 0, downsampling_offset, row_range=row_range)
+    batch = torch.stack((ro.reshape(-1, 3), rd.reshape(-1, 3)), 0)
+    return run_one_iter_of_nerf(height, width, focal, model_coarse, model_fine, batch, options, scene_id,
+                                mode="validation", encode_position_fn=encode_position_fn,
+                                encode_direction_fn=encode_direction_fn, scene_config=scene_config)
+
+
+_installed = {}
+
+
+def install(train_utils_module, nerf_helpers_module=None):
+    """Rebind the reference's seams: `train_utils.run_one_iter_of_nerf` (which
+    `eval_nerf` resolves through module globals at call time, train_utils.py:311) and, optionally,
+    `nerf_helpers.get_ray_bundle`.  Under autograd the original functions keep running."""
+    orig = train_utils_module.run_one_iter_of_nerf
+    if getattr(orig, "_nvsr_b200", False):
+        return
+
+    def run_one_iter_of_nerf_b200(*args, **kwargs):
+        if torch.is_grad_enabled():
+            return orig(*args, **kwargs)
+        return run_one_iter_of_nerf(*args, **kwargs)
+
+    run_one_iter_of_nerf_b200._nvsr_b200 = True
+    _installed[train_utils_module] = orig
+    train_utils_module.run_one_iter_of_nerf = run_one_iter_of_nerf_b200
+    if nerf_helpers_module is not None:
+        orig_grb = nerf_helpers_module.get_ray_bundle
+
+        def get_ray_bundle_b200(height, width, focal_length, tform_cam2world, padding_size=0, downsampling_offset=0):
+            if not tform_cam2world.is_cuda:
+                return orig_grb(height, width, focal_length, tform_cam2world, padding_size, downsampling_offset)
+            return ops.get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size, downsampling_offset)
+
+        nerf_helpers_module.get_ray_bundle = get_ray_bundle_b200
+
+
+def uninstall(train_utils_module):
+    orig = _installed.pop(train_utils_module, None)
+    if orig is not None:
+        train_utils_module.run_one_iter_of_nerf = orig

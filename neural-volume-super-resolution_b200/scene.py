@@ -1,0 +1,460 @@
+"""Scene / model state the render path reads, and how it is packed for the kernels.
+
+Two things live here:
+  1. duck-typed STAND-INS for the reference objects the hot path reads (`TwoDimPlanesModel`,
+     `FlexibleNeRFModel`, `SceneCoupler`, `CfgNode`) — just enough state, with the reference's
+     attribute names, to build synthetic Blender-shaped scenes on a box where the reference is
+     not importable (tests, bench, smoke).  The render path itself works on the real reference
+     objects as well: it only reads the attributes listed in SURVEY.md §8(b).
+  2. the packers: planes NCHW fp32 -> channels-last (fp32|bf16), decoder weights -> chain layers.
+     Packing is cached per (tensor identity, version) so it happens once per scene / weight update,
+     never per chunk (the reference re-uploads the SR plane for every network chunk, models.py:893).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import NVSR_BF16, NVSR_F32
+
+
+# --------------------------------------------------------------------------------------------------
+# config containers (cfgnode.py:36 CfgNode is an attribute-access dict; this is the minimal equal)
+class Cfg(dict):
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = Cfg(v) if isinstance(v, dict) and not isinstance(v, Cfg) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def render_options(num_coarse=64, num_fine=128, perturb=False, lindisp=False, white_background=False,
+                   noise_std=0.0, chunksize=131072, use_viewdirs=True, mip=False):
+    """options.nerf.<mode>.* keys read by the path (train_utils.py:82-113,136-151,210-234)."""
+    sub = dict(chunksize=chunksize, perturb=perturb, num_coarse=num_coarse, num_fine=num_fine,
+               white_background=white_background, radiance_field_noise_std=noise_std, lindisp=lindisp)
+    nerf = dict(use_viewdirs=use_viewdirs, train=dict(sub), validation=dict(sub))
+    if mip:
+        nerf["encode_position_fn"] = "mip"
+    return Cfg(nerf=nerf)
+
+
+def scene_cfg(near=2.0, far=6.0, no_ndc=True):
+    return Cfg(near=near, far=far, no_ndc=no_ndc)
+
+
+# --------------------------------------------------------------------------------------------------
+# stand-ins
+def get_plane_name(scene_id, dimension):  # naming scheme of models.py:110-113
+    return "_D%d" % dimension if scene_id is None else "sc%s_D%d" % (scene_id, dimension)
+
+
+class SingleSceneCoupler:
+    """SceneCoupler (models.py:928-1019) for scenes without LR/HR pairing, plus an optional explicit
+    HR->LR map for the super-resolution configuration (planes are stored under the LR id)."""
+
+    def __init__(self, sr_pairs=None):
+        self.downsample_couples = dict(sr_pairs or {})  # hr_scene -> lr_scene
+        self.upsample_couples = {}
+        self.HR_planes = []
+        self.ds_factor = 1
+
+    def _scene_of(self, plane_name):
+        return plane_name[2:plane_name.rindex("_D")]
+
+    def scene_with_saved_plane(self, name, plane_not_scene=False):
+        if plane_not_scene:
+            sc = self._scene_of(name)
+            return name.replace(sc, self.downsample_couples.get(sc, sc))
+        return self.downsample_couples.get(name, name)
+
+    def should_SR(self, name, plane_not_scene=False):
+        sc = self._scene_of(name) if plane_not_scene else name
+        return sc in self.downsample_couples
+
+    def should_downsample(self, plane_name, for_LR_loading=False):
+        return False
+
+
+class _Projector(nn.Module):
+    def __init__(self):
+        super().__init__()
+        eye = torch.eye(3)
+        # CoordProjector (models.py:477-478): plane d keeps columns [1:] of these
+        self.rot_mats_NON_LEARNED = nn.ParameterList(
+            [nn.Parameter(m.clone(), requires_grad=False) for m in (eye, eye[:, [1, 0, 2]], eye[:, [2, 0, 1]])])
+
+
+class TriPlaneModel(nn.Module):
+    """State-compatible stand-in of TwoDimPlanesModel (models.py:118-421) for the shipped config
+    (config/TrainModels.yml:66-93): 3 position planes + 1 view plane, proj 'avg', view 'concat_pos',
+    rgb input 'projections', density 48->128x4->1, rgb 192->128x4->3, no skip firing."""
+
+    def __init__(self, num_plane_channels=48, dec_channels=128, dec_density_layers=4, dec_rgb_layers=4,
+                 scene_coupler=None):
+        super().__init__()
+        self.use_viewdirs = True
+        self.num_density_planes = 3
+        self.num_plane_channels = num_plane_channels
+        self.num_viewdir_plane_channels = num_plane_channels
+        self.rgb_dec_input = "projections"
+        self.proj_combination = "avg"
+        self.viewdir_proj_combination = "concat_pos"
+        self.plane_interp = "bilinear"
+        self.align_corners = True
+        self.skip_connect_every = 3
+        self.skip_SR_ = False
+        self.coord_projector = _Projector()
+        self.scene_coupler = scene_coupler or SingleSceneCoupler()
+        c = num_plane_channels
+        self.density_dec = nn.ModuleDict({"0": nn.ModuleList(
+            [nn.Linear(c, dec_channels)] + [nn.Linear(dec_channels, dec_channels) for _ in range(dec_density_layers - 1)])})
+        self.fc_alpha = nn.ModuleDict({"0": nn.Linear(dec_channels, 1)})
+        self.rgb_dec = nn.ModuleDict({"0": nn.ModuleList(
+            [nn.Linear(4 * c, dec_channels)] + [nn.Linear(dec_channels, dec_channels) for _ in range(dec_rgb_layers - 1)])})
+        self.fc_rgb = nn.ModuleDict({"0": nn.Linear(dec_channels, 3)})
+        self.planes_ = nn.ParameterDict()
+        self.box_coords = {}
+        self.cur_id = None
+
+    def set_cur_scene_id(self, scene_id):
+        self.cur_id = scene_id
+
+    def raw_plane(self, plane_name, downsample=False, detach=False):
+        return self.planes_[plane_name]
+
+    def assign_SR_model(self, sr_model):
+        self.SR_model = sr_model
+        self.skip_SR_ = False
+
+    def planes(self, dim_num, super_resolve, grid=None):
+        name = self.scene_coupler.scene_with_saved_plane(get_plane_name(self.cur_id, dim_num), plane_not_scene=True)
+        return self.SR_model(name) if super_resolve else self.planes_[name]
+
+
+class PlaneUpsampler(nn.Module):
+    """Stand-in for PlanesSR (models.py:824-926): stock-PyTorch plane super-resolution, run once per
+    plane and cached.  Only its OUTPUT tensor matters to the hot path (SR inference is out of scope,
+    SURVEY.md §2 row 7); the architecture here is a bilinear x`scale` upsample plus a small residual conv."""
+
+    def __init__(self, channels=48, scale=4, hidden=32):
+        super().__init__()
+        self.scale_factor = scale
+        self.body = nn.Sequential(nn.Conv2d(channels, hidden, 3, padding=1), nn.ReLU(), nn.Conv2d(hidden, channels, 3, padding=1))
+        self.LR_planes, self.SR_planes = {}, {}
+
+    def set_LR_plane(self, plane, id):
+        self.LR_planes[id] = plane
+
+    @torch.no_grad()
+    def forward(self, plane_name):
+        if plane_name not in self.SR_planes:
+            up = nn.functional.interpolate(self.LR_planes[plane_name], scale_factor=self.scale_factor, mode="bilinear",
+                                           align_corners=True)
+            self.SR_planes[plane_name] = up + 0.1 * self.body(up)
+        return self.SR_planes[plane_name]
+
+
+class MipMLP(nn.Module):
+    """Stand-in of FlexibleNeRFModel as train_nerf.py:342-348 builds it for the mip baseline
+    (models.py:14-108 with defaults num_layers=4, hidden=128, skip=4, use_viewdirs)."""
+
+    def __init__(self, num_encoding_fn_xyz=6, num_encoding_fn_dir=4, hidden_size=128):
+        super().__init__()
+        self.dim_xyz = 2 * 3 * num_encoding_fn_xyz          # include_input_xyz=False
+        self.dim_dir = 3 + 2 * 3 * num_encoding_fn_dir      # include_input_dir=True
+        self.skip_connect_every = 4
+        self.use_viewdirs = True
+        self.xyz_input_2_dir = False
+        self.layer1 = nn.Linear(self.dim_xyz, hidden_size)
+        self.layers_xyz = nn.ModuleList([nn.Linear(hidden_size, hidden_size) for _ in range(3)])
+        self.layers_dir = nn.ModuleList([nn.Linear(self.dim_dir + hidden_size, hidden_size // 2)])
+        self.fc_alpha = nn.Linear(hidden_size, 1)
+        self.fc_rgb = nn.Linear(hidden_size // 2, 3)
+        self.fc_feat = nn.Linear(hidden_size, hidden_size)
+
+
+DEFAULT_BOX = [[-1.5, -1.5, -1.5, -math.pi, -math.pi / 2], [1.5, 1.5, 1.5, math.pi, math.pi / 2]]
+
+
+def shape_density(model, gain, shift):
+    """Random-init decoders give degenerate volumes (coarse acc == 1, fine sigma == 0).
+    Rescale the density head so that sigma is positive on a minority of samples with O(10) values."""
+    heads = [model.fc_alpha["0"]] if isinstance(model.fc_alpha, nn.ModuleDict) else [model.fc_alpha]
+    with torch.no_grad():
+        for h in heads:
+            h.weight.mul_(gain)
+            h.bias.fill_(shift)
+
+
+def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device="cpu", scene_id=None,
+                         plane_std=0.5, density_gain=120.0, density_shift=-4.0, sr_scale=None):
+    """Synthetic Blender-shaped scene: seeded coarse+fine decoders, then planes.
+
+    With `sr_scale`, planes are stored at plane_res under an LR id, and the FINE model reads
+    `PlaneUpsampler` output (plane_res*sr_scale) while the coarse model reads the LR planes
+    (apply_2_coarse: False, config/TrainModels.yml:166) — BASELINE config 3a."""
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    sid = scene_id or "synth_DS2_PlRes%d_%d" % (plane_res * (sr_scale or 1), view_res)
+    pairs = None
+    stored_sid = sid
+    if sr_scale:
+        stored_sid = "synth_DS%d_PlRes%d_%d" % (2 * sr_scale, plane_res, view_res)
+        pairs = {sid: stored_sid}
+    coarse = TriPlaneModel(channels, scene_coupler=SingleSceneCoupler())
+    fine = TriPlaneModel(channels, scene_coupler=SingleSceneCoupler(pairs))
+    if sr_scale:
+        coarse.scene_coupler = SingleSceneCoupler(pairs)  # same stored planes, but no SR model attached
+    fine.coord_projector = coarse.coord_projector
+    planes = nn.ParameterDict()
+    for d in range(4):
+        r = plane_res if d < 3 else view_res
+        planes[get_plane_name(stored_sid, d)] = nn.Parameter(plane_std * torch.randn(1, channels, r, r))
+    box = torch.tensor(DEFAULT_BOX, dtype=torch.float64)
+    for m in (coarse, fine):
+        m.planes_ = planes
+        m.box_coords = {sid: box, stored_sid: box}
+        shape_density(m, density_gain, density_shift)
+        m.eval()
+    coarse.to(device)
+    fine.to(device)
+    if sr_scale:
+        sr = PlaneUpsampler(channels, sr_scale).to(device).eval()
+        for d in range(3):
+            n = get_plane_name(stored_sid, d)
+            sr.set_LR_plane(planes[n].detach(), n)
+        fine.assign_SR_model(sr)
+    return coarse, fine, sid
+
+
+def make_mip_models(seed=0, device="cpu", density_gain=40.0, density_shift=-2.0):
+    torch.manual_seed(seed)
+    coarse, fine = MipMLP(), MipMLP()
+    for m in (coarse, fine):
+        shape_density(m, density_gain, density_shift)
+        m.eval().to(device)
+    return coarse, fine
+
+
+def blender_camera(width, theta=30.0, phi=-30.0, radius=4.0, camera_angle_x=0.6911112070083618):
+    """pose_spherical (load_blender.py:34-39) + focal from camera_angle_x (load_blender.py:257-258,288)."""
+    def rx(p):
+        return np.array([[1, 0, 0, 0], [0, np.cos(p), -np.sin(p), 0], [0, np.sin(p), np.cos(p), 0], [0, 0, 0, 1]], np.float32)
+
+    def ry(t):
+        return np.array([[np.cos(t), 0, -np.sin(t), 0], [0, 1, 0, 0], [np.sin(t), 0, np.cos(t), 0], [0, 0, 0, 1]], np.float32)
+
+    tz = np.eye(4, dtype=np.float32)
+    tz[2, 3] = radius
+    c2w = ry(theta / 180.0 * np.pi) @ (rx(phi / 180.0 * np.pi) @ tz)
+    c2w = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ c2w
+    focal = 0.5 * width / np.tan(0.5 * camera_angle_x)
+    return torch.from_numpy(c2w).float(), float(focal)
+
+
+# --------------------------------------------------------------------------------------------------
+# packers
+class _Cache:
+    """Keyed on tensor identity + in-place version: re-pack only when a plane / weight changed."""
+
+    def __init__(self):
+        self.store = {}
+
+    @staticmethod
+    def key_of(t):
+        return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+
+    def get(self, key, make):
+        hit = self.store.get(key[0])
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        val = make()
+        self.store[key[0]] = (key, val)
+        return val
+
+
+_plane_cache = _Cache()
+_decoder_cache = _Cache()
+
+
+def clear_caches():
+    _plane_cache.store.clear()
+    _decoder_cache.store.clear()
+
+
+def _should_sr(model, d):
+    """models.py:296-300"""
+    name = get_plane_name(model.cur_id, d)
+    sr = hasattr(model, "SR_model") and (not hasattr(model, "scene_coupler") or
+                                         model.scene_coupler.should_SR(name, plane_not_scene=True))
+    return bool(sr and not getattr(model, "skip_SR_", False))
+
+
+def _source_plane(model, d):
+    """The NCHW plane tensor `model` reads for dimension d of the current scene, with a STABLE identity.
+
+    PlanesSR caches its output on the CPU and re-uploads it on every call (models.py:893,925), so
+    `model.planes()` returns a fresh tensor each time; here the cached tensor itself is used as the
+    cache key, making the SR plane device-resident after the first frame."""
+    sr = d < 3 and _should_sr(model, d)
+    if sr and hasattr(model.SR_model, "SR_planes"):
+        name = model.scene_coupler.scene_with_saved_plane(get_plane_name(model.cur_id, d), plane_not_scene=True)
+        if name not in model.SR_model.SR_planes:
+            model.planes(d, super_resolve=True)  # stock-PyTorch SR inference, once per plane
+        if name in model.SR_model.SR_planes:
+            return model.SR_model.SR_planes[name]
+    return model.planes(d, super_resolve=sr)
+
+
+def check_supported_planes_model(model):
+    """Engagement rule: unsupported configurations raise — there is no fallback."""
+    bad = []
+    if getattr(model, "num_density_planes", 3) != 3:
+        bad.append("num_density_planes != 3")
+    if getattr(model, "plane_interp", "bilinear") != "bilinear" or not getattr(model, "align_corners", True):
+        bad.append("plane_interp/align_corners")
+    if getattr(model, "proj_combination", "avg") != "avg":
+        bad.append("proj_combination != 'avg'")
+    if getattr(model, "viewdir_proj_combination", "concat_pos") != "concat_pos":
+        bad.append("viewdir_proj_combination != 'concat_pos'")
+    if getattr(model, "rgb_dec_input", "projections") != "projections" or not getattr(model, "use_viewdirs", True):
+        bad.append("rgb_dec_input/use_viewdirs")
+    s = getattr(model, "skip_connect_every", None)
+    n_layers = max(len(model.density_dec["0"]), len(model.rgb_dec["0"]))
+    if s is not None and any(((i - 1) % s == 0 and (i - 1) > 0) for i in range(n_layers)):
+        bad.append("a skip connection fires")
+    if len(model.density_dec) != 1:
+        bad.append("ensemble_size != 1")
+    if getattr(model, "point_coords_noise", 0) and model.training:
+        bad.append("point_coords_noise in training mode")
+    if bad:
+        raise NotImplementedError("nvsr_b200: unsupported TwoDimPlanesModel configuration: " + ", ".join(bad))
+
+
+def pack_scene_planes(model, scene_id, dtype):
+    """Channels-last device planes for `scene_id` as `model` would read them (models.py:270-310)."""
+    model.set_cur_scene_id(scene_id)
+    packed = []
+    for d in range(3):
+        src = _source_plane(model, d)
+        key = _Cache.key_of(src) + (dtype,)
+        packed.append(_plane_cache.get(key, lambda s=src: ops.pack_plane(s.cuda(), dtype)))
+    vsrc = _source_plane(model, 3)
+    vkey = _Cache.key_of(vsrc) + (NVSR_F32,)
+    vplane = _plane_cache.get(vkey, lambda: ops.pack_plane(vsrc.cuda(), NVSR_F32))
+    box = model.box_coords[scene_id].detach().double().cpu()
+    lo = box[0].float()                  # .type(coords.type()) of the fp64 box (models.py:264)
+    rng = (box[1] - box[0]).float()      # difference in fp64, then cast (models.py:265)
+    rots = model.coord_projector.rot_mats_NON_LEARNED
+    proj = [rots[d].detach().float().cpu()[:, 1:].tolist() for d in range(3)]
+    return ops.PackedPlanes(packed, dtype, lo[:3].tolist(), rng[:3].tolist(), proj, vplane,
+                            (float(lo[3]), float(rng[3]), float(lo[4]), float(rng[4])))
+
+
+class PackedPlanesDecoder:
+    """Decoder chains of one TwoDimPlanesModel instance, in fp32 (SIMT) or bf16 (tcgen05) form."""
+
+    def __init__(self, model, precision):
+        dd, rd = list(model.density_dec["0"]), list(model.rgb_dec["0"])
+        fa, fr = model.fc_alpha["0"], model.fc_rgb["0"]
+        c = model.num_plane_channels
+        self.precision = precision
+        self.view_w = rd[0].weight.detach()[:, 3 * c:]      # per-ray columns of rgb_dec[0] (models.py:186)
+        self.view_b = rd[0].bias.detach().float().contiguous()
+
+        def wpack(w):
+            w = w.detach().float()
+            return ops.pack_weight_bf16(w) if precision == NVSR_BF16 else w.contiguous()
+
+        def f(t):
+            return t.detach().float().contiguous()
+
+        self.density = []
+        for i, lin in enumerate(dd):
+            last = i == len(dd) - 1
+            self.density.append(ops.ChainLayer(wpack(lin.weight), f(lin.bias), lin.in_features, lin.out_features, True,
+                                               head_w=f(fa.weight) if last else None,
+                                               head_b=f(fa.bias) if last else None, head_ch=3))
+        self.rgb = []
+        for i, lin in enumerate(rd):
+            last = i == len(rd) - 1
+            w = lin.weight.detach()[:, :3 * c] if i == 0 else lin.weight
+            self.rgb.append(ops.ChainLayer(wpack(w), None if i == 0 else f(lin.bias), w.shape[1], lin.out_features, True,
+                                           head_w=f(fr.weight) if last else None,
+                                           head_b=f(fr.bias) if last else None, head_ch=0))
+
+    def rgb_chain(self, row_bias):
+        first = self.rgb[0]
+        l0 = ops.ChainLayer(first.w, None, first.k, first.n_out, True, row_bias=row_bias,
+                            head_w=first.head_w, head_b=first.head_b, head_ch=first.head_ch)
+        return [l0] + self.rgb[1:]
+
+
+def pack_planes_decoder(model, precision):
+    params = list(model.density_dec["0"].parameters()) + list(model.rgb_dec["0"].parameters()) + \
+        list(model.fc_alpha["0"].parameters()) + list(model.fc_rgb["0"].parameters())
+    key = (id(model), tuple((p.data_ptr(), p._version) for p in params), precision)
+    return _decoder_cache.get(key, lambda: PackedPlanesDecoder(model, precision))
+
+
+class PackedMipDecoder:
+    """FlexibleNeRFModel chain (models.py:85-108): layer1 (no ReLU) -> 3x(128,ReLU) -> [fc_alpha tap]
+    -> fc_feat (ReLU) -> layers_dir[0] (per-ray view bias, ReLU) -> fc_rgb head."""
+
+    def __init__(self, model, precision):
+        if not model.use_viewdirs or getattr(model, "xyz_input_2_dir", False) or len(model.layers_dir) != 1:
+            raise NotImplementedError("nvsr_b200: unsupported FlexibleNeRFModel configuration")
+        n_xyz = len(model.layers_xyz)
+        if any(i % model.skip_connect_every == 0 and i > 0 and i != n_xyz for i in range(n_xyz)):
+            raise NotImplementedError("nvsr_b200: FlexibleNeRFModel with a firing skip connection")
+        self.precision = precision
+        self.dim_xyz = model.dim_xyz
+        self.k0 = (model.dim_xyz + 15) // 16 * 16 if precision == NVSR_BF16 else model.dim_xyz
+
+        def wpack(w, k_pad=None):
+            w = w.detach().float()
+            if precision == NVSR_BF16:
+                return ops.pack_weight_bf16(w, k_pad)
+            if k_pad is not None and k_pad != w.shape[1]:
+                w = torch.cat([w, w.new_zeros(w.shape[0], k_pad - w.shape[1])], 1)
+            return w.contiguous()
+
+        def f(t):
+            return t.detach().float().contiguous()
+
+        hid = model.layer1.out_features
+        L = [ops.ChainLayer(wpack(model.layer1.weight, self.k0), f(model.layer1.bias), self.k0, hid, False)]
+        for i, lin in enumerate(model.layers_xyz):
+            last = i == n_xyz - 1
+            L.append(ops.ChainLayer(wpack(lin.weight), f(lin.bias), lin.in_features, lin.out_features, True,
+                                    head_w=f(model.fc_alpha.weight) if last else None,
+                                    head_b=f(model.fc_alpha.bias) if last else None, head_ch=3))
+        L.append(ops.ChainLayer(wpack(model.fc_feat.weight), f(model.fc_feat.bias), hid, hid, True))
+        dl = model.layers_dir[0]
+        self.dir_w = dl.weight.detach()[:, hid:]
+        self.dir_b = f(dl.bias)
+        self.dir_layer = ops.ChainLayer(wpack(dl.weight.detach()[:, :hid]), None, hid, dl.out_features, True,
+                                        head_w=f(model.fc_rgb.weight), head_b=f(model.fc_rgb.bias), head_ch=0)
+        self.front = L
+
+    def chain(self, row_bias):
+        d = self.dir_layer
+        return self.front + [ops.ChainLayer(d.w, None, d.k, d.n_out, True, row_bias=row_bias, head_w=d.head_w,
+                                            head_b=d.head_b, head_ch=0)]
+
+
+def pack_mip_decoder(model, precision):
+    params = list(model.parameters())
+    key = (id(model), tuple((p.data_ptr(), p._version) for p in params), precision)
+    return _decoder_cache.get(key, lambda: PackedMipDecoder(model, precision))
