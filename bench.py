@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — rays/s & samples/s of the 800x800 render (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one full frame of BASELINE config 2: synthetic Blender-shaped scene (random-init tri-planes
+200^2 x 48 ch + 32^2 view plane, shared 4+4-layer x128 decoder pair), 800x800 rays, 64 coarse + 128
+fine samples (hierarchical sample_pdf) -> rgb/disp/acc, coarse and fine.
+  value : whole-job rays/s, rays resident in HBM, timed on the device (CUDA events), max over ranks
+  e2e   : same metric through run_one_iter_of_nerf with HOST ray buffers: H2D of the rays and D2H of
+          the six result maps inside the timed region
+  N > 1 : the frame's rows are split into N contiguous bands (ray order preserved), one rank per GPU,
+          one NCCL all_gather of the result tiles per frame (inside the timed region)
+  --impl reference : the reference algorithm's CPU path (oracle port, all host threads) on a bounded
+          ray sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = 800
+NC, NF = 64, 128
+PLANE_RES = 200
+EVALS_PER_RAY = NC + (NC + NF)          # decoder evaluations per ray (coarse net + fine net on merged set)
+FLOP_PER_EVAL = 259072                  # true MACs x 2, planes decoder
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(device):
+    import nvsr_b200
+    from nvsr_b200 import scene
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=PLANE_RES, view_res=32, seed=0, device=device)
+    pose, focal = scene.blender_camera(RES)
+    return mc, mf, sid, pose, focal, scene.render_options(NC, NF), scene.scene_cfg(2.0, 6.0, True)
+
+
+def cpu_sample_rays(pose, focal, n_side):
+    """a bounded sample of the SAME workload: an n_side x n_side lattice of the 800x800 frame's rays"""
+    from oracle import nvsr_oracle as O
+    ro, rd = O.get_ray_bundle(RES, RES, focal, pose)
+    idx = torch.linspace(0, RES - 1, n_side).round().long()
+    ro, rd = ro[idx][:, idx], rd[idx][:, idx]
+    return torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+
+
+def time_cpu_oracle(n_side, steps, warmup):
+    """the reference algorithm's CPU path (oracle port, torch CPU ops on all host threads)"""
+    from oracle import nvsr_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    mc, mf, sid, pose, focal, opt, scfg = build_scene("cpu")
+    batch = cpu_sample_rays(pose, focal, n_side)
+    n = batch.shape[1]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.run_one_iter_of_nerf(RES, RES, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return dict(rays_per_s=n * len(times) / total, ms_per_step=1e3 * total / len(times), rays=n,
+                cores=torch.get_num_threads(),
+                sample=f"{n_side}x{n_side} lattice of the 800x800 frame's rays ({n} rays, 64+128 samples, planes 200^2), "
+                       f"{len(times)} timed passes after {warmup} warm-up")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = time_cpu_oracle(n_side=48, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "rays/s (800x800 render, 64 coarse + 128 fine samples/ray)", "value": r["rays_per_s"],
+        "unit": "rays/s", "samples_per_s": r["rays_per_s"] * EVALS_PER_RAY, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2_800x800_64+128_planes200 (bounded ray sample per step)", "rays_per_step": r["rays"]},
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ray-chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import nvsr_b200
+    from nvsr_b200 import ops
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    nvsr_b200.set_precision(args.precision)
+    if args.ray_chunk:
+        nvsr_b200.set_ray_chunk(args.ray_chunk)
+    mc, mf, sid, pose, focal, opt, scfg = build_scene(dev)
+    pose = pose.to(dev)
+
+    # row-band sharding: rank r renders rows [r0, r1)
+    rows_per = (RES + world - 1) // world
+    r0, r1 = min(RES, rank * rows_per), min(RES, (rank + 1) * rows_per)
+    n_local = (r1 - r0) * RES
+    tile = torch.zeros((rows_per * RES, 10), device=dev)          # rgb_c,disp_c,acc_c,rgb_f,disp_f,acc_f
+    gathered = torch.zeros((world * rows_per * RES, 10), device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def pack_outputs(out):
+        tile[:n_local, 0:3], tile[:n_local, 3], tile[:n_local, 4] = out[0], out[1], out[2]
+        tile[:n_local, 5:8], tile[:n_local, 8], tile[:n_local, 9] = out[3], out[4], out[5]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, tile)   # the one collective per frame (NVLink)
+            return gathered
+        return tile
+
+    def frame_device():
+        """rays generated on the device (get_ray_bundle kernel), everything resident"""
+        flush.zero_()
+        out = nvsr_b200.render_frame(RES, RES, focal, pose, mc, mf, opt, sid, scfg, row_range=(r0, r1))
+        return pack_outputs(out)
+
+    # host buffers for the e2e leg (the call a user of the reference makes: rays in, maps out)
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(RES, RES, focal, pose, row_range=(r0, r1))
+    host_rays = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0).cpu().pin_memory()
+    host_out = torch.empty((rows_per * RES, 10), dtype=torch.float32).pin_memory()
+
+    def frame_e2e():
+        flush.zero_()
+        batch = host_rays.to(dev, non_blocking=True)
+        out = nvsr_b200.run_one_iter_of_nerf(RES, RES, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
+        res = pack_outputs(out)
+        host_out.copy_(res[rank * rows_per * RES:(rank + 1) * rows_per * RES] if world > 1 else res, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            frame_device()
+        clocks = ClockSampler(local)
+        clocks.start()
+        ops.LAUNCHES.clear()
+        ms_dev = timed(frame_device, args.steps)
+        launches = sum(ops.LAUNCHES.values())
+        clk = clocks.stop()
+        for _ in range(2):
+            frame_e2e()
+        ms_e2e = timed(frame_e2e, args.steps)
+
+        # per-kernel live timing (CUDA events around every launch of ours, same stream) for the roofline
+        ops.PROFILE = []
+        barrier()
+        for _ in range(min(3, args.steps)):
+            frame_device()
+        barrier()
+        prof, ops.PROFILE = ops.PROFILE, None
+    agg = {}
+    for name, a, b, meta in prof:
+        key = name
+        if name == "nvsr_mlp_chain":
+            key = "mlp_density" if meta["flops"] / max(meta["rows"], 1) < 150000 else "mlp_rgb"
+        d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=0, flops=0))
+        d["ms"] += a.elapsed_time(b)
+        d["n"] += 1
+        d["bytes"] += meta.get("bytes", 0)
+        d["flops"] += meta.get("flops", 0)
+    pk = peaks()
+    total_ms = sum(d["ms"] for d in agg.values())
+    kernels = {}
+    for k, d in agg.items():
+        e = {"launches": d["n"], "avg_ms": d["ms"] / d["n"], "share": d["ms"] / total_ms}
+        if d["flops"]:
+            e["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            e["frac_tensor_peak"] = e["tflops"] / pk["tf_sust"]
+        if d["bytes"]:
+            e["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            e["frac_hbm_peak"] = e["gbs"] / pk["hbm"]
+        kernels[k] = e
+    mlp = [agg[k] for k in ("mlp_rgb", "mlp_density") if k in agg]
+    mlp_ms = sum(d["ms"] for d in mlp)
+    mlp_fl = sum(d["flops"] for d in mlp)
+    mlp_n = sum(d["n"] for d in mlp)
+    roofline = None
+    if mlp_ms > 0 and args.precision == "bf16":
+        ach = mlp_fl / (mlp_ms * 1e-3) / 1e12
+        roofline = {"kernel": "mlp_chain_tc_kernel (decoder, tcgen05)", "bound": "tensor", "achieved": ach,
+                    "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
+                    "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                    "avg_launch_ms": mlp_ms / mlp_n, "flop_per_launch": mlp_fl / mlp_n, "share_of_step": mlp_ms / total_ms}
+    elif mlp_ms > 0:
+        ach = mlp_fl / (mlp_ms * 1e-3) / 1e12
+        roofline = {"kernel": "mlp_chain_f32_kernel (decoder, SIMT fp32 parity mode)", "bound": "tensor", "achieved": ach,
+                    "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
+                    "peak_source": pk["src"], "share_of_step": mlp_ms / total_ms}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            r = time_cpu_oracle(n_side=64, steps=2, warmup=1)
+            cpu = {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        rays = RES * RES
+        line = {
+            "metric": "rays/s (800x800 render, 64 coarse + 128 fine samples/ray)",
+            "value": rays / (ms_dev * 1e-3), "unit": "rays/s",
+            "samples_per_s": rays * EVALS_PER_RAY / (ms_dev * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "cfg2_800x800_64+128_planes200", "rays_per_step": rays, "planes": "3x48x200^2 + 48x32^2",
+                       "decoder": "48->128x4->1 + 192->128x4->3 (coarse+fine)", "sharding": f"{world} row bands",
+                       "ray_chunk": nvsr_b200.render._state["ray_chunk"],
+                       "l2": "256 MiB buffer rewritten before every step; per-step intermediates (>60 GB) exceed L2"},
+            "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(host_rays.numel() * 4), "d2h_bytes_per_step": int(n_local * 10 * 4)},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,25 @@ def _require_cuda(t, name):
         raise _lib.NvsrError(f"{name} must be a CUDA tensor: nvsr_b200 has no CPU path")
 
 
+# Launch accounting: every C-ABI call below launches exactly one kernel of ours.  `LAUNCHES` counts
+# them (bench.py reports it as gpu_launches); when `PROFILE` is a list, each call is bracketed by CUDA
+# events on the launching stream and appended as (name, start, end, meta) for the roofline numbers.
+LAUNCHES = {}
+PROFILE = None
+
+
+def _call(name, fn, *args, **meta):
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
+    if PROFILE is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = fn(*args)
+    e1.record()
+    PROFILE.append((name, e0, e1, meta))
+    return st
+
+
 # ---------------------------------------------------------------------------------------------
 # a1  get_ray_bundle
 def get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size=0, downsampling_offset=0,
@@ -63,7 +82,7 @@ def get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size=0,
     ro = torch.empty((r1 - r0, wp, 3), dtype=torch.float32, device=dev)
     rd = torch.empty_like(ro)
     with torch.cuda.device(dev):
-        st = lib.nvsr_ray_bundle(height, width, fx, fy, c2w_arr, padding_size, float(downsampling_offset), r0, r1,
+        st = _call("nvsr_ray_bundle", lib.nvsr_ray_bundle, height, width, fx, fy, c2w_arr, padding_size, float(downsampling_offset), r0, r1,
                                  _ptr(ro), _ptr(rd), _stream())
     _lib.check(st, "nvsr_ray_bundle")
     return ro, rd
@@ -84,7 +103,7 @@ def prepare_rays(ray_origins, ray_directions, use_ndc=False, height=0, width=0, 
     if isinstance(focal, (list, tuple)):
         raise _lib.NvsrError("ndc_rays needs a scalar focal (as in the reference)")
     with torch.cuda.device(ro.device):
-        st = lib.nvsr_prepare_rays(_ptr(ro), _ptr(rd), n, int(bool(use_ndc)), int(height), int(width), float(focal),
+        st = _call("nvsr_prepare_rays", lib.nvsr_prepare_rays, _ptr(ro), _ptr(rd), n, int(bool(use_ndc)), int(height), int(width), float(focal),
                                    float(ndc_near), _ptr(ro_o), _ptr(rd_o), _ptr(vd), _stream())
     _lib.check(st, "nvsr_prepare_rays")
     return ro_o, rd_o, vd
@@ -102,7 +121,7 @@ def pack_plane(plane_nchw, dtype=NVSR_F32):
     c, rh, rw = p.shape
     out = torch.empty((rh, rw, c), dtype=torch.float32 if dtype == NVSR_F32 else torch.bfloat16, device=p.device)
     with torch.cuda.device(p.device):
-        st = lib.nvsr_pack_plane(_ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
+        st = _call("nvsr_pack_plane", lib.nvsr_pack_plane, _ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
     _lib.check(st, "nvsr_pack_plane")
     return out
 
@@ -120,7 +139,7 @@ def pack_weight_bf16(weight, k_pad=None):
         k_pad = (k + 15) // 16 * 16
     out = torch.empty((k_pad // 8, n_out, 8), dtype=torch.bfloat16, device=w.device)
     with torch.cuda.device(w.device):
-        st = lib.nvsr_pack_weight_bf16(_ptr(w), n_out, k, ldw, k_pad, _ptr(out), _stream())
+        st = _call("nvsr_pack_weight_bf16", lib.nvsr_pack_weight_bf16, _ptr(w), n_out, k, ldw, k_pad, _ptr(out), _stream())
     _lib.check(st, "nvsr_pack_weight_bf16")
     return out
 
@@ -190,7 +209,10 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
     s.z_in = 0 if z_in is None else z_in.data_ptr()
     pl = packed.cstruct()
     with torch.cuda.device(ro.device):
-        st = lib.nvsr_sample_gather(C.byref(s), C.byref(pl), layout, _ptr(feat_p), _ptr(feat_m), _ptr(z_out), _stream())
+        st = _call("nvsr_sample_gather", lib.nvsr_sample_gather, C.byref(s), C.byref(pl), layout, _ptr(feat_p),
+                   _ptr(feat_m), _ptr(z_out), _stream(),
+                   # algorithmic HBM bytes: feature write 4C*e per row + z (4 B) + rays (24 B/ray)
+                   bytes=rows * (4 * packed.channels * (2 if layout == FEAT_TILE_BF16 else 4) + 4) + n * 24, rows=rows)
     _lib.check(st, "nvsr_sample_gather")
     return feat_p, feat_m, (z_out if z_in is None else z_in)
 
@@ -204,7 +226,7 @@ def viewdir_gather(viewdirs, packed):
     out = torch.empty((n, vp.shape[-1]), dtype=torch.float32, device=vd.device)
     az_lo, az_rng, el_lo, el_rng = packed.view_lo_rng
     with torch.cuda.device(vd.device):
-        st = lib.nvsr_viewdir_gather(_ptr(vd), n, _ptr(vp), vp.shape[0], vp.shape[1], vp.shape[2], az_lo, az_rng,
+        st = _call("nvsr_viewdir_gather", lib.nvsr_viewdir_gather, _ptr(vd), n, _ptr(vp), vp.shape[0], vp.shape[1], vp.shape[2], az_lo, az_rng,
                                      el_lo, el_rng, _ptr(out), _stream())
     _lib.check(st, "nvsr_viewdir_gather")
     return out
@@ -223,7 +245,7 @@ def row_bias(vin, weight_cols, bias):
     b = None if bias is None else _f32c(bias.detach())
     out = torch.empty((n, n_out), dtype=torch.float32, device=vin.device)
     with torch.cuda.device(vin.device):
-        st = lib.nvsr_row_bias(_ptr(vin), n, k, _ptr(w), w.stride(0), _ptr(b), n_out, _ptr(out), _stream())
+        st = _call("nvsr_row_bias", lib.nvsr_row_bias, _ptr(vin), n, k, _ptr(w), w.stride(0), _ptr(b), n_out, _ptr(out), _stream())
     _lib.check(st, "nvsr_row_bias")
     return out
 
@@ -262,7 +284,12 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1):
     m.raw = raw.data_ptr()
     m.raw_stride = raw.stride(0)
     with torch.cuda.device(raw.device):
-        st = lib.nvsr_mlp_chain(C.byref(m), _stream())
+        st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows,
+                   # true MACs x2 only (no padding): layers + heads
+                   flops=2 * rows * sum(ly.k * ly.n_out + (0 if ly.head_w is None else ly.head_w.shape[0] * ly.n_out)
+                                        for ly in layers),
+                   bytes=rows * (layers[0].k * (2 if precision == NVSR_BF16 else 4) + 4 * sum(
+                       0 if ly.head_w is None else ly.head_w.shape[0] for ly in layers)))
     _lib.check(st, "nvsr_mlp_chain")
     return raw
 
@@ -311,7 +338,9 @@ def composite(raw, z, rd, n_samples, noise=None, white_background=False, mip=Fal
             out["z_samples"] = torch.empty((n, n_fine), dtype=torch.float32, device=dev)
             c.z_samples = out["z_samples"].data_ptr()
     with torch.cuda.device(dev):
-        st = lib.nvsr_composite(C.byref(c), _stream())
+        st = _call("nvsr_composite", lib.nvsr_composite, C.byref(c), _stream(), rows=n * n_samples,
+                   # per sample 16 B raw + 4 B z; per ray 12 B rd + 24 B out; coarse pass: merged depths written
+                   bytes=n * n_samples * 20 + n * 36 + (n * (n_samples + n_fine) * 4 if n_fine > 0 else 0))
     _lib.check(st, "nvsr_composite")
     return out
 
@@ -359,7 +388,7 @@ def sample_pdf(bins, weights, num_samples, det=False, u=None, cdf=None, return_a
     samples = torch.empty((n, num_samples), dtype=torch.float32, device=dev)
     cdf_out = torch.empty((n, nb), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        st = lib.nvsr_sample_pdf(_ptr(bins), _ptr(w), _ptr(cdf), n, nb, _ptr(u), int(u.dim() == 2), num_samples,
+        st = _call("nvsr_sample_pdf", lib.nvsr_sample_pdf, _ptr(bins), _ptr(w), _ptr(cdf), n, nb, _ptr(u), int(u.dim() == 2), num_samples,
                                  _ptr(inds), _ptr(samples), _ptr(cdf_out), _stream())
     _lib.check(st, "nvsr_sample_pdf")
     if return_all:
@@ -383,7 +412,7 @@ def ipe(z_edges, ro, rd, radius, n_freqs, layout=FEAT_ROWMAJOR_F32, k_pad=None):
         tiles = (n * S + TILE_ROWS - 1) // TILE_ROWS
         out = torch.empty((tiles, k_pad // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev):
-        st = lib.nvsr_ipe(_ptr(z), _ptr(_f32c(ro)), _ptr(_f32c(rd)), n, S, float(radius), n_freqs, layout, k_pad,
+        st = _call("nvsr_ipe", lib.nvsr_ipe, _ptr(z), _ptr(_f32c(ro)), _ptr(_f32c(rd)), n, S, float(radius), n_freqs, layout, k_pad,
                           _ptr(out), _stream())
     _lib.check(st, "nvsr_ipe")
     return out
@@ -396,7 +425,7 @@ def dir_encoding(dirs, n_freqs, include_input=True):
     n = d.shape[0]
     out = torch.empty((n, (3 if include_input else 0) + 6 * n_freqs), dtype=torch.float32, device=d.device)
     with torch.cuda.device(d.device):
-        st = lib.nvsr_dir_encoding(_ptr(d), n, n_freqs, int(bool(include_input)), _ptr(out), _stream())
+        st = _call("nvsr_dir_encoding", lib.nvsr_dir_encoding, _ptr(d), n, n_freqs, int(bool(include_input)), _ptr(out), _stream())
     _lib.check(st, "nvsr_dir_encoding")
     return out
 

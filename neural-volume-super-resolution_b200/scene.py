@@ -187,18 +187,33 @@ class MipMLP(nn.Module):
 DEFAULT_BOX = [[-1.5, -1.5, -1.5, -math.pi, -math.pi / 2], [1.5, 1.5, 1.5, math.pi, math.pi / 2]]
 
 
-def shape_density(model, gain, shift):
+def shape_density(model, target_std=15.0, shift=-12.0, feat_std=0.5, n_draws=4096, seed=1234):
     """Random-init decoders give degenerate volumes (coarse acc == 1, fine sigma == 0).
-    Rescale the density head so that sigma is positive on a minority of samples with O(10) values."""
-    heads = [model.fc_alpha["0"]] if isinstance(model.fc_alpha, nn.ModuleDict) else [model.fc_alpha]
+    Standardise the density head on synthetic decoder inputs so that raw sigma ~ N(shift, target_std^2):
+    positive on a minority of samples, with O(10) values.  Only the head's weight/bias are rescaled
+    (weight initialisation, not part of the render path)."""
+    g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
-        for h in heads:
-            h.weight.mul_(gain)
-            h.bias.fill_(shift)
+        if isinstance(model.fc_alpha, nn.ModuleDict):       # tri-plane decoder: input = mean of 3 bilinear samples
+            head = model.fc_alpha["0"]
+            c = model.num_plane_channels
+            h = torch.randn(n_draws, c, generator=g) * (feat_std * (4.0 / 9.0 / 3.0) ** 0.5)
+            for lin in model.density_dec["0"]:
+                h = torch.relu(lin(h))
+        else:                                               # mip MLP: input = IPE features in [-1,1]
+            head = model.fc_alpha
+            h = model.layer1(torch.sin(torch.rand(n_draws, model.dim_xyz, generator=g) * 6.2831853))
+            for lin in model.layers_xyz:
+                h = torch.relu(lin(h))
+        y = head(h).squeeze(-1)
+        mu, sd = float(y.mean()), float(y.std())
+        a = target_std / max(sd, 1e-8)
+        head.weight.mul_(a)
+        head.bias.copy_(a * (head.bias - mu) + shift)
 
 
 def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device="cpu", scene_id=None,
-                         plane_std=0.5, density_gain=120.0, density_shift=-4.0, sr_scale=None):
+                         plane_std=0.5, density_std=10.0, density_shift=-10.0, sr_scale=None):
     """Synthetic Blender-shaped scene: seeded coarse+fine decoders, then planes.
 
     With `sr_scale`, planes are stored at plane_res under an LR id, and the FINE model reads
@@ -220,12 +235,15 @@ def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device
     planes = nn.ParameterDict()
     for d in range(4):
         r = plane_res if d < 3 else view_res
-        planes[get_plane_name(stored_sid, d)] = nn.Parameter(plane_std * torch.randn(1, channels, r, r))
+        # smooth blobs + texel noise: spatially coherent density (some rays empty, some opaque)
+        low = nn.functional.interpolate(torch.randn(1, channels, max(r // 8, 2), max(r // 8, 2)), size=(r, r),
+                                        mode="bicubic", align_corners=True)
+        planes[get_plane_name(stored_sid, d)] = nn.Parameter(plane_std * (0.9 * low + 0.45 * torch.randn(1, channels, r, r)))
     box = torch.tensor(DEFAULT_BOX, dtype=torch.float64)
     for m in (coarse, fine):
         m.planes_ = planes
         m.box_coords = {sid: box, stored_sid: box}
-        shape_density(m, density_gain, density_shift)
+        shape_density(m, density_std, density_shift, plane_std)
         m.eval()
     coarse.to(device)
     fine.to(device)
@@ -238,11 +256,11 @@ def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device
     return coarse, fine, sid
 
 
-def make_mip_models(seed=0, device="cpu", density_gain=40.0, density_shift=-2.0):
+def make_mip_models(seed=0, device="cpu", density_std=10.0, density_shift=-10.0):
     torch.manual_seed(seed)
     coarse, fine = MipMLP(), MipMLP()
     for m in (coarse, fine):
-        shape_density(m, density_gain, density_shift)
+        shape_density(m, density_std, density_shift)
         m.eval().to(device)
     return coarse, fine
 

@@ -54,11 +54,22 @@ def pose_spherical(theta, phi, radius):  # load_blender.py:34-39 restated (load_
     return np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ c2w
 
 
-def shape_density(m, gain, shift):
+def shape_density(m, x, target_std=10.0, shift=-8.0):
+    """Standardise the density head on the model's own outputs at inputs `x` so that the volume is
+    not degenerate: raw sigma ~ N(shift, target_std^2)."""
     with torch.no_grad():
-        heads = [m.fc_alpha["0"]] if isinstance(m.fc_alpha, torch.nn.ModuleDict) else [m.fc_alpha]
-        for h in heads:
-            h.weight.mul_(gain); h.bias.fill_(shift)
+        y = m(x)[..., 3]
+        a = target_std / float(y.std())
+        head = m.fc_alpha["0"] if isinstance(m.fc_alpha, torch.nn.ModuleDict) else m.fc_alpha
+        head.weight.mul_(a)
+        head.bias.copy_(a * (head.bias - float(y.mean())) + shift)
+
+
+def random_points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(n, 3, generator=g) * 3.0 - 1.5
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    return torch.cat([pts, dirs], -1)
 
 
 def build_planes_models(sid, res, vres, seed, lr_sid=None, lr_res=None):
@@ -76,8 +87,11 @@ def build_planes_models(sid, res, vres, seed, lr_sid=None, lr_res=None):
     for m in (mc, mf):
         m.planes_, m.plane_rank, m.generated_planes, m.downsampled_planes, m.coverages = planes, None, {}, {}, {}
         m.box_coords = {i: box for i in ids}
-        shape_density(m, 120.0, -4.0)
         m.eval()
+    if lr_sid is None:
+        for m in (mc, mf):
+            m.set_cur_scene_id(sid)
+            shape_density(m, random_points(4096, 99))
     return mc, mf, coupler
 
 
@@ -252,15 +266,16 @@ def main():
 
     # ------------------------------------------------------------------ mip / IPE + FlexibleNeRFModel
     torch.manual_seed(1)
+    pe = lambda x: nerf_helpers.positional_encoding(x, 4, True)
     fc = models.FlexibleNeRFModel(num_encoding_fn_xyz=6, num_encoding_fn_dir=4, include_input_xyz=False,
                                   include_input_dir=True, use_viewdirs=True)
     ff = models.FlexibleNeRFModel(num_encoding_fn_xyz=6, num_encoding_fn_dir=4, include_input_xyz=False,
                                   include_input_dir=True, use_viewdirs=True)
     for m in (fc, ff):
-        shape_density(m, 40.0, -2.0); m.eval()
+        m.eval()
+        shape_density(m, torch.cat([torch.sin(torch.rand(4096, 36) * 6.2831853), pe(random_points(4096, 98)[:, 3:])], -1))
     fc.optional_no_grad = nerf_helpers.null_with
     enc = mip.IntegratedPositionalEncoding(3, multires=7)
-    pe = lambda x: nerf_helpers.positional_encoding(x, 4, True)
     save_scene("scene_mip_small.npz", fc, ff, None)
     e2e_case("e2e_mip_det.npz", fc, ff, "lego_DS2", "scene_mip_small.npz", options(16, 24, mip_enc=True), scfg, H, W, focal,
              pose, enc=enc, encd=pe)
@@ -284,6 +299,10 @@ def main():
                          sr_config=CfgNode({"model": {"hidden_size": 16, "n_blocks": 2}}), plane_interp="bilinear").eval()
     mf2.assign_SR_model(sr, SR_viewdir=False)
     mf2.assign_LR_planes()
+    for m in (mc2, mf2):   # calibrate after the SR model is attached: the fine model reads SR planes
+        m.set_cur_scene_id(hr)
+        shape_density(m, random_points(4096, 97))
+    sr.clear_SR_planes()
     with torch.no_grad():
         e2e_case("e2e_planes_sr.npz", mc2, mf2, hr, "scene_planes_sr.npz", options(16, 24), scfg, H, W, focal, pose,
                  offset=(2 - 1) / (2 * 2), extra={"lr_scene_id": np.array(lr)})

@@ -1,0 +1,235 @@
+"""GPU parity, stage by stage: the CUDA path (through the C-ABI) against golden vectors produced by
+the reference and against the CPU oracle on seeded inputs.
+
+Tolerances (stated, per BASELINE.json north_star):
+  fp32 mode  : rgb/depth/acc/weights within 1e-3 abs of the reference (observed ~1e-6);
+  bf16 mode  : decoder outputs carry bf16 rounding of features/activations: stated in BF16_*.
+  integer/index work (searchsorted indices, ray order): bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import T, golden
+from oracle import nvsr_oracle as O
+
+import nvsr_b200
+from nvsr_b200 import NVSR_BF16, NVSR_F32, ops, scene
+from nvsr_b200._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF16_RAW_ATOL, BF16_RAW_RTOL = 0.35, 0.05   # raw decoder outputs (pre-sigmoid, |raw| up to ~1e2)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_get_ray_bundle_golden(tag):
+    g = golden(f"stage_raybundle_{tag}.npz")
+    ro, rd = nvsr_b200.get_ray_bundle(int(g["H"]), int(g["W"]), g["focal"].tolist(), T(g["pose"], DEV), int(g["pad"]),
+                                      float(g["offset"]))
+    H.assert_close(ro, g["ro"], 0, what="ro")
+    H.assert_close(rd, g["rd"], 1e-6, what="rd")
+
+
+def test_get_ray_bundle_800_bands_and_order():
+    pose, focal = scene.blender_camera(800)
+    ro, rd = nvsr_b200.get_ray_bundle(800, 800, focal, pose.to(DEV))
+    ro_o, rd_o = O.get_ray_bundle(800, 800, focal, pose)
+    H.assert_close(rd, rd_o, 1e-6, what="rd 800")
+    frac_exact = float((rd.cpu() == rd_o).float().mean())
+    assert frac_exact > 0.99, frac_exact
+    bands = [nvsr_b200.get_ray_bundle(800, 800, focal, pose.to(DEV), row_range=(r, r + 100))[1] for r in range(0, 800, 100)]
+    assert torch.equal(torch.cat(bands, 0), rd)  # row-band sharding preserves ray order bit-exactly
+    assert ro.shape == (800, 800, 3) and torch.equal(ro[5, 7].cpu(), pose[:3, 3])
+
+
+def test_prepare_rays_ndc_golden():
+    g = golden("stage_ndc.npz")
+    ro, rd, vd = ops.prepare_rays(T(g["ro"], DEV), T(g["rd"], DEV), True, int(g["H"]), int(g["W"]), float(g["focal"]), 1.0)
+    H.assert_close(ro, g["ro_ndc"], 2e-6, 2e-6, what="ro_ndc")
+    H.assert_close(rd, g["rd_ndc"], 2e-6, 2e-6, what="rd_ndc")
+    ref = T(g["rd"]) / T(g["rd"]).norm(p=2, dim=-1).unsqueeze(-1)
+    H.assert_close(vd, ref, 2e-7, what="viewdirs")
+
+
+def _forward_points(model, sid, x6, precision):
+    """TwoDimPlanesModel.forward(x[n,6]) through the kernels: points as 1-sample rays (rd = 0)."""
+    model.set_cur_scene_id(sid)
+    packed = scene.pack_scene_planes(model, sid, precision)
+    dec = scene.pack_planes_decoder(model, precision)
+    n = x6.shape[0]
+    ro = x6[:, :3].contiguous()
+    rd = torch.zeros_like(ro)
+    layout = FEAT_TILE_BF16 if precision == NVSR_BF16 else FEAT_ROWMAJOR_F32
+    fp, fm, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, layout, z_in=torch.zeros(n, 1, device=DEV))
+    vfeat = ops.viewdir_gather(x6[:, 3:].contiguous(), packed)
+    rb = ops.row_bias(vfeat, dec.view_w, dec.view_b)
+    raw = torch.zeros(4, (n + 127) // 128 * 128, device=DEV)
+    ops.mlp_chain(fm, dec.density, n, raw, precision, 1, n)
+    ops.mlp_chain(fp, dec.rgb_chain(rb), n, raw, precision, 1, n)
+    return fp, fm, vfeat, raw[:, :n].t()
+
+
+def _untile(img, rows):
+    """[tiles, K/8, 128, 8] bf16 tile image -> [rows, K] fp32"""
+    t, kc, r, e = img.shape
+    return img.permute(0, 2, 1, 3).reshape(t * r, kc * e)[:rows].float()
+
+
+def test_planes_forward_fp32_golden():
+    g = golden("stage_planes_forward.npz")
+    sid = str(g["scene_id"])
+    mc, _ = H.load_planes_scene("scene_planes_small.npz", sid, DEV)
+    fp, fm, vfeat, out = _forward_points(mc, sid, T(g["x6"], DEV), NVSR_F32)
+    for d in range(3):
+        H.assert_close(fp[:, d * 48:(d + 1) * 48], g[f"pos{d}"], 2e-6, what=f"pos{d}")
+    mean = (T(g["pos0"]) + T(g["pos1"]) + T(g["pos2"])) / 3
+    H.assert_close(fm, mean, 2e-6, what="mean")
+    H.assert_close(vfeat, g["view"], 5e-6, what="view")
+    H.assert_close(out, g["out"], 1e-3, 1e-5, what="forward out")
+
+
+def test_planes_forward_bf16_golden():
+    g = golden("stage_planes_forward.npz")
+    sid = str(g["scene_id"])
+    mc, _ = H.load_planes_scene("scene_planes_small.npz", sid, DEV)
+    n = g["x6"].shape[0]
+    fp, fm, vfeat, out = _forward_points(mc, sid, T(g["x6"], DEV), NVSR_BF16)
+    feats = _untile(fp, n)
+    for d in range(3):
+        H.assert_close(feats[:, d * 48:(d + 1) * 48], g[f"pos{d}"], 2e-2, 1e-2, what=f"bf16 pos{d}")
+    err = (out.cpu() - T(g["out"])).abs()
+    print("bf16 forward: max abs err rgb %.4f sigma %.4f (|sigma| max %.1f)" % (
+        float(err[:, :3].max()), float(err[:, 3].max()), float(np.abs(g["out"][:, 3]).max())))
+    H.assert_close(out, g["out"], BF16_RAW_ATOL, BF16_RAW_RTOL, what="bf16 forward out")
+
+
+@pytest.mark.parametrize("precision", [NVSR_F32, NVSR_BF16])
+@pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40000])
+def test_mlp_chain_vs_torch(precision, rows):
+    """decoder chain kernels vs a plain fp32 torch evaluation of the same layers (ragged tile counts)"""
+    torch.manual_seed(rows)
+    k0, S = 144, 8
+    n_rays = (rows + S - 1) // S
+    lins = [torch.nn.Linear(k0, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 128)]
+    head = torch.nn.Linear(128, 3)
+    x = torch.randn(rows, k0)
+    rbias = torch.randn(n_rays, 128)
+    with torch.no_grad():
+        if precision == NVSR_BF16:
+            xq = x.bfloat16().float()
+            h = xq
+            for i, l in enumerate(lins):
+                w = l.weight.bfloat16().float()
+                b = rbias[torch.arange(rows) // S] if i == 0 else l.bias
+                h = torch.relu(h @ w.t() + b)
+                if i < 3:
+                    h = h.bfloat16().float()
+            ref = h @ head.weight.t() + head.bias
+        else:
+            h = x
+            for i, l in enumerate(lins):
+                b = rbias[torch.arange(rows) // S] if i == 0 else l.bias
+                h = torch.relu(h @ l.weight.t() + b)
+            ref = h @ head.weight.t() + head.bias
+    layers = []
+    for i, l in enumerate(lins):
+        w = l.weight.detach().to(DEV)
+        wp = ops.pack_weight_bf16(w) if precision == NVSR_BF16 else w.contiguous()
+        layers.append(ops.ChainLayer(wp, None if i == 0 else l.bias.detach().to(DEV), l.in_features, 128, True,
+                                     row_bias=rbias.to(DEV) if i == 0 else None,
+                                     head_w=head.weight.detach().to(DEV) if i == 3 else None,
+                                     head_b=head.bias.detach().to(DEV) if i == 3 else None, head_ch=0))
+    if precision == NVSR_BF16:
+        tiles = (rows + 127) // 128
+        xin = torch.zeros(tiles * 128, k0)
+        xin[:rows] = x
+        inp = xin.reshape(tiles, 128, k0 // 8, 8).permute(0, 2, 1, 3).contiguous().bfloat16().to(DEV)
+    else:
+        inp = x.to(DEV)
+    raw = torch.full((4, (rows + 127) // 128 * 128), float("nan"), device=DEV)
+    ops.mlp_chain(inp, layers, rows, raw, precision, S, n_rays)
+    torch.cuda.synchronize()
+    out = raw[:3, :rows].t()
+    tol = 2e-3 if precision == NVSR_BF16 else 2e-4   # same bf16-rounded operands: only accumulation order differs
+    H.assert_close(out, ref, tol, tol, what=f"mlp rows={rows}")
+    assert torch.isnan(raw[3]).all()  # untouched channel stays untouched
+
+
+@pytest.mark.parametrize("tag,kw", [("plain", {}), ("white", dict(white_background=True)), ("mip", dict(mip_nerf=True))])
+def test_volume_render_golden(tag, kw):
+    g = golden(f"stage_composite_{tag}.npz")
+    o = nvsr_b200.volume_render_radiance_field(T(g["raw"], DEV), T(g["z"], DEV), T(g["rd"], DEV), **kw)
+    for name, v in zip(("rgb", "disp", "acc", "weights", "depth"), o):
+        H.assert_close(v, g[name], 2e-6, 1e-5, what=name)   # NaN pattern of disp is checked inside
+
+
+@pytest.mark.parametrize("tag", ["rand", "dyadic"])
+def test_sample_pdf_golden(tag):
+    g = golden(f"stage_samplepdf_{tag}.npz")
+    bins, w = T(g["bins"], DEV), T(g["weights"], DEV)
+    # (i) stage test: same cdf, same u  =>  indices bit-exact, always
+    smp, inds, _ = nvsr_b200.sample_pdf(bins, None, 48, det=True, cdf=T(g["cdf"], DEV), return_all=True)
+    assert torch.equal(inds.cpu(), T(g["inds"]))
+    H.assert_close(smp, g["samples"], 1e-6, what="samples from golden cdf")
+    # (ii)/(iii) full path
+    smp, inds, cdf = nvsr_b200.sample_pdf(bins, w, 48, det=True, return_all=True)
+    H.assert_close(cdf, g["cdf"], 2e-7, what="cdf")
+    mism = inds.cpu() != T(g["inds"])
+    if tag == "dyadic":
+        assert not mism.any()       # order-independent sums: bit-exact end to end
+    else:
+        # every mismatch must sit within 2 ulp of a cdf edge, and the sample value must agree anyway
+        u = T(g["u"])[None].expand_as(mism)
+        cdf_ref = T(g["cdf"])
+        for r, j in zip(*torch.nonzero(mism, as_tuple=True)):
+            assert float((cdf_ref[r] - u[r, j]).abs().min()) <= 2.4e-7
+        assert float(mism.float().mean()) < 0.01
+    H.assert_close(smp, g["samples"], 2e-6, what="samples")
+
+
+def test_sample_pdf_random_u_golden():
+    g = golden("stage_samplepdf_random_u.npz")
+    smp = nvsr_b200.sample_pdf(T(g["bins"], DEV), T(g["weights"], DEV), 31, det=False, u=T(g["u"], DEV))
+    H.assert_close(smp, g["samples"], 2e-6, what="samples")
+
+
+def test_composite_resample_merge_properties():
+    """sort(cat(z_vals, z_samples)) by rank-merge: output sorted and a permutation of the inputs,
+    for deterministic u (fast path) and random u (all-pairs path)."""
+    torch.manual_seed(3)
+    n, S, nf = 513, 64, 128
+    z = torch.sort(torch.rand(n, S) * 4 + 2, -1)[0].to(DEV)
+    raw = (torch.randn(4, n * S) * 3).to(DEV)
+    rd = torch.randn(n, 3).to(DEV)
+    for u in (torch.linspace(0, 1, nf).to(DEV), torch.rand(n, nf).to(DEV)):
+        o = ops.composite(raw, z, rd, S, n_fine=nf, u=u, want_samples=True, want_inds=True, want_weights=True)
+        zm = o["z_merged"]
+        assert bool((zm[:, 1:] >= zm[:, :-1]).all())
+        ref = torch.sort(torch.cat([z, o["z_samples"]], -1), -1)[0]
+        assert torch.equal(zm, ref)
+        # oracle on the same weights
+        w = o["weights"].cpu()
+        mid = 0.5 * (z[:, 1:] + z[:, :-1]).cpu()
+        smp, inds, _ = O.sample_pdf(mid, w[:, 1:-1], nf, det=True, u=u.cpu(), return_all=True)
+        H.assert_close(o["z_samples"], smp, 2e-6, what="z_samples")
+        assert float((o["inds"].cpu() != inds).float().mean()) < 5e-3
+
+
+def test_ipe_golden():
+    g = golden("stage_ipe.npz")
+    enc = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6)
+    H.assert_close(enc, g["enc"].reshape(-1, 36), 5e-6, what="ipe")
+    tile = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6, FEAT_TILE_BF16, 48)
+    un = _untile(tile, 180)
+    H.assert_close(un[:, :36], g["enc"].reshape(-1, 36), 4e-3, what="ipe bf16 tile")
+    assert float(un[:, 36:].abs().max()) == 0.0
+    H.assert_close(ops.dir_encoding(T(g["viewdirs"], DEV), 4, True), g["dir_enc"], 2e-6, what="dir enc")
+
+
+def test_invalid_arguments_fail_loudly():
+    with pytest.raises(nvsr_b200.NvsrError):
+        ops.composite(torch.zeros(4, 64, device=DEV), torch.zeros(1, 2000, device=DEV), torch.zeros(1, 3, device=DEV), 2000)
+    with pytest.raises(nvsr_b200.NvsrError):
+        ops.pack_weight_bf16(torch.zeros(128, 48, device=DEV), k_pad=40)
