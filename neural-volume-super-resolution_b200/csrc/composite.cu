@@ -81,12 +81,52 @@ __device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins,
   return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
 }
 
+// torch.sum(x, -1) of ATen's CPU kernel for a contiguous inner reduction of n fp32 values
+// (aten/src/ATen/native/cpu/SumKernel.cpp: vectorized_inner_sum -> row_sum -> multi_row_sum): 8-lane
+// vectors, 4 interleaved vector accumulators, a 4-level cascade every 16 steps, then the leftover
+// vectors, the scalar tail and the 8 lane partials added sequentially.  Floating-point sums are
+// order dependent; reproducing THIS order makes `total` — and with it every cdf edge and every
+// searchsorted index — bit-identical to the reference's CPU path for identical weights (probed:
+// 100% agreement with torch.sum for n in 14..2050).  The 32 (accumulator, lane) pairs map onto the
+// 32 lanes of the warp.  x(i) = w[i] + 1e-5 (nerf_helpers.py:672).
+__device__ __forceinline__ float aten_sum_w(const float* w, int n, int lane) {
+  auto X = [&](int i) { return __fadd_rn(w[i], 1e-5f); };
+  if (n < 8) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s = __fadd_rn(s, X(i));
+    return s;
+  }
+  const int vec_size = n >> 3, size_ilp = vec_size >> 2;
+  const int k = lane >> 3, L = lane & 7;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int i = 0;
+  while (i + 16 <= size_ilp) {
+    for (int j = 0; j < 16; ++j, ++i) acc[0] = __fadd_rn(acc[0], X(((i << 2) + k) * 8 + L));
+    for (int j = 1; j < 4; ++j) {
+      acc[j] = __fadd_rn(acc[j], acc[j - 1]);
+      acc[j - 1] = 0.f;
+      if ((i & (15 << (j * 4))) != 0) break;
+    }
+  }
+  for (; i < size_ilp; ++i) acc[0] = __fadd_rn(acc[0], X(((i << 2) + k) * 8 + L));
+  for (int j = 1; j < 4; ++j) acc[0] = __fadd_rn(acc[0], acc[j]);
+  if (k == 0)
+    for (int v = size_ilp << 2; v < vec_size; ++v) acc[0] = __fadd_rn(acc[0], X(v * 8 + L));
+  float p = acc[0];
+  p = __fadd_rn(p, __shfl_sync(kFull, acc[0], L + 8));
+  p = __fadd_rn(p, __shfl_sync(kFull, acc[0], L + 16));
+  p = __fadd_rn(p, __shfl_sync(kFull, acc[0], L + 24));
+  float fin = 0.f;
+  for (int idx = vec_size << 3; idx < n; ++idx) fin = __fadd_rn(fin, X(idx));
+  for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(kFull, p, l));
+  return fin;
+}
+
 // pdf/cdf of sample_pdf_2 (nerf_helpers.py:673-676) from weights w[0..nw) in shared memory:
-// cdf[0]=0, cdf[i] = sum_{m<=i-1} (w[m]+1e-5)/total, i = 1..nw  -> nw+1 entries
+// cdf[0]=0, cdf[i] = sum_{m<=i-1} (w[m]+1e-5)/total, i = 1..nw  -> nw+1 entries.
+// cumsum: ATen accumulates fp32 cumsum in double on the CPU and rounds each prefix to fp32.
 __device__ __forceinline__ void build_cdf(const float* w, int nw, float* cdf, int lane) {
-  double part = 0.0;
-  for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(w[i], 1e-5f);
-  float total = (float)warp_sum_d(part);
+  const float total = aten_sum_w(w, nw, lane);
   double carry = 0.0;
   if (lane == 0) cdf[0] = 0.f;
   for (int base = 0; base < nw; base += 32) {

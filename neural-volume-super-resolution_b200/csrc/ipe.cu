@@ -14,21 +14,26 @@ struct IpeRow {
 
 __device__ __forceinline__ IpeRow ipe_gaussian(float t0, float t1, const float o[3], const float d[3], float radius) {
   // conical_frustum_to_gaussian (mip.py:21-29); python-double scalars are cast to fp32 by torch
-  float mu = (t0 + t1) / 2.f;
-  float hw = (t1 - t0) / 2.f;
-  float mu2 = mu * mu, hw2 = hw * hw, hw4 = hw2 * hw2;
-  float den = 3.f * mu2 + hw2;
-  float t_mean = mu + (2.f * mu * hw2) / den;
-  float t_var = hw2 / 3.f - (float)(4.0 / 15.0) * ((hw4 * (12.f * mu2 - hw2)) / (den * den));
-  float r_var = (radius * radius) * (mu2 / 4.f + (float)(5.0 / 12.0) * hw2 - (float)(4.0 / 15.0) * hw4 / den);
+  // every op separately rounded (no FMA contraction): sin(2^i * mean) amplifies last-ulp differences
+  float mu = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+  float hw = __fmul_rn(__fsub_rn(t1, t0), 0.5f);
+  float mu2 = __fmul_rn(mu, mu), hw2 = __fmul_rn(hw, hw), hw4 = __fmul_rn(hw2, hw2);  // hw**4 == (hw^2)^2 in torch.pow
+  float den = __fadd_rn(__fmul_rn(3.f, mu2), hw2);
+  float t_mean = __fadd_rn(mu, __fdiv_rn(__fmul_rn(__fmul_rn(2.f, mu), hw2), den));
+  float t_var = __fsub_rn(__fdiv_rn(hw2, 3.f),
+                          __fmul_rn((float)(4.0 / 15.0),
+                                    __fdiv_rn(__fmul_rn(hw4, __fsub_rn(__fmul_rn(12.f, mu2), hw2)), __fmul_rn(den, den))));
+  float r_var = __fmul_rn(__fmul_rn(radius, radius),
+                          __fsub_rn(__fadd_rn(__fdiv_rn(mu2, 4.f), __fmul_rn((float)(5.0 / 12.0), hw2)),
+                                    __fdiv_rn(__fmul_rn((float)(4.0 / 15.0), hw4), den)));
   // lift_gaussian (mip.py:32-43)
-  float dmag = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  float dmag = fmaxf(1e-10f, __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
   IpeRow g;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float dd = d[c] * d[c];
-    g.mean[c] = d[c] * t_mean + o[c];
-    g.cov[c] = t_var * dd + r_var * (1.f - dd / dmag);
+    float dd = __fmul_rn(d[c], d[c]);
+    g.mean[c] = __fadd_rn(__fmul_rn(d[c], t_mean), o[c]);
+    g.cov[c] = __fadd_rn(__fmul_rn(t_var, dd), __fmul_rn(r_var, __fsub_rn(1.f, __fdiv_rn(dd, dmag))));
   }
   return g;
 }
@@ -39,10 +44,10 @@ __device__ __forceinline__ float ipe_value(const IpeRow& g, int nf, int j) {
   int jj = j - blk * 3 * nf;
   int i = jj / 3, c = jj - i * 3;
   float sc = (float)(1 << i);
-  float y = g.mean[c] * sc;
-  float yv = g.cov[c] * (sc * sc);
-  if (blk) y = y + (float)(0.5 * 3.14159265358979323846);
-  return expf(-0.5f * yv) * sinf(y);
+  float y = __fmul_rn(g.mean[c], sc);
+  float yv = __fmul_rn(g.cov[c], sc * sc);
+  if (blk) y = __fadd_rn(y, (float)(0.5 * 3.14159265358979323846));
+  return __fmul_rn(expf(__fmul_rn(-0.5f, yv)), sinf(y));
 }
 
 __global__ void ipe_rowmajor_kernel(const float* __restrict__ z, const float* __restrict__ ro, const float* __restrict__ rd,

@@ -15,6 +15,7 @@ keeps calling the reference's own function there; calling this module's function
 grad enabled raises.  Unsupported model configurations raise NotImplementedError — no fallback.
 """
 import os
+import weakref
 
 import torch
 
@@ -60,7 +61,7 @@ def _slice(t, i0, i1):
     return None if t is None else t[i0:i1]
 
 
-_pass_cache = {}
+_pass_cache = scene._Cache()
 
 
 def _params_sig(model):
@@ -70,23 +71,23 @@ def _params_sig(model):
 def _planes_pass(model, scene_id, precision):
     """Cached _PlanesPass: rebuilt only when a plane tensor or a decoder weight changed."""
     model.set_cur_scene_id(scene_id)
-    sig = tuple(scene._Cache.key_of(scene._source_plane(model, d)) for d in range(4)) + _params_sig(model)
-    key = (id(model), scene_id, precision)
-    hit = _pass_cache.get(key)
-    if hit is None or hit[0] != sig:
-        hit = (sig, _PlanesPass(model, scene_id, precision))
-        _pass_cache[key] = hit
+    srcs = [scene._source_plane(model, d) for d in range(4)]
+    sig = tuple((id(t),) + scene._Cache.key_of(t) for t in srcs) + _params_sig(model)
+    per_key = _pass_cache.get(model, sig, dict)
+    key = (scene_id, precision)
+    hit = per_key.get(key)
+    # the source planes are held weakly: a recycled id()/data_ptr() of a dead tensor must not match
+    if hit is None or any(r() is not t for r, t in zip(hit[0], srcs)):
+        hit = ([weakref.ref(t) for t in srcs], _PlanesPass(model, scene_id, precision))
+        per_key[key] = hit
     return hit[1]
 
 
 def _mip_pass(model, precision):
-    sig = _params_sig(model)
-    key = (id(model), "mip", precision)
-    hit = _pass_cache.get(key)
-    if hit is None or hit[0] != sig:
-        hit = (sig, _MipPass(model, precision))
-        _pass_cache[key] = hit
-    return hit[1]
+    per_key = _pass_cache.get(model, _params_sig(model), dict)
+    if precision not in per_key:
+        per_key[precision] = _MipPass(model, precision)
+    return per_key[precision]
 
 
 class _PlanesPass:

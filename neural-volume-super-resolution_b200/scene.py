@@ -284,7 +284,10 @@ def blender_camera(width, theta=30.0, phi=-30.0, radius=4.0, camera_angle_x=0.69
 # --------------------------------------------------------------------------------------------------
 # packers
 class _Cache:
-    """Keyed on tensor identity + in-place version: re-pack only when a plane / weight changed."""
+    """Identity + version cache.  Entries hold a WEAK reference to the object they were made from:
+    `id()`/`data_ptr()` alone can be recycled by a new object after the old one died, which would
+    silently serve another scene's packed planes.  An entry is valid only while the very same object
+    is alive and its (data_ptr, _version) signature is unchanged."""
 
     def __init__(self):
         self.store = {}
@@ -293,12 +296,16 @@ class _Cache:
     def key_of(t):
         return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
 
-    def get(self, key, make):
-        hit = self.store.get(key[0])
-        if hit is not None and hit[0] == key:
-            return hit[1]
+    def get(self, obj, sig, make):
+        import weakref
+        hit = self.store.get(id(obj))
+        if hit is not None and hit[0]() is obj and hit[1] == sig:
+            return hit[2]
+        if len(self.store) > 64:  # drop entries whose owners died
+            for k in [k for k, v in self.store.items() if v[0]() is None]:
+                del self.store[k]
         val = make()
-        self.store[key[0]] = (key, val)
+        self.store[id(obj)] = (weakref.ref(obj), sig, val)
         return val
 
 
@@ -360,17 +367,23 @@ def check_supported_planes_model(model):
         raise NotImplementedError("nvsr_b200: unsupported TwoDimPlanesModel configuration: " + ", ".join(bad))
 
 
+def _packed_plane(src, dtype):
+    """channels-last copy of one NCHW plane tensor, cached per (tensor object, version) and dtype"""
+    per_dtype = _plane_cache.get(src, _Cache.key_of(src), dict)
+    if dtype not in per_dtype:
+        per_dtype[dtype] = ops.pack_plane(src.cuda(), dtype)
+    return per_dtype[dtype]
+
+
 def pack_scene_planes(model, scene_id, dtype):
     """Channels-last device planes for `scene_id` as `model` would read them (models.py:270-310)."""
     model.set_cur_scene_id(scene_id)
     packed = []
     for d in range(3):
         src = _source_plane(model, d)
-        key = _Cache.key_of(src) + (dtype,)
-        packed.append(_plane_cache.get(key, lambda s=src: ops.pack_plane(s.cuda(), dtype)))
+        packed.append(_packed_plane(src, dtype))
     vsrc = _source_plane(model, 3)
-    vkey = _Cache.key_of(vsrc) + (NVSR_F32,)
-    vplane = _plane_cache.get(vkey, lambda: ops.pack_plane(vsrc.cuda(), NVSR_F32))
+    vplane = _packed_plane(vsrc, NVSR_F32)
     box = model.box_coords[scene_id].detach().double().cpu()
     lo = box[0].float()                  # .type(coords.type()) of the fp64 box (models.py:264)
     rng = (box[1] - box[0]).float()      # difference in fp64, then cast (models.py:265)
@@ -422,8 +435,11 @@ class PackedPlanesDecoder:
 def pack_planes_decoder(model, precision):
     params = list(model.density_dec["0"].parameters()) + list(model.rgb_dec["0"].parameters()) + \
         list(model.fc_alpha["0"].parameters()) + list(model.fc_rgb["0"].parameters())
-    key = (id(model), tuple((p.data_ptr(), p._version) for p in params), precision)
-    return _decoder_cache.get(key, lambda: PackedPlanesDecoder(model, precision))
+    sig = tuple((p.data_ptr(), p._version) for p in params)
+    per_prec = _decoder_cache.get(model, sig, dict)
+    if precision not in per_prec:
+        per_prec[precision] = PackedPlanesDecoder(model, precision)
+    return per_prec[precision]
 
 
 class PackedMipDecoder:
@@ -474,5 +490,8 @@ class PackedMipDecoder:
 
 def pack_mip_decoder(model, precision):
     params = list(model.parameters())
-    key = (id(model), tuple((p.data_ptr(), p._version) for p in params), precision)
-    return _decoder_cache.get(key, lambda: PackedMipDecoder(model, precision))
+    sig = tuple((p.data_ptr(), p._version) for p in params)
+    per_prec = _decoder_cache.get(model, sig, dict)
+    if precision not in per_prec:
+        per_prec[precision] = PackedMipDecoder(model, precision)
+    return per_prec[precision]

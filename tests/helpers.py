@@ -101,3 +101,37 @@ def assert_close(a, b, atol, rtol=0.0, what=""):
         i = int(torch.argmax(d - tol))
         raise AssertionError(f"{what}: max |diff| {float(d.max()):.3e} (tol {atol:g}+{rtol:g}*|ref|), "
                              f"worst at flat index {i}: {float(a[~nan_a][i])} vs {float(b[~nan_a][i])}")
+
+
+def pdf_sample_tolerance(cdf, bins, inds, eps=2.4e-7):
+    """Per-sample bound on |delta z_sample| caused by an `eps` (2 ulp at 1.0) perturbation of the cdf:
+    t = (u - cdf_below)/denom, so delta z <= width * 3*eps/denom.  Near-empty bins (denom ~ 1e-5) are
+    ill-conditioned in the reference itself; across its `denom < 1e-5 -> 1` switch the sample may move
+    by a whole bin."""
+    B = cdf.shape[-1]
+    below, above = (inds - 1).clamp(min=0), inds.clamp(max=B - 1)
+    denom = cdf.gather(1, above) - cdf.gather(1, below)
+    width = (bins.gather(1, above) - bins.gather(1, below)).abs()
+    switch = (denom - 1e-5).abs() < 2e-6
+    d = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    tol = 2e-6 + width * 3 * eps / d
+    return torch.where(switch, width + 2e-6, tol)
+
+
+def check_resampling(inds_gpu, zs_gpu, inds_ref, zs_ref, cdf_ref, bins_ref, u, what="", max_flip_frac=0.02):
+    """Bin indices must be bit-exact except where u sits within 2 ulp of a cdf edge ("legit flips");
+    samples must agree within the conditioning bound of the reference's own formula."""
+    inds_gpu, zs_gpu = inds_gpu.cpu(), zs_gpu.cpu()
+    u = u.expand_as(inds_ref) if u.dim() == 2 else u[None].expand_as(inds_ref)
+    mism = inds_gpu != inds_ref
+    for r, j in zip(*torch.nonzero(mism, as_tuple=True)):
+        edge = float((cdf_ref[r] - u[r, j]).abs().min())
+        assert edge <= 3.6e-7, f"{what}: index mismatch at ray {int(r)} sample {int(j)} but u is {edge:.2e} from the nearest cdf edge"
+    assert float(mism.float().mean()) <= max_flip_frac, (what, float(mism.float().mean()))
+    tol = pdf_sample_tolerance(cdf_ref, bins_ref, inds_ref)
+    width = (bins_ref[:, 1:] - bins_ref[:, :-1]).abs().max(-1, keepdim=True)[0]
+    tol = torch.where(mism, 2 * width.expand_as(tol), tol)
+    d = (zs_gpu - zs_ref).abs()
+    bad = d > tol
+    assert not bool(bad.any()), f"{what}: z_samples off by {float((d - tol).max()):.3e} beyond the conditioning bound"
+    return mism
