@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--ray-chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -255,7 +255,7 @@ def main():
     for name, a, b, meta in prof:
         key = name
         if name == "nvsr_mlp_chain":
-            key = "mlp_density" if meta["flops"] / max(meta["rows"], 1) < 150000 else "mlp_rgb"
+            key = "mlp_density" if meta["flops"] / max(meta["rows"], 1) < 120000 else "mlp_rgb"
         d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=0, flops=0))
         d["ms"] += a.elapsed_time(b)
         d["n"] += 1
@@ -278,7 +278,7 @@ def main():
     mlp_fl = sum(d["flops"] for d in mlp)
     mlp_n = sum(d["n"] for d in mlp)
     roofline = None
-    if mlp_ms > 0 and args.precision == "bf16":
+    if mlp_ms > 0 and args.precision != "fp32":
         ach = mlp_fl / (mlp_ms * 1e-3) / 1e12
         roofline = {"kernel": "mlp_chain_tc_kernel (decoder, tcgen05)", "bound": "tensor", "achieved": ach,
                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
@@ -302,7 +302,8 @@ def main():
             "samples_per_s": rays * EVALS_PER_RAY / (ms_dev * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": "cfg2_800x800_64+128_planes200", "rays_per_step": rays, "planes": "3x48x200^2 + 48x32^2",
                        "decoder": "48->128x4->1 + 192->128x4->3 (coarse+fine)", "sharding": f"{world} row bands",
                        "ray_chunk": nvsr_b200.render._state["ray_chunk"],

@@ -35,6 +35,7 @@ extern "C" {
 
 #define NVSR_F32 0
 #define NVSR_BF16 1
+#define NVSR_F16 2  /* IEEE half: same tensor-core rate as bf16, 8x finer rounding, max 65504 (saturating) */
 
 #define NVSR_TILE_ROWS 128
 #define NVSR_MAX_LAYERS 8
@@ -71,10 +72,10 @@ int32_t nvsr_prepare_rays(const float* ro_in, const float* rd_in, int64_t n_rays
 int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int32_t rw, void* dst,
                         int32_t dst_dtype, void* stream);
 
-/* nn.Linear weight [n_out, k] (row stride ldw, fp32) -> bf16 UMMA image [k_pad/8][n_out][8],
- * zero-padded for k <= kk < k_pad.  k_pad % 16 == 0. */
-int32_t nvsr_pack_weight_bf16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
-                              void* dst, void* stream);
+/* nn.Linear weight [n_out, k] (row stride ldw, fp32) -> 16-bit (NVSR_BF16|NVSR_F16) UMMA image
+ * [k_pad/8][n_out][8], zero-padded for k <= kk < k_pad.  k_pad % 16 == 0. */
+int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
+                           void* dst, int32_t dst_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a4 + a5  stratified sampler (train_utils.py:95-111) fused with the tri-plane bilinear gather of
@@ -86,7 +87,7 @@ typedef struct nvsr_planes {
   const void* plane[3];   /* channels-last [rh][rw][channels] */
   int32_t rh[3], rw[3];
   int32_t channels;       /* multiple of 8, <= 64 */
-  int32_t dtype;          /* NVSR_F32 | NVSR_BF16 */
+  int32_t dtype;          /* NVSR_F32 | NVSR_BF16 | NVSR_F16 */
   float box_lo[3];        /* fp32(box_coords[scene][0,:3]) */
   float box_rng[3];       /* fp32(box[1,:3] - box[0,:3]) with the difference taken in fp64 */
   float proj[3][6];       /* rot_mats[d][:,1:] row-major [3][2]: grid = n_xyz @ proj[d] */
@@ -106,6 +107,7 @@ typedef struct nvsr_sampler {
 
 #define NVSR_FEAT_ROWMAJOR_F32 0 /* featP [rows,3C] fp32, featM [rows,C] fp32                  */
 #define NVSR_FEAT_TILE_BF16 1    /* featP [tiles][3C/8][128][8] bf16, featM [tiles][C/8][128][8] */
+#define NVSR_FEAT_TILE_F16 2     /* same tile image with fp16 elements (planes must be NVSR_F16)   */
 
 /* rows = n_rays*n_samples, row = ray*S + s.  Tile-image outputs must be sized for
  * ceil(rows/128) tiles; rows past the end are written as zeros.  z_out [n,S] may be NULL. */
@@ -133,7 +135,7 @@ int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, const float* 
  * writes its heads into planar raw[ch][raw_stride].
  */
 typedef struct nvsr_layer {
-  const void* w;         /* F32: [n_out,k] row-major;  BF16: UMMA image [k/8][n_out][8] */
+  const void* w;         /* F32: [n_out,k] row-major;  BF16/F16: UMMA image [k/8][n_out][8] */
   const float* bias;     /* [n_out]; ignored when row_bias != NULL */
   const float* row_bias; /* [n_rays,n_out] per-ray bias (already includes bias) or NULL */
   const float* head_w;   /* [head_n,n_out] fp32 head tapped on this layer's output, or NULL */
@@ -144,7 +146,7 @@ typedef struct nvsr_layer {
 
 typedef struct nvsr_mlp {
   int32_t precision;     /* NVSR_F32: SIMT fp32 kernel, input row-major fp32 [rows,k0];
-                            NVSR_BF16: tcgen05 kernel, input tile image bf16 */
+                            NVSR_BF16 | NVSR_F16: tcgen05 kernel, input = 16-bit tile image */
   int32_t n_layers;
   nvsr_layer_t layer[NVSR_MAX_LAYERS];
   const void* in;

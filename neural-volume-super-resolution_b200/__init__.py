@@ -10,7 +10,7 @@ Host code is Python; every kernel is hand-written CUDA behind the C-ABI of inclu
 There is no CPU fallback: without libnvsr_b200.so (or without a GPU) every entry point raises.
 """
 from . import _lib, build, ops, render, scene  # noqa: F401
-from ._lib import NVSR_BF16, NVSR_F32, NvsrError  # noqa: F401
+from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32, NvsrError  # noqa: F401
 from .ops import (get_ray_bundle, sample_pdf, volume_render_radiance_field)  # noqa: F401
 from .render import (eval_nerf, get_precision, install, render_frame, run_one_iter_of_nerf, set_precision,  # noqa: F401
                      set_ray_chunk, uninstall)

@@ -7,8 +7,8 @@ import os
 
 from . import build as _build
 
-NVSR_F32, NVSR_BF16 = 0, 1
-FEAT_ROWMAJOR_F32, FEAT_TILE_BF16 = 0, 1
+NVSR_F32, NVSR_BF16, NVSR_F16 = 0, 1, 2
+FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, FEAT_TILE_F16 = 0, 1, 2
 TILE_ROWS = 128
 MAX_LAYERS = 8
 MAX_SAMPLES = 1024
@@ -108,7 +108,7 @@ SIGNATURES = {
     "nvsr_ray_bundle": (c_i32, [c_i32, c_i32, c_f, c_f, C.POINTER(c_f), c_i32, c_f, c_i32, c_i32, c_p, c_p, c_p]),
     "nvsr_prepare_rays": (c_i32, [c_p, c_p, c_i64, c_i32, c_i32, c_i32, C.c_double, C.c_double, c_p, c_p, c_p, c_p]),
     "nvsr_pack_plane": (c_i32, [c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),
-    "nvsr_pack_weight_bf16": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),
+    "nvsr_pack_weight16": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),
     "nvsr_sample_gather": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_viewdir_gather": (c_i32, [c_p, c_i64, c_p, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p]),
     "nvsr_row_bias": (c_i32, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p]),

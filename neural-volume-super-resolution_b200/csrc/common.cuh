@@ -1,6 +1,7 @@
 // Shared device/host helpers for libnvsr_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,6 +36,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit operand type of the tensor-core path: bf16 (8-bit significand, fp32 range) or fp16 (11-bit
+// significand, max 65504 — values are clamped on conversion so an overflow saturates instead of inf)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+  else return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t v) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  else return make_float2(bf16lo_to_f32(v), bf16hi_to_f32(v));
+}
+inline bool is_16bit(int dtype) { return dtype == NVSR_BF16 || dtype == NVSR_F16; }
 
 // ---- shared-memory address / mbarrier ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

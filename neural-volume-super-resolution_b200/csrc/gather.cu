@@ -2,7 +2,7 @@
 //
 // Two kernels:
 //   gather_rowmajor_f32 : fp32 planes -> fp32 row-major features (parity mode, feeds the SIMT decoder)
-//   gather_tile_bf16    : bf16 channels-last planes -> bf16 "tile image" features.  A CTA builds one
+//   gather_tile_16      : bf16|fp16 channels-last planes -> 16-bit "tile image" features.  A CTA builds one
 //                         128-row decoder tile in shared memory (coalesced 16-byte texel reads, six
 //                         lanes per texel) and ships it with two bulk (TMA-engine) stores, so the
 //                         tcgen05 decoder can fetch the tile with a single bulk copy.
@@ -117,22 +117,21 @@ struct __align__(16) RowCorners {
   float w00[3], w01[3], w10[3], w11[3];
 };
 
-__device__ __forceinline__ void fma_bf16x8(float acc[8], const uint4& v, float w) {
-  acc[0] = fmaf(bf16lo_to_f32(v.x), w, acc[0]);
-  acc[1] = fmaf(bf16hi_to_f32(v.x), w, acc[1]);
-  acc[2] = fmaf(bf16lo_to_f32(v.y), w, acc[2]);
-  acc[3] = fmaf(bf16hi_to_f32(v.y), w, acc[3]);
-  acc[4] = fmaf(bf16lo_to_f32(v.z), w, acc[4]);
-  acc[5] = fmaf(bf16hi_to_f32(v.z), w, acc[5]);
-  acc[6] = fmaf(bf16lo_to_f32(v.w), w, acc[6]);
-  acc[7] = fmaf(bf16hi_to_f32(v.w), w, acc[7]);
+template <bool F16>
+__device__ __forceinline__ void fma_16x8(float acc[8], const uint4& v, float w) {
+  float2 a = unpack16x2<F16>(v.x), b = unpack16x2<F16>(v.y), c = unpack16x2<F16>(v.z), d = unpack16x2<F16>(v.w);
+  acc[0] = fmaf(a.x, w, acc[0]), acc[1] = fmaf(a.y, w, acc[1]);
+  acc[2] = fmaf(b.x, w, acc[2]), acc[3] = fmaf(b.y, w, acc[3]);
+  acc[4] = fmaf(c.x, w, acc[4]), acc[5] = fmaf(c.y, w, acc[5]);
+  acc[6] = fmaf(d.x, w, acc[6]), acc[7] = fmaf(d.y, w, acc[7]);
 }
 
 constexpr int kGatherThreads = 256;
 
 // dynamic smem: [P image 3C/8 x 2048 B][M image C/8 x 2048 B][RowCorners x 128]
+template <bool F16>
 __global__ void __launch_bounds__(kGatherThreads)
-gather_tile_bf16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
+gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
                  float* __restrict__ z_out, int64_t n_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int CH = p.C / 8;                 // 16-byte chunks per plane texel (6 for C=48)
@@ -198,20 +197,20 @@ gather_tile_bf16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        fma_bf16x8(acc, v[d][0], rc.w00[d]);
-        fma_bf16x8(acc, v[d][1], rc.w01[d]);
-        fma_bf16x8(acc, v[d][2], rc.w10[d]);
-        fma_bf16x8(acc, v[d][3], rc.w11[d]);
+        fma_16x8<F16>(acc, v[d][0], rc.w00[d]);
+        fma_16x8<F16>(acc, v[d][1], rc.w01[d]);
+        fma_16x8<F16>(acc, v[d][2], rc.w10[d]);
+        fma_16x8<F16>(acc, v[d][3], rc.w11[d]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) mean[e] += acc[e];
         uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]), o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]), o.w = pack_bf16x2(acc[6], acc[7]);
+        o.x = pack16x2<F16>(acc[0], acc[1]), o.y = pack16x2<F16>(acc[2], acc[3]);
+        o.z = pack16x2<F16>(acc[4], acc[5]), o.w = pack16x2<F16>(acc[6], acc[7]);
         *reinterpret_cast<uint4*>(sP + (uint32_t)(d * CH + c) * 2048u + (uint32_t)r * 16u) = o;
       }
       uint4 o;
-      o.x = pack_bf16x2(mean[0] / 3.f, mean[1] / 3.f), o.y = pack_bf16x2(mean[2] / 3.f, mean[3] / 3.f);
-      o.z = pack_bf16x2(mean[4] / 3.f, mean[5] / 3.f), o.w = pack_bf16x2(mean[6] / 3.f, mean[7] / 3.f);
+      o.x = pack16x2<F16>(mean[0] / 3.f, mean[1] / 3.f), o.y = pack16x2<F16>(mean[2] / 3.f, mean[3] / 3.f);
+      o.z = pack16x2<F16>(mean[4] / 3.f, mean[5] / 3.f), o.w = pack16x2<F16>(mean[6] / 3.f, mean[7] / 3.f);
       *reinterpret_cast<uint4*>(sM + (uint32_t)c * 2048u + (uint32_t)r * 16u) = o;
     }
     // phase 3: ship the two images with the bulk-copy engine
@@ -262,23 +261,21 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     gather_rowmajor_f32<<<(unsigned)blocks, 256, 0, st>>>(a, p, (float*)feat_p, (float*)feat_m, z_out);
     NVSR_RETURN_LAST_ERROR();
   }
-  if (feat_layout == NVSR_FEAT_TILE_BF16) {
-    if (pl->dtype != NVSR_BF16) return NVSR_ERR_UNSUPPORTED;
+  if (feat_layout == NVSR_FEAT_TILE_BF16 || feat_layout == NVSR_FEAT_TILE_F16) {
+    const bool f16 = feat_layout == NVSR_FEAT_TILE_F16;
+    if (pl->dtype != (f16 ? NVSR_F16 : NVSR_BF16)) return NVSR_ERR_UNSUPPORTED;
+    auto kernel = f16 ? gather_tile_16<true> : gather_tile_16<false>;
     int CH = p.C / 8;
     size_t smem = (size_t)4 * CH * 2048 + sizeof(RowCorners) * kTileRows;
-    static bool configured = false;  // attribute is per-function, idempotent
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(gather_tile_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return (int32_t)e;
-      configured = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int32_t)e;
     int64_t n_tiles = ceil_div64(rows, kTileRows);
     int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
     if (ctas_per_sm > 8) ctas_per_sm = 8;
     if (ctas_per_sm < 1) return NVSR_ERR_RESOURCE;
     int64_t grid = (int64_t)kNumSMs * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    gather_tile_bf16<<<(unsigned)grid, kGatherThreads, smem, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out,
+    kernel<<<(unsigned)grid, kGatherThreads, smem, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out,
                                                                   n_tiles);
     NVSR_RETURN_LAST_ERROR();
   }

@@ -65,7 +65,8 @@ __global__ void ipe_rowmajor_kernel(const float* __restrict__ z, const float* __
   out[idx] = ipe_value(g, nf, j);
 }
 
-// bf16 tile image [tile][k_pad/8][128][8]: one thread per (row, 8-column chunk)
+// 16-bit tile image [tile][k_pad/8][128][8]: one thread per (row, 8-column chunk)
+template <bool F16>
 __global__ void ipe_tile_kernel(const float* __restrict__ z, const float* __restrict__ ro, const float* __restrict__ rd,
                                 int64_t n_rays, int S, float radius, int nf, int k_pad, uint4* __restrict__ out,
                                 int64_t n_tiles) {
@@ -91,8 +92,8 @@ __global__ void ipe_tile_kernel(const float* __restrict__ z, const float* __rest
     }
   }
   uint4 o4;
-  o4.x = pack_bf16x2(f[0], f[1]), o4.y = pack_bf16x2(f[2], f[3]);
-  o4.z = pack_bf16x2(f[4], f[5]), o4.w = pack_bf16x2(f[6], f[7]);
+  o4.x = pack16x2<F16>(f[0], f[1]), o4.y = pack16x2<F16>(f[2], f[3]);
+  o4.z = pack16x2<F16>(f[4], f[5]), o4.w = pack16x2<F16>(f[6], f[7]);
   out[idx] = o4;  // idx == (tile*chunks + c)*128 + r
 }
 
@@ -134,15 +135,19 @@ extern "C" int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, in
     ipe_rowmajor_kernel<<<(unsigned)blocks, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, n_freqs, (float*)out);
     NVSR_RETURN_LAST_ERROR();
   }
-  if (out_layout == NVSR_FEAT_TILE_BF16) {
+  if (out_layout == NVSR_FEAT_TILE_BF16 || out_layout == NVSR_FEAT_TILE_F16) {
     NVSR_CHECK_ARG(k_pad >= 6 * n_freqs && k_pad % 16 == 0);
     if (!aligned16(out)) return NVSR_ERR_ALIGNMENT;
     int64_t n_tiles = ceil_div64(n_rays * n_intervals, kTileRows);
     int64_t total = n_tiles * (k_pad / 8) * kTileRows;
     int64_t blocks = ceil_div64(total, 256);
     NVSR_CHECK_ARG(blocks < ((int64_t)1 << 31));
-    ipe_tile_kernel<<<(unsigned)blocks, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, n_freqs, k_pad,
-                                                     (uint4*)out, n_tiles);
+    if (out_layout == NVSR_FEAT_TILE_F16)
+      ipe_tile_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, n_freqs, k_pad,
+                                                             (uint4*)out, n_tiles);
+    else
+      ipe_tile_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, n_freqs, k_pad,
+                                                              (uint4*)out, n_tiles);
     NVSR_RETURN_LAST_ERROR();
   }
   return NVSR_ERR_UNSUPPORTED;

@@ -71,12 +71,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
-  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(n >> 3) << 17) |
+// kind::f16 instruction descriptor: (bf16|f16) x (bf16|f16) -> fp32, both operands K-major, M=128
+__host__ __device__ constexpr uint32_t umma_idesc_16(int n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;  // F16F32Format: 0 = F16, 1 = BF16
+  return (1u << 4) /*D=f32*/ | (fmt << 7) /*A*/ | (fmt << 10) /*B*/ | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16kind(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -107,6 +108,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // barrier block layout (uint64_t each)
 enum { BAR_W = 0, BAR_IN_FULL = 1, BAR_IN_FREE = 3, BAR_ACC_FULL = 5, BAR_ACT_READY = 7, BAR_ACC_FREE = 9, BAR_COUNT = 11 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -184,7 +186,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         if (!valid[0]) break;
         for (int l = 0; l < L; ++l) {
           const TcLayer& ly = a.layer[l];
-          const uint32_t idesc = umma_idesc_bf16(ly.n);
+          const uint32_t idesc = umma_idesc_16(ly.n, F16);
           const uint32_t b_lbo = (uint32_t)ly.n * 16u;
           for (int s = 0; s < 2; ++s) {
             if (!valid[s]) continue;
@@ -203,7 +205,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
             for (int ks = 0; ks < ksteps; ++ks) {
               uint64_t ad = umma_desc(a_base + (uint32_t)ks * 2u * 2048u, 2048u, 128u);
               uint64_t bd = umma_desc(b_base + (uint32_t)ks * 2u * b_lbo, b_lbo, 128u);
-              umma_bf16(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+              umma_f16kind(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
             }
             umma_commit(&bars[BAR_ACC_FULL + s]);
             if (l == L - 1) umma_commit(&bars[BAR_IN_FREE + s]);
@@ -272,10 +274,10 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 uint4 o;
-                o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                o.x = pack16x2<F16>(f[q * 8 + 0], f[q * 8 + 1]);
+                o.y = pack16x2<F16>(f[q * 8 + 2], f[q * 8 + 3]);
+                o.z = pack16x2<F16>(f[q * 8 + 4], f[q * 8 + 5]);
+                o.w = pack16x2<F16>(f[q * 8 + 6], f[q * 8 + 7]);
                 *reinterpret_cast<uint4*>(act + (uint32_t)((col >> 3) + q) * 2048u + (uint32_t)r * 16u) = o;
               }
             }
@@ -363,10 +365,11 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   a.raw = m->raw;
   a.raw_stride = m->raw_stride;
 
-  cudaError_t e = cudaFuncSetAttribute(mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  auto kernel = m->precision == NVSR_F16 ? mlp_chain_tc_kernel<true> : mlp_chain_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
   int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
-  mlp_chain_tc_kernel<<<(unsigned)grid, kTcThreads, smem_bytes, st>>>(a);
+  kernel<<<(unsigned)grid, kTcThreads, smem_bytes, st>>>(a);
   NVSR_RETURN_LAST_ERROR();
 }
 

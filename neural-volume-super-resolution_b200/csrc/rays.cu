@@ -89,15 +89,15 @@ __global__ void pack_plane_kernel(const float* __restrict__ src, int C, int64_t 
     int c = c0 + tx;
     if (c < C && p < HW) {
       float v = tile[tx][j];
-      if constexpr (sizeof(OutT) == 2) dst[p * C + c] = __float2bfloat16_rn(v);
-      else dst[p * C + c] = v;
+      dst[p * C + c] = OutT(v);
     }
   }
 }
 
-// W [n_out,k] (ld) fp32 -> bf16 image [k_pad/8][n_out][8]
+// W [n_out,k] (ld) fp32 -> 16-bit image [k_pad/8][n_out][8]
+template <typename OutT>
 __global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int k, int ldw, int k_pad,
-                                   __nv_bfloat16* __restrict__ dst) {
+                                   OutT* __restrict__ dst) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int total = n_out * k_pad;
   if (idx >= total) return;
@@ -106,7 +106,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int k
   int chunk = (idx >> 3) / n_out;
   int kk = chunk * 8 + e;
   float v = kk < k ? w[(int64_t)n * ldw + kk] : 0.f;
-  dst[idx] = __float2bfloat16_rn(v);
+  dst[idx] = OutT(v);
 }
 
 // a5 (view half): one thread per (ray, 4-channel chunk)
@@ -205,24 +205,30 @@ extern "C" int32_t nvsr_prepare_rays(const float* ro_in, const float* rd_in, int
 extern "C" int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int32_t rw, void* dst,
                                    int32_t dst_dtype, void* stream) {
   NVSR_CHECK_ARG(src_nchw && dst && channels > 0 && rh > 0 && rw > 0);
-  NVSR_CHECK_ARG(dst_dtype == NVSR_F32 || dst_dtype == NVSR_BF16);
+  NVSR_CHECK_ARG(dst_dtype == NVSR_F32 || dst_dtype == NVSR_BF16 || dst_dtype == NVSR_F16);
   int64_t HW = (int64_t)rh * rw;
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)((channels + 31) / 32));
   dim3 block(32, 8);
   if (dst_dtype == NVSR_F32)
     pack_plane_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (float*)dst);
-  else
+  else if (dst_dtype == NVSR_BF16)
     pack_plane_kernel<__nv_bfloat16>
         <<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (__nv_bfloat16*)dst);
+  else
+    pack_plane_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (__half*)dst);
   NVSR_RETURN_LAST_ERROR();
 }
 
-extern "C" int32_t nvsr_pack_weight_bf16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
-                                         void* dst, void* stream) {
+extern "C" int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
+                                      void* dst, int32_t dst_dtype, void* stream) {
   NVSR_CHECK_ARG(w && dst && n_out > 0 && k > 0 && ldw >= k && k_pad >= k && (k_pad % 16) == 0);
+  NVSR_CHECK_ARG(dst_dtype == NVSR_BF16 || dst_dtype == NVSR_F16);
   int total = n_out * k_pad;
-  pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, ldw, k_pad,
-                                                                            (__nv_bfloat16*)dst);
+  if (dst_dtype == NVSR_BF16)
+    pack_weight_kernel<__nv_bfloat16>
+        <<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, ldw, k_pad, (__nv_bfloat16*)dst);
+  else
+    pack_weight_kernel<__half><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_out, k, ldw, k_pad, (__half*)dst);
   NVSR_RETURN_LAST_ERROR();
 }
 

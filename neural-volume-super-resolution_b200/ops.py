@@ -11,7 +11,11 @@ import math
 import torch
 
 from . import _lib
-from ._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, NVSR_BF16, NVSR_F32, TILE_ROWS
+from ._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, FEAT_TILE_F16, NVSR_BF16, NVSR_F16, NVSR_F32, TILE_ROWS
+
+TORCH_DTYPE = {NVSR_F32: torch.float32, NVSR_BF16: torch.bfloat16, NVSR_F16: torch.float16}
+FEAT_LAYOUT = {NVSR_F32: FEAT_ROWMAJOR_F32, NVSR_BF16: FEAT_TILE_BF16, NVSR_F16: FEAT_TILE_F16}
+LAYOUT_DTYPE = {FEAT_TILE_BF16: torch.bfloat16, FEAT_TILE_F16: torch.float16}
 
 
 def _stream():
@@ -119,15 +123,15 @@ def pack_plane(plane_nchw, dtype=NVSR_F32):
         assert p.shape[0] == 1
         p = p[0]
     c, rh, rw = p.shape
-    out = torch.empty((rh, rw, c), dtype=torch.float32 if dtype == NVSR_F32 else torch.bfloat16, device=p.device)
+    out = torch.empty((rh, rw, c), dtype=TORCH_DTYPE[dtype], device=p.device)
     with torch.cuda.device(p.device):
         st = _call("nvsr_pack_plane", lib.nvsr_pack_plane, _ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
     _lib.check(st, "nvsr_pack_plane")
     return out
 
 
-def pack_weight_bf16(weight, k_pad=None):
-    """nn.Linear weight [n_out,k] (may be a column-slice view) -> UMMA image [k_pad/8, n_out, 8] bf16."""
+def pack_weight16(weight, k_pad=None, dtype=NVSR_BF16):
+    """nn.Linear weight [n_out,k] (may be a column-slice view) -> UMMA image [k_pad/8, n_out, 8] bf16|fp16."""
     lib = _lib.load()
     w = weight.detach()
     _require_cuda(w, "weight")
@@ -137,10 +141,10 @@ def pack_weight_bf16(weight, k_pad=None):
     ldw = w.stride(0)
     if k_pad is None:
         k_pad = (k + 15) // 16 * 16
-    out = torch.empty((k_pad // 8, n_out, 8), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((k_pad // 8, n_out, 8), dtype=TORCH_DTYPE[dtype], device=w.device)
     with torch.cuda.device(w.device):
-        st = _call("nvsr_pack_weight_bf16", lib.nvsr_pack_weight_bf16, _ptr(w), n_out, k, ldw, k_pad, _ptr(out), _stream())
-    _lib.check(st, "nvsr_pack_weight_bf16")
+        st = _call("nvsr_pack_weight16", lib.nvsr_pack_weight16, _ptr(w), n_out, k, ldw, k_pad, _ptr(out), dtype, _stream())
+    _lib.check(st, "nvsr_pack_weight16")
     return out
 
 
@@ -178,8 +182,9 @@ def feature_buffers(rows, channels, layout, device):
         return (torch.empty((rows, 3 * channels), dtype=torch.float32, device=device),
                 torch.empty((rows, channels), dtype=torch.float32, device=device))
     tiles = (rows + TILE_ROWS - 1) // TILE_ROWS
-    return (torch.empty((tiles, 3 * channels // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=device),
-            torch.empty((tiles, channels // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=device))
+    dt = LAYOUT_DTYPE[layout]
+    return (torch.empty((tiles, 3 * channels // 8, TILE_ROWS, 8), dtype=dt, device=device),
+            torch.empty((tiles, channels // 8, TILE_ROWS, 8), dtype=dt, device=device))
 
 
 def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_rand=None, lindisp=False,
@@ -212,7 +217,7 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
         st = _call("nvsr_sample_gather", lib.nvsr_sample_gather, C.byref(s), C.byref(pl), layout, _ptr(feat_p),
                    _ptr(feat_m), _ptr(z_out), _stream(),
                    # algorithmic HBM bytes: feature write 4C*e per row + z (4 B) + rays (24 B/ray)
-                   bytes=rows * (4 * packed.channels * (2 if layout == FEAT_TILE_BF16 else 4) + 4) + n * 24, rows=rows)
+                   bytes=rows * (4 * packed.channels * (4 if layout == FEAT_ROWMAJOR_F32 else 2) + 4) + n * 24, rows=rows)
     _lib.check(st, "nvsr_sample_gather")
     return feat_p, feat_m, (z_out if z_in is None else z_in)
 
@@ -288,7 +293,7 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1):
                    # true MACs x2 only (no padding): layers + heads
                    flops=2 * rows * sum(ly.k * ly.n_out + (0 if ly.head_w is None else ly.head_w.shape[0] * ly.n_out)
                                         for ly in layers),
-                   bytes=rows * (layers[0].k * (2 if precision == NVSR_BF16 else 4) + 4 * sum(
+                   bytes=rows * (layers[0].k * (4 if precision == NVSR_F32 else 2) + 4 * sum(
                        0 if ly.head_w is None else ly.head_w.shape[0] for ly in layers)))
     _lib.check(st, "nvsr_mlp_chain")
     return raw
@@ -410,7 +415,7 @@ def ipe(z_edges, ro, rd, radius, n_freqs, layout=FEAT_ROWMAJOR_F32, k_pad=None):
     else:
         k_pad = k_pad or (6 * n_freqs + 15) // 16 * 16
         tiles = (n * S + TILE_ROWS - 1) // TILE_ROWS
-        out = torch.empty((tiles, k_pad // 8, TILE_ROWS, 8), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((tiles, k_pad // 8, TILE_ROWS, 8), dtype=LAYOUT_DTYPE[layout], device=dev)
     with torch.cuda.device(dev):
         st = _call("nvsr_ipe", lib.nvsr_ipe, _ptr(z), _ptr(_f32c(ro)), _ptr(_f32c(rd)), n, S, float(radius), n_freqs, layout, k_pad,
                           _ptr(out), _stream())

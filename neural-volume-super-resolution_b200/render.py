@@ -20,23 +20,24 @@ import weakref
 import torch
 
 from . import _lib, ops, scene
-from ._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, NVSR_BF16, NVSR_F32
+from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32
 
-_PRECISION = {"bf16": NVSR_BF16, "fp32": NVSR_F32}
+_PRECISION = {"bf16": NVSR_BF16, "fp16": NVSR_F16, "fp32": NVSR_F32}
 _state = {
-    "precision": _PRECISION[os.environ.get("NVSR_PRECISION", "bf16")],
+    "precision": _PRECISION[os.environ.get("NVSR_PRECISION", "fp16")],
     "ray_chunk": int(os.environ.get("NVSR_RAY_CHUNK", "32768")),
 }
 
 
 def set_precision(name):
-    """'bf16': tcgen05 decoder + bf16 planes/features (fp32 accumulate) — the performance contract;
+    """'bf16' / 'fp16': tcgen05 decoder with 16-bit planes/features/weights/activations and fp32
+    accumulation (same tensor-core rate; fp16 rounds 8x finer, bf16 has fp32's range);
     'fp32': SIMT fp32 everywhere — the 1e-3 parity contract."""
     _state["precision"] = _PRECISION[name]
 
 
 def get_precision():
-    return "bf16" if _state["precision"] == NVSR_BF16 else "fp32"
+    return {v: k for k, v in _PRECISION.items()}[_state["precision"]]
 
 
 def set_ray_chunk(n):
@@ -96,7 +97,7 @@ class _PlanesPass:
     def __init__(self, model, scene_id, precision):
         scene.check_supported_planes_model(model)
         self.precision = precision
-        self.layout = FEAT_TILE_BF16 if precision == NVSR_BF16 else FEAT_ROWMAJOR_F32
+        self.layout = ops.FEAT_LAYOUT[precision]
         self.planes = scene.pack_scene_planes(model, scene_id, precision)
         self.dec = scene.pack_planes_decoder(model, precision)
 
@@ -135,7 +136,7 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
                      depth_coarse=co["depth"])
     fo = None
     if Nf > 0:
-        zf = co["z_merged"]
+        zf = randoms["z_fine"] if "z_fine" in randoms else co["z_merged"]   # test hook: teacher-forced depths
         # fine model may read different (super-resolved) planes but shares the view-direction plane
         vfeat_f = vfeat if pf.planes.vplane is pc.planes.vplane else ops.viewdir_gather(vd, pf.planes)
         raw_f, _ = pf.radiance(ro, rd, vfeat_f, near, far, cfg.lindisp, Nc + Nf, z_in=zf)
@@ -159,14 +160,14 @@ def _noise(given, cfg, n, S, dev):
 class _MipPass:
     def __init__(self, model, precision):
         self.precision = precision
-        self.layout = FEAT_TILE_BF16 if precision == NVSR_BF16 else FEAT_ROWMAJOR_F32
+        self.layout = ops.FEAT_LAYOUT[precision]
         self.dec = scene.pack_mip_decoder(model, precision)
 
     def radiance(self, z_edges, ro, rd, denc, radius, n_freqs):
         n, s1 = z_edges.shape
         S = s1 - 1
         rows = n * S
-        enc = ops.ipe(z_edges, ro, rd, radius, n_freqs, self.layout, self.dec.k0 if self.precision == NVSR_BF16 else None)
+        enc = ops.ipe(z_edges, ro, rd, radius, n_freqs, self.layout, self.dec.k0 if self.precision != NVSR_F32 else None)
         rbias = ops.row_bias(denc, self.dec.dir_w, self.dec.dir_b)
         raw = _raw_buffer(rows, ro.device)
         ops.mlp_chain(enc, self.dec.chain(rbias), rows, raw, self.precision, S, n)

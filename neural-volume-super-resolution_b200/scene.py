@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from ._lib import NVSR_BF16, NVSR_F32
+from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32
 
 
 # --------------------------------------------------------------------------------------------------
@@ -406,7 +406,7 @@ class PackedPlanesDecoder:
 
         def wpack(w):
             w = w.detach().float()
-            return ops.pack_weight_bf16(w) if precision == NVSR_BF16 else w.contiguous()
+            return ops.pack_weight16(w, dtype=precision) if precision != NVSR_F32 else w.contiguous()
 
         def f(t):
             return t.detach().float().contiguous()
@@ -454,12 +454,12 @@ class PackedMipDecoder:
             raise NotImplementedError("nvsr_b200: FlexibleNeRFModel with a firing skip connection")
         self.precision = precision
         self.dim_xyz = model.dim_xyz
-        self.k0 = (model.dim_xyz + 15) // 16 * 16 if precision == NVSR_BF16 else model.dim_xyz
+        self.k0 = (model.dim_xyz + 15) // 16 * 16 if precision != NVSR_F32 else model.dim_xyz
 
         def wpack(w, k_pad=None):
             w = w.detach().float()
-            if precision == NVSR_BF16:
-                return ops.pack_weight_bf16(w, k_pad)
+            if precision != NVSR_F32:
+                return ops.pack_weight16(w, k_pad, precision)
             if k_pad is not None and k_pad != w.shape[1]:
                 w = torch.cat([w, w.new_zeros(w.shape[0], k_pad - w.shape[1])], 1)
             return w.contiguous()

@@ -15,12 +15,11 @@ from helpers import T, golden
 from oracle import nvsr_oracle as O
 
 import nvsr_b200
-from nvsr_b200 import NVSR_BF16, NVSR_F32, ops, scene
-from nvsr_b200._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16
+from nvsr_b200 import NVSR_BF16, NVSR_F16, NVSR_F32, ops, scene
+from nvsr_b200._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, FEAT_TILE_F16
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-BF16_RAW_ATOL, BF16_RAW_RTOL = 0.35, 0.05   # raw decoder outputs (pre-sigmoid, |raw| up to ~1e2)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
@@ -61,7 +60,7 @@ def _forward_points(model, sid, x6, precision):
     n = x6.shape[0]
     ro = x6[:, :3].contiguous()
     rd = torch.zeros_like(ro)
-    layout = FEAT_TILE_BF16 if precision == NVSR_BF16 else FEAT_ROWMAJOR_F32
+    layout = ops.FEAT_LAYOUT[precision]
     fp, fm, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, layout, z_in=torch.zeros(n, 1, device=DEV))
     vfeat = ops.viewdir_gather(x6[:, 3:].contiguous(), packed)
     rb = ops.row_bias(vfeat, dec.view_w, dec.view_b)
@@ -90,22 +89,29 @@ def test_planes_forward_fp32_golden():
     H.assert_close(out, g["out"], 1e-3, 1e-5, what="forward out")
 
 
-def test_planes_forward_bf16_golden():
+# raw decoder outputs (pre-sigmoid; |sigma| up to ~50 on these scenes), 16-bit operand modes
+RAW_TOL = {NVSR_BF16: (0.40, 0.02), NVSR_F16: (0.05, 0.003)}
+FEAT_TOL = {NVSR_BF16: (2e-2, 1e-2), NVSR_F16: (2e-3, 1.5e-3)}
+
+
+@pytest.mark.parametrize("precision", [NVSR_BF16, NVSR_F16], ids=["bf16", "fp16"])
+def test_planes_forward_16bit_golden(precision):
     g = golden("stage_planes_forward.npz")
     sid = str(g["scene_id"])
     mc, _ = H.load_planes_scene("scene_planes_small.npz", sid, DEV)
     n = g["x6"].shape[0]
-    fp, fm, vfeat, out = _forward_points(mc, sid, T(g["x6"], DEV), NVSR_BF16)
+    fp, fm, vfeat, out = _forward_points(mc, sid, T(g["x6"], DEV), precision)
     feats = _untile(fp, n)
     for d in range(3):
-        H.assert_close(feats[:, d * 48:(d + 1) * 48], g[f"pos{d}"], 2e-2, 1e-2, what=f"bf16 pos{d}")
+        H.assert_close(feats[:, d * 48:(d + 1) * 48], g[f"pos{d}"], *FEAT_TOL[precision], what=f"16-bit pos{d}")
     err = (out.cpu() - T(g["out"])).abs()
-    print("bf16 forward: max abs err rgb %.4f sigma %.4f (|sigma| max %.1f)" % (
-        float(err[:, :3].max()), float(err[:, 3].max()), float(np.abs(g["out"][:, 3]).max())))
-    H.assert_close(out, g["out"], BF16_RAW_ATOL, BF16_RAW_RTOL, what="bf16 forward out")
+    print("16-bit forward (%s): max abs err rgb %.4f sigma %.4f (|sigma| max %.1f)" % (
+        "bf16" if precision == NVSR_BF16 else "fp16", float(err[:, :3].max()), float(err[:, 3].max()),
+        float(np.abs(g["out"][:, 3]).max())))
+    H.assert_close(out, g["out"], *RAW_TOL[precision], what="16-bit forward out")
 
 
-@pytest.mark.parametrize("precision", [NVSR_F32, NVSR_BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("precision", [NVSR_F32, NVSR_BF16, NVSR_F16], ids=["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40000])
 def test_mlp_chain_vs_torch(precision, rows):
     """decoder chain kernels vs a plain fp32 torch evaluation of the same layers (ragged tile counts)"""
@@ -117,15 +123,15 @@ def test_mlp_chain_vs_torch(precision, rows):
     x = torch.randn(rows, k0)
     rbias = torch.randn(n_rays, 128)
     with torch.no_grad():
-        if precision == NVSR_BF16:
-            xq = x.bfloat16().float()
-            h = xq
+        if precision != NVSR_F32:
+            q = (lambda t: t.bfloat16().float()) if precision == NVSR_BF16 else (lambda t: t.half().float())
+            h = q(x)
             for i, l in enumerate(lins):
-                w = l.weight.bfloat16().float()
+                w = q(l.weight)
                 b = rbias[torch.arange(rows) // S] if i == 0 else l.bias
                 h = torch.relu(h @ w.t() + b)
                 if i < 3:
-                    h = h.bfloat16().float()
+                    h = q(h)
             ref = h @ head.weight.t() + head.bias
         else:
             h = x
@@ -136,23 +142,25 @@ def test_mlp_chain_vs_torch(precision, rows):
     layers = []
     for i, l in enumerate(lins):
         w = l.weight.detach().to(DEV)
-        wp = ops.pack_weight_bf16(w) if precision == NVSR_BF16 else w.contiguous()
+        wp = ops.pack_weight16(w, dtype=precision) if precision != NVSR_F32 else w.contiguous()
         layers.append(ops.ChainLayer(wp, None if i == 0 else l.bias.detach().to(DEV), l.in_features, 128, True,
                                      row_bias=rbias.to(DEV) if i == 0 else None,
                                      head_w=head.weight.detach().to(DEV) if i == 3 else None,
                                      head_b=head.bias.detach().to(DEV) if i == 3 else None, head_ch=0))
-    if precision == NVSR_BF16:
+    if precision != NVSR_F32:
         tiles = (rows + 127) // 128
         xin = torch.zeros(tiles * 128, k0)
         xin[:rows] = x
-        inp = xin.reshape(tiles, 128, k0 // 8, 8).permute(0, 2, 1, 3).contiguous().bfloat16().to(DEV)
+        inp = xin.reshape(tiles, 128, k0 // 8, 8).permute(0, 2, 1, 3).contiguous().to(ops.TORCH_DTYPE[precision]).to(DEV)
     else:
         inp = x.to(DEV)
     raw = torch.full((4, (rows + 127) // 128 * 128), float("nan"), device=DEV)
     ops.mlp_chain(inp, layers, rows, raw, precision, S, n_rays)
     torch.cuda.synchronize()
     out = raw[:3, :rows].t()
-    tol = 2e-3 if precision == NVSR_BF16 else 2e-4   # same bf16-rounded operands: only accumulation order differs
+    # the torch evaluation rounds operands exactly like the kernel: only accumulation order (and rare
+    # one-ulp re-rounding of a hidden activation) differs
+    tol = {NVSR_F32: 2e-4, NVSR_BF16: 4e-3, NVSR_F16: 5e-4}[precision]
     H.assert_close(out, ref, tol, tol, what=f"mlp rows={rows}")
     assert torch.isnan(raw[3]).all()  # untouched channel stays untouched
 
@@ -232,10 +240,11 @@ def test_ipe_golden():
     g = golden("stage_ipe.npz")
     enc = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6)
     H.assert_close(enc, g["enc"].reshape(-1, 36), 5e-6, what="ipe")
-    tile = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6, FEAT_TILE_BF16, 48)
-    un = _untile(tile, 180)
-    H.assert_close(un[:, :36], g["enc"].reshape(-1, 36), 4e-3, what="ipe bf16 tile")
-    assert float(un[:, 36:].abs().max()) == 0.0
+    for layout, tol in ((FEAT_TILE_BF16, 4e-3), (FEAT_TILE_F16, 5e-4)):
+        tile = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6, layout, 48)
+        un = _untile(tile, 180)
+        H.assert_close(un[:, :36], g["enc"].reshape(-1, 36), tol, what="ipe 16-bit tile")
+        assert float(un[:, 36:].abs().max()) == 0.0
     H.assert_close(ops.dir_encoding(T(g["viewdirs"], DEV), 4, True), g["dir_enc"], 2e-6, what="dir enc")
 
 
@@ -243,4 +252,4 @@ def test_invalid_arguments_fail_loudly():
     with pytest.raises(nvsr_b200.NvsrError):
         ops.composite(torch.zeros(4, 64, device=DEV), torch.zeros(1, 2000, device=DEV), torch.zeros(1, 3, device=DEV), 2000)
     with pytest.raises(nvsr_b200.NvsrError):
-        ops.pack_weight_bf16(torch.zeros(128, 48, device=DEV), k_pad=40)
+        ops.pack_weight16(torch.zeros(128, 48, device=DEV), k_pad=40)

@@ -88,7 +88,7 @@ E2E = ["e2e_planes_det.npz", "e2e_planes_perturb.npz", "e2e_planes_ndc.npz", "e2
        "e2e_planes_sr.npz", "e2e_mip_det.npz"]
 
 
-def run_oracle_e2e(name, device="cpu", runner=None, **kw):
+def run_oracle_e2e(name, device="cpu", runner=None, z_fine=None, **kw):
     g = golden(name)
     sid = str(g["scene_id"])
     mip = name.startswith("e2e_mip")
@@ -101,6 +101,8 @@ def run_oracle_e2e(name, device="cpu", runner=None, **kw):
     opt, scfg = H.options_from(g, mip), H.scene_cfg_from(g)
     batch = torch.stack([T(g["ro"], device).reshape(-1, 3), T(g["rd"], device).reshape(-1, 3)], 0)
     rnd = H.randoms_from(g, device)
+    if z_fine is not None:
+        rnd["z_fine"] = z_fine
     if runner is None:
         if mip:
             enc = lambda mc_: O.integrated_pos_enc(mc_[0], mc_[1], 7)
