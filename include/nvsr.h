@@ -38,6 +38,20 @@ extern "C" {
 #define NVSR_F16 2  /* IEEE half: same tensor-core rate as bf16, 8x finer rounding, max 65504 (saturating) */
 
 #define NVSR_TILE_ROWS 128
+
+/* Row order of a (n_rays x S samples) point set inside feature tile images and the planar raw buffer.
+ *   RAY_MAJOR : row = ray*S + s                                (the reference's flatten order)
+ *   BLOCKED   : a 128-row tile holds NVSR_BLK_RAYS consecutive rays x NVSR_BLK_SAMPLES consecutive
+ *               samples:  tile = (ray/8)*ceil(S/16) + s/16,  row = tile*128 + (s%16)*8 + ray%8.
+ *               Consecutive rows are adjacent pixels at the same depth, so the texel reads of a warp
+ *               coalesce in L1, and the 8 rays of a block own one contiguous span of the raw buffer.
+ *               Rows of padding rays/samples exist in the buffers and are ignored.
+ * Buffers hold nvsr_rows_padded() rows. */
+#define NVSR_ROWS_RAY_MAJOR 0
+#define NVSR_ROWS_BLOCKED 1
+#define NVSR_BLK_RAYS 8
+#define NVSR_BLK_SAMPLES 16
+int64_t nvsr_rows_padded(int64_t n_rays, int32_t n_samples, int32_t row_order);
 #define NVSR_MAX_LAYERS 8
 #define NVSR_MAX_SAMPLES 1024 /* samples per ray handled by the warp-per-ray kernels */
 
@@ -105,12 +119,13 @@ typedef struct nvsr_sampler {
   const float* z_in;      /* [n,S] fine pass: merged depths; when non-NULL t_vals/t_rand unused */
 } nvsr_sampler_t;
 
-#define NVSR_FEAT_ROWMAJOR_F32 0 /* featP [rows,3C] fp32, featM [rows,C] fp32                  */
-#define NVSR_FEAT_TILE_BF16 1    /* featP [tiles][3C/8][128][8] bf16, featM [tiles][C/8][128][8] */
+#define NVSR_FEAT_ROWMAJOR_F32 0 /* featP [rows,3C] fp32, featM [rows,C] fp32; rows RAY_MAJOR       */
+#define NVSR_FEAT_TILE_BF16 1    /* featP [tiles][3C/8][128][8] bf16, featM [tiles][C/8][128][8]; BLOCKED */
 #define NVSR_FEAT_TILE_F16 2     /* same tile image with fp16 elements (planes must be NVSR_F16)   */
 
-/* rows = n_rays*n_samples, row = ray*S + s.  Tile-image outputs must be sized for
- * ceil(rows/128) tiles; rows past the end are written as zeros.  z_out [n,S] may be NULL. */
+/* Row-major output: rows = n_rays*n_samples, row = ray*S + s.  Tile-image outputs use the BLOCKED
+ * row order and must be sized for nvsr_rows_padded(n,S,BLOCKED)/128 tiles; padding rows are written
+ * as zeros.  z_out [n,S] (always ray-major) may be NULL. */
 int32_t nvsr_sample_gather(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes,
                            int32_t feat_layout, void* feat_p, void* feat_m, float* z_out,
                            void* stream);
@@ -150,11 +165,12 @@ typedef struct nvsr_mlp {
   int32_t n_layers;
   nvsr_layer_t layer[NVSR_MAX_LAYERS];
   const void* in;
-  int64_t rows;
-  int32_t samples_per_ray; /* row -> ray = row / samples_per_ray (for row_bias) */
+  int64_t rows;          /* rows to evaluate (RAY_MAJOR: n_rays*S; BLOCKED: nvsr_rows_padded) */
+  int32_t samples_per_ray; /* S: with row_order gives row -> ray (for row_bias) */
   int64_t n_rays;
-  float* raw;            /* planar [4][raw_stride] */
+  float* raw;            /* planar [4][raw_stride], same row order as the input */
   int64_t raw_stride;
+  int32_t row_order;     /* NVSR_ROWS_* of the input rows (tcgen05 path; the fp32 path is RAY_MAJOR) */
 } nvsr_mlp_t;
 
 int32_t nvsr_mlp_chain(const nvsr_mlp_t* mlp, void* stream);
@@ -167,8 +183,9 @@ int32_t nvsr_mlp_chain(const nvsr_mlp_t* mlp, void* stream);
 typedef struct nvsr_composite {
   int64_t n_rays;
   int32_t n_samples;       /* S: radiance samples per ray */
-  const float* raw;        /* planar [4][raw_stride]: r,g,b,sigma of row = ray*S + s */
+  const float* raw;        /* planar [4][raw_stride]: r,g,b,sigma of row(ray,s) in `row_order` */
   int64_t raw_stride;
+  int32_t row_order;       /* NVSR_ROWS_RAY_MAJOR | NVSR_ROWS_BLOCKED */
   const float* z;          /* [n,S]  (mip: [n,S+1] interval edges) */
   const float* rd;         /* [n,3] */
   const float* noise;      /* [n,S] noise already scaled by radiance_field_noise_std, or NULL */
@@ -200,7 +217,8 @@ int32_t nvsr_sample_pdf(const float* bins, const float* weights, const float* cd
 /* ------------------------------------------------------------------------------------------------
  * a9  mip path: cast_rays + conical_frustum_to_gaussian + lift_gaussian (mip.py:9-43) fused with
  * IntegratedPositionalEncoding (mip.py:154-199).  z: [n,S+1] interval edges; out: [n*S, 6*n_freqs]
- * (row-major fp32, out_layout 0) or bf16 tile image padded to k_pad columns (out_layout 1).
+ * (row-major fp32, out_layout 0) or a 16-bit tile image padded to k_pad columns (out_layout 1|2);
+ * rows are RAY_MAJOR in both.
  */
 int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, int64_t n_rays, int32_t n_intervals,
                  float radius, int32_t n_freqs, int32_t out_layout, int32_t k_pad, void* out,

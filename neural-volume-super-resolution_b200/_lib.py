@@ -9,6 +9,8 @@ from . import build as _build
 
 NVSR_F32, NVSR_BF16, NVSR_F16 = 0, 1, 2
 FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, FEAT_TILE_F16 = 0, 1, 2
+ROWS_RAY_MAJOR, ROWS_BLOCKED = 0, 1
+BLK_RAYS, BLK_SAMPLES = 8, 16
 TILE_ROWS = 128
 MAX_LAYERS = 8
 MAX_SAMPLES = 1024
@@ -73,6 +75,7 @@ class Mlp(C.Structure):
         ("n_rays", c_i64),
         ("raw", c_p),
         ("raw_stride", c_i64),
+        ("row_order", c_i32),
     ]
 
 
@@ -82,6 +85,7 @@ class Composite(C.Structure):
         ("n_samples", c_i32),
         ("raw", c_p),
         ("raw_stride", c_i64),
+        ("row_order", c_i32),
         ("z", c_p),
         ("rd", c_p),
         ("noise", c_p),
@@ -105,6 +109,7 @@ class Composite(C.Structure):
 SIGNATURES = {
     "nvsr_abi_version": (c_i32, []),
     "nvsr_status_string": (C.c_char_p, [c_i32]),
+    "nvsr_rows_padded": (c_i64, [c_i64, c_i32, c_i32]),
     "nvsr_ray_bundle": (c_i32, [c_i32, c_i32, c_f, c_f, C.POINTER(c_f), c_i32, c_f, c_i32, c_i32, c_p, c_p, c_p]),
     "nvsr_prepare_rays": (c_i32, [c_p, c_p, c_i64, c_i32, c_i32, c_i32, C.c_double, C.c_double, c_p, c_p, c_p, c_p]),
     "nvsr_pack_plane": (c_i32, [c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),

@@ -25,6 +25,22 @@ constexpr int kNumSMs = 148;
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- BLOCKED row order (nvsr.h): a tile = 8 consecutive rays x 16 consecutive samples ----------
+constexpr int kBlkRays = NVSR_BLK_RAYS, kBlkSamples = NVSR_BLK_SAMPLES;
+static_assert(kBlkRays * kBlkSamples == NVSR_TILE_ROWS, "a block is one decoder tile");
+__host__ __device__ inline int tiles_per_block(int S) { return (S + kBlkSamples - 1) / kBlkSamples; }
+__host__ __device__ inline int64_t rows_padded(int64_t n_rays, int S, int order) {
+  if (order == NVSR_ROWS_BLOCKED) return ceil_div64(n_rays, kBlkRays) * tiles_per_block(S) * kTileRows;
+  return n_rays * S;
+}
+// (tile, row-in-tile) -> (ray, sample)
+__device__ __forceinline__ void blocked_decode(int64_t tile, int r, int TS, int64_t* ray, int* s) {
+  int64_t b = tile / TS;
+  int sb = (int)(tile - b * TS);
+  *s = sb * kBlkSamples + (r >> 3);
+  *ray = b * kBlkRays + (r & 7);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- bf16 packing -------------------------------------------------------------------------

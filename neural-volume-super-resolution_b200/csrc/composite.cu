@@ -154,7 +154,13 @@ struct CompositeArgs {
   int64_t* inds;
   float* z_samples;
   float* z_merged;
+  int row_order;
 };
+
+// BLOCKED raw staging: the 8 rays of a block own one contiguous span of TS*128 floats per channel.
+// The CTA copies it (coalesced) into shared memory as [ch][ray-in-block][pitch]; pitch % 32 == 4 makes
+// both the transposing store (8 rays x 4 samples per warp) and the per-ray reads conflict-free.
+__host__ __device__ inline int stage_pitch(int S) { return ((S - 4 + 31) / 32) * 32 + 4; }
 
 // per-warp shared floats: zv[S+1] | w[S] | cdf[S] | bins[S] | zs[n_fine]
 __host__ __device__ inline int composite_smem_floats(int S, int n_fine) {
@@ -173,16 +179,36 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
   float* cdf = wbuf + S;
   float* bins = cdf + S;
   float* zs = bins + S;
+  const bool blocked = a.row_order == NVSR_ROWS_BLOCKED;  // then warps_per_cta == kBlkRays
+  float* sraw = sm + (size_t)warps_per_cta * composite_smem_floats(S, a.n_fine);
+  const int P = stage_pitch(S);
+  const int TS = tiles_per_block(S);
+  const int64_t n_groups = ceil_div64(a.n_rays, warps_per_cta);
 
-  for (int64_t ray = (int64_t)blockIdx.x * warps_per_cta + wid; ray < a.n_rays;
-       ray += (int64_t)gridDim.x * warps_per_cta) {
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int64_t ray = grp * warps_per_cta + wid;
+    if (blocked) {
+      __syncthreads();  // previous group's readers are done with sraw
+      const int span = TS * kTileRows;
+      for (int ch = 0; ch < 4; ++ch) {
+        const float* src = a.raw + ch * a.raw_stride + grp * span;
+        for (int e = threadIdx.x; e < span; e += blockDim.x) {
+          int r = e & (kTileRows - 1);
+          int sidx = (e >> 7) * kBlkSamples + (r >> 3);
+          if (sidx < S) sraw[(ch * kBlkRays + (r & 7)) * P + sidx] = __ldg(src + e);
+        }
+      }
+      __syncthreads();
+    }
+    if (ray >= a.n_rays) continue;
     __syncwarp();
     for (int i = lane; i < S1; i += 32) zv[i] = __ldg(a.z + ray * S1 + i);
     float dx = __ldg(a.rd + ray * 3), dy = __ldg(a.rd + ray * 3 + 1), dz = __ldg(a.rd + ray * 3 + 2);
     float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     __syncwarp();
 
-    const float* raw_r = a.raw + ray * S;
+    const float* raw_r = blocked ? sraw + wid * P : a.raw + ray * S;
+    const int64_t chs = blocked ? (int64_t)kBlkRays * P : a.raw_stride;
     double carry = 1.0;  // product of (1-alpha+1e-10) over previous chunks
     double sr = 0.0, sg = 0.0, sb = 0.0, sd = 0.0, sa = 0.0;
     for (int base = 0; base < S; base += 32) {
@@ -199,10 +225,10 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
           zc = zv[i];
         }
         dist = __fmul_rn(dist, dnorm);
-        r = sigmoid_ref(__ldg(raw_r + i));
-        g = sigmoid_ref(__ldg(raw_r + a.raw_stride + i));
-        b = sigmoid_ref(__ldg(raw_r + 2 * a.raw_stride + i));
-        float sig = __ldg(raw_r + 3 * a.raw_stride + i);
+        r = sigmoid_ref(raw_r[i]);
+        g = sigmoid_ref(raw_r[chs + i]);
+        b = sigmoid_ref(raw_r[2 * chs + i]);
+        float sig = raw_r[3 * chs + i];
         if (a.noise) sig = __fadd_rn(sig, __ldg(a.noise + ray * S + i));
         sig = fmaxf(sig, 0.f);
         alpha = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
@@ -347,18 +373,30 @@ using namespace nvsr;
 extern "C" int32_t nvsr_composite(const nvsr_composite_t* c, void* stream) {
   NVSR_CHECK_ARG(c && c->n_rays >= 0 && c->n_samples > 0 && c->n_samples <= NVSR_MAX_SAMPLES);
   NVSR_CHECK_ARG(c->raw && c->z && c->rd && c->rgb && c->disp && c->acc && c->depth);
-  NVSR_CHECK_ARG(c->raw_stride >= c->n_rays * c->n_samples);
   if (c->n_fine > 0) {
     NVSR_CHECK_ARG(c->u && c->z_merged && c->n_samples >= 3 && c->n_fine <= NVSR_MAX_SAMPLES);
   }
   if (c->n_rays == 0) return NVSR_OK;
+  NVSR_CHECK_ARG(c->row_order == NVSR_ROWS_RAY_MAJOR || c->row_order == NVSR_ROWS_BLOCKED);
+  NVSR_CHECK_ARG(c->raw_stride >= rows_padded(c->n_rays, c->n_samples, c->row_order));
   CompositeArgs a{c->n_rays, c->n_samples, c->raw, c->raw_stride, c->z, c->rd, c->noise, c->white_bkgd, c->mip,
                   c->rgb, c->disp, c->acc, c->depth, c->weights, c->n_fine > 0 ? c->n_fine : 0, c->u, c->u_per_ray,
-                  c->inds, c->z_samples, c->z_merged};
+                  c->inds, c->z_samples, c->z_merged, c->row_order};
   int warps;
   size_t smem;
-  int32_t st = pick_warps(composite_kernel, composite_smem_floats(a.S, a.n_fine), &warps, &smem);
-  if (st != NVSR_OK) return st;
+  if (a.row_order == NVSR_ROWS_BLOCKED) {
+    // one CTA = the 8 rays of a block, staged through shared memory
+    warps = kBlkRays;
+    smem = ((size_t)warps * composite_smem_floats(a.S, a.n_fine) + (size_t)4 * kBlkRays * stage_pitch(a.S)) * sizeof(float);
+    if (smem > 200 * 1024) return NVSR_ERR_RESOURCE;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int32_t)e;
+    }
+  } else {
+    int32_t st = pick_warps(composite_kernel, composite_smem_floats(a.S, a.n_fine), &warps, &smem);
+    if (st != NVSR_OK) return st;
+  }
   int64_t blocks = ceil_div64(c->n_rays, warps);
   int64_t max_blocks = (int64_t)kNumSMs * 16;
   if (blocks > max_blocks) blocks = max_blocks;

@@ -5,7 +5,10 @@
 //   gather_tile_16      : bf16|fp16 channels-last planes -> 16-bit "tile image" features.  A CTA builds one
 //                         128-row decoder tile in shared memory (coalesced 16-byte texel reads, six
 //                         lanes per texel) and ships it with two bulk (TMA-engine) stores, so the
-//                         tcgen05 decoder can fetch the tile with a single bulk copy.
+//                         tcgen05 decoder can fetch the tile with a single bulk copy.  Rows are in the
+//                         BLOCKED order (8 adjacent rays x 16 samples per tile): consecutive rows are
+//                         adjacent pixels at one depth, whose bilinear footprints overlap, so the
+//                         texel requests of a warp collapse onto a few L1 lines.
 // Nothing of pts / embedded ([N,S,3] / [N*S,6] in the reference) is ever materialised in HBM.
 #include "bilinear.cuh"
 #include "common.cuh"
@@ -140,7 +143,7 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
   uint8_t* sP = smem;
   uint8_t* sM = smem + p_bytes;
   RowCorners* sc = reinterpret_cast<RowCorners*>(smem + p_bytes + m_bytes);
-  const int64_t rows = a.n_rays * a.S;
+  const int TS = tiles_per_block(a.S);
   const int tid = threadIdx.x;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -149,13 +152,13 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
     __syncthreads();
     // phase 1: per-row sample position -> 3 planes' corner indices and weights
     if (tid < kTileRows) {
-      int64_t row = tile * kTileRows + tid;
+      int64_t ray;
+      int s;
+      blocked_decode(tile, tid, TS, &ray, &s);
       RowCorners rc;
-      if (row < rows) {
-        int64_t ray = row / a.S;
-        int s = (int)(row % a.S);
+      if (ray < a.n_rays && s < a.S) {
         float z = sample_depth(a, ray, s);
-        if (z_out) z_out[row] = z;
+        if (z_out) z_out[ray * a.S + s] = z;
         Bilin b[3];
         sample_corners(a, p, ray, z, b);
 #pragma unroll
@@ -269,7 +272,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     size_t smem = (size_t)4 * CH * 2048 + sizeof(RowCorners) * kTileRows;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int32_t)e;
-    int64_t n_tiles = ceil_div64(rows, kTileRows);
+    int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
     int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
     if (ctas_per_sm > 8) ctas_per_sm = 8;
     if (ctas_per_sm < 1) return NVSR_ERR_RESOURCE;

@@ -138,25 +138,52 @@ __global__ void viewdir_gather_kernel(const float* __restrict__ viewdirs, int64_
   *reinterpret_cast<float4*>(vfeat + ray * C + ch) = o;
 }
 
-// out[ray,n] = b[n] + sum_k w[n,k]*vin[ray,k]; block = (n_out threads) x rays-per-block rows
-__global__ void row_bias_kernel(const float* __restrict__ vin, int64_t n_rays, int K, const float* __restrict__ w,
-                                int ldw, const float* __restrict__ b, int n_out, float* __restrict__ out) {
-  extern __shared__ float sw[];  // [K][n_out] transposed weights
-  for (int i = threadIdx.x; i < K * n_out; i += blockDim.x) {
-    int n = i % n_out, k = i / n_out;
-    sw[i] = w[(int64_t)n * ldw + k];
+// out[ray,n] = b[n] + sum_k w[n,k]*vin[ray,k].  Persistent blocks: the weights are transposed into
+// shared memory once per block (coalesced reads, padded rows -> conflict-free), then every iteration
+// stages 64 rays of vin and each thread produces 8 rays x 1 output column from LDS.128 operands.
+constexpr int kRbRays = 64;
+__global__ void __launch_bounds__(512)
+row_bias_kernel(const float* __restrict__ vin, int64_t n_rays, int K, int Kp, const float* __restrict__ w, int ldw,
+                const float* __restrict__ b, int n_out, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sw[];  // [Kp][n_out+1] transposed weights | [kRbRays][Kp] vin tile
+  const int ldn = n_out + 1;
+  float* sv = sw + (size_t)Kp * ldn + ((4 - ((Kp * ldn) & 3)) & 3);
+  for (int i = threadIdx.x; i < n_out * Kp; i += blockDim.x) {
+    int n = i / Kp, k = i - n * Kp;
+    sw[k * ldn + n] = k < K ? w[(int64_t)n * ldw + k] : 0.f;
   }
-  __syncthreads();
-  const int rays_per_block = 64;
-  int64_t r0 = (int64_t)blockIdx.x * rays_per_block;
-  for (int i = threadIdx.x; i < rays_per_block * n_out; i += blockDim.x) {
-    int n = i % n_out;
-    int64_t ray = r0 + i / n_out;
-    if (ray >= n_rays) break;
-    float acc = b ? b[n] : 0.f;
-    const float* v = vin + ray * K;
-    for (int k = 0; k < K; ++k) acc = fmaf(sw[k * n_out + n], __ldg(v + k), acc);
-    out[ray * n_out + n] = acc;
+  const int groups = kRbRays / 8;  // 8 rays per thread
+  for (int64_t r0 = (int64_t)blockIdx.x * kRbRays; r0 < n_rays; r0 += (int64_t)gridDim.x * kRbRays) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRbRays * Kp; i += blockDim.x) {
+      int rr = i / Kp, k = i - rr * Kp;
+      int64_t ray = r0 + rr;
+      sv[i] = (k < K && ray < n_rays) ? __ldg(vin + ray * K + k) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * n_out; i += blockDim.x) {
+      int n = i % n_out, g = i / n_out;
+      float acc[8];
+      float bn = b ? __ldg(b + n) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bn;
+      for (int k = 0; k < Kp; k += 4) {
+        float w0 = sw[k * ldn + n], w1 = sw[(k + 1) * ldn + n], w2 = sw[(k + 2) * ldn + n], w3 = sw[(k + 3) * ldn + n];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = *reinterpret_cast<const float4*>(sv + (g * 8 + j) * Kp + k);
+          acc[j] = fmaf(w0, v.x, acc[j]);
+          acc[j] = fmaf(w1, v.y, acc[j]);
+          acc[j] = fmaf(w2, v.z, acc[j]);
+          acc[j] = fmaf(w3, v.w, acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int64_t ray = r0 + g * 8 + j;
+        if (ray < n_rays) out[ray * n_out + n] = acc[j];
+      }
+    }
   }
 }
 
@@ -250,13 +277,25 @@ extern "C" int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, co
   NVSR_CHECK_ARG(vin && w && out && n_rays >= 0 && k > 0 && n_out > 0 && ldw >= k);
   NVSR_CHECK_ARG((size_t)k * n_out * sizeof(float) <= 48 * 1024);
   if (n_rays == 0) return NVSR_OK;
-  size_t smem = (size_t)k * n_out * sizeof(float);
-  row_bias_kernel<<<(unsigned)ceil_div64(n_rays, 64), 256, smem, (cudaStream_t)stream>>>(vin, n_rays, k, w, ldw, b,
-                                                                                        n_out, out);
+  const int kp = (k + 3) & ~3;
+  size_t smem = ((size_t)kp * (n_out + 1) + 4 + (size_t)kRbRays * kp) * sizeof(float);
+  if (smem > 200 * 1024) return NVSR_ERR_RESOURCE;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(row_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int32_t)e;
+  }
+  int64_t blocks = ceil_div64(n_rays, kRbRays);
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  row_bias_kernel<<<(unsigned)blocks, 512, smem, (cudaStream_t)stream>>>(vin, n_rays, k, kp, w, ldw, b, n_out, out);
   NVSR_RETURN_LAST_ERROR();
 }
 
 extern "C" int32_t nvsr_abi_version(void) { return NVSR_ABI_VERSION; }
+
+extern "C" int64_t nvsr_rows_padded(int64_t n_rays, int32_t n_samples, int32_t row_order) {
+  if (n_rays < 0 || n_samples <= 0) return 0;
+  return rows_padded(n_rays, n_samples, row_order);
+}
 
 extern "C" const char* nvsr_status_string(int32_t status) {
   switch (status) {

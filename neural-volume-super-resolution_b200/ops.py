@@ -11,11 +11,39 @@ import math
 import torch
 
 from . import _lib
-from ._lib import FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, FEAT_TILE_F16, NVSR_BF16, NVSR_F16, NVSR_F32, TILE_ROWS
+from ._lib import (BLK_RAYS, BLK_SAMPLES, FEAT_ROWMAJOR_F32, FEAT_TILE_BF16, FEAT_TILE_F16, NVSR_BF16, NVSR_F16, NVSR_F32,
+                   ROWS_BLOCKED, ROWS_RAY_MAJOR, TILE_ROWS)
 
 TORCH_DTYPE = {NVSR_F32: torch.float32, NVSR_BF16: torch.bfloat16, NVSR_F16: torch.float16}
 FEAT_LAYOUT = {NVSR_F32: FEAT_ROWMAJOR_F32, NVSR_BF16: FEAT_TILE_BF16, NVSR_F16: FEAT_TILE_F16}
 LAYOUT_DTYPE = {FEAT_TILE_BF16: torch.bfloat16, FEAT_TILE_F16: torch.float16}
+# row order of the rows a feature layout carries (include/nvsr.h): the 16-bit tile images written by the
+# gather are BLOCKED (8 adjacent rays x 16 samples per 128-row tile), everything fp32 is ray-major
+LAYOUT_ROWS = {FEAT_ROWMAJOR_F32: ROWS_RAY_MAJOR, FEAT_TILE_BF16: ROWS_BLOCKED, FEAT_TILE_F16: ROWS_BLOCKED}
+
+
+def rows_padded(n_rays, n_samples, row_order):
+    """rows a feature/raw buffer holds for n_rays x n_samples points in `row_order` (nvsr_rows_padded)."""
+    if row_order == ROWS_BLOCKED:
+        return -(-n_rays // BLK_RAYS) * -(-n_samples // BLK_SAMPLES) * TILE_ROWS
+    return n_rays * n_samples
+
+
+def raw_buffer(n_rays, n_samples, row_order, device):
+    """planar raw [4, stride] for the decoder heads (stride padded to whole tiles)"""
+    rows = rows_padded(n_rays, n_samples, row_order)
+    stride = (rows + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS
+    return torch.empty((4, stride), dtype=torch.float32, device=device)
+
+
+def raw_to_nsc(raw, n_rays, n_samples, row_order):
+    """planar raw [4, stride] in `row_order` -> the reference's radiance_field layout [N, S, 4]"""
+    if row_order == ROWS_RAY_MAJOR:
+        return raw[:, :n_rays * n_samples].t().reshape(n_rays, n_samples, 4)
+    nb, ts = -(-n_rays // BLK_RAYS), -(-n_samples // BLK_SAMPLES)
+    r = raw[:, :nb * ts * TILE_ROWS].reshape(4, nb, ts, BLK_SAMPLES, BLK_RAYS)   # [ch, block, sblock, s%16, ray%8]
+    r = r.permute(1, 4, 2, 3, 0).reshape(nb * BLK_RAYS, ts * BLK_SAMPLES, 4)
+    return r[:n_rays, :n_samples]
 
 
 def _stream():
@@ -176,12 +204,13 @@ class PackedPlanes:
         return s
 
 
-def feature_buffers(rows, channels, layout, device):
-    """Allocate (featP, featM) for `rows` rows in the given layout."""
+def feature_buffers(n_rays, n_samples, channels, layout, device):
+    """Allocate (featP, featM) for n_rays x n_samples points in the given layout."""
+    rows = rows_padded(n_rays, n_samples, LAYOUT_ROWS[layout])
     if layout == FEAT_ROWMAJOR_F32:
         return (torch.empty((rows, 3 * channels), dtype=torch.float32, device=device),
                 torch.empty((rows, channels), dtype=torch.float32, device=device))
-    tiles = (rows + TILE_ROWS - 1) // TILE_ROWS
+    tiles = rows // TILE_ROWS
     dt = LAYOUT_DTYPE[layout]
     return (torch.empty((tiles, 3 * channels // 8, TILE_ROWS, 8), dtype=dt, device=device),
             torch.empty((tiles, channels // 8, TILE_ROWS, 8), dtype=dt, device=device))
@@ -202,7 +231,7 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
         t_vals = _f32c(t_vals)
     rows = n * S
     if out is None:
-        out = feature_buffers(rows, packed.channels, layout, ro.device)
+        out = feature_buffers(n, S, packed.channels, layout, ro.device)
     feat_p, feat_m = out
     z_out = torch.empty((n, S), dtype=torch.float32, device=ro.device) if (want_z and z_in is None) else None
     s = _lib.Sampler()
@@ -264,8 +293,9 @@ class ChainLayer:
         self.row_bias, self.head_w, self.head_b, self.head_ch = row_bias, head_w, head_b, head_ch
 
 
-def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1):
-    """Evaluate one decoder chain (models.py:393-421 / :85-108) over `rows` rows into planar raw [4,stride]."""
+def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, row_order=ROWS_RAY_MAJOR):
+    """Evaluate one decoder chain (models.py:393-421 / :85-108) over `rows` rows into planar raw [4,stride].
+    `rows` counts the rows of the input buffer (padded rows included for ROWS_BLOCKED)."""
     lib = _lib.load()
     m = _lib.Mlp()
     m.precision = precision
@@ -288,6 +318,7 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1):
     m.n_rays = n_rays
     m.raw = raw.data_ptr()
     m.raw_stride = raw.stride(0)
+    m.row_order = row_order
     with torch.cuda.device(raw.device):
         st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows,
                    # true MACs x2 only (no padding): layers + heads
@@ -301,7 +332,7 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1):
 
 # ---------------------------------------------------------------------------------------------
 def composite(raw, z, rd, n_samples, noise=None, white_background=False, mip=False, n_fine=0, u=None,
-              want_weights=False, want_inds=False, want_samples=False):
+              want_weights=False, want_inds=False, want_samples=False, row_order=ROWS_RAY_MAJOR):
     """volume_render_radiance_field (+ sample_pdf and the sort-merge on the coarse pass).
 
     raw: planar [4, stride] (r,g,b,sigma).  Returns a dict with rgb/disp/acc/depth and, optionally,
@@ -311,7 +342,7 @@ def composite(raw, z, rd, n_samples, noise=None, white_background=False, mip=Fal
     dev = rd.device
     c = _lib.Composite()
     c.n_rays, c.n_samples = n, n_samples
-    c.raw, c.raw_stride = raw.data_ptr(), raw.stride(0)
+    c.raw, c.raw_stride, c.row_order = raw.data_ptr(), raw.stride(0), row_order
     z = _f32c(z)
     rd = _f32c(rd)
     c.z, c.rd = z.data_ptr(), rd.data_ptr()

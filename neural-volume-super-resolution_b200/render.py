@@ -53,11 +53,6 @@ def _t_vals(n, device):
     return torch.linspace(0.0, 1.0, n).to(device=device, dtype=torch.float32)
 
 
-def _raw_buffer(rows, device):
-    stride = (rows + 127) // 128 * 128
-    return torch.empty((4, stride), dtype=torch.float32, device=device)
-
-
 def _slice(t, i0, i1):
     return None if t is None else t[i0:i1]
 
@@ -98,19 +93,20 @@ class _PlanesPass:
         scene.check_supported_planes_model(model)
         self.precision = precision
         self.layout = ops.FEAT_LAYOUT[precision]
+        self.rows = ops.LAYOUT_ROWS[self.layout]
         self.planes = scene.pack_scene_planes(model, scene_id, precision)
         self.dec = scene.pack_planes_decoder(model, precision)
 
     def radiance(self, ro, rd, vfeat, near, far, lindisp, S, t_vals=None, z_in=None, t_rand=None):
         """-> (raw planar [4,stride], z [n,S])"""
         n = ro.shape[0]
-        rows = n * S
+        rows = ops.rows_padded(n, S, self.rows)
         fp, fm, z = ops.sample_gather(ro, rd, near, far, self.planes, self.layout, t_vals=t_vals, z_in=z_in,
                                       t_rand=t_rand, lindisp=lindisp)
         rbias = ops.row_bias(vfeat, self.dec.view_w, self.dec.view_b)
-        raw = _raw_buffer(rows, ro.device)
-        ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n)
-        ops.mlp_chain(fp, self.dec.rgb_chain(rbias), rows, raw, self.precision, S, n)
+        raw = ops.raw_buffer(n, S, self.rows, ro.device)
+        ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n, self.rows)
+        ops.mlp_chain(fp, self.dec.rgb_chain(rbias), rows, raw, self.precision, S, n, self.rows)
         return raw, z
 
 
@@ -130,9 +126,10 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
             u = _t_vals(Nf, dev) if cfg.perturb == 0.0 else torch.rand([n, Nf]).to(dev)
     noise_c = _noise(randoms.get("noise_c"), cfg, n, Nc, dev)
     co = ops.composite(raw, z, rd, Nc, noise=noise_c, white_background=cfg.white_background, n_fine=Nf, u=u,
-                       want_weights=trace is not None, want_inds=trace is not None, want_samples=trace is not None)
+                       want_weights=trace is not None, want_inds=trace is not None, want_samples=trace is not None,
+                       row_order=pc.rows)
     if trace is not None:
-        trace.update(z_coarse=z, raw_coarse=raw[:, :n * Nc].t().reshape(n, Nc, 4), weights_coarse=co["weights"],
+        trace.update(z_coarse=z, raw_coarse=ops.raw_to_nsc(raw, n, Nc, pc.rows), weights_coarse=co["weights"],
                      depth_coarse=co["depth"])
     fo = None
     if Nf > 0:
@@ -141,10 +138,11 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
         vfeat_f = vfeat if pf.planes.vplane is pc.planes.vplane else ops.viewdir_gather(vd, pf.planes)
         raw_f, _ = pf.radiance(ro, rd, vfeat_f, near, far, cfg.lindisp, Nc + Nf, z_in=zf)
         noise_f = _noise(randoms.get("noise_f"), cfg, n, Nc + Nf, dev)
-        fo = ops.composite(raw_f, zf, rd, Nc + Nf, noise=noise_f, white_background=cfg.white_background)
+        fo = ops.composite(raw_f, zf, rd, Nc + Nf, noise=noise_f, white_background=cfg.white_background,
+                           row_order=pf.rows)
         if trace is not None:
             trace.update(inds=co["inds"], z_samples=co["z_samples"], z_fine=zf,
-                         raw_fine=raw_f[:, :n * (Nc + Nf)].t().reshape(n, Nc + Nf, 4), depth_fine=fo["depth"])
+                         raw_fine=ops.raw_to_nsc(raw_f, n, Nc + Nf, pf.rows), depth_fine=fo["depth"])
     return co, fo
 
 
@@ -169,7 +167,7 @@ class _MipPass:
         rows = n * S
         enc = ops.ipe(z_edges, ro, rd, radius, n_freqs, self.layout, self.dec.k0 if self.precision != NVSR_F32 else None)
         rbias = ops.row_bias(denc, self.dec.dir_w, self.dec.dir_b)
-        raw = _raw_buffer(rows, ro.device)
+        raw = ops.raw_buffer(n, S, ops.ROWS_RAY_MAJOR, ro.device)   # IPE rows are ray-major in every precision
         ops.mlp_chain(enc, self.dec.chain(rbias), rows, raw, self.precision, S, n)
         return raw
 

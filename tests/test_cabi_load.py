@@ -34,10 +34,30 @@ def test_library_exports_every_declared_symbol():
     assert b"invalid" in lib.nvsr_status_string(-1)
 
 
-def test_struct_sizes_match_c_layout():
-    # sizeof() of the ABI structs as compiled by g++/nvcc on LP64 (checked with a C program)
-    sizes = [ctypes.sizeof(x) for x in (_lib.Layer, _lib.Planes, _lib.Sampler, _lib.Mlp, _lib.Composite)]
-    assert sizes == [64, 152, 72, 568, 152]
+def test_struct_sizes_match_c_layout(tmp_path):
+    """sizeof/offsetof of the ABI structs as gcc lays them out from include/nvsr.h == the ctypes mirror."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = [("nvsr_layer_t", _lib.Layer, "head_ch"), ("nvsr_planes_t", _lib.Planes, "proj"),
+             ("nvsr_sampler_t", _lib.Sampler, "z_in"), ("nvsr_mlp_t", _lib.Mlp, "row_order"),
+             ("nvsr_composite_t", _lib.Composite, "z_merged")]
+    src = "#include <stdio.h>\n#include <stddef.h>\n#include \"nvsr.h\"\nint main(void){\n"
+    for cname, _, last in pairs:
+        src += f'printf("%zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));\n'
+    src += "return 0;}\n"
+    c = tmp_path / "sz.c"
+    c.write_text(src)
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, "-o", str(exe), str(c)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for (cname, ct, last), line in zip(pairs, out):
+        size, off = (int(v) for v in line.split())
+        field = {"in": "in_"}.get(last, last)
+        assert ctypes.sizeof(ct) == size, (cname, ctypes.sizeof(ct), size)
+        assert getattr(ct, field).offset == off, (cname, last)
 
 
 def test_no_cpu_fallback():

@@ -25,7 +25,7 @@ FP32_TOL = 1e-3
 # the few rays where sigma_last ~ 0; the resampling adds its own discontinuities.  The small
 # golden scenes use 16 coarse samples (0.25-long intervals, ~1 with lindisp), which amplify sigma rounding.
 TOL16_SMALL = {"bf16": (4e-2, 1.5e-2), "fp16": (6e-3, 2.5e-3)}
-TOL16_FULL = {"bf16": (1.5e-2, 5e-3), "fp16": (2e-3, 1e-3)}   # config-2 sized sampling (64+128)
+TOL16_FULL = {"bf16": (1.5e-2, 5e-3), "fp16": (3e-3, 1.2e-3)}   # config-2 sized sampling (64+128)
 
 
 def _stats16(out, ref):

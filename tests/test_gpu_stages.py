@@ -64,16 +64,21 @@ def _forward_points(model, sid, x6, precision):
     fp, fm, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, layout, z_in=torch.zeros(n, 1, device=DEV))
     vfeat = ops.viewdir_gather(x6[:, 3:].contiguous(), packed)
     rb = ops.row_bias(vfeat, dec.view_w, dec.view_b)
-    raw = torch.zeros(4, (n + 127) // 128 * 128, device=DEV)
-    ops.mlp_chain(fm, dec.density, n, raw, precision, 1, n)
-    ops.mlp_chain(fp, dec.rgb_chain(rb), n, raw, precision, 1, n)
-    return fp, fm, vfeat, raw[:, :n].t()
+    order = ops.LAYOUT_ROWS[layout]
+    rows = ops.rows_padded(n, 1, order)
+    raw = ops.raw_buffer(n, 1, order, DEV).zero_()
+    ops.mlp_chain(fm, dec.density, rows, raw, precision, 1, n, order)
+    ops.mlp_chain(fp, dec.rgb_chain(rb), rows, raw, precision, 1, n, order)
+    return fp, fm, vfeat, ops.raw_to_nsc(raw, n, 1, order)[:, 0, :]
 
 
-def _untile(img, rows):
-    """[tiles, K/8, 128, 8] bf16 tile image -> [rows, K] fp32"""
+def _untile(img, n_rays, n_samples=1):
+    """BLOCKED [tiles, K/8, 128, 8] 16-bit tile image -> [n_rays*n_samples, K] fp32 in ray-major order"""
     t, kc, r, e = img.shape
-    return img.permute(0, 2, 1, 3).reshape(t * r, kc * e)[:rows].float()
+    flat = img.permute(0, 2, 1, 3).reshape(t * r, kc * e).float()          # [padded rows, K], BLOCKED order
+    nb, ts = -(-n_rays // 8), -(-n_samples // 16)
+    x = flat.reshape(nb, ts, 16, 8, kc * e).permute(0, 3, 1, 2, 4).reshape(nb * 8, ts * 16, kc * e)
+    return x[:n_rays, :n_samples].reshape(n_rays * n_samples, kc * e)
 
 
 def test_planes_forward_fp32_golden():
@@ -236,13 +241,36 @@ def test_composite_resample_merge_properties():
         H.check_resampling(o["inds"], o["z_samples"], inds, smp, cdf, mid, u.cpu(), "composite resample")
 
 
+@pytest.mark.parametrize("n,S,nf", [(513, 64, 128), (37, 193, 0), (8, 16, 5), (1, 70, 0)])
+def test_composite_blocked_equals_ray_major(n, S, nf):
+    """The BLOCKED raw order (8 rays x 16 samples per tile, what the tcgen05 decoder writes) must give
+    bit-identical maps, indices and merged depths to the ray-major order, ragged sizes included."""
+    torch.manual_seed(5)
+    z = torch.sort(torch.rand(n, S) * 4 + 2, -1)[0].to(DEV)
+    rf = (torch.randn(n, S, 4) * 3).to(DEV)
+    rd = torch.randn(n, 3).to(DEV)
+    u = torch.linspace(0, 1, nf).to(DEV) if nf else None
+    raw_rm = ops.raw_to_planar(rf)
+    nb, ts = -(-n // 8), -(-S // 16)
+    pad = torch.full((nb * 8, ts * 16, 4), float("nan"), device=DEV)       # padding rows must never be read
+    pad[:n, :S] = rf
+    raw_bl = pad.reshape(nb, 8, ts, 16, 4).permute(4, 0, 2, 3, 1).reshape(4, -1).contiguous()
+    assert torch.equal(ops.raw_to_nsc(raw_bl, n, S, ops.ROWS_BLOCKED), rf)
+    kw = dict(n_fine=nf, u=u, want_samples=nf > 0, want_inds=nf > 0, want_weights=True)
+    a = ops.composite(raw_rm, z, rd, S, row_order=ops.ROWS_RAY_MAJOR, **kw)
+    b = ops.composite(raw_bl, z, rd, S, row_order=ops.ROWS_BLOCKED, **kw)
+    for k in a:
+        assert torch.equal(a[k], b[k]) or (k == "disp" and torch.equal(torch.nan_to_num(a[k], 7.0), torch.nan_to_num(b[k], 7.0))), k
+
+
 def test_ipe_golden():
     g = golden("stage_ipe.npz")
     enc = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6)
     H.assert_close(enc, g["enc"].reshape(-1, 36), 5e-6, what="ipe")
     for layout, tol in ((FEAT_TILE_BF16, 4e-3), (FEAT_TILE_F16, 5e-4)):
         tile = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6, layout, 48)
-        un = _untile(tile, 180)
+        t_, kc_, r_, e_ = tile.shape   # IPE tile images are ray-major
+        un = tile.permute(0, 2, 1, 3).reshape(t_ * r_, kc_ * e_)[:180].float()
         H.assert_close(un[:, :36], g["enc"].reshape(-1, 36), tol, what="ipe 16-bit tile")
         assert float(un[:, 36:].abs().max()) == 0.0
     H.assert_close(ops.dir_encoding(T(g["viewdirs"], DEV), 4, True), g["dir_enc"], 2e-6, what="dir enc")
