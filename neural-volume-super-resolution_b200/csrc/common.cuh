@@ -92,14 +92,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires, so a
+// waiting warp costs (almost) no issue slots; it wakes as soon as the phase flips.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -108,18 +110,23 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Spin on the barrier phase.  A protocol bug must surface as a launch failure, never as a hung GPU:
+// Wait on the barrier phase.  A protocol bug must surface as a launch failure, never as a hung GPU:
 // after ~4 s without progress the kernel traps (cudaErrorLaunchFailure on the host).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfffu) == 0) {
+    if ((++spins & 0x3ffu) == 0) {
       uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000ull) __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;   // fast path: already complete / completes within the hint
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ---- bulk async copies (TMA engine, no tensor map) --------------------------------------------

@@ -2,21 +2,24 @@
 // activations in TMEM).
 //
 // Persistent kernel, one CTA per SM, cta_group::1, UMMA M=128 (one 128-row tile), N = layer width.
-//   warp 0 (1 lane)  : producer — bulk-copies (TMA engine) the chain's 16-bit weights into shared
-//                      memory once, then one feature tile image per tile into a 2-deep ring
-//   warp 1 (1 lane)  : MMA issuer — layer 0: A = feature tile in smem (SS form); hidden layers: A =
-//                      previous layer's activations in TMEM (TS form); B = resident weights in smem;
-//                      D = fp32 accumulator in TMEM; completion committed to an mbarrier
-//   warps 2..17      : epilogue — tcgen05.ld the accumulator (warp w owns TMEM lanes 32*(w%4)..+31,
-//                      i.e. 32 rows, and one quarter of the layer's columns), + bias (smem, or per-ray
-//                      from global), ReLU + saturate + 16-bit pack in ONE F2FP per pair, tcgen05.st
-//                      the packed row back into TMEM as the next layer's A operand.  Output heads
-//                      (128 -> 1 / 3) are fp32 dot products on the CUDA cores over the UNROUNDED
-//                      last activations.
-// Two tiles ("slots") are in flight and ping-pong: while the epilogue warps work on slot A's layer l,
-// the tensor core runs slot B's layer l.  Hidden activations never leave the SM (never even touch
-// shared memory); weights are read from HBM/L2 once per CTA; the feature ring slot is released as
-// soon as layer 0's MMAs have been committed.
+// Two tiles ("slots") are in flight, each with its OWN issuer warp and epilogue warps, so the slots
+// advance independently and the tensor core runs one slot's layer while the other slot is in its
+// epilogue:
+//   warp 0 (1 lane)   : producer — bulk-copies (TMA engine) the chain's 16-bit weights into shared
+//                       memory once, then per tile one feature tile image into the slot's ring
+//                       buffer and (for a layer with a per-ray bias) the tile's <= 8 bias rows
+//   warp 1+s (1 lane) : MMA issuer of slot s — layer 0: A = feature tile in smem (SS form); hidden
+//                       layers: A = previous activations in TMEM (TS form); B = resident weights in
+//                       smem; D = fp32 accumulator in TMEM.  Every MMA ACCUMULATES: the epilogue
+//                       pre-loads D with the layer's bias, so no bias add is ever executed.
+//   warps 4+8s..+7    : epilogue of slot s — warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and
+//                       columns [64h, 64h+64): tcgen05.ld the accumulator, tcgen05.st the NEXT
+//                       layer's bias (smem broadcast rows, or the staged per-ray rows) into the same
+//                       columns, ReLU + saturate + 16-bit pack in ONE F2FP per pair, tcgen05.st the
+//                       packed row into the slot's A region.  Output heads (128 -> 1 / 3) are fp32
+//                       dot products on the CUDA cores over the UNROUNDED last activations.
+// Hidden activations never leave the SM (never even touch shared memory); weights are read from
+// HBM/L2 once per CTA; a ring buffer is released as soon as layer 0's MMAs have been committed.
 //
 // TMEM map (512 columns allocated): slot s -> D_s = [192 s, 192 s + 128) fp32 accumulator,
 // A_s = [192 s + 128, 192 s + 192): 128 rows x 128 16-bit activations, two per 32-bit column
@@ -30,9 +33,12 @@
 
 namespace nvsr {
 
-constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = 32 * (2 + kTcEpiWarps);
-constexpr int kTcMaxHeads = 2;
+constexpr int kTcEpiWarpsPerSlot = 8;
+constexpr int kTcFirstEpiWarp = 4;  // warps 0..3: producer, issuer slot 0, issuer slot 1, spare
+constexpr int kTcThreads = 32 * (kTcFirstEpiWarp + 2 * kTcEpiWarpsPerSlot);
+constexpr int kTcMaxHeadRows = 4;   // total head outputs of a chain (r,g,b,sigma)
+constexpr int kRbRowsMax = 8;       // staged per-ray bias rows per tile
+constexpr int kRbPitch = 132;       // floats per staged row (528 B: conflict-free for 8 rows)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSlotCols = 192;  // D (128 fp32 columns) + A (64 columns of packed 16-bit pairs)
 constexpr uint32_t kSlotAOff = 128;
@@ -43,7 +49,7 @@ struct TcLayer {
   const float* row_bias;  // global per-ray or null
   const float* head_w;
   const float* head_b;
-  int k, n, relu, head_n, head_ch, head_slot;
+  int k, n, relu, head_n, head_ch, head_row;  // head_row: first row of this head in the smem head table
   uint32_t w_off;         // smem byte offset of the weight image
 };
 
@@ -57,8 +63,10 @@ struct TcArgs {
   int64_t n_rays;
   float* raw;
   int64_t raw_stride;
+  int rb_layer;           // layer with a per-ray bias (-1: none)
+  int rb_staged;          // 1: the producer stages the tile's bias rows in smem (BLOCKED order)
   // smem carve-up (byte offsets from the 1024-aligned base)
-  uint32_t in_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total;
+  uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total;
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------
@@ -136,6 +144,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // (ReLU +) saturate-to-finite + round + pack two fp32 into one 16-bit pair: a single F2FP
@@ -149,8 +168,24 @@ __device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
   return r;
 }
 
-// barrier block layout (uint64_t each)
-enum { BAR_W = 0, BAR_IN_FULL = 1, BAR_IN_FREE = 3, BAR_ACC_FULL = 5, BAR_ACT_READY = 7, BAR_ACC_FREE = 9, BAR_COUNT = 11 };
+// barrier block layout (uint64_t each, [2] = one per slot)
+enum {
+  BAR_W = 0, BAR_IN_FULL = 1, BAR_IN_FREE = 3, BAR_ACC_FULL = 5, BAR_ACT_READY = 7, BAR_ACC_FREE = 9,
+  BAR_RB_FULL = 11, BAR_RB_FREE = 13, BAR_COUNT = 15
+};
+
+// bias values of `layer` for the 32 columns [col, col+32) of this thread's row -> v (as raw bits)
+//   staged rows : smem [8][kRbPitch], row = r_local        (per-ray bias, BLOCKED order)
+//   global rows : row_bias[ray]                            (per-ray bias, RAY_MAJOR order)
+//   otherwise   : the layer's bias vector in smem (broadcast)
+__device__ __forceinline__ void load_bias32(const float* src, uint32_t (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 b4 = *reinterpret_cast<const float4*>(src + 4 * j);
+    v[4 * j + 0] = __float_as_uint(b4.x), v[4 * j + 1] = __float_as_uint(b4.y);
+    v[4 * j + 2] = __float_as_uint(b4.z), v[4 * j + 3] = __float_as_uint(b4.w);
+  }
+}
 
 template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -159,8 +194,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   float* sbias = reinterpret_cast<float*>(smem + a.bias_off);    // [n_layers][128]
-  float* sheadw = reinterpret_cast<float*>(smem + a.headw_off);  // [kTcMaxHeads][4][128]
-  float* shpart = reinterpret_cast<float*>(smem + a.hpart_off);  // [2 parity][3 quarters][128 rows][4]
+  float* sheadw = reinterpret_cast<float*>(smem + a.headw_off);  // [kTcMaxHeadRows][128]
+  float* shpart = reinterpret_cast<float*>(smem + a.hpart_off);  // [2 slots][128 rows][4]: half 1 -> half 0
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.n_layers;
@@ -173,8 +208,10 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       mbar_init(&bars[BAR_IN_FULL + s], 1);
       mbar_init(&bars[BAR_IN_FREE + s], 1);
       mbar_init(&bars[BAR_ACC_FULL + s], 1);
-      mbar_init(&bars[BAR_ACT_READY + s], kTcEpiWarps);
-      mbar_init(&bars[BAR_ACC_FREE + s], kTcEpiWarps);
+      mbar_init(&bars[BAR_ACT_READY + s], kTcEpiWarpsPerSlot);
+      mbar_init(&bars[BAR_ACC_FREE + s], kTcEpiWarpsPerSlot);
+      mbar_init(&bars[BAR_RB_FULL + s], 1);
+      mbar_init(&bars[BAR_RB_FREE + s], kTcEpiWarpsPerSlot);
     }
     mbar_fence_init();
   }
@@ -185,14 +222,14 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     const TcLayer& ly = a.layer[l];
     sbias[i] = (n < ly.n && ly.bias) ? __ldg(ly.bias + n) : 0.f;
   }
-  for (int i = threadIdx.x; i < kTcMaxHeads * 4 * 128; i += kTcThreads) sheadw[i] = 0.f;
+  for (int i = threadIdx.x; i < kTcMaxHeadRows * 128; i += kTcThreads) sheadw[i] = 0.f;
   __syncthreads();
   for (int l = 0; l < L; ++l) {
     const TcLayer& ly = a.layer[l];
     if (ly.head_w) {
       for (int i = threadIdx.x; i < ly.head_n * ly.n; i += kTcThreads) {
         int h = i / ly.n, n = i - h * ly.n;
-        sheadw[(ly.head_slot * 4 + h) * 128 + n] = __ldg(ly.head_w + i);
+        sheadw[(ly.head_row + h) * 128 + n] = __ldg(ly.head_w + i);
       }
     }
   }
@@ -209,6 +246,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         const TcLayer& ly = a.layer[l];
         bulk_g2s(smem + ly.w_off, ly.w, (uint32_t)(ly.k * ly.n * 2), &bars[BAR_W]);
       }
+      const float* rbg = a.rb_staged ? a.layer[a.rb_layer].row_bias : nullptr;
+      const int rbn = a.rb_staged ? a.layer[a.rb_layer].n : 0;
       for (int64_t it = 0;; ++it) {
         int64_t tile = blockIdx.x + it * G;
         if (tile >= a.n_tiles) break;
@@ -217,171 +256,216 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         mbar_wait(&bars[BAR_IN_FREE + s], (use & 1) ^ 1);
         mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], a.in_bytes);
         bulk_g2s(smem + a.in_off[s], a.in + tile * (int64_t)a.in_bytes, a.in_bytes, &bars[BAR_IN_FULL + s]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      mbar_wait(&bars[BAR_W], 0);
-      uint32_t ph_act[2] = {0, 0};
-      for (int64_t p = 0;; ++p) {
-        bool valid[2];
-        valid[0] = blockIdx.x + (2 * p) * G < a.n_tiles;
-        valid[1] = blockIdx.x + (2 * p + 1) * G < a.n_tiles;
-        if (!valid[0]) break;
-        for (int l = 0; l < L; ++l) {
-          const TcLayer& ly = a.layer[l];
-          const uint32_t idesc = umma_idesc_16(ly.n, F16);
-          const uint32_t b_lbo = (uint32_t)ly.n * 16u;
-          const uint32_t b_base = smem_u32(smem + ly.w_off);
-          const int ksteps = ly.k >> 4;
-          for (int s = 0; s < 2; ++s) {
-            if (!valid[s]) continue;
-            const uint32_t d_tmem = tmem_base + (uint32_t)s * kSlotCols;
-            if (l == 0) {
-              mbar_wait(&bars[BAR_IN_FULL + s], (uint32_t)(p & 1));
-              mbar_wait(&bars[BAR_ACC_FREE + s], (uint32_t)(p & 1) ^ 1);
-              tc_fence_after();
-              const uint32_t a_base = smem_u32(smem + a.in_off[s]);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                uint64_t ad = umma_desc(a_base + (uint32_t)ks * 2u * 2048u, 2048u, 128u);
-                uint64_t bd = umma_desc(b_base + (uint32_t)ks * 2u * b_lbo, b_lbo, 128u);
-                umma_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-              }
-              umma_commit(&bars[BAR_IN_FREE + s]);  // ring slot reusable once these MMAs have read it
-            } else {
-              mbar_wait(&bars[BAR_ACT_READY + s], ph_act[s]);
-              ph_act[s] ^= 1;
-              tc_fence_after();
-              const uint32_t a_tmem = d_tmem + kSlotAOff;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                uint64_t bd = umma_desc(b_base + (uint32_t)ks * 2u * b_lbo, b_lbo, 128u);
-                umma_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, bd, idesc, ks > 0 ? 1u : 0u);
-              }
-            }
-            umma_commit(&bars[BAR_ACC_FULL + s]);
-          }
+        if (rbg) {
+          // the tile's 8 rays (BLOCKED order) are consecutive rows of row_bias
+          int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays;
+          int64_t left = a.n_rays - ray0;
+          int cnt = left >= kRbRowsMax ? kRbRowsMax : (int)left;
+          mbar_wait(&bars[BAR_RB_FREE + s], (use & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], (uint32_t)(cnt * rbn * 4));
+          float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
+          for (int j = 0; j < cnt; ++j)
+            bulk_g2s(dst + j * kRbPitch, rbg + (ray0 + j) * rbn, (uint32_t)(rbn * 4), &bars[BAR_RB_FULL + s]);
         }
       }
     }
     __syncwarp();
-  } else {
-    // ================= epilogue =================
-    const int ew = warp - 2;
-    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-    const int qtr = ew >> 2;              // which quarter of the layer's columns
-    const int r = quad * 32 + lane;       // row within the tile == TMEM lane
-    const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
-    uint32_t ph_acc[2] = {0, 0};
-    uint32_t head_parity = 0;
-    for (int64_t p = 0;; ++p) {
-      int64_t tile_of[2] = {blockIdx.x + (2 * p) * G, blockIdx.x + (2 * p + 1) * G};
-      bool valid[2] = {tile_of[0] < a.n_tiles, tile_of[1] < a.n_tiles};
-      if (!valid[0]) break;
+  } else if (warp == 1 || warp == 2) {
+    // ================= MMA issuer of slot s (warp-uniform control flow, one elected lane issues) ======
+    const int s = warp - 1;
+    mbar_wait(&bars[BAR_W], 0);
+    const uint32_t d_tmem = tmem_base + (uint32_t)s * kSlotCols;
+    const uint32_t a_tmem = d_tmem + kSlotAOff;
+    const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
+    uint32_t ph_act = 0;
+    for (uint32_t use = 0;; ++use) {
+      if (blockIdx.x + (int64_t)(2 * use + s) * G >= a.n_tiles) break;
       for (int l = 0; l < L; ++l) {
         const TcLayer& ly = a.layer[l];
-        const bool last = l == L - 1;
-        // 32 columns per warp: a 128-wide layer uses all four quarters, a 64-wide one the first two
-        const int col = qtr * 32;
-        const bool active = col < ly.n;
-        for (int s = 0; s < 2; ++s) {
-          if (!valid[s]) continue;
-          const int64_t row = tile_of[s] * kTileRows + r;
-          const uint32_t d_tmem = tmem_base + lane_field + (uint32_t)s * kSlotCols;
-          mbar_wait(&bars[BAR_ACC_FULL + s], ph_acc[s]);
-          ph_acc[s] ^= 1;
+        const uint32_t idesc = umma_idesc_16(ly.n, F16);
+        const uint32_t b_lbo = (uint32_t)ly.n * 16u;
+        const uint64_t bdesc0 = umma_desc(smem_u32(smem + ly.w_off), b_lbo, 128u);
+        const uint32_t b_step = (2u * b_lbo) >> 4;  // descriptor address units per K step of 16
+        const int ksteps = ly.k >> 4;
+        if (l == 0) {
+          mbar_wait(&bars[BAR_IN_FULL + s], use & 1);
+          mbar_wait(&bars[BAR_ACC_FREE + s], use & 1);  // D_s holds this tile's layer-0 bias
           tc_fence_after();
-          float f[32];
-          if (active) {
-            uint32_t v[32];
-            tmem_ld32(d_tmem + (uint32_t)col, v);
-            tmem_ld_wait();
-            if (ly.row_bias) {
-              int64_t ray = a.row_order == NVSR_ROWS_BLOCKED
-                                ? (tile_of[s] / a.tiles_per_blk) * kBlkRays + (r & (kBlkRays - 1))
-                                : row / a.samples_per_ray;
-              if (ray >= a.n_rays) ray = a.n_rays - 1;
-              const float4* rb = reinterpret_cast<const float4*>(ly.row_bias + ray * ly.n + col);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 b4 = __ldg(rb + j);
-                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-              }
-            } else {
-              const float4* sb = reinterpret_cast<const float4*>(sbias + l * 128 + col);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 b4 = sb[j];
-                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-              }
-            }
+          if (elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_ss(d_tmem, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+            umma_commit(&bars[BAR_IN_FREE + s]);  // ring buffer reusable once these MMAs have read it
+            umma_commit(&bars[BAR_ACC_FULL + s]);
           }
-          if (last) {
-            // the accumulator has been read: the slot may start its next tile
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BAR_ACC_FREE + s]);
-          } else {
-            if (active) {
-              uint32_t pk[16];
-              if (ly.relu) {
+        } else {
+          mbar_wait(&bars[BAR_ACT_READY + s], ph_act);
+          ph_act ^= 1;
+          tc_fence_after();
+          if (elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+            umma_commit(&bars[BAR_ACC_FULL + s]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kTcFirstEpiWarp) {
+    // ================= epilogue of slot s =================
+    const int ew = warp - kTcFirstEpiWarp;
+    const int s = ew >> 3;
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (ew & 7) >> 2;       // column ownership: half h owns columns [64h, 64h+64) of every layer
+    const int r = quad * 32 + lane;       // row within the tile == TMEM lane
+    const int col0 = half * 64;
+    const uint32_t d_tmem = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * kSlotCols + (uint32_t)col0;
+    const uint32_t a_tmem = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * kSlotCols + kSlotAOff +
+                            (uint32_t)(col0 >> 1);
+    const float* rb_row = reinterpret_cast<const float*>(smem + a.rb_off[s]) + (r & (kBlkRays - 1)) * kRbPitch + col0;
+    float* hp = shpart + (s * 128 + r) * 4;
+    uint64_t* bar_acc_full = &bars[BAR_ACC_FULL + s];
+    uint64_t* bar_rb_full = &bars[BAR_RB_FULL + s];
+    uint64_t* bar_rb_free = &bars[BAR_RB_FREE + s];
+    const int rb_layer = a.rb_layer, rb_staged = a.rb_staged;
+    uint32_t ph_acc = 0, ph_rb = 0;
+
+    // bias of `layer` (tile `tile`) for this thread's row, columns col0 + [c, c+32) -> D_s
+    auto preload_bias = [&](int layer, int64_t tile, int c) {
+      uint32_t v[32];
+      if (layer != rb_layer) {
+        load_bias32(sbias + layer * 128 + col0 + c, v);
+      } else if (rb_staged) {
+        load_bias32(rb_row + c, v);
+      } else {
+        const TcLayer& ly = a.layer[layer];
+        int64_t row = tile * kTileRows + r;
+        int64_t ray = a.rows < 0x7fffffff ? (int64_t)((uint32_t)row / (uint32_t)a.samples_per_ray)
+                                          : row / a.samples_per_ray;
+        if (ray >= a.n_rays) ray = a.n_rays - 1;
+        const float4* g = reinterpret_cast<const float4*>(ly.row_bias + ray * ly.n + col0 + c);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(f[2 * j], f[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) {
+          float4 b4 = __ldg(g + j);
+          v[4 * j + 0] = __float_as_uint(b4.x), v[4 * j + 1] = __float_as_uint(b4.y);
+          v[4 * j + 2] = __float_as_uint(b4.z), v[4 * j + 3] = __float_as_uint(b4.w);
+        }
+      }
+      tmem_st32(d_tmem + (uint32_t)c, v);
+    };
+
+    // prologue: D_s <- layer-0 bias of the slot's first tile
+    const int64_t first = blockIdx.x + (int64_t)s * G;
+    if (first < a.n_tiles) {
+      const bool rb0 = rb_layer == 0 && rb_staged;
+      if (rb0) {
+        mbar_wait(bar_rb_full, ph_rb);
+        ph_rb ^= 1;
+      }
+      for (int c = 0; c < 64; c += 32)
+        if (col0 + c < a.layer[0].n) preload_bias(0, first, c);
+      if (rb0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_rb_free);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_ACC_FREE + s]);
+    }
+
+    for (uint32_t use = 0;; ++use) {
+      const int64_t tile = blockIdx.x + (int64_t)(2 * use + s) * G;
+      if (tile >= a.n_tiles) break;
+      const int64_t next_tile = tile + 2 * G;
+      const bool next_valid = next_tile < a.n_tiles;
+      for (int l = 0; l < L; ++l) {
+        // ---- everything that does not depend on the accumulator: done before the wait ----
+        const TcLayer& ly = a.layer[l];
+        const bool last = l == L - 1;
+        const int n_cur = ly.n, relu = ly.relu;
+        const int head_n = ly.head_w ? ly.head_n : 0;
+        const int head_ch = ly.head_ch;
+        const float* hw = sheadw + ly.head_row * 128 + col0;
+        const float* head_b = ly.head_b;
+        // what gets pre-loaded into D_s once this layer's accumulator has been read
+        const int nl = last ? 0 : l + 1;
+        const int n_next = (last && !next_valid) ? 0 : a.layer[nl].n;
+        const int64_t nl_tile = last ? next_tile : tile;
+        const bool nl_rb = n_next > 0 && nl == rb_layer && rb_staged;
+        uint64_t* bar_done = &bars[(last ? BAR_ACC_FREE : BAR_ACT_READY) + s];
+        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (nl_rb) {
+          mbar_wait(bar_rb_full, ph_rb);
+          ph_rb ^= 1;
+        }
+        mbar_wait(bar_acc_full, ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          if (col0 + c < n_cur) {
+            uint32_t v[32];
+            tmem_ld32(d_tmem + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (!last) {
+              uint32_t pk[16];
+              if (relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  pk[j] = pack_act<F16, true>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
               } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, false>(f[2 * j], f[2 * j + 1]);
+                for (int j = 0; j < 16; ++j)
+                  pk[j] = pack_act<F16, false>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
               }
-              tmem_st16(d_tmem + kSlotAOff + (uint32_t)(col >> 1), pk);
-              tmem_st_wait();
+              tmem_st16(a_tmem + (uint32_t)(c >> 1), pk);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BAR_ACT_READY + s]);
-          }
-          if (ly.head_w) {
-            float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (active) {
-              if (ly.relu) {
+            if (head_n > 0) {
+              if (relu) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
               }
-              const float* hw = sheadw + (ly.head_slot * 4) * 128 + col;
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
-                if (h < ly.head_n) {
+                if (h < head_n) {
+                  const float4* hw4 = reinterpret_cast<const float4*>(hw + h * 128 + c);
+                  float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    float4 w4 = *reinterpret_cast<const float4*>(hw + h * 128 + j);
-                    hacc[h] = fmaf(f[j + 0], w4.x, hacc[h]);
-                    hacc[h] = fmaf(f[j + 1], w4.y, hacc[h]);
-                    hacc[h] = fmaf(f[j + 2], w4.z, hacc[h]);
-                    hacc[h] = fmaf(f[j + 3], w4.w, hacc[h]);
+                  for (int j = 0; j < 8; ++j) {
+                    float4 w4 = hw4[j];
+                    acc0 = fmaf(__uint_as_float(v[4 * j + 0]), w4.x, acc0);
+                    acc1 = fmaf(__uint_as_float(v[4 * j + 1]), w4.y, acc1);
+                    acc0 = fmaf(__uint_as_float(v[4 * j + 2]), w4.z, acc0);
+                    acc1 = fmaf(__uint_as_float(v[4 * j + 3]), w4.w, acc1);
                   }
+                  hacc[h] += acc0 + acc1;
                 }
               }
             }
-            // combine the four column quarters of a row: quarters 1..3 -> smem -> quarter 0
-            float* hp = shpart + head_parity * (3 * 128 * 4);
-            if (qtr > 0)
-              *reinterpret_cast<float4*>(hp + ((qtr - 1) * 128 + r) * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
-            named_bar_sync(1 + quad, 4 * 32);  // the four warps that share this lane quadrant
-            if (qtr == 0 && row < a.rows) {
-              float4 o1 = *reinterpret_cast<const float4*>(hp + (0 * 128 + r) * 4);
-              float4 o2 = *reinterpret_cast<const float4*>(hp + (1 * 128 + r) * 4);
-              float4 o3 = *reinterpret_cast<const float4*>(hp + (2 * 128 + r) * 4);
-              float hv[4] = {(hacc[0] + o1.x) + (o2.x + o3.x), (hacc[1] + o1.y) + (o2.y + o3.y),
-                             (hacc[2] + o1.z) + (o2.z + o3.z), (hacc[3] + o1.w) + (o2.w + o3.w)};
-              for (int h = 0; h < ly.head_n; ++h)
-                a.raw[(int64_t)(ly.head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(ly.head_b + h);
-            }
-            head_parity ^= 1;
+          }
+          // the next accumulation into these columns starts from its bias
+          if (col0 + c < n_next) preload_bias(nl, nl_tile, c);
+        }
+        if (nl_rb) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_rb_free);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_done);
+
+        if (head_n > 0) {
+          // combine the two column halves of a row: half 1 -> smem -> half 0
+          if (half == 1) *reinterpret_cast<float4*>(hp) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+          named_bar_sync(1 + s * 4 + quad, 64);  // the two warps sharing this slot and lane quadrant
+          const int64_t row = tile * kTileRows + r;
+          if (half == 0 && row < a.rows) {
+            float4 o = *reinterpret_cast<const float4*>(hp);
+            float hv[4] = {hacc[0] + o.x, hacc[1] + o.y, hacc[2] + o.z, hacc[3] + o.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+              if (h < head_n) a.raw[(int64_t)(head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(head_b + h);
           }
         }
       }
@@ -400,8 +484,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   TcArgs a;
   a.n_layers = m->n_layers;
+  a.rb_layer = -1;
   uint32_t off = 0;
-  int heads = 0;
+  int head_rows = 0;
   for (int l = 0; l < m->n_layers; ++l) {
     const nvsr_layer_t& L = m->layer[l];
     if (L.k <= 0 || (L.k % 16) != 0 || L.k > 256) return NVSR_ERR_UNSUPPORTED;
@@ -410,13 +495,20 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
     if (!L.w || (!L.bias && !L.row_bias)) return NVSR_ERR_INVALID_ARG;
     if (!aligned16(L.w) || (L.row_bias && !aligned16(L.row_bias))) return NVSR_ERR_ALIGNMENT;
     if (l > 0 && L.k != m->layer[l - 1].n_out) return NVSR_ERR_INVALID_ARG;
+    if (L.row_bias) {
+      if (a.rb_layer >= 0) return NVSR_ERR_UNSUPPORTED;  // one per-ray bias layer per chain
+      a.rb_layer = l;
+    }
     TcLayer& t = a.layer[l];
     t.w = L.w, t.bias = L.bias, t.row_bias = L.row_bias, t.head_w = L.head_w, t.head_b = L.head_b;
-    t.k = L.k, t.n = L.n_out, t.relu = L.relu, t.head_n = L.head_n, t.head_ch = L.head_ch, t.head_slot = 0;
+    t.k = L.k, t.n = L.n_out, t.relu = L.relu, t.head_n = L.head_n, t.head_ch = L.head_ch, t.head_row = 0;
     if (L.head_w) {
       if (L.head_n <= 0 || L.head_n > 4 || !L.head_b || L.head_ch < 0 || L.head_ch + L.head_n > 4) return NVSR_ERR_INVALID_ARG;
-      if (heads >= kTcMaxHeads) return NVSR_ERR_UNSUPPORTED;
-      t.head_slot = heads++;
+      if (head_rows + L.head_n > kTcMaxHeadRows) return NVSR_ERR_UNSUPPORTED;
+      t.head_row = head_rows;
+      head_rows += L.head_n;
+    } else {
+      t.head_n = 0;
     }
     t.w_off = off;
     off += (uint32_t)(L.k * L.n_out * 2);
@@ -426,9 +518,15 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   const uint32_t in_bytes = (uint32_t)m->layer[0].k * 256u;  // 128 rows * K * 2 B
   a.in_off[0] = off, off += in_bytes;
   a.in_off[1] = off, off += in_bytes;
+  a.rb_staged = (a.rb_layer >= 0 && m->row_order == NVSR_ROWS_BLOCKED) ? 1 : 0;
+  a.rb_off[0] = a.rb_off[1] = off;
+  if (a.rb_staged) {
+    a.rb_off[1] = off + kRbRowsMax * kRbPitch * 4u;
+    off += 2u * kRbRowsMax * kRbPitch * 4u;
+  }
   a.bias_off = off, off += (uint32_t)m->n_layers * 128u * 4u;
-  a.headw_off = off, off += kTcMaxHeads * 4u * 128u * 4u;
-  a.hpart_off = off, off += 2u * 3u * 128u * 4u * 4u;
+  a.headw_off = off, off += kTcMaxHeadRows * 128u * 4u;
+  a.hpart_off = off, off += 2u * 128u * 4u * 4u;
   a.bar_off = off, off += BAR_COUNT * 8u + 16u;
   const uint32_t smem_bytes = off;
   if (smem_bytes > 227u * 1024u) return NVSR_ERR_RESOURCE;
