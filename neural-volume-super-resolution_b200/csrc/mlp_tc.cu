@@ -2,22 +2,22 @@
 // activations in TMEM).
 //
 // Persistent kernel, one CTA per SM, cta_group::1, UMMA M=128 (one 128-row tile), N = layer width.
-// Two tiles ("slots") are in flight, each with its OWN issuer warp and epilogue warps, so the slots
-// advance independently and the tensor core runs one slot's layer while the other slot is in its
-// epilogue:
-//   warp 0 (1 lane)   : producer — bulk-copies (TMA engine) the chain's 16-bit weights into shared
-//                       memory once, then per tile one feature tile image into the slot's ring
-//                       buffer and (for a layer with a per-ray bias) the tile's <= 8 bias rows
-//   warp 1+s (1 lane) : MMA issuer of slot s — layer 0: A = feature tile in smem (SS form); hidden
-//                       layers: A = previous activations in TMEM (TS form); B = resident weights in
-//                       smem; D = fp32 accumulator in TMEM.  Every MMA ACCUMULATES: the epilogue
-//                       pre-loads D with the layer's bias, so no bias add is ever executed.
-//   warps 4+8s..+7    : epilogue of slot s — warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and
-//                       columns [64h, 64h+64): tcgen05.ld the accumulator, tcgen05.st the NEXT
-//                       layer's bias (smem broadcast rows, or the staged per-ray rows) into the same
-//                       columns, ReLU + saturate + 16-bit pack in ONE F2FP per pair, tcgen05.st the
-//                       packed row into the slot's A region.  Output heads (128 -> 1 / 3) are fp32
-//                       dot products on the CUDA cores over the UNROUNDED last activations.
+// Two tiles ("slots") are in flight, each owned by 8 warps, so the slots advance independently and
+// the tensor core runs one slot's layer while the other slot is in its epilogue.  There is no
+// producer warp and no MMA-issuer warp:
+//   epilogue (all 16 warps, 8 per slot): warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and columns
+//       [64h, 64h+64): tcgen05.ld the accumulator, ReLU + saturate + 16-bit pack in ONE F2FP per
+//       pair, tcgen05.st the packed row into the slot's A region, and tcgen05.st the NEXT layer's
+//       bias (smem broadcast rows, or the staged per-ray rows) into the accumulator columns just
+//       read — every MMA ACCUMULATES, so no bias add is ever executed.  Output heads (128 -> 1 / 3)
+//       are fp32 dot products on the CUDA cores over the UNROUNDED last activations.
+//   MMA issue: the LAST of a slot's 8 warps to finish a layer (shared-memory arrival counter) issues
+//       the next layer's tcgen05.mma itself from one elected lane — layer 0: A = feature tile in smem
+//       (SS form); hidden layers: A = previous activations in TMEM (TS form); B = resident weights
+//       in smem; D = fp32 accumulator in TMEM — and commits them to the slot's mbarrier.
+//   loads: weights are bulk-copied (TMA engine) into shared memory once; per tile ONE thread of the
+//       slot issues the bulk copies of the next feature tile image (and of its 8 per-ray bias rows)
+//       the moment layer 0's accumulator is complete — exactly when the ring buffer is free.
 // Hidden activations never leave the SM (never even touch shared memory); weights are read from
 // HBM/L2 once per CTA; a ring buffer is released as soon as layer 0's MMAs have been committed.
 //
@@ -34,8 +34,7 @@
 namespace nvsr {
 
 constexpr int kTcEpiWarpsPerSlot = 8;
-constexpr int kTcFirstEpiWarp = 4;  // warps 0..3: producer, issuer slot 0, issuer slot 1, spare
-constexpr int kTcThreads = 32 * (kTcFirstEpiWarp + 2 * kTcEpiWarpsPerSlot);
+constexpr int kTcThreads = 32 * 2 * kTcEpiWarpsPerSlot;  // 16 warps = 4 per scheduler -> 128 registers each
 constexpr int kTcMaxHeadRows = 4;   // total head outputs of a chain (r,g,b,sigma)
 constexpr int kRbRowsMax = 8;       // staged per-ray bias rows per tile
 constexpr int kRbPitch = 132;       // floats per staged row (528 B: conflict-free for 8 rows)
@@ -169,15 +168,8 @@ __device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
 }
 
 // barrier block layout (uint64_t each, [2] = one per slot)
-enum {
-  BAR_W = 0, BAR_IN_FULL = 1, BAR_IN_FREE = 3, BAR_ACC_FULL = 5, BAR_ACT_READY = 7, BAR_ACC_FREE = 9,
-  BAR_RB_FULL = 11, BAR_RB_FREE = 13, BAR_COUNT = 15
-};
+enum { BAR_W = 0, BAR_IN_FULL = 1, BAR_RB_FULL = 3, BAR_ACC_FULL = 5, BAR_COUNT = 7 };
 
-// bias values of `layer` for the 32 columns [col, col+32) of this thread's row -> v (as raw bits)
-//   staged rows : smem [8][kRbPitch], row = r_local        (per-ray bias, BLOCKED order)
-//   global rows : row_bias[ray]                            (per-ray bias, RAY_MAJOR order)
-//   otherwise   : the layer's bias vector in smem (broadcast)
 __device__ __forceinline__ void load_bias32(const float* src, uint32_t (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -187,9 +179,74 @@ __device__ __forceinline__ void load_bias32(const float* src, uint32_t (&v)[32])
   }
 }
 
+// One 32-column pass of a layer epilogue for one thread (= one row of the tile):
+//   read    : tcgen05.ld the accumulator columns
+//   pack    : (ReLU,) saturate, round to 16 bit, tcgen05.st as the next layer's A operand
+//   head_n  : accumulate head_n fp32 dot products of the (ReLU'd) unrounded activations
+//   bias    : tcgen05.st the next accumulation's bias into the same columns (1: smem/generic ptr, 2: global)
 template <bool F16>
+__device__ __forceinline__ void epi_pass(uint32_t d_addr, uint32_t a_addr, bool read, bool pack, bool relu, int head_n,
+                                         const float* hw, float (&hacc)[4], int bias_mode, const float* bsrc) {
+  uint32_t v[32];
+  if (read) {
+    tmem_ld32(d_addr, v);
+    tmem_ld_wait();
+    if (pack) {
+      uint32_t pk[16];
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, false>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      }
+      tmem_st16(a_addr, pk);
+    }
+    if (head_n > 0) {
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        if (h < head_n) {
+          const float4* hw4 = reinterpret_cast<const float4*>(hw + h * 128);
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 w4 = hw4[j];
+            acc0 = fmaf(__uint_as_float(v[4 * j + 0]), w4.x, acc0);
+            acc1 = fmaf(__uint_as_float(v[4 * j + 1]), w4.y, acc1);
+            acc0 = fmaf(__uint_as_float(v[4 * j + 2]), w4.z, acc0);
+            acc1 = fmaf(__uint_as_float(v[4 * j + 3]), w4.w, acc1);
+          }
+          hacc[h] += acc0 + acc1;
+        }
+      }
+    }
+  }
+  if (bias_mode == 1) {
+    load_bias32(bsrc, v);
+    tmem_st32(d_addr, v);
+  } else if (bias_mode == 2) {
+    const float4* g = reinterpret_cast<const float4*>(bsrc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b4 = __ldg(g + j);
+      v[4 * j + 0] = __float_as_uint(b4.x), v[4 * j + 1] = __float_as_uint(b4.y);
+      v[4 * j + 2] = __float_as_uint(b4.z), v[4 * j + 3] = __float_as_uint(b4.w);
+    }
+    tmem_st32(d_addr, v);
+  }
+}
+
+// LC > 0: "uniform" chain known at compile time — LC layers, all 128 wide with ReLU, one head of HN
+// rows on the last layer, per-ray bias on layer 0 iff RB0 (staged rows, BLOCKED order).  Both decoders
+// of the tri-plane model are of this shape (LC = 4).  LC == 0: generic chain described at run time.
+template <bool F16, int LC, int HN, bool RB0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
+  constexpr bool kFixed = LC > 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
@@ -198,24 +255,23 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   float* shpart = reinterpret_cast<float*>(smem + a.hpart_off);  // [2 slots][128 rows][4]: half 1 -> half 0
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = a.n_layers;
+  const int L = kFixed ? LC : a.n_layers;
   const int64_t G = gridDim.x;
+  const int rb_layer = kFixed ? (RB0 ? 0 : -1) : a.rb_layer;
+  const bool rb_staged = kFixed ? RB0 : (a.rb_staged != 0);
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     mbar_init(&bars[BAR_W], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars[BAR_IN_FULL + s], 1);
-      mbar_init(&bars[BAR_IN_FREE + s], 1);
-      mbar_init(&bars[BAR_ACC_FULL + s], 1);
-      mbar_init(&bars[BAR_ACT_READY + s], kTcEpiWarpsPerSlot);
-      mbar_init(&bars[BAR_ACC_FREE + s], kTcEpiWarpsPerSlot);
       mbar_init(&bars[BAR_RB_FULL + s], 1);
-      mbar_init(&bars[BAR_RB_FREE + s], kTcEpiWarpsPerSlot);
+      mbar_init(&bars[BAR_ACC_FULL + s], 1);
     }
+    tmem_slot[1] = tmem_slot[2] = 0;  // per-slot arrival counters
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   // biases / head weights -> smem (tiny, read by every epilogue thread for every tile)
   for (int i = threadIdx.x; i < L * 128; i += kTcThreads) {
     int l = i >> 7, n = i & 127;
@@ -238,139 +294,131 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= producer =================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars[BAR_W], a.w_bytes_total);
-      for (int l = 0; l < L; ++l) {
-        const TcLayer& ly = a.layer[l];
-        bulk_g2s(smem + ly.w_off, ly.w, (uint32_t)(ly.k * ly.n * 2), &bars[BAR_W]);
-      }
-      const float* rbg = a.rb_staged ? a.layer[a.rb_layer].row_bias : nullptr;
-      const int rbn = a.rb_staged ? a.layer[a.rb_layer].n : 0;
-      for (int64_t it = 0;; ++it) {
-        int64_t tile = blockIdx.x + it * G;
-        if (tile >= a.n_tiles) break;
-        int s = (int)(it & 1);
-        uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(&bars[BAR_IN_FREE + s], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], a.in_bytes);
-        bulk_g2s(smem + a.in_off[s], a.in + tile * (int64_t)a.in_bytes, a.in_bytes, &bars[BAR_IN_FULL + s]);
-        if (rbg) {
-          // the tile's 8 rays (BLOCKED order) are consecutive rows of row_bias
-          int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays;
-          int64_t left = a.n_rays - ray0;
-          int cnt = left >= kRbRowsMax ? kRbRowsMax : (int)left;
-          mbar_wait(&bars[BAR_RB_FREE + s], (use & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], (uint32_t)(cnt * rbn * 4));
-          float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
-          for (int j = 0; j < cnt; ++j)
-            bulk_g2s(dst + j * kRbPitch, rbg + (ray0 + j) * rbn, (uint32_t)(rbn * 4), &bars[BAR_RB_FULL + s]);
-        }
-      }
+  // Loads of one tile into slot s: the feature tile image and, when staged, the bias rows of its 8 rays
+  // (consecutive rows of row_bias in the BLOCKED order).  Issued by ONE thread.
+  auto issue_tile_loads = [&](int s, int64_t tile) {
+    mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], a.in_bytes);
+    bulk_g2s(smem + a.in_off[s], a.in + tile * (int64_t)a.in_bytes, a.in_bytes, &bars[BAR_IN_FULL + s]);
+    if (rb_staged) {
+      const TcLayer& rl = a.layer[rb_layer];
+      int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays;
+      int64_t left = a.n_rays - ray0;
+      int cnt = left >= kRbRowsMax ? kRbRowsMax : (int)left;
+      mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], (uint32_t)(cnt * rl.n * 4));
+      float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
+      for (int j = 0; j < cnt; ++j)
+        bulk_g2s(dst + j * kRbPitch, rl.row_bias + (ray0 + j) * rl.n, (uint32_t)(rl.n * 4), &bars[BAR_RB_FULL + s]);
     }
-    __syncwarp();
-  } else if (warp == 1 || warp == 2) {
-    // ================= MMA issuer of slot s (warp-uniform control flow, one elected lane issues) ======
-    const int s = warp - 1;
-    mbar_wait(&bars[BAR_W], 0);
-    const uint32_t d_tmem = tmem_base + (uint32_t)s * kSlotCols;
-    const uint32_t a_tmem = d_tmem + kSlotAOff;
-    const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
-    uint32_t ph_act = 0;
-    for (uint32_t use = 0;; ++use) {
-      if (blockIdx.x + (int64_t)(2 * use + s) * G >= a.n_tiles) break;
-      for (int l = 0; l < L; ++l) {
-        const TcLayer& ly = a.layer[l];
-        const uint32_t idesc = umma_idesc_16(ly.n, F16);
-        const uint32_t b_lbo = (uint32_t)ly.n * 16u;
-        const uint64_t bdesc0 = umma_desc(smem_u32(smem + ly.w_off), b_lbo, 128u);
-        const uint32_t b_step = (2u * b_lbo) >> 4;  // descriptor address units per K step of 16
-        const int ksteps = ly.k >> 4;
-        if (l == 0) {
-          mbar_wait(&bars[BAR_IN_FULL + s], use & 1);
-          mbar_wait(&bars[BAR_ACC_FREE + s], use & 1);  // D_s holds this tile's layer-0 bias
-          tc_fence_after();
-          if (elect_one()) {
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_ss(d_tmem, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
-            umma_commit(&bars[BAR_IN_FREE + s]);  // ring buffer reusable once these MMAs have read it
-            umma_commit(&bars[BAR_ACC_FULL + s]);
-          }
-        } else {
-          mbar_wait(&bars[BAR_ACT_READY + s], ph_act);
-          ph_act ^= 1;
-          tc_fence_after();
-          if (elect_one()) {
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
-            umma_commit(&bars[BAR_ACC_FULL + s]);
-          }
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp >= kTcFirstEpiWarp) {
-    // ================= epilogue of slot s =================
-    const int ew = warp - kTcFirstEpiWarp;
+  };
+
+  {
+    // ================= slot s: epilogue warps, the last one to finish a layer issues the next MMAs ======
+    const int ew = warp;
     const int s = ew >> 3;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = (ew & 7) >> 2;       // column ownership: half h owns columns [64h, 64h+64) of every layer
     const int r = quad * 32 + lane;       // row within the tile == TMEM lane
     const int col0 = half * 64;
-    const uint32_t d_tmem = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * kSlotCols + (uint32_t)col0;
-    const uint32_t a_tmem = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * kSlotCols + kSlotAOff +
-                            (uint32_t)(col0 >> 1);
+    const bool loader = (ew & 7) == 0 && lane == 0;  // this thread also feeds the slot's ring buffer
+    const uint32_t d_base = tmem_base + (uint32_t)s * kSlotCols;  // lane 0: the MMA's D / A operands
+    const uint32_t d_tmem = d_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
+    const uint32_t a_tmem = d_base + ((uint32_t)(quad * 32) << 16) + kSlotAOff + (uint32_t)(col0 >> 1);
     const float* rb_row = reinterpret_cast<const float*>(smem + a.rb_off[s]) + (r & (kBlkRays - 1)) * kRbPitch + col0;
     float* hp = shpart + (s * 128 + r) * 4;
     uint64_t* bar_acc_full = &bars[BAR_ACC_FULL + s];
     uint64_t* bar_rb_full = &bars[BAR_RB_FULL + s];
-    uint64_t* bar_rb_free = &bars[BAR_RB_FREE + s];
-    const int rb_layer = a.rb_layer, rb_staged = a.rb_staged;
+    uint32_t* done_cnt = tmem_slot + 1 + s;  // arrivals of the slot's 8 warps (monotonic; every 8th issues)
+    const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
     uint32_t ph_acc = 0, ph_rb = 0;
 
-    // bias of `layer` (tile `tile`) for this thread's row, columns col0 + [c, c+32) -> D_s
-    auto preload_bias = [&](int layer, int64_t tile, int c) {
-      uint32_t v[32];
-      if (layer != rb_layer) {
-        load_bias32(sbias + layer * 128 + col0 + c, v);
-      } else if (rb_staged) {
-        load_bias32(rb_row + c, v);
-      } else {
-        const TcLayer& ly = a.layer[layer];
-        int64_t row = tile * kTileRows + r;
-        int64_t ray = a.rows < 0x7fffffff ? (int64_t)((uint32_t)row / (uint32_t)a.samples_per_ray)
-                                          : row / a.samples_per_ray;
-        if (ray >= a.n_rays) ray = a.n_rays - 1;
-        const float4* g = reinterpret_cast<const float4*>(ly.row_bias + ray * ly.n + col0 + c);
+    // MMAs of layer l of the slot's tile number `use` (whole warp; one elected lane issues).
+    //   layer 0: A = feature tile in smem (SS form); l > 0: A = activations in TMEM (TS form).
+    // Every MMA accumulates onto the bias the epilogue pre-loaded into D_s.
+    auto issue_layer = [&](int l, uint32_t use) {
+      const TcLayer& ly = a.layer[l];
+      const int n = kFixed ? 128 : ly.n;
+      const uint32_t idesc = umma_idesc_16(n, F16);
+      const uint32_t b_lbo = (uint32_t)n * 16u;
+      const uint64_t bdesc0 = umma_desc(smem_u32(smem + ly.w_off), b_lbo, 128u);
+      const uint32_t b_step = (2u * b_lbo) >> 4;  // descriptor address units per K step of 16
+      const int ksteps = ly.k >> 4;
+      if (l == 0) {
+        mbar_wait(&bars[BAR_W], 0);
+        mbar_wait(&bars[BAR_IN_FULL + s], use & 1);
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        if (l == 0) {
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_ss(d_base, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+        } else if (kFixed) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 b4 = __ldg(g + j);
-          v[4 * j + 0] = __float_as_uint(b4.x), v[4 * j + 1] = __float_as_uint(b4.y);
-          v[4 * j + 2] = __float_as_uint(b4.z), v[4 * j + 3] = __float_as_uint(b4.w);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
         }
+        umma_commit(bar_acc_full);
       }
-      tmem_st32(d_tmem + (uint32_t)c, v);
+      __syncwarp();
     };
-
-    // prologue: D_s <- layer-0 bias of the slot's first tile
-    const int64_t first = blockIdx.x + (int64_t)s * G;
-    if (first < a.n_tiles) {
-      const bool rb0 = rb_layer == 0 && rb_staged;
-      if (rb0) {
-        mbar_wait(bar_rb_full, ph_rb);
-        ph_rb ^= 1;
-      }
-      for (int c = 0; c < 64; c += 32)
-        if (col0 + c < a.layer[0].n) preload_bias(0, first, c);
-      if (rb0) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_rb_free);
-      }
+    // This warp's TMEM writes for the next accumulation are done: count it; the slot's 8th arrival
+    // issues the MMAs of (layer nl, tile number nuse) — no issuer warp, no wake-up hop.
+    auto arrive_then_issue = [&](bool issue_next, int nl, uint32_t nuse) {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[BAR_ACC_FREE + s]);
+      uint32_t last_in = 0;
+      if (lane == 0) {
+        uint32_t old;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(done_cnt)) : "memory");
+        last_in = (old & (kTcEpiWarpsPerSlot - 1)) == kTcEpiWarpsPerSlot - 1;
+      }
+      last_in = __shfl_sync(0xffffffffu, last_in, 0);
+      if (last_in && issue_next) issue_layer(nl, nuse);
+    };
+
+    // source of the bias rows of `layer` for this thread: mode 1 = smem pointer, 2 = global pointer
+    auto bias_src = [&](int layer, int64_t tile, int* mode) -> const float* {
+      if (layer != rb_layer) {
+        *mode = 1;
+        return sbias + layer * 128 + col0;
+      }
+      if (rb_staged) {
+        *mode = 1;
+        return rb_row;
+      }
+      const TcLayer& ly = a.layer[layer];
+      int64_t row = tile * kTileRows + r;
+      int64_t ray = a.rows < 0x7fffffff ? (int64_t)((uint32_t)row / (uint32_t)a.samples_per_ray) : row / a.samples_per_ray;
+      if (ray >= a.n_rays) ray = a.n_rays - 1;
+      *mode = 2;
+      return ly.row_bias + ray * ly.n + col0;
+    };
+
+    // prologue: weights (once per CTA) and the first tile's loads, then D_s <- its layer-0 bias
+    const int64_t first = blockIdx.x + (int64_t)s * G;
+    if (warp == 0 && lane == 0) {
+      mbar_arrive_expect_tx(&bars[BAR_W], a.w_bytes_total);
+      for (int l = 0; l < L; ++l) {
+        const TcLayer& ly = a.layer[l];
+        bulk_g2s(smem + ly.w_off, ly.w, (uint32_t)(ly.k * ly.n * 2), &bars[BAR_W]);
+      }
+    }
+    if (first < a.n_tiles) {
+      if (loader) issue_tile_loads(s, first);
+      if (rb_layer == 0 && rb_staged) {
+        mbar_wait(bar_rb_full, ph_rb);
+        ph_rb ^= 1;
+      }
+      int mode;
+      const float* bsrc = bias_src(0, first, &mode);
+      const int n0 = kFixed ? 128 : a.layer[0].n;
+      float dummy[4];
+      for (int c = 0; c < 64; c += 32)
+        if (col0 + c < n0) epi_pass<F16>(d_tmem + (uint32_t)c, 0u, false, false, false, 0, nullptr, dummy, mode, bsrc + c);
+      arrive_then_issue(true, 0, 0u);
     }
 
     for (uint32_t use = 0;; ++use) {
@@ -378,21 +426,21 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       if (tile >= a.n_tiles) break;
       const int64_t next_tile = tile + 2 * G;
       const bool next_valid = next_tile < a.n_tiles;
+#pragma unroll 1
       for (int l = 0; l < L; ++l) {
         // ---- everything that does not depend on the accumulator: done before the wait ----
         const TcLayer& ly = a.layer[l];
         const bool last = l == L - 1;
-        const int n_cur = ly.n, relu = ly.relu;
-        const int head_n = ly.head_w ? ly.head_n : 0;
-        const int head_ch = ly.head_ch;
-        const float* hw = sheadw + ly.head_row * 128 + col0;
-        const float* head_b = ly.head_b;
+        const int n_cur = kFixed ? 128 : ly.n;
+        const bool relu = kFixed ? true : (ly.relu != 0);
+        const int head_n = kFixed ? (last ? HN : 0) : (ly.head_w ? ly.head_n : 0);
+        const float* hw = sheadw + (kFixed ? 0 : ly.head_row) * 128 + col0;
         // what gets pre-loaded into D_s once this layer's accumulator has been read
         const int nl = last ? 0 : l + 1;
-        const int n_next = (last && !next_valid) ? 0 : a.layer[nl].n;
-        const int64_t nl_tile = last ? next_tile : tile;
+        const int n_next = (last && !next_valid) ? 0 : (kFixed ? 128 : a.layer[nl].n);
         const bool nl_rb = n_next > 0 && nl == rb_layer && rb_staged;
-        uint64_t* bar_done = &bars[(last ? BAR_ACC_FREE : BAR_ACT_READY) + s];
+        int mode = 0;
+        const float* bsrc = n_next > 0 ? bias_src(nl, last ? next_tile : tile, &mode) : nullptr;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         if (nl_rb) {
           mbar_wait(bar_rb_full, ph_rb);
@@ -401,59 +449,18 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         mbar_wait(bar_acc_full, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
-#pragma unroll 1
+        // layer 0's MMAs have completed: the slot's ring buffer (and, since all 8 warps finished reading
+        // them before those MMAs were issued, its staged bias rows) may take the slot's next tile
+        if (l == 0 && loader && next_valid) issue_tile_loads(s, next_tile);
+#pragma unroll
         for (int c = 0; c < 64; c += 32) {
-          if (col0 + c < n_cur) {
-            uint32_t v[32];
-            tmem_ld32(d_tmem + (uint32_t)c, v);
-            tmem_ld_wait();
-            if (!last) {
-              uint32_t pk[16];
-              if (relu) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  pk[j] = pack_act<F16, true>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  pk[j] = pack_act<F16, false>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-              }
-              tmem_st16(a_tmem + (uint32_t)(c >> 1), pk);
-            }
-            if (head_n > 0) {
-              if (relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
-              }
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                if (h < head_n) {
-                  const float4* hw4 = reinterpret_cast<const float4*>(hw + h * 128 + c);
-                  float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    float4 w4 = hw4[j];
-                    acc0 = fmaf(__uint_as_float(v[4 * j + 0]), w4.x, acc0);
-                    acc1 = fmaf(__uint_as_float(v[4 * j + 1]), w4.y, acc1);
-                    acc0 = fmaf(__uint_as_float(v[4 * j + 2]), w4.z, acc0);
-                    acc1 = fmaf(__uint_as_float(v[4 * j + 3]), w4.w, acc1);
-                  }
-                  hacc[h] += acc0 + acc1;
-                }
-              }
-            }
-          }
-          // the next accumulation into these columns starts from its bias
-          if (col0 + c < n_next) preload_bias(nl, nl_tile, c);
+          const bool read = col0 + c < n_cur;
+          const bool bias = col0 + c < n_next;
+          if (read || bias)
+            epi_pass<F16>(d_tmem + (uint32_t)c, a_tmem + (uint32_t)(c >> 1), read, !last, relu, head_n, hw + c, hacc,
+                          bias ? mode : 0, bsrc + c);
         }
-        if (nl_rb) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_rb_free);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_done);
+        arrive_then_issue(n_next > 0, nl, last ? use + 1 : use);
 
         if (head_n > 0) {
           // combine the two column halves of a row: half 1 -> smem -> half 0
@@ -465,7 +472,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
             float hv[4] = {hacc[0] + o.x, hacc[1] + o.y, hacc[2] + o.z, hacc[3] + o.w};
 #pragma unroll
             for (int h = 0; h < 4; ++h)
-              if (h < head_n) a.raw[(int64_t)(head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(head_b + h);
+              if (h < head_n) a.raw[(int64_t)(ly.head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(ly.head_b + h);
           }
         }
       }
@@ -475,7 +482,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -487,6 +494,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   a.rb_layer = -1;
   uint32_t off = 0;
   int head_rows = 0;
+  bool uniform = true;  // all layers 128 wide with ReLU, one head on the last layer
   for (int l = 0; l < m->n_layers; ++l) {
     const nvsr_layer_t& L = m->layer[l];
     if (L.k <= 0 || (L.k % 16) != 0 || L.k > 256) return NVSR_ERR_UNSUPPORTED;
@@ -510,15 +518,18 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
     } else {
       t.head_n = 0;
     }
+    uniform = uniform && L.n_out == 128 && L.relu && ((L.head_w != nullptr) == (l == m->n_layers - 1));
     t.w_off = off;
     off += (uint32_t)(L.k * L.n_out * 2);
   }
-  if (!m->layer[m->n_layers - 1].head_w) return NVSR_ERR_INVALID_ARG;  // the chain must end in a head
+  const nvsr_layer_t& lastL = m->layer[m->n_layers - 1];
+  if (!lastL.head_w) return NVSR_ERR_INVALID_ARG;  // the chain must end in a head
   a.w_bytes_total = off;
   const uint32_t in_bytes = (uint32_t)m->layer[0].k * 256u;  // 128 rows * K * 2 B
   a.in_off[0] = off, off += in_bytes;
   a.in_off[1] = off, off += in_bytes;
-  a.rb_staged = (a.rb_layer >= 0 && m->row_order == NVSR_ROWS_BLOCKED) ? 1 : 0;
+  // per-ray bias rows are staged through smem when the 8 rays of a tile are consecutive (BLOCKED order)
+  a.rb_staged = (a.rb_layer == 0 && m->row_order == NVSR_ROWS_BLOCKED) ? 1 : 0;
   a.rb_off[0] = a.rb_off[1] = off;
   if (a.rb_staged) {
     a.rb_off[1] = off + kRbRowsMax * kRbPitch * 4u;
@@ -527,7 +538,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   a.bias_off = off, off += (uint32_t)m->n_layers * 128u * 4u;
   a.headw_off = off, off += kTcMaxHeadRows * 128u * 4u;
   a.hpart_off = off, off += 2u * 128u * 4u * 4u;
-  a.bar_off = off, off += BAR_COUNT * 8u + 16u;
+  a.bar_off = off, off += BAR_COUNT * 8u + 16u;  // barriers, then {tmem base, arrival counter x2}
   const uint32_t smem_bytes = off;
   if (smem_bytes > 227u * 1024u) return NVSR_ERR_RESOURCE;
   if (!aligned16(m->in)) return NVSR_ERR_ALIGNMENT;
@@ -544,7 +555,16 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   a.raw = m->raw;
   a.raw_stride = m->raw_stride;
 
-  auto kernel = m->precision == NVSR_F16 ? mlp_chain_tc_kernel<true> : mlp_chain_tc_kernel<false>;
+  const bool f16 = m->precision == NVSR_F16;
+  void (*kernel)(TcArgs) = nullptr;
+  // compile-time specialisations: the two decoders of the tri-plane model
+  const bool rb_ok = a.rb_layer < 0 || a.rb_staged;
+  if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 1 && a.rb_layer < 0)
+    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 1, false> : mlp_chain_tc_kernel<false, 4, 1, false>;
+  else if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 3 && a.rb_layer == 0)
+    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 3, true> : mlp_chain_tc_kernel<false, 4, 3, true>;
+  else
+    kernel = f16 ? mlp_chain_tc_kernel<true, 0, 0, false> : mlp_chain_tc_kernel<false, 0, 0, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
   int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
