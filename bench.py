@@ -37,6 +37,15 @@ EVALS_PER_RAY = NC + (NC + NF)          # decoder evaluations per ray (coarse ne
 FLOP_PER_EVAL = 259072                  # true MACs x 2, planes decoder
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -177,27 +186,16 @@ def main():
     mc, mf, sid, pose, focal, opt, scfg = build_scene(dev)
     pose = pose.to(dev)
 
-    # row-band sharding: rank r renders rows [r0, r1)
-    rows_per = (RES + world - 1) // world
-    r0, r1 = min(RES, rank * rows_per), min(RES, (rank + 1) * rows_per)
-    n_local = (r1 - r0) * RES
-    tile = torch.zeros((rows_per * RES, 10), device=dev)          # rgb_c,disp_c,acc_c,rgb_f,disp_f,acc_f
-    gathered = torch.zeros((world * rows_per * RES, 10), device=dev) if world > 1 else None
+    # row-band sharding: rank r renders rows [r0, r1); one all_gather of the result tiles per frame
+    from nvsr_b200 import sharding
+    sh = sharding.FrameSharder(RES, RES, rank, world, dev)
+    r0, r1, rows_per, n_local = sh.r0, sh.r1, sh.per, sh.n_local
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def pack_outputs(out):
-        tile[:n_local, 0:3], tile[:n_local, 3], tile[:n_local, 4] = out[0], out[1], out[2]
-        tile[:n_local, 5:8], tile[:n_local, 8], tile[:n_local, 9] = out[3], out[4], out[5]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, tile)   # the one collective per frame (NVLink)
-            return gathered
-        return tile
 
     def frame_device():
         """rays generated on the device (get_ray_bundle kernel), everything resident"""
         flush.zero_()
-        out = nvsr_b200.render_frame(RES, RES, focal, pose, mc, mf, opt, sid, scfg, row_range=(r0, r1))
-        return pack_outputs(out)
+        return sh.render(lambda a, b: nvsr_b200.render_frame(RES, RES, focal, pose, mc, mf, opt, sid, scfg, row_range=(a, b)))
 
     # host buffers for the e2e leg (the call a user of the reference makes: rays in, maps out)
     with torch.no_grad():
@@ -208,8 +206,8 @@ def main():
     def frame_e2e():
         flush.zero_()
         batch = host_rays.to(dev, non_blocking=True)
-        out = nvsr_b200.run_one_iter_of_nerf(RES, RES, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
-        res = pack_outputs(out)
+        res = sh.render(lambda a, b: nvsr_b200.run_one_iter_of_nerf(RES, RES, focal, mc, mf, batch, opt, sid, "validation",
+                                                                    scene_config=scfg))
         host_out.copy_(res[rank * rows_per * RES:(rank + 1) * rows_per * RES] if world > 1 else res, non_blocking=True)
 
     def barrier():
@@ -281,7 +279,8 @@ def main():
     if mlp_ms > 0 and args.precision != "fp32":
         ach = mlp_fl / (mlp_ms * 1e-3) / 1e12
         roofline = {"kernel": "mlp_chain_tc_kernel (decoder, tcgen05)", "bound": "tensor", "achieved": ach,
-                    "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
+                    "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                    "traffic": ncu_traffic("mlp_chain_tc_kernel"),
                     "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "avg_launch_ms": mlp_ms / mlp_n, "flop_per_launch": mlp_fl / mlp_n, "share_of_step": mlp_ms / total_ms}
     elif mlp_ms > 0:
