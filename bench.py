@@ -137,7 +137,7 @@ def time_cpu_oracle(n_side, steps, warmup):
                        f"{len(times)} timed passes after {warmup} warm-up")
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, guard):
     if rank != 0:
         return
     r = time_cpu_oracle(n_side=48, steps=max(1, args.steps), warmup=min(args.warmup, 1))
@@ -151,10 +151,25 @@ def run_reference(args, rank):
         "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    guard.emit(json.dumps(line))
+
+
+class StdoutGuard:
+    """Everything libraries print to fd 1 during the run (e.g. the 'NCCL version ...' banner) is sent to
+    stderr; only `emit()` writes to the real stdout, so rank 0 prints exactly ONE JSON line there."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
 
 
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -168,7 +183,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, guard)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -315,7 +330,7 @@ def main():
             "kernels": kernels,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
