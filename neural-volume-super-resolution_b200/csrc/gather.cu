@@ -2,10 +2,10 @@
 //
 // Two kernels:
 //   gather_rowmajor_f32 : fp32 planes -> fp32 row-major features (parity mode, feeds the SIMT decoder)
-//   gather_tile_16      : bf16|fp16 channels-last planes -> 16-bit "tile image" features.  A CTA builds one
-//                         128-row decoder tile in shared memory (coalesced 16-byte texel reads, six
-//                         lanes per texel) and ships it with two bulk (TMA-engine) stores, so the
-//                         tcgen05 decoder can fetch the tile with a single bulk copy.  Rows are in the
+//   gather_tile_16      : bf16|fp16 channels-last planes -> 16-bit "tile image" features, which the tcgen05
+//                         decoder fetches with a single bulk copy per 128-row tile.  One thread per row,
+//                         corners/weights in registers, 12 texel loads in flight per chunk, packed-fp32
+//                         (FFMA2) interpolation, coalesced streaming stores; no shared memory.  Rows are in the
 //                         BLOCKED order (8 adjacent rays x 16 samples per tile): consecutive rows are
 //                         adjacent pixels at one depth, whose bilinear footprints overlap, so the
 //                         texel requests of a warp collapse onto a few L1 lines.
@@ -114,118 +114,128 @@ gather_rowmajor_f32(SamplerArgs a, PlaneArgs p, float* __restrict__ featP, float
 }
 
 // ------------------------------------------------------------------------------------------------
-// bf16 tile kernel
-struct __align__(16) RowCorners {
-  int o00[3], o01[3], o10[3], o11[3];  // texel indices (y*rw + x)
-  float w00[3], w01[3], w10[3], w11[3];
-};
-
+// 16-bit tile kernel: ONE THREAD PER ROW of the 128-row tile (lane = row, so consecutive lanes are
+// adjacent rays at one depth and every shared-memory store of a warp covers 512 contiguous bytes of a
+// K-chunk: conflict-free).  The row's 12 texel offsets / bilinear weights live in registers; the thread
+// walks the C/8 16-byte channel chunks, issuing the 12 texel loads of a chunk back to back and
+// interpolating with packed fp32 FMAs (FFMA2).
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 template <bool F16>
-__device__ __forceinline__ void fma_16x8(float acc[8], const uint4& v, float w) {
-  float2 a = unpack16x2<F16>(v.x), b = unpack16x2<F16>(v.y), c = unpack16x2<F16>(v.z), d = unpack16x2<F16>(v.w);
-  acc[0] = fmaf(a.x, w, acc[0]), acc[1] = fmaf(a.y, w, acc[1]);
-  acc[2] = fmaf(b.x, w, acc[2]), acc[3] = fmaf(b.y, w, acc[3]);
-  acc[4] = fmaf(c.x, w, acc[4]), acc[5] = fmaf(c.y, w, acc[5]);
-  acc[6] = fmaf(d.x, w, acc[6]), acc[7] = fmaf(d.y, w, acc[7]);
+__device__ __forceinline__ unsigned long long unpack16x2_pair(uint32_t v) {
+  float2 f = unpack16x2<F16>(v);
+  return pack_f32x2(f.x, f.y);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16_pair(unsigned long long v) {
+  return pack16x2<F16>(__uint_as_float((uint32_t)v), __uint_as_float((uint32_t)(v >> 32)));
 }
 
-constexpr int kGatherThreads = 256;
+constexpr int kGatherThreads = kTileRows;  // one thread per row
 
-// dynamic smem: [P image 3C/8 x 2048 B][M image C/8 x 2048 B][RowCorners x 128]
+// 16-byte streaming store (the feature tile is written once and read by the next kernel: keep it out of L1,
+// which the texel reads need)
+__device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// No shared memory: in the tile image [K/8][128 rows][16 B] a warp's 32 rows of one chunk are 512
+// contiguous bytes, so the stores go straight to global, fully coalesced.
 template <bool F16>
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, 6)
 gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
-                 float* __restrict__ z_out, int64_t n_tiles) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int CH = p.C / 8;                 // 16-byte chunks per plane texel (6 for C=48)
+               float* __restrict__ z_out, int64_t n_tiles) {
+  const int CH = p.C / 8;                    // 16-byte chunks per plane texel (6 for C=48)
   const uint32_t p_bytes = 3u * CH * 2048u;  // 128 rows * 3C * 2 B
   const uint32_t m_bytes = (uint32_t)CH * 2048u;
-  uint8_t* sP = smem;
-  uint8_t* sM = smem + p_bytes;
-  RowCorners* sc = reinterpret_cast<RowCorners*>(smem + p_bytes + m_bytes);
   const int TS = tiles_per_block(a.S);
-  const int tid = threadIdx.x;
+  const int r = threadIdx.x;
+  const unsigned long long third = pack_f32x2(1.f / 3.f, 1.f / 3.f);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // previous tile's bulk stores must have finished READING smem before we overwrite it
-    if (tid == 0) bulk_wait_read<0>();
-    __syncthreads();
-    // phase 1: per-row sample position -> 3 planes' corner indices and weights
-    if (tid < kTileRows) {
-      int64_t ray;
-      int s;
-      blocked_decode(tile, tid, TS, &ray, &s);
-      RowCorners rc;
-      if (ray < a.n_rays && s < a.S) {
-        float z = sample_depth(a, ray, s);
-        if (z_out) z_out[ray * a.S + s] = z;
-        Bilin b[3];
-        sample_corners(a, p, ray, z, b);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          int rw = p.rw[d];
-          rc.o00[d] = b[d].y0 * rw + b[d].x0, rc.o01[d] = b[d].y0 * rw + b[d].x1;
-          rc.o10[d] = b[d].y1 * rw + b[d].x0, rc.o11[d] = b[d].y1 * rw + b[d].x1;
-          rc.w00[d] = b[d].w00, rc.w01[d] = b[d].w01, rc.w10[d] = b[d].w10, rc.w11[d] = b[d].w11;
-        }
-      } else {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          rc.o00[d] = rc.o01[d] = rc.o10[d] = rc.o11[d] = 0;
-          rc.w00[d] = rc.w01[d] = rc.w10[d] = rc.w11[d] = 0.f;  // padded rows -> zeros
-        }
-      }
-      sc[tid] = rc;
-    }
-    __syncthreads();
-    // phase 2: items (row, chunk); consecutive lanes take consecutive chunks of one texel
-    for (int item = tid; item < kTileRows * CH; item += kGatherThreads) {
-      int r = item / CH;
-      int c = item - r * CH;
-      const RowCorners& rc = sc[r];
-      float mean[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) mean[e] = 0.f;
-      uint4 v[3][4];
+    // ---- per-row sample position -> 3 planes' corner texels and weights (registers) ----
+    int64_t ray;
+    int s;
+    blocked_decode(tile, r, TS, &ray, &s);
+    const uint4* tex[12];
+    unsigned long long w2[12];
+    if (ray < a.n_rays && s < a.S) {
+      float z = sample_depth(a, ray, s);
+      if (z_out) z_out[ray * a.S + s] = z;
+      Bilin b[3];
+      sample_corners(a, p, ray, z, b);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         const uint4* pl = reinterpret_cast<const uint4*>(p.plane[d]);
-        v[d][0] = __ldg(pl + (int64_t)rc.o00[d] * CH + c);
-        v[d][1] = __ldg(pl + (int64_t)rc.o01[d] * CH + c);
-        v[d][2] = __ldg(pl + (int64_t)rc.o10[d] * CH + c);
-        v[d][3] = __ldg(pl + (int64_t)rc.o11[d] * CH + c);
+        const int rw = p.rw[d];
+        tex[d * 4 + 0] = pl + (int64_t)(b[d].y0 * rw + b[d].x0) * CH;
+        tex[d * 4 + 1] = pl + (int64_t)(b[d].y0 * rw + b[d].x1) * CH;
+        tex[d * 4 + 2] = pl + (int64_t)(b[d].y1 * rw + b[d].x0) * CH;
+        tex[d * 4 + 3] = pl + (int64_t)(b[d].y1 * rw + b[d].x1) * CH;
+        w2[d * 4 + 0] = pack_f32x2(b[d].w00, b[d].w00), w2[d * 4 + 1] = pack_f32x2(b[d].w01, b[d].w01);
+        w2[d * 4 + 2] = pack_f32x2(b[d].w10, b[d].w10), w2[d * 4 + 3] = pack_f32x2(b[d].w11, b[d].w11);
       }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        tex[k] = reinterpret_cast<const uint4*>(p.plane[k >> 2]);  // padded rows -> zeros
+        w2[k] = 0ull;
+      }
+    }
+    uint8_t* gP = featP + tile * (int64_t)p_bytes + (uint32_t)r * 16u;
+    uint8_t* gM = featM + tile * (int64_t)m_bytes + (uint32_t)r * 16u;
+    // ---- channel chunks ----
+#pragma unroll 1
+    for (int c = 0; c < CH; ++c) {
+      uint4 v[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) v[k] = __ldg(tex[k] + c);
+      unsigned long long mean[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        float acc[8];
+        unsigned long long acc[4];
+        {
+          const uint4& t = v[d * 4];
+          const unsigned long long w = w2[d * 4];
+          acc[0] = mul_f32x2(unpack16x2_pair<F16>(t.x), w), acc[1] = mul_f32x2(unpack16x2_pair<F16>(t.y), w);
+          acc[2] = mul_f32x2(unpack16x2_pair<F16>(t.z), w), acc[3] = mul_f32x2(unpack16x2_pair<F16>(t.w), w);
+        }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        fma_16x8<F16>(acc, v[d][0], rc.w00[d]);
-        fma_16x8<F16>(acc, v[d][1], rc.w01[d]);
-        fma_16x8<F16>(acc, v[d][2], rc.w10[d]);
-        fma_16x8<F16>(acc, v[d][3], rc.w11[d]);
+        for (int k = 1; k < 4; ++k) {
+          const uint4& t = v[d * 4 + k];
+          const unsigned long long w = w2[d * 4 + k];
+          acc[0] = fma_f32x2(unpack16x2_pair<F16>(t.x), w, acc[0]), acc[1] = fma_f32x2(unpack16x2_pair<F16>(t.y), w, acc[1]);
+          acc[2] = fma_f32x2(unpack16x2_pair<F16>(t.z), w, acc[2]), acc[3] = fma_f32x2(unpack16x2_pair<F16>(t.w), w, acc[3]);
+        }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) mean[e] += acc[e];
+        for (int e = 0; e < 4; ++e) mean[e] = add_f32x2(mean[e], acc[e]);
         uint4 o;
-        o.x = pack16x2<F16>(acc[0], acc[1]), o.y = pack16x2<F16>(acc[2], acc[3]);
-        o.z = pack16x2<F16>(acc[4], acc[5]), o.w = pack16x2<F16>(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(sP + (uint32_t)(d * CH + c) * 2048u + (uint32_t)r * 16u) = o;
+        o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
+        o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
+        st_stream16(gP + (uint32_t)(d * CH + c) * 2048u, o);
       }
       uint4 o;
-      o.x = pack16x2<F16>(mean[0] / 3.f, mean[1] / 3.f), o.y = pack16x2<F16>(mean[2] / 3.f, mean[3] / 3.f);
-      o.z = pack16x2<F16>(mean[4] / 3.f, mean[5] / 3.f), o.w = pack16x2<F16>(mean[6] / 3.f, mean[7] / 3.f);
-      *reinterpret_cast<uint4*>(sM + (uint32_t)c * 2048u + (uint32_t)r * 16u) = o;
-    }
-    // phase 3: ship the two images with the bulk-copy engine
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(featP + tile * (int64_t)p_bytes, sP, p_bytes);
-      bulk_s2g(featM + tile * (int64_t)m_bytes, sM, m_bytes);
-      bulk_commit();
+      o.x = pack16_pair<F16>(mul_f32x2(mean[0], third)), o.y = pack16_pair<F16>(mul_f32x2(mean[1], third));
+      o.z = pack16_pair<F16>(mul_f32x2(mean[2], third)), o.w = pack16_pair<F16>(mul_f32x2(mean[3], third));
+      st_stream16(gM + (uint32_t)c * 2048u, o);
     }
   }
-  if (tid == 0) bulk_wait<0>();
 }
 
 }  // namespace nvsr
@@ -268,18 +278,10 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     const bool f16 = feat_layout == NVSR_FEAT_TILE_F16;
     if (pl->dtype != (f16 ? NVSR_F16 : NVSR_BF16)) return NVSR_ERR_UNSUPPORTED;
     auto kernel = f16 ? gather_tile_16<true> : gather_tile_16<false>;
-    int CH = p.C / 8;
-    size_t smem = (size_t)4 * CH * 2048 + sizeof(RowCorners) * kTileRows;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int32_t)e;
     int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
-    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
-    if (ctas_per_sm < 1) return NVSR_ERR_RESOURCE;
-    int64_t grid = (int64_t)kNumSMs * ctas_per_sm;
+    int64_t grid = (int64_t)kNumSMs * 6 * 4;  // a few waves of the 6 resident CTAs per SM, grid-stride beyond
     if (grid > n_tiles) grid = n_tiles;
-    kernel<<<(unsigned)grid, kGatherThreads, smem, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out,
-                                                                  n_tiles);
+    kernel<<<(unsigned)grid, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_tiles);
     NVSR_RETURN_LAST_ERROR();
   }
   return NVSR_ERR_UNSUPPORTED;
