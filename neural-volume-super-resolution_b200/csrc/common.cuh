@@ -92,16 +92,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
-// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires, so a
-// waiting warp costs (almost) no issue slots; it wakes as soon as the phase flips.
+// try_wait suspends the warp in hardware for a bounded, implementation-defined time while the phase is
+// incomplete, so a polling warp issues about one instruction per ~200 cycles.  (An explicit suspend-time
+// hint compiles to NANOSLEEP.SYNCS and measured ~1% slower on the decoder: -DNVSR_WAIT_HINT_NS=<ns>.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef NVSR_WAIT_HINT_NS
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+#ifdef NVSR_WAIT_HINT_NS
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)NVSR_WAIT_HINT_NS)
+#else
+      : "r"(smem_u32(bar)), "r"(parity)
+#endif
       : "memory");
   return ok != 0;
 }

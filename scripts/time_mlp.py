@@ -1,0 +1,32 @@
+"""Time the decoder kernel alone on synthetic features (density and rgb chains, fine-pass size)."""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nvsr_b200
+from nvsr_b200 import ops, scene
+from nvsr_b200._lib import NVSR_F16
+dev = torch.device("cuda", 0)
+mc, mf, sid = scene.make_synthetic_scene(plane_res=64, view_res=16, seed=0, device=dev)
+dec = scene.pack_planes_decoder(mf, NVSR_F16)
+n, S = 32768, 192
+rows = ops.rows_padded(n, S, ops.ROWS_BLOCKED)
+tiles = rows // 128
+fp = (torch.randn(tiles, 18, 128, 8, device=dev) * 0.3).half()
+fm = (torch.randn(tiles, 6, 128, 8, device=dev) * 0.3).half()
+rb = torch.randn(n, 128, device=dev)
+raw = ops.raw_buffer(n, S, ops.ROWS_BLOCKED, dev)
+def run(which):
+    if which == "density":
+        ops.mlp_chain(fm, dec.density, rows, raw, NVSR_F16, S, n, ops.ROWS_BLOCKED)
+    else:
+        ops.mlp_chain(fp, dec.rgb_chain(rb), rows, raw, NVSR_F16, S, n, ops.ROWS_BLOCKED)
+for which in ("density", "rgb"):
+    for _ in range(3): run(which)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): run(which)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = 2 * rows * (55424 if which == "density" else 74112 - 48 * 128)
+    print(f"NVSR_DBG={os.environ.get('NVSR_DBG','0'):>3s} {which:8s} {ms:7.3f} ms  {fl/ms/1e9:7.1f} TFLOP/s  cycles/tile {ms*1e-3*1.965e9/(tiles/148):7.0f}")
