@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -253,6 +253,17 @@ def main():
         ms_dev = timed(frame_device, args.steps)
         launches = sum(ops.LAUNCHES.values())
         clk = clocks.stop()
+        if not clk.get("samples"):
+            # the timed region was shorter than nvidia-smi's sampling period: sample the clocks under the
+            # same load over a longer (untimed) stretch of the same step and say so
+            clocks = ClockSampler(local)
+            clocks.start()
+            t_end = time.perf_counter() + 0.6
+            while time.perf_counter() < t_end:
+                frame_device()
+            barrier()
+            clk = clocks.stop()
+            clk["note"] = "timed region shorter than the sampling period; sampled over 0.6 s of the same step right after it"
         for _ in range(2):
             frame_e2e()
         ms_e2e = timed(frame_e2e, args.steps)

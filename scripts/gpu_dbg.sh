@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-for i in 1 2; do
-for v in ${VARIANTS:-V0 V1 V2}; do echo "lib $v"; NVSR_B200_LIB=$GRAFT_REPO_ROOT/ab_libs/lib$v.so python scripts/time_mlp.py 2>&1 | grep NVSR_DBG; done
-done
+for c in 32768 131072 640000; do echo "chunk $c"; python bench.py --steps 4 --warmup 3 --no-cpu-baseline --ray-chunk $c 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], {k:round(v['avg_ms'],3) for k,v in d['kernels'].items()})"; done
