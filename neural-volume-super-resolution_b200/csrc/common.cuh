@@ -58,11 +58,14 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 // 16-bit operand type of the tensor-core path: bf16 (8-bit significand, fp32 range) or fp16 (11-bit
-// significand, max 65504 — values are clamped on conversion so an overflow saturates instead of inf)
+// significand, max 65504).  cvt.satfinite: an overflow saturates to the largest finite value instead of
+// inf, in the conversion instruction itself (F2FP.SATFINITE.*.PACK_AB, no separate clamps).
 template <bool F16>
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
-  if constexpr (F16) return pack_f16x2(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-  else return pack_bf16x2(lo, hi);
+  uint32_t r;
+  if constexpr (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 template <bool F16>
 __device__ __forceinline__ float2 unpack16x2(uint32_t v) {

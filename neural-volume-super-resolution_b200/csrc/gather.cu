@@ -120,7 +120,9 @@ gather_rowmajor_f32(SamplerArgs a, PlaneArgs p, float* __restrict__ featP, float
 // walks the C/8 16-byte channel chunks, issuing the 12 texel loads of a chunk back to back and
 // interpolating with packed fp32 FMAs (FFMA2).
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
 }
 __device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -155,76 +157,97 @@ __device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Per row and plane: the two plane rows (y0, y1) of the footprint at its left column, and the four
+// weights in (left, right) form.  16-bit planes are "row-chunk-major" [Rh][C/8][Rw][8] (rays.cu
+// pack_plane16_kernel): chunk c of texel (y, x) sits at ((y*CH + c)*Rw + x)*16 B, so the right corner is
+// the NEXT 16-byte unit (+1) of the left one and the footprints of the 8 adjacent rays of a quarter
+// warp land in one or two 128-byte lines per load instruction.  At the right border (x0 == Rw-1; the
+// right weights are exactly 0 there) the pair is shifted one texel left and the weights swap sides, so
+// the +1 access never leaves the plane row.
+struct Foot {
+  uint32_t top, bot;      // 16-byte-unit offsets of (y0, xl), (y1, xl), chunk 0
+  float wtl, wtr, wbl, wbr;
+};
+__device__ __forceinline__ Foot make_foot(const Bilin& b, int rw, int CH) {
+  Foot f;
+  const bool edge = b.x0 >= rw - 1;
+  const int xl = edge ? rw - 2 : b.x0;
+  f.top = (uint32_t)((b.y0 * CH) * rw + xl);
+  f.bot = (uint32_t)((b.y1 * CH) * rw + xl);
+  f.wtl = edge ? 0.f : b.w00, f.wtr = edge ? b.w00 : b.w01;
+  f.wbl = edge ? 0.f : b.w10, f.wbr = edge ? b.w10 : b.w11;
+  return f;
+}
+
+// acc[e] (+)= unpack(t) * w for the 4 channel pairs of one 16-byte texel chunk
+template <bool F16, bool FIRST>
+__device__ __forceinline__ void texel_fma(unsigned long long acc[4], const uint4& t, float wgt) {
+  const unsigned long long w = pack_f32x2(wgt, wgt);
+  if constexpr (FIRST) {
+    acc[0] = mul_f32x2(unpack16x2_pair<F16>(t.x), w), acc[1] = mul_f32x2(unpack16x2_pair<F16>(t.y), w);
+    acc[2] = mul_f32x2(unpack16x2_pair<F16>(t.z), w), acc[3] = mul_f32x2(unpack16x2_pair<F16>(t.w), w);
+  } else {
+    acc[0] = fma_f32x2(unpack16x2_pair<F16>(t.x), w, acc[0]), acc[1] = fma_f32x2(unpack16x2_pair<F16>(t.y), w, acc[1]);
+    acc[2] = fma_f32x2(unpack16x2_pair<F16>(t.z), w, acc[2]), acc[3] = fma_f32x2(unpack16x2_pair<F16>(t.w), w, acc[3]);
+  }
+}
+
 // No shared memory: in the tile image [K/8][128 rows][16 B] a warp's 32 rows of one chunk are 512
-// contiguous bytes, so the stores go straight to global, fully coalesced.
-template <bool F16>
-__global__ void __launch_bounds__(kGatherThreads, 6)
+// contiguous bytes, so the stores go straight to global, fully coalesced.  CH_T > 0 fixes the chunk
+// count at compile time (6 for the reference's 48-channel planes): the chunk loop is fully unrolled
+// and the loads of the next chunk are in flight while one is interpolated.
+template <bool F16, int CH_T>
+__global__ void __launch_bounds__(kGatherThreads, 5)
 gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
                float* __restrict__ z_out, int64_t n_tiles) {
-  const int CH = p.C / 8;                    // 16-byte chunks per plane texel (6 for C=48)
+  const int CH = CH_T > 0 ? CH_T : p.C / 8;  // 16-byte chunks per plane texel (6 for C=48)
   const uint32_t p_bytes = 3u * CH * 2048u;  // 128 rows * 3C * 2 B
   const uint32_t m_bytes = (uint32_t)CH * 2048u;
   const int TS = tiles_per_block(a.S);
   const int r = threadIdx.x;
   const unsigned long long third = pack_f32x2(1.f / 3.f, 1.f / 3.f);
+  const uint4* const pl0 = reinterpret_cast<const uint4*>(p.plane[0]);
+  const uint4* const pl1 = reinterpret_cast<const uint4*>(p.plane[1]);
+  const uint4* const pl2 = reinterpret_cast<const uint4*>(p.plane[2]);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- per-row sample position -> 3 planes' corner texels and weights (registers) ----
+    // ---- per-row sample position -> 3 planes' footprints (registers) ----
     int64_t ray;
     int s;
     blocked_decode(tile, r, TS, &ray, &s);
-    const uint4* tex[12];
-    unsigned long long w2[12];
+    Foot f[3];
     if (ray < a.n_rays && s < a.S) {
       float z = sample_depth(a, ray, s);
       if (z_out) z_out[ray * a.S + s] = z;
       Bilin b[3];
       sample_corners(a, p, ray, z, b);
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const uint4* pl = reinterpret_cast<const uint4*>(p.plane[d]);
-        const int rw = p.rw[d];
-        tex[d * 4 + 0] = pl + (int64_t)(b[d].y0 * rw + b[d].x0) * CH;
-        tex[d * 4 + 1] = pl + (int64_t)(b[d].y0 * rw + b[d].x1) * CH;
-        tex[d * 4 + 2] = pl + (int64_t)(b[d].y1 * rw + b[d].x0) * CH;
-        tex[d * 4 + 3] = pl + (int64_t)(b[d].y1 * rw + b[d].x1) * CH;
-        w2[d * 4 + 0] = pack_f32x2(b[d].w00, b[d].w00), w2[d * 4 + 1] = pack_f32x2(b[d].w01, b[d].w01);
-        w2[d * 4 + 2] = pack_f32x2(b[d].w10, b[d].w10), w2[d * 4 + 3] = pack_f32x2(b[d].w11, b[d].w11);
-      }
+      for (int d = 0; d < 3; ++d) f[d] = make_foot(b[d], p.rw[d], CH);
     } else {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        tex[k] = reinterpret_cast<const uint4*>(p.plane[k >> 2]);  // padded rows -> zeros
-        w2[k] = 0ull;
-      }
+      for (int d = 0; d < 3; ++d) f[d] = Foot{0u, 0u, 0.f, 0.f, 0.f, 0.f};  // padded rows -> zeros
     }
     uint8_t* gP = featP + tile * (int64_t)p_bytes + (uint32_t)r * 16u;
     uint8_t* gM = featM + tile * (int64_t)m_bytes + (uint32_t)r * 16u;
+    const uint4* rowT[3] = {pl0 + f[0].top, pl1 + f[1].top, pl2 + f[2].top};
+    const uint4* rowB[3] = {pl0 + f[0].bot, pl1 + f[1].bot, pl2 + f[2].bot};
     // ---- channel chunks ----
-#pragma unroll 1
-    for (int c = 0; c < CH; ++c) {
-      uint4 v[12];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) v[k] = __ldg(tex[k] + c);
-      unsigned long long mean[4] = {0ull, 0ull, 0ull, 0ull};
+    for (int c = 0; c < CH; ++c) {
+      unsigned long long mean[4];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
+        const uint4* t = rowT[d] + c * p.rw[d];
+        const uint4* bt = rowB[d] + c * p.rw[d];
+        const uint4 vtl = __ldg(t), vtr = __ldg(t + 1), vbl = __ldg(bt), vbr = __ldg(bt + 1);
         unsigned long long acc[4];
-        {
-          const uint4& t = v[d * 4];
-          const unsigned long long w = w2[d * 4];
-          acc[0] = mul_f32x2(unpack16x2_pair<F16>(t.x), w), acc[1] = mul_f32x2(unpack16x2_pair<F16>(t.y), w);
-          acc[2] = mul_f32x2(unpack16x2_pair<F16>(t.z), w), acc[3] = mul_f32x2(unpack16x2_pair<F16>(t.w), w);
-        }
+        // ATen order: nw*w + ne*w + sw*w + se*w
+        texel_fma<F16, true>(acc, vtl, f[d].wtl);
+        texel_fma<F16, false>(acc, vtr, f[d].wtr);
+        texel_fma<F16, false>(acc, vbl, f[d].wbl);
+        texel_fma<F16, false>(acc, vbr, f[d].wbr);
 #pragma unroll
-        for (int k = 1; k < 4; ++k) {
-          const uint4& t = v[d * 4 + k];
-          const unsigned long long w = w2[d * 4 + k];
-          acc[0] = fma_f32x2(unpack16x2_pair<F16>(t.x), w, acc[0]), acc[1] = fma_f32x2(unpack16x2_pair<F16>(t.y), w, acc[1]);
-          acc[2] = fma_f32x2(unpack16x2_pair<F16>(t.z), w, acc[2]), acc[3] = fma_f32x2(unpack16x2_pair<F16>(t.w), w, acc[3]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) mean[e] = add_f32x2(mean[e], acc[e]);
+        for (int e = 0; e < 4; ++e) mean[e] = d == 0 ? acc[e] : add_f32x2(mean[e], acc[e]);
         uint4 o;
         o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
         o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
@@ -277,9 +300,12 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
   if (feat_layout == NVSR_FEAT_TILE_BF16 || feat_layout == NVSR_FEAT_TILE_F16) {
     const bool f16 = feat_layout == NVSR_FEAT_TILE_F16;
     if (pl->dtype != (f16 ? NVSR_F16 : NVSR_BF16)) return NVSR_ERR_UNSUPPORTED;
-    auto kernel = f16 ? gather_tile_16<true> : gather_tile_16<false>;
+    for (int d = 0; d < 3; ++d) NVSR_CHECK_ARG(pl->rw[d] >= 2);  // the footprint is read as an x pair
+    const bool c48 = pl->channels == 48;
+    auto kernel = f16 ? (c48 ? gather_tile_16<true, 6> : gather_tile_16<true, 0>)
+                      : (c48 ? gather_tile_16<false, 6> : gather_tile_16<false, 0>);
     int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
-    int64_t grid = (int64_t)kNumSMs * 6 * 4;  // a few waves of the 6 resident CTAs per SM, grid-stride beyond
+    int64_t grid = (int64_t)kNumSMs * 5 * 4;  // a few waves of the 5 resident CTAs per SM, grid-stride beyond
     if (grid > n_tiles) grid = n_tiles;
     kernel<<<(unsigned)grid, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_tiles);
     NVSR_RETURN_LAST_ERROR();

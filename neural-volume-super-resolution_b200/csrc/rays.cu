@@ -94,6 +94,31 @@ __global__ void pack_plane_kernel(const float* __restrict__ src, int C, int64_t 
   }
 }
 
+// NCHW fp32 -> 16-bit "row-chunk-major" image [Rh][C/8][Rw][8]: the 8-channel chunk c of the texels of one
+// plane row is contiguous along x, so the x0 / x0+1 corners of a bilinear footprint are adjacent 16-byte
+// units and the footprints of neighbouring rays fall into the same 128-byte line (csrc/gather.cu).
+// One thread per (y, chunk, x): 8 coalesced-along-x reads, one 16-byte store.  Values beyond the fp16
+// range saturate to +-65504 (the interpolation is a convex combination, so features stay finite).
+template <bool F16>
+__global__ void pack_plane16_kernel(const float* __restrict__ src, int C, int rh, int rw, uint4* __restrict__ dst) {
+  const int CH = C / 8;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)rh * CH * rw;
+  if (idx >= total) return;
+  int x = (int)(idx % rw);
+  int c8 = (int)((idx / rw) % CH);
+  int y = (int)(idx / ((int64_t)rw * CH));
+  const int64_t HW = (int64_t)rh * rw;
+  const float* s = src + (int64_t)(c8 * 8) * HW + (int64_t)y * rw + x;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = s[e * HW];
+  uint4 o;
+  o.x = pack16x2<F16>(v[0], v[1]), o.y = pack16x2<F16>(v[2], v[3]);
+  o.z = pack16x2<F16>(v[4], v[5]), o.w = pack16x2<F16>(v[6], v[7]);
+  dst[idx] = o;
+}
+
 // W [n_out,k] (ld) fp32 -> 16-bit image [k_pad/8][n_out][8]
 template <typename OutT>
 __global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int k, int ldw, int k_pad,
@@ -236,13 +261,18 @@ extern "C" int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int3
   int64_t HW = (int64_t)rh * rw;
   dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)((channels + 31) / 32));
   dim3 block(32, 8);
-  if (dst_dtype == NVSR_F32)
+  if (dst_dtype == NVSR_F32) {
     pack_plane_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (float*)dst);
-  else if (dst_dtype == NVSR_BF16)
-    pack_plane_kernel<__nv_bfloat16>
-        <<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (__nv_bfloat16*)dst);
-  else
-    pack_plane_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (__half*)dst);
+  } else {
+    NVSR_CHECK_ARG(channels % 8 == 0);
+    if (!aligned16(dst)) return NVSR_ERR_ALIGNMENT;
+    int64_t total = HW * (channels / 8);
+    unsigned blocks = (unsigned)ceil_div64(total, 256);
+    if (dst_dtype == NVSR_BF16)
+      pack_plane16_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(src_nchw, channels, rh, rw, (uint4*)dst);
+    else
+      pack_plane16_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src_nchw, channels, rh, rw, (uint4*)dst);
+  }
   NVSR_RETURN_LAST_ERROR();
 }
 

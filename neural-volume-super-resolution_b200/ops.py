@@ -143,7 +143,8 @@ def prepare_rays(ray_origins, ray_directions, use_ndc=False, height=0, width=0, 
 
 # ---------------------------------------------------------------------------------------------
 def pack_plane(plane_nchw, dtype=NVSR_F32):
-    """[1,C,Rh,Rw] fp32 (models.py:436-439) -> channels-last [Rh,Rw,C] fp32|bf16."""
+    """[1,C,Rh,Rw] fp32 (models.py:436-439) -> device plane image: fp32 channels-last [Rh,Rw,C], or 16-bit
+    row-chunk-major [Rh,C/8,Rw,8] (nvsr.h: the x-neighbour of a texel chunk is the next 16-byte unit)."""
     lib = _lib.load()
     p = _f32c(plane_nchw.detach())
     _require_cuda(p, "plane")
@@ -151,7 +152,12 @@ def pack_plane(plane_nchw, dtype=NVSR_F32):
         assert p.shape[0] == 1
         p = p[0]
     c, rh, rw = p.shape
-    out = torch.empty((rh, rw, c), dtype=TORCH_DTYPE[dtype], device=p.device)
+    if dtype == NVSR_F32:
+        out = torch.empty((rh, rw, c), dtype=torch.float32, device=p.device)
+    else:
+        if c % 8:
+            raise ValueError("16-bit planes need a channel count that is a multiple of 8")
+        out = torch.empty((rh, c // 8, rw, 8), dtype=TORCH_DTYPE[dtype], device=p.device)
     with torch.cuda.device(p.device):
         st = _call("nvsr_pack_plane", lib.nvsr_pack_plane, _ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
     _lib.check(st, "nvsr_pack_plane")
@@ -181,20 +187,20 @@ class PackedPlanes:
     """Device-resident, channels-last position planes of one scene + box + projection matrices."""
 
     def __init__(self, planes, dtype, box_lo, box_rng, proj, vplane=None, view_lo_rng=None):
-        self.planes = planes            # list of 3 tensors [Rh,Rw,C]
+        self.planes = planes            # list of 3 tensors: fp32 [Rh,Rw,C] or 16-bit [Rh,C/8,Rw,8]
         self.dtype = dtype
         self.box_lo = [float(v) for v in box_lo]
         self.box_rng = [float(v) for v in box_rng]
         self.proj = proj                # 3 x [3][2] nested lists
         self.vplane = vplane            # [Rh,Rw,C] fp32 view-direction plane or None
         self.view_lo_rng = view_lo_rng  # (az_lo, az_rng, el_lo, el_rng)
-        self.channels = planes[0].shape[-1]
+        self.channels = planes[0].shape[-1] if planes[0].dim() == 3 else planes[0].shape[1] * 8
 
     def cstruct(self):
         s = _lib.Planes()
         for d in range(3):
             s.plane[d] = self.planes[d].data_ptr()
-            s.rh[d], s.rw[d] = self.planes[d].shape[0], self.planes[d].shape[1]
+            s.rh[d], s.rw[d] = self.planes[d].shape[0], self.planes[d].shape[-2]
             s.box_lo[d], s.box_rng[d] = self.box_lo[d], self.box_rng[d]
             for i in range(3):
                 for j in range(2):
