@@ -82,10 +82,11 @@ int32_t nvsr_prepare_rays(const float* ro_in, const float* rd_in, int64_t n_rays
 /* ------------------------------------------------------------------------------------------------
  * plane re-pack (once per scene / per SR inference): reference planes are NCHW fp32 [1,C,Rh,Rw]
  * (models.py:436-439).  dst_dtype NVSR_F32: channels-last [Rh][Rw][C] fp32 (parity-mode gather, view
- * plane).  NVSR_BF16 | NVSR_F16: "row-chunk-major" [Rh][C/8][Rw][8] 16-bit, C % 8 == 0 — the 8-channel
- * chunk c of texel (y,x) is the 16-byte unit (y*(C/8) + c)*Rw + x, so the two x corners of a bilinear
- * footprint are adjacent units and neighbouring rays share 128-byte lines; values are saturated to the
- * 16-bit format's finite range.  dst must be 16-byte aligned for the 16-bit forms.
+ * plane).  NVSR_BF16 | NVSR_F16: "x-pair records" [Rh][C/8][Rw][2][8] 16-bit, C % 8 == 0 — the 32-byte
+ * record (y*(C/8) + c)*Rw + x holds the 8-channel chunk c of texel (y,x) followed by the same chunk of
+ * texel (y, min(x+1, Rw-1)): both x corners of a bilinear footprint row arrive with one 256-bit load and
+ * neighbouring rays share 128-byte lines (2x the plane bytes: 7.7 MB per 200^2 plane, 123 MB per 800^2).
+ * Values are saturated to the 16-bit format's finite range.  dst must be 32-byte aligned for these.
  */
 int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int32_t rw, void* dst,
                         int32_t dst_dtype, void* stream);
@@ -102,8 +103,8 @@ int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, int32_t ldw
  * :355-361 combine_pos_planes('avg')).
  */
 typedef struct nvsr_planes {
-  const void* plane[3];   /* nvsr_pack_plane images: fp32 [rh][rw][channels] | 16-bit [rh][channels/8][rw][8] */
-  int32_t rh[3], rw[3];   /* 16-bit planes: rw >= 2 */
+  const void* plane[3];   /* nvsr_pack_plane images: fp32 [rh][rw][channels] | 16-bit [rh][channels/8][rw][2][8] */
+  int32_t rh[3], rw[3];
   int32_t channels;       /* multiple of 8, <= 64 */
   int32_t dtype;          /* NVSR_F32 | NVSR_BF16 | NVSR_F16 */
   float box_lo[3];        /* fp32(box_coords[scene][0,:3]) */

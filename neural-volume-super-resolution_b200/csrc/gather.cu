@@ -157,26 +157,33 @@ __device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Per row and plane: the two plane rows (y0, y1) of the footprint at its left column, and the four
-// weights in (left, right) form.  16-bit planes are "row-chunk-major" [Rh][C/8][Rw][8] (rays.cu
-// pack_plane16_kernel): chunk c of texel (y, x) sits at ((y*CH + c)*Rw + x)*16 B, so the right corner is
-// the NEXT 16-byte unit (+1) of the left one and the footprints of the 8 adjacent rays of a quarter
-// warp land in one or two 128-byte lines per load instruction.  At the right border (x0 == Rw-1; the
-// right weights are exactly 0 there) the pair is shifted one texel left and the weights swap sides, so
-// the +1 access never leaves the plane row.
+// Per row and plane: the two plane rows (y0, y1) of the footprint at its left column x0, and the four
+// weights.  16-bit planes are "x-pair records" [Rh][C/8][Rw][2][8] (rays.cu pack_plane16_kernel): the
+// 32-byte record (y, c, x) holds the 8-channel chunk c of texel (y, x) followed by the same chunk of its
+// right neighbour (y, min(x+1, Rw-1)), so ONE 256-bit load fetches both x corners of a footprint row —
+// half the load instructions and L1 data-pipe wavefronts of separate 16-byte corner loads — and the
+// footprints of the adjacent rays of a quarter warp fall into one or two 128-byte lines.
 struct Foot {
-  uint32_t top, bot;      // 16-byte-unit offsets of (y0, xl), (y1, xl), chunk 0
-  float wtl, wtr, wbl, wbr;
+  uint32_t top, bot;      // record offsets of (y0, x0), (y1, x0), chunk 0
+  float w00, w01, w10, w11;
 };
 __device__ __forceinline__ Foot make_foot(const Bilin& b, int rw, int CH) {
   Foot f;
-  const bool edge = b.x0 >= rw - 1;
-  const int xl = edge ? rw - 2 : b.x0;
-  f.top = (uint32_t)((b.y0 * CH) * rw + xl);
-  f.bot = (uint32_t)((b.y1 * CH) * rw + xl);
-  f.wtl = edge ? 0.f : b.w00, f.wtr = edge ? b.w00 : b.w01;
-  f.wbl = edge ? 0.f : b.w10, f.wbr = edge ? b.w10 : b.w11;
+  f.top = (uint32_t)((b.y0 * CH) * rw + b.x0);
+  f.bot = (uint32_t)((b.y1 * CH) * rw + b.x0);
+  f.w00 = b.w00, f.w01 = b.w01, f.w10 = b.w10, f.w11 = b.w11;
   return f;
+}
+struct alignas(32) XPair {
+  uint4 l, r;  // chunk of texel x0, chunk of texel x0+1
+};
+// 256-bit read-only load (LDG.E.256, sm_100+)
+__device__ __forceinline__ XPair ldg256(const XPair* p) {
+  XPair v;
+  asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v.l.x), "=r"(v.l.y), "=r"(v.l.z), "=r"(v.l.w), "=r"(v.r.x), "=r"(v.r.y), "=r"(v.r.z), "=r"(v.r.w)
+      : "l"(p));
+  return v;
 }
 
 // acc[e] (+)= unpack(t) * w for the 4 channel pairs of one 16-byte texel chunk
@@ -206,9 +213,9 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
   const int TS = tiles_per_block(a.S);
   const int r = threadIdx.x;
   const unsigned long long third = pack_f32x2(1.f / 3.f, 1.f / 3.f);
-  const uint4* const pl0 = reinterpret_cast<const uint4*>(p.plane[0]);
-  const uint4* const pl1 = reinterpret_cast<const uint4*>(p.plane[1]);
-  const uint4* const pl2 = reinterpret_cast<const uint4*>(p.plane[2]);
+  const XPair* const pl0 = reinterpret_cast<const XPair*>(p.plane[0]);
+  const XPair* const pl1 = reinterpret_cast<const XPair*>(p.plane[1]);
+  const XPair* const pl2 = reinterpret_cast<const XPair*>(p.plane[2]);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- per-row sample position -> 3 planes' footprints (registers) ----
@@ -229,23 +236,22 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
     }
     uint8_t* gP = featP + tile * (int64_t)p_bytes + (uint32_t)r * 16u;
     uint8_t* gM = featM + tile * (int64_t)m_bytes + (uint32_t)r * 16u;
-    const uint4* rowT[3] = {pl0 + f[0].top, pl1 + f[1].top, pl2 + f[2].top};
-    const uint4* rowB[3] = {pl0 + f[0].bot, pl1 + f[1].bot, pl2 + f[2].bot};
+    const XPair* rowT[3] = {pl0 + f[0].top, pl1 + f[1].top, pl2 + f[2].top};
+    const XPair* rowB[3] = {pl0 + f[0].bot, pl1 + f[1].bot, pl2 + f[2].bot};
     // ---- channel chunks ----
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       unsigned long long mean[4];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const uint4* t = rowT[d] + c * p.rw[d];
-        const uint4* bt = rowB[d] + c * p.rw[d];
-        const uint4 vtl = __ldg(t), vtr = __ldg(t + 1), vbl = __ldg(bt), vbr = __ldg(bt + 1);
+        const XPair vt = ldg256(rowT[d] + c * p.rw[d]);
+        const XPair vb = ldg256(rowB[d] + c * p.rw[d]);
         unsigned long long acc[4];
         // ATen order: nw*w + ne*w + sw*w + se*w
-        texel_fma<F16, true>(acc, vtl, f[d].wtl);
-        texel_fma<F16, false>(acc, vtr, f[d].wtr);
-        texel_fma<F16, false>(acc, vbl, f[d].wbl);
-        texel_fma<F16, false>(acc, vbr, f[d].wbr);
+        texel_fma<F16, true>(acc, vt.l, f[d].w00);
+        texel_fma<F16, false>(acc, vt.r, f[d].w01);
+        texel_fma<F16, false>(acc, vb.l, f[d].w10);
+        texel_fma<F16, false>(acc, vb.r, f[d].w11);
 #pragma unroll
         for (int e = 0; e < 4; ++e) mean[e] = d == 0 ? acc[e] : add_f32x2(mean[e], acc[e]);
         uint4 o;
@@ -273,7 +279,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
   NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64);
   for (int d = 0; d < 3; ++d) {
     NVSR_CHECK_ARG(pl->plane[d] && pl->rh[d] > 0 && pl->rw[d] > 0);
-    if (!aligned16(pl->plane[d])) return NVSR_ERR_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(pl->plane[d]) & (is_16bit(pl->dtype) ? 31u : 15u)) != 0) return NVSR_ERR_ALIGNMENT;
   }
   if (!aligned16(feat_p) || !aligned16(feat_m)) return NVSR_ERR_ALIGNMENT;
   if (s->n_rays == 0) return NVSR_OK;
@@ -300,7 +306,6 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
   if (feat_layout == NVSR_FEAT_TILE_BF16 || feat_layout == NVSR_FEAT_TILE_F16) {
     const bool f16 = feat_layout == NVSR_FEAT_TILE_F16;
     if (pl->dtype != (f16 ? NVSR_F16 : NVSR_BF16)) return NVSR_ERR_UNSUPPORTED;
-    for (int d = 0; d < 3; ++d) NVSR_CHECK_ARG(pl->rw[d] >= 2);  // the footprint is read as an x pair
     const bool c48 = pl->channels == 48;
     auto kernel = f16 ? (c48 ? gather_tile_16<true, 6> : gather_tile_16<true, 0>)
                       : (c48 ? gather_tile_16<false, 6> : gather_tile_16<false, 0>);

@@ -94,11 +94,12 @@ __global__ void pack_plane_kernel(const float* __restrict__ src, int C, int64_t 
   }
 }
 
-// NCHW fp32 -> 16-bit "row-chunk-major" image [Rh][C/8][Rw][8]: the 8-channel chunk c of the texels of one
-// plane row is contiguous along x, so the x0 / x0+1 corners of a bilinear footprint are adjacent 16-byte
-// units and the footprints of neighbouring rays fall into the same 128-byte line (csrc/gather.cu).
-// One thread per (y, chunk, x): 8 coalesced-along-x reads, one 16-byte store.  Values beyond the fp16
-// range saturate to +-65504 (the interpolation is a convex combination, so features stay finite).
+// NCHW fp32 -> 16-bit "x-pair record" image [Rh][C/8][Rw][2][8]: the 32-byte record (y, c, x) holds the
+// 8-channel chunk c of texel (y, x) and of its right neighbour (y, min(x+1, Rw-1)), so a bilinear
+// footprint row is ONE 256-bit load and neighbouring rays share 128-byte lines (csrc/gather.cu).
+// One thread per record: 8 coalesced-along-x reads (the neighbour's come from L1), two 16-byte stores.
+// Values beyond the format's finite range saturate (the interpolation is a convex combination, so
+// features stay finite).
 template <bool F16>
 __global__ void pack_plane16_kernel(const float* __restrict__ src, int C, int rh, int rw, uint4* __restrict__ dst) {
   const int CH = C / 8;
@@ -109,14 +110,18 @@ __global__ void pack_plane16_kernel(const float* __restrict__ src, int C, int rh
   int c8 = (int)((idx / rw) % CH);
   int y = (int)(idx / ((int64_t)rw * CH));
   const int64_t HW = (int64_t)rh * rw;
-  const float* s = src + (int64_t)(c8 * 8) * HW + (int64_t)y * rw + x;
-  float v[8];
+  const float* s = src + (int64_t)(c8 * 8) * HW + (int64_t)y * rw;
+  const int xr = min(x + 1, rw - 1);
+  float v[8], w[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = s[e * HW];
-  uint4 o;
+  for (int e = 0; e < 8; ++e) v[e] = s[e * HW + x], w[e] = s[e * HW + xr];
+  uint4 o, q;
   o.x = pack16x2<F16>(v[0], v[1]), o.y = pack16x2<F16>(v[2], v[3]);
   o.z = pack16x2<F16>(v[4], v[5]), o.w = pack16x2<F16>(v[6], v[7]);
-  dst[idx] = o;
+  q.x = pack16x2<F16>(w[0], w[1]), q.y = pack16x2<F16>(w[2], w[3]);
+  q.z = pack16x2<F16>(w[4], w[5]), q.w = pack16x2<F16>(w[6], w[7]);
+  dst[idx * 2] = o;
+  dst[idx * 2 + 1] = q;
 }
 
 // W [n_out,k] (ld) fp32 -> 16-bit image [k_pad/8][n_out][8]
@@ -265,7 +270,7 @@ extern "C" int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int3
     pack_plane_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src_nchw, channels, HW, (float*)dst);
   } else {
     NVSR_CHECK_ARG(channels % 8 == 0);
-    if (!aligned16(dst)) return NVSR_ERR_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) != 0) return NVSR_ERR_ALIGNMENT;
     int64_t total = HW * (channels / 8);
     unsigned blocks = (unsigned)ceil_div64(total, 256);
     if (dst_dtype == NVSR_BF16)

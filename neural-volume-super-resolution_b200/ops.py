@@ -144,7 +144,7 @@ def prepare_rays(ray_origins, ray_directions, use_ndc=False, height=0, width=0, 
 # ---------------------------------------------------------------------------------------------
 def pack_plane(plane_nchw, dtype=NVSR_F32):
     """[1,C,Rh,Rw] fp32 (models.py:436-439) -> device plane image: fp32 channels-last [Rh,Rw,C], or 16-bit
-    row-chunk-major [Rh,C/8,Rw,8] (nvsr.h: the x-neighbour of a texel chunk is the next 16-byte unit)."""
+    x-pair records [Rh,C/8,Rw,2,8] (nvsr.h: 8-channel chunk of a texel followed by its right neighbour's)."""
     lib = _lib.load()
     p = _f32c(plane_nchw.detach())
     _require_cuda(p, "plane")
@@ -157,7 +157,7 @@ def pack_plane(plane_nchw, dtype=NVSR_F32):
     else:
         if c % 8:
             raise ValueError("16-bit planes need a channel count that is a multiple of 8")
-        out = torch.empty((rh, c // 8, rw, 8), dtype=TORCH_DTYPE[dtype], device=p.device)
+        out = torch.empty((rh, c // 8, rw, 2, 8), dtype=TORCH_DTYPE[dtype], device=p.device)
     with torch.cuda.device(p.device):
         st = _call("nvsr_pack_plane", lib.nvsr_pack_plane, _ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
     _lib.check(st, "nvsr_pack_plane")
@@ -187,7 +187,7 @@ class PackedPlanes:
     """Device-resident, channels-last position planes of one scene + box + projection matrices."""
 
     def __init__(self, planes, dtype, box_lo, box_rng, proj, vplane=None, view_lo_rng=None):
-        self.planes = planes            # list of 3 tensors: fp32 [Rh,Rw,C] or 16-bit [Rh,C/8,Rw,8]
+        self.planes = planes            # list of 3 tensors: fp32 [Rh,Rw,C] or 16-bit [Rh,C/8,Rw,2,8]
         self.dtype = dtype
         self.box_lo = [float(v) for v in box_lo]
         self.box_rng = [float(v) for v in box_rng]
@@ -200,7 +200,7 @@ class PackedPlanes:
         s = _lib.Planes()
         for d in range(3):
             s.plane[d] = self.planes[d].data_ptr()
-            s.rh[d], s.rw[d] = self.planes[d].shape[0], self.planes[d].shape[-2]
+            s.rh[d], s.rw[d] = self.planes[d].shape[0], self.planes[d].shape[1 if self.planes[d].dim() == 3 else 2]
             s.box_lo[d], s.box_rng[d] = self.box_lo[d], self.box_rng[d]
             for i in range(3):
                 for j in range(2):
