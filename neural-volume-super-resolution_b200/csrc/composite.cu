@@ -1,9 +1,19 @@
 // a7+a8: alpha compositing with cumulative transmittance, inverse-CDF resampling and sort-merge.
-// One warp per ray; samples are striped over the lanes (sample i -> lane i%32) so every global
-// access is coalesced, and the two scans (cumprod of 1-alpha, cumsum of the pdf) are warp-shuffle
-// scans with a running carry.  Scans run in fp64 and are rounded to fp32 per prefix: that is what
-// the reference's CPU path does (ATen accumulates float cumsum/cumprod in double), so cdf edges —
-// and with them the searchsorted bin indices — track the oracle.
+//
+// composite_kernel: one warp per block of 8 consecutive rays.  Lane = (ray-in-block rl = lane & 7,
+// quarter q = lane >> 3); per 16-sample tile a lane owns 4 consecutive samples (16t + 4q .. +3) of its
+// ray.  In the BLOCKED raw order (what the tcgen05 decoder writes: row = (s % 16) * 8 + ray % 8 inside a
+// 128-row tile) every load instruction of a warp then covers four full 32-byte sectors, without any
+// shared-memory staging or block-wide barrier.  The transmittance cumprod runs sequentially over the
+// lane's 4 samples and as a 2-step shuffle scan over the 4 quarters, with a running carry; it is
+// accumulated in fp64 and rounded to fp32 per prefix — what the reference's CPU path does (ATen
+// accumulates float cumprod/cumsum in double) — so weights, cdf edges and with them the searchsorted
+// bin indices track the oracle.  The map sums accumulate per tile in fp32 and across tiles in fp64.
+// On the coarse pass the warp then resamples its 8 rays one after the other, all 32 lanes on one ray:
+// pdf/cdf in ATen's summation orders, a fixed-trip-count branch-free searchsorted, and the
+// sort(cat(z_vals, z_samples)) as a rank merge whose ranks start from the bin index the inversion just
+// produced (z_samples[j] lies between the two bin centres around it), written out coalesced through a
+// position bitmap.
 #include "common.cuh"
 
 namespace nvsr {
@@ -13,21 +23,7 @@ constexpr unsigned kFull = 0xffffffffu;
 __device__ __forceinline__ double shfl_up_d(double v, int off) { return __shfl_up_sync(kFull, v, off); }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
-
 // inclusive scans over the 32 lanes
-__device__ __forceinline__ double warp_scan_mul(double v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double n = shfl_up_d(v, o);
-    if (lane >= o) v *= n;
-  }
-  return v;
-}
 __device__ __forceinline__ double warp_scan_add(double v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -36,9 +32,6 @@ __device__ __forceinline__ double warp_scan_add(double v, int lane) {
   }
   return v;
 }
-
-// torch.sigmoid on CPU: 1/(1+exp(-x))
-__device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
 
 // total order used by the slow-path merge: NaN sorts last (torch.sort), ties by index
 __device__ __forceinline__ bool key_less(float a, int ia, float b, int ib) {
@@ -57,16 +50,6 @@ __device__ __forceinline__ int upper_bound_f(const float* a, int n, float u) {
   }
   return lo;
 }
-__device__ __forceinline__ int lower_bound_f(const float* a, int n, float x) {  // #(a < x)
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (a[mid] < x) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
-}
-
 // nerf_helpers.py:686-700 given cdf/bins (B entries) in shared memory
 __device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int B, float u, int* ind_out) {
   int ind = upper_bound_f(cdf, B, u);
@@ -154,163 +137,245 @@ struct CompositeArgs {
   int64_t* inds;
   float* z_samples;
   float* z_merged;
-  int row_order;
 };
 
-// BLOCKED raw staging: the 8 rays of a block own one contiguous span of TS*128 floats per channel.
-// The CTA copies it (coalesced) into shared memory as [ch][ray-in-block][pitch]; pitch % 32 == 4 makes
-// both the transposing store (8 rays x 4 samples per warp) and the per-ray reads conflict-free.
-__host__ __device__ inline int stage_pitch(int S) { return ((S - 4 + 31) / 32) * 32 + 4; }
-
-// per-warp shared floats: zv[S+1] | w[S] | cdf[S] | bins[S] | zs[n_fine]
-__host__ __device__ inline int composite_smem_floats(int S, int n_fine) {
-  return (S + 1) + (n_fine > 0 ? 3 * S + n_fine : 0) + 3;
+// searchsorted(a[0..n), u, side='right') = #(a <= u) for sorted a, with a fixed trip count (top = the
+// largest power of two <= n) and no divergent branches.  NaN u -> n, as torch.
+__device__ __forceinline__ int upper_bound_fixed(const float* a, int n, int top, float u) {
+  int pos = 0;
+  for (int step = top; step > 0; step >>= 1) {
+    int p = pos + step;
+    if (p <= n && !(a[p - 1] > u)) pos = p;
+  }
+  return pos;
 }
 
-__global__ void __launch_bounds__(256)
+// sigmoid for the colour channels: MUFU.EX2 + MUFU.RCP (abs error < 3e-7, far inside the 1e-3 map
+// tolerance).  The density path below keeps expf: its weights feed the bit-exact index path.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// row pitch (floats) of the per-warp [8 rays][n] shared arrays: a multiple of 4 (16-byte stores) with
+// pitch % 32 == 4, so the 8 rays of a quarter-warp store phase hit 8 distinct 16-byte bank groups.
+__host__ __device__ inline int pitch4(int n) { return ((n - 4 + 31) / 32) * 32 + 4; }
+
+// per-warp shared floats (coarse pass only): zv[8][P1] | w[8][P] | cdf[S] | bins[S] | zs[n_fine] | bitmap
+__host__ __device__ inline int composite_warp_floats(int S, int S1, int n_fine) {
+  if (n_fine <= 0) return 0;
+  const int n = 8 * pitch4(S1) + 8 * pitch4(S) + 2 * S + n_fine + (S1 + n_fine + 31) / 32;
+  return (n + 3) & ~3;  // every warp's slice stays 16-byte aligned
+}
+
+constexpr int kCompWarps = 4;  // warps per CTA at the usual sample counts (fewer when shared memory is short)
+
+template <bool BLOCKED>
+__global__ void __launch_bounds__(kCompWarps * 32)
 composite_kernel(CompositeArgs a, int warps_per_cta) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
+  const int rl = lane & 7, q = lane >> 3;
   const int S = a.S;
   const int S1 = S + (a.mip ? 1 : 0);  // depth entries per ray
-  float* zv = sm + (size_t)wid * composite_smem_floats(S, a.n_fine);
-  float* wbuf = zv + (S + 1);
-  float* cdf = wbuf + S;
+  const int nf = a.n_fine;
+  const int P = pitch4(S), P1 = pitch4(S1);
+  float* zsm = sm + (size_t)wid * composite_warp_floats(S, S1, nf);
+  float* wsm = zsm + 8 * P1;
+  float* cdf = wsm + 8 * P;
   float* bins = cdf + S;
   float* zs = bins + S;
-  const bool blocked = a.row_order == NVSR_ROWS_BLOCKED;  // then warps_per_cta == kBlkRays
-  float* sraw = sm + (size_t)warps_per_cta * composite_smem_floats(S, a.n_fine);
-  const int P = stage_pitch(S);
+  unsigned* bm = reinterpret_cast<unsigned*>(zs + nf);
   const int TS = tiles_per_block(S);
-  const int64_t n_groups = ceil_div64(a.n_rays, warps_per_cta);
+  const int64_t n_blocks = ceil_div64(a.n_rays, kBlkRays);
+  const bool vec_z = (S1 & 3) == 0 && (reinterpret_cast<uintptr_t>(a.z) & 15u) == 0;
+  const bool vec_w = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(a.weights) & 15u) == 0;
 
-  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int64_t ray = grp * warps_per_cta + wid;
-    if (blocked) {
-      __syncthreads();  // previous group's readers are done with sraw
-      const int span = TS * kTileRows;
-      for (int ch = 0; ch < 4; ++ch) {
-        const float* src = a.raw + ch * a.raw_stride + grp * span;
-        for (int e = threadIdx.x; e < span; e += blockDim.x) {
-          int r = e & (kTileRows - 1);
-          int sidx = (e >> 7) * kBlkSamples + (r >> 3);
-          if (sidx < S) sraw[(ch * kBlkRays + (r & 7)) * P + sidx] = __ldg(src + e);
-        }
-      }
-      __syncthreads();
-    }
-    if (ray >= a.n_rays) continue;
-    __syncwarp();
-    for (int i = lane; i < S1; i += 32) zv[i] = __ldg(a.z + ray * S1 + i);
-    float dx = __ldg(a.rd + ray * 3), dy = __ldg(a.rd + ray * 3 + 1), dz = __ldg(a.rd + ray * 3 + 2);
-    float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    __syncwarp();
+  for (int64_t blk = (int64_t)blockIdx.x * warps_per_cta + wid; blk < n_blocks;
+       blk += (int64_t)gridDim.x * warps_per_cta) {
+    const int64_t ray = blk * kBlkRays + rl;
+    const bool valid = ray < a.n_rays;
+    const int64_t rayc = valid ? ray : a.n_rays - 1;  // clamped: loads stay in bounds, results are dropped
+    const float dx = __ldg(a.rd + rayc * 3), dy = __ldg(a.rd + rayc * 3 + 1), dz = __ldg(a.rd + rayc * 3 + 2);
+    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float* zrow = a.z + rayc * S1;
+    const float* raw_blk = BLOCKED ? a.raw + blk * TS * (int64_t)kTileRows + rl : a.raw + rayc * S;
 
-    const float* raw_r = blocked ? sraw + wid * P : a.raw + ray * S;
-    const int64_t chs = blocked ? (int64_t)kBlkRays * P : a.raw_stride;
-    double carry = 1.0;  // product of (1-alpha+1e-10) over previous chunks
+    double carry = 1.0;  // product of (1-alpha+1e-10) over the previous tiles
     double sr = 0.0, sg = 0.0, sb = 0.0, sd = 0.0, sa = 0.0;
-    for (int base = 0; base < S; base += 32) {
-      int i = base + lane;
-      float alpha = 0.f, r = 0.f, g = 0.f, b = 0.f, zc = 0.f;
-      double t = 1.0;
-      if (i < S) {
-        float dist;
-        if (a.mip) {
-          dist = __fsub_rn(zv[i + 1], zv[i]);
-          zc = __fmul_rn(0.5f, __fadd_rn(zv[i], zv[i + 1]));
-        } else {
-          dist = (i + 1 < S) ? __fsub_rn(zv[i + 1], zv[i]) : 1e10f;
-          zc = zv[i];
+    if (nf > 0) __syncwarp();  // the previous block's resampling is done with zsm / wsm
+    for (int t = 0; t < TS; ++t) {
+      const int s0 = t * kBlkSamples + 4 * q;
+      // ---- depths s0 .. s0+4 ----
+      float zz[5];
+      if (vec_z && s0 + 4 <= S1) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(zrow + s0));
+        zz[0] = v.x, zz[1] = v.y, zz[2] = v.z, zz[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) zz[j] = (s0 + j < S1) ? __ldg(zrow + s0 + j) : 0.f;
+      }
+      zz[4] = (s0 + 4 < S1) ? __ldg(zrow + s0 + 4) : 0.f;
+      if (nf > 0) {  // keep the depths for the resampling pass (entries beyond S1 are zeros, never used)
+        float* zd = zsm + rl * P1 + s0;
+        if (s0 + 4 <= P1) *reinterpret_cast<float4*>(zd) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+        if (q == 3 && s0 + 4 < S1) zd[4] = zz[4];  // mip: the last edge when S is a multiple of 16
+      }
+      // ---- radiance samples ----
+      float alpha[4], cr[4], cg[4], cb[4], zc[4];
+      double tt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = s0 + j;
+        const bool live = valid && s < S;
+        alpha[j] = 0.f, cr[j] = 0.f, cg[j] = 0.f, cb[j] = 0.f, zc[j] = 0.f, tt[j] = 1.0;
+        if (live) {
+          const float* rp = BLOCKED ? raw_blk + t * kTileRows + (4 * q + j) * kBlkRays : raw_blk + s;
+          const float r0 = __ldg(rp), r1 = __ldg(rp + a.raw_stride), r2 = __ldg(rp + 2 * a.raw_stride);
+          float sig = __ldg(rp + 3 * a.raw_stride);
+          float dist;
+          if (a.mip) {
+            dist = __fsub_rn(zz[j + 1], zz[j]);
+            zc[j] = __fmul_rn(0.5f, __fadd_rn(zz[j], zz[j + 1]));
+          } else {
+            dist = (s + 1 < S) ? __fsub_rn(zz[j + 1], zz[j]) : 1e10f;
+            zc[j] = zz[j];
+          }
+          dist = __fmul_rn(dist, dnorm);
+          cr[j] = sigmoid_fast(r0), cg[j] = sigmoid_fast(r1), cb[j] = sigmoid_fast(r2);
+          if (a.noise) sig = __fadd_rn(sig, __ldg(a.noise + ray * S + s));
+          sig = fmaxf(sig, 0.f);
+          alpha[j] = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
+          tt[j] = (double)__fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
         }
-        dist = __fmul_rn(dist, dnorm);
-        r = sigmoid_ref(raw_r[i]);
-        g = sigmoid_ref(raw_r[chs + i]);
-        b = sigmoid_ref(raw_r[2 * chs + i]);
-        float sig = raw_r[3 * chs + i];
-        if (a.noise) sig = __fadd_rn(sig, __ldg(a.noise + ray * S + i));
-        sig = fmaxf(sig, 0.f);
-        alpha = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
-        t = (double)__fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
       }
-      double inc = warp_scan_mul(t, lane);
-      double prev = shfl_up_d(inc, 1);
-      double excl = carry * (lane ? prev : 1.0);
-      carry *= shfl_d(inc, 31);
-      if (i < S) {
-        float T = (float)excl;
-        float w = __fmul_rn(alpha, T);
-        if (a.weights) a.weights[ray * S + i] = w;
-        if (a.n_fine > 0) wbuf[i] = w;
-        sr += (double)__fmul_rn(w, r);
-        sg += (double)__fmul_rn(w, g);
-        sb += (double)__fmul_rn(w, b);
-        sd += (double)__fmul_rn(w, zc);
-        sa += (double)w;
+      // ---- exclusive cumprod: over the 4 quarters of the ray (lanes rl, rl+8, rl+16, rl+24), then in-lane ----
+      double incl = (tt[0] * tt[1]) * (tt[2] * tt[3]);
+      {
+        double n1 = shfl_up_d(incl, 8);
+        if (q >= 1) incl *= n1;
+        double n2 = shfl_up_d(incl, 16);
+        if (q >= 2) incl *= n2;
       }
+      double excl = shfl_up_d(incl, 8);
+      double run = carry * (q ? excl : 1.0);
+      carry *= shfl_d(incl, 24 + rl);
+      float w[4];
+      float pr = 0.f, pg = 0.f, pb = 0.f, pd = 0.f, pa = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        w[j] = __fmul_rn(alpha[j], (float)run);
+        run *= tt[j];
+        pr = fmaf(w[j], cr[j], pr), pg = fmaf(w[j], cg[j], pg), pb = fmaf(w[j], cb[j], pb);
+        pd = fmaf(w[j], zc[j], pd), pa += w[j];
+      }
+      sr += (double)pr, sg += (double)pg, sb += (double)pb, sd += (double)pd, sa += (double)pa;
+      if (a.weights && valid) {
+        float* wd = a.weights + ray * S + s0;
+        if (vec_w && s0 + 4 <= S) *reinterpret_cast<float4*>(wd) = make_float4(w[0], w[1], w[2], w[3]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (s0 + j < S) wd[j] = w[j];
+        }
+      }
+      if (nf > 0 && s0 + 4 <= P) *reinterpret_cast<float4*>(wsm + rl * P + s0) = make_float4(w[0], w[1], w[2], w[3]);
     }
-    sr = warp_sum_d(sr), sg = warp_sum_d(sg), sb = warp_sum_d(sb), sd = warp_sum_d(sd), sa = warp_sum_d(sa);
-    if (lane == 0) {
+    // ---- per-ray maps: reduce the 4 quarters, quarter 0 writes ----
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      sr += __shfl_xor_sync(kFull, sr, o), sg += __shfl_xor_sync(kFull, sg, o), sb += __shfl_xor_sync(kFull, sb, o);
+      sd += __shfl_xor_sync(kFull, sd, o), sa += __shfl_xor_sync(kFull, sa, o);
+    }
+    if (q == 0 && valid) {
       float accv = (float)sa, depthv = (float)sd;
-      float cr = (float)sr, cg = (float)sg, cb = (float)sb;
+      float vr = (float)sr, vg = (float)sg, vb = (float)sb;
       // 1/max(1e-10, depth/acc): torch.max propagates NaN (acc == 0 -> 0/0)
-      float q = __fdiv_rn(depthv, accv);
-      float m = isnan(q) ? q : fmaxf(1e-10f, q);
+      float qd = __fdiv_rn(depthv, accv);
+      float m = isnan(qd) ? qd : fmaxf(1e-10f, qd);
       float dispv = __fdiv_rn(1.f, m);
       if (a.white_bkgd) {
         float bg = __fsub_rn(1.f, accv);
-        cr = __fadd_rn(cr, bg), cg = __fadd_rn(cg, bg), cb = __fadd_rn(cb, bg);
+        vr = __fadd_rn(vr, bg), vg = __fadd_rn(vg, bg), vb = __fadd_rn(vb, bg);
       }
-      a.rgb[ray * 3] = cr, a.rgb[ray * 3 + 1] = cg, a.rgb[ray * 3 + 2] = cb;
+      a.rgb[ray * 3] = vr, a.rgb[ray * 3 + 1] = vg, a.rgb[ray * 3 + 2] = vb;
       a.disp[ray] = dispv, a.acc[ray] = accv, a.depth[ray] = depthv;
     }
-    if (a.n_fine <= 0) continue;
+    if (nf <= 0) continue;
 
-    // ---- hierarchical resampling: train_utils.py:144-156 + nerf_helpers.py:668-702 ----
+    // ---- hierarchical resampling, one ray at a time on all 32 lanes:
+    //      train_utils.py:144-156 + nerf_helpers.py:668-702 ----
     __syncwarp();
     const int B = S - 1;  // bins (z_mid; mip: mids of mids)
-    for (int i = lane; i < B; i += 32) {
-      float m0 = __fmul_rn(0.5f, __fadd_rn(zv[i + 1], zv[i]));
-      if (a.mip) {
-        float m1 = __fmul_rn(0.5f, __fadd_rn(zv[i + 2], zv[i + 1]));
-        m0 = __fmul_rn(0.5f, __fadd_rn(m1, m0));
-      }
-      bins[i] = m0;
-    }
-    build_cdf(wbuf + 1, S - 2, cdf, lane);  // weights[...,1:-1]
-    __syncwarp();
-    const int nf = a.n_fine;
-    for (int j = lane; j < nf; j += 32) {
-      float u = a.u_per_ray ? __ldg(a.u + ray * nf + j) : __ldg(a.u + j);
-      int ind;
-      float smp = invert_cdf(cdf, bins, B, u, &ind);
-      zs[j] = smp;
-      if (a.inds) a.inds[ray * nf + j] = ind;
-      if (a.z_samples) a.z_samples[ray * nf + j] = smp;
-    }
-    __syncwarp();
-    // ---- sort(cat(z_vals, z_samples)): merge by rank ----
-    bool sorted = true;
-    for (int i = lane; i + 1 < S1; i += 32) sorted &= (zv[i] <= zv[i + 1]);
-    for (int j = lane; j + 1 < nf; j += 32) sorted &= (zs[j] <= zs[j + 1]);
-    sorted = __all_sync(kFull, sorted);
-    float* out = a.z_merged + ray * (int64_t)(S1 + nf);
-    if (sorted) {
-      for (int i = lane; i < S1; i += 32) out[i + lower_bound_f(zs, nf, zv[i])] = zv[i];
-      for (int j = lane; j < nf; j += 32) out[j + upper_bound_f(zv, S1, zs[j])] = zs[j];
-    } else {
-      // rare (rounding-induced inversions, random u, NaNs): all-pairs ranking, still exact
-      const int M = S1 + nf;
-      for (int e = lane; e < M; e += 32) {
-        float x = e < S1 ? zv[e] : zs[e - S1];
-        int rank = 0;
-        for (int k = 0; k < M; ++k) {
-          float y = k < S1 ? zv[k] : zs[k - S1];
-          rank += key_less(y, k, x, e) ? 1 : 0;
+    int top = 1;
+    while (top * 2 <= B) top *= 2;
+    const int M = S1 + nf;
+    const int n_words = (M + 31) >> 5;
+    for (int r = 0; r < kBlkRays; ++r) {
+      const int64_t rr = blk * kBlkRays + r;
+      if (rr >= a.n_rays) break;
+      const float* zv = zsm + r * P1;
+      const float* wv = wsm + r * P;
+      for (int i = lane; i < B; i += 32) {
+        float m0 = __fmul_rn(0.5f, __fadd_rn(zv[i + 1], zv[i]));
+        if (a.mip) {
+          float m1 = __fmul_rn(0.5f, __fadd_rn(zv[i + 2], zv[i + 1]));
+          m0 = __fmul_rn(0.5f, __fadd_rn(m1, m0));
         }
-        out[rank] = x;
+        bins[i] = m0;
       }
+      for (int k = lane; k < n_words; k += 32) bm[k] = 0u;
+      build_cdf(wv + 1, S - 2, cdf, lane);  // weights[...,1:-1]
+      __syncwarp();
+      bool sorted = true;
+      for (int i = lane; i + 1 < S1; i += 32) sorted &= (zv[i] <= zv[i + 1]);
+      for (int j = lane; j < nf; j += 32) {
+        const float u = a.u_per_ray ? __ldg(a.u + rr * nf + j) : __ldg(a.u + j);
+        const int ind = upper_bound_fixed(cdf, B, top, u);
+        const int below = max(0, ind - 1), above = min(B - 1, ind);
+        const float cb_ = cdf[below], ca_ = cdf[above];
+        float denom = __fsub_rn(ca_, cb_);
+        if (denom < 1e-5f) denom = 1.f;
+        const float tq = __fdiv_rn(__fsub_rn(u, cb_), denom);
+        const float bb = bins[below], ba = bins[above];
+        const float x = __fadd_rn(bb, __fmul_rn(tq, __fsub_rn(ba, bb)));
+        zs[j] = x;
+        if (a.inds) a.inds[rr * nf + j] = ind;
+        if (a.z_samples) a.z_samples[rr * nf + j] = x;
+        // rank of z_samples[j] in the merge = j + #(z_vals <= z_samples[j]).  The sample lies between the
+        // bin centres around the bin it was drawn from, so the count starts at that bin index and is
+        // corrected by a couple of probes (exact whenever z_vals is sorted; the guess only sets the probe
+        // count).  The position goes into the bitmap; it is used only if both inputs turn out sorted.
+        int c = min(max(ind + a.mip, 1), S1);
+        while (c < S1 && zv[c] <= x) ++c;
+        while (c > 0 && zv[c - 1] > x) --c;
+        const int pos = j + c;
+        atomicOr(&bm[pos >> 5], 1u << (pos & 31));
+      }
+      __syncwarp();
+      for (int j = lane; j + 1 < nf; j += 32) sorted &= (zs[j] <= zs[j + 1]);
+      sorted = __all_sync(kFull, sorted);
+      float* out = a.z_merged + rr * (int64_t)M;
+      if (sorted) {
+        int ones = 0;  // z_samples entries before this word
+        for (int k = 0; k < n_words; ++k) {
+          const unsigned word = bm[k];
+          const int p = (k << 5) + lane;
+          const int before = ones + __popc(word & ((1u << lane) - 1u));
+          if (p < M) out[p] = ((word >> lane) & 1u) ? zs[before] : zv[p - before];
+          ones += __popc(word);
+        }
+      } else {
+        // rare (rounding-induced inversions, random u, NaNs): all-pairs ranking, still exact
+        for (int e = lane; e < M; e += 32) {
+          float x = e < S1 ? zv[e] : zs[e - S1];
+          int rank = 0;
+          for (int k = 0; k < M; ++k) {
+            float y = k < S1 ? zv[k] : zs[k - S1];
+            rank += key_less(y, k, x, e) ? 1 : 0;
+          }
+          out[rank] = x;
+        }
+      }
+      __syncwarp();  // cdf / bins / zs / bitmap are reused by the next ray
     }
   }
 }
@@ -351,9 +416,9 @@ sample_pdf_kernel(const float* __restrict__ bins_g, const float* __restrict__ w_
 }
 
 template <typename K>
-static int32_t pick_warps(K kernel, size_t floats_per_warp, int* warps_out, size_t* smem_out) {
+static int32_t pick_warps(K kernel, size_t floats_per_warp, int max_warps, int* warps_out, size_t* smem_out) {
   size_t per_warp = floats_per_warp * sizeof(float);
-  int warps = 8;
+  int warps = max_warps;
   while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
   if (per_warp * warps > 200 * 1024) return NVSR_ERR_RESOURCE;
   size_t smem = per_warp * warps;
@@ -379,28 +444,22 @@ extern "C" int32_t nvsr_composite(const nvsr_composite_t* c, void* stream) {
   if (c->n_rays == 0) return NVSR_OK;
   NVSR_CHECK_ARG(c->row_order == NVSR_ROWS_RAY_MAJOR || c->row_order == NVSR_ROWS_BLOCKED);
   NVSR_CHECK_ARG(c->raw_stride >= rows_padded(c->n_rays, c->n_samples, c->row_order));
-  CompositeArgs a{c->n_rays, c->n_samples, c->raw, c->raw_stride, c->z, c->rd, c->noise, c->white_bkgd, c->mip,
+  CompositeArgs a{c->n_rays, c->n_samples, c->raw, c->raw_stride, c->z, c->rd, c->noise, c->white_bkgd, c->mip ? 1 : 0,
                   c->rgb, c->disp, c->acc, c->depth, c->weights, c->n_fine > 0 ? c->n_fine : 0, c->u, c->u_per_ray,
-                  c->inds, c->z_samples, c->z_merged, c->row_order};
-  int warps;
-  size_t smem;
-  if (a.row_order == NVSR_ROWS_BLOCKED) {
-    // one CTA = the 8 rays of a block, staged through shared memory
-    warps = kBlkRays;
-    smem = ((size_t)warps * composite_smem_floats(a.S, a.n_fine) + (size_t)4 * kBlkRays * stage_pitch(a.S)) * sizeof(float);
-    if (smem > 200 * 1024) return NVSR_ERR_RESOURCE;
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int32_t)e;
-    }
-  } else {
-    int32_t st = pick_warps(composite_kernel, composite_smem_floats(a.S, a.n_fine), &warps, &smem);
+                  c->inds, c->z_samples, c->z_merged};
+  const bool blocked = c->row_order == NVSR_ROWS_BLOCKED;
+  auto kernel = blocked ? composite_kernel<true> : composite_kernel<false>;
+  int warps = kCompWarps;
+  size_t smem = 0;
+  if (a.n_fine > 0) {
+    int32_t st = pick_warps(kernel, composite_warp_floats(a.S, a.S + a.mip, a.n_fine), kCompWarps, &warps, &smem);
     if (st != NVSR_OK) return st;
   }
-  int64_t blocks = ceil_div64(c->n_rays, warps);
-  int64_t max_blocks = (int64_t)kNumSMs * 16;
+  int64_t ray_blocks = ceil_div64(c->n_rays, kBlkRays);
+  int64_t blocks = ceil_div64(ray_blocks, warps);
+  int64_t max_blocks = (int64_t)kNumSMs * 32;
   if (blocks > max_blocks) blocks = max_blocks;
-  composite_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(a, warps);
+  kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(a, warps);
   NVSR_RETURN_LAST_ERROR();
 }
 
@@ -412,7 +471,7 @@ extern "C" int32_t nvsr_sample_pdf(const float* bins, const float* weights, cons
   if (n_rays == 0) return NVSR_OK;
   int warps;
   size_t smem;
-  int32_t st = pick_warps(sample_pdf_kernel, (size_t)3 * n_bins + 2, &warps, &smem);
+  int32_t st = pick_warps(sample_pdf_kernel, (size_t)3 * n_bins + 2, 8, &warps, &smem);
   if (st != NVSR_OK) return st;
   int64_t blocks = ceil_div64(n_rays, warps);
   int64_t max_blocks = (int64_t)kNumSMs * 16;

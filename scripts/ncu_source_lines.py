@@ -26,10 +26,16 @@ for row in csv.reader(io.StringIO(raw)):
     elif cur is not None and row[0] not in ("", "Line No") and "hdr" in cur:
         h = cur["hdr"]
         i_s, i_ex = h.index("Warp Stall Sampling (All Samples)"), h.index("Instructions Executed")
+        if not row[0].isdigit():
+            continue
         key = (cur["path"].split("/")[-1], int(row[0]))
+        try:
+            ex, st = int(row[i_ex] or 0), int(row[i_s] or 0)
+        except (ValueError, IndexError):
+            continue  # a source line whose quotes broke the CSV row
         e = cur["lines"].setdefault(key, [0, 0, row[1]])
-        e[0] += int(row[i_ex] or 0)
-        e[1] += int(row[i_s] or 0)
+        e[0] += ex
+        e[1] += st
 for b in blocks:
     if pat not in b["name"]:
         continue
