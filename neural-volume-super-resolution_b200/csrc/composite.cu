@@ -143,9 +143,17 @@ struct CompositeArgs {
 // largest power of two <= n) and no divergent branches.  NaN u -> n, as torch.
 __device__ __forceinline__ int upper_bound_fixed(const float* a, int n, int top, float u) {
   int pos = 0;
-  for (int step = top; step > 0; step >>= 1) {
-    int p = pos + step;
-    if (p <= n && !(a[p - 1] > u)) pos = p;
+  if (top == 32) {  // 32 <= n < 64: the reference's 64-sample coarse pass
+#pragma unroll
+    for (int step = 32; step > 0; step >>= 1) {
+      int p = pos + step;
+      if (p <= n && !(a[p - 1] > u)) pos = p;
+    }
+  } else {
+    for (int step = top; step > 0; step >>= 1) {
+      int p = pos + step;
+      if (p <= n && !(a[p - 1] > u)) pos = p;
+    }
   }
   return pos;
 }
@@ -166,9 +174,46 @@ __host__ __device__ inline int composite_warp_floats(int S, int S1, int n_fine) 
 }
 
 constexpr int kCompWarps = 4;  // warps per CTA at the usual sample counts (fewer when shared memory is short)
+// Resident CTAs per SM (measured, profiles/README.md): the resampling pass is latency-bound on shared memory
+// and short dependent chains and wants warps (7 CTAs, 72 registers; 8 CTAs spill); the compositing-only fine pass wants
+// the next tile's 21 loads per lane in registers without spills (4 CTAs, 128 registers).
+#ifndef NVSR_COMP_MINB_RESAMPLE
+#define NVSR_COMP_MINB_RESAMPLE 7
+#endif
+#ifndef NVSR_COMP_MINB_PLAIN
+#define NVSR_COMP_MINB_PLAIN 4
+#endif
+constexpr int kCompMinCtasResample = NVSR_COMP_MINB_RESAMPLE, kCompMinCtasPlain = NVSR_COMP_MINB_PLAIN;
+
+// One lane's share of a 16-sample tile: 4 consecutive samples x (r,g,b,sigma), and depths s0 .. s0+4.
+struct TileData {
+  float c[4][4];  // [sample][channel]
+  float zz[5];
+};
 
 template <bool BLOCKED>
-__global__ void __launch_bounds__(kCompWarps * 32)
+__device__ __forceinline__ void load_tile(const CompositeArgs& a, TileData& d, const float* raw_blk, const float* zrow,
+                                          int t, int q, int S, int S1, bool valid, bool vec_z) {
+  const int s0 = t * kBlkSamples + 4 * q;
+  if (vec_z && s0 + 4 <= S1) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(zrow + s0));
+    d.zz[0] = v.x, d.zz[1] = v.y, d.zz[2] = v.z, d.zz[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d.zz[j] = (s0 + j < S1) ? __ldg(zrow + s0 + j) : 0.f;
+  }
+  d.zz[4] = (s0 + 4 < S1) ? __ldg(zrow + s0 + 4) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool live = valid && s0 + j < S;  // padding rows are never read
+    const float* rp = BLOCKED ? raw_blk + t * kTileRows + (4 * q + j) * kBlkRays : raw_blk + s0 + j;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) d.c[j][ch] = live ? __ldg(rp + ch * a.raw_stride) : 0.f;
+  }
+}
+
+template <bool BLOCKED, bool RESAMPLE>
+__global__ void __launch_bounds__(kCompWarps * 32, RESAMPLE ? kCompMinCtasResample : kCompMinCtasPlain)
 composite_kernel(CompositeArgs a, int warps_per_cta) {
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31;
@@ -176,7 +221,7 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
   const int rl = lane & 7, q = lane >> 3;
   const int S = a.S;
   const int S1 = S + (a.mip ? 1 : 0);  // depth entries per ray
-  const int nf = a.n_fine;
+  const int nf = RESAMPLE ? a.n_fine : 0;
   const int P = pitch4(S), P1 = pitch4(S1);
   float* zsm = sm + (size_t)wid * composite_warp_floats(S, S1, nf);
   float* wsm = zsm + 8 * P1;
@@ -188,36 +233,50 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
   const int64_t n_blocks = ceil_div64(a.n_rays, kBlkRays);
   const bool vec_z = (S1 & 3) == 0 && (reinterpret_cast<uintptr_t>(a.z) & 15u) == 0;
   const bool vec_w = (S & 3) == 0 && (reinterpret_cast<uintptr_t>(a.weights) & 15u) == 0;
+  // resampling constants
+  const int B = S - 1;  // bins (z_mid; mip: mids of mids)
+  int top = 1;
+  while (top * 2 <= B) top *= 2;
+  const int M = S1 + nf;
+  const int n_words = (M + 31) >> 5;
+  // shared deterministic u (perturb == 0): the same for every ray, kept in registers
+  const bool u_regs = RESAMPLE && nf <= 128 && !a.u_per_ray;
+  float ureg[4] = {0.f, 0.f, 0.f, 0.f};
+  if (u_regs) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < nf) ureg[k] = __ldg(a.u + lane + 32 * k);
+  }
 
   for (int64_t blk = (int64_t)blockIdx.x * warps_per_cta + wid; blk < n_blocks;
        blk += (int64_t)gridDim.x * warps_per_cta) {
     const int64_t ray = blk * kBlkRays + rl;
     const bool valid = ray < a.n_rays;
     const int64_t rayc = valid ? ray : a.n_rays - 1;  // clamped: loads stay in bounds, results are dropped
-    const float dx = __ldg(a.rd + rayc * 3), dy = __ldg(a.rd + rayc * 3 + 1), dz = __ldg(a.rd + rayc * 3 + 2);
-    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     const float* zrow = a.z + rayc * S1;
     const float* raw_blk = BLOCKED ? a.raw + blk * TS * (int64_t)kTileRows + rl : a.raw + rayc * S;
+    TileData cur;
+    load_tile<BLOCKED>(a, cur, raw_blk, zrow, 0, q, S, S1, valid, vec_z);
+    const float dx = __ldg(a.rd + rayc * 3), dy = __ldg(a.rd + rayc * 3 + 1), dz = __ldg(a.rd + rayc * 3 + 2);
+    const float dnorm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 
     double carry = 1.0;  // product of (1-alpha+1e-10) over the previous tiles
     double sr = 0.0, sg = 0.0, sb = 0.0, sd = 0.0, sa = 0.0;
-    if (nf > 0) __syncwarp();  // the previous block's resampling is done with zsm / wsm
+    bool z_sorted = true;  // this lane's depths are non-decreasing (NaN -> false)
     for (int t = 0; t < TS; ++t) {
+      // fine pass: the next tile's loads are in flight while this one is composited (the resampling
+      // variant runs at 64 registers for occupancy and has no room for a second tile)
+      TileData nxt;
+      if (!RESAMPLE && t + 1 < TS) load_tile<BLOCKED>(a, nxt, raw_blk, zrow, t + 1, q, S, S1, valid, vec_z);
       const int s0 = t * kBlkSamples + 4 * q;
-      // ---- depths s0 .. s0+4 ----
-      float zz[5];
-      if (vec_z && s0 + 4 <= S1) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(zrow + s0));
-        zz[0] = v.x, zz[1] = v.y, zz[2] = v.z, zz[3] = v.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) zz[j] = (s0 + j < S1) ? __ldg(zrow + s0 + j) : 0.f;
-      }
-      zz[4] = (s0 + 4 < S1) ? __ldg(zrow + s0 + 4) : 0.f;
-      if (nf > 0) {  // keep the depths for the resampling pass (entries beyond S1 are zeros, never used)
+      const float(&zz)[5] = cur.zz;
+      if (RESAMPLE) {  // keep the depths for the resampling pass (entries beyond S1 are zeros, never used)
         float* zd = zsm + rl * P1 + s0;
         if (s0 + 4 <= P1) *reinterpret_cast<float4*>(zd) = make_float4(zz[0], zz[1], zz[2], zz[3]);
         if (q == 3 && s0 + 4 < S1) zd[4] = zz[4];  // mip: the last edge when S is a multiple of 16
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (s0 + j + 1 < S1) z_sorted &= (zz[j] <= zz[j + 1]);
       }
       // ---- radiance samples ----
       float alpha[4], cr[4], cg[4], cb[4], zc[4];
@@ -228,9 +287,7 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
         const bool live = valid && s < S;
         alpha[j] = 0.f, cr[j] = 0.f, cg[j] = 0.f, cb[j] = 0.f, zc[j] = 0.f, tt[j] = 1.0;
         if (live) {
-          const float* rp = BLOCKED ? raw_blk + t * kTileRows + (4 * q + j) * kBlkRays : raw_blk + s;
-          const float r0 = __ldg(rp), r1 = __ldg(rp + a.raw_stride), r2 = __ldg(rp + 2 * a.raw_stride);
-          float sig = __ldg(rp + 3 * a.raw_stride);
+          float sig = cur.c[j][3];
           float dist;
           if (a.mip) {
             dist = __fsub_rn(zz[j + 1], zz[j]);
@@ -240,7 +297,7 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
             zc[j] = zz[j];
           }
           dist = __fmul_rn(dist, dnorm);
-          cr[j] = sigmoid_fast(r0), cg[j] = sigmoid_fast(r1), cb[j] = sigmoid_fast(r2);
+          cr[j] = sigmoid_fast(cur.c[j][0]), cg[j] = sigmoid_fast(cur.c[j][1]), cb[j] = sigmoid_fast(cur.c[j][2]);
           if (a.noise) sig = __fadd_rn(sig, __ldg(a.noise + ray * S + s));
           sig = fmaxf(sig, 0.f);
           alpha[j] = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
@@ -277,7 +334,11 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
             if (s0 + j < S) wd[j] = w[j];
         }
       }
-      if (nf > 0 && s0 + 4 <= P) *reinterpret_cast<float4*>(wsm + rl * P + s0) = make_float4(w[0], w[1], w[2], w[3]);
+      if (RESAMPLE && s0 + 4 <= P) *reinterpret_cast<float4*>(wsm + rl * P + s0) = make_float4(w[0], w[1], w[2], w[3]);
+      if (t + 1 < TS) {
+        if (RESAMPLE) load_tile<BLOCKED>(a, cur, raw_blk, zrow, t + 1, q, S, S1, valid, vec_z);
+        else cur = nxt;
+      }
     }
     // ---- per-ray maps: reduce the 4 quarters, quarter 0 writes ----
 #pragma unroll
@@ -299,16 +360,12 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
       a.rgb[ray * 3] = vr, a.rgb[ray * 3 + 1] = vg, a.rgb[ray * 3 + 2] = vb;
       a.disp[ray] = dispv, a.acc[ray] = accv, a.depth[ray] = depthv;
     }
-    if (nf <= 0) continue;
+    if (!RESAMPLE) continue;
 
     // ---- hierarchical resampling, one ray at a time on all 32 lanes:
     //      train_utils.py:144-156 + nerf_helpers.py:668-702 ----
+    const unsigned zs_ballot = __ballot_sync(kFull, z_sorted);  // ray r: bits r, r+8, r+16, r+24
     __syncwarp();
-    const int B = S - 1;  // bins (z_mid; mip: mids of mids)
-    int top = 1;
-    while (top * 2 <= B) top *= 2;
-    const int M = S1 + nf;
-    const int n_words = (M + 31) >> 5;
     for (int r = 0; r < kBlkRays; ++r) {
       const int64_t rr = blk * kBlkRays + r;
       if (rr >= a.n_rays) break;
@@ -325,33 +382,43 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
       for (int k = lane; k < n_words; k += 32) bm[k] = 0u;
       build_cdf(wv + 1, S - 2, cdf, lane);  // weights[...,1:-1]
       __syncwarp();
-      bool sorted = true;
-      for (int i = lane; i + 1 < S1; i += 32) sorted &= (zv[i] <= zv[i + 1]);
-      for (int j = lane; j < nf; j += 32) {
-        const float u = a.u_per_ray ? __ldg(a.u + rr * nf + j) : __ldg(a.u + j);
-        const int ind = upper_bound_fixed(cdf, B, top, u);
-        const int below = max(0, ind - 1), above = min(B - 1, ind);
-        const float cb_ = cdf[below], ca_ = cdf[above];
-        float denom = __fsub_rn(ca_, cb_);
-        if (denom < 1e-5f) denom = 1.f;
-        const float tq = __fdiv_rn(__fsub_rn(u, cb_), denom);
-        const float bb = bins[below], ba = bins[above];
-        const float x = __fadd_rn(bb, __fmul_rn(tq, __fsub_rn(ba, bb)));
-        zs[j] = x;
-        if (a.inds) a.inds[rr * nf + j] = ind;
-        if (a.z_samples) a.z_samples[rr * nf + j] = x;
-        // rank of z_samples[j] in the merge = j + #(z_vals <= z_samples[j]).  The sample lies between the
-        // bin centres around the bin it was drawn from, so the count starts at that bin index and is
-        // corrected by a couple of probes (exact whenever z_vals is sorted; the guess only sets the probe
-        // count).  The position goes into the bitmap; it is used only if both inputs turn out sorted.
-        int c = min(max(ind + a.mip, 1), S1);
-        while (c < S1 && zv[c] <= x) ++c;
-        while (c > 0 && zv[c - 1] > x) --c;
-        const int pos = j + c;
-        atomicOr(&bm[pos >> 5], 1u << (pos & 31));
+      bool sorted = ((zs_ballot >> r) & 0x01010101u) == 0x01010101u;  // z_vals non-decreasing
+      float prev_last = 0.f;
+      for (int j0 = 0; j0 < nf; j0 += 32) {
+        const int j = j0 + lane;
+        const bool act = j < nf;
+        float x = 0.f;
+        if (act) {
+          const float u = u_regs ? ureg[j0 >> 5] : (a.u_per_ray ? __ldg(a.u + rr * nf + j) : __ldg(a.u + j));
+          const int ind = upper_bound_fixed(cdf, B, top, u);
+          const int below = max(0, ind - 1), above = min(B - 1, ind);
+          const float cb_ = cdf[below], ca_ = cdf[above];
+          float denom = __fsub_rn(ca_, cb_);
+          if (denom < 1e-5f) denom = 1.f;
+          const float tq = __fdiv_rn(__fsub_rn(u, cb_), denom);
+          const float bb = bins[below], ba = bins[above];
+          x = __fadd_rn(bb, __fmul_rn(tq, __fsub_rn(ba, bb)));
+          zs[j] = x;
+          if (a.inds) a.inds[rr * nf + j] = ind;
+          if (a.z_samples) a.z_samples[rr * nf + j] = x;
+          // rank of z_samples[j] in the merge = j + #(z_vals <= z_samples[j]).  The sample lies between the
+          // bin centres around the bin it was drawn from, so the count starts at that bin index and is
+          // corrected by a couple of probes (exact whenever z_vals is sorted; the guess only sets the probe
+          // count).  The position goes into the bitmap; it is used only if both inputs turn out sorted.
+          int c = min(max(ind + a.mip, 1), S1);
+          while (c < S1 && zv[c] <= x) ++c;
+          while (c > 0 && zv[c - 1] > x) --c;
+          const int pos = j + c;
+          atomicOr(&bm[pos >> 5], 1u << (pos & 31));
+        }
+        // z_samples non-decreasing?  neighbours live in the next lane / the next round's lane 0
+        const float up = __shfl_down_sync(kFull, x, 1);
+        if (lane < 31 && j + 1 < nf) sorted &= (x <= up);
+        const float first = __shfl_sync(kFull, x, 0);
+        if (j0 > 0 && lane == 0) sorted &= (prev_last <= first);
+        prev_last = __shfl_sync(kFull, x, 31);
       }
       __syncwarp();
-      for (int j = lane; j + 1 < nf; j += 32) sorted &= (zs[j] <= zs[j + 1]);
       sorted = __all_sync(kFull, sorted);
       float* out = a.z_merged + rr * (int64_t)M;
       if (sorted) {
@@ -448,7 +515,8 @@ extern "C" int32_t nvsr_composite(const nvsr_composite_t* c, void* stream) {
                   c->rgb, c->disp, c->acc, c->depth, c->weights, c->n_fine > 0 ? c->n_fine : 0, c->u, c->u_per_ray,
                   c->inds, c->z_samples, c->z_merged};
   const bool blocked = c->row_order == NVSR_ROWS_BLOCKED;
-  auto kernel = blocked ? composite_kernel<true> : composite_kernel<false>;
+  auto kernel = a.n_fine > 0 ? (blocked ? composite_kernel<true, true> : composite_kernel<false, true>)
+                             : (blocked ? composite_kernel<true, false> : composite_kernel<false, false>);
   int warps = kCompWarps;
   size_t smem = 0;
   if (a.n_fine > 0) {
