@@ -29,6 +29,8 @@
 // 8x16-byte core matrices, stored [K/8][rows][8 x 16 bit]: LBO (K-chunk stride) = rows*16 B,
 // SBO (8-row group stride) = 128 B.  The feature tile image written by the gather kernel and the
 // weight image written by nvsr_pack_weight16 are exactly this, so both arrive with plain bulk copies.
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace nvsr {
@@ -168,7 +170,7 @@ __device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
 }
 
 // barrier block layout (uint64_t each, [2] = one per slot)
-enum { BAR_W = 0, BAR_IN_FULL = 1, BAR_RB_FULL = 3, BAR_ACC_FULL = 5, BAR_COUNT = 7 };
+enum { BAR_W = 0, BAR_IN_FULL = 1, BAR_RB_FULL = 3, BAR_ACC_FULL = 5, BAR_DONE = 7, BAR_COUNT = 9 };
 
 __device__ __forceinline__ void load_bias32(const float* src, uint32_t (&v)[32]) {
 #pragma unroll
@@ -240,6 +242,84 @@ __device__ __forceinline__ void epi_pass(uint32_t d_addr, uint32_t a_addr, bool 
   }
 }
 
+// packed fp32x2 helpers for the head dot products (FFMA2: two MACs per instruction)
+__device__ __forceinline__ unsigned long long tc_pack2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ unsigned long long tc_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float tc_sum2(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+
+// HN fp32 head dot products over 32 ReLU'd accumulator columns of one row
+template <int HN>
+__device__ __forceinline__ void head_dot32(const uint32_t (&v)[32], const float* hw, float (&hacc)[4]) {
+  unsigned long long x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    x[j] = tc_pack2(fmaxf(__uint_as_float(v[2 * j]), 0.f), fmaxf(__uint_as_float(v[2 * j + 1]), 0.f));
+#pragma unroll
+  for (int h = 0; h < HN; ++h) {
+    const float4* hw4 = reinterpret_cast<const float4*>(hw + h * 128);
+    unsigned long long acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w4 = hw4[j];
+      acc0 = tc_fma2(x[2 * j], tc_pack2(w4.x, w4.y), acc0);
+      acc1 = tc_fma2(x[2 * j + 1], tc_pack2(w4.z, w4.w), acc1);
+    }
+    hacc[h] += tc_sum2(acc0) + tc_sum2(acc1);
+  }
+}
+
+// Epilogue of one layer of a FIXED chain for one thread (= one row, this warp's 64 columns): both
+// 32-column accumulator loads are issued back to back and waited for once, so the second load's latency
+// hides behind the first group's pack/store.  ReLU always; HN > 0: last layer (heads, no A operand).
+template <bool F16, int HN>
+__device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, const float* hw, float (&hacc)[4],
+                                          bool bias, const float* bsrc) {
+  if constexpr (HN == 0) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(d_addr, v0);
+    tmem_ld32(d_addr + 32u, v1);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+    tmem_st16(a_addr, pk);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+    tmem_st16(a_addr + 16u, pk);
+    if (bias) {
+      load_bias32(bsrc, v0);
+      tmem_st32(d_addr, v0);
+      load_bias32(bsrc + 32, v1);
+      tmem_st32(d_addr + 32u, v1);
+    }
+  } else {
+    // head layer: one 32-column group at a time keeps the register peak at one group + the packed pairs
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(d_addr + (uint32_t)c, v);
+      tmem_ld_wait();
+      head_dot32<HN>(v, hw + c, hacc);
+      if (bias) {
+        load_bias32(bsrc + c, v);
+        tmem_st32(d_addr + (uint32_t)c, v);
+      }
+    }
+  }
+}
+
 // LC > 0: "uniform" chain known at compile time — LC layers, all 128 wide with ReLU, one head of HN
 // rows on the last layer, per-ray bias on layer 0 iff RB0 (staged rows, BLOCKED order).  Both decoders
 // of the tri-plane model are of this shape (LC = 4).  LC == 0: generic chain described at run time.
@@ -267,6 +347,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       mbar_init(&bars[BAR_IN_FULL + s], 1);
       mbar_init(&bars[BAR_RB_FULL + s], 1);
       mbar_init(&bars[BAR_ACC_FULL + s], 1);
+      mbar_init(&bars[BAR_DONE + s], kTcEpiWarpsPerSlot);
     }
     tmem_slot[1] = tmem_slot[2] = 0;  // per-slot arrival counters
     mbar_fence_init();
@@ -328,6 +409,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     uint64_t* bar_acc_full = &bars[BAR_ACC_FULL + s];
     uint64_t* bar_rb_full = &bars[BAR_RB_FULL + s];
     uint32_t* done_cnt = tmem_slot + 1 + s;  // arrivals of the slot's 8 warps (monotonic; every 8th issues)
+    uint64_t* bar_done = &bars[BAR_DONE + s];
+    (void)done_cnt, (void)bar_done;
     const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
     uint32_t ph_acc = 0, ph_rb = 0;
 
@@ -365,17 +448,47 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     };
     // This warp's TMEM writes for the next accumulation are done: count it; the slot's 8th arrival
     // issues the MMAs of (layer nl, tile number nuse) — no issuer warp, no wake-up hop.
+#ifdef NVSR_TC_TRACE
+    long long tr[4][7];
+    long long tr_t4 = 0, tr_t5 = 0;
+#define TC_TRACE(slot_, expr_) do { slot_ = (expr_); } while (0)
+#else
+#define TC_TRACE(slot_, expr_) do { } while (0)
+#endif
     auto arrive_then_issue = [&](bool issue_next, int nl, uint32_t nuse) {
       tmem_st_wait();
+#ifdef NVSR_TC_TRACE
+      tr_t4 = clock64();
+#endif
       tc_fence_before();
       __syncwarp();
       uint32_t last_in = 0;
       if (lane == 0) {
+#ifndef NVSR_TC_ATOMIC_ARRIVE
+        // count the arrival on an mbarrier (release, no MEMBAR): the state it returns holds the pending count
+        // before this arrival, 1 = this warp completes the phase and is the issuer; the test_wait on that
+        // (now complete) phase is the acquire side towards the other seven warps' arrivals
+        uint64_t state;
+        uint32_t pending;
+        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_u32(bar_done)) : "memory");
+        asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+        last_in = pending == 1;
+        if (last_in) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(smem_u32(bar_done)), "l"(state) : "memory");
+          (void)ok;
+        }
+#else
         uint32_t old;
         asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(done_cnt)) : "memory");
         last_in = (old & (kTcEpiWarpsPerSlot - 1)) == kTcEpiWarpsPerSlot - 1;
+#endif
       }
       last_in = __shfl_sync(0xffffffffu, last_in, 0);
+#ifdef NVSR_TC_TRACE
+      tr_t5 = clock64();
+#endif
       if (last_in && issue_next) issue_layer(nl, nuse);
     };
 
@@ -426,7 +539,14 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       if (tile >= a.n_tiles) break;
       const int64_t next_tile = tile + 2 * G;
       const bool next_valid = next_tile < a.n_tiles;
+      // fixed chains: the layer loop is fully unrolled, so `last`, the bias source and the next layer are
+      // compile-time per copy (~100 instructions per layer and warp instead of ~350: the kernel is largely
+      // issue-bound, measured -18% / -8% on the density / rgb chains); the generic chain stays rolled
+#ifdef NVSR_TC_ROLLED
 #pragma unroll 1
+#else
+#pragma unroll(kFixed ? 4 : 1)
+#endif
       for (int l = 0; l < L; ++l) {
         // ---- everything that does not depend on the accumulator: done before the wait ----
         const TcLayer& ly = a.layer[l];
@@ -446,21 +566,42 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           mbar_wait(bar_rb_full, ph_rb);
           ph_rb ^= 1;
         }
+#ifdef NVSR_TC_TRACE
+        if (kFixed) tr[l][0] = clock64();
+#endif
         mbar_wait(bar_acc_full, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
+#ifdef NVSR_TC_TRACE
+        if (kFixed) tr[l][1] = clock64();
+#endif
         // layer 0's MMAs have completed: the slot's ring buffer (and, since all 8 warps finished reading
         // them before those MMAs were issued, its staged bias rows) may take the slot's next tile
         if (l == 0 && loader && next_valid) issue_tile_loads(s, next_tile);
+#ifndef NVSR_TC_OLD_EPI
+        if constexpr (kFixed) {
+          // fixed chains: bias rows always come from shared memory (mode 1)
+          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, n_next > 0, bsrc);
+          else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, true, bsrc);
+        } else
+#endif
+        {
 #pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          const bool read = col0 + c < n_cur;
-          const bool bias = col0 + c < n_next;
-          if (read || bias)
-            epi_pass<F16>(d_tmem + (uint32_t)c, a_tmem + (uint32_t)(c >> 1), read, !last, relu, head_n, hw + c, hacc,
-                          bias ? mode : 0, bsrc + c);
+          for (int c = 0; c < 64; c += 32) {
+            const bool read = col0 + c < n_cur;
+            const bool bias = col0 + c < n_next;
+            if (read || bias)
+              epi_pass<F16>(d_tmem + (uint32_t)c, a_tmem + (uint32_t)(c >> 1), read, !last, relu, head_n, hw + c, hacc,
+                            bias ? mode : 0, bsrc + c);
+          }
         }
+#ifdef NVSR_TC_TRACE
+        if (kFixed) tr[l][2] = clock64();
+#endif
         arrive_then_issue(n_next > 0, nl, last ? use + 1 : use);
+#ifdef NVSR_TC_TRACE
+        if (kFixed) tr[l][3] = tr_t4, tr[l][4] = tr_t5, tr[l][5] = clock64();
+#endif
 
         if (head_n > 0) {
           // combine the two column halves of a row: half 1 -> smem -> half 0
@@ -475,7 +616,18 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
               if (h < head_n) a.raw[(int64_t)(ly.head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(ly.head_b + h);
           }
         }
+#ifdef NVSR_TC_TRACE
+        if (kFixed) tr[l][6] = clock64();
+#endif
       }
+#ifdef NVSR_TC_TRACE
+      if (kFixed && blockIdx.x == 3 && use == 5 && lane == 0) {
+        for (int l = 0; l < L; ++l)
+          printf("w%02d s%d l%d  wait@%lld  acc+%lld  epi+%lld  stwait+%lld  atom+%lld  issued+%lld  head+%lld\n", warp, s, l,
+                 tr[l][0] - tr[0][0], tr[l][1] - tr[l][0], tr[l][2] - tr[l][1], tr[l][3] - tr[l][2], tr[l][4] - tr[l][3],
+                 tr[l][5] - tr[l][4], tr[l][6] - tr[l][5]);
+      }
+#endif
     }
   }
 
