@@ -29,8 +29,6 @@
 // 8x16-byte core matrices, stored [K/8][rows][8 x 16 bit]: LBO (K-chunk stride) = rows*16 B,
 // SBO (8-row group stride) = 128 B.  The feature tile image written by the gather kernel and the
 // weight image written by nvsr_pack_weight16 are exactly this, so both arrive with plain bulk copies.
-#include <cstdio>
-
 #include "common.cuh"
 
 namespace nvsr {
@@ -259,13 +257,12 @@ __device__ __forceinline__ float tc_sum2(unsigned long long v) {
   return lo + hi;
 }
 
-// HN fp32 head dot products over 32 ReLU'd accumulator columns of one row
+// HN fp32 head dot products over 32 accumulator columns of one row; the ReLU is applied in place
+// (v is dead afterwards), column pairs are the FFMA2 operands as they sit in the registers
 template <int HN>
-__device__ __forceinline__ void head_dot32(const uint32_t (&v)[32], const float* hw, float (&hacc)[4]) {
-  unsigned long long x[16];
+__device__ __forceinline__ void head_dot32(uint32_t (&v)[32], const float* hw, float (&hacc)[4]) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    x[j] = tc_pack2(fmaxf(__uint_as_float(v[2 * j]), 0.f), fmaxf(__uint_as_float(v[2 * j + 1]), 0.f));
+  for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
 #pragma unroll
   for (int h = 0; h < HN; ++h) {
     const float4* hw4 = reinterpret_cast<const float4*>(hw + h * 128);
@@ -273,8 +270,8 @@ __device__ __forceinline__ void head_dot32(const uint32_t (&v)[32], const float*
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 w4 = hw4[j];
-      acc0 = tc_fma2(x[2 * j], tc_pack2(w4.x, w4.y), acc0);
-      acc1 = tc_fma2(x[2 * j + 1], tc_pack2(w4.z, w4.w), acc1);
+      acc0 = tc_fma2(tc_pack2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), tc_pack2(w4.x, w4.y), acc0);
+      acc1 = tc_fma2(tc_pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), tc_pack2(w4.z, w4.w), acc1);
     }
     hacc[h] += tc_sum2(acc0) + tc_sum2(acc1);
   }
@@ -305,17 +302,21 @@ __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, cons
       tmem_st32(d_addr + 32u, v1);
     }
   } else {
-    // head layer: one 32-column group at a time keeps the register peak at one group + the packed pairs
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(d_addr + (uint32_t)c, v);
-      tmem_ld_wait();
-      head_dot32<HN>(v, hw + c, hacc);
-      if (bias) {
-        load_bias32(bsrc + c, v);
-        tmem_st32(d_addr + (uint32_t)c, v);
-      }
+    // head layer: both groups are loaded up front as well (a TMEM load costs a few hundred cycles while the
+    // other slot's MMAs run); each group's registers are reused for its bias once its dot products are done
+    uint32_t v0[32], v1[32];
+    tmem_ld32(d_addr, v0);
+    tmem_ld32(d_addr + 32u, v1);
+    tmem_ld_wait();
+    head_dot32<HN>(v0, hw, hacc);
+    if (bias) {
+      load_bias32(bsrc, v0);
+      tmem_st32(d_addr, v0);
+    }
+    head_dot32<HN>(v1, hw + 32, hacc);
+    if (bias) {
+      load_bias32(bsrc + 32, v1);
+      tmem_st32(d_addr + 32u, v1);
     }
   }
 }
@@ -344,8 +345,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   if (threadIdx.x == 0) {
     mbar_init(&bars[BAR_W], 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[BAR_IN_FULL + s], 1);
-      mbar_init(&bars[BAR_RB_FULL + s], 1);
+      mbar_init(&bars[BAR_IN_FULL + s], kTcEpiWarpsPerSlot);
+      mbar_init(&bars[BAR_RB_FULL + s], kTcEpiWarpsPerSlot);
       mbar_init(&bars[BAR_ACC_FULL + s], 1);
       mbar_init(&bars[BAR_DONE + s], kTcEpiWarpsPerSlot);
     }
@@ -376,19 +377,23 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   // Loads of one tile into slot s: the feature tile image and, when staged, the bias rows of its 8 rays
-  // (consecutive rows of row_bias in the BLOCKED order).  Issued by ONE thread.
-  auto issue_tile_loads = [&](int s, int64_t tile) {
-    mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], a.in_bytes);
-    bulk_g2s(smem + a.in_off[s], a.in + tile * (int64_t)a.in_bytes, a.in_bytes, &bars[BAR_IN_FULL + s]);
+  // (consecutive rows of row_bias in the BLOCKED order).  Issuing a bulk copy costs its thread well over a
+  // hundred cycles, so the work is spread: lane 0 of EACH of the slot's 8 warps copies one eighth of the
+  // image and one bias row (wi = warp index within the slot); both barriers count 8 arrivals.
+  auto issue_tile_loads = [&](int s, int64_t tile, int wi) {
+    const uint32_t piece = a.in_bytes / kTcEpiWarpsPerSlot;  // K * 32 bytes: a multiple of 16
+    mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], piece);
+    bulk_g2s(smem + a.in_off[s] + wi * piece, a.in + tile * (int64_t)a.in_bytes + wi * piece, piece, &bars[BAR_IN_FULL + s]);
     if (rb_staged) {
       const TcLayer& rl = a.layer[rb_layer];
       int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays;
-      int64_t left = a.n_rays - ray0;
-      int cnt = left >= kRbRowsMax ? kRbRowsMax : (int)left;
-      mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], (uint32_t)(cnt * rl.n * 4));
-      float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
-      for (int j = 0; j < cnt; ++j)
-        bulk_g2s(dst + j * kRbPitch, rl.row_bias + (ray0 + j) * rl.n, (uint32_t)(rl.n * 4), &bars[BAR_RB_FULL + s]);
+      if (ray0 + wi < a.n_rays) {
+        mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], (uint32_t)(rl.n * 4));
+        float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
+        bulk_g2s(dst + wi * kRbPitch, rl.row_bias + (ray0 + wi) * rl.n, (uint32_t)(rl.n * 4), &bars[BAR_RB_FULL + s]);
+      } else {
+        mbar_arrive(&bars[BAR_RB_FULL + s]);
+      }
     }
   };
 
@@ -400,7 +405,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     const int half = (ew & 7) >> 2;       // column ownership: half h owns columns [64h, 64h+64) of every layer
     const int r = quad * 32 + lane;       // row within the tile == TMEM lane
     const int col0 = half * 64;
-    const bool loader = (ew & 7) == 0 && lane == 0;  // this thread also feeds the slot's ring buffer
+    const int wi = ew & 7;                // warp index within the slot (also its share of the tile loads)
     const uint32_t d_base = tmem_base + (uint32_t)s * kSlotCols;  // lane 0: the MMA's D / A operands
     const uint32_t d_tmem = d_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
     const uint32_t a_tmem = d_base + ((uint32_t)(quad * 32) << 16) + kSlotAOff + (uint32_t)(col0 >> 1);
@@ -448,18 +453,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     };
     // This warp's TMEM writes for the next accumulation are done: count it; the slot's 8th arrival
     // issues the MMAs of (layer nl, tile number nuse) — no issuer warp, no wake-up hop.
-#ifdef NVSR_TC_TRACE
-    long long tr[4][7];
-    long long tr_t4 = 0, tr_t5 = 0;
-#define TC_TRACE(slot_, expr_) do { slot_ = (expr_); } while (0)
-#else
-#define TC_TRACE(slot_, expr_) do { } while (0)
-#endif
     auto arrive_then_issue = [&](bool issue_next, int nl, uint32_t nuse) {
       tmem_st_wait();
-#ifdef NVSR_TC_TRACE
-      tr_t4 = clock64();
-#endif
       tc_fence_before();
       __syncwarp();
       uint32_t last_in = 0;
@@ -486,9 +481,6 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #endif
       }
       last_in = __shfl_sync(0xffffffffu, last_in, 0);
-#ifdef NVSR_TC_TRACE
-      tr_t5 = clock64();
-#endif
       if (last_in && issue_next) issue_layer(nl, nuse);
     };
 
@@ -520,7 +512,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       }
     }
     if (first < a.n_tiles) {
-      if (loader) issue_tile_loads(s, first);
+      if (lane == 0) issue_tile_loads(s, first, wi);
       if (rb_layer == 0 && rb_staged) {
         mbar_wait(bar_rb_full, ph_rb);
         ph_rb ^= 1;
@@ -566,18 +558,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           mbar_wait(bar_rb_full, ph_rb);
           ph_rb ^= 1;
         }
-#ifdef NVSR_TC_TRACE
-        if (kFixed) tr[l][0] = clock64();
-#endif
         mbar_wait(bar_acc_full, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
-#ifdef NVSR_TC_TRACE
-        if (kFixed) tr[l][1] = clock64();
-#endif
-        // layer 0's MMAs have completed: the slot's ring buffer (and, since all 8 warps finished reading
-        // them before those MMAs were issued, its staged bias rows) may take the slot's next tile
-        if (l == 0 && loader && next_valid) issue_tile_loads(s, next_tile);
 #ifndef NVSR_TC_OLD_EPI
         if constexpr (kFixed) {
           // fixed chains: bias rows always come from shared memory (mode 1)
@@ -595,13 +578,11 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
                             bias ? mode : 0, bsrc + c);
           }
         }
-#ifdef NVSR_TC_TRACE
-        if (kFixed) tr[l][2] = clock64();
-#endif
         arrive_then_issue(n_next > 0, nl, last ? use + 1 : use);
-#ifdef NVSR_TC_TRACE
-        if (kFixed) tr[l][3] = tr_t4, tr[l][4] = tr_t5, tr[l][5] = clock64();
-#endif
+        // layer 0's MMAs have completed: the slot's ring buffer (and, since all 8 warps finished reading
+        // them before those MMAs were issued, its staged bias rows) may take the slot's next tile.  Issued
+        // after the arrival: the warp would only be waiting for layer 1's accumulator now.
+        if (l == 0 && next_valid && lane == 0) issue_tile_loads(s, next_tile, wi);
 
         if (head_n > 0) {
           // combine the two column halves of a row: half 1 -> smem -> half 0
@@ -616,18 +597,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
               if (h < head_n) a.raw[(int64_t)(ly.head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(ly.head_b + h);
           }
         }
-#ifdef NVSR_TC_TRACE
-        if (kFixed) tr[l][6] = clock64();
-#endif
       }
-#ifdef NVSR_TC_TRACE
-      if (kFixed && blockIdx.x == 3 && use == 5 && lane == 0) {
-        for (int l = 0; l < L; ++l)
-          printf("w%02d s%d l%d  wait@%lld  acc+%lld  epi+%lld  stwait+%lld  atom+%lld  issued+%lld  head+%lld\n", warp, s, l,
-                 tr[l][0] - tr[0][0], tr[l][1] - tr[l][0], tr[l][2] - tr[l][1], tr[l][3] - tr[l][2], tr[l][4] - tr[l][3],
-                 tr[l][5] - tr[l][4], tr[l][6] - tr[l][5]);
-      }
-#endif
     }
   }
 

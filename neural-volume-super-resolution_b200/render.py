@@ -25,7 +25,12 @@ from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32
 _PRECISION = {"bf16": NVSR_BF16, "fp16": NVSR_F16, "fp32": NVSR_F32}
 _state = {
     "precision": _PRECISION[os.environ.get("NVSR_PRECISION", "fp16")],
-    "ray_chunk": int(os.environ.get("NVSR_RAY_CHUNK", "32768")),
+    # rays per chunk of the frame loop.  The reference chunks for memory (131 072 points per network call,
+    # train_utils.py:228-234); here a chunk only bounds the temporaries (384 B of features per sample row),
+    # and 180 GB of HBM take half a frame at once: fewer, longer launches (measured -2.8 % per frame against
+    # 32 768-ray chunks).  NVSR_MAX_CHUNK_ROWS caps rays x samples of one chunk (64 Mi rows ~ 25 GB).
+    "ray_chunk": int(os.environ.get("NVSR_RAY_CHUNK", "327680")),
+    "max_chunk_rows": int(os.environ.get("NVSR_MAX_CHUNK_ROWS", str(64 << 20))),
 }
 
 
@@ -262,7 +267,10 @@ def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, opti
         runner = lambda a, b, c, rnd, tr: _render_mip_chunk(mc, mf, a, b, c, near, far, cfg, radius, n_freqs, n_dir,
                                                             rnd, tr)
 
-    chunk = _state["ray_chunk"]
+    # equal-sized chunks (multiples of the 8-ray block), bounded in rays and in rays x samples
+    chunk = max(8, min(_state["ray_chunk"], _state["max_chunk_rows"] // max(1, cfg.num_coarse + cfg.num_fine)))
+    n_chunks = max(1, -(-n_total // chunk))
+    chunk = max(8, -(-(-(-n_total // n_chunks)) // 8) * 8)
     outs_c, outs_f, traces = [], [], []
     for i0 in range(0, n_total, chunk):
         i1 = min(n_total, i0 + chunk)
