@@ -37,11 +37,13 @@ EVALS_PER_RAY = NC + (NC + NF)          # decoder evaluations per ray (coarse ne
 FLOP_PER_EVAL = 259072                  # true MACs x 2, planes decoder
 
 
-def ncu_traffic(kernel):
-    """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/)"""
+def ncu_traffic(kernel, evals_per_launch):
+    """dram read+write bytes per launch of `kernel`: the committed `ncu --set full` capture (profiles/) gives
+    bytes per decoder evaluation (launch sizes follow the ray chunk), scaled to this run's launches"""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            per_eval = json.load(f).get(kernel + "_bytes_per_eval")
+        return None if per_eval is None else per_eval * evals_per_launch
     except Exception:
         return None
 
@@ -306,7 +308,7 @@ def main():
         ach = mlp_fl / (mlp_ms * 1e-3) / 1e12
         roofline = {"kernel": "mlp_chain_tc_kernel (decoder, tcgen05)", "bound": "tensor", "achieved": ach,
                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                    "traffic": ncu_traffic("mlp_chain_tc_kernel"),
+                    "traffic": ncu_traffic("mlp_chain_tc_kernel", mlp_fl / mlp_n / (FLOP_PER_EVAL / 2.0)),
                     "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "avg_launch_ms": mlp_ms / mlp_n, "flop_per_launch": mlp_fl / mlp_n, "share_of_step": mlp_ms / total_ms}
     elif mlp_ms > 0:

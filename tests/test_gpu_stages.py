@@ -52,6 +52,31 @@ def test_prepare_rays_ndc_golden():
     H.assert_close(vd, ref, 2e-7, what="viewdirs")
 
 
+@pytest.mark.parametrize("dtype,tdt", [(NVSR_F16, torch.float16), (NVSR_BF16, torch.bfloat16), (NVSR_F32, torch.float32)])
+@pytest.mark.parametrize("shape", [(48, 200, 200), (16, 5, 9), (8, 3, 1)])
+def test_pack_plane_layouts(dtype, tdt, shape):
+    """nvsr_pack_plane: fp32 -> channels-last [Rh,Rw,C]; 16-bit -> x-pair records [Rh,C/8,Rw,2,8] (texel chunk +
+    its right neighbour's, the last column paired with itself), values rounded to nearest and saturated."""
+    torch.manual_seed(11)
+    c, rh, rw = shape
+    plane = torch.randn(1, c, rh, rw) * 3
+    plane[0, 0, 0, 0] = 1e6     # beyond fp16: saturates to the largest finite value instead of inf
+    plane[0, 1, 0, 0] = -1e6
+    out = ops.pack_plane(plane.to(DEV), dtype).cpu()
+    if dtype == NVSR_F32:
+        assert out.shape == (rh, rw, c)
+        assert torch.equal(out, plane[0].permute(1, 2, 0).contiguous())
+        return
+    assert out.shape == (rh, c // 8, rw, 2, 8) and out.dtype == tdt
+    fmax = torch.finfo(tdt).max
+    ref = plane[0].clamp(-fmax, fmax).to(tdt)                      # [C,Rh,Rw], round to nearest even
+    left = ref.reshape(c // 8, 8, rh, rw).permute(2, 0, 3, 1)      # [Rh,C/8,Rw,8]
+    right = left[:, :, torch.clamp(torch.arange(rw) + 1, max=rw - 1)]
+    assert torch.equal(out[..., 0, :], left)
+    assert torch.equal(out[..., 1, :], right)
+    assert torch.isfinite(out.float()).all()
+
+
 def _forward_points(model, sid, x6, precision):
     """TwoDimPlanesModel.forward(x[n,6]) through the kernels: points as 1-sample rays (rd = 0)."""
     model.set_cur_scene_id(sid)
