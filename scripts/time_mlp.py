@@ -25,8 +25,8 @@ for which in ("density", "rgb"):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): run(which)
+    for _ in range(int(os.environ.get("REPS", "10"))): run(which)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    ms = e0.elapsed_time(e1) / int(os.environ.get("REPS", "10"))
     fl = 2 * rows * (55424 if which == "density" else 74112 - 48 * 128)
     print(f"NVSR_DBG={os.environ.get('NVSR_DBG','0'):>3s} {which:8s} {ms:7.3f} ms  {fl/ms/1e9:7.1f} TFLOP/s  cycles/tile {ms*1e-3*1.965e9/(tiles/148):7.0f}")
