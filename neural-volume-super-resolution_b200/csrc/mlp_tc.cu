@@ -610,251 +610,6 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fixed 4x128 chains, "all hands" schedule.  Same data path as mlp_chain_tc_kernel (weights resident in
-// shared memory, accumulator D_s and hidden activations A_s of two tiles in TMEM, bias pre-loaded into D_s,
-// last arriver issues the next MMAs), but ALL 16 warps work on ONE slot's layer at a time, each on
-// 32 rows x 32 columns (one tcgen05.ld / pack / st group), and the two slots strictly alternate: while the
-// tensor core runs slot A's layer, every warp is in slot B's epilogue.  A layer epilogue is a chain of
-// dependent instructions (measured ~400 cycles for two column groups per warp, of which the TMEM load is 33);
-// halving the per-warp chain shortens the MMA -> epilogue -> MMA round trip that bounds a slot, and no warp
-// ever idles waiting for its own slot's MMA.  Issuing a layer's eight tcgen05.mma blocks the issuing thread
-// for about as long as they execute (~450 cycles), which in this schedule would delay that warp's share of
-// the NEXT epilogue and with it the whole CTA — so a 17th warp does nothing but wait for a slot's 16 arrivals
-// and issue (17 warps x 120 registers still fit the register file).
-constexpr int kTc16Warps = 16;
-constexpr int kTc16Threads = 32 * (kTc16Warps + 1);
-constexpr int kHpPitch = 9;  // floats per row of the head partials: 3 column groups x 3 heads (odd: conflict-free)
-
-template <bool F16, int HN, bool RB0>
-__global__ void __launch_bounds__(kTc16Threads, 1)
-mlp_chain_tc16_kernel(const __grid_constant__ TcArgs a) {
-  constexpr int L = 4;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
-  float* sbias = reinterpret_cast<float*>(smem + a.bias_off);    // [4][128]
-  float* sheadw = reinterpret_cast<float*>(smem + a.headw_off);  // [kTcMaxHeadRows][128]
-  float* shpart = reinterpret_cast<float*>(smem + a.hpart_off);  // [128 rows][kHpPitch]: groups 1..3 -> group 0
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t G = gridDim.x;
-  const int quad = warp & 3;   // TMEM lane quadrant this warp may access
-  const int grp = warp >> 2;   // column group: columns [32 grp, 32 grp + 32) of every layer
-  const int r = quad * 32 + lane;
-  const int col0 = grp * 32;
-
-  // ---- one-time setup ----
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[BAR_W], 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[BAR_IN_FULL + s], kTc16Warps);
-      mbar_init(&bars[BAR_RB_FULL + s], kRbRowsMax);
-      mbar_init(&bars[BAR_ACC_FULL + s], 1);
-      mbar_init(&bars[BAR_DONE + s], kTc16Warps);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < L * 128; i += kTc16Threads) {
-    const TcLayer& ly = a.layer[i >> 7];
-    sbias[i] = ly.bias ? __ldg(ly.bias + (i & 127)) : 0.f;
-  }
-  for (int i = threadIdx.x; i < kTcMaxHeadRows * 128; i += kTc16Threads)
-    sheadw[i] = (i < HN * 128) ? __ldg(a.layer[L - 1].head_w + i) : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // lane 0 of every warp copies one sixteenth of the tile image; warps 0..7 one staged bias row each
-  auto issue_tile_loads = [&](int s, int64_t tile) {
-    const uint32_t piece = a.in_bytes / kTc16Warps;  // K * 16 bytes: a multiple of 16
-    mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], piece);
-    bulk_g2s(smem + a.in_off[s] + warp * piece, a.in + tile * (int64_t)a.in_bytes + warp * piece, piece,
-             &bars[BAR_IN_FULL + s]);
-    if (RB0 && warp < kRbRowsMax) {
-      const TcLayer& rl = a.layer[0];
-      const int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays;
-      if (ray0 + warp < a.n_rays) {
-        mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], 128u * 4u);
-        float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
-        bulk_g2s(dst + warp * kRbPitch, rl.row_bias + (ray0 + warp) * 128, 128u * 4u, &bars[BAR_RB_FULL + s]);
-      } else {
-        mbar_arrive(&bars[BAR_RB_FULL + s]);
-      }
-    }
-  };
-  auto d_base = [&](int s) { return tmem_base + (uint32_t)s * kSlotCols; };
-  auto d_tmem = [&](int s) { return d_base(s) + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0; };
-  auto a_tmem = [&](int s) { return d_base(s) + ((uint32_t)(quad * 32) << 16) + kSlotAOff + (uint32_t)(col0 >> 1); };
-
-  // MMAs of layer l of slot s's tile number `use` (whole warp; one elected lane issues); all accumulate
-  // onto the bias pre-loaded into D_s
-  auto issue_layer = [&](int s, int l, uint32_t use) {
-    const TcLayer& ly = a.layer[l];
-    const uint32_t idesc = umma_idesc_16(128, F16);
-    const uint64_t bdesc0 = umma_desc(smem_u32(smem + ly.w_off), 2048u, 128u);
-    if (l == 0) {
-      mbar_wait(&bars[BAR_W], 0);
-      mbar_wait(&bars[BAR_IN_FULL + s], use & 1);
-    }
-    tc_fence_after();
-    if (elect_one()) {
-      if (l == 0) {
-        const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
-        const int ksteps = ly.k >> 4;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_ss(d_base(s), adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * 256), idesc, 1u);
-      } else {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ts(d_base(s), d_base(s) + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * 256), idesc, 1u);
-      }
-      umma_commit(&bars[BAR_ACC_FULL + s]);
-    }
-    __syncwarp();
-  };
-  // this warp's TMEM writes for slot s's next accumulation are done: count it on the slot's mbarrier
-  // (the issuer warp waits for all 16)
-  auto arrive_done = [&](int s) {
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[BAR_DONE + s]);
-  };
-  // this thread's 32 bias values of `layer` for slot s (layer 0 of an RB0 chain: the staged row of its ray)
-  auto bias_ptr = [&](int s, int layer) -> const float* {
-    if (RB0 && layer == 0)
-      return reinterpret_cast<const float*>(smem + a.rb_off[s]) + (r & (kBlkRays - 1)) * kRbPitch + col0;
-    return sbias + layer * 128 + col0;
-  };
-  auto store_bias32 = [&](int s, int layer) {
-    uint32_t b[32];
-    load_bias32(bias_ptr(s, layer), b);
-    tmem_st32(d_tmem(s), b);
-  };
-
-  if (warp == kTc16Warps) {
-    // ================= issuer warp: same (tile, layer, slot) walk as the epilogue warps =================
-    uint32_t ph_done[2] = {0, 0};
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars[BAR_W], a.w_bytes_total);
-      for (int l = 0; l < L; ++l) {
-        const TcLayer& ly = a.layer[l];
-        bulk_g2s(smem + ly.w_off, ly.w, (uint32_t)(ly.k * 128 * 2), &bars[BAR_W]);
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (blockIdx.x + (int64_t)s * G < a.n_tiles) {
-        mbar_wait(&bars[BAR_DONE + s], ph_done[s]);
-        ph_done[s] ^= 1;
-        issue_layer(s, 0, 0u);
-      }
-    }
-    for (uint32_t use = 0;; ++use) {
-      if (blockIdx.x + (int64_t)(2 * use) * G >= a.n_tiles) break;
-#pragma unroll
-      for (int l = 0; l < L; ++l) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int64_t tile = blockIdx.x + (int64_t)(2 * use + s) * G;
-          if (tile >= a.n_tiles) continue;
-          const bool last = l == L - 1;
-          const bool issue_next = last ? (tile + 2 * G < a.n_tiles) : true;
-          mbar_wait(&bars[BAR_DONE + s], ph_done[s]);
-          ph_done[s] ^= 1;
-          if (issue_next) issue_layer(s, last ? 0 : l + 1, last ? use + 1 : use);
-        }
-      }
-    }
-  } else {
-  uint32_t ph_acc[2] = {0, 0}, ph_rb[2] = {0, 0};
-
-  // prologue: both slots' first tiles, D_s <- layer-0 bias
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int64_t first = blockIdx.x + (int64_t)s * G;
-    if (first < a.n_tiles) {
-      if (lane == 0) issue_tile_loads(s, first);
-      if (RB0) {
-        mbar_wait(&bars[BAR_RB_FULL + s], ph_rb[s]);
-        ph_rb[s] ^= 1;
-      }
-      store_bias32(s, 0);
-      arrive_done(s);
-    }
-  }
-
-  for (uint32_t use = 0;; ++use) {
-    if (blockIdx.x + (int64_t)(2 * use) * G >= a.n_tiles) break;
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int64_t tile = blockIdx.x + (int64_t)(2 * use + s) * G;
-        if (tile >= a.n_tiles) continue;
-        const int64_t next_tile = tile + 2 * G;
-        const bool next_valid = next_tile < a.n_tiles;
-        const bool last = l == L - 1;
-        if (RB0 && last && next_valid) {  // the next tile's staged bias rows (issued three layers ago)
-          mbar_wait(&bars[BAR_RB_FULL + s], ph_rb[s]);
-          ph_rb[s] ^= 1;
-        }
-        mbar_wait(&bars[BAR_ACC_FULL + s], ph_acc[s]);
-        ph_acc[s] ^= 1;
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(d_tmem(s), v);
-        tmem_ld_wait();
-        if (!last) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          tmem_st16(a_tmem(s), pk);
-          store_bias32(s, l + 1);
-          arrive_done(s);
-          // layer 0's MMAs have completed: the slot's ring buffer and staged bias rows may take the next tile
-          if (l == 0 && next_valid && lane == 0) issue_tile_loads(s, next_tile);
-        } else {
-          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-          head_dot32<HN>(v, sheadw + col0, hacc);
-          if (next_valid) store_bias32(s, 0);
-          arrive_done(s);
-          // combine the four column groups of a row: groups 1..3 -> smem -> group 0
-          float* hp = shpart + r * kHpPitch;
-          if (grp > 0) {
-#pragma unroll
-            for (int h = 0; h < HN; ++h) hp[(grp - 1) * 3 + h] = hacc[h];
-          }
-          named_bar_sync(1 + quad, 128);  // the four warps sharing this lane quadrant
-          const int64_t row = tile * kTileRows + r;
-          if (grp == 0 && row < a.rows) {
-            const TcLayer& ly = a.layer[L - 1];
-#pragma unroll
-            for (int h = 0; h < HN; ++h)
-              a.raw[(int64_t)(ly.head_ch + h) * a.raw_stride + row] =
-                  hacc[h] + hp[h] + hp[3 + h] + hp[6 + h] + __ldg(ly.head_b + h);
-          }
-          named_bar_sync(5 + quad, 128);  // partials consumed: the other slot's head phase may overwrite them
-        }
-      }
-    }
-  }
-
-  }  // epilogue warps
-
-  // ---- teardown ----
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
 int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   TcArgs a;
   a.n_layers = m->n_layers;
@@ -904,7 +659,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   }
   a.bias_off = off, off += (uint32_t)m->n_layers * 128u * 4u;
   a.headw_off = off, off += kTcMaxHeadRows * 128u * 4u;
-  a.hpart_off = off, off += 128u * (uint32_t)kHpPitch * 4u > 2u * 128u * 4u * 4u ? 128u * (uint32_t)kHpPitch * 4u : 2u * 128u * 4u * 4u;
+  a.hpart_off = off, off += 2u * 128u * 4u * 4u;
   a.bar_off = off, off += BAR_COUNT * 8u + 16u;  // barriers, then {tmem base, arrival counter x2}
   const uint32_t smem_bytes = off;
   if (smem_bytes > 227u * 1024u) return NVSR_ERR_RESOURCE;
@@ -926,15 +681,6 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   void (*kernel)(TcArgs) = nullptr;
   // compile-time specialisations: the two decoders of the tri-plane model
   const bool rb_ok = a.rb_layer < 0 || a.rb_staged;
-  int threads = kTcThreads;
-#ifndef NVSR_TC_NO16
-  const bool all_hands = a.layer[m->n_layers - 1].head_row == 0 && m->layer[0].k % 16 == 0;
-  if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 1 && a.rb_layer < 0 && all_hands)
-    kernel = f16 ? mlp_chain_tc16_kernel<true, 1, false> : mlp_chain_tc16_kernel<false, 1, false>, threads = kTc16Threads;
-  else if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 3 && a.rb_layer == 0 && all_hands)
-    kernel = f16 ? mlp_chain_tc16_kernel<true, 3, true> : mlp_chain_tc16_kernel<false, 3, true>, threads = kTc16Threads;
-  else
-#endif
   if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 1 && a.rb_layer < 0)
     kernel = f16 ? mlp_chain_tc_kernel<true, 4, 1, false> : mlp_chain_tc_kernel<false, 4, 1, false>;
   else if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 3 && a.rb_layer == 0)
@@ -944,7 +690,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
   int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
-  kernel<<<(unsigned)grid, threads, smem_bytes, st>>>(a);
+  kernel<<<(unsigned)grid, kTcThreads, smem_bytes, st>>>(a);
   NVSR_RETURN_LAST_ERROR();
 }
 
