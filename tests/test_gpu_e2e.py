@@ -218,6 +218,8 @@ def test_full_frame_properties(big_scene):
         nvsr_b200.set_ray_chunk(20000)   # ragged chunks
         again = nvsr_b200.eval_nerf(800, 800, focal, mc, mf, ro, rd, opt, sid, scene_config=scfg)
         assert torch.equal(full[0], again[0]) and torch.equal(full[3], again[3])
-        nvsr_b200.set_ray_chunk(32768)
+        nvsr_b200.set_ray_chunk(327680)  # the default: two balanced half-frame chunks
+        again = nvsr_b200.eval_nerf(800, 800, focal, mc, mf, ro, rd, opt, sid, scene_config=scfg)
+        assert torch.equal(full[0], again[0]) and torch.equal(full[3], again[3])
         band = nvsr_b200.render_frame(800, 800, focal, pose, mc, mf, opt, sid, scfg, row_range=(300, 400))
         assert torch.equal(band[3].reshape(100, 800, 3), full[3][300:400])
