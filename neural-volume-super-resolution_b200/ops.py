@@ -184,7 +184,7 @@ def pack_weight16(weight, k_pad=None, dtype=NVSR_BF16):
 
 # ---------------------------------------------------------------------------------------------
 class PackedPlanes:
-    """Device-resident, channels-last position planes of one scene + box + projection matrices."""
+    """Device-resident packed position planes of one scene (nvsr_pack_plane images) + box + projection matrices."""
 
     def __init__(self, planes, dtype, box_lo, box_rng, proj, vplane=None, view_lo_rng=None):
         self.planes = planes            # list of 3 tensors: fp32 [Rh,Rw,C] or 16-bit [Rh,C/8,Rw,2,8]

@@ -6,7 +6,7 @@ Two things live here:
      attribute names, to build synthetic Blender-shaped scenes on a box where the reference is
      not importable (tests, bench, smoke).  The render path itself works on the real reference
      objects as well: it only reads the attributes listed in SURVEY.md §8(b).
-  2. the packers: planes NCHW fp32 -> channels-last (fp32|bf16), decoder weights -> chain layers.
+  2. the packers: planes NCHW fp32 -> nvsr_pack_plane images (fp32 channels-last / 16-bit x-pair records), decoder weights -> chain layers.
      Packing is cached per (tensor identity, version) so it happens once per scene / weight update,
      never per chunk (the reference re-uploads the SR plane for every network chunk, models.py:893).
 """
@@ -368,7 +368,7 @@ def check_supported_planes_model(model):
 
 
 def _packed_plane(src, dtype):
-    """channels-last copy of one NCHW plane tensor, cached per (tensor object, version) and dtype"""
+    """packed device image of one NCHW plane tensor, cached per (tensor object, version) and dtype"""
     per_dtype = _plane_cache.get(src, _Cache.key_of(src), dict)
     if dtype not in per_dtype:
         per_dtype[dtype] = ops.pack_plane(src.cuda(), dtype)
