@@ -288,6 +288,87 @@ def test_composite_blocked_equals_ray_major(n, S, nf):
         assert torch.equal(a[k], b[k]) or (k == "disp" and torch.equal(torch.nan_to_num(a[k], 7.0), torch.nan_to_num(b[k], 7.0))), k
 
 
+def test_composite_full_size_properties():
+    """BASELINE config-2 chunk size (327 680 rays, 64 coarse -> 128 fine) through size-independent properties:
+    merged depths sorted and a permutation of cat(z, z_samples); inds within range and consistent with the
+    samples' bins; acc = sum(weights); the white-background identity; blocked == ray-major at full size."""
+    torch.manual_seed(21)
+    n, S, nf = 327680, 64, 128
+    t = torch.linspace(0, 1, S, device=DEV)
+    z = (2.0 * (1 - t) + 6.0 * t).expand(n, S).contiguous()
+    rf = torch.randn(n, S, 4, device=DEV) * 2
+    rf[..., 3] = rf[..., 3] * 3 - 4                       # sparse density: weights concentrate on a few bins
+    rd = torch.randn(n, 3, device=DEV)
+    u = torch.linspace(0, 1, nf, device=DEV)
+    raw = ops.raw_to_planar(rf)
+    o = ops.composite(raw, z, rd, S, n_fine=nf, u=u, want_samples=True, want_inds=True, want_weights=True)
+    zm, zs, inds, w = o["z_merged"], o["z_samples"], o["inds"], o["weights"]
+    assert bool((zm[:, 1:] >= zm[:, :-1]).all())
+    assert torch.equal(zm, torch.sort(torch.cat([z, zs], -1), -1)[0])
+    assert int(inds.min()) >= 1 and int(inds.max()) <= S - 1       # u in [0,1], cdf[0] = 0
+    mid = 0.5 * (z[:, 1:] + z[:, :-1])
+    below = (inds - 1).clamp(min=0)
+    above = inds.clamp(max=S - 2)
+    lo, hi = torch.gather(mid, 1, below), torch.gather(mid, 1, above)
+    assert bool(((zs >= lo - 1e-6) & (zs <= hi + 1e-6)).all())     # every sample lies in the bin its index names
+    H.assert_close(o["acc"], w.sum(-1), 2e-5, what="acc = sum(weights)")
+    assert bool((w >= 0).all()) and float(o["acc"].max()) <= 1.0 + 1e-5
+    ow = ops.composite(raw, z, rd, S, white_background=True)
+    H.assert_close(ow["rgb"], o["rgb"] + (1.0 - o["acc"])[:, None], 1e-6, what="white background identity")
+    # the BLOCKED order (what the decoder writes) gives bit-identical results at this size too
+    pad = rf.reshape(n // 8, 8, S // 16, 16, 4).permute(4, 0, 2, 3, 1).reshape(4, -1).contiguous()
+    ob = ops.composite(pad, z, rd, S, n_fine=nf, u=u, want_samples=True, want_inds=True, want_weights=True,
+                       row_order=ops.ROWS_BLOCKED)
+    for k in ("rgb", "acc", "depth", "weights", "inds", "z_samples", "z_merged"):
+        assert torch.equal(o[k], ob[k]), k
+
+
+@pytest.mark.parametrize("precision", [NVSR_F32, NVSR_F16])
+def test_gather_constant_planes_and_linearity(precision):
+    """Bilinear gather properties that hold at any size (1.3 M points here): constant planes interpolate to the
+    constant (weights sum to 1), and fp32 gathering is linear in the planes."""
+    torch.manual_seed(22)
+    mc, _, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=1, device=DEV)
+    n, S = 20480, 64
+    pose, focal = scene.blender_camera(800)
+    ro, rd = nvsr_b200.get_ray_bundle(800, 800, focal, pose.to(DEV))
+    ro, rd = ro.reshape(-1, 3)[250 * 800:250 * 800 + n].contiguous(), rd.reshape(-1, 3)[250 * 800:250 * 800 + n].contiguous()
+    t_vals = torch.linspace(0, 1, S, device=DEV)
+    layout = ops.FEAT_LAYOUT[precision]
+    names = [scene.get_plane_name(sid, d) for d in range(3)]
+    keep = {k: mc.planes_[k].detach().clone() for k in names}
+    const = torch.linspace(-2.0, 2.0, 48, device=DEV).reshape(1, 48, 1, 1)
+
+    def gather():
+        scene.clear_caches()
+        packed = scene.pack_scene_planes(mc, sid, precision)
+        fp, fm, _ = ops.sample_gather(ro, rd, 2.0, 6.0, packed, layout, t_vals=t_vals)
+        if precision == NVSR_F32:
+            return fp, fm                                   # row-major fp32 [rows, 3C] / [rows, C]
+        return _untile(fp, n, S).float(), _untile(fm, n, S).float()
+
+    with torch.no_grad():
+        for k in names:
+            mc.planes_[k].copy_(const.expand_as(mc.planes_[k]))
+        fp, fm = gather()
+        ref = const.reshape(48).to(torch.float16 if precision == NVSR_F16 else torch.float32).float()
+        tol = 2e-3 if precision == NVSR_F16 else 1e-6
+        H.assert_close(fp, ref.repeat(3).expand_as(fp), tol, what="constant planes -> constant features")
+        H.assert_close(fm, ref.expand_as(fm), tol, what="constant planes -> constant mean")
+        if precision == NVSR_F32:
+            a = {k: torch.randn_like(keep[k]) for k in names}
+            b = {k: torch.randn_like(keep[k]) for k in names}
+            outs = []
+            for planes in (a, b, {k: a[k] + b[k] for k in names}):
+                for k in names:
+                    mc.planes_[k].copy_(planes[k])
+                outs.append(gather()[0])
+            H.assert_close(outs[2], outs[0] + outs[1], 2e-6, what="gather(A + B) = gather(A) + gather(B)")
+        for k in names:
+            mc.planes_[k].copy_(keep[k])
+    scene.clear_caches()
+
+
 def test_ipe_golden():
     g = golden("stage_ipe.npz")
     enc = ops.ipe(T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV), float(g["radius"]), 6)
