@@ -267,137 +267,6 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// gather_run_16: the same arithmetic per row as gather_tile_16, but a thread owns a RUN of 4 consecutive samples
-// of one ray (a CTA = 8 rays x 64 samples = 4 tiles of the BLOCKED order; thread = (ray-in-block t & 7,
-// run t >> 3)).  On the fine pass the merged depths cluster around surfaces: ~57 % of the consecutive samples
-// of a ray fall into the texel cell of their predecessor (measured on the bench scene), and then the two
-// footprint records already sit in registers — the 256-bit loads are issued only by the lanes whose cell
-// changed, which is what the L1 data pipe (the fine pass's limiter, 91 %) is charged for.  The bilinear
-// weights of the run live in shared memory (thread-private slots, no barrier), the record offsets in
-// registers.  Stores are as coalesced as before: for a fixed sample of the run a warp covers four full
-// 128-byte segments of one chunk of one tile.
-constexpr int kRun = 4;                 // consecutive samples per thread
-constexpr int kRunTiles = 4;            // tiles per CTA pass: 16 runs x 4 samples = 64 samples of 8 rays
-#ifndef NVSR_GATHER_MINB
-#define NVSR_GATHER_MINB 4
-#endif
-
-template <bool F16>
-__device__ __forceinline__ void interp_row(unsigned long long acc[4], const XPair& vt, const XPair& vb, const float4& w) {
-  // ATen order: nw*w + ne*w + sw*w + se*w
-  texel_fma<F16, true>(acc, vt.l, w.x);
-  texel_fma<F16, false>(acc, vt.r, w.y);
-  texel_fma<F16, false>(acc, vb.l, w.z);
-  texel_fma<F16, false>(acc, vb.r, w.w);
-}
-
-template <bool F16, int CH_T>
-__global__ void __launch_bounds__(kGatherThreads, NVSR_GATHER_MINB)
-gather_run_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
-              float* __restrict__ z_out, int64_t n_units, int units_per_block) {
-  __shared__ float4 wsm[kRun * 3 * kGatherThreads];  // [sample of the run][plane][thread]: (w00, w01, w10, w11)
-  const int CH = CH_T > 0 ? CH_T : p.C / 8;
-  const uint32_t p_bytes = 3u * CH * 2048u;
-  const uint32_t m_bytes = (uint32_t)CH * 2048u;
-  const int TS = tiles_per_block(a.S);
-  const int t = threadIdx.x;
-  const int rl = t & 7, q = t >> 3;              // ray in block, run index 0..15
-  const unsigned long long third = pack_f32x2(1.f / 3.f, 1.f / 3.f);
-  const XPair* const pl[3] = {reinterpret_cast<const XPair*>(p.plane[0]), reinterpret_cast<const XPair*>(p.plane[1]),
-                              reinterpret_cast<const XPair*>(p.plane[2])};
-  const bool vec_z = (a.S & 3) == 0;
-
-  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int64_t blk = unit / units_per_block;
-    const int pass = (int)(unit - blk * units_per_block);
-    const int64_t ray = blk * kBlkRays + rl;
-    const int s0 = pass * (kRunTiles * kBlkSamples) + kRun * q;
-    const bool ray_ok = ray < a.n_rays;
-    // ---- the run's depths, footprints and weights ----
-    float z[kRun];
-    if (ray_ok && a.z_in && vec_z && s0 + kRun <= a.S) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(a.z_in + ray * a.S + s0));
-      z[0] = v.x, z[1] = v.y, z[2] = v.z, z[3] = v.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < kRun; ++j) z[j] = (ray_ok && s0 + j < a.S) ? sample_depth(a, ray, s0 + j) : 0.f;
-    }
-    if (z_out && ray_ok) {
-      float* zd = z_out + ray * a.S + s0;
-      if (vec_z && s0 + kRun <= a.S) *reinterpret_cast<float4*>(zd) = make_float4(z[0], z[1], z[2], z[3]);
-      else {
-#pragma unroll
-        for (int j = 0; j < kRun; ++j)
-          if (s0 + j < a.S) zd[j] = z[j];
-      }
-    }
-    uint32_t top[kRun][3], bot[kRun][3];
-    unsigned reload = 0;  // bit j*3+d: sample j of the run needs plane d's records loaded (its cell changed)
-#pragma unroll
-    for (int j = 0; j < kRun; ++j) {
-      if (ray_ok && s0 + j < a.S) {
-        Bilin b[3];
-        sample_corners(a, p, ray, z[j], b);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const Foot f = make_foot(b[d], p.rw[d], CH);
-          top[j][d] = f.top, bot[j][d] = f.bot;
-          wsm[(j * 3 + d) * kGatherThreads + t] = make_float4(f.w00, f.w01, f.w10, f.w11);
-        }
-      } else {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          top[j][d] = 0u, bot[j][d] = 0u;  // padded rows -> zeros
-          wsm[(j * 3 + d) * kGatherThreads + t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        if (j == 0 || top[j][d] != top[j - 1][d] || bot[j][d] != bot[j - 1][d]) reload |= 1u << (j * 3 + d);
-    }
-    // ---- the run's rows: tile (pass*4 + q/4) of the block, rows (4 (q%4) + j) * 8 + rl ----
-    const int tile_in_blk = pass * kRunTiles + (q >> 2);
-    if (tile_in_blk >= TS) continue;   // (whole warps: the 4 runs of a tile share a warp)
-    const int64_t tile = blk * TS + tile_in_blk;
-    const uint32_t row0 = (uint32_t)((kRun * (q & 3)) * kBlkRays + rl);
-    uint8_t* gP = featP + tile * (int64_t)p_bytes + row0 * 16u;
-    uint8_t* gM = featM + tile * (int64_t)m_bytes + row0 * 16u;
-#pragma unroll 1
-    for (int c = 0; c < CH; ++c) {
-      unsigned long long mean[kRun][4];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        XPair vt, vb;
-        const uint32_t coff = (uint32_t)(c * p.rw[d]);
-#pragma unroll
-        for (int j = 0; j < kRun; ++j) {
-          if ((reload >> (j * 3 + d)) & 1u) {
-            vt = ldg256(pl[d] + top[j][d] + coff);
-            vb = ldg256(pl[d] + bot[j][d] + coff);
-          }
-          const float4 w = wsm[(j * 3 + d) * kGatherThreads + t];
-          unsigned long long acc[4];
-          interp_row<F16>(acc, vt, vb, w);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) mean[j][e] = d == 0 ? acc[e] : add_f32x2(mean[j][e], acc[e]);
-          uint4 o;
-          o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
-          o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
-          st_stream16(gP + (uint32_t)(d * CH + c) * 2048u + (uint32_t)j * (kBlkRays * 16u), o);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kRun; ++j) {
-        uint4 o;
-        o.x = pack16_pair<F16>(mul_f32x2(mean[j][0], third)), o.y = pack16_pair<F16>(mul_f32x2(mean[j][1], third));
-        o.z = pack16_pair<F16>(mul_f32x2(mean[j][2], third)), o.w = pack16_pair<F16>(mul_f32x2(mean[j][3], third));
-        st_stream16(gM + (uint32_t)c * 2048u + (uint32_t)j * (kBlkRays * 16u), o);
-      }
-    }
-  }
-}
-
 }  // namespace nvsr
 
 using namespace nvsr;
@@ -441,18 +310,6 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     auto kernel = f16 ? (c48 ? gather_tile_16<true, 6> : gather_tile_16<true, 0>)
                       : (c48 ? gather_tile_16<false, 6> : gather_tile_16<false, 0>);
     int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
-#ifndef NVSR_GATHER_PER_ROW
-    {
-      auto krun = f16 ? (c48 ? gather_run_16<true, 6> : gather_run_16<true, 0>)
-                      : (c48 ? gather_run_16<false, 6> : gather_run_16<false, 0>);
-      const int upb = (tiles_per_block(s->n_samples) + kRunTiles - 1) / kRunTiles;
-      const int64_t n_units = ceil_div64(s->n_rays, kBlkRays) * upb;
-      int64_t g = (int64_t)kNumSMs * NVSR_GATHER_MINB * 4;
-      if (g > n_units) g = n_units;
-      krun<<<(unsigned)g, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_units, upb);
-      NVSR_RETURN_LAST_ERROR();
-    }
-#endif
     int64_t grid = (int64_t)kNumSMs * 5 * 4;  // a few waves of the 5 resident CTAs per SM, grid-stride beyond
     if (grid > n_tiles) grid = n_tiles;
     kernel<<<(unsigned)grid, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_tiles);
