@@ -217,6 +217,61 @@ row_bias_kernel(const float* __restrict__ vin, int64_t n_rays, int K, int Kp, co
   }
 }
 
+
+// Same product for the shapes of the hot path (n_out a multiple of 4, n_out <= 128): one warp per group of 8
+// consecutive rays, lane l owns output columns 4l..4l+3, so a ray's row is written as one coalesced 512-byte
+// store per warp.  Weights sit transposed in shared memory ([k][n_out]: one conflict-free LDS.128 per lane and
+// k), the group's 8 x K inputs are staged transposed per warp ([k][8 rays]: two broadcast LDS.128 per k), the
+// accumulation runs over k in order with fused multiply-adds — bit-identical to row_bias_kernel.  HBM-bound:
+// 4 K + 4 n_out bytes per ray.
+constexpr int kRb2Warps = 8;
+__global__ void __launch_bounds__(kRb2Warps * 32)
+row_bias_warp_kernel(const float* __restrict__ vin, int64_t n_rays, int K, const float* __restrict__ w, int ldw,
+                     const float* __restrict__ b, int n_out, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sw[];  // [K][n_out] transposed weights | per warp [K][8] inputs
+  float* sv = sw + (size_t)K * n_out + (threadIdx.x >> 5) * (K * 8);
+  for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) {
+    int n = i / K, k = i - n * K;
+    sw[k * n_out + n] = w[(int64_t)n * ldw + k];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int col = 4 * lane;
+  const bool active = col < n_out;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (b && active) bias = make_float4(__ldg(b + col), __ldg(b + col + 1), __ldg(b + col + 2), __ldg(b + col + 3));
+  const int64_t n_groups = ceil_div64(n_rays, 8);
+  for (int64_t g = (int64_t)blockIdx.x * kRb2Warps + (threadIdx.x >> 5); g < n_groups; g += (int64_t)gridDim.x * kRb2Warps) {
+    const int64_t r0 = g * 8;
+    __syncwarp();
+    // the group's inputs are 8*K contiguous floats: coalesced read, transposed store
+    for (int i = lane; i < 8 * K; i += 32) {
+      int j = i / K, k = i - j * K;
+      sv[k * 8 + j] = (r0 + j < n_rays) ? __ldg(vin + r0 * K + i) : 0.f;
+    }
+    __syncwarp();
+    float4 acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias;
+    if (active) {
+      for (int k = 0; k < K; ++k) {
+        const float4 wk = *reinterpret_cast<const float4*>(sw + k * n_out + col);
+        const float4 va = *reinterpret_cast<const float4*>(sv + k * 8);
+        const float4 vb = *reinterpret_cast<const float4*>(sv + k * 8 + 4);
+        const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j].x = fmaf(wk.x, v[j], acc[j].x), acc[j].y = fmaf(wk.y, v[j], acc[j].y);
+          acc[j].z = fmaf(wk.z, v[j], acc[j].z), acc[j].w = fmaf(wk.w, v[j], acc[j].w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + j < n_rays) *reinterpret_cast<float4*>(out + (r0 + j) * n_out + col) = acc[j];
+    }
+  }
+}
+
 }  // namespace nvsr
 
 using namespace nvsr;
@@ -312,6 +367,17 @@ extern "C" int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, co
   NVSR_CHECK_ARG(vin && w && out && n_rays >= 0 && k > 0 && n_out > 0 && ldw >= k);
   NVSR_CHECK_ARG((size_t)k * n_out * sizeof(float) <= 48 * 1024);
   if (n_rays == 0) return NVSR_OK;
+  if ((n_out & 3) == 0 && n_out <= 128 && aligned16(out)) {
+    size_t smem2 = ((size_t)k * n_out + (size_t)kRb2Warps * k * 8) * sizeof(float);
+    if (smem2 > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(row_bias_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e != cudaSuccess) return (int32_t)e;
+    }
+    int64_t blocks2 = ceil_div64(ceil_div64(n_rays, 8), kRb2Warps);
+    if (blocks2 > 6 * kNumSMs) blocks2 = 6 * kNumSMs;
+    row_bias_warp_kernel<<<(unsigned)blocks2, kRb2Warps * 32, smem2, (cudaStream_t)stream>>>(vin, n_rays, k, w, ldw, b, n_out, out);
+    NVSR_RETURN_LAST_ERROR();
+  }
   const int kp = (k + 3) & ~3;
   size_t smem = ((size_t)kp * (n_out + 1) + 4 + (size_t)kRbRays * kp) * sizeof(float);
   if (smem > 200 * 1024) return NVSR_ERR_RESOURCE;
@@ -320,7 +386,7 @@ extern "C" int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, co
     if (e != cudaSuccess) return (int32_t)e;
   }
   int64_t blocks = ceil_div64(n_rays, kRbRays);
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;  // up to 4 resident CTAs per SM (37 KB smem, 512 threads each)
   row_bias_kernel<<<(unsigned)blocks, 512, smem, (cudaStream_t)stream>>>(vin, n_rays, k, kp, w, ldw, b, n_out, out);
   NVSR_RETURN_LAST_ERROR();
 }
