@@ -150,6 +150,9 @@ __device__ __forceinline__ uint32_t pack16_pair(unsigned long long v) {
 }
 
 constexpr int kGatherThreads = kTileRows;  // one thread per row
+#ifndef NVSR_GATHER_MINB
+#define NVSR_GATHER_MINB 5  // resident CTAs per SM the register budget is set for (A/B measured)
+#endif
 
 // 16-byte streaming store (the feature tile is written once and read by the next kernel: keep it out of L1,
 // which the texel reads need)
@@ -204,7 +207,7 @@ __device__ __forceinline__ void texel_fma(unsigned long long acc[4], const uint4
 // count at compile time (6 for the reference's 48-channel planes): the chunk loop is fully unrolled
 // and the loads of the next chunk are in flight while one is interpolated.
 template <bool F16, int CH_T>
-__global__ void __launch_bounds__(kGatherThreads, 5)
+__global__ void __launch_bounds__(kGatherThreads, NVSR_GATHER_MINB)
 gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
                float* __restrict__ z_out, int64_t n_tiles) {
   const int CH = CH_T > 0 ? CH_T : p.C / 8;  // 16-byte chunks per plane texel (6 for C=48)
@@ -310,7 +313,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     auto kernel = f16 ? (c48 ? gather_tile_16<true, 6> : gather_tile_16<true, 0>)
                       : (c48 ? gather_tile_16<false, 6> : gather_tile_16<false, 0>);
     int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
-    int64_t grid = (int64_t)kNumSMs * 5 * 4;  // a few waves of the 5 resident CTAs per SM, grid-stride beyond
+    int64_t grid = (int64_t)kNumSMs * NVSR_GATHER_MINB * 4;  // a few waves of the resident CTAs per SM, grid-stride beyond
     if (grid > n_tiles) grid = n_tiles;
     kernel<<<(unsigned)grid, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_tiles);
     NVSR_RETURN_LAST_ERROR();
