@@ -1,0 +1,65 @@
+"""The drop-in seam: `install()` rebinds `train_utils.run_one_iter_of_nerf` — which the reference's
+`eval_nerf` resolves through its module globals at call time (train_utils.py:311) — and optionally
+`nerf_helpers.get_ray_bundle`; the reference's own functions keep running under autograd (train(), train_nerf.py:860)
+and `uninstall()` restores them.  Host logic only: no kernel is launched here."""
+import types
+
+import torch
+
+import nvsr_b200
+from nvsr_b200 import render
+
+
+def _fake_reference_modules():
+    tu = types.ModuleType("train_utils")
+    nh = types.ModuleType("nerf_helpers")
+    calls = []
+
+    def run_one_iter_of_nerf(*a, **k):
+        calls.append(("ref_run", a, k))
+        return ("ref",) * 9
+
+    def get_ray_bundle(h, w, f, pose, padding_size=0, downsampling_offset=0):
+        calls.append(("ref_grb", h, w))
+        return "ref_ro", "ref_rd"
+
+    # like train_utils.eval_nerf: the callee is looked up in the module's globals when eval_nerf RUNS
+    exec("def eval_nerf(*a, **k):\n    return run_one_iter_of_nerf(*a, **k)\n", tu.__dict__)
+    tu.run_one_iter_of_nerf = run_one_iter_of_nerf
+    nh.get_ray_bundle = get_ray_bundle
+    return tu, nh, calls
+
+
+def test_install_dispatch_and_uninstall(monkeypatch):
+    tu, nh, calls = _fake_reference_modules()
+    ref_run, ref_grb = tu.run_one_iter_of_nerf, nh.get_ray_bundle
+    seen = []
+    monkeypatch.setattr(render, "run_one_iter_of_nerf", lambda *a, **k: seen.append((a, k)) or ("b200",) * 9)
+    nvsr_b200.install(tu, nh)
+    assert tu.run_one_iter_of_nerf is not ref_run and nh.get_ray_bundle is not ref_grb
+    wrapped = tu.run_one_iter_of_nerf
+    nvsr_b200.install(tu, nh)                       # idempotent: no double wrapping
+    assert tu.run_one_iter_of_nerf is wrapped
+
+    with torch.enable_grad():                       # train(): the reference's autograd path is untouched
+        assert tu.eval_nerf(1, 2, mode="train")[0] == "ref"
+    assert calls[-1][0] == "ref_run" and calls[-1][1] == (1, 2) and calls[-1][2] == {"mode": "train"}
+    with torch.no_grad():                           # evaluate(): through eval_nerf's late-bound global
+        assert tu.eval_nerf(3, 4, mode="validation")[0] == "b200"
+    assert seen == [((3, 4), {"mode": "validation"})]
+
+    # get_ray_bundle: host poses keep the reference's function, device poses take the kernel
+    assert nh.get_ray_bundle(4, 4, 1.0, torch.eye(4)) == ("ref_ro", "ref_rd")
+    assert calls[-1] == ("ref_grb", 4, 4)
+
+    nvsr_b200.uninstall(tu)
+    assert tu.run_one_iter_of_nerf is ref_run
+    with torch.no_grad():
+        assert tu.eval_nerf(5)[0] == "ref"
+
+
+def test_no_cpu_fallback():
+    """The product path has no CPU / PyTorch fallback: host tensors are refused, loudly."""
+    import pytest
+    with pytest.raises((nvsr_b200.NvsrError, RuntimeError, ValueError, AssertionError)):
+        nvsr_b200.get_ray_bundle(4, 4, 1.0, torch.eye(4))
