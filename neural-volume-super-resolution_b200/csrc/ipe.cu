@@ -97,6 +97,57 @@ __global__ void ipe_tile_kernel(const float* __restrict__ z, const float* __rest
   out[idx] = o4;  // idx == (tile*chunks + c)*128 + r
 }
 
+// 16-bit tile image, the six-frequency encoding of the reference's mip baseline (multires = 7 -> 36 columns,
+// k_pad = 48): ONE thread per row.  The Gaussian is computed once per row (the per-chunk kernel above repeats
+// its eight IEEE divisions for every 8-column chunk), the exponential once per (frequency, axis) for both the
+// sin and the phase-shifted block, and sin / cos of the base frequency once per axis with the precise
+// sincosf; the higher frequencies follow by the double-angle recurrence (the abs error doubles per octave:
+// < 4e-6 after five, against the 16-bit rounding of 5e-4 / 4e-3 of the value).  The reference evaluates
+// sin(fl(y + pi/2)) for the shifted block, which differs from cos(y) by the rounding of the sum (< 8e-6 at
+// |y| ~ 200): also below the 16-bit rounding.  Stores: a warp's 32 rows of one chunk are 512 contiguous bytes.
+template <bool F16>
+__global__ void __launch_bounds__(256)
+ipe_tile6_kernel(const float* __restrict__ z, const float* __restrict__ ro, const float* __restrict__ rd,
+                 int64_t n_rays, int S, float radius, uint4* __restrict__ out, int64_t n_tiles) {
+  constexpr int NF = 6, CHUNKS = 6;  // 36 values + 12 zero columns = 48 = 6 chunks of 8
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tiles * kTileRows) return;
+  const int r = (int)(idx % kTileRows);
+  const int64_t tile = idx / kTileRows;
+  const int64_t row = idx;
+  float f[48];
+#pragma unroll
+  for (int j = 0; j < 48; ++j) f[j] = 0.f;
+  if (row < n_rays * S) {
+    int64_t ray = row / S;
+    int s = (int)(row - ray * S);
+    float o[3] = {__ldg(ro + ray * 3), __ldg(ro + ray * 3 + 1), __ldg(ro + ray * 3 + 2)};
+    float d[3] = {__ldg(rd + ray * 3), __ldg(rd + ray * 3 + 1), __ldg(rd + ray * 3 + 2)};
+    IpeRow g = ipe_gaussian(__ldg(z + ray * (S + 1) + s), __ldg(z + ray * (S + 1) + s + 1), o, d, radius);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sn, cs;
+      sincosf(g.mean[c], &sn, &cs);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const float sc2 = (float)(1 << (2 * i));
+        const float e = expf(__fmul_rn(-0.5f, __fmul_rn(g.cov[c], sc2)));
+        f[i * 3 + c] = e * sn;            // sin block
+        f[3 * NF + i * 3 + c] = e * cs;   // shifted block: sin(y + pi/2)
+        const float s2 = 2.f * sn * cs, c2 = fmaf(-2.f * sn, sn, 1.f);
+        sn = s2, cs = c2;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    uint4 o4;
+    o4.x = pack16x2<F16>(f[c * 8 + 0], f[c * 8 + 1]), o4.y = pack16x2<F16>(f[c * 8 + 2], f[c * 8 + 3]);
+    o4.z = pack16x2<F16>(f[c * 8 + 4], f[c * 8 + 5]), o4.w = pack16x2<F16>(f[c * 8 + 6], f[c * 8 + 7]);
+    out[(tile * CHUNKS + c) * kTileRows + r] = o4;
+  }
+}
+
 // positional_encoding(d, nf, include_input): [d, sin(2^0 d), cos(2^0 d), sin(2^1 d), ...]
 __global__ void dir_encoding_kernel(const float* __restrict__ dirs, int64_t n, int nf, int include_input,
                                     float* __restrict__ out) {
@@ -139,6 +190,15 @@ extern "C" int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, in
     NVSR_CHECK_ARG(k_pad >= 6 * n_freqs && k_pad % 16 == 0);
     if (!aligned16(out)) return NVSR_ERR_ALIGNMENT;
     int64_t n_tiles = ceil_div64(n_rays * n_intervals, kTileRows);
+    if (n_freqs == 6 && k_pad == 48) {  // the reference's mip baseline: one thread per row
+      int64_t blocks6 = ceil_div64(n_tiles * kTileRows, 256);
+      NVSR_CHECK_ARG(blocks6 < ((int64_t)1 << 31));
+      if (out_layout == NVSR_FEAT_TILE_F16)
+        ipe_tile6_kernel<true><<<(unsigned)blocks6, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, (uint4*)out, n_tiles);
+      else
+        ipe_tile6_kernel<false><<<(unsigned)blocks6, 256, 0, st>>>(z, ro, rd, n_rays, n_intervals, radius, (uint4*)out, n_tiles);
+      NVSR_RETURN_LAST_ERROR();
+    }
     int64_t total = n_tiles * (k_pad / 8) * kTileRows;
     int64_t blocks = ceil_div64(total, 256);
     NVSR_CHECK_ARG(blocks < ((int64_t)1 << 31));
