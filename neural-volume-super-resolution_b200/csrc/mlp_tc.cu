@@ -336,7 +336,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   float* shpart = reinterpret_cast<float*>(smem + a.hpart_off);  // [2 slots][128 rows][4]: half 1 -> half 0
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = kFixed ? LC : a.n_layers;
+  const int L = kFixed ? LC : (LC < 0 ? -LC : a.n_layers);  // LC < 0: generic chain of -LC layers, loop unrolled
   const int64_t G = gridDim.x;
   const int rb_layer = kFixed ? (RB0 ? 0 : -1) : a.rb_layer;
   const bool rb_staged = kFixed ? RB0 : (a.rb_staged != 0);
@@ -537,7 +537,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #ifdef NVSR_TC_ROLLED
 #pragma unroll 1
 #else
-#pragma unroll(kFixed ? 4 : 1)
+#pragma unroll(kFixed ? 4 : (LC < 0 ? -LC : 1))
 #endif
       for (int l = 0; l < L; ++l) {
         // ---- everything that does not depend on the accumulator: done before the wait ----
@@ -686,6 +686,11 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   else if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 3 && a.rb_layer == 0)
     kernel = f16 ? mlp_chain_tc_kernel<true, 4, 3, true> : mlp_chain_tc_kernel<false, 4, 3, true>;
   else
+#ifndef NVSR_TC_MIP_ROLLED
+  if (m->n_layers == 6)  // the mip decoder (FlexibleNeRFModel): run-time layer shapes, layer loop unrolled
+    kernel = f16 ? mlp_chain_tc_kernel<true, -6, 0, false> : mlp_chain_tc_kernel<false, -6, 0, false>;
+  else
+#endif
     kernel = f16 ? mlp_chain_tc_kernel<true, 0, 0, false> : mlp_chain_tc_kernel<false, 0, 0, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
