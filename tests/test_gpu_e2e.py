@@ -153,6 +153,50 @@ def test_trace_indices_bit_exact_given_same_weights():
     assert torch.equal(tr["z_fine"].cpu(), zf)
 
 
+@pytest.mark.parametrize("channels,res", [(32, 96), (16, 40), (64, 64)])
+def test_other_plane_shapes_vs_oracle(channels, res):
+    """Plane channel counts other than the reference default (48) take the run-time-chunk-count gather and other
+    decoder input widths (K = C and 3C); ragged ray / sample counts (37 x 37 rays, 24 + 40 samples) on top."""
+    import copy
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=res, view_res=12, channels=channels, seed=3, device=DEV)
+    pose, focal = scene.blender_camera(37)
+    opt, scfg = scene.render_options(24, 40), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(37, 37, focal, pose.to(DEV))
+        batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+        tc = {}
+        ref = O.run_one_iter_of_nerf(37, 37, focal, copy.deepcopy(mc).cpu(), copy.deepcopy(mf).cpu(), batch.cpu(), opt,
+                                     sid, "validation", scene_config=scfg, trace=tc)
+        nvsr_b200.set_precision("fp32")
+        tg = {}
+        out = nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg,
+                                             trace=tg)
+        flips = _flip_rays(tg, tc, 40, torch.linspace(0.0, 1.0, 40))
+        assert torch.equal(tg["z_coarse"].cpu(), tc["z_coarse"])
+        for k, v in _errors(out, ref, ~flips).items():
+            if "coarse" in k:      # coarse maps: the 1e-3 contract everywhere
+                assert v <= FP32_TOL, (channels, k, v)
+        # fine maps: free-running resampling is ill-conditioned in the reference itself (see
+        # test_full_size_subset_vs_oracle): 1e-3 on >= 99 % of the rays, small mean, bounded max
+        for k, a, b in zip(NAMES, out[:6], ref[:6]):
+            if "fine" in k and "disp" not in k:
+                d = (a.cpu() - b).abs()
+                frac = float((d <= FP32_TOL).float().mean())
+                assert frac >= 0.99 and float(d.mean()) <= 5e-5 and float(d.max()) <= 2e-2, (channels, k, frac, float(d.mean()), float(d.max()))
+        for prec in ("fp16", "bf16"):
+            nvsr_b200.set_precision(prec)
+            if channels > 48:
+                # 3C = 192 input columns: resident rgb weights + the two ring buffers exceed the 227 KB of shared
+                # memory of the tensor-core decoder — refused loudly (fp32 parity mode above still serves it)
+                with pytest.raises(nvsr_b200.NvsrError, match="resource"):
+                    nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
+                torch.cuda.synchronize()
+                continue
+            o16 = nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
+            _check16(f"C={channels} {prec}", _stats16(o16, ref), TOL16_SMALL[prec])
+    nvsr_b200.set_precision("fp16")
+
+
 @pytest.fixture(scope="module")
 def big_scene():
     mc, mf, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=0, device=DEV)
