@@ -256,6 +256,25 @@ def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device
     return coarse, fine, sid
 
 
+def add_synthetic_scene(coarse, fine, scene_id, plane_res=200, view_res=32, seed=1, plane_std=0.5):
+    """Another scene's planes for an existing decoder pair (BASELINE config 5: several scenes share one decoder —
+    in the reference `planes_` is one ParameterDict keyed by scene id, models.py:545-550, and `set_cur_scene_id`
+    selects the scene per frame).  Same plane statistics as make_synthetic_scene, different seed."""
+    g = torch.Generator().manual_seed(seed)
+    channels = coarse.num_plane_channels
+    dev = next(coarse.parameters()).device
+    for d in range(4):
+        r = plane_res if d < 3 else view_res
+        low = nn.functional.interpolate(torch.randn(1, channels, max(r // 8, 2), max(r // 8, 2), generator=g), size=(r, r),
+                                        mode="bicubic", align_corners=True)
+        p = nn.Parameter((plane_std * (0.9 * low + 0.45 * torch.randn(1, channels, r, r, generator=g))).to(dev))
+        coarse.planes_[get_plane_name(scene_id, d)] = p      # fine shares the same ParameterDict object
+    box = torch.tensor(DEFAULT_BOX, dtype=torch.float64)
+    for m in (coarse, fine):
+        m.box_coords[scene_id] = box
+    return scene_id
+
+
 def make_mip_models(seed=0, device="cpu", density_std=10.0, density_shift=-10.0):
     torch.manual_seed(seed)
     coarse, fine = MipMLP(), MipMLP()

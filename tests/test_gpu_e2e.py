@@ -197,6 +197,37 @@ def test_other_plane_shapes_vs_oracle(channels, res):
     nvsr_b200.set_precision("fp16")
 
 
+def test_multi_scene_shared_decoder():
+    """BASELINE config 5: several scenes' planes behind ONE decoder pair (the reference keys `planes_` by scene id
+    and switches with set_cur_scene_id per frame).  Every scene matches the oracle, and switching back and forth
+    serves each scene its own cached planes (bit-identical re-render)."""
+    import copy
+    mc, mf, s0 = scene.make_synthetic_scene(plane_res=48, view_res=12, seed=4, device=DEV, scene_id="a_DS2_PlRes48_12")
+    s1 = scene.add_synthetic_scene(mc, mf, "b_DS2_PlRes48_12", plane_res=48, view_res=12, seed=41)
+    s2 = scene.add_synthetic_scene(mc, mf, "c_DS2_PlRes64_12", plane_res=64, view_res=12, seed=42)
+    pose, focal = scene.blender_camera(24)
+    opt, scfg = scene.render_options(32, 48), scene.scene_cfg()
+    nvsr_b200.set_precision("fp32")
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(24, 24, focal, pose.to(DEV))
+        batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+        mc_c, mf_c = copy.deepcopy(mc).cpu(), copy.deepcopy(mf).cpu()
+        first = {}
+        for sid in (s0, s1, s2, s1, s0, s2):
+            out = nvsr_b200.run_one_iter_of_nerf(24, 24, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
+            if sid in first:
+                for a, b in zip(out[:6], first[sid][:6]):
+                    assert torch.equal(torch.nan_to_num(a, 7.0), torch.nan_to_num(b, 7.0)), sid
+                continue
+            first[sid] = out
+            ref = O.run_one_iter_of_nerf(24, 24, focal, mc_c, mf_c, batch.cpu(), opt, sid, "validation", scene_config=scfg)
+            for k, a, b in zip(NAMES, out[:6], ref[:6]):
+                if "coarse" in k and "disp" not in k:
+                    H.assert_close(a, b, FP32_TOL, what=f"{sid} {k}")
+        assert not torch.equal(first[s0][0], first[s1][0]) and not torch.equal(first[s1][0], first[s2][0])
+    nvsr_b200.set_precision("fp16")
+
+
 @pytest.fixture(scope="module")
 def big_scene():
     mc, mf, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=0, device=DEV)
