@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--ray-chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense", action="store_true",
+                    help="evaluate the rgb decoder on every sample (default: only where sigma > 0, which is exact)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,6 +200,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     nvsr_b200.set_precision(args.precision)
+    sparse = (not args.dense) and args.precision != "fp32" and nvsr_b200.render._state["sparse_rgb"]
+    nvsr_b200.set_sparse_rgb(sparse)
     if args.ray_chunk:
         nvsr_b200.set_ray_chunk(args.ray_chunk)
     mc, mf, sid, pose, focal, opt, scfg = build_scene(dev)
@@ -277,16 +281,29 @@ def main():
             frame_device()
         barrier()
         prof, ops.PROFILE = ops.PROFILE, None
+        # companion number with the rgb decoder evaluated on EVERY sample (what the reference does), same frame
+        ms_dense = None
+        if sparse:
+            nvsr_b200.set_sparse_rgb(False)
+            for _ in range(2):
+                frame_device()
+            ms_dense = timed(frame_device, min(3, args.steps))
+            nvsr_b200.set_sparse_rgb(True)
     agg = {}
     for name, a, b, meta in prof:
         key = name
+        rows_done = meta.get("rows", 0)
+        if meta.get("count") is not None:           # sparse launch: the rows it evaluated are counted on the device
+            rows_done = int(meta["count"].item())
         if name == "nvsr_mlp_chain":
-            key = "mlp_density" if meta["flops"] / max(meta["rows"], 1) < 120000 else "mlp_rgb"
-        d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=0, flops=0))
+            key = "mlp_density" if meta["flops_per_row"] < 120000 else "mlp_rgb"
+        d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=0, flops=0, rows=0, rows_cap=0))
         d["ms"] += a.elapsed_time(b)
         d["n"] += 1
-        d["bytes"] += meta.get("bytes", 0)
-        d["flops"] += meta.get("flops", 0)
+        d["rows"] += rows_done
+        d["rows_cap"] += meta.get("rows", rows_done)
+        d["bytes"] += rows_done * meta["bytes_per_row"] if "bytes_per_row" in meta else meta.get("bytes", 0)
+        d["flops"] += rows_done * meta["flops_per_row"] if "flops_per_row" in meta else meta.get("flops", 0)
     pk = peaks()
     total_ms = sum(d["ms"] for d in agg.values())
     kernels = {}
@@ -299,6 +316,7 @@ def main():
             e["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             e["frac_hbm_peak"] = e["gbs"] / pk["hbm"]
         kernels[k] = e
+    rgb_frac = (agg["mlp_rgb"]["rows"] / max(agg["mlp_rgb"]["rows_cap"], 1)) if "mlp_rgb" in agg else None
     mlp = [agg[k] for k in ("mlp_rgb", "mlp_density") if k in agg]
     mlp_ms = sum(d["ms"] for d in mlp)
     mlp_fl = sum(d["flops"] for d in mlp)
@@ -326,6 +344,8 @@ def main():
         line = {
             "metric": "rays/s (800x800 render, 64 coarse + 128 fine samples/ray)",
             "value": rays / (ms_dev * 1e-3), "unit": "rays/s",
+            # nominal decoder evaluations of the reference per second: rays/s x (Nc + (Nc + Nf)); with sparse_rgb the
+            # rgb chain is evaluated only on `rgb_rows_evaluated` of them (the others have weight exactly 0)
             "samples_per_s": rays * EVALS_PER_RAY / (ms_dev * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -334,9 +354,13 @@ def main():
             "config": {"workload": "cfg2_800x800_64+128_planes200", "rays_per_step": rays, "planes": "3x48x200^2 + 48x32^2",
                        "decoder": "48->128x4->1 + 192->128x4->3 (coarse+fine)", "sharding": f"{world} row bands",
                        "ray_chunk": nvsr_b200.render._state["ray_chunk"],
+                       "sparse_rgb": bool(sparse), "rgb_rows_evaluated": rgb_frac,
                        "l2": "256 MiB buffer rewritten before every step; per-step intermediates (>60 GB) exceed L2"},
             "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(host_rays.numel() * 4), "d2h_bytes_per_step": int(n_local * 10 * 4)},
+            "dense": None if ms_dense is None else {
+                "ms_per_step": ms_dense, "value": rays / (ms_dense * 1e-3), "unit": "rays/s",
+                "note": "same frame with the rgb decoder evaluated on every sample (sparse_rgb off); outputs are bit-identical"},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": roofline,

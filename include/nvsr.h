@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NVSR_ABI_VERSION 1
+#define NVSR_ABI_VERSION 2
 
 #define NVSR_OK 0
 #define NVSR_ERR_INVALID_ARG (-1)
@@ -128,7 +128,9 @@ typedef struct nvsr_sampler {
 #define NVSR_FEAT_TILE_BF16 1    /* featP [tiles][3C/8][128][8] bf16, featM [tiles][C/8][128][8]; BLOCKED */
 #define NVSR_FEAT_TILE_F16 2     /* same tile image with fp16 elements (planes must be NVSR_F16)   */
 
-/* Row-major output: rows = n_rays*n_samples, row = ray*S + s.  Tile-image outputs use the BLOCKED
+/* feat_p may be NULL for the tile-image layouts (density features only: the sparse colour path gathers the
+ * 3-plane features of the contributing rows afterwards, nvsr_sample_gather_rows).
+ * Row-major output: rows = n_rays*n_samples, row = ray*S + s.  Tile-image outputs use the BLOCKED
  * row order and must be sized for nvsr_rows_padded(n,S,BLOCKED)/128 tiles; padding rows are written
  * as zeros.  z_out [n,S] (always ray-major) may be NULL. */
 int32_t nvsr_sample_gather(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes,
@@ -148,6 +150,22 @@ int32_t nvsr_viewdir_gather(const float* viewdirs, int64_t n_rays, const float* 
  * models.py:186 / layers_dir[0], models.py:68) */
 int32_t nvsr_row_bias(const float* vin, int64_t n_rays, int32_t k, const float* w, int32_t ldw,
                       const float* b, int32_t n_out, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse colour path (exact): a sample with sigma (+ noise) <= 0 has alpha = 1 - exp(-relu(sigma) * dist) = 0, so
+ * its weight alpha * T is exactly 0 and its colour cannot reach rgb_map / depth / acc
+ * (volume_rendering_utils.py:29-44).  After the density chain, nvsr_keep_rows lists the BLOCKED row ids of the
+ * samples that can contribute (sigma + noise > 0, or NaN) — `count` must be zeroed by the caller, the order of the
+ * list is unspecified — and nvsr_sample_gather_rows writes the 3-plane features (featP) of exactly those rows into
+ * densely packed tile images in list order (entry i -> tile i/128, row i%128; the last tile is zero-padded),
+ * ready for nvsr_mlp_chain with row_ids/row_count.  sigma: channel 3 of the planar raw buffer (BLOCKED order).
+ * z_in of the sampler is required ([n,S] depths of the pass).  max_rows bounds *count (buffer capacity).
+ */
+int32_t nvsr_keep_rows(const float* sigma, const float* noise, int64_t n_rays, int32_t n_samples,
+                       int32_t* keep_rows, int32_t* count, void* stream);
+int32_t nvsr_sample_gather_rows(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes, int32_t feat_layout,
+                                const int32_t* keep_rows, const int32_t* count, int64_t max_rows, void* feat_p,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a6 / a6'  decoder MLP as a chain of dense layers   models.py:168-197,393-421 (planes decoder),
@@ -176,6 +194,11 @@ typedef struct nvsr_mlp {
   float* raw;            /* planar [4][raw_stride], same row order as the input */
   int64_t raw_stride;
   int32_t row_order;     /* NVSR_ROWS_* of the input rows (tcgen05 path; the fp32 path is RAY_MAJOR) */
+  /* sparse evaluation (tcgen05 path, NVSR_ROWS_BLOCKED): input row i is the BLOCKED row row_ids[i] of the chunk —
+   * the per-ray bias and the raw output position follow row_ids; *row_count (device) rows are evaluated, `rows`
+   * is then the capacity of the input buffer.  NULL/NULL: every row is evaluated in place. */
+  const int32_t* row_ids;
+  const int32_t* row_count;
 } nvsr_mlp_t;
 
 int32_t nvsr_mlp_chain(const nvsr_mlp_t* mlp, void* stream);

@@ -13,7 +13,7 @@ from . import _lib, build, ops, render, scene, sharding  # noqa: F401
 from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32, NvsrError  # noqa: F401
 from .ops import (get_ray_bundle, sample_pdf, volume_render_radiance_field)  # noqa: F401
 from .render import (eval_nerf, get_precision, install, render_frame, run_one_iter_of_nerf, set_precision,  # noqa: F401
-                     set_ray_chunk, uninstall)
+                     set_ray_chunk, set_sparse_rgb, uninstall)
 
 
 class IntegratedPositionalEncoding:

@@ -76,6 +76,8 @@ class Mlp(C.Structure):
         ("raw", c_p),
         ("raw_stride", c_i64),
         ("row_order", c_i32),
+        ("row_ids", c_p),
+        ("row_count", c_p),
     ]
 
 
@@ -115,6 +117,8 @@ SIGNATURES = {
     "nvsr_pack_plane": (c_i32, [c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),
     "nvsr_pack_weight16": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),
     "nvsr_sample_gather": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_i32, c_p, c_p, c_p, c_p]),
+    "nvsr_keep_rows": (c_i32, [c_p, c_p, c_i64, c_i32, c_p, c_p, c_p]),
+    "nvsr_sample_gather_rows": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_i32, c_p, c_p, c_i64, c_p, c_p]),
     "nvsr_viewdir_gather": (c_i32, [c_p, c_i64, c_p, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p]),
     "nvsr_row_bias": (c_i32, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p]),
     "nvsr_mlp_chain": (c_i32, [C.POINTER(Mlp), c_p]),
@@ -156,7 +160,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.nvsr_abi_version() != 1:
+    if lib.nvsr_abi_version() != 2:
         raise NvsrError("libnvsr_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -297,8 +297,14 @@ composite_kernel(CompositeArgs a, int warps_per_cta) {
             zc[j] = zz[j];
           }
           dist = __fmul_rn(dist, dnorm);
-          cr[j] = sigmoid_fast(cur.c[j][0]), cg[j] = sigmoid_fast(cur.c[j][1]), cb[j] = sigmoid_fast(cur.c[j][2]);
           if (a.noise) sig = __fadd_rn(sig, __ldg(a.noise + ray * S + s));
+          // sigma + noise <= 0: relu gives 0, alpha = 1 - exp(-0) = 0 and the weight alpha*T is exactly 0, so the
+          // sample's colour contributes exactly 0 whatever it is (a finite sigmoid in the reference).  Its colour
+          // channels are not touched here: the sparse decoder path does not even evaluate them (nvsr_keep_rows).
+          const bool lit = !(sig <= 0.f);
+          cr[j] = lit ? sigmoid_fast(cur.c[j][0]) : 0.f;
+          cg[j] = lit ? sigmoid_fast(cur.c[j][1]) : 0.f;
+          cb[j] = lit ? sigmoid_fast(cur.c[j][2]) : 0.f;
           sig = fmaxf(sig, 0.f);
           alpha[j] = __fsub_rn(1.f, expf(__fmul_rn(-sig, dist)));
           tt[j] = (double)__fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);

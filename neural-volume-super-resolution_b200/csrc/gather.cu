@@ -260,12 +260,127 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
         uint4 o;
         o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
         o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
-        st_stream16(gP + (uint32_t)(d * CH + c) * 2048u, o);
+        if (featP) st_stream16(gP + (uint32_t)(d * CH + c) * 2048u, o);  // featP == NULL: density features only
       }
       uint4 o;
       o.x = pack16_pair<F16>(mul_f32x2(mean[0], third)), o.y = pack16_pair<F16>(mul_f32x2(mean[1], third));
       o.z = pack16_pair<F16>(mul_f32x2(mean[2], third)), o.w = pack16_pair<F16>(mul_f32x2(mean[3], third));
       st_stream16(gM + (uint32_t)c * 2048u, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse colour path.  A sample whose density (+ noise) is <= 0 has alpha = 0 and weight exactly 0: its colour
+// never reaches any output (volume_rendering_utils.py:29-44), so the rgb decoder need not see it.  After the
+// density chain, keep_rows_kernel lists the rows that CAN contribute; gather_rows_16 then writes the 3-plane
+// features of exactly those rows, densely packed into tile images in list order, for the rgb decoder.
+// Rows are identified by their BLOCKED row id (tile * 128 + row-in-tile); the order of the list is irrelevant to
+// the result (rows are independent), so it is built with warp-aggregated atomics.
+__global__ void __launch_bounds__(256)
+keep_rows_kernel(const float* __restrict__ sigma, const float* __restrict__ noise, int64_t n_rays, int S, int64_t n_tiles,
+                 int32_t* __restrict__ keep, int32_t* __restrict__ count) {
+  __shared__ int warp_cnt[8];
+  __shared__ int block_base;
+  const int TS = tiles_per_block(S);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_rows = n_tiles * kTileRows;
+  // 1024 rows per block pass (4 per thread): one atomic on the global counter per pass
+  for (int64_t base = (int64_t)blockIdx.x * 1024; base < n_rows; base += (int64_t)gridDim.x * 1024) {
+    unsigned m[4];
+    bool k[4];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t row = base + j * 256 + threadIdx.x;
+      k[j] = false;
+      if (row < n_rows) {
+        int64_t ray;
+        int s;
+        blocked_decode(row / kTileRows, (int)(row % kTileRows), TS, &ray, &s);
+        if (ray < n_rays && s < S) {
+          float v = __ldg(sigma + row);
+          if (noise) v = __fadd_rn(v, __ldg(noise + ray * S + s));
+          k[j] = !(v <= 0.f);  // NaN is kept: it must reach the maps as NaN
+        }
+      }
+      m[j] = __ballot_sync(0xffffffffu, k[j]);
+      mine += __popc(m[j]);
+    }
+    if (lane == 0) warp_cnt[wid] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        int c = warp_cnt[w];
+        warp_cnt[w] = tot;  // exclusive prefix
+        tot += c;
+      }
+      block_base = tot ? atomicAdd(count, tot) : 0;
+    }
+    __syncthreads();
+    int at = block_base + warp_cnt[wid];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (k[j]) keep[at + __popc(m[j] & ((1u << lane) - 1u))] = (int32_t)(base + j * 256 + threadIdx.x);
+      at += __popc(m[j]);
+    }
+    __syncthreads();  // warp_cnt / block_base are reused by the next pass
+  }
+}
+
+// featP of the listed rows, packed densely: list entry i -> tile image i / 128, row i % 128.  One thread per
+// entry, same arithmetic per row as gather_tile_16.  Entries beyond *count (up to a whole tile) are zero rows.
+template <bool F16, int CH_T>
+__global__ void __launch_bounds__(kGatherThreads, NVSR_GATHER_MINB)
+gather_rows_16(SamplerArgs a, PlaneArgs p, const int32_t* __restrict__ keep, const int32_t* __restrict__ count,
+               uint8_t* __restrict__ featP) {
+  const int CH = CH_T > 0 ? CH_T : p.C / 8;
+  const uint32_t p_bytes = 3u * CH * 2048u;
+  const int TS = tiles_per_block(a.S);
+  const int r = threadIdx.x;
+  const XPair* const pl0 = reinterpret_cast<const XPair*>(p.plane[0]);
+  const XPair* const pl1 = reinterpret_cast<const XPair*>(p.plane[1]);
+  const XPair* const pl2 = reinterpret_cast<const XPair*>(p.plane[2]);
+  const int64_t n = *count;
+  const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * kTileRows + r;
+    Foot f[3];
+    if (i < n) {
+      const int64_t row = keep[i];
+      int64_t ray;
+      int s;
+      blocked_decode(row / kTileRows, (int)(row % kTileRows), TS, &ray, &s);
+      const float z = sample_depth(a, ray, s);
+      Bilin b[3];
+      sample_corners(a, p, ray, z, b);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) f[d] = make_foot(b[d], p.rw[d], CH);
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) f[d] = Foot{0u, 0u, 0.f, 0.f, 0.f, 0.f};
+    }
+    uint8_t* gP = featP + tile * (int64_t)p_bytes + (uint32_t)r * 16u;
+    const XPair* rowT[3] = {pl0 + f[0].top, pl1 + f[1].top, pl2 + f[2].top};
+    const XPair* rowB[3] = {pl0 + f[0].bot, pl1 + f[1].bot, pl2 + f[2].bot};
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const XPair vt = ldg256(rowT[d] + c * p.rw[d]);
+        const XPair vb = ldg256(rowB[d] + c * p.rw[d]);
+        unsigned long long acc[4];
+        texel_fma<F16, true>(acc, vt.l, f[d].w00);
+        texel_fma<F16, false>(acc, vt.r, f[d].w01);
+        texel_fma<F16, false>(acc, vb.l, f[d].w10);
+        texel_fma<F16, false>(acc, vb.r, f[d].w11);
+        uint4 o;
+        o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
+        o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
+        st_stream16(gP + (uint32_t)(d * CH + c) * 2048u, o);
+      }
     }
   }
 }
@@ -276,7 +391,7 @@ using namespace nvsr;
 
 extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes_t* pl, int32_t feat_layout,
                                       void* feat_p, void* feat_m, float* z_out, void* stream) {
-  NVSR_CHECK_ARG(s && pl && feat_p && feat_m);
+  NVSR_CHECK_ARG(s && pl && feat_m && (feat_p || feat_layout != NVSR_FEAT_ROWMAJOR_F32));
   NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd);
   NVSR_CHECK_ARG(s->z_in || s->t_vals);
   NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64);
@@ -284,7 +399,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     NVSR_CHECK_ARG(pl->plane[d] && pl->rh[d] > 0 && pl->rw[d] > 0);
     if ((reinterpret_cast<uintptr_t>(pl->plane[d]) & (is_16bit(pl->dtype) ? 31u : 15u)) != 0) return NVSR_ERR_ALIGNMENT;
   }
-  if (!aligned16(feat_p) || !aligned16(feat_m)) return NVSR_ERR_ALIGNMENT;
+  if ((feat_p && !aligned16(feat_p)) || !aligned16(feat_m)) return NVSR_ERR_ALIGNMENT;
   if (s->n_rays == 0) return NVSR_OK;
 
   SamplerArgs a{s->n_rays, s->n_samples, s->ro, s->rd, s->near_, s->far_, s->lindisp, s->t_vals, s->t_rand, s->z_in};
@@ -319,4 +434,49 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     NVSR_RETURN_LAST_ERROR();
   }
   return NVSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int32_t nvsr_keep_rows(const float* sigma, const float* noise, int64_t n_rays, int32_t n_samples,
+                                  int32_t* keep_rows, int32_t* count, void* stream) {
+  NVSR_CHECK_ARG(sigma && keep_rows && count && n_rays >= 0 && n_samples > 0);
+  if (n_rays == 0) return NVSR_OK;
+  const int64_t n_tiles = rows_padded(n_rays, n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
+  NVSR_CHECK_ARG(n_tiles * kTileRows < ((int64_t)1 << 31));
+  int64_t blocks = ceil_div64(n_tiles * kTileRows, 1024);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  keep_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sigma, noise, n_rays, n_samples, n_tiles, keep_rows, count);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_sample_gather_rows(const nvsr_sampler_t* s, const nvsr_planes_t* pl, int32_t feat_layout,
+                                           const int32_t* keep_rows, const int32_t* count, int64_t max_rows,
+                                           void* feat_p, void* stream) {
+  NVSR_CHECK_ARG(s && pl && keep_rows && count && feat_p && max_rows >= 0);
+  NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd && s->z_in);
+  NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64);
+  NVSR_CHECK_ARG(feat_layout == NVSR_FEAT_TILE_BF16 || feat_layout == NVSR_FEAT_TILE_F16);
+  const bool f16 = feat_layout == NVSR_FEAT_TILE_F16;
+  if (pl->dtype != (f16 ? NVSR_F16 : NVSR_BF16)) return NVSR_ERR_UNSUPPORTED;
+  for (int d = 0; d < 3; ++d) {
+    NVSR_CHECK_ARG(pl->plane[d] && pl->rh[d] > 0 && pl->rw[d] > 0);
+    if ((reinterpret_cast<uintptr_t>(pl->plane[d]) & 31u) != 0) return NVSR_ERR_ALIGNMENT;
+  }
+  if (!aligned16(feat_p)) return NVSR_ERR_ALIGNMENT;
+  if (s->n_rays == 0 || max_rows == 0) return NVSR_OK;
+  SamplerArgs a{s->n_rays, s->n_samples, s->ro, s->rd, s->near_, s->far_, s->lindisp, s->t_vals, s->t_rand, s->z_in};
+  PlaneArgs p;
+  for (int d = 0; d < 3; ++d) {
+    p.plane[d] = pl->plane[d], p.rh[d] = pl->rh[d], p.rw[d] = pl->rw[d];
+    p.lo[d] = pl->box_lo[d], p.rng[d] = pl->box_rng[d];
+    for (int j = 0; j < 6; ++j) p.proj[d][j] = pl->proj[d][j];
+  }
+  p.C = pl->channels;
+  const bool c48 = pl->channels == 48;
+  auto kernel = f16 ? (c48 ? gather_rows_16<true, 6> : gather_rows_16<true, 0>)
+                    : (c48 ? gather_rows_16<false, 6> : gather_rows_16<false, 0>);
+  int64_t grid = (int64_t)kNumSMs * NVSR_GATHER_MINB * 4;   // grid-stride over the tiles *count turns out to need
+  const int64_t max_tiles = ceil_div64(max_rows, kTileRows);
+  if (grid > max_tiles) grid = max_tiles;
+  kernel<<<(unsigned)grid, kGatherThreads, 0, (cudaStream_t)stream>>>(a, p, keep_rows, count, (uint8_t*)feat_p);
+  NVSR_RETURN_LAST_ERROR();
 }

@@ -62,6 +62,8 @@ struct TcArgs {
   int64_t n_rays;
   float* raw;
   int64_t raw_stride;
+  const int32_t* row_ids;    // sparse mode: list entry i (input row i) is BLOCKED row row_ids[i] of the frame chunk
+  const int32_t* row_count;  // sparse mode: number of list entries (device memory)
   int rb_layer;           // layer with a per-ray bias (-1: none)
   int rb_staged;          // 1: the producer stages the tile's bias rows in smem (BLOCKED order)
   // smem carve-up (byte offsets from the 1024-aligned base)
@@ -324,7 +326,7 @@ __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, cons
 // LC > 0: "uniform" chain known at compile time — LC layers, all 128 wide with ReLU, one head of HN
 // rows on the last layer, per-ray bias on layer 0 iff RB0 (staged rows, BLOCKED order).  Both decoders
 // of the tri-plane model are of this shape (LC = 4).  LC == 0: generic chain described at run time.
-template <bool F16, int LC, int HN, bool RB0>
+template <bool F16, int LC, int HN, int RB0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool kFixed = LC > 0;
@@ -338,8 +340,15 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = kFixed ? LC : (LC < 0 ? -LC : a.n_layers);  // LC < 0: generic chain of -LC layers, loop unrolled
   const int64_t G = gridDim.x;
+  // RB0 (fixed chains): 0 = no per-ray bias, 1 = layer-0 bias rows staged per tile (dense BLOCKED order),
+  // 2 = layer-0 bias read per row from global memory (sparse row list)
   const int rb_layer = kFixed ? (RB0 ? 0 : -1) : a.rb_layer;
-  const bool rb_staged = kFixed ? RB0 : (a.rb_staged != 0);
+  const bool rb_staged = kFixed ? (RB0 == 1) : (a.rb_staged != 0);
+  int64_t rows = a.rows, n_tiles = a.n_tiles;
+  if (a.row_count) {  // sparse mode: the list length is known on the device only
+    rows = *a.row_count;
+    n_tiles = (rows + kTileRows - 1) / kTileRows;
+  }
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
@@ -496,7 +505,13 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       }
       const TcLayer& ly = a.layer[layer];
       int64_t row = tile * kTileRows + r;
-      int64_t ray = a.rows < 0x7fffffff ? (int64_t)((uint32_t)row / (uint32_t)a.samples_per_ray) : row / a.samples_per_ray;
+      int64_t ray;
+      if (a.row_ids) {  // sparse list: the entry names a BLOCKED row of the chunk -> its ray
+        const uint32_t rid = row < rows ? (uint32_t)__ldg(a.row_ids + row) : 0u;
+        ray = (int64_t)((rid >> 7) / (uint32_t)a.tiles_per_blk) * kBlkRays + (rid & (kBlkRays - 1));
+      } else {
+        ray = rows < 0x7fffffff ? (int64_t)((uint32_t)row / (uint32_t)a.samples_per_ray) : row / a.samples_per_ray;
+      }
       if (ray >= a.n_rays) ray = a.n_rays - 1;
       *mode = 2;
       return ly.row_bias + ray * ly.n + col0;
@@ -511,7 +526,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         bulk_g2s(smem + ly.w_off, ly.w, (uint32_t)(ly.k * ly.n * 2), &bars[BAR_W]);
       }
     }
-    if (first < a.n_tiles) {
+    if (first < n_tiles) {
       if (lane == 0) issue_tile_loads(s, first, wi);
       if (rb_layer == 0 && rb_staged) {
         mbar_wait(bar_rb_full, ph_rb);
@@ -528,9 +543,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 
     for (uint32_t use = 0;; ++use) {
       const int64_t tile = blockIdx.x + (int64_t)(2 * use + s) * G;
-      if (tile >= a.n_tiles) break;
+      if (tile >= n_tiles) break;
       const int64_t next_tile = tile + 2 * G;
-      const bool next_valid = next_tile < a.n_tiles;
+      const bool next_valid = next_tile < n_tiles;
       // fixed chains: the layer loop is fully unrolled, so `last`, the bias source and the next layer are
       // compile-time per copy (~100 instructions per layer and warp instead of ~350: the kernel is largely
       // issue-bound, measured -18% / -8% on the density / rgb chains); the generic chain stays rolled
@@ -588,8 +603,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           // combine the two column halves of a row: half 1 -> smem -> half 0
           if (half == 1) *reinterpret_cast<float4*>(hp) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
           named_bar_sync(1 + s * 4 + quad, 64);  // the two warps sharing this slot and lane quadrant
-          const int64_t row = tile * kTileRows + r;
-          if (half == 0 && row < a.rows) {
+          int64_t row = tile * kTileRows + r;
+          if (half == 0 && row < rows) {
+            if (a.row_ids) row = __ldg(a.row_ids + row);  // sparse list: write the row the entry stands for
             float4 o = *reinterpret_cast<const float4*>(hp);
             float hv[4] = {hacc[0] + o.x, hacc[1] + o.y, hacc[2] + o.z, hacc[3] + o.w};
 #pragma unroll
@@ -651,7 +667,10 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   a.in_off[0] = off, off += in_bytes;
   a.in_off[1] = off, off += in_bytes;
   // per-ray bias rows are staged through smem when the 8 rays of a tile are consecutive (BLOCKED order)
-  a.rb_staged = (a.rb_layer == 0 && m->row_order == NVSR_ROWS_BLOCKED) ? 1 : 0;
+  const bool sparse = m->row_ids != nullptr;
+  if (sparse && (!m->row_count || m->row_order != NVSR_ROWS_BLOCKED)) return NVSR_ERR_INVALID_ARG;
+  a.row_ids = m->row_ids, a.row_count = sparse ? m->row_count : nullptr;
+  a.rb_staged = (a.rb_layer == 0 && m->row_order == NVSR_ROWS_BLOCKED && !sparse) ? 1 : 0;
   a.rb_off[0] = a.rb_off[1] = off;
   if (a.rb_staged) {
     a.rb_off[1] = off + kRbRowsMax * kRbPitch * 4u;
@@ -672,7 +691,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   a.samples_per_ray = m->samples_per_ray > 0 ? m->samples_per_ray : 1;
   a.row_order = m->row_order;
   a.tiles_per_blk = tiles_per_block(a.samples_per_ray);
-  if (a.row_order == NVSR_ROWS_BLOCKED && (m->rows % kTileRows) != 0) return NVSR_ERR_INVALID_ARG;
+  if (a.row_order == NVSR_ROWS_BLOCKED && !sparse && (m->rows % kTileRows) != 0) return NVSR_ERR_INVALID_ARG;
   a.n_rays = m->n_rays > 0 ? m->n_rays : 1;
   a.raw = m->raw;
   a.raw_stride = m->raw_stride;
@@ -682,16 +701,18 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   // compile-time specialisations: the two decoders of the tri-plane model
   const bool rb_ok = a.rb_layer < 0 || a.rb_staged;
   if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 1 && a.rb_layer < 0)
-    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 1, false> : mlp_chain_tc_kernel<false, 4, 1, false>;
+    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 1, 0> : mlp_chain_tc_kernel<false, 4, 1, 0>;
+  else if (uniform && m->n_layers == 4 && lastL.head_n == 3 && a.rb_layer == 0 && sparse)
+    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 3, 2> : mlp_chain_tc_kernel<false, 4, 3, 2>;
   else if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 3 && a.rb_layer == 0)
-    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 3, true> : mlp_chain_tc_kernel<false, 4, 3, true>;
+    kernel = f16 ? mlp_chain_tc_kernel<true, 4, 3, 1> : mlp_chain_tc_kernel<false, 4, 3, 1>;
   else
 #ifndef NVSR_TC_MIP_ROLLED
   if (m->n_layers == 6)  // the mip decoder (FlexibleNeRFModel): run-time layer shapes, layer loop unrolled
-    kernel = f16 ? mlp_chain_tc_kernel<true, -6, 0, false> : mlp_chain_tc_kernel<false, -6, 0, false>;
+    kernel = f16 ? mlp_chain_tc_kernel<true, -6, 0, 0> : mlp_chain_tc_kernel<false, -6, 0, 0>;
   else
 #endif
-    kernel = f16 ? mlp_chain_tc_kernel<true, 0, 0, false> : mlp_chain_tc_kernel<false, 0, 0, false>;
+    kernel = f16 ? mlp_chain_tc_kernel<true, 0, 0, 0> : mlp_chain_tc_kernel<false, 0, 0, 0>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
   int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;

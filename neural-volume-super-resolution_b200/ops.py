@@ -210,9 +210,11 @@ class PackedPlanes:
         return s
 
 
-def feature_buffers(n_rays, n_samples, channels, layout, device):
+def feature_buffers(n_rays, n_samples, channels, layout, device, density_only=False):
     """Allocate (featP, featM) for n_rays x n_samples points in the given layout."""
     rows = rows_padded(n_rays, n_samples, LAYOUT_ROWS[layout])
+    if density_only and layout != FEAT_ROWMAJOR_F32:
+        return (None, torch.empty((rows // TILE_ROWS, channels // 8, TILE_ROWS, 8), dtype=LAYOUT_DTYPE[layout], device=device))
     if layout == FEAT_ROWMAJOR_F32:
         return (torch.empty((rows, 3 * channels), dtype=torch.float32, device=device),
                 torch.empty((rows, channels), dtype=torch.float32, device=device))
@@ -223,10 +225,11 @@ def feature_buffers(n_rays, n_samples, channels, layout, device):
 
 
 def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_rand=None, lindisp=False,
-                  n_samples=None, out=None, want_z=True):
+                  n_samples=None, out=None, want_z=True, density_only=False):
     """Fused stratified sampler + tri-plane gather (train_utils.py:95-111 + models.py:381-391 xyz half).
 
-    Returns (featP, featM, z_vals[n,S] or None)."""
+    Returns (featP, featM, z_vals[n,S] or None).  `density_only` (tile layouts): only the mean features featM are
+    written (featP is None) — the sparse colour path gathers the 3-plane features of the contributing rows later."""
     lib = _lib.load()
     n = ro.shape[0]
     if z_in is not None:
@@ -237,7 +240,7 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
         t_vals = _f32c(t_vals)
     rows = n * S
     if out is None:
-        out = feature_buffers(n, S, packed.channels, layout, ro.device)
+        out = feature_buffers(n, S, packed.channels, layout, ro.device, density_only=density_only)
     feat_p, feat_m = out
     z_out = torch.empty((n, S), dtype=torch.float32, device=ro.device) if (want_z and z_in is None) else None
     s = _lib.Sampler()
@@ -252,9 +255,47 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
         st = _call("nvsr_sample_gather", lib.nvsr_sample_gather, C.byref(s), C.byref(pl), layout, _ptr(feat_p),
                    _ptr(feat_m), _ptr(z_out), _stream(),
                    # algorithmic HBM bytes: feature write 4C*e per row + z (4 B) + rays (24 B/ray)
-                   bytes=rows * (4 * packed.channels * (4 if layout == FEAT_ROWMAJOR_F32 else 2) + 4) + n * 24, rows=rows)
+                   bytes=rows * ((1 if feat_p is None else 4) * packed.channels * (4 if layout == FEAT_ROWMAJOR_F32 else 2) + 4)
+                   + n * 24, rows=rows)
     _lib.check(st, "nvsr_sample_gather")
     return feat_p, feat_m, (z_out if z_in is None else z_in)
+
+
+def keep_rows(raw, n_rays, n_samples, noise=None):
+    """Rows of a BLOCKED raw buffer that can contribute to the maps: sigma (+ noise) > 0 (or NaN) — every other
+    sample has alpha = 0 and weight exactly 0 (volume_rendering_utils.py:29-44).  Returns (row_ids int32
+    [rows_padded], count int32 [1]) on the device; the list order is unspecified."""
+    lib = _lib.load()
+    rows = rows_padded(n_rays, n_samples, ROWS_BLOCKED)
+    keep = torch.empty((rows,), dtype=torch.int32, device=raw.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=raw.device)
+    noise = None if noise is None else _f32c(noise)
+    with torch.cuda.device(raw.device):
+        st = _call("nvsr_keep_rows", lib.nvsr_keep_rows, _ptr(raw[3]), _ptr(noise), n_rays, n_samples, _ptr(keep),
+                   _ptr(count), _stream(), bytes=rows * 4, rows=rows)
+    _lib.check(st, "nvsr_keep_rows")
+    return keep, count
+
+
+def sample_gather_rows(ro, rd, packed, layout, z, keep, count, out=None):
+    """3-plane features (featP) of the listed rows only, densely packed in list order (nvsr_sample_gather_rows)."""
+    lib = _lib.load()
+    n, S = z.shape
+    max_rows = keep.numel()
+    if out is None:
+        out = torch.empty((max_rows // TILE_ROWS, 3 * packed.channels // 8, TILE_ROWS, 8), dtype=LAYOUT_DTYPE[layout],
+                          device=ro.device)
+    s = _lib.Sampler()
+    s.n_rays, s.n_samples = n, S
+    s.ro, s.rd = ro.data_ptr(), rd.data_ptr()
+    s.near_, s.far_, s.lindisp = 0.0, 1.0, 0
+    s.t_vals, s.t_rand, s.z_in = 0, 0, z.data_ptr()
+    pl = packed.cstruct()
+    with torch.cuda.device(ro.device):
+        st = _call("nvsr_sample_gather_rows", lib.nvsr_sample_gather_rows, C.byref(s), C.byref(pl), layout, _ptr(keep),
+                   _ptr(count), max_rows, _ptr(out), _stream(), count=count, bytes_per_row=3 * packed.channels * 2)
+    _lib.check(st, "nvsr_sample_gather_rows")
+    return out
 
 
 def viewdir_gather(viewdirs, packed):
@@ -299,9 +340,12 @@ class ChainLayer:
         self.row_bias, self.head_w, self.head_b, self.head_ch = row_bias, head_w, head_b, head_ch
 
 
-def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, row_order=ROWS_RAY_MAJOR):
+def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, row_order=ROWS_RAY_MAJOR,
+              row_ids=None, row_count=None):
     """Evaluate one decoder chain (models.py:393-421 / :85-108) over `rows` rows into planar raw [4,stride].
-    `rows` counts the rows of the input buffer (padded rows included for ROWS_BLOCKED)."""
+    `rows` counts the rows of the input buffer (padded rows included for ROWS_BLOCKED).  With `row_ids` /
+    `row_count` (sparse colour path) input row i stands for BLOCKED row row_ids[i] and row_count[0] rows are
+    evaluated; `rows` is then the capacity of the input buffer."""
     lib = _lib.load()
     m = _lib.Mlp()
     m.precision = precision
@@ -325,13 +369,15 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, ro
     m.raw = raw.data_ptr()
     m.raw_stride = raw.stride(0)
     m.row_order = row_order
+    m.row_ids = 0 if row_ids is None else row_ids.data_ptr()
+    m.row_count = 0 if row_count is None else row_count.data_ptr()
     with torch.cuda.device(raw.device):
-        st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows,
-                   # true MACs x2 only (no padding): layers + heads
-                   flops=2 * rows * sum(ly.k * ly.n_out + (0 if ly.head_w is None else ly.head_w.shape[0] * ly.n_out)
-                                        for ly in layers),
-                   bytes=rows * (layers[0].k * (4 if precision == NVSR_F32 else 2) + 4 * sum(
-                       0 if ly.head_w is None else ly.head_w.shape[0] for ly in layers)))
+        # true MACs x2 only (no padding): layers + heads; `count` (sparse): rows actually evaluated, on the device
+        fpr = 2 * sum(ly.k * ly.n_out + (0 if ly.head_w is None else ly.head_w.shape[0] * ly.n_out) for ly in layers)
+        bpr = layers[0].k * (4 if precision == NVSR_F32 else 2) + 4 * sum(
+            0 if ly.head_w is None else ly.head_w.shape[0] for ly in layers)
+        st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows, count=row_count,
+                   flops_per_row=fpr, bytes_per_row=bpr, flops=rows * fpr, bytes=rows * bpr)
     _lib.check(st, "nvsr_mlp_chain")
     return raw
 

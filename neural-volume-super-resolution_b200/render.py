@@ -31,6 +31,10 @@ _state = {
     # 32 768-ray chunks).  NVSR_MAX_CHUNK_ROWS caps rays x samples of one chunk (64 Mi rows ~ 25 GB).
     "ray_chunk": int(os.environ.get("NVSR_RAY_CHUNK", "327680")),
     "max_chunk_rows": int(os.environ.get("NVSR_MAX_CHUNK_ROWS", str(64 << 20))),
+    # sparse colour path (16-bit modes): the rgb decoder is evaluated only for samples with sigma (+ noise) > 0 —
+    # every other sample has alpha = 0 and weight exactly 0, so its colour cannot reach any map (exact, not a
+    # tolerance: volume_rendering_utils.py:29-44).  NVSR_SPARSE_RGB=0 evaluates every sample.
+    "sparse_rgb": os.environ.get("NVSR_SPARSE_RGB", "1") != "0",
 }
 
 
@@ -47,6 +51,11 @@ def get_precision():
 
 def set_ray_chunk(n):
     _state["ray_chunk"] = int(n)
+
+
+def set_sparse_rgb(on):
+    """Evaluate the rgb decoder only where alpha can be non-zero (exact; default on) or everywhere."""
+    _state["sparse_rgb"] = bool(on)
 
 
 def _is_planes_model(m):
@@ -102,16 +111,24 @@ class _PlanesPass:
         self.planes = scene.pack_scene_planes(model, scene_id, precision)
         self.dec = scene.pack_planes_decoder(model, precision)
 
-    def radiance(self, ro, rd, vfeat, near, far, lindisp, S, t_vals=None, z_in=None, t_rand=None):
-        """-> (raw planar [4,stride], z [n,S])"""
+    def radiance(self, ro, rd, vfeat, near, far, lindisp, S, t_vals=None, z_in=None, t_rand=None, noise=None):
+        """-> (raw planar [4,stride], z [n,S]).  `noise`: what the compositing will add to sigma (decides which
+        samples can contribute on the sparse colour path)."""
         n = ro.shape[0]
         rows = ops.rows_padded(n, S, self.rows)
+        sparse = _state["sparse_rgb"] and self.precision != NVSR_F32
         fp, fm, z = ops.sample_gather(ro, rd, near, far, self.planes, self.layout, t_vals=t_vals, z_in=z_in,
-                                      t_rand=t_rand, lindisp=lindisp)
+                                      t_rand=t_rand, lindisp=lindisp, density_only=sparse)
         rbias = ops.row_bias(vfeat, self.dec.view_w, self.dec.view_b)
         raw = ops.raw_buffer(n, S, self.rows, ro.device)
         ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n, self.rows)
-        ops.mlp_chain(fp, self.dec.rgb_chain(rbias), rows, raw, self.precision, S, n, self.rows)
+        if sparse:
+            keep, count = ops.keep_rows(raw, n, S, noise)
+            fp = ops.sample_gather_rows(ro, rd, self.planes, self.layout, z, keep, count)
+            ops.mlp_chain(fp, self.dec.rgb_chain(rbias), rows, raw, self.precision, S, n, self.rows, row_ids=keep,
+                          row_count=count)
+        else:
+            ops.mlp_chain(fp, self.dec.rgb_chain(rbias), rows, raw, self.precision, S, n, self.rows)
         return raw, z
 
 
@@ -123,13 +140,13 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
     t_rand = randoms.get("t_rand") if cfg.perturb else None
     if cfg.perturb and t_rand is None:
         t_rand = torch.rand([n, Nc]).to(dev)  # CPU RNG like train_utils.py:108
-    raw, z = pc.radiance(ro, rd, vfeat, near, far, cfg.lindisp, Nc, t_vals=_t_vals(Nc, dev), t_rand=t_rand)
+    noise_c = _noise(randoms.get("noise_c"), cfg, n, Nc, dev)
+    raw, z = pc.radiance(ro, rd, vfeat, near, far, cfg.lindisp, Nc, t_vals=_t_vals(Nc, dev), t_rand=t_rand, noise=noise_c)
     u = None
     if Nf > 0:
         u = randoms.get("u")
         if u is None:
             u = _t_vals(Nf, dev) if cfg.perturb == 0.0 else torch.rand([n, Nf]).to(dev)
-    noise_c = _noise(randoms.get("noise_c"), cfg, n, Nc, dev)
     co = ops.composite(raw, z, rd, Nc, noise=noise_c, white_background=cfg.white_background, n_fine=Nf, u=u,
                        want_weights=trace is not None, want_inds=trace is not None, want_samples=trace is not None,
                        row_order=pc.rows)
@@ -141,8 +158,8 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
         zf = randoms["z_fine"] if "z_fine" in randoms else co["z_merged"]   # test hook: teacher-forced depths
         # fine model may read different (super-resolved) planes but shares the view-direction plane
         vfeat_f = vfeat if pf.planes.vplane is pc.planes.vplane else ops.viewdir_gather(vd, pf.planes)
-        raw_f, _ = pf.radiance(ro, rd, vfeat_f, near, far, cfg.lindisp, Nc + Nf, z_in=zf)
         noise_f = _noise(randoms.get("noise_f"), cfg, n, Nc + Nf, dev)
+        raw_f, _ = pf.radiance(ro, rd, vfeat_f, near, far, cfg.lindisp, Nc + Nf, z_in=zf, noise=noise_f)
         fo = ops.composite(raw_f, zf, rd, Nc + Nf, noise=noise_f, white_background=cfg.white_background,
                            row_order=pf.rows)
         if trace is not None:

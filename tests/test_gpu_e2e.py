@@ -228,6 +228,48 @@ def test_multi_scene_shared_decoder():
     nvsr_b200.set_precision("fp16")
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("kw", [dict(), dict(noise_std=1.0, white_background=True), dict(perturb=True)])
+def test_sparse_rgb_equals_dense(prec, kw):
+    """The sparse colour path (rgb decoder only where sigma + noise > 0) is EXACT: a sample with alpha = 0 has
+    weight 0 and cannot reach any map, so every output is bit-identical to evaluating every sample — with
+    density noise, white background and stratified jitter too, and for ragged ray counts."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=64, view_res=16, seed=6, device=DEV)
+    pose, focal = scene.blender_camera(45)
+    opt, scfg = scene.render_options(64, 128, **kw), scene.scene_cfg()
+    nvsr_b200.set_precision(prec)
+    n = 45 * 45 - 3
+    g = torch.Generator().manual_seed(8)
+    rnd = {"noise_c": torch.randn(n, 64, generator=g), "noise_f": torch.randn(n, 192, generator=g),
+           "t_rand": torch.rand(n, 64, generator=g), "u": torch.rand(n, 128, generator=g)}
+    if not kw.get("perturb"):
+        rnd.pop("t_rand"), rnd.pop("u")
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(45, 45, focal, pose.to(DEV))
+        batch = torch.stack([ro.reshape(-1, 3)[:n], rd.reshape(-1, 3)[:n]], 0)
+        outs = []
+        for sparse in (False, True):
+            nvsr_b200.set_sparse_rgb(sparse)
+            tr = {}
+            outs.append((nvsr_b200.run_one_iter_of_nerf(45, 45, focal, mc, mf, batch, opt, sid, "validation",
+                                                        scene_config=scfg, randoms=dict(rnd), trace=tr), tr))
+    nvsr_b200.set_sparse_rgb(True)
+    nvsr_b200.set_precision("fp16")
+    (dense, td), (sparse_o, ts) = outs
+    for k, a, b in zip(NAMES, dense[:6], sparse_o[:6]):
+        assert torch.equal(torch.nan_to_num(a, 7.0), torch.nan_to_num(b, 7.0)), (k, float((a - b).abs().max()))
+    for k in ("z_fine", "inds", "weights_coarse"):
+        assert torch.equal(td[k], ts[k]), k
+    sig = td["raw_fine"][..., 3]
+    if kw.get("noise_std"):
+        sig = sig + (rnd["noise_f"] * kw["noise_std"]).to(sig)     # what the compositing adds before the relu
+    lit = sig > 0                                            # where the colour matters it is the same number
+    assert torch.equal(td["raw_fine"][lit], ts["raw_fine"][lit])
+    frac = float(lit.float().mean())
+    print(f"sparse rgb [{prec} {kw}]: {100 * frac:.1f} % of the fine samples evaluated")
+    assert 0.01 < frac < 0.9
+
+
 @pytest.fixture(scope="module")
 def big_scene():
     mc, mf, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=0, device=DEV)
