@@ -519,7 +519,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 
     // prologue: weights (once per CTA) and the first tile's loads, then D_s <- its layer-0 bias
     const int64_t first = blockIdx.x + (int64_t)s * G;
-    if (warp == 0 && lane == 0) {
+    // (sparse mode: a CTA that the list leaves without a tile must not start copies it will never wait for)
+    if (warp == 0 && lane == 0 && blockIdx.x < n_tiles) {
       mbar_arrive_expect_tx(&bars[BAR_W], a.w_bytes_total);
       for (int l = 0; l < L; ++l) {
         const TcLayer& ly = a.layer[l];

@@ -270,6 +270,33 @@ def test_sparse_rgb_equals_dense(prec, kw):
     assert 0.01 < frac < 0.9
 
 
+@pytest.mark.parametrize("shift,n_rays", [(-200.0, 300), (-45.0, 2000), (30.0, 300)])
+def test_sparse_rgb_extremes(shift, n_rays):
+    """Sparse colour path at its extremes: no sample lit at all (empty list: acc = 0, disp = NaN), a handful lit
+    (fewer tiles than CTAs), every sample lit — always bit-identical to the dense evaluation."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=32, view_res=8, seed=9, device=DEV, density_shift=shift)
+    pose, focal = scene.blender_camera(48)
+    opt, scfg = scene.render_options(64, 128), scene.scene_cfg()
+    nvsr_b200.set_precision("fp16")
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(48, 48, focal, pose.to(DEV))
+        batch = torch.stack([ro.reshape(-1, 3)[:n_rays], rd.reshape(-1, 3)[:n_rays]], 0)
+        outs = []
+        for sparse in (False, True):
+            nvsr_b200.set_sparse_rgb(sparse)
+            tr = {}
+            outs.append((nvsr_b200.run_one_iter_of_nerf(48, 48, focal, mc, mf, batch, opt, sid, "validation",
+                                                        scene_config=scfg, trace=tr), tr))
+            torch.cuda.synchronize()
+    nvsr_b200.set_sparse_rgb(True)
+    (dense, td), (sp, _) = outs
+    for k, a, b in zip(NAMES, dense[:6], sp[:6]):
+        assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a, 7.0), torch.nan_to_num(b, 7.0)), k
+    lit = float((td["raw_fine"][..., 3] > 0).float().mean())
+    print(f"density shift {shift}: {100 * lit:.3f} % of the fine samples lit")
+    assert (lit == 0.0) if shift <= -200 else (lit > 0.9 if shift > 0 else 0.0 < lit < 0.05)
+
+
 @pytest.fixture(scope="module")
 def big_scene():
     mc, mf, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=0, device=DEV)
