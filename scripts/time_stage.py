@@ -56,3 +56,8 @@ if which in ("all", "gather"):
     tc = timed(lambda: ops.sample_gather(ro, rd, 2.0, 6.0, packed, ops.FEAT_TILE_F16, t_vals=t_vals, out=bc))
     tf = timed(lambda: ops.sample_gather(ro, rd, 2.0, 6.0, packed, ops.FEAT_TILE_F16, z_in=zf, out=bf))
     print(f"{tag:24s} gather    coarse {tc:7.1f} us   fine {tf:7.1f} us")
+    dc = ops.feature_buffers(n, Sc, 48, ops.FEAT_TILE_F16, dev, density_only=True)
+    df = ops.feature_buffers(n, Sf, 48, ops.FEAT_TILE_F16, dev, density_only=True)
+    tc = timed(lambda: ops.sample_gather(ro, rd, 2.0, 6.0, packed, ops.FEAT_TILE_F16, t_vals=t_vals, out=dc, density_only=True))
+    tf = timed(lambda: ops.sample_gather(ro, rd, 2.0, 6.0, packed, ops.FEAT_TILE_F16, z_in=zf, out=df, density_only=True))
+    print(f"{tag:24s} gather-M  coarse {tc:7.1f} us   fine {tf:7.1f} us   (density features only)")
