@@ -14,6 +14,13 @@ fine samples (hierarchical sample_pdf) -> rgb/disp/acc, coarse and fine.
           one NCCL all_gather of the result tiles per frame (inside the timed region)
   --impl reference : the reference algorithm's CPU path (oracle port, all host threads) on a bounded
           ray sample of the same workload.
+  sparse colour path (default): the rgb decoder is evaluated only for samples whose density
+          (+ noise) is > 0 — every other sample has alpha = 0 and weight exactly 0, so every output map is
+          bit-identical to evaluating all samples (tests/test_gpu_e2e.py::test_sparse_rgb_equals_dense).  The
+          line says so: config.sparse_rgb, config.rgb_rows_evaluated (fraction of the samples that reached
+          the rgb decoder), and `dense` = the same frame timed with every sample through both decoders, which
+          is what `--dense` makes the headline.  samples_per_s stays the reference's nominal count
+          (rays/s x (Nc + (Nc + Nf))); the roofline / kernels entries count only the rows actually evaluated.
 Prints ONE JSON line on rank 0.
 """
 import argparse
