@@ -289,12 +289,14 @@ def main():
         barrier()
         prof, ops.PROFILE = ops.PROFILE, None
         # companion number with the rgb decoder evaluated on EVERY sample (what the reference does), same frame
-        ms_dense = None
+        ms_dense = ms_dense_e2e = None
         if sparse:
             nvsr_b200.set_sparse_rgb(False)
             for _ in range(2):
                 frame_device()
             ms_dense = timed(frame_device, min(3, args.steps))
+            frame_e2e()
+            ms_dense_e2e = timed(frame_e2e, min(3, args.steps))
             nvsr_b200.set_sparse_rgb(True)
     agg = {}
     for name, a, b, meta in prof:
@@ -367,6 +369,8 @@ def main():
                     "h2d_bytes_per_step": int(host_rays.numel() * 4), "d2h_bytes_per_step": int(n_local * 10 * 4)},
             "dense": None if ms_dense is None else {
                 "ms_per_step": ms_dense, "value": rays / (ms_dense * 1e-3), "unit": "rays/s",
+                "e2e": {"value": rays / (ms_dense_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_dense_e2e},
+                "samples_per_s": rays * EVALS_PER_RAY / (ms_dense * 1e-3),
                 "note": "same frame with the rgb decoder evaluated on every sample (sparse_rgb off); outputs are bit-identical"},
             "gpu_launches": launches,
             "clocks": clk,

@@ -68,6 +68,11 @@ const char* nvsr_status_string(int32_t status);
 int32_t nvsr_ray_bundle(int32_t height, int32_t width, float focal_x, float focal_y,
                         const float* c2w_host, int32_t padding, float offset, int32_t row_begin,
                         int32_t row_end, float* ro, float* rd, void* stream);
+/* Same, with the pose in DEVICE memory (row-major 4x4 fp32, read by the kernel): no device->host copy of a pose
+ * the caller keeps on the GPU (the reference does, train_nerf.py:659), hence no synchronisation per frame. */
+int32_t nvsr_ray_bundle_dev(int32_t height, int32_t width, float focal_x, float focal_y,
+                            const float* c2w_device, int32_t padding, float offset, int32_t row_begin,
+                            int32_t row_end, float* ro, float* rd, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a2/a3  ray preparation of run_one_iter_of_nerf      train_utils.py:210-226, ndc_rays

@@ -113,6 +113,7 @@ SIGNATURES = {
     "nvsr_status_string": (C.c_char_p, [c_i32]),
     "nvsr_rows_padded": (c_i64, [c_i64, c_i32, c_i32]),
     "nvsr_ray_bundle": (c_i32, [c_i32, c_i32, c_f, c_f, C.POINTER(c_f), c_i32, c_f, c_i32, c_i32, c_p, c_p, c_p]),
+    "nvsr_ray_bundle_dev": (c_i32, [c_i32, c_i32, c_f, c_f, c_p, c_i32, c_f, c_i32, c_i32, c_p, c_p, c_p]),
     "nvsr_prepare_rays": (c_i32, [c_p, c_p, c_i64, c_i32, c_i32, c_i32, C.c_double, C.c_double, c_p, c_p, c_p, c_p]),
     "nvsr_pack_plane": (c_i32, [c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),
     "nvsr_pack_weight16": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p]),

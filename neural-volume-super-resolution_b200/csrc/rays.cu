@@ -10,12 +10,18 @@ struct Mat4 {
 };
 
 // a1: nerf_helpers.py:530-549.  No FMA contraction: the reference rounds every op separately.
-__global__ void ray_bundle_kernel(int H, int W, float fx, float fy, Mat4 c2w, int padding, float offset,
-                                  int row_begin, int n_rows, int Wp, float* __restrict__ ro,
-                                  float* __restrict__ rd) {
+// c2w_dev != NULL: the pose is read from device memory (row-major 4x4 fp32) instead of the by-value copy, so a
+// caller holding the pose on the GPU (the reference does, train_nerf.py:659) needs no device->host round trip.
+__global__ void ray_bundle_kernel(int H, int W, float fx, float fy, Mat4 c2w, const float* __restrict__ c2w_dev,
+                                  int padding, float offset, int row_begin, int n_rows, int Wp,
+                                  float* __restrict__ ro, float* __restrict__ rd) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)n_rows * Wp;
   if (idx >= total) return;
+  if (c2w_dev) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c2w.m[i] = __ldg(c2w_dev + i);
+  }
   int r = (int)(idx / Wp) + row_begin;
   int c = (int)(idx % Wp);
   // ii = (arange(W+2p) + offset) - p ; jj likewise
@@ -289,8 +295,25 @@ extern "C" int32_t nvsr_ray_bundle(int32_t height, int32_t width, float focal_x,
   int64_t total = (int64_t)n_rows * Wp;
   int threads = 256;
   int64_t blocks = ceil_div64(total, threads);
-  ray_bundle_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(height, width, focal_x, focal_y, m, padding,
-                                                                          offset, row_begin, n_rows, Wp, ro, rd);
+  ray_bundle_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(height, width, focal_x, focal_y, m, nullptr,
+                                                                          padding, offset, row_begin, n_rows, Wp, ro, rd);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_ray_bundle_dev(int32_t height, int32_t width, float focal_x, float focal_y,
+                                       const float* c2w_device, int32_t padding, float offset, int32_t row_begin,
+                                       int32_t row_end, float* ro, float* rd, void* stream) {
+  NVSR_CHECK_ARG(height > 0 && width > 0 && c2w_device && ro && rd && padding >= 0);
+  NVSR_CHECK_ARG(row_begin >= 0 && row_end >= row_begin && row_end <= height + 2 * padding);
+  int n_rows = row_end - row_begin;
+  if (n_rows == 0) return NVSR_OK;
+  Mat4 m = {};
+  int Wp = width + 2 * padding;
+  int64_t total = (int64_t)n_rows * Wp;
+  int threads = 256;
+  int64_t blocks = ceil_div64(total, threads);
+  ray_bundle_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(height, width, focal_x, focal_y, m, c2w_device,
+                                                                          padding, offset, row_begin, n_rows, Wp, ro, rd);
   NVSR_RETURN_LAST_ERROR();
 }
 

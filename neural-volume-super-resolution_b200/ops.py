@@ -106,17 +106,17 @@ def get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size=0,
         fx = fy = float(focal_length)
     hp, wp = height + 2 * padding_size, width + 2 * padding_size
     r0, r1 = (0, hp) if row_range is None else row_range
-    c2w = tform_cam2world.detach().to(torch.float32).cpu().contiguous().view(-1)
-    if c2w.numel() != 16:
+    if tform_cam2world.numel() != 16:
         raise _lib.NvsrError("tform_cam2world must be 4x4")
-    c2w_arr = (C.c_float * 16)(*c2w.tolist())
+    # the pose stays on the device: the kernel reads it there (no .cpu() round trip, no sync per frame)
+    c2w = _f32c(tform_cam2world.detach()).reshape(-1)
     dev = tform_cam2world.device
     ro = torch.empty((r1 - r0, wp, 3), dtype=torch.float32, device=dev)
     rd = torch.empty_like(ro)
     with torch.cuda.device(dev):
-        st = _call("nvsr_ray_bundle", lib.nvsr_ray_bundle, height, width, fx, fy, c2w_arr, padding_size, float(downsampling_offset), r0, r1,
-                                 _ptr(ro), _ptr(rd), _stream())
-    _lib.check(st, "nvsr_ray_bundle")
+        st = _call("nvsr_ray_bundle", lib.nvsr_ray_bundle_dev, height, width, fx, fy, _ptr(c2w), padding_size,
+                   float(downsampling_offset), r0, r1, _ptr(ro), _ptr(rd), _stream())
+    _lib.check(st, "nvsr_ray_bundle_dev")
     return ro, rd
 
 

@@ -62,9 +62,17 @@ def _is_planes_model(m):
     return hasattr(m, "planes_") or hasattr(m, "coord_projector")
 
 
+_t_vals_cache = {}
+
+
 def _t_vals(n, device):
-    # torch.linspace has its own rounding rule; take it from torch itself
-    return torch.linspace(0.0, 1.0, n).to(device=device, dtype=torch.float32)
+    # torch.linspace has its own rounding rule; take it from torch itself.  Cached per
+    # (n, device): an upload from pageable memory every pass would synchronise the host with the stream.
+    key = (int(n), str(device))
+    t = _t_vals_cache.get(key)
+    if t is None:
+        t = _t_vals_cache[key] = torch.linspace(0.0, 1.0, n).to(device=device, dtype=torch.float32)
+    return t
 
 
 def _slice(t, i0, i1):
