@@ -25,6 +25,7 @@ Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -266,17 +267,19 @@ def main():
         ms_dev = timed(frame_device, args.steps)
         launches = sum(ops.LAUNCHES.values())
         clk = clocks.stop()
-        if not clk.get("samples"):
-            # the timed region was shorter than nvidia-smi's sampling period: sample the clocks under the
-            # same load over a longer (untimed) stretch of the same step and say so
+        # A short timed region (many GPUs, few steps) gives nvidia-smi too few samples: then the clocks are sampled
+        # over a longer, untimed stretch of the same step.  Every rank must run the SAME number of frames (each
+        # frame holds a collective), so both the decision and the count derive from ms_dev — the all-reduced
+        # maximum, identical on every rank — never from a rank's own sampler or wall clock.
+        if ms_dev * args.steps < 250.0:
+            n_extra = max(1, int(math.ceil(600.0 / max(ms_dev, 1e-3))))
             clocks = ClockSampler(local)
             clocks.start()
-            t_end = time.perf_counter() + 0.6
-            while time.perf_counter() < t_end:
+            for _ in range(n_extra):
                 frame_device()
             barrier()
             clk = clocks.stop()
-            clk["note"] = "timed region shorter than the sampling period; sampled over 0.6 s of the same step right after it"
+            clk["note"] = f"timed region shorter than 0.25 s; sampled over {n_extra} more frames of the same step right after it"
         for _ in range(2):
             frame_e2e()
         ms_e2e = timed(frame_e2e, args.steps)
