@@ -199,6 +199,17 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    # Watchdog: a collective mismatch or a stuck rank must end as a failed run, never as a hung box.
+    limit_s = float(os.environ.get("NVSR_BENCH_WATCHDOG_S", "300" if world > 1 else "900"))
+
+    def _watchdog():
+        time.sleep(limit_s)
+        sys.stderr.write(f"bench.py: rank {rank} still running after {limit_s:.0f} s - aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+
+    threading.Thread(target=_watchdog, daemon=True).start()
+
     import nvsr_b200
     from nvsr_b200 import ops
     dev = torch.device("cuda", local)
