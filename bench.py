@@ -14,13 +14,14 @@ fine samples (hierarchical sample_pdf) -> rgb/disp/acc, coarse and fine.
           one NCCL all_gather of the result tiles per frame (inside the timed region)
   --impl reference : the reference algorithm's CPU path (oracle port, all host threads) on a bounded
           ray sample of the same workload.
-  sparse colour path (default): the rgb decoder is evaluated only for samples whose density
-          (+ noise) is > 0 — every other sample has alpha = 0 and weight exactly 0, so every output map is
+  sparse colour path (the library's default): the rgb decoder is evaluated only for samples whose
+          density (+ noise) is > 0 — every other sample has alpha = 0 and weight exactly 0, so every output map is
           bit-identical to evaluating all samples (tests/test_gpu_e2e.py::test_sparse_rgb_equals_dense).  The
-          line says so: config.sparse_rgb, config.rgb_rows_evaluated (fraction of the samples that reached
-          the rgb decoder), and `dense` = the same frame timed with every sample through both decoders, which
-          is what `--dense` makes the headline.  samples_per_s stays the reference's nominal count
-          (rays/s x (Nc + (Nc + Nf))); the roofline / kernels entries count only the rows actually evaluated.
+          HEADLINE (value, e2e, roofline, kernels) is nevertheless measured with EVERY sample through both
+          decoders — the work the reference does; the same frame with the sparse path is reported beside it under
+          `sparse` (value, e2e, rgb_rows_evaluated = fraction of the samples that reached the rgb decoder).
+          `--sparse` swaps the two (the companion is then `dense`).  samples_per_s is the reference's nominal
+          count, rays/s x (Nc + (Nc + Nf)).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -188,8 +189,10 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--ray-chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dense", action="store_true",
-                    help="evaluate the rgb decoder on every sample (default: only where sigma > 0, which is exact)")
+    ap.add_argument("--sparse", action="store_true",
+                    help="headline with the exact sparse colour path (default headline: every sample through both "
+                         "decoders; the other mode is always reported beside it)")
+    ap.add_argument("--dense", action="store_true", help="(default) headline with every sample through both decoders")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +222,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     nvsr_b200.set_precision(args.precision)
-    sparse = (not args.dense) and args.precision != "fp32" and nvsr_b200.render._state["sparse_rgb"]
+    sparse = bool(args.sparse) and not args.dense and args.precision != "fp32"   # mode of the headline
     nvsr_b200.set_sparse_rgb(sparse)
     if args.ray_chunk:
         nvsr_b200.set_ray_chunk(args.ray_chunk)
@@ -302,16 +305,33 @@ def main():
             frame_device()
         barrier()
         prof, ops.PROFILE = ops.PROFILE, None
-        # companion number with the rgb decoder evaluated on EVERY sample (what the reference does), same frame
-        ms_dense = ms_dense_e2e = None
-        if sparse:
-            nvsr_b200.set_sparse_rgb(False)
+        # companion: the same frame in the OTHER mode (sparse colour path <-> every sample through both decoders)
+        other = None
+        if args.precision != "fp32":
+            nvsr_b200.set_sparse_rgb(not sparse)
             for _ in range(2):
                 frame_device()
-            ms_dense = timed(frame_device, min(3, args.steps))
+            ms_o = timed(frame_device, min(3, args.steps))
             frame_e2e()
-            ms_dense_e2e = timed(frame_e2e, min(3, args.steps))
-            nvsr_b200.set_sparse_rgb(True)
+            ms_o_e2e = timed(frame_e2e, min(3, args.steps))
+            other = {"ms_per_step": ms_o, "value": RES * RES / (ms_o * 1e-3), "unit": "rays/s",
+                     "e2e": {"value": RES * RES / (ms_o_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_o_e2e},
+                     "samples_per_s": RES * RES * EVALS_PER_RAY / (ms_o * 1e-3)}
+            if not sparse:
+                # the companion is the sparse path: how many samples reached the rgb decoder (counted on the device)
+                ops.PROFILE = []
+                barrier()
+                frame_device()
+                barrier()
+                p2, ops.PROFILE = ops.PROFILE, None
+                lit = sum(int(m["count"].item()) for n_, _, _, m in p2 if n_ == "nvsr_mlp_chain" and m.get("count") is not None)
+                cap = sum(m["rows"] for n_, _, _, m in p2 if n_ == "nvsr_mlp_chain" and m.get("count") is not None)
+                other["rgb_rows_evaluated"] = (lit / cap) if cap else None
+                other["note"] = ("same frame with the exact sparse colour path (rgb decoder only where sigma + noise > 0; "
+                                 "maps bit-identical, DESIGN.md 4.5)")
+            else:
+                other["note"] = "same frame with every sample through both decoders; maps bit-identical"
+            nvsr_b200.set_sparse_rgb(sparse)
     agg = {}
     for name, a, b, meta in prof:
         key = name
@@ -381,11 +401,7 @@ def main():
                        "l2": "256 MiB buffer rewritten before every step; per-step intermediates (>60 GB) exceed L2"},
             "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(host_rays.numel() * 4), "d2h_bytes_per_step": int(n_local * 10 * 4)},
-            "dense": None if ms_dense is None else {
-                "ms_per_step": ms_dense, "value": rays / (ms_dense * 1e-3), "unit": "rays/s",
-                "e2e": {"value": rays / (ms_dense_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_dense_e2e},
-                "samples_per_s": rays * EVALS_PER_RAY / (ms_dense * 1e-3),
-                "note": "same frame with the rgb decoder evaluated on every sample (sparse_rgb off); outputs are bit-identical"},
+            ("dense" if sparse else "sparse"): other,
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": roofline,
