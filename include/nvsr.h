@@ -261,6 +261,41 @@ int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, int64_t n_ray
 int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, int32_t include_input,
                           float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * BACKWARD of the memory-bound stages (the reference differentiates
+ * run_one_iter_of_nerf with autograd, train_nerf.py:860-916 — mse on rgb_coarse / rgb_fine, loss.backward(),
+ * PlanesOptimizer.step()).  The decoder between them stays with the caller's autograd in this version
+ * (`nvsr_b200.autograd`); z_samples are detached in the reference (train_utils.py:153), so sample_pdf has no
+ * backward.  All tensors fp32, rows RAY_MAJOR (row = ray*S + s), as in the reference.
+ *
+ * a5 backward — scatter-add of the feature gradients through the bilinear footprints of
+ * F.grid_sample(bilinear, align_corners=True, padding_mode='border') (models.py:289-310) and the 'avg'
+ * combination (models.py:355-361):  d plane_d[y,x,c] += w * (d_feat_p[row, d*C+c] + d_feat_m[row, c] / 3).
+ * sampler->z_in ([n,S], the depths the forward used) is required; planes->plane[] is not read (geometry only:
+ * rh, rw, channels, box, proj).  d_plane: HOST array of 3 device pointers to channels-last fp32 accumulators
+ * [rh][rw][channels] that the caller zeroed (or wants accumulated into); the reference's NCHW parameter gradient is
+ * their permutation.  Either of d_feat_p [rows,3C] / d_feat_m [rows,C] may be NULL.  channels % 4 == 0.
+ */
+int32_t nvsr_sample_gather_bwd(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes, const float* d_feat_p,
+                               const float* d_feat_m, float* const d_plane[3], void* stream);
+
+/* a5 backward, view-direction half (cart2az_el nerf_helpers.py:492-496 + project_viewdir models.py:312-326):
+ * d_vplane[y,x,c] += w * d_vfeat[ray,c]; d_vplane channels-last fp32 [rh][rw][channels]; arguments as in
+ * nvsr_viewdir_gather. */
+int32_t nvsr_viewdir_gather_bwd(const float* viewdirs, int64_t n_rays, int32_t rh, int32_t rw, int32_t channels,
+                                float az_lo, float az_rng, float el_lo, float el_rng, const float* d_vfeat,
+                                float* d_vplane, void* stream);
+
+/* a7 backward — volume_render_radiance_field (volume_rendering_utils.py:15-51, cumprod_exclusive
+ * nerf_helpers.py:409-430).  radiance_field / d_radiance_field: [n,S,4] interleaved (the reference's tensor);
+ * z: [n,S] depths ([n,S+1] interval edges when mip != 0); noise: [n,S] already scaled by radiance_field_noise_std, or
+ * NULL.  Upstream gradients: d_rgb [n,3] (required), d_acc [n], d_depth [n], d_weights [n,S] (each may be NULL).
+ * disp_map is not differentiated (the reference's losses do not use it).  d_radiance_field is fully overwritten. */
+int32_t nvsr_composite_bwd(const float* radiance_field, const float* z, const float* rd, const float* noise,
+                           int64_t n_rays, int32_t n_samples, int32_t white_bkgd, int32_t mip, const float* d_rgb,
+                           const float* d_acc, const float* d_depth, const float* d_weights,
+                           float* d_radiance_field, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,9 @@ SIGNATURES = {
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),
     "nvsr_dir_encoding": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_p]),
+    "nvsr_sample_gather_bwd": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_p, c_p, C.POINTER(c_p), c_p]),
+    "nvsr_viewdir_gather_bwd": (c_i32, [c_p, c_i64, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p, c_p]),
+    "nvsr_composite_bwd": (c_i32, [c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 
 _LIB = None

@@ -1,0 +1,223 @@
+"""Differentiable wrappers of the gather and compositing stages (SURVEY.md §8f rank 1 — first version).
+
+The reference trains through `run_one_iter_of_nerf` with autograd (train_nerf.py:860-916).  This module gives the two
+memory-bound stages of that path hand-written forward AND backward kernels as `torch.autograd.Function`s; the decoder
+MLP between them stays an ordinary `nn.Module` under torch autograd in this version (its backward is two plain GEMMs
+per layer).  z_samples are detached in the reference (train_utils.py:153): nothing flows through sample_pdf.
+
+    feats  = TriPlaneGather.apply(plane0, plane1, plane2, ro, rd, z, geometry)      # a5 (xyz half), fp32
+    vfeat  = ViewdirGather.apply(view_plane, viewdirs, geometry)                     # a5 (view half)
+    raw    = decoder(feats, vfeat)                                                   # torch (models.py:393-421)
+    rgb, disp, acc, weights, depth = volume_render_radiance_field(raw, z, rd, ...)   # a7, differentiable
+
+There is no CPU path: every tensor must live on a CUDA device (`NvsrError` otherwise).
+STATUS: the kernels' arithmetic is verified on the CPU against autograd of the oracle (tests/test_backward_bodies.py
+compiles the kernels' own per-element source for the host); the CUDA launch path was written after the round's GPU
+budget was spent and has its first GPU run in tests/test_gpu_zz_backward.py.
+"""
+import torch
+
+from . import _lib, ops
+from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
+
+
+class Geometry:
+    """What the gather needs besides the plane values: box, projection matrices, view-angle box (models.py:261-268,
+    :495-497) — `ops.PackedPlanes` without plane images."""
+
+    def __init__(self, box_lo, box_rng, proj, view_lo_rng):
+        self.box_lo, self.box_rng, self.proj, self.view_lo_rng = box_lo, box_rng, proj, view_lo_rng
+
+    @classmethod
+    def of_model(cls, model, scene_id):
+        box = model.box_coords[scene_id].detach().double().cpu()
+        lo, rng = box[0].float(), (box[1] - box[0]).float()
+        rots = model.coord_projector.rot_mats_NON_LEARNED
+        proj = [rots[d].detach().float().cpu()[:, 1:].tolist() for d in range(3)]
+        return cls(lo[:3].tolist(), rng[:3].tolist(), proj, (float(lo[3]), float(rng[3]), float(lo[4]), float(rng[4])))
+
+
+def _packed(planes_nchw, geom, vplane=None):
+    imgs = [ops.pack_plane(p, NVSR_F32) for p in planes_nchw]
+    return ops.PackedPlanes(imgs, NVSR_F32, geom.box_lo, geom.box_rng, geom.proj, vplane, geom.view_lo_rng)
+
+
+class TriPlaneGather(torch.autograd.Function):
+    """(plane0, plane1, plane2 [1,C,R,R] fp32, ro [n,3], rd [n,3], z [n,S]) -> featP [n*S,3C], featM [n*S,C]
+    (project_xyz + combine_pos_planes('avg'), models.py:289-310,355-361).  Gradients: the three planes only."""
+
+    @staticmethod
+    def forward(ctx, p0, p1, p2, ro, rd, z, geom):
+        packed = _packed((p0, p1, p2), geom)
+        feat_p, feat_m, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, FEAT_ROWMAJOR_F32, z_in=z)
+        ctx.save_for_backward(ro, rd, z)
+        ctx.geom, ctx.shapes = geom, [tuple(p.shape) for p in (p0, p1, p2)]
+        ctx.set_materialize_grads(False)
+        return feat_p, feat_m
+
+    @staticmethod
+    def backward(ctx, g_p, g_m):
+        ro, rd, z = ctx.saved_tensors
+        dev = ro.device
+        acc = [torch.zeros((s[-2], s[-1], s[-3]), dtype=torch.float32, device=dev) for s in ctx.shapes]
+        shell = ops.PackedPlanes(acc, NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, None, ctx.geom.view_lo_rng)
+        if g_p is not None or g_m is not None:
+            ops.sample_gather_bwd(ro, rd, z, shell, g_p, g_m, acc)
+        grads = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc, ctx.shapes)]   # channels-last -> the parameter's NCHW
+        return grads[0], grads[1], grads[2], None, None, None, None
+
+
+class ViewdirGather(torch.autograd.Function):
+    """(view plane [1,C,Rv,Rv], viewdirs [n,3]) -> per-ray view features [n,C] (cart2az_el + project_viewdir,
+    nerf_helpers.py:492-496, models.py:312-326).  The decoder broadcasts them over a ray's samples; autograd sums."""
+
+    @staticmethod
+    def forward(ctx, vplane, viewdirs, geom):
+        img = ops.pack_plane(vplane, NVSR_F32)
+        packed = ops.PackedPlanes([img, img, img], NVSR_F32, geom.box_lo, geom.box_rng, geom.proj, img, geom.view_lo_rng)
+        ctx.save_for_backward(viewdirs)
+        ctx.geom, ctx.shape = geom, tuple(vplane.shape)
+        ctx.set_materialize_grads(False)
+        return ops.viewdir_gather(viewdirs, packed)
+
+    @staticmethod
+    def backward(ctx, g):
+        (viewdirs,) = ctx.saved_tensors
+        s = ctx.shape
+        acc = torch.zeros((s[-2], s[-1], s[-3]), dtype=torch.float32, device=viewdirs.device)
+        shell = ops.PackedPlanes([acc, acc, acc], NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, acc,
+                                 ctx.geom.view_lo_rng)
+        if g is not None:
+            ops.viewdir_gather_bwd(viewdirs, shell, g, acc)
+        return acc.permute(2, 0, 1).reshape(s), None, None
+
+
+class _VolumeRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, radiance_field, depth_values, ray_directions, noise_scaled, white_background, mip):
+        n, S, _ = radiance_field.shape
+        o = ops.composite(ops.raw_to_planar(radiance_field), depth_values, ray_directions, S, noise=noise_scaled,
+                          white_background=white_background, mip=mip, want_weights=True)
+        ctx.save_for_backward(radiance_field, depth_values, ray_directions, noise_scaled)
+        ctx.white, ctx.mip = bool(white_background), bool(mip)
+        ctx.mark_non_differentiable(o["disp"])
+        ctx.set_materialize_grads(False)
+        return o["rgb"], o["disp"], o["acc"], o["weights"], o["depth"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, _g_disp, g_acc, g_w, g_depth):
+        rf, z, rd, nz = ctx.saved_tensors
+        if g_rgb is None:
+            g_rgb = torch.zeros((rf.shape[0], 3), dtype=torch.float32, device=rf.device)
+        d_rf = ops.composite_bwd(rf, z, rd, g_rgb, d_acc=g_acc, d_depth=g_depth, d_weights=g_w, noise=nz,
+                                 white_background=ctx.white, mip=ctx.mip)
+        return d_rf, None, None, None, None, None
+
+
+def _render(radiance_field, depth_values, ray_directions, noise_std, white_background, noise, mip=False):
+    nz = None
+    if noise_std > 0.0:
+        if noise is None:
+            noise = torch.randn(radiance_field[..., 3].shape)
+        nz = (noise * noise_std).to(radiance_field).contiguous()
+    return _VolumeRender.apply(radiance_field.float().contiguous(), depth_values.float().contiguous(),
+                               ray_directions.float().contiguous(), nz, white_background, mip)
+
+
+def volume_render_radiance_field(radiance_field, depth_values, ray_directions, radiance_field_noise_std=0.0,
+                                 white_background=False, mip_nerf=False, noise=None):
+    """Differentiable drop-in for volume_rendering_utils.volume_render_radiance_field (:6-51): same signature and
+    5-tuple as `ops.volume_render_radiance_field`, gradient w.r.t. `radiance_field` (disp_map is not differentiated:
+    no loss of the reference uses it).  `noise`: the CPU randn draw of :32 ([N,S], unscaled) for parity."""
+    if not radiance_field.is_cuda:
+        raise _lib.NvsrError("radiance_field must be a CUDA tensor: nvsr_b200 has no CPU path")
+    return _render(radiance_field, depth_values, ray_directions, radiance_field_noise_std, white_background, noise, mip_nerf)
+
+
+def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
+    """TwoDimPlanesModel.forward (models.py:381-421) for the points ro + rd*z of n rays x S samples with the gather
+    done by the Functions above and the decoder by the model's own nn.Linear layers under torch autograd.
+    Returns radiance_field [n,S,4].  Gradients reach the model's planes_ parameters and decoder weights."""
+    from . import scene
+    scene.check_supported_planes_model(model)
+    model.set_cur_scene_id(scene_id)
+    geom = Geometry.of_model(model, scene_id)
+    planes = [model.planes(d, super_resolve=False) for d in range(4)]
+    n, S = z.shape
+    feat_p, feat_m = TriPlaneGather.apply(planes[0], planes[1], planes[2], ro, rd, z, geom)
+    vfeat = ViewdirGather.apply(planes[3], viewdirs, geom)
+    h = feat_m
+    for lin in model.density_dec["0"]:
+        h = torch.relu(lin(h))
+    alpha = model.fc_alpha["0"](h)
+    h = torch.cat([feat_p, vfeat[:, None, :].expand(n, S, vfeat.shape[-1]).reshape(n * S, -1)], 1)
+    for lin in model.rgb_dec["0"]:
+        h = torch.relu(lin(h))
+    rgb = model.fc_rgb["0"](h)
+    return torch.cat([rgb, alpha], -1).reshape(n, S, 4)
+
+
+def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode="train",
+                         encode_position_fn=None, encode_direction_fn=None, scene_config=None, randoms=None):
+    """Differentiable `run_one_iter_of_nerf` (train_utils.py:185-282 -> predict_and_render_radiance :71-182) for the
+    tri-plane model: same signature and 9-tuple as the reference; gradients reach `planes_` and the decoder weights of
+    both models.  Gather and compositing run on this package's kernels (forward and backward), the decoder on torch.
+    `randoms` (optional dict: 't_rand' [n,Nc], 'u' [n,Nf], 'noise_c' [n,Nc], 'noise_f' [n,Nc+Nf], unscaled) replaces
+    the reference's CPU RNG draws (train_utils.py:108, nerf_helpers.py:683, volume_rendering_utils.py:32)."""
+    if getattr(options.nerf, "encode_position_fn", None) == "mip":
+        raise NotImplementedError("nvsr_b200.autograd: the mip/IPE path has no backward yet")
+    if not options.nerf.use_viewdirs:
+        raise NotImplementedError("nvsr_b200: use_viewdirs=False is not supported")
+    if not batch_rays.is_cuda:
+        raise _lib.NvsrError("batch_rays must be CUDA tensors: nvsr_b200 has no CPU path")
+    return _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms)
+
+
+def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms):
+    cfg = getattr(options.nerf, mode)
+    randoms = randoms or {}
+    ro_in, rd_in = batch_rays[0], batch_rays[1]
+    dev = ro_in.device
+    use_ndc = scene_config.no_ndc is False
+    ro, rd, vd = ops.prepare_rays(ro_in, rd_in, use_ndc, H, W, focal if use_ndc else 1.0, 1.0)
+    n = ro.shape[0]
+    near, far = float(scene_config.near), float(scene_config.far)
+    Nc, Nf = int(cfg.num_coarse), int(cfg.num_fine)
+
+    def draw(name, shape):
+        t = randoms[name] if name in randoms else torch.rand(shape)     # the reference draws on the CPU
+        return t.to(device=dev, dtype=torch.float32)
+
+    # stratified depths (train_utils.py:95-109); data, not parameters: no gradient
+    t_vals = torch.linspace(0.0, 1.0, Nc).to(dev)
+    if not cfg.lindisp:
+        z = near * (1.0 - t_vals) + far * t_vals
+    else:
+        z = 1.0 / (1.0 / near * (1.0 - t_vals) + 1.0 / far * t_vals)
+    z = z.expand(n, Nc)
+    if cfg.perturb:
+        mids = 0.5 * (z[..., 1:] + z[..., :-1])
+        upper, lower = torch.cat((mids, z[..., -1:]), -1), torch.cat((z[..., :1], mids), -1)
+        z = lower + (upper - lower) * draw("t_rand", (n, Nc))
+    z = z.contiguous()
+    std = float(cfg.radiance_field_noise_std)
+
+    def noise_of(name, S):
+        if std <= 0.0:
+            return None
+        return randoms[name] if name in randoms else torch.randn((n, S))
+
+    rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd)
+    rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc))
+    rgb_f = disp_f = acc_f = None
+    if Nf > 0:
+        with torch.no_grad():    # z_samples.detach() (train_utils.py:153)
+            mid = 0.5 * (z[..., 1:] + z[..., :-1])
+            u = randoms.get("u")
+            if u is None and cfg.perturb != 0.0:
+                u = torch.rand([n, Nf])
+            z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf, det=(cfg.perturb == 0.0), u=u)
+            z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
+        rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd)
+        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background, noise_of("noise_f", Nc + Nf))
+    return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, None, None, None

@@ -525,3 +525,70 @@ def mip_radius(scene_id):
     if m is None:
         raise _lib.NvsrError(f"mip path needs a scene id ending in _DS<k>, got {scene_id!r}")
     return int(m.group(0)) * 0.00135 * 2 / math.sqrt(12.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward of the memory-bound stages (include/nvsr.h "BACKWARD")
+def sample_gather_bwd(ro, rd, z, packed, d_feat_p, d_feat_m, d_planes=None):
+    """Scatter-add of the row-major fp32 feature gradients into channels-last plane gradients [Rh,Rw,C] (x3).
+
+    `packed` supplies the geometry (box, projections, plane sizes); its plane images are not read.  `d_planes`
+    (list of 3 tensors) are accumulated into when given, else allocated zeroed.  Returns the list."""
+    lib = _lib.load()
+    ro, rd, z = _f32c(ro), _f32c(rd), _f32c(z)
+    _require_cuda(ro, "ray_origins")
+    n, S = z.shape
+    pl = packed.cstruct()
+    Cc = packed.channels
+    if d_planes is None:
+        d_planes = [torch.zeros((pl.rh[d], pl.rw[d], Cc), dtype=torch.float32, device=ro.device) for d in range(3)]
+    gp = None if d_feat_p is None else _f32c(d_feat_p)
+    gm = None if d_feat_m is None else _f32c(d_feat_m)
+    if gp is not None and tuple(gp.shape) != (n * S, 3 * Cc) or gm is not None and tuple(gm.shape) != (n * S, Cc):
+        raise _lib.NvsrError("sample_gather_bwd: feature gradients must be [n*S, 3C] / [n*S, C]")
+    s = _lib.Sampler()
+    s.n_rays, s.n_samples = n, S
+    s.ro, s.rd, s.z_in = ro.data_ptr(), rd.data_ptr(), z.data_ptr()
+    ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in d_planes])
+    with torch.cuda.device(ro.device):
+        st = _call("nvsr_sample_gather_bwd", lib.nvsr_sample_gather_bwd, C.byref(s), C.byref(pl), _ptr(gp), _ptr(gm), ptrs,
+                   _stream(), rows=n * S, bytes=n * S * (4 * Cc * 4 + 4))
+    _lib.check(st, "nvsr_sample_gather_bwd")
+    return d_planes
+
+
+def viewdir_gather_bwd(viewdirs, packed, d_vfeat, d_vplane=None):
+    """Scatter-add of the per-ray view-feature gradient [n,C] into the channels-last view-plane gradient."""
+    lib = _lib.load()
+    vd, g = _f32c(viewdirs), _f32c(d_vfeat)
+    _require_cuda(vd, "viewdirs")
+    n = vd.shape[0]
+    rh, rw, Cc = packed.vplane.shape
+    if d_vplane is None:
+        d_vplane = torch.zeros((rh, rw, Cc), dtype=torch.float32, device=vd.device)
+    az_lo, az_rng, el_lo, el_rng = packed.view_lo_rng
+    with torch.cuda.device(vd.device):
+        st = _call("nvsr_viewdir_gather_bwd", lib.nvsr_viewdir_gather_bwd, _ptr(vd), n, rh, rw, Cc, az_lo, az_rng, el_lo,
+                   el_rng, _ptr(g), _ptr(d_vplane), _stream())
+    _lib.check(st, "nvsr_viewdir_gather_bwd")
+    return d_vplane
+
+
+def composite_bwd(radiance_field, depth_values, ray_directions, d_rgb, d_acc=None, d_depth=None, d_weights=None,
+                  noise=None, white_background=False, mip=False):
+    """d radiance_field [N,S,4] of volume_render_radiance_field (volume_rendering_utils.py:15-51) from the upstream
+    gradients of rgb_map (required), acc_map, depth_map and weights.  `noise`: [N,S] ALREADY scaled by the std."""
+    lib = _lib.load()
+    rf, z, rd = _f32c(radiance_field), _f32c(depth_values), _f32c(ray_directions)
+    _require_cuda(rf, "radiance_field")
+    n, S, _ = rf.shape
+    if z.shape[1] != S + (1 if mip else 0):
+        raise _lib.NvsrError("composite_bwd: depth_values must be [N,S] ([N,S+1] interval edges for mip)")
+    out = torch.empty_like(rf)
+    args = [None if t is None else _f32c(t) for t in (noise, d_rgb, d_acc, d_depth, d_weights)]
+    with torch.cuda.device(rf.device):
+        st = _call("nvsr_composite_bwd", lib.nvsr_composite_bwd, _ptr(rf), _ptr(z), _ptr(rd), _ptr(args[0]), n, S,
+                   int(bool(white_background)), int(bool(mip)), _ptr(args[1]), _ptr(args[2]), _ptr(args[3]), _ptr(args[4]),
+                   _ptr(out), _stream(), rows=n * S, bytes=n * S * 36 + n * 24)
+    _lib.check(st, "nvsr_composite_bwd")
+    return out
