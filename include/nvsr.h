@@ -296,6 +296,13 @@ int32_t nvsr_composite_bwd(const float* radiance_field, const float* z, const fl
                            const float* d_acc, const float* d_depth, const float* d_weights,
                            float* d_radiance_field, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Frame sink: write_image's conversion (train_nerf.py:270,273:
+ * np.array(255*torch.clamp(im,0,1).cpu()).astype(np.uint8)) done on the device, so the device->host copy carries one
+ * byte per channel.  rgb: n_elems fp32 values (a frame [H,W,3] flat, or any map); out: n_elems bytes, 4-byte aligned
+ * (NVSR_ERR_ALIGNMENT otherwise).  fp32 product, truncating cast, NaN -> 0 (what the x86 cast of the reference gives). */
+int32_t nvsr_frame_to_u8(const float* rgb, int64_t n_elems, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

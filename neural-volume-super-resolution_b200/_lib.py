@@ -129,6 +129,7 @@ SIGNATURES = {
     "nvsr_dir_encoding": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_p]),
     "nvsr_sample_gather_bwd": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_p, c_p, C.POINTER(c_p), c_p]),
     "nvsr_viewdir_gather_bwd": (c_i32, [c_p, c_i64, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p, c_p]),
+    "nvsr_frame_to_u8": (c_i32, [c_p, c_i64, c_p, c_p]),
     "nvsr_composite_bwd": (c_i32, [c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 

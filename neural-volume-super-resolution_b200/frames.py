@@ -1,0 +1,235 @@
+"""Either side of the render path: camera-path generators in front of it, the frame sink
+behind it.
+
+Camera paths (host, numpy — a few hundred 4x4 matrices per video):
+  pose_spherical          load_blender.py:15-39      camera on a sphere looking at the origin (Blender scenes)
+  orbit_poses             load_blender.py:308-311       the 360-degree evaluation orbit
+  normalize / viewmatrix / poses_avg / render_path_spiral     load_llff.py:143-186   forward-facing spiral
+  interpolate_pose_rows   load_llff.py:73-78         `min_eval_frames` pose interpolation
+Frame sink:
+  to_uint8                train_nerf.py:270,273      255*clamp(im,0,1) -> uint8 ON THE DEVICE (nvsr_frame_to_u8)
+  encode_png              (imageio.imwrite in the reference) stdlib-only PNG writer: zlib + crc32
+  FrameSink               converts on the device, copies one byte per channel into pinned host buffers on a side stream
+                          (double-buffered, no host synchronisation per frame), hands finished frames to a writer
+There is no CPU path for the conversion: `to_uint8` refuses CPU tensors.
+"""
+import struct
+import zlib
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+
+# --------------------------------------------------------------------------------------------------
+# camera paths
+def pose_spherical(theta, phi, radius):
+    """load_blender.py:15-39; angles in degrees.  Returns a [4,4] camera-to-world matrix (float64, as the reference's
+    product of a float32 chain with an int64 matrix is)."""
+    def trans_t(t):
+        m = np.eye(4, dtype=np.float32)
+        m[2, 3] = t
+        return m
+
+    def rot_phi(p):
+        m = np.eye(4, dtype=np.float32)
+        m[1, 1] = m[2, 2] = np.cos(p)
+        m[1, 2] = -np.sin(p)
+        m[2, 1] = -m[1, 2]
+        return m
+
+    def rot_theta(th):
+        m = np.eye(4, dtype=np.float32)
+        m[0, 0] = m[2, 2] = np.cos(th)
+        m[0, 2] = -np.sin(th)
+        m[2, 0] = -m[0, 2]
+        return m
+
+    c2w = trans_t(radius)
+    c2w = rot_phi(phi / 180.0 * np.pi) @ c2w
+    c2w = rot_theta(theta / 180 * np.pi) @ c2w
+    return np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ c2w
+
+
+def orbit_poses(n_frames=40, phi=-30.0, radius=4.0):
+    """The evaluation orbit of the Blender loader: pose_spherical(angle, -30, 4) for angle in
+    linspace(-180, 180, n+1)[:-1] (load_blender.py:308-311, n = 40 there; SURVEY §8d config 5 uses n = 200).  [n,4,4] float32."""
+    return np.stack([pose_spherical(a, phi, radius) for a in np.linspace(-180, 180, n_frames + 1)[:-1]], 0).astype(np.float32)
+
+
+def normalize(x):
+    return x / np.linalg.norm(x)
+
+
+def viewmatrix(z, up, pos):
+    """load_llff.py:147-153: [3,4] camera frame looking along z."""
+    vec2 = normalize(z)
+    vec0 = normalize(np.cross(up, vec2))
+    vec1 = normalize(np.cross(vec2, vec0))
+    return np.stack([vec0, vec1, vec2, pos], 1)
+
+
+def poses_avg(poses):
+    """load_llff.py:161-170: average [3,5] pose (with hwf column) of [N,3,5] LLFF poses."""
+    hwf = poses[0, :3, -1:]
+    center = poses[:, :3, 3].mean(0)
+    vec2 = normalize(poses[:, :3, 2].sum(0))
+    up = poses[:, :3, 1].sum(0)
+    return np.concatenate([viewmatrix(vec2, up, center), hwf], 1)
+
+
+def render_path_spiral(c2w, up, rads, focal, zdelta, zrate, rots, N):
+    """load_llff.py:173-186: N [3,5] poses on a spiral around the average pose (zdelta is unused there too)."""
+    out = []
+    rads = np.array(list(rads) + [1.0])
+    hwf = c2w[:, 4:5]
+    for theta in np.linspace(0.0, 2.0 * np.pi * rots, N + 1)[:-1]:
+        c = np.dot(c2w[:3, :4], np.array([np.cos(theta), -np.sin(theta), -np.sin(theta * zrate), 1.0]) * rads)
+        z = normalize(c - np.dot(c2w[:3, :4], np.array([0, 0, -focal, 1.0])))
+        out.append(np.concatenate([viewmatrix(z, up, c), hwf], 1))
+    return out
+
+
+def interpolate_pose_rows(poses_arr, min_eval_frames):
+    """load_llff.py:73-78: linear interpolation of the rows of poses_bounds.npy up to at least `min_eval_frames` rows
+    (rounded up so that the original rows stay on the grid; they are written back verbatim).  Returns
+    (rows [M,17], repeat) with M = repeat*(N-1)+1."""
+    n = len(poses_arr)
+    m = int(np.ceil(min_eval_frames / (n - 1)) * (n - 1) + 1)
+    repeat = (m - 1) // (n - 1)
+    x = np.linspace(start=0, stop=n - 1, num=m)
+    # scipy.interpolate.interp1d(kind='linear', axis=0): y[lo] + slope * (x - lo), lo = searchsorted - 1 clipped
+    hi = np.clip(np.searchsorted(np.arange(n), x), 1, n - 1)
+    lo = hi - 1
+    slope = (poses_arr[hi] - poses_arr[lo]) / (np.arange(n)[hi] - np.arange(n)[lo])[:, None]
+    out = slope * (x - lo)[:, None] + poses_arr[lo]
+    out[::repeat, :] = poses_arr
+    return out, repeat
+
+
+# --------------------------------------------------------------------------------------------------
+# frame sink
+def to_uint8(image, out=None):
+    """255*clamp(image,0,1) -> uint8 on the device (train_nerf.py:270,273); same shape as `image`."""
+    lib = _lib.load()
+    if not image.is_cuda:
+        raise _lib.NvsrError("image must be a CUDA tensor: nvsr_b200 has no CPU path")
+    src = image.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        st = ops._call("nvsr_frame_to_u8", lib.nvsr_frame_to_u8, ops._ptr(src), src.numel(), ops._ptr(out), ops._stream(),
+                       bytes=src.numel() * 5)
+    _lib.check(st, "nvsr_frame_to_u8")
+    return out
+
+
+def _chunk(tag, data):
+    return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+
+def encode_png(u8, level=3):
+    """uint8 [H,W,3] (or [H,W] / [H,W,1] / [H,W,4]) -> PNG file bytes; filter type 0 on every scanline."""
+    a = np.ascontiguousarray(u8)
+    if a.dtype != np.uint8 or a.ndim not in (2, 3):
+        raise ValueError("encode_png expects a uint8 [H,W] or [H,W,C] array")
+    if a.ndim == 2:
+        a = a[..., None]
+    h, w, c = a.shape
+    color = {1: 0, 3: 2, 4: 6}.get(c)
+    if color is None:
+        raise ValueError("encode_png: 1, 3 or 4 channels")
+    raw = np.concatenate([np.zeros((h, 1), np.uint8), a.reshape(h, w * c)], 1).tobytes()
+    return (b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, color, 0, 0, 0))
+            + _chunk(b"IDAT", zlib.compress(raw, level)) + _chunk(b"IEND", b""))
+
+
+def decode_png(data):
+    """Inverse of encode_png for its own output (filter 0, 8 bit, non-interlaced) — used by the tests."""
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, hdr = 8, b"", None
+    while pos < len(data):
+        n, tag = struct.unpack(">I", data[pos:pos + 4])[0], data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+        if tag == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    w, h, depth, color = hdr[:4]
+    c = {0: 1, 2: 3, 6: 4}[color]
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + w * c)
+    assert depth == 8 and not rows[:, 0].any()
+    return rows[:, 1:].reshape(h, w, c)
+
+
+class FrameSink:
+    """Takes rendered frames off the GPU without stalling the render stream.
+
+    submit(frame [H,W,3] fp32 CUDA): converts to uint8 on the device (render stream), then a side stream copies the
+    bytes into one of `depth` pinned host buffers and records an event; the render stream never waits for the host.
+    A buffer is reused only after its frame has been handed to `writer(index, uint8 ndarray [H,W,3])`, which happens
+    on later submit() calls and in flush().  Default writer: keep the arrays in `self.frames`."""
+
+    def __init__(self, writer=None, depth=2):
+        self.writer = writer
+        self.depth = int(depth)
+        self.frames = []
+        self._slots = []       # (index, host tensor, event, device uint8 tensor kept alive)
+        self._free = []
+        self._count = 0
+        self._copy_stream = None
+
+    def _emit(self, index, host):
+        arr = host.numpy().copy()
+        if self.writer is None:
+            self.frames.append(arr)
+        else:
+            self.writer(index, arr)
+
+    def _drain(self, wait_all):
+        while self._slots and (wait_all or len(self._slots) >= self.depth or self._slots[0][2].query()):
+            index, host, ev, _dev = self._slots.pop(0)
+            ev.synchronize()
+            self._emit(index, host)
+            self._free.append(host)
+
+    def submit(self, frame):
+        u8 = to_uint8(frame)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=u8.device)
+        self._drain(wait_all=False)
+        host = next((h for h in self._free if h.shape == u8.shape), None)
+        if host is not None:
+            self._free.remove(host)
+        else:
+            host = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+        done = torch.cuda.Event()
+        self._copy_stream.wait_stream(torch.cuda.current_stream(u8.device))
+        with torch.cuda.stream(self._copy_stream):
+            host.copy_(u8, non_blocking=True)
+            done.record()
+        u8.record_stream(self._copy_stream)
+        self._slots.append((self._count, host, done, u8))
+        self._count += 1
+        return self._count - 1
+
+    def flush(self):
+        self._drain(wait_all=True)
+        return self.frames
+
+
+def png_writer(directory, pattern="%d.png"):
+    """writer for FrameSink: one PNG per frame, named like write_image does (train_nerf.py:268: '%d.png')."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+
+    def write(index, arr):
+        with open(os.path.join(directory, pattern % index), "wb") as f:
+            f.write(encode_png(arr))
+
+    return write

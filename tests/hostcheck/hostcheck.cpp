@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "backward_bodies.h"
+#include "frame_bodies.h"
 
 using namespace nvsr::bwd;
 
@@ -48,5 +49,10 @@ void hc_composite_bwd(const float* raw, const float* z, const float* rd, const f
                       g_acc ? g_acc + ray : nullptr, g_depth ? g_depth + ray : nullptr, g_w ? g_w + ray * S : nullptr,
                       d_raw + ray * S * 4);
   }
+}
+
+// mirrors frame_to_u8_kernel: one "thread" per quad
+void hc_frame_to_u8(const float* in, int64_t n_elems, uint8_t* out) {
+  for (int64_t i = 0; i < (n_elems + 3) / 4; ++i) nvsr::frame::to_u8_quad(in, out, i, n_elems);
 }
 }

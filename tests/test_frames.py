@@ -1,0 +1,108 @@
+"""Frame sink and camera paths: host logic and the conversion kernel's body on the CPU.
+
+Camera paths are checked against the live reference where its checkout exists (tests/golden/check_live_reference.py) and
+against committed vectors the reference produced (tests/golden/stage_camera_paths.npz) everywhere else."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import nvsr_b200
+from nvsr_b200 import frames
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), "neural-volume-super-resolution_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def hc(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("hostcheck") / "libhostcheck.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, "-o", out,
+                    os.path.join(HERE, "hostcheck", "hostcheck.cpp")], check=True)
+    return C.CDLL(out)
+
+
+def reference_u8(im):
+    """write_image's expression, verbatim (train_nerf.py:270)"""
+    with np.errstate(invalid="ignore"):
+        return np.array(255 * torch.clamp(im, 0, 1).cpu()).astype(np.uint8)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 7, 4096 * 3 + 2])
+def test_to_u8_body_matches_write_image(hc, n):
+    g = torch.Generator().manual_seed(n)
+    x = torch.rand(n, generator=g) * 1.6 - 0.3
+    if n >= 5:
+        x[0], x[1], x[2], x[3], x[4] = 1.0, 0.0, float("nan"), float("inf"), -float("inf")
+    if n > 100:   # values right at the byte boundaries k/255
+        k = torch.arange(256, dtype=torch.float32) / 255.0
+        x[100:356] = k
+        x[400:656] = torch.nextafter(k, torch.tensor(2.0))
+        x[700:956] = torch.nextafter(k, torch.tensor(-1.0))
+    out = torch.full((n + 4,), 77, dtype=torch.uint8)
+    hc.hc_frame_to_u8(C.c_void_p(x.data_ptr()), C.c_int64(n), C.c_void_p(out.data_ptr()))
+    assert np.array_equal(out[:n].numpy(), reference_u8(x))
+    assert (out[n:] == 77).all()          # nothing written past the end
+
+
+def test_png_roundtrip():
+    rng = np.random.default_rng(0)
+    for shape in ((5, 7, 3), (1, 1, 3), (16, 9), (4, 4, 4)):
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        data = frames.encode_png(a)
+        back = frames.decode_png(data)
+        assert np.array_equal(back.reshape(a.shape), a)
+        try:                                   # an independent decoder, when the box has one
+            import io
+            from PIL import Image
+        except ImportError:
+            continue
+        assert np.array_equal(np.array(Image.open(io.BytesIO(data))).reshape(a.shape), a)
+    with pytest.raises(ValueError):
+        frames.encode_png(np.zeros((2, 2, 3), np.float32))
+
+
+def test_camera_paths_match_reference_vectors():
+    g = H.golden("stage_camera_paths.npz")
+    for i, (th, ph, r) in enumerate(g["spherical_args"]):
+        assert np.array_equal(frames.pose_spherical(th, ph, r), g["spherical"][i])
+    assert np.array_equal(frames.orbit_poses(40), g["orbit40"])
+    poses = g["llff_poses"]
+    c2w = frames.poses_avg(poses)
+    assert np.array_equal(c2w, g["poses_avg"])
+    spiral = np.stack(frames.render_path_spiral(c2w, g["up"], g["rads"], float(g["focal"]), float(g["zdelta"]), 0.5, 2, 30), 0)
+    assert np.array_equal(spiral, g["spiral"])
+    rows, rep = frames.interpolate_pose_rows(g["pose_rows"], int(g["min_eval_frames"]))
+    assert rep == int(g["repeat"]) and rows.shape == g["pose_rows_interp"].shape
+    np.testing.assert_allclose(rows, g["pose_rows_interp"], rtol=0, atol=1e-12)
+    assert np.array_equal(rows[::rep], g["pose_rows"])
+
+
+def test_to_uint8_refuses_cpu_tensors():
+    with pytest.raises(nvsr_b200.NvsrError):
+        frames.to_uint8(torch.zeros(2, 2, 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="frame sink kernel: CPU-verified body, first GPU run")
+def test_gpu_frame_sink_matches_write_image(tmp_path):
+    g = torch.Generator().manual_seed(1)
+    sink = frames.FrameSink(writer=frames.png_writer(str(tmp_path)), depth=2)
+    imgs = [torch.rand(37, 41, 3, generator=g) * 1.4 - 0.2 for _ in range(5)]
+    imgs[1][0, 0, 0] = float("nan")
+    for im in imgs:
+        sink.submit(im.cuda())
+    sink.flush()
+    for i, im in enumerate(imgs):
+        with open(tmp_path / f"{i}.png", "rb") as f:
+            assert np.array_equal(frames.decode_png(f.read()), reference_u8(im))
+    big = torch.rand(800, 800, 3, generator=g)
+    assert np.array_equal(frames.to_uint8(big.cuda()).cpu().numpy(), reference_u8(big))
