@@ -9,7 +9,7 @@ Public surface = the reference's own call surface for this path
 Host code is Python; every kernel is hand-written CUDA behind the C-ABI of include/nvsr.h.
 There is no CPU fallback: without libnvsr_b200.so (or without a GPU) every entry point raises.
 """
-from . import _lib, autograd, build, frames, ops, render, scene, sharding  # noqa: F401
+from . import _lib, autograd, build, frames, ops, plane_store, render, scene, sharding  # noqa: F401
 from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32, NvsrError  # noqa: F401
 from .ops import (get_ray_bundle, sample_pdf, volume_render_radiance_field)  # noqa: F401
 from .render import (eval_nerf, get_precision, install, render_frame, run_one_iter_of_nerf, set_precision,  # noqa: F401
