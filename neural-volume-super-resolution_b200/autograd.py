@@ -13,7 +13,7 @@ per layer).  z_samples are detached in the reference (train_utils.py:153): nothi
 There is no CPU path: every tensor must live on a CUDA device (`NvsrError` otherwise).
 STATUS: the kernels' arithmetic is verified on the CPU against autograd of the oracle (tests/test_backward_bodies.py
 compiles the kernels' own per-element source for the host); the CUDA launch path was written after the round's GPU
-budget was spent and has its first GPU run in tests/test_gpu_zz_backward.py.
+budget was spent and has its first GPU run in tests/test_gpu_zz_next_rows.py.
 """
 import torch
 

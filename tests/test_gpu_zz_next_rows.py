@@ -1,4 +1,5 @@
-"""GPU parity of the backward kernels through the C-ABI.
+"""GPU parity of the §8f rows written at the end of round 1 — backward kernels (rank 1), frame sink (rank 4), plane store
+device staging (rank 3) — through the C-ABI.
 
 These kernels were written after the round's GPU budget was spent: their arithmetic is verified on the CPU (the
 kernels' own per-element source compiled for the host, tests/test_backward_bodies.py), but the CUDA launch path has
@@ -16,7 +17,7 @@ from nvsr_b200 import autograd as A, ops, scene
 from oracle import nvsr_oracle as O
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="backward kernels: CPU-verified bodies, first GPU run (see module docstring)")]
+              pytest.mark.xfail(strict=False, reason="8f rows: CPU-verified bodies, first GPU run (see module docstring)")]
 DEV = "cuda:0"
 
 
@@ -129,3 +130,41 @@ def test_gather_bwd_full_batch_mass_conservation():
     ops.sample_gather_bwd(ro, rd, z, packed, None, gm, acc)
     for d in range(3):
         H.assert_close(acc[d], 2 * once[d], 1e-3, rtol=1e-4, what="accumulate")
+
+
+# ---- the other §8f rows written at the end of round 1 (frame sink, plane store): kept here so that a fault in
+# never-run device code cannot disturb the forward path's tests, which sort before this file
+def test_gpu_frame_sink_matches_write_image(tmp_path):
+    from nvsr_b200 import frames
+    from test_frames import reference_u8
+    g = torch.Generator().manual_seed(1)
+    sink = frames.FrameSink(writer=frames.png_writer(str(tmp_path)), depth=2)
+    imgs = [torch.rand(37, 41, 3, generator=g) * 1.4 - 0.2 for _ in range(5)]
+    imgs[1][0, 0, 0] = float("nan")
+    for im in imgs:
+        sink.submit(im.cuda())
+    sink.flush()
+    for i, im in enumerate(imgs):
+        with open(tmp_path / f"{i}.png", "rb") as f:
+            assert np.array_equal(frames.decode_png(f.read()), reference_u8(im))
+    big = torch.rand(800, 800, 3, generator=g)
+    assert np.array_equal(frames.to_uint8(big.cuda()).cpu().numpy(), reference_u8(big))
+
+
+def test_gpu_attach_overlaps_and_renders(tmp_path):
+    import os
+    import shutil
+    from nvsr_b200 import plane_store as PS
+    from test_plane_store import SCENE, _twin
+    shutil.copy(os.path.join(H.GOLDEN, "coarse_%s.par" % SCENE), tmp_path)
+    store_dir = str(tmp_path)
+    from nvsr_b200 import scene
+    st = PS.PlaneStore(store_dir, device="cuda:0")
+    st.prefetch(SCENE)
+    m = scene.TriPlaneModel(num_plane_channels=8, scene_coupler=scene.SingleSceneCoupler(None))
+    params = st.attach([m], SCENE)
+    torch.cuda.synchronize()
+    twin = _twin()
+    for k in PS.plane_names(SCENE):
+        assert params[k].is_cuda and np.array_equal(params[k].detach().cpu().numpy(), twin[k])
+    assert SCENE in m.box_coords

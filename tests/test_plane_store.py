@@ -1,6 +1,6 @@
 """Plane store: the reference's `.par` scene files, read and written with its safe_saving /
 safe_loading protocol (nerf_helpers.py:19-67, models.py:612-678), host staging, and the torch.distributed broadcast.
-Host logic only — the device staging (`to_device` / `attach`) needs a GPU and is covered in the gpu-marked test."""
+Host logic only — the device staging (`to_device` / `attach`) needs a GPU: tests/test_gpu_zz_next_rows.py."""
 import json
 import os
 import shutil
@@ -131,18 +131,3 @@ def test_two_rank_broadcast(store_dir, tmp_path_factory):
     for k in PS.plane_names(SCENE):
         assert torch.equal(a["planes"][k], b["planes"][k]) and np.array_equal(a["planes"][k].numpy(), twin[k])
     assert torch.equal(a["box"], b["box"]) and np.array_equal(a["box"].numpy(), twin["box"])
-
-
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="plane store device staging: first GPU run")
-def test_gpu_attach_overlaps_and_renders(store_dir):
-    from nvsr_b200 import scene
-    st = PS.PlaneStore(store_dir, device="cuda:0")
-    st.prefetch(SCENE)
-    m = scene.TriPlaneModel(num_plane_channels=8, scene_coupler=scene.SingleSceneCoupler(None))
-    params = st.attach([m], SCENE)
-    torch.cuda.synchronize()
-    twin = _twin()
-    for k in PS.plane_names(SCENE):
-        assert params[k].is_cuda and np.array_equal(params[k].detach().cpu().numpy(), twin[k])
-    assert SCENE in m.box_coords
