@@ -160,20 +160,89 @@ def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
 def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode="train",
                          encode_position_fn=None, encode_direction_fn=None, scene_config=None, randoms=None):
     """Differentiable `run_one_iter_of_nerf` (train_utils.py:185-282 -> predict_and_render_radiance :71-182) for the
-    tri-plane model: same signature and 9-tuple as the reference; gradients reach `planes_` and the decoder weights of
-    both models.  Gather and compositing run on this package's kernels (forward and backward), the decoder on torch.
+    tri-plane model and for the mip/IPE model: same signature and 9-tuple as the reference; gradients reach `planes_` and
+    the decoder weights of both models.  Gather / IPE and compositing run on this package's kernels (forward and
+    backward), the decoder on torch.
     `randoms` (optional dict: 't_rand' [n,Nc], 'u' [n,Nf], 'noise_c' [n,Nc], 'noise_f' [n,Nc+Nf], unscaled) replaces
     the reference's CPU RNG draws (train_utils.py:108, nerf_helpers.py:683, volume_rendering_utils.py:32)."""
-    if getattr(options.nerf, "encode_position_fn", None) == "mip":
-        raise NotImplementedError("nvsr_b200.autograd: the mip/IPE path has no backward yet")
     if not options.nerf.use_viewdirs:
         raise NotImplementedError("nvsr_b200: use_viewdirs=False is not supported")
     if not batch_rays.is_cuda:
         raise _lib.NvsrError("batch_rays must be CUDA tensors: nvsr_b200 has no CPU path")
-    return _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms)
+    return _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms,
+                         encode_position_fn)
 
 
-def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms):
+def mip_model_forward(model, xyz_feat, dir_feat):
+    """FlexibleNeRFModel.forward (models.py:85-108, use_viewdirs, xyz_input_2_dir=False) on torch autograd:
+    xyz_feat [rows, dim_xyz] (IPE), dir_feat [rows, dim_dir] -> [rows, 4].  No ReLU after layer1 (models.py:88)."""
+    h = model.layer1(xyz_feat)
+    for i, lin in enumerate(model.layers_xyz):
+        if i % model.skip_connect_every == 0 and i > 0 and i != len(model.layers_xyz):
+            h = torch.cat((h, xyz_feat), dim=-1)
+        h = torch.relu(lin(h))
+    feat = torch.relu(model.fc_feat(h))
+    alpha = model.fc_alpha(h)
+    h = torch.cat((feat, dir_feat), dim=-1)
+    for lin in model.layers_dir:
+        h = torch.relu(lin(h))
+    return torch.cat((model.fc_rgb(h), alpha), dim=-1)
+
+
+def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scene_id, n_freqs, randoms):
+    """mip/IPE branch (train_utils.py:15-64 run_network with cast_rays, mip.py:9-43,154-199): the encodings are data
+    (no parameters), so only the decoder (torch autograd) and the compositing (nvsr_composite_bwd, interval edges)
+    carry gradients."""
+    n, dev = ro.shape[0], ro.device
+    Nc, Nf = int(cfg.num_coarse), int(cfg.num_fine)
+    radius = ops.mip_radius(scene_id)
+    n_dir = (model_coarse.dim_dir - 3) // 6
+    if model_coarse.dim_xyz != 6 * n_freqs:
+        raise _lib.NvsrError("IPE width does not match the model's dim_xyz")
+    t = torch.linspace(0.0, 1.0, Nc + 1).to(dev)
+    z = near * (1.0 - t) + far * t if not cfg.lindisp else 1.0 / (1.0 / near * (1.0 - t) + 1.0 / far * t)
+    z = z.expand(n, Nc + 1)
+    if cfg.perturb:
+        mids = 0.5 * (z[..., 1:] + z[..., :-1])
+        upper, lower = torch.cat((mids, z[..., -1:]), -1), torch.cat((z[..., :1], mids), -1)
+        t_rand = randoms["t_rand"] if "t_rand" in randoms else torch.rand((n, Nc + 1))
+        z = lower + (upper - lower) * t_rand.to(device=dev, dtype=torch.float32)
+    z = z.contiguous()
+    denc = ops.dir_encoding(vd, n_dir, True)
+    std = float(cfg.radiance_field_noise_std)
+
+    def noise_of(name, S):
+        if std <= 0.0:
+            return None
+        return randoms[name] if name in randoms else torch.randn((n, S))
+
+    def radiance(model, z_edges):
+        S = z_edges.shape[1] - 1
+        with torch.no_grad():
+            enc = ops.ipe(z_edges, ro, rd, radius, n_freqs)
+            dirs = denc[:, None, :].expand(n, S, denc.shape[-1]).reshape(n * S, -1)
+        return mip_model_forward(model, enc, dirs).reshape(n, S, 4)
+
+    rf = radiance(model_coarse, z)
+    rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc), mip=True)
+    rgb_f = disp_f = acc_f = None
+    if Nf > 0:
+        with torch.no_grad():
+            mid = 0.5 * (z[..., 1:] + z[..., :-1])
+            mid = 0.5 * (mid[..., 1:] + mid[..., :-1])
+            u = randoms.get("u")
+            if u is None and cfg.perturb != 0.0:
+                u = torch.rand([n, Nf + 1])
+            z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf + 1, det=(cfg.perturb == 0.0), u=u)
+            z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
+        rf_f = radiance(model_fine, z_f)
+        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background,
+                                             noise_of("noise_f", z_f.shape[1] - 1), mip=True)
+    return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, None, None, None
+
+
+def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms,
+                  encode_position_fn=None):
     cfg = getattr(options.nerf, mode)
     randoms = randoms or {}
     ro_in, rd_in = batch_rays[0], batch_rays[1]
@@ -183,6 +252,11 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
     n = ro.shape[0]
     near, far = float(scene_config.near), float(scene_config.far)
     Nc, Nf = int(cfg.num_coarse), int(cfg.num_fine)
+    if getattr(options.nerf, "encode_position_fn", None) == "mip":
+        n_freqs = getattr(encode_position_fn, "max_freq", None)
+        if n_freqs is None or hasattr(model_coarse, "planes_"):
+            raise NotImplementedError("nvsr_b200: the mip path needs an IntegratedPositionalEncoding and a FlexibleNeRFModel")
+        return _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scene_id, n_freqs, randoms)
 
     def draw(name, shape):
         t = randoms[name] if name in randoms else torch.rand(shape)     # the reference draws on the CPU

@@ -230,9 +230,18 @@ def host_ops(hc, monkeypatch):
     def sample_pdf(bins, weights, num_samples, det=False, u=None, **kw):
         return O.sample_pdf(bins, weights, num_samples, det=det, u=u)
 
+    def ipe(z_edges, ro, rd, radius, n_freqs, **kw):
+        means, covs = O.cast_rays(z_edges, ro, rd, torch.full((ro.shape[0], 1), float(radius)))
+        e = O.integrated_pos_enc(means, covs, n_freqs + 1)
+        return e.reshape(-1, e.shape[-1]).contiguous()
+
+    def dir_encoding(dirs, n_freqs, include_input=True):
+        return O.positional_encoding(dirs, n_freqs, include_input)
+
     for name, fn in dict(pack_plane=pack_plane, sample_gather=sample_gather, sample_gather_bwd=sample_gather_bwd,
                          viewdir_gather=viewdir_gather, viewdir_gather_bwd=viewdir_gather_bwd, composite=composite,
-                         composite_bwd=composite_bwd, prepare_rays=prepare_rays, sample_pdf=sample_pdf).items():
+                         composite_bwd=composite_bwd, prepare_rays=prepare_rays, sample_pdf=sample_pdf, ipe=ipe,
+                         dir_encoding=dir_encoding).items():
         monkeypatch.setattr(ops, name, fn)
     return ops
 
@@ -354,3 +363,47 @@ def test_product_backward_composition_matches_reference_gradients(host_ops):
     for k in [k[len("grad__"):] for k in g if k.startswith("grad__")]:
         assert named[k].grad is not None, k
         _close(named[k].grad, torch.from_numpy(g["grad__" + k]), rel=5e-4)
+
+
+def test_mip_train_step_matches_oracle_autograd(host_ops):
+    """mip/IPE family (FlexibleNeRFModel + IntegratedPositionalEncoding): train-mode step through
+    nvsr_b200.autograd (IPE and direction encodings are data; decoder on torch; compositing with interval edges through
+    the host-built backward body) against autograd of the oracle, on the golden mip scene."""
+    import helpers as H
+    from nvsr_b200 import autograd as A
+    g = H.golden("e2e_mip_det.npz")
+    sid = str(g["scene_id"])
+    mc, mf = H.load_mip_scene(str(g["scene_file"]))
+    opt = scene.render_options(int(g["num_coarse"]), int(g["num_fine"]), perturb=True, white_background=True, noise_std=0.3, mip=True)
+    scfg = H.scene_cfg_from(g)
+    batch = torch.stack([H.T(g["ro"]).reshape(-1, 3), H.T(g["rd"]).reshape(-1, 3)], 0)
+    n, Nc, Nf = batch.shape[1], int(g["num_coarse"]), int(g["num_fine"])
+    gen = torch.Generator().manual_seed(6)
+    rnd = {"t_rand": torch.rand(n, Nc + 1, generator=gen), "u": torch.rand(n, Nf + 1, generator=gen),
+           "noise_c": torch.randn(n, Nc, generator=gen), "noise_f": torch.randn(n, Nc + Nf + 1, generator=gen)}
+    target = torch.rand(n, 3, generator=gen)
+    params = [p for m in (mc, mf) for p in m.parameters()]
+
+    def step(fn):
+        for p in params:
+            p.grad = None
+        out = fn()
+        (((out[0] - target) ** 2).mean() + ((out[3] - target) ** 2).mean()).backward()
+        return out, [None if p.grad is None else p.grad.clone() for p in params]
+
+    enc_o = lambda mc_: O.integrated_pos_enc(mc_[0], mc_[1], 7)
+    encd_o = lambda x: O.positional_encoding(x, 4, True)
+    Hh, Ww, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    out_o, want = step(lambda: O.run_one_iter_of_nerf(Hh, Ww, f, mc, mf, batch, opt, sid, "train", encode_position_fn=enc_o,
+                                                      encode_direction_fn=encd_o, scene_config=scfg, randoms=rnd))
+    out_p, got = step(lambda: A._run_one_iter(Hh, Ww, f, mc, mf, batch, opt, sid, "train", scfg, rnd,
+                                              nvsr_b200.IntegratedPositionalEncoding(3, 7)))
+    for j in (0, 2, 3, 5):
+        assert torch.allclose(out_p[j], out_o[j], atol=2e-5), j
+    n_checked = 0
+    for a, b in zip(got, want):
+        assert (a is None) == (b is None)
+        if b is not None and float(b.abs().max()) > 0:
+            _close(a, b, rel=5e-4)
+            n_checked += 1
+    assert n_checked >= 16

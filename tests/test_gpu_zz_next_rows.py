@@ -132,6 +132,39 @@ def test_gather_bwd_full_batch_mass_conservation():
         H.assert_close(acc[d], 2 * once[d], 1e-3, rtol=1e-4, what="accumulate")
 
 
+def test_mip_train_step_gradients_match_oracle_autograd():
+    """mip/IPE family: train-mode step through nvsr_b200.autograd on the GPU (nvsr_ipe, nvsr_dir_encoding, nvsr_composite
+    with interval edges and its backward; decoder on torch) against autograd of the oracle on the CPU."""
+    import copy
+    g = H.golden("e2e_mip_det.npz")
+    sid = str(g["scene_id"])
+    mc, mf = H.load_mip_scene(str(g["scene_file"]))
+    mc_g, mf_g = copy.deepcopy(mc).to(DEV), copy.deepcopy(mf).to(DEV)
+    Nc, Nf = int(g["num_coarse"]), int(g["num_fine"])
+    opt = scene.render_options(Nc, Nf, perturb=True, white_background=True, noise_std=0.3, mip=True)
+    scfg = H.scene_cfg_from(g)
+    batch = torch.stack([H.T(g["ro"]).reshape(-1, 3), H.T(g["rd"]).reshape(-1, 3)], 0)
+    n = batch.shape[1]
+    gen = torch.Generator().manual_seed(6)
+    rnd = {"t_rand": torch.rand(n, Nc + 1, generator=gen), "u": torch.rand(n, Nf + 1, generator=gen),
+           "noise_c": torch.randn(n, Nc, generator=gen), "noise_f": torch.randn(n, Nc + Nf + 1, generator=gen)}
+    target = torch.rand(n, 3, generator=gen)
+    Hh, Ww, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    out_o = O.run_one_iter_of_nerf(Hh, Ww, f, mc, mf, batch, opt, sid, "train",
+                                   encode_position_fn=lambda m: O.integrated_pos_enc(m[0], m[1], 7),
+                                   encode_direction_fn=lambda x: O.positional_encoding(x, 4, True), scene_config=scfg, randoms=rnd)
+    (((out_o[0] - target) ** 2).mean() + ((out_o[3] - target) ** 2).mean()).backward()
+    out_g = A.run_one_iter_of_nerf(Hh, Ww, f, mc_g, mf_g, batch.to(DEV), opt, sid, "train",
+                                   encode_position_fn=nvsr_b200.IntegratedPositionalEncoding(3, 7), encode_direction_fn=object(),
+                                   scene_config=scfg, randoms={k: v.to(DEV) for k, v in rnd.items()})
+    (((out_g[0] - target.to(DEV)) ** 2).mean() + ((out_g[3] - target.to(DEV)) ** 2).mean()).backward()
+    H.assert_close(out_g[0], out_o[0].detach(), 5e-5, what="rgb_coarse")
+    for (k, a), b in zip(list(mc_g.named_parameters()) + list(mf_g.named_parameters()), list(mc.parameters()) + list(mf.parameters())):
+        assert (a.grad is None) == (b.grad is None), k
+        if b.grad is not None and float(b.grad.abs().max()) > 0:
+            _close(a.grad, b.grad, 5e-3)
+
+
 # ---- the other §8f rows written at the end of round 1 (frame sink, plane store): kept here so that a fault in
 # never-run device code cannot disturb the forward path's tests, which sort before this file
 def test_gpu_frame_sink_matches_write_image(tmp_path):
