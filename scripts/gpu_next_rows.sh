@@ -1,0 +1,12 @@
+#!/bin/bash
+# First GPU run of the §8f rows written at the end of round 1 (backward kernels, frame sink, plane store staging):
+#   gpurun --timeout 900 -- 'bash scripts/gpu_next_rows.sh'
+# --runxfail turns the xfail(strict=False) marks off, so a failure shows its traceback; compute-sanitizer then checks
+# the never-run kernels for out-of-bounds accesses; the train-step timing comes last.
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu --runxfail -x 2>&1 | tail -40 > gpurun_out/next_rows_tests.log
+timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu --runxfail \
+  -k "composite_bwd or gather_bwd_matches or frame_sink" 2>&1 | tail -30 > gpurun_out/next_rows_memcheck.log
+timeout 600 python scripts/bench_train_step.py --steps 20 > gpurun_out/train_step.json 2> gpurun_out/train_step.err
+tail -5 gpurun_out/next_rows_tests.log; cat gpurun_out/train_step.json
