@@ -9,4 +9,5 @@ timeout 600 python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu --runxfail
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zz_next_rows.py -q -m gpu --runxfail \
   -k "composite_bwd or gather_bwd_matches or frame_sink" 2>&1 | tail -30 > gpurun_out/next_rows_memcheck.log
 timeout 600 python scripts/bench_train_step.py --steps 20 > gpurun_out/train_step.json 2> gpurun_out/train_step.err
-tail -5 gpurun_out/next_rows_tests.log; cat gpurun_out/train_step.json
+timeout 600 python scripts/render_video.py --out /tmp/nvsr_video --scenes 2 --frames 8 --res 400 > gpurun_out/render_video.json 2> gpurun_out/render_video.err
+tail -5 gpurun_out/next_rows_tests.log; cat gpurun_out/train_step.json gpurun_out/render_video.json
