@@ -274,7 +274,8 @@ int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, in
  * sampler->z_in ([n,S], the depths the forward used) is required; planes->plane[] is not read (geometry only:
  * rh, rw, channels, box, proj).  d_plane: HOST array of 3 device pointers to channels-last fp32 accumulators
  * [rh][rw][channels] that the caller zeroed (or wants accumulated into); the reference's NCHW parameter gradient is
- * their permutation.  Either of d_feat_p [rows,3C] / d_feat_m [rows,C] may be NULL.  channels % 4 == 0.
+ * their permutation.  Either of d_feat_p [rows,3C] / d_feat_m [rows,C] may be NULL.  channels % 4 == 0 and 16-byte
+ * aligned accumulators (NVSR_ERR_ALIGNMENT otherwise): the updates are 128-bit vector reductions.
  */
 int32_t nvsr_sample_gather_bwd(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes, const float* d_feat_p,
                                const float* d_feat_m, float* const d_plane[3], void* stream);

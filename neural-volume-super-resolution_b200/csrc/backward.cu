@@ -27,7 +27,8 @@ struct GatherBwdArgs {
 };
 
 // one thread per (row, 4-channel chunk): consecutive threads hold consecutive channel chunks of one row, so the
-// four corner updates of a warp are runs of 16-byte-adjacent fp32 reductions into channels-last accumulators
+// four corner updates of a warp are runs of adjacent 128-bit vector reductions (RED.E.ADD.F32x4) into channels-last
+// accumulators
 __global__ void __launch_bounds__(256) gather_bwd_kernel(GatherBwdArgs a) {
   const int chunks = a.g.C / 4;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,6 +77,7 @@ extern "C" int32_t nvsr_sample_gather_bwd(const nvsr_sampler_t* s, const nvsr_pl
   GatherBwdArgs a;
   for (int d = 0; d < 3; ++d) {
     NVSR_CHECK_ARG(d_plane[d] && pl->rh[d] > 0 && pl->rw[d] > 0);
+    if (!aligned16(d_plane[d])) return NVSR_ERR_ALIGNMENT;   // 128-bit vector reductions
     a.g.rh[d] = pl->rh[d], a.g.rw[d] = pl->rw[d];
     a.g.lo[d] = pl->box_lo[d], a.g.rng[d] = pl->box_rng[d];
     for (int k = 0; k < 6; ++k) a.g.proj[d][k] = pl->proj[d][k];
@@ -96,6 +98,7 @@ extern "C" int32_t nvsr_viewdir_gather_bwd(const float* viewdirs, int64_t n_rays
                                            const float* d_vfeat, float* d_vplane, void* stream) {
   NVSR_CHECK_ARG(viewdirs && d_vfeat && d_vplane && n_rays >= 0 && rh > 0 && rw > 0);
   NVSR_CHECK_ARG(channels > 0 && channels % 4 == 0);
+  if (!aligned16(d_vplane)) return NVSR_ERR_ALIGNMENT;
   int64_t total = n_rays * (channels / 4);
   if (total == 0) return NVSR_OK;
   viewdir_gather_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
