@@ -33,20 +33,36 @@ def _stale():
 
 
 def build_library(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library with nvcc (cross-compiles without a GPU)."""
+    """Compile every .cu under csrc/ into one shared library with nvcc (cross-compiles without a GPU).
+
+    Safe under several processes (torchrun ranks, pytest-xdist): the build is serialised with an exclusive file lock,
+    a process that waited re-checks staleness (the winner has built it), and the library appears atomically
+    (compiled to a temporary name, then renamed) — a reader never maps a half-written file."""
     if LIB_OVERRIDE or (not force and not _stale()):
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-o", LIB_PATH] + sources()
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "nvcc")
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-o", tmp] + sources()
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr, file=sys.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -79,3 +79,42 @@ def test_forward_only_guard():
     with pytest.raises(RuntimeError, match="forward-only"):
         nvsr_b200.run_one_iter_of_nerf(2, 2, 3.0, mc, mf, torch.zeros(2, 4, 3), scene.render_options(8, 8), sid,
                                        "validation", scene_config=scene.scene_cfg())
+
+
+def test_concurrent_builds_are_serialised(tmp_path, monkeypatch):
+    """Several processes asking for a stale library (torchrun ranks on a box whose mtimes were disturbed) must build it
+    once at a time and publish it atomically: with a stand-in compiler, 4 racing processes produce exactly one build
+    after the first, and the library file is never observed half-written."""
+    import subprocess
+    import sys
+    import textwrap
+    fake = tmp_path / "fake_nvcc.py"
+    fake.write_text(textwrap.dedent("""\
+        #!%s
+        import sys, time, os
+        out = sys.argv[sys.argv.index('-o') + 1]
+        with open(os.path.join(os.path.dirname(out), 'build_count'), 'a') as f:
+            f.write('x')
+        with open(out, 'w') as f:
+            f.write('half'); f.flush(); time.sleep(0.5); f.write('-whole')
+        """ % sys.executable))
+    fake.chmod(0o755)
+    work = tmp_path / "pkg"
+    (work / "csrc").mkdir(parents=True)
+    (work / "csrc" / "a.cu").write_text("// source\n")
+    (tmp_path / "include").mkdir()
+    (tmp_path / "include" / "nvsr.h").write_text("// header\n")
+    script = textwrap.dedent("""\
+        import importlib.util, os, sys
+        spec = importlib.util.spec_from_file_location('b', %r)
+        b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+        b.PKG_DIR, b.REPO_DIR, b.CSRC = %r, %r, %r
+        b.LIB_PATH = os.path.join(b.PKG_DIR, 'libnvsr_b200.so'); b.LIB_OVERRIDE = None
+        b.build_library()
+        assert open(b.LIB_PATH).read() == 'half-whole'
+        """ % (nvsr_b200.build.__file__, str(work), str(tmp_path), str(work / "csrc")))
+    env = dict(os.environ, NVCC=str(fake))
+    procs = [subprocess.Popen([sys.executable, "-c", script], env=env) for _ in range(4)]
+    assert [p.wait(timeout=120) for p in procs] == [0, 0, 0, 0]
+    assert (work / "build_count").read_text() == "x"          # built once; the three that waited found it fresh
+    assert not [f for f in os.listdir(work) if ".tmp." in f]
