@@ -4,7 +4,7 @@ behind it.
 Camera paths (host, numpy — a few hundred 4x4 matrices per video):
   pose_spherical          load_blender.py:15-39      camera on a sphere looking at the origin (Blender scenes)
   orbit_poses             load_blender.py:308-311       the 360-degree evaluation orbit
-  normalize / viewmatrix / poses_avg / render_path_spiral     load_llff.py:143-186   forward-facing spiral
+  look_along / poses_avg / render_path_spiral                 load_llff.py:143-186   forward-facing spiral (batched)
   interpolate_pose_rows   load_llff.py:73-78         `min_eval_frames` pose interpolation
 Frame sink:
   to_uint8                train_nerf.py:270,273      255*clamp(im,0,1) -> uint8 ON THE DEVICE (nvsr_frame_to_u8)
@@ -58,37 +58,40 @@ def orbit_poses(n_frames=40, phi=-30.0, radius=4.0):
     return np.stack([pose_spherical(a, phi, radius) for a in np.linspace(-180, 180, n_frames + 1)[:-1]], 0).astype(np.float32)
 
 
-def normalize(x):
-    return x / np.linalg.norm(x)
+def _unit(v):
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
 
 
-def viewmatrix(z, up, pos):
-    """load_llff.py:147-153: [3,4] camera frame looking along z."""
-    vec2 = normalize(z)
-    vec0 = normalize(np.cross(up, vec2))
-    vec1 = normalize(np.cross(vec2, vec0))
-    return np.stack([vec0, vec1, vec2, pos], 1)
+def look_along(z, up, pos):
+    """Camera frames [...,3,4] = [x | y | z | pos] looking along `z` with `up` as the rough vertical — the frame
+    construction of load_llff.viewmatrix (:147-153), batched over leading dimensions."""
+    z = _unit(np.asarray(z, dtype=np.float64))
+    x = _unit(np.cross(np.broadcast_to(up, z.shape), z))
+    y = _unit(np.cross(z, x))
+    return np.stack([x, y, z, np.broadcast_to(pos, z.shape)], -1)
 
 
 def poses_avg(poses):
-    """load_llff.py:161-170: average [3,5] pose (with hwf column) of [N,3,5] LLFF poses."""
-    hwf = poses[0, :3, -1:]
-    center = poses[:, :3, 3].mean(0)
-    vec2 = normalize(poses[:, :3, 2].sum(0))
-    up = poses[:, :3, 1].sum(0)
-    return np.concatenate([viewmatrix(vec2, up, center), hwf], 1)
+    """Average pose of [N,3,5] LLFF poses (load_llff.poses_avg :161-170): mean centre, summed z and y axes, the hwf
+    column of the first pose.  Returns [3,5]."""
+    poses = np.asarray(poses, dtype=np.float64)
+    frame = look_along(poses[:, :, 2].sum(0), poses[:, :, 1].sum(0), poses[:, :, 3].mean(0))
+    return np.concatenate([frame, poses[0, :, 4:5]], -1)
 
 
 def render_path_spiral(c2w, up, rads, focal, zdelta, zrate, rots, N):
-    """load_llff.py:173-186: N [3,5] poses on a spiral around the average pose (zdelta is unused there too)."""
-    out = []
-    rads = np.array(list(rads) + [1.0])
-    hwf = c2w[:, 4:5]
-    for theta in np.linspace(0.0, 2.0 * np.pi * rots, N + 1)[:-1]:
-        c = np.dot(c2w[:3, :4], np.array([np.cos(theta), -np.sin(theta), -np.sin(theta * zrate), 1.0]) * rads)
-        z = normalize(c - np.dot(c2w[:3, :4], np.array([0, 0, -focal, 1.0])))
-        out.append(np.concatenate([viewmatrix(z, up, c), hwf], 1))
-    return out
+    """N poses [N,3,5] on the spiral of load_llff.render_path_spiral (:173-186) around the pose `c2w` [3,5]: centres
+    c2w @ (cos t * rx, -sin t * ry, -sin(t * zrate) * rz, 1), every camera looking at the point `focal` in front of
+    c2w.  All N frames are built at once (`zdelta` is accepted and unused, as in the reference)."""
+    c2w = np.asarray(c2w, dtype=np.float64)
+    rot, origin = c2w[:, :3], c2w[:, 3]
+    t = np.linspace(0.0, 2.0 * np.pi * rots, N + 1)[:-1]
+    rads = np.asarray(list(rads), dtype=np.float64)
+    local = np.stack([np.cos(t), -np.sin(t), -np.sin(t * zrate)], -1) * rads          # [N,3] in the camera frame
+    centres = local @ rot.T + origin
+    target = origin - focal * rot[:, 2]
+    frames_ = look_along(centres - target, up, centres)
+    return np.concatenate([frames_, np.broadcast_to(c2w[:, 4:5], (N, 3, 1))], -1)
 
 
 def interpolate_pose_rows(poses_arr, min_eval_frames):
