@@ -1,7 +1,8 @@
-"""Stage-by-stage diff of the CUDA path vs the CPU oracle on a golden case (diagnostics)."""
+"""Stage-by-stage diff of the CUDA path vs the CPU oracle on a golden case (diagnostics; lives under tests/ because it
+runs the oracle — only tests/, smoke() and bench.py's CPU baseline may)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import nvsr_b200
 from test_oracle_golden import run_oracle_e2e, NAMES
