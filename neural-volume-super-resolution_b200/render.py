@@ -377,22 +377,34 @@ def render_frame(height, width, focal, pose, model_coarse, model_fine, options, 
 _installed = {}
 
 
-def install(train_utils_module, nerf_helpers_module=None):
+def install(train_utils_module, nerf_helpers_module=None, train_nerf_module=None, differentiable=False):
     """Rebind the reference's seams: `train_utils.run_one_iter_of_nerf` (which
     `eval_nerf` resolves through module globals at call time, train_utils.py:311) and, optionally,
-    `nerf_helpers.get_ray_bundle`.  Under autograd the original functions keep running."""
+    `nerf_helpers.get_ray_bundle`.  Under autograd the original functions keep running.
+
+    `train_nerf_module`: also rebind the name `train()` itself uses (`from train_utils import run_one_iter_of_nerf`,
+    train_nerf.py:13, resolved in train_nerf's globals at train_nerf.py:860).  With `differentiable=True` a
+    grad-enabled call then goes to `nvsr_b200.autograd.run_one_iter_of_nerf` (hand-written backward of the gather
+    and compositing stages) instead of the reference's function; unsupported configurations raise, there is no
+    silent fallback.  Default: training stays on the reference's own autograd path."""
     orig = train_utils_module.run_one_iter_of_nerf
     if getattr(orig, "_nvsr_b200", False):
         return
 
     def run_one_iter_of_nerf_b200(*args, **kwargs):
         if torch.is_grad_enabled():
+            if differentiable:
+                from . import autograd
+                return autograd.run_one_iter_of_nerf(*args, **kwargs)
             return orig(*args, **kwargs)
         return run_one_iter_of_nerf(*args, **kwargs)
 
     run_one_iter_of_nerf_b200._nvsr_b200 = True
     _installed[train_utils_module] = orig
     train_utils_module.run_one_iter_of_nerf = run_one_iter_of_nerf_b200
+    if train_nerf_module is not None and getattr(train_nerf_module, "run_one_iter_of_nerf", None) is orig:
+        _installed[train_nerf_module] = orig
+        train_nerf_module.run_one_iter_of_nerf = run_one_iter_of_nerf_b200
     if nerf_helpers_module is not None:
         orig_grb = nerf_helpers_module.get_ray_bundle
 

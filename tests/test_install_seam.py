@@ -63,3 +63,27 @@ def test_no_cpu_fallback():
     import pytest
     with pytest.raises((nvsr_b200.NvsrError, RuntimeError, ValueError, AssertionError)):
         nvsr_b200.get_ray_bundle(4, 4, 1.0, torch.eye(4))
+
+
+def test_install_training_seam(monkeypatch):
+    """train() resolves `run_one_iter_of_nerf` in train_nerf's OWN globals (train_nerf.py:13,860): passing that module
+    rebinds it too; grad-enabled calls stay on the reference unless `differentiable=True`, which routes them to
+    nvsr_b200.autograd (no silent fallback either way)."""
+    from nvsr_b200 import autograd
+    for differentiable in (False, True):
+        tu, nh, calls = _fake_reference_modules()
+        tn = types.ModuleType("train_nerf")
+        tn.run_one_iter_of_nerf = tu.run_one_iter_of_nerf            # `from train_utils import run_one_iter_of_nerf`
+        exec("def train(*a, **k):\n    return run_one_iter_of_nerf(*a, **k)\n", tn.__dict__)
+        ref_run = tu.run_one_iter_of_nerf
+        monkeypatch.setattr(render, "run_one_iter_of_nerf", lambda *a, **k: ("b200",) * 9)
+        monkeypatch.setattr(autograd, "run_one_iter_of_nerf", lambda *a, **k: ("b200_autograd",) * 9)
+        nvsr_b200.install(tu, nh, train_nerf_module=tn, differentiable=differentiable)
+        assert tn.run_one_iter_of_nerf is tu.run_one_iter_of_nerf is not ref_run
+        with torch.enable_grad():
+            assert tn.train(1, mode="train")[0] == ("b200_autograd" if differentiable else "ref")
+        with torch.no_grad():
+            assert tn.train(1, mode="validation")[0] == "b200"
+        nvsr_b200.uninstall(tu)
+        nvsr_b200.uninstall(tn)
+        assert tu.run_one_iter_of_nerf is ref_run and tn.run_one_iter_of_nerf is ref_run
