@@ -22,3 +22,21 @@ def test_oracle_matches_live_reference_bit_exactly():
     assert len(diffs) >= 30
     bad = {k: v for k, v in diffs.items() if v != 0.0}
     assert not bad, bad
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present on this machine")
+def test_autograd_composition_matches_live_reference_training_step():
+    """nvsr_b200.autograd (with the kernels' host-built bodies standing in for the C-ABI) on the reference's OWN
+    TwoDimPlanesModel / FlexibleNeRFModel objects against the reference's run_one_iter_of_nerf(mode='train') +
+    loss.backward(): every parameter gradient within 1e-5 relative, both model families."""
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    res = subprocess.run([sys.executable, os.path.join(HERE, "golden", "check_live_backward.py")], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("LIVE_BACKWARD_JSON ")][-1]
+    d = json.loads(line[len("LIVE_BACKWARD_JSON "):])
+    assert set(d) == {"planes_grad_rel", "planes_rgb_abs", "mip_grad_rel", "mip_rgb_abs"}
+    assert d["planes_grad_rel"] <= 1e-5 and d["mip_grad_rel"] <= 1e-5, d
+    assert d["planes_rgb_abs"] <= 1e-6 and d["mip_rgb_abs"] <= 1e-6, d
