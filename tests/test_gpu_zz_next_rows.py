@@ -16,7 +16,7 @@ import nvsr_b200
 from nvsr_b200 import autograd as A, ops, scene
 from oracle import nvsr_oracle as O
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),     # never-run device code must not be able to hang the suite
               pytest.mark.xfail(strict=False, reason="8f rows: CPU-verified bodies, first GPU run (see module docstring)")]
 DEV = "cuda:0"
 
