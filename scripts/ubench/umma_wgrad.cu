@@ -16,7 +16,8 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I neural-volume-super-resolution_b200/csrc -I include \
 //        -o scripts/ubench/umma_wgrad scripts/ubench/umma_wgrad.cu && scripts/ubench/umma_wgrad [k_in=128] [tiles_per_cta=64]
 //
-// Prints the max relative error against a CPU fp64 reference and the achieved TFLOP/s / GB/s.  A protocol bug traps
+// A second kernel checks the DATA gradient the same way (dgrad_kernel below: the forward WEIGHT image read as an
+// MN-major B operand).  Prints the max relative error against a CPU fp64 reference and the achieved TFLOP/s / GB/s.  A protocol bug traps
 // after 4 s (mbar_wait in common.cuh) instead of hanging the GPU.
 #include <cstdio>
 #include <cstdlib>
@@ -43,9 +44,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;
 }
-// kind::f16, fp16 x fp16 -> fp32, M = 128, N = n, BOTH operands MN-major (bits 15 and 16)
-__host__ __device__ constexpr uint32_t idesc_mn(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16, fp16 x fp16 -> fp32, M = 128, N = n; a_mn / b_mn: operand is MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t idesc_f16(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -105,7 +107,7 @@ wgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ act, in
     };
     load(0);
     if (tiles_per_cta > 1) load(1);
-    const uint32_t idesc = idesc_mn(k_in);
+    const uint32_t idesc = idesc_f16(k_in, true, true);
     for (int t = 0; t < tiles_per_cta; ++t) {
       int s = t & 1;
       mbar_wait(&full[s], (uint32_t)((t >> 1) & 1));
@@ -135,6 +137,66 @@ wgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ act, in
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+// DATA-GRADIENT of one layer with the FORWARD weight image, no transposed packing:
+//   dX[r][k_in] = sum over o of dY[r][o] * W[o][k_in]
+// A = dY tile image, K-major exactly as the forward's layer-0 operand (K = n_out: LBO = 128 rows * 16 B between
+// K-chunks, SBO = 128 B between 8-row groups, + 2 K-chunks = 4096 B per K = 16 step).  B = W as [N = k_in][K = n_out]:
+// the forward weight image [k_in/8][n_out][8] read MN-major (8 consecutive k_in in 16 B, consecutive o 16 B apart,
+// LBO = 128 B, SBO = n_out * 16 B = 2048 B, + 256 B per K = 16 step).  One tile at a time, serialised: a correctness test.
+__global__ void __launch_bounds__(128, 1)
+dgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ w_img, int k_in, int tiles_per_cta,
+             float* __restrict__ dx) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full, mma_done;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t dy_bytes = kRows * kNOut * 2, w_bytes = (uint32_t)kNOut * k_in * 2;
+  uint8_t* dy_s = smem;
+  uint8_t* w_s = smem + dy_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&full, 1), mbar_init(&mma_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = idesc_f16(k_in, false, true);
+  for (int t = 0; t < tiles_per_cta; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x * tiles_per_cta + t;
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&full, dy_bytes + (t == 0 ? w_bytes : 0u));
+      bulk_g2s(dy_s, dy + tile * dy_bytes, dy_bytes, &full);
+      if (t == 0) bulk_g2s(w_s, w_img, w_bytes, &full);
+      mbar_wait(&full, (uint32_t)(t & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint64_t a0 = smem_desc(smem_u32(dy_s), kRows * 16, 128), b0 = smem_desc(smem_u32(w_s), kLbo, (uint32_t)kNOut * 16);
+#pragma unroll
+      for (int ks = 0; ks < kNOut / 16; ++ks)
+        umma_ss(tmem, a0 + (uint64_t)(ks * 256), b0 + (uint64_t)(ks * 16), idesc, ks ? 1u : 0u);
+      umma_commit(&mma_done);
+    }
+    __syncwarp();
+    mbar_wait(&mma_done, (uint32_t)(t & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* out = dx + (tile * kRows + warp * 32 + lane) * k_in;     // TMEM lane = row of the tile
+    for (int c0 = 0; c0 < k_in; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32 && c0 + j < k_in; ++j) out[c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // the accumulator and the dY buffer are free for the next tile
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
@@ -212,5 +274,38 @@ int main(int argc, char** argv) {
   ms /= 10;
   double flop = 2.0 * tiles * kRows * kNOut * k_in, bytes = (double)(dy_elems + act_elems) * 2;
   std::printf("%.3f ms per launch: %.1f TFLOP/s, %.1f GB/s of operand traffic\n", ms, flop / ms * 1e-9, bytes / ms * 1e-6);
+
+  // ---- dgrad: dX = dY @ W with the forward weight image [k_in/8][n_out][8] as an MN-major B operand
+  std::vector<__half> w_img((size_t)kNOut * k_in);
+  std::vector<float> wf((size_t)kNOut * k_in);
+  for (int o = 0; o < kNOut; ++o)
+    for (int i = 0; i < k_in; ++i) {
+      __half h = __float2half(rnd());
+      w_img[((size_t)(i / 8) * kNOut + o) * 8 + i % 8] = h;       // nvsr_pack_weight16's image of W[o][i]
+      wf[(size_t)o * k_in + i] = __half2float(h);
+    }
+  uint8_t* d_w;
+  float* d_dx;
+  const int dg_tiles = 4, dg_ctas = 8;
+  CK(cudaMalloc(&d_w, w_img.size() * 2));
+  CK(cudaMalloc(&d_dx, (size_t)dg_ctas * dg_tiles * kRows * k_in * 4));
+  CK(cudaMemcpy(d_w, w_img.data(), w_img.size() * 2, cudaMemcpyHostToDevice));
+  const size_t smem_d = (size_t)kRows * kNOut * 2 + (size_t)kNOut * k_in * 2 + 1024;
+  CK(cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+  dgrad_kernel<<<dg_ctas, 128, smem_d>>>(d_dy, d_w, k_in, dg_tiles, d_dx);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> dx((size_t)dg_ctas * dg_tiles * kRows * k_in);
+  CK(cudaMemcpy(dx.data(), d_dx, dx.size() * 4, cudaMemcpyDeviceToHost));
+  worst = scale = 0.0;
+  for (int64_t t = 0; t < (int64_t)dg_ctas * dg_tiles; ++t)
+    for (int r = 0; r < kRows; ++r)
+      for (int i = 0; i < k_in; ++i) {
+        double acc = 0.0;
+        for (int o = 0; o < kNOut; ++o) acc += (double)dyf[((size_t)t * kRows + r) * kNOut + o] * (double)wf[(size_t)o * k_in + i];
+        worst = std::fmax(worst, std::fabs((double)dx[((size_t)t * kRows + r) * k_in + i] - acc));
+        scale = std::fmax(scale, std::fabs(acc));
+      }
+  std::printf("dgrad k_in %d: max abs err %.3e (largest |dX| %.3e, relative %.2e) -> %s\n", k_in, worst, scale, worst / scale,
+              worst <= 1e-3 * scale ? "FORWARD WEIGHT IMAGE AS MN-MAJOR B OK" : "MISMATCH");
   return 0;
 }
