@@ -2,6 +2,7 @@
 (host logic only: the numbers are fake, the keys, the headline/companion modes and the launch accounting are real).
 """
 import json
+import os
 import sys
 import types
 
@@ -69,29 +70,47 @@ def _fake_package(state):
     return pkg
 
 
+def _patch_bench(setattr_, setitem, state, argv, elapsed_ms=10.0):
+    """Replace the GPU pieces bench.py touches (package, events, device, pinned memory, clock sampler, CPU baseline)."""
+    pkg = _fake_package(state)
+    setitem(sys.modules, "nvsr_b200", pkg)
+    setitem(sys.modules, "nvsr_b200.ops", pkg.ops)
+    import importlib
+    real_sharding = importlib.import_module("neural-volume-super-resolution_b200.sharding")
+    setitem(sys.modules, "nvsr_b200.sharding", real_sharding)
+    pkg.sharding = real_sharding
+
+    class Ev(_Event):
+        def elapsed_time(self, other):
+            return elapsed_ms
+
+    class Proxy:
+        """the real module with a few names replaced — only bench.py sees it, torch itself stays untouched"""
+
+        def __init__(self, real, **over):
+            self.__dict__.update(_real=real, _over=over)
+
+        def __getattr__(self, k):
+            return self._over[k] if k in self._over else getattr(self._real, k)
+
+    cuda = Proxy(torch.cuda, Event=Ev, synchronize=lambda *a, **k: None, set_device=lambda *a, **k: None)
+    real_empty = torch.empty
+    small = lambda *a, **k: (real_empty(1024, dtype=k.get("dtype")) if a and isinstance(a[0], int) and a[0] > 1 << 20
+                             else real_empty(*a, **k))
+    setattr_(bench, "torch", Proxy(torch, cuda=cuda, device=lambda *a, **k: torch.device("cpu"), empty=small))
+    setattr_(bench, "ClockSampler", _Clock)
+    setattr_(bench, "build_scene", lambda dev: (None, None, "sid", torch.eye(4), 1111.0, None, None))
+    setattr_(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2000.0, "cores": 8, "sample": "fake"})
+    setattr_(bench, "RES", 16)
+    setattr_(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    setattr_(sys, "argv", ["bench.py"] + argv)
+    return pkg
+
+
 @pytest.mark.parametrize("flags,headline_sparse", [([], False), (["--sparse"], True), (["--precision", "fp32"], False)])
 def test_bench_line_contract(monkeypatch, capfd, flags, headline_sparse):
     state = {"sparse": None, "frames": [], "precision": None}
-    pkg = _fake_package(state)
-    monkeypatch.setitem(sys.modules, "nvsr_b200", pkg)
-    monkeypatch.setitem(sys.modules, "nvsr_b200.ops", pkg.ops)
-    import importlib
-    real_sharding = importlib.import_module("neural-volume-super-resolution_b200.sharding")
-    monkeypatch.setitem(sys.modules, "nvsr_b200.sharding", real_sharding)
-    pkg.sharding = real_sharding
-    monkeypatch.setattr(bench, "ClockSampler", _Clock)
-    monkeypatch.setattr(bench, "build_scene", lambda dev: (None, None, "sid", torch.eye(4), 1111.0, None, None))
-    monkeypatch.setattr(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2000.0, "cores": 8, "sample": "fake"})
-    monkeypatch.setattr(bench, "RES", 16)
-    monkeypatch.setattr(torch.cuda, "Event", _Event)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
-    monkeypatch.setattr(torch, "device", lambda *a, **k: "cpu")
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-    real_empty = torch.empty
-    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"})
-                        if a and isinstance(a[0], int) and a[0] > 1 << 20 else real_empty(*a, **k))
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "3"] + flags)
+    _patch_bench(monkeypatch.setattr, monkeypatch.setitem, state, ["--steps", "4", "--warmup", "3"] + flags)
     monkeypatch.setenv("NVSR_BENCH_WATCHDOG_S", "600")
     bench.main()
     out = [l for l in capfd.readouterr().out.splitlines() if l.startswith("{")]
@@ -116,3 +135,41 @@ def test_bench_line_contract(monkeypatch, capfd, flags, headline_sparse):
     assert state["sparse"] is (headline_sparse and not fp32)
     assert state["frames"][:7] == [headline_sparse and not fp32] * 7
     assert fp32 or (True in state["frames"] and False in state["frames"])
+
+
+def _rank_main(rank, world, port, out_dir):
+    """One rank of a 2-rank bench run on the CPU: gloo instead of nccl, per-rank event times that DIFFER (so any
+    decision taken from a rank's own clock would make the ranks issue different numbers of collectives and hang)."""
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), NVSR_BENCH_WATCHDOG_S="120")
+    torch.set_num_threads(1)
+    state = {"sparse": None, "frames": [], "precision": None}
+    setitem = lambda d, k, v: d.__setitem__(k, v)
+    _patch_bench(setattr, setitem, state, ["--gpus", str(world), "--steps", "3", "--warmup", "3"], elapsed_ms=4.0 + 3.0 * rank)
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, device_id=None, **k: real_init("gloo", rank=rank, world_size=world)
+    fd = os.open(os.path.join(out_dir, "rank%d.out" % rank), os.O_WRONLY | os.O_CREAT)
+    os.dup2(fd, 1)
+    bench.main()
+    with open(os.path.join(out_dir, "rank%d.frames" % rank), "w") as f:
+        f.write(str(len(state["frames"])))
+
+
+def test_two_rank_bench_flow_issues_the_same_collectives_on_every_rank(tmp_path):
+    """bench.py under torchrun, world size 2, on the CPU (gloo): the short timed region forces the clock-sampling
+    fallback, whose frame count must come from the all-reduced step time — with a rank-local count the ranks would issue
+    different numbers of all_gathers and this test would die on the watchdog instead of finishing."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    lines = [l for l in open(tmp_path / "rank0.out").read().splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and not [l for l in open(tmp_path / "rank1.out").read().splitlines() if l.startswith("{")]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["config"]["sharding"] == "2 row bands" and d["cpu_baseline"] is None
+    assert d["ms_per_step"] == pytest.approx(7.0 / 3)          # MAX over ranks of the per-rank event time / steps
+    assert "timed region shorter" in d["clocks"].get("note", "")   # the fallback path ran
+    assert open(tmp_path / "rank0.frames").read() == open(tmp_path / "rank1.frames").read()
