@@ -157,7 +157,8 @@ def run_reference(args, rank, guard):
         "unit": "rays/s", "samples_per_s": r["rays_per_s"] * EVALS_PER_RAY, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2_800x800_64+128_planes200 (bounded ray sample per step)", "rays_per_step": r["rays"]},
+        "config": {"workload": "cfg2_800x800_64+128_planes200", "rays_per_step": r["rays"],
+                   "sample": "each step renders a bounded ray sample of the workload's frame (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

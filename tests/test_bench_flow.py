@@ -173,3 +173,24 @@ def test_two_rank_bench_flow_issues_the_same_collectives_on_every_rank(tmp_path)
     assert d["ms_per_step"] == pytest.approx(7.0 / 3)          # MAX over ranks of the per-rank event time / steps
     assert "timed region shorter" in d["clocks"].get("note", "")   # the fallback path ran
     assert open(tmp_path / "rank0.frames").read() == open(tmp_path / "rank1.frames").read()
+
+
+def test_reference_arm_line_contract(monkeypatch, capfd):
+    """`bench.py --impl reference`: rank 0 prints one line with impl / cpu_baseline / zero-byte e2e on the b200 arm's
+    metric and unit; other ranks print nothing and return."""
+    monkeypatch.setattr(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2345.0, "ms_per_step": 982.0, "rays": 2304, "cores": 24,
+                                                               "sample": "fake lattice"})
+    for rank, expect in ((0, 1), (1, 0)):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("WORLD_SIZE", "2")
+        monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"])
+        bench.main()
+        out = [l for l in capfd.readouterr().out.splitlines() if l.startswith("{")]
+        assert len(out) == expect
+        if expect:
+            d = json.loads(out[0])
+            assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] == 2345.0 and d["higher_is_better"] is True
+            assert d["metric"].startswith("rays/s (800x800 render") and d["config"]["workload"] == "cfg2_800x800_64+128_planes200"
+            assert d["cpu_baseline"] == {"value": 2345.0, "unit": "rays/s", "cores": 24, "kind": "port", "sample": "fake lattice"}
+            assert d["e2e"] == {"value": 2345.0, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+            assert d["n_gpus"] == 2 and d["steps"] == 2 and d["gpu_launches"] == 0
