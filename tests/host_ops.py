@@ -44,7 +44,9 @@ def standins(hc):
             feats.append(F.grid_sample(img, grid, mode="bilinear", align_corners=True, padding_mode="border")[0, :, :, 0].t())
         return torch.cat(feats, 1).contiguous(), torch.stack(feats, 0).mean(0).contiguous(), z_in
 
-    def sample_gather_bwd(ro, rd, z, packed, gp, gm, acc):
+    def sample_gather_bwd(ro, rd, z, packed, gp, gm, acc=None):
+        if acc is None:
+            acc = [torch.zeros(tuple(p.shape[:2]) + (packed.channels,)) for p in packed.planes]
         n, S = z.shape
         rh = (C.c_int * 3)(*[a.shape[0] for a in acc])
         rw = (C.c_int * 3)(*[a.shape[1] for a in acc])
