@@ -142,7 +142,10 @@ def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
     scene.check_supported_planes_model(model)
     model.set_cur_scene_id(scene_id)
     geom = Geometry.of_model(model, scene_id)
-    planes = [model.planes(d, super_resolve=False) for d in range(4)]
+    # models.py:296-310: a position plane is read through the SR model when the scene is an SR scene of this model —
+    # the gather's gradient then flows on into the SR network and the LR planes through torch autograd; the
+    # view-direction plane is never super-resolved (models.py:312-326)
+    planes = [model.planes(d, super_resolve=scene._should_sr(model, d)) for d in range(3)] + [model.planes(3, super_resolve=False)]
     n, S = z.shape
     feat_p, feat_m = TriPlaneGather.apply(planes[0], planes[1], planes[2], ro, rd, z, geom)
     vfeat = ViewdirGather.apply(planes[3], viewdirs, geom)

@@ -331,3 +331,48 @@ def test_mip_train_step_matches_oracle_autograd(host_ops):
             _close(a, b, rel=5e-4)
             n_checked += 1
     assert n_checked >= 16
+
+
+def test_sr_scene_gradients_reach_the_sr_network(host_ops):
+    """Super-resolution configuration (BASELINE config 3a; models.py:296-310): the fine model reads its position planes
+    through an SR network.  In training the gather's plane gradient must flow on into that network and into the LR planes
+    (torch autograd behind the TriPlaneGather Function) — checked against autograd of the oracle with a small
+    differentiable SR module."""
+    from nvsr_b200 import autograd as A
+
+    class TinySR(torch.nn.Module):                       # differentiable stand-in of PlanesSR.forward(plane_name)
+        def __init__(self, planes, channels, scale):
+            super().__init__()
+            self.planes, self.scale = planes, scale
+            self.conv = torch.nn.Conv2d(channels, channels, 3, padding=1)
+
+        def forward(self, name):
+            up = torch.nn.functional.interpolate(self.planes[name], scale_factor=self.scale, mode="bilinear", align_corners=True)
+            return up + 0.1 * self.conv(up)
+
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=6, view_res=5, channels=8, seed=2, sr_scale=2)
+    torch.manual_seed(0)
+    mf.assign_SR_model(TinySR(mf.planes_, 8, 2))
+    g = torch.Generator().manual_seed(3)
+    n, S = 17, 6
+    ro = torch.randn(n, 3, generator=g) * 0.2
+    rd = torch.randn(n, 3, generator=g)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    z = torch.sort(0.3 + 2.0 * torch.rand(n, S, generator=g), -1).values
+    gout = torch.randn(n, S, 4, generator=g)
+    params = list(mf.planes_.values()) + list(mf.SR_model.conv.parameters())
+
+    def grads(rf):
+        for p in params:
+            p.grad = None
+        (rf * gout).sum().backward()
+        return [p.grad.clone() for p in params]
+
+    got = grads(A.planes_model_forward(mf, sid, ro, rd, z, vd))
+    mf.set_cur_scene_id(sid)
+    pts = ro[:, None, :] + rd[:, None, :] * z[..., None]
+    x6 = torch.cat([pts, vd[:, None, :].expand(pts.shape)], -1).reshape(-1, 6)
+    want = grads(O.planes_model_forward(mf, x6).reshape(n, S, 4))
+    assert len(got) == 6 and all(float(w.abs().max()) > 0 for w in want)   # 3 LR planes + view plane + conv weight/bias
+    for a, b in zip(got, want):
+        _close(a, b, rel=2e-4)
