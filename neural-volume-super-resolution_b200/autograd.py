@@ -137,9 +137,13 @@ def volume_render_radiance_field(radiance_field, depth_values, ray_directions, r
 def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
     """TwoDimPlanesModel.forward (models.py:381-421) for the points ro + rd*z of n rays x S samples with the gather
     done by the Functions above and the decoder by the model's own nn.Linear layers under torch autograd.
-    Returns radiance_field [n,S,4].  Gradients reach the model's planes_ parameters and decoder weights."""
+    Returns radiance_field [n,S,4].  Gradients reach the model's planes_ parameters and decoder weights.
+    Not reproduced: the region-of-interest SR of a TRAINING SR model (models.py:277-280 crops the SR input to the
+    footprint of the batch; here the whole plane is super-resolved, which differs near the crop borders)."""
     from . import scene
     scene.check_supported_planes_model(model)
+    if getattr(model, "plane_stats", False) and model.training:
+        raise NotImplementedError("nvsr_b200.autograd: plane_stats coverage bookkeeping (models.py:304-305) is not reproduced")
     model.set_cur_scene_id(scene_id)
     geom = Geometry.of_model(model, scene_id)
     # models.py:296-310: a position plane is read through the SR model when the scene is an SR scene of this model —
@@ -174,6 +178,14 @@ def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, opti
         raise _lib.NvsrError("batch_rays must be CUDA tensors: nvsr_b200 has no CPU path")
     return _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms,
                          encode_position_fn)
+
+
+def _coarse_context(model_coarse):
+    """train_utils.py:88: the whole coarse pass runs inside `model_coarse.optional_no_grad()` — `torch.no_grad` when
+    the decoder is not being trained (train_nerf.py:560), a null context otherwise (train_nerf.py:349)."""
+    import contextlib
+    ctx = getattr(model_coarse, "optional_no_grad", None)
+    return ctx() if ctx is not None else contextlib.nullcontext()
 
 
 def mip_model_forward(model, xyz_feat, dir_feat):
@@ -226,8 +238,9 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
             dirs = denc[:, None, :].expand(n, S, denc.shape[-1]).reshape(n * S, -1)
         return mip_model_forward(model, enc, dirs).reshape(n, S, 4)
 
-    rf = radiance(model_coarse, z)
-    rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc), mip=True)
+    with _coarse_context(model_coarse):
+        rf = radiance(model_coarse, z)
+        rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc), mip=True)
     rgb_f = disp_f = acc_f = None
     if Nf > 0:
         with torch.no_grad():
@@ -284,8 +297,9 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
             return None
         return randoms[name] if name in randoms else torch.randn((n, S))
 
-    rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd)
-    rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc))
+    with _coarse_context(model_coarse):
+        rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd)
+        rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc))
     rgb_f = disp_f = acc_f = None
     if Nf > 0:
         with torch.no_grad():    # z_samples.detach() (train_utils.py:153)

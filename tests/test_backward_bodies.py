@@ -376,3 +376,20 @@ def test_sr_scene_gradients_reach_the_sr_network(host_ops):
     assert len(got) == 6 and all(float(w.abs().max()) > 0 for w in want)   # 3 LR planes + view plane + conv weight/bias
     for a, b in zip(got, want):
         _close(a, b, rel=2e-4)
+
+
+def test_coarse_pass_honours_optional_no_grad(host_ops):
+    """train_utils.py:88 / train_nerf.py:560: with `model_coarse.optional_no_grad = torch.no_grad` the coarse maps carry
+    no graph (the coarse decoder receives no gradient), the fine pass still does."""
+    from nvsr_b200 import autograd as A
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=8, view_res=4, channels=8, seed=5)
+    g = torch.Generator().manual_seed(1)
+    batch = torch.stack([torch.randn(9, 3, generator=g) * 0.2, torch.randn(9, 3, generator=g)], 0)
+    opt, scfg = scene.render_options(6, 4), scene.scene_cfg(0.3, 2.3, True)
+    mc.optional_no_grad = torch.no_grad
+    out = A._run_one_iter(3, 3, 4.0, mc, mf, batch, opt, sid, "train", scfg, None)
+    assert not out[0].requires_grad and out[3].requires_grad
+    out[3].sum().backward()
+    assert all(p.grad is None for p in mc.density_dec.parameters()) and any(p.grad is not None for p in mf.rgb_dec.parameters())
+    mc.optional_no_grad = __import__("contextlib").nullcontext
+    assert A._run_one_iter(3, 3, 4.0, mc, mf, batch, opt, sid, "train", scfg, None)[0].requires_grad
