@@ -21,6 +21,17 @@ from . import _lib, ops
 from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
 
 
+_state = {"fast_frozen_coarse": False}
+
+
+def set_fast_frozen_coarse(on):
+    """Opt-in: while the decoder is frozen (`model_coarse.optional_no_grad is torch.no_grad`, train_nerf.py:560 — the
+    phase in which only the SR model trains) the gradient-free coarse pass runs on the forward kernels in the
+    precision of `set_precision()` instead of the fp32 gather + torch decoder.  Off by default: in the 16-bit modes
+    the coarse maps and the resampled depths then carry the forward path's stated tolerance."""
+    _state["fast_frozen_coarse"] = bool(on)
+
+
 class Geometry:
     """What the gather needs besides the plane values: box, projection matrices, view-angle box (models.py:261-268,
     :495-497) — `ops.PackedPlanes` without plane images."""
@@ -278,18 +289,21 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
         t = randoms[name] if name in randoms else torch.rand(shape)     # the reference draws on the CPU
         return t.to(device=dev, dtype=torch.float32)
 
-    # stratified depths (train_utils.py:95-109); data, not parameters: no gradient
-    t_vals = torch.linspace(0.0, 1.0, Nc).to(dev)
-    if not cfg.lindisp:
-        z = near * (1.0 - t_vals) + far * t_vals
-    else:
-        z = 1.0 / (1.0 / near * (1.0 - t_vals) + 1.0 / far * t_vals)
-    z = z.expand(n, Nc)
-    if cfg.perturb:
-        mids = 0.5 * (z[..., 1:] + z[..., :-1])
-        upper, lower = torch.cat((mids, z[..., -1:]), -1), torch.cat((z[..., :1], mids), -1)
-        z = lower + (upper - lower) * draw("t_rand", (n, Nc))
-    z = z.contiguous()
+    def coarse_depths():
+        # stratified depths (train_utils.py:95-109); data, not parameters: no gradient
+        t_vals = torch.linspace(0.0, 1.0, Nc).to(dev)
+        if not cfg.lindisp:
+            z = near * (1.0 - t_vals) + far * t_vals
+        else:
+            z = 1.0 / (1.0 / near * (1.0 - t_vals) + 1.0 / far * t_vals)
+        z = z.expand(n, Nc)
+        if cfg.perturb:
+            mids = 0.5 * (z[..., 1:] + z[..., :-1])
+            upper, lower = torch.cat((mids, z[..., -1:]), -1), torch.cat((z[..., :1], mids), -1)
+            z = lower + (upper - lower) * draw("t_rand", (n, Nc))
+        z = z.contiguous()
+        return z
+
     std = float(cfg.radiance_field_noise_std)
 
     def noise_of(name, S):
@@ -297,11 +311,27 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
             return None
         return randoms[name] if name in randoms else torch.randn((n, S))
 
-    with _coarse_context(model_coarse):
-        rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd)
-        rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc))
+    z_f = None
+    if _state["fast_frozen_coarse"] and getattr(model_coarse, "optional_no_grad", None) is torch.no_grad:
+        # decoder frozen (train_nerf.py:560): the coarse pass carries no gradient at all, so it can run on the forward
+        # kernels (16-bit gather + tcgen05 decoder + compositing fused with sample_pdf and the sort-merge)
+        from . import render
+        with torch.no_grad():
+            pc = render._planes_pass(model_coarse, scene_id, render._state["precision"])
+            rnd = {k: v.to(dev) for k, v in randoms.items() if k in ("t_rand", "u", "noise_c") and torch.is_tensor(v)}
+            co, _ = render._render_planes_chunk(pc, None, ro, rd, vd, near, far, cfg, rnd, None, coarse_only=True)
+        rgb_c, disp_c, acc_c = co["rgb"], co["disp"], co["acc"]
+        z_f = co.get("z_merged")
+    else:
+        z = coarse_depths()
+        with _coarse_context(model_coarse):
+            rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd)
+            rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc))
     rgb_f = disp_f = acc_f = None
-    if Nf > 0:
+    if Nf > 0 and z_f is not None:
+        rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd)
+        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background, noise_of("noise_f", Nc + Nf))
+    elif Nf > 0:
         with torch.no_grad():    # z_samples.detach() (train_utils.py:153)
             mid = 0.5 * (z[..., 1:] + z[..., :-1])
             u = randoms.get("u")

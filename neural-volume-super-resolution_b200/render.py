@@ -168,7 +168,9 @@ class _PlanesPass:
         return raw, z
 
 
-def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
+def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace, coarse_only=False):
+    """`coarse_only`: stop after the coarse pass (maps + merged depths in the returned dict) — the frozen-decoder
+    training path of nvsr_b200.autograd renders its gradient-free coarse pass through these kernels."""
     n = ro.shape[0]
     dev = ro.device
     Nc, Nf = cfg.num_coarse, cfg.num_fine
@@ -190,7 +192,7 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace):
         trace.update(z_coarse=z, raw_coarse=ops.raw_to_nsc(raw, n, Nc, pc.rows), weights_coarse=co["weights"],
                      depth_coarse=co["depth"])
     fo = None
-    if Nf > 0:
+    if Nf > 0 and not coarse_only:
         zf = randoms["z_fine"] if "z_fine" in randoms else co["z_merged"]   # test hook: teacher-forced depths
         # fine model may read different (super-resolved) planes but shares the view-direction plane
         vfeat_f = vfeat if pf.planes.vplane is pc.planes.vplane else ops.viewdir_gather(vd, pf.planes)

@@ -165,6 +165,34 @@ def test_mip_train_step_gradients_match_oracle_autograd():
             _close(a.grad, b.grad, 5e-3)
 
 
+def test_frozen_decoder_coarse_pass_on_the_forward_kernels():
+    """Opt-in `autograd.set_fast_frozen_coarse(True)`: with the decoder frozen (`optional_no_grad = torch.no_grad`,
+    train_nerf.py:560) the gradient-free coarse pass runs on the forward kernels.  In fp32 mode it must agree with the
+    default route to the forward path's 1e-3 contract, and the fine pass keeps its graph."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=48, view_res=12, seed=1, device=DEV)
+    mc.optional_no_grad = torch.no_grad
+    pose, focal = scene.blender_camera(24)
+    opt, scfg = scene.render_options(32, 32), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(24, 24, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    prec = nvsr_b200.get_precision()
+    try:
+        nvsr_b200.set_precision("fp32")
+        slow = A.run_one_iter_of_nerf(24, 24, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg)
+        A.set_fast_frozen_coarse(True)
+        fast = A.run_one_iter_of_nerf(24, 24, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg)
+    finally:
+        A.set_fast_frozen_coarse(False)
+        nvsr_b200.set_precision(prec)
+    assert not fast[0].requires_grad and fast[3].requires_grad
+    H.assert_close(fast[0], slow[0].detach(), 1e-3, what="rgb_coarse")
+    H.assert_close(fast[2], slow[2].detach(), 1e-3, what="acc_coarse")
+    assert float((fast[3].detach() - slow[3].detach()).abs().mean()) < 1e-3     # fine maps: resampling is ill-conditioned per ray
+    fast[3].sum().backward()
+    assert any(p.grad is not None for p in mf.rgb_dec.parameters())
+
+
 # ---- the other §8f rows written at the end of round 1 (frame sink, plane store): kept here so that a fault in
 # never-run device code cannot disturb the forward path's tests, which sort before this file
 def test_gpu_frame_sink_matches_write_image(tmp_path):
