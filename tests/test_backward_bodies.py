@@ -393,3 +393,39 @@ def test_coarse_pass_honours_optional_no_grad(host_ops):
     assert all(p.grad is None for p in mc.density_dec.parameters()) and any(p.grad is not None for p in mf.rgb_dec.parameters())
     mc.optional_no_grad = __import__("contextlib").nullcontext
     assert A._run_one_iter(3, 3, 4.0, mc, mf, batch, opt, sid, "train", scfg, None)[0].requires_grad
+
+
+def test_fast_frozen_coarse_route_plumbing(host_ops, monkeypatch):
+    """Control flow of `autograd.set_fast_frozen_coarse(True)` on the CPU: the forward-kernel chunk renderer is replaced by
+    a stand-in that computes the same coarse pass with the oracle, so the fast route must reproduce the default route
+    exactly (same draws handed over, merged depths used for the fine pass, coarse maps without a graph)."""
+    from nvsr_b200 import autograd as A, render
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=8, view_res=4, channels=8, seed=6)
+    mc.optional_no_grad = torch.no_grad
+    g = torch.Generator().manual_seed(2)
+    n, Nc, Nf = 11, 7, 5
+    batch = torch.stack([torch.randn(n, 3, generator=g) * 0.2, torch.randn(n, 3, generator=g)], 0)
+    opt, scfg = scene.render_options(Nc, Nf, perturb=True, noise_std=0.3, white_background=True), scene.scene_cfg(0.3, 2.3, True)
+    rnd = {"t_rand": torch.rand(n, Nc, generator=g), "u": torch.rand(n, Nf, generator=g),
+           "noise_c": torch.randn(n, Nc, generator=g), "noise_f": torch.randn(n, Nc + Nf, generator=g)}
+    seen = {}
+
+    def fake_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace, coarse_only=False):
+        assert pc == "pc" and pf is None and coarse_only and set(randoms) == {"t_rand", "u", "noise_c"}
+        seen["called"] = True
+        tr = {}
+        rays = torch.cat([ro, rd, torch.full((n, 1), near), torch.full((n, 1), far), vd], -1)
+        out = O.predict_and_render_radiance(rays, mc, mf, opt, sid, mode="train", randoms=dict(randoms, noise_f=rnd["noise_f"]), trace=tr)
+        return {"rgb": out[0], "disp": out[1], "acc": out[2], "z_merged": tr["z_fine"]}, None
+
+    monkeypatch.setattr(render, "_planes_pass", lambda *a, **k: "pc")
+    monkeypatch.setattr(render, "_render_planes_chunk", fake_chunk)
+    slow = A._run_one_iter(3, 3, 4.0, mc, mf, batch, opt, sid, "train", scfg, rnd)
+    A.set_fast_frozen_coarse(True)
+    try:
+        fast = A._run_one_iter(3, 3, 4.0, mc, mf, batch, opt, sid, "train", scfg, rnd)
+    finally:
+        A.set_fast_frozen_coarse(False)
+    assert seen.get("called") and not fast[0].requires_grad and fast[3].requires_grad
+    for j in (0, 2, 3, 5):
+        assert torch.allclose(fast[j], slow[j], atol=2e-6), j
