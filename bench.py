@@ -260,17 +260,28 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    per_step = {}
+
+    def timed(fn, steps, tag=None):
+        """K steps bracketed by barrier + synchronize, device time from CUDA events, MAX over ranks.  With `tag`, an
+        event is also recorded after every step (no synchronisation added) and this rank's per-step median / min are
+        kept in per_step[tag] (SURVEY.md §8d asks for median + min next to the mean)."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1 if tag else 2)]
+        ev[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            if tag:
+                ev[i + 1].record()
+        if not tag:
+            ev[1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([ev[0].elapsed_time(ev[-1])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if tag:
+            each = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+            per_step[tag] = {"median_ms": statistics.median(each), "min_ms": each[0], "max_ms": each[-1], "rank": rank}
         return float(ms) / steps
 
     with torch.no_grad():
@@ -279,7 +290,7 @@ def main():
         clocks = ClockSampler(local)
         clocks.start()
         ops.LAUNCHES.clear()
-        ms_dev = timed(frame_device, args.steps)
+        ms_dev = timed(frame_device, args.steps, tag="device")
         launches = sum(ops.LAUNCHES.values())
         clk = clocks.stop()
         # A short timed region (many GPUs, few steps) gives nvidia-smi too few samples: then the clocks are sampled
@@ -392,6 +403,7 @@ def main():
             # rgb chain is evaluated only on `rgb_rows_evaluated` of them (the others have weight exactly 0)
             "samples_per_s": rays * EVALS_PER_RAY / (ms_dev * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "per_step": per_step.get("device"),   # rank 0's own per-frame median / min / max over the timed steps
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",

@@ -120,6 +120,8 @@ def test_bench_line_contract(monkeypatch, capfd, flags, headline_sparse):
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "kernels", "cpu_baseline"):
         assert k in d, k
     assert d["config"]["sparse_rgb"] is headline_sparse and d["steps"] == 4 and d["n_gpus"] == 1
+    assert d["per_step"] == {"median_ms": 10.0, "min_ms": 10.0, "max_ms": 10.0, "rank": 0}
+    assert d["ms_per_step"] == pytest.approx(10.0 / 4)
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     fp32 = "fp32" in flags
     comp = "dense" if headline_sparse else "sparse"
