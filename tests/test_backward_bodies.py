@@ -429,3 +429,23 @@ def test_fast_frozen_coarse_route_plumbing(host_ops, monkeypatch):
     assert seen.get("called") and not fast[0].requires_grad and fast[3].requires_grad
     for j in (0, 2, 3, 5):
         assert torch.allclose(fast[j], slow[j], atol=2e-6), j
+
+
+@pytest.mark.parametrize("n,S,mip", [(1, 1, False), (3, 2, False), (2, 1, True), (0, 5, False)])
+def test_composite_bwd_body_degenerate_sizes(hc, n, S, mip):
+    """A single sample per ray (only the 1e10 tail interval / one mip interval), two samples, and an empty ray set."""
+    g = torch.Generator().manual_seed(n * 10 + S)
+    raw = torch.randn(n, S, 4, generator=g)
+    raw[..., 3] = raw[..., 3].abs() * 0.3 + 0.05 if n else raw[..., 3]
+    z = torch.sort(2.0 + torch.rand(n, S + int(mip), generator=g), -1).values
+    rd = torch.randn(n, 3, generator=g)
+    g_rgb = torch.randn(n, 3, generator=g)
+    d_raw = torch.full((n, S, 4), 7.0)
+    hc.hc_composite_bwd(_p(raw), _p(z), _p(rd), None, C.c_int64(n), S, 0, int(mip), _p(g_rgb), None, None, None, _p(d_raw))
+    if n == 0:
+        return
+    raw_req = raw.clone().requires_grad_(True)
+    rgb = O.volume_render_radiance_field(raw_req, z, rd, 0.0, False, mip_nerf=mip)[0]
+    (rgb * g_rgb).sum().backward()
+    _close(d_raw[..., :3], raw_req.grad[..., :3])
+    assert torch.allclose(d_raw[..., 3], raw_req.grad[..., 3], rtol=1e-4, atol=1e-7 * float(raw_req.grad.abs().max() + 1))
