@@ -94,3 +94,67 @@ def test_camera_paths_match_reference_vectors():
 def test_to_uint8_refuses_cpu_tensors():
     with pytest.raises(nvsr_b200.NvsrError):
         frames.to_uint8(torch.zeros(2, 2, 3))
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+def test_frame_sink_order_and_buffer_reuse(hc, monkeypatch):
+    """FrameSink's host logic with the CUDA pieces replaced by stand-ins: frames reach the writer in submission order,
+    exactly once, with the bytes write_image would produce; at most `depth` copies are in flight; pinned buffers are
+    recycled only after their frame has been handed over."""
+    import contextlib
+
+    class Ev:
+        def __init__(self, *a, **k):
+            self.done = False
+
+        def record(self):
+            pending.append(self)
+
+        def query(self):
+            return self.done
+
+        def synchronize(self):
+            self.done = True
+
+    class Stream:
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_stream(self, other):
+            pass
+
+    pending, allocated = [], []
+
+    def to_u8(frame):
+        x = frame.contiguous()
+        out = torch.empty(x.shape, dtype=torch.uint8)
+        hc.hc_frame_to_u8(C.c_void_p(x.data_ptr()), C.c_int64(x.numel()), C.c_void_p(out.data_ptr()))
+        return out
+
+    real_pin = torch.Tensor.pin_memory
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: allocated.append(self) or self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "Stream", Stream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(frames, "to_uint8", to_u8)
+    got = []
+    sink = frames.FrameSink(writer=lambda i, arr: got.append((i, arr)), depth=2)
+    g = torch.Generator().manual_seed(0)
+    imgs = [torch.rand(6, 5, 3, generator=g) * 1.4 - 0.2 for _ in range(7)]
+    for k, im in enumerate(imgs):
+        assert sink.submit(im) == k
+        assert len(sink._slots) <= 2                              # never more than `depth` copies in flight
+        if k == 3:
+            for e in pending:                                     # the copies issued so far complete "asynchronously"
+                e.done = True
+    sink.flush()
+    assert [i for i, _ in got] == list(range(7)) and not sink._slots
+    for (i, arr), im in zip(got, imgs):
+        assert np.array_equal(arr, reference_u8(im))
+    assert len(allocated) <= 3                                    # buffers are recycled, not allocated per frame
+    # default writer keeps the frames
+    keep = frames.FrameSink()
+    keep.submit(imgs[0])
+    assert len(keep.flush()) == 1 and np.array_equal(keep.frames[0], reference_u8(imgs[0]))
