@@ -11,5 +11,5 @@ timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zz
 timeout 600 python scripts/bench_train_step.py --steps 20 > gpurun_out/train_step.json 2> gpurun_out/train_step.err
 timeout 600 python scripts/render_video.py --out /tmp/nvsr_video --scenes 2 --frames 8 --res 400 > gpurun_out/render_video.json 2> gpurun_out/render_video.err
 timeout 600 python scripts/bench_torch_frame.py --frames 2 > gpurun_out/torch_frame.json 2> gpurun_out/torch_frame.err; cat gpurun_out/torch_frame.json
-(nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I neural-volume-super-resolution_b200/csrc -I include -o /tmp/umma_wgrad scripts/ubench/umma_wgrad.cu && for k in 48 128 144; do timeout 60 /tmp/umma_wgrad $k 64; done) > gpurun_out/umma_wgrad.log 2>&1
+(nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I neural-volume-super-resolution_b200/csrc -I include -o /tmp/umma_wgrad scripts/ubench/umma_wgrad.cu && for k in 48 128 144; do timeout 60 /tmp/umma_wgrad $k 64 0; done; timeout 60 /tmp/umma_wgrad 128 64 1) > gpurun_out/umma_wgrad.log 2>&1
 cat gpurun_out/umma_wgrad.log; tail -5 gpurun_out/next_rows_tests.log; cat gpurun_out/train_step.json gpurun_out/render_video.json

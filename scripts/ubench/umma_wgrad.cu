@@ -14,7 +14,7 @@
 // per 16 rows (descriptor start + 256 B), 8 steps per 128-row tile, the accumulator stays in TMEM over all tiles.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I neural-volume-super-resolution_b200/csrc -I include \
-//        -o scripts/ubench/umma_wgrad scripts/ubench/umma_wgrad.cu && scripts/ubench/umma_wgrad [k_in=128] [tiles_per_cta=64]
+//        -o scripts/ubench/umma_wgrad scripts/ubench/umma_wgrad.cu && scripts/ubench/umma_wgrad [k_in=128] [tiles_per_cta=64] [swap_lbo_sbo=0]
 //
 // A second kernel checks the DATA gradient the same way (dgrad_kernel below: the forward WEIGHT image read as an
 // MN-major B operand).  Prints the max relative error against a CPU fp64 reference and the achieved TFLOP/s / GB/s.  A protocol bug traps
@@ -76,7 +76,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // test, not the final schedule): two stages, stage s is refilled once the MMAs that read it have committed.
 __global__ void __launch_bounds__(128, 1)
 wgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ act, int k_in, int tiles_per_cta,
-             float* __restrict__ dw_partial) {
+             float* __restrict__ dw_partial, uint32_t mn_lbo, uint32_t mn_sbo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2], done;
   __shared__ uint32_t tmem_slot;
@@ -112,7 +112,7 @@ wgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ act, in
       int s = t & 1;
       mbar_wait(&full[s], (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint64_t a0 = smem_desc(smem_u32(dy_s[s]), kLbo, kSbo), b0 = smem_desc(smem_u32(act_s[s]), kLbo, kSbo);
+      uint64_t a0 = smem_desc(smem_u32(dy_s[s]), mn_lbo, mn_sbo), b0 = smem_desc(smem_u32(act_s[s]), mn_lbo, mn_sbo);
 #pragma unroll
       for (int ks = 0; ks < kRows / 16; ++ks)   // 16 rows per MMA: descriptor start address + 256 B (>> 4 = 16)
         umma_ss(tmem, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, (t | ks) ? 1u : 0u);
@@ -148,7 +148,7 @@ wgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ act, in
 // LBO = 128 B, SBO = n_out * 16 B = 2048 B, + 256 B per K = 16 step).  One tile at a time, serialised: a correctness test.
 __global__ void __launch_bounds__(128, 1)
 dgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ w_img, int k_in, int tiles_per_cta,
-             float* __restrict__ dx) {
+             float* __restrict__ dx, uint32_t mn_lbo, uint32_t mn_sbo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full, mma_done;
   __shared__ uint32_t tmem_slot;
@@ -177,7 +177,7 @@ dgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ w_img, 
       if (t == 0) bulk_g2s(w_s, w_img, w_bytes, &full);
       mbar_wait(&full, (uint32_t)(t & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint64_t a0 = smem_desc(smem_u32(dy_s), kRows * 16, 128), b0 = smem_desc(smem_u32(w_s), kLbo, (uint32_t)kNOut * 16);
+      uint64_t a0 = smem_desc(smem_u32(dy_s), kRows * 16, 128), b0 = smem_desc(smem_u32(w_s), mn_lbo, mn_sbo);
 #pragma unroll
       for (int ks = 0; ks < kNOut / 16; ++ks)
         umma_ss(tmem, a0 + (uint64_t)(ks * 256), b0 + (uint64_t)(ks * 16), idesc, ks ? 1u : 0u);
@@ -214,6 +214,8 @@ dgrad_kernel(const uint8_t* __restrict__ dy, const uint8_t* __restrict__ w_img, 
 int main(int argc, char** argv) {
   const int k_in = argc > 1 ? std::atoi(argv[1]) : 128;          // 48 | 128 | 144 (N % 16 == 0, <= 256)
   const int tiles_per_cta = argc > 2 ? std::atoi(argv[2]) : 64;
+  const bool swap = argc > 3 && std::atoi(argv[3]) != 0;   // 1: exchange LBO and SBO of the MN-major descriptors
+  const uint32_t mn_lbo = swap ? kSbo : kLbo, mn_sbo = swap ? kLbo : kSbo;
   const int ctas = 148;
   if (k_in % 16 || k_in > 256 || k_in < 16) return std::printf("k_in must be a multiple of 16 in [16, 256]\n"), 1;
   const int64_t tiles = (int64_t)ctas * tiles_per_cta;
@@ -242,7 +244,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_act, act.data(), act_elems * 2, cudaMemcpyHostToDevice));
   const size_t smem = 2 * ((size_t)kRows * kNOut * 2 + (size_t)kRows * k_in * 2) + 1024;
   CK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_kernel<<<ctas, 128, smem>>>(d_dy, d_act, k_in, tiles_per_cta, d_dw);
+  wgrad_kernel<<<ctas, 128, smem>>>(d_dy, d_act, k_in, tiles_per_cta, d_dw, mn_lbo, mn_sbo);
   CK(cudaDeviceSynchronize());
   std::vector<float> dw((size_t)ctas * kNOut * k_in);
   CK(cudaMemcpy(dw.data(), d_dw, dw.size() * 4, cudaMemcpyDeviceToHost));
@@ -260,13 +262,13 @@ int main(int argc, char** argv) {
         scale = std::fmax(scale, std::fabs(acc));
       }
   }
-  std::printf("k_in %d, %d tiles per CTA: max abs err %.3e (largest |dW| %.3e, relative %.2e) -> %s\n", k_in, tiles_per_cta, worst,
+  std::printf("[MN-major LBO %u SBO %u] k_in %d, %d tiles per CTA: max abs err %.3e (largest |dW| %.3e, relative %.2e) -> %s\n", mn_lbo, mn_sbo, k_in, tiles_per_cta, worst,
               scale, worst / scale, worst <= 1e-3 * scale ? "MN-MAJOR TILE IMAGES OK" : "MISMATCH");
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < 10; ++i) wgrad_kernel<<<ctas, 128, smem>>>(d_dy, d_act, k_in, tiles_per_cta, d_dw);
+  for (int i = 0; i < 10; ++i) wgrad_kernel<<<ctas, 128, smem>>>(d_dy, d_act, k_in, tiles_per_cta, d_dw, mn_lbo, mn_sbo);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0;
@@ -292,7 +294,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_w, w_img.data(), w_img.size() * 2, cudaMemcpyHostToDevice));
   const size_t smem_d = (size_t)kRows * kNOut * 2 + (size_t)kNOut * k_in * 2 + 1024;
   CK(cudaFuncSetAttribute(dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
-  dgrad_kernel<<<dg_ctas, 128, smem_d>>>(d_dy, d_w, k_in, dg_tiles, d_dx);
+  dgrad_kernel<<<dg_ctas, 128, smem_d>>>(d_dy, d_w, k_in, dg_tiles, d_dx, mn_lbo, mn_sbo);
   CK(cudaDeviceSynchronize());
   std::vector<float> dx((size_t)dg_ctas * dg_tiles * kRows * k_in);
   CK(cudaMemcpy(dx.data(), d_dx, dx.size() * 4, cudaMemcpyDeviceToHost));
