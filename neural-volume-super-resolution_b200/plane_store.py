@@ -101,9 +101,13 @@ def _pin(t):
 class PlaneStore:
     """Reads/writes the reference's `.par` files and stages scenes for the GPU (see the module docstring)."""
 
-    def __init__(self, save_location, model_name="coarse", device=None):
+    def __init__(self, save_location, model_name="coarse", device=None, prepack=None):
+        """`prepack`: "fp16" | "bf16" | "fp32" — also build the gather's packed plane images (`nvsr_pack_plane`) on the
+        COPY stream right behind the upload and seed the render path's plane cache with them, so the first frame of a
+        scene finds its planes packed (the packing of scene k+1 overlaps the rendering of scene k as well)."""
         self.save_location, self.model_name = save_location, model_name
         self.device = device
+        self.prepack = prepack
         self._host = {}        # scene -> SceneRecord (pinned)
         self._pending = {}     # scene -> (thread, result dict)
         self._device = {}      # scene -> (dict name -> device tensor, box, event or None)
@@ -180,7 +184,16 @@ class PlaneStore:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=device)
         with torch.cuda.stream(self._copy_stream):
-            planes = {k: v.to(device, non_blocking=True) for k, v in rec.planes.items()}
+            # Parameters are made HERE (not in attach) so that their identity can key the render path's plane cache
+            planes = {k: nn.Parameter(v.to(device, non_blocking=True), requires_grad=False) for k, v in rec.planes.items()}
+            if self.prepack is not None:
+                from . import ops, render, scene as scene_mod
+                dtype = render._PRECISION[self.prepack]
+                for k, p in planes.items():
+                    is_view = k.endswith("_D%d" % (len(planes) - 1))
+                    dt = ops.NVSR_F32 if is_view else dtype            # the view plane is always gathered in fp32
+                    per_dtype = scene_mod._plane_cache.get(p, scene_mod._Cache.key_of(p), dict)
+                    per_dtype[dt] = ops.pack_plane(p, dt)
             ev = torch.cuda.Event()
             ev.record()
         self._device[scene] = (planes, rec.box, ev)
@@ -193,10 +206,17 @@ class PlaneStore:
         saved = saved_scene or scene
         planes, box, ev = self.to_device(saved)
         if ev is not None:
-            torch.cuda.current_stream().wait_event(ev)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            from . import scene as scene_mod
             for p in planes.values():
-                p.record_stream(torch.cuda.current_stream())
-        params = nn.ParameterDict([(k, nn.Parameter(v, requires_grad=False)) for k, v in planes.items()])
+                p.record_stream(cur)
+                hit = scene_mod._plane_cache.store.get(id(p))
+                if hit is not None and hit[0]() is p:                  # pre-packed images were allocated on the copy stream
+                    for img in hit[2].values():
+                        img.record_stream(cur)
+        params = nn.ParameterDict([(k, v if isinstance(v, nn.Parameter) else nn.Parameter(v, requires_grad=False))
+                                   for k, v in planes.items()])
         for m in models:
             m.planes_ = params
             m.box_coords = {saved: box, scene: box}

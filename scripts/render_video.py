@@ -39,7 +39,7 @@ def main():
                                               scene_id="s0_DS2_PlRes%d_32" % args.plane_res)
     sids = [sid0] + [scene.add_synthetic_scene(mc, mf, "s%d_DS2_PlRes%d_32" % (i, args.plane_res), plane_res=args.plane_res, seed=100 + i)
                      for i in range(1, args.scenes)]
-    store = plane_store.PlaneStore(planes_dir, device=dev)
+    store = plane_store.PlaneStore(planes_dir, device=dev, prepack=nvsr_b200.get_precision())
     for sid in sids:
         store.write(sid, {k: mc.planes_[k] for k in plane_store.plane_names(sid)}, mc.box_coords[sid])
     opt, scfg = scene.render_options(64, 128), scene.scene_cfg()

@@ -220,7 +220,7 @@ def test_gpu_attach_overlaps_and_renders(tmp_path):
     shutil.copy(os.path.join(H.GOLDEN, "coarse_%s.par" % SCENE), tmp_path)
     store_dir = str(tmp_path)
     from nvsr_b200 import scene
-    st = PS.PlaneStore(store_dir, device="cuda:0")
+    st = PS.PlaneStore(store_dir, device="cuda:0", prepack="fp16")
     st.prefetch(SCENE)
     m = scene.TriPlaneModel(num_plane_channels=8, scene_coupler=scene.SingleSceneCoupler(None))
     params = st.attach([m], SCENE)
@@ -229,3 +229,10 @@ def test_gpu_attach_overlaps_and_renders(tmp_path):
     for k in PS.plane_names(SCENE):
         assert params[k].is_cuda and np.array_equal(params[k].detach().cpu().numpy(), twin[k])
     assert SCENE in m.box_coords
+    # prepack: the render path's plane cache already holds the packed images of exactly these Parameter objects
+    for d, k in enumerate(PS.plane_names(SCENE)):
+        hit = scene._plane_cache.store.get(id(params[k]))
+        assert hit is not None and hit[0]() is params[k]
+        want_dtype = nvsr_b200.NVSR_F32 if d == 3 else nvsr_b200.NVSR_F16
+        assert want_dtype in hit[2]
+        assert torch.equal(hit[2][want_dtype], ops.pack_plane(params[k], want_dtype))
