@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NVSR_ABI_VERSION 2
+#define NVSR_ABI_VERSION 3
 
 #define NVSR_OK 0
 #define NVSR_ERR_INVALID_ARG (-1)
@@ -115,6 +115,7 @@ typedef struct nvsr_planes {
   float box_lo[3];        /* fp32(box_coords[scene][0,:3]) */
   float box_rng[3];       /* fp32(box[1,:3] - box[0,:3]) with the difference taken in fp64 */
   float proj[3][6];       /* rot_mats[d][:,1:] row-major [3][2]: grid = n_xyz @ proj[d] */
+  int32_t combine;        /* combine_pos_planes (models.py:355-361) for featM: 0 = 'avg' (sum / 3), 1 = 'sum' */
 } nvsr_planes_t;
 
 typedef struct nvsr_sampler {
@@ -256,6 +257,18 @@ int32_t nvsr_sample_pdf(const float* bins, const float* weights, const float* cd
 int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, int64_t n_rays, int32_t n_intervals,
                  float radius, int32_t n_freqs, int32_t out_layout, int32_t k_pad, void* out,
                  void* stream);
+
+/* a9 stage-level, with the reference's own tensors at the boundary (same-signature drop-ins):
+ * cast_rays(t_vals, origins, directions, radii, ray_shape) mip.py:9-18 (+ conical_frustum_to_gaussian :21-29,
+ * lift_gaussian :32-43): z [n,S+1] interval edges -> means, covs [n,S,3] (diagonal covariances).
+ * radii: [n] per-ray base radius (device) or NULL, then the scalar `radius` (train_utils.py:21-24 builds a
+ * constant column). */
+int32_t nvsr_cast_rays(const float* z, const float* ro, const float* rd, const float* radii, float radius,
+                       int64_t n_rays, int32_t n_intervals, float* means, float* covs, void* stream);
+/* IntegratedPositionalEncoding.forward((means, covs)) mip.py:164-191: means, covs [rows,3] ->
+ * out [rows, 6*n_freqs] = exp(-0.5*[y_var,y_var]) * sin([y, y+pi/2]), y = means x 2^i, i < n_freqs = multires-1. */
+int32_t nvsr_ipe_encode(const float* means, const float* covs, int64_t rows, int32_t n_freqs, float* out,
+                        void* stream);
 
 /* positional_encoding(viewdirs, n_freqs, include_input) nerf_helpers.py:552-575, per ray. */
 int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, int32_t include_input,

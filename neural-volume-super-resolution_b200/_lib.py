@@ -31,6 +31,7 @@ class Planes(C.Structure):
         ("box_lo", c_f * 3),
         ("box_rng", c_f * 3),
         ("proj", (c_f * 6) * 3),
+        ("combine", c_i32),
     ]
 
 
@@ -127,6 +128,8 @@ SIGNATURES = {
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),
     "nvsr_dir_encoding": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_p]),
+    "nvsr_cast_rays": (c_i32, [c_p, c_p, c_p, c_p, c_f, c_i64, c_i32, c_p, c_p, c_p]),
+    "nvsr_ipe_encode": (c_i32, [c_p, c_p, c_i64, c_i32, c_p, c_p]),
     "nvsr_sample_gather_bwd": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_p, c_p, C.POINTER(c_p), c_p]),
     "nvsr_viewdir_gather_bwd": (c_i32, [c_p, c_i64, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p, c_p]),
     "nvsr_frame_to_u8": (c_i32, [c_p, c_i64, c_p, c_p]),
@@ -165,7 +168,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.nvsr_abi_version() != 2:
+    if lib.nvsr_abi_version() != 3:
         raise NvsrError("libnvsr_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -11,9 +11,8 @@ per layer).  z_samples are detached in the reference (train_utils.py:153): nothi
     rgb, disp, acc, weights, depth = volume_render_radiance_field(raw, z, rd, ...)   # a7, differentiable
 
 There is no CPU path: every tensor must live on a CUDA device (`NvsrError` otherwise).
-STATUS: the kernels' arithmetic is verified on the CPU against autograd of the oracle (tests/test_backward_bodies.py
-compiles the kernels' own per-element source for the host); the CUDA launch path was written after the round's GPU
-budget was spent and has its first GPU run in tests/test_gpu_zz_next_rows.py.
+Verified on the CPU against autograd of the oracle (tests/test_backward_bodies.py compiles the kernels' own
+per-element source for the host) and on a B200 through the C-ABI (tests/test_gpu_next_rows.py).
 """
 import torch
 
@@ -36,8 +35,8 @@ class Geometry:
     """What the gather needs besides the plane values: box, projection matrices, view-angle box (models.py:261-268,
     :495-497) — `ops.PackedPlanes` without plane images."""
 
-    def __init__(self, box_lo, box_rng, proj, view_lo_rng):
-        self.box_lo, self.box_rng, self.proj, self.view_lo_rng = box_lo, box_rng, proj, view_lo_rng
+    def __init__(self, box_lo, box_rng, proj, view_lo_rng, combine="avg"):
+        self.box_lo, self.box_rng, self.proj, self.view_lo_rng, self.combine = box_lo, box_rng, proj, view_lo_rng, combine
 
     @classmethod
     def of_model(cls, model, scene_id):
@@ -45,12 +44,24 @@ class Geometry:
         lo, rng = box[0].float(), (box[1] - box[0]).float()
         rots = model.coord_projector.rot_mats_NON_LEARNED
         proj = [rots[d].detach().float().cpu()[:, 1:].tolist() for d in range(3)]
-        return cls(lo[:3].tolist(), rng[:3].tolist(), proj, (float(lo[3]), float(rng[3]), float(lo[4]), float(rng[4])))
+        return cls(lo[:3].tolist(), rng[:3].tolist(), proj, (float(lo[3]), float(rng[3]), float(lo[4]), float(rng[4])),
+                   getattr(model, "proj_combination", "avg"))
+
+
+def _cl_image(plane_nchw):
+    """fp32 channels-last image of a plane, cached per (tensor, version) like the forward path's packed planes: the
+    coarse and the fine pass of a step (and every ray chunk) share one transpose; an optimizer step bumps the version."""
+    from . import scene
+    per = scene._plane_cache.get(plane_nchw, scene._Cache.key_of(plane_nchw), dict)
+    if "autograd_cl" not in per:
+        per["autograd_cl"] = ops.pack_plane(plane_nchw, NVSR_F32)
+    return per["autograd_cl"]
 
 
 def _packed(planes_nchw, geom, vplane=None):
-    imgs = [ops.pack_plane(p, NVSR_F32) for p in planes_nchw]
-    return ops.PackedPlanes(imgs, NVSR_F32, geom.box_lo, geom.box_rng, geom.proj, vplane, geom.view_lo_rng)
+    imgs = [_cl_image(p) for p in planes_nchw]
+    return ops.PackedPlanes(imgs, NVSR_F32, geom.box_lo, geom.box_rng, geom.proj, vplane, geom.view_lo_rng,
+                            combine=geom.combine)
 
 
 class TriPlaneGather(torch.autograd.Function):
@@ -73,6 +84,9 @@ class TriPlaneGather(torch.autograd.Function):
         acc = [torch.zeros((s[-2], s[-1], s[-3]), dtype=torch.float32, device=dev) for s in ctx.shapes]
         shell = ops.PackedPlanes(acc, NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, None, ctx.geom.view_lo_rng)
         if g_p is not None or g_m is not None:
+            # the kernel scatters w * (dP + dM / 3) ('avg'); for 'sum' the combined features' gradient counts fully
+            if g_m is not None and ctx.geom.combine == "sum":
+                g_m = g_m * 3.0
             ops.sample_gather_bwd(ro, rd, z, shell, g_p, g_m, acc)
         grads = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc, ctx.shapes)]   # channels-last -> the parameter's NCHW
         return grads[0], grads[1], grads[2], None, None, None, None
@@ -84,7 +98,7 @@ class ViewdirGather(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, vplane, viewdirs, geom):
-        img = ops.pack_plane(vplane, NVSR_F32)
+        img = _cl_image(vplane)
         packed = ops.PackedPlanes([img, img, img], NVSR_F32, geom.box_lo, geom.box_rng, geom.proj, img, geom.view_lo_rng)
         ctx.save_for_backward(viewdirs)
         ctx.geom, ctx.shape = geom, tuple(vplane.shape)
@@ -187,8 +201,26 @@ def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, opti
         raise NotImplementedError("nvsr_b200: use_viewdirs=False is not supported")
     if not batch_rays.is_cuda:
         raise _lib.NvsrError("batch_rays must be CUDA tensors: nvsr_b200 has no CPU path")
-    return _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config, randoms,
-                         encode_position_fn)
+    # ray batches of `chunksize` like train_utils.py:228-247 (get_minibatches over the rays; with an SR model / mip
+    # encoding the reference divides the chunk, :231-234): bounds the live activations of one decoder call
+    n = batch_rays.shape[1]
+    chunk = int(getattr(getattr(options.nerf, mode), "chunksize", 0) or n)
+    if hasattr(model_fine, "SR_model"):
+        chunk //= 10
+    if getattr(options.nerf, "encode_position_fn", None) == "mip":
+        chunk //= 4
+    chunk = max(1, chunk)
+    if n <= chunk:
+        return _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, scene_id, mode, scene_config,
+                             randoms, encode_position_fn)
+    outs = []
+    for i0 in range(0, n, chunk):
+        i1 = min(n, i0 + chunk)
+        rnd = {k: (v[i0:i1] if (torch.is_tensor(v) and v.dim() == 2 and v.shape[0] == n) else v)
+               for k, v in (randoms or {}).items()}
+        outs.append(_run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays[:, i0:i1], options, scene_id, mode,
+                                  scene_config, rnd, encode_position_fn))
+    return tuple(None if outs[0][k] is None else torch.cat([o[k] for o in outs], 0) for k in range(9))
 
 
 def _coarse_context(model_coarse):

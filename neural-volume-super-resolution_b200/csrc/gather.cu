@@ -33,6 +33,7 @@ struct PlaneArgs {
   int C;
   float lo[3], rng[3];
   float proj[3][6];
+  int combine_sum;  // combine_pos_planes: 0 = 'avg', 1 = 'sum' (models.py:355-361)
 };
 
 // train_utils.py:95-109: depth of sample s on a ray (every op separately rounded)
@@ -108,8 +109,8 @@ gather_rowmajor_f32(SamplerArgs a, PlaneArgs p, float* __restrict__ featP, float
     *reinterpret_cast<float4*>(featP + row * (3 * p.C) + d * p.C + ch) = o;
     m.x = __fadd_rn(m.x, o.x), m.y = __fadd_rn(m.y, o.y), m.z = __fadd_rn(m.z, o.z), m.w = __fadd_rn(m.w, o.w);
   }
-  // combine_pos_planes('avg'): stack(...).mean(0) = sum / 3
-  m.x = __fdiv_rn(m.x, 3.f), m.y = __fdiv_rn(m.y, 3.f), m.z = __fdiv_rn(m.z, 3.f), m.w = __fdiv_rn(m.w, 3.f);
+  // combine_pos_planes('avg'): stack(...).mean(0) = sum / 3; 'sum': the sum itself
+  if (!p.combine_sum) m.x = __fdiv_rn(m.x, 3.f), m.y = __fdiv_rn(m.y, 3.f), m.z = __fdiv_rn(m.z, 3.f), m.w = __fdiv_rn(m.w, 3.f);
   *reinterpret_cast<float4*>(featM + row * p.C + ch) = m;
 }
 
@@ -215,7 +216,8 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
   const uint32_t m_bytes = (uint32_t)CH * 2048u;
   const int TS = tiles_per_block(a.S);
   const int r = threadIdx.x;
-  const unsigned long long third = pack_f32x2(1.f / 3.f, 1.f / 3.f);
+  const float comb = p.combine_sum ? 1.f : 1.f / 3.f;
+  const unsigned long long third = pack_f32x2(comb, comb);
   const XPair* const pl0 = reinterpret_cast<const XPair*>(p.plane[0]);
   const XPair* const pl1 = reinterpret_cast<const XPair*>(p.plane[1]);
   const XPair* const pl2 = reinterpret_cast<const XPair*>(p.plane[2]);
@@ -395,6 +397,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
   NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd);
   NVSR_CHECK_ARG(s->z_in || s->t_vals);
   NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64);
+  NVSR_CHECK_ARG(pl->combine == 0 || pl->combine == 1);
   for (int d = 0; d < 3; ++d) {
     NVSR_CHECK_ARG(pl->plane[d] && pl->rh[d] > 0 && pl->rw[d] > 0);
     if ((reinterpret_cast<uintptr_t>(pl->plane[d]) & (is_16bit(pl->dtype) ? 31u : 15u)) != 0) return NVSR_ERR_ALIGNMENT;
@@ -410,6 +413,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     for (int j = 0; j < 6; ++j) p.proj[d][j] = pl->proj[d][j];
   }
   p.C = pl->channels;
+  p.combine_sum = pl->combine == 1;
   int64_t rows = s->n_rays * (int64_t)s->n_samples;
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -471,6 +475,7 @@ extern "C" int32_t nvsr_sample_gather_rows(const nvsr_sampler_t* s, const nvsr_p
     for (int j = 0; j < 6; ++j) p.proj[d][j] = pl->proj[d][j];
   }
   p.C = pl->channels;
+  p.combine_sum = pl->combine == 1;
   const bool c48 = pl->channels == 48;
   auto kernel = f16 ? (c48 ? gather_rows_16<true, 6> : gather_rows_16<true, 0>)
                     : (c48 ? gather_rows_16<false, 6> : gather_rows_16<false, 0>);

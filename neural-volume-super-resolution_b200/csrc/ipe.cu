@@ -148,6 +148,36 @@ ipe_tile6_kernel(const float* __restrict__ z, const float* __restrict__ ro, cons
   }
 }
 
+// Stand-alone stages with the reference's own tensors at the boundary (SURVEY.md §8b lists both as same-signature
+// drop-ins): cast_rays (mip.py:9-18) -> means, covs [n,S,3]; IntegratedPositionalEncoding.forward((means, covs))
+// (mip.py:164-191) -> [rows, 6*nf].  Same per-element arithmetic as the fused kernels above.
+__global__ void cast_rays_kernel(const float* __restrict__ z, const float* __restrict__ ro, const float* __restrict__ rd,
+                                 const float* __restrict__ radii, float radius, int64_t n_rays, int S,
+                                 float* __restrict__ means, float* __restrict__ covs) {
+  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rays * S) return;
+  int64_t ray = row / S;
+  int s = (int)(row - ray * S);
+  float o[3] = {__ldg(ro + ray * 3), __ldg(ro + ray * 3 + 1), __ldg(ro + ray * 3 + 2)};
+  float d[3] = {__ldg(rd + ray * 3), __ldg(rd + ray * 3 + 1), __ldg(rd + ray * 3 + 2)};
+  IpeRow g = ipe_gaussian(__ldg(z + ray * (S + 1) + s), __ldg(z + ray * (S + 1) + s + 1), o, d,
+                          radii ? __ldg(radii + ray) : radius);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) means[row * 3 + c] = g.mean[c], covs[row * 3 + c] = g.cov[c];
+}
+
+__global__ void ipe_encode_kernel(const float* __restrict__ means, const float* __restrict__ covs, int64_t rows, int nf,
+                                  float* __restrict__ out) {
+  const int D = 6 * nf;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * D) return;
+  int64_t row = idx / D;
+  IpeRow g;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) g.mean[c] = __ldg(means + row * 3 + c), g.cov[c] = __ldg(covs + row * 3 + c);
+  out[idx] = ipe_value(g, nf, (int)(idx - row * D));
+}
+
 // positional_encoding(d, nf, include_input): [d, sin(2^0 d), cos(2^0 d), sin(2^1 d), ...]
 __global__ void dir_encoding_kernel(const float* __restrict__ dirs, int64_t n, int nf, int include_input,
                                     float* __restrict__ out) {
@@ -211,6 +241,27 @@ extern "C" int32_t nvsr_ipe(const float* z, const float* ro, const float* rd, in
     NVSR_RETURN_LAST_ERROR();
   }
   return NVSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int32_t nvsr_cast_rays(const float* z, const float* ro, const float* rd, const float* radii, float radius,
+                                  int64_t n_rays, int32_t n_intervals, float* means, float* covs, void* stream) {
+  NVSR_CHECK_ARG(z && ro && rd && means && covs && n_rays >= 0 && n_intervals > 0);
+  if (n_rays == 0) return NVSR_OK;
+  int64_t blocks = ceil_div64(n_rays * n_intervals, 256);
+  NVSR_CHECK_ARG(blocks < ((int64_t)1 << 31));
+  cast_rays_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, ro, rd, radii, radius, n_rays, n_intervals,
+                                                                       means, covs);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_ipe_encode(const float* means, const float* covs, int64_t rows, int32_t n_freqs, float* out,
+                                   void* stream) {
+  NVSR_CHECK_ARG(means && covs && out && rows >= 0 && n_freqs > 0 && n_freqs <= kIpeMaxFreqs);
+  if (rows == 0) return NVSR_OK;
+  int64_t blocks = ceil_div64(rows * 6 * n_freqs, 256);
+  NVSR_CHECK_ARG(blocks < ((int64_t)1 << 31));
+  ipe_encode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(means, covs, rows, n_freqs, out);
+  NVSR_RETURN_LAST_ERROR();
 }
 
 extern "C" int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, int32_t include_input,

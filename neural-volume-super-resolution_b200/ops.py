@@ -142,12 +142,25 @@ def prepare_rays(ray_origins, ray_directions, use_ndc=False, height=0, width=0, 
 
 
 # ---------------------------------------------------------------------------------------------
+F16_MAX = 65504.0
+
+
+def _check_f16_range(t, what):
+    """fp16 images saturate (cvt.satfinite) instead of overflowing to inf — silently.  Packing happens once per scene /
+    weight update, so one reduction + host read here is free; a tensor that does not fit is refused loudly."""
+    if t.numel() and float(t.abs().max()) > F16_MAX:
+        raise _lib.NvsrError(f"{what}: |value| exceeds the fp16 range ({F16_MAX:g}); values would saturate silently - "
+                             "use set_precision('bf16') (fp32 range) or 'fp32' for this scene")
+
+
 def pack_plane(plane_nchw, dtype=NVSR_F32):
     """[1,C,Rh,Rw] fp32 (models.py:436-439) -> device plane image: fp32 channels-last [Rh,Rw,C], or 16-bit
     x-pair records [Rh,C/8,Rw,2,8] (nvsr.h: 8-channel chunk of a texel followed by its right neighbour's)."""
     lib = _lib.load()
     p = _f32c(plane_nchw.detach())
     _require_cuda(p, "plane")
+    if dtype == NVSR_F16:
+        _check_f16_range(p, "pack_plane")
     if p.dim() == 4:
         assert p.shape[0] == 1
         p = p[0]
@@ -171,6 +184,8 @@ def pack_weight16(weight, k_pad=None, dtype=NVSR_BF16):
     _require_cuda(w, "weight")
     if w.dtype != torch.float32 or w.stride(1) != 1:
         w = w.float().contiguous()
+    if dtype == NVSR_F16:
+        _check_f16_range(w, "pack_weight16")
     n_out, k = w.shape
     ldw = w.stride(0)
     if k_pad is None:
@@ -186,7 +201,10 @@ def pack_weight16(weight, k_pad=None, dtype=NVSR_BF16):
 class PackedPlanes:
     """Device-resident packed position planes of one scene (nvsr_pack_plane images) + box + projection matrices."""
 
-    def __init__(self, planes, dtype, box_lo, box_rng, proj, vplane=None, view_lo_rng=None):
+    def __init__(self, planes, dtype, box_lo, box_rng, proj, vplane=None, view_lo_rng=None, combine="avg"):
+        if combine not in ("avg", "sum"):
+            raise NotImplementedError(f"nvsr_b200: proj_combination={combine!r} (supported: 'avg', 'sum')")
+        self.combine = combine          # combine_pos_planes for the density features (models.py:355-361)
         self.planes = planes            # list of 3 tensors: fp32 [Rh,Rw,C] or 16-bit [Rh,C/8,Rw,2,8]
         self.dtype = dtype
         self.box_lo = [float(v) for v in box_lo]
@@ -207,6 +225,7 @@ class PackedPlanes:
                     s.proj[d][i * 2 + j] = float(self.proj[d][i][j])
         s.channels = self.channels
         s.dtype = self.dtype
+        s.combine = 1 if self.combine == "sum" else 0
         return s
 
 
@@ -503,6 +522,50 @@ def ipe(z_edges, ro, rd, radius, n_freqs, layout=FEAT_ROWMAJOR_F32, k_pad=None):
         st = _call("nvsr_ipe", lib.nvsr_ipe, _ptr(z), _ptr(_f32c(ro)), _ptr(_f32c(rd)), n, S, float(radius), n_freqs, layout, k_pad,
                           _ptr(out), _stream())
     _lib.check(st, "nvsr_ipe")
+    return out
+
+
+def cast_rays(t_vals, origins, directions, radii, ray_shape=None):
+    """Drop-in for mip.cast_rays (mip.py:9-18): t_vals [n,S+1] interval edges, origins / directions [n,3], radii a
+    scalar or a per-ray tensor [n] / [n,1] (train_utils.py:21-24 passes a constant column) ->
+    (means [n,S,3], covs [n,S,3]) — the diagonal-covariance conical-frustum Gaussians.  `ray_shape` is unused in the
+    reference as well."""
+    lib = _lib.load()
+    z = _f32c(t_vals)
+    _require_cuda(z, "t_vals")
+    n, s1 = z.shape
+    S = s1 - 1
+    ro, rd = _f32c(origins, z.device), _f32c(directions, z.device)
+    rad_t, rad = None, 0.0
+    if torch.is_tensor(radii):
+        rad_t = _f32c(radii.reshape(-1), z.device)
+        if rad_t.numel() == 1:
+            rad_t = rad_t.expand(n).contiguous()
+        if rad_t.numel() != n:
+            raise _lib.NvsrError("cast_rays: radii must be a scalar or one value per ray")
+    else:
+        rad = float(radii)
+    means = torch.empty((n, S, 3), dtype=torch.float32, device=z.device)
+    covs = torch.empty_like(means)
+    with torch.cuda.device(z.device):
+        st = _call("nvsr_cast_rays", lib.nvsr_cast_rays, _ptr(z), _ptr(ro), _ptr(rd), _ptr(rad_t), rad, n, S, _ptr(means),
+                   _ptr(covs), _stream())
+    _lib.check(st, "nvsr_cast_rays")
+    return means, covs
+
+
+def ipe_encode(means, covs, n_freqs):
+    """IntegratedPositionalEncoding.forward((means, covs)) (mip.py:164-191): [..., 3] x2 -> [..., 6*n_freqs]."""
+    lib = _lib.load()
+    m, c = _f32c(means), _f32c(covs)
+    _require_cuda(m, "means")
+    if m.shape != c.shape or m.shape[-1] != 3:
+        raise _lib.NvsrError("ipe_encode: means and covs must both be [..., 3]")
+    rows = m.numel() // 3
+    out = torch.empty(tuple(m.shape[:-1]) + (6 * n_freqs,), dtype=torch.float32, device=m.device)
+    with torch.cuda.device(m.device):
+        st = _call("nvsr_ipe_encode", lib.nvsr_ipe_encode, _ptr(m), _ptr(c), rows, int(n_freqs), _ptr(out), _stream())
+    _lib.check(st, "nvsr_ipe_encode")
     return out
 
 

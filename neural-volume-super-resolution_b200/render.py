@@ -259,7 +259,8 @@ def _render_mip_chunk(mc, mf, ro, rd, vd, near, far, cfg, radius, n_freqs, n_dir
                        white_background=cfg.white_background, mip=True, n_fine=(Nf + 1 if Nf > 0 else 0), u=u,
                        want_weights=trace is not None, want_inds=trace is not None, want_samples=trace is not None)
     if trace is not None:
-        trace.update(z_coarse=z, raw_coarse=raw[:, :n * Nc].t().reshape(n, Nc, 4), weights_coarse=co["weights"])
+        trace.update(z_coarse=z, raw_coarse=raw[:, :n * Nc].t().reshape(n, Nc, 4), weights_coarse=co["weights"],
+                     depth_coarse=co["depth"])
     fo = None
     if Nf > 0:
         zf = co["z_merged"]
@@ -269,7 +270,7 @@ def _render_mip_chunk(mc, mf, ro, rd, vd, near, far, cfg, radius, n_freqs, n_dir
                            white_background=cfg.white_background, mip=True)
         if trace is not None:
             trace.update(inds=co["inds"], z_samples=co["z_samples"], z_fine=zf,
-                         raw_fine=raw_f[:, :n * Sf].t().reshape(n, Sf, 4))
+                         raw_fine=raw_f[:, :n * Sf].t().reshape(n, Sf, 4), depth_fine=fo["depth"])
     return co, fo
 
 
@@ -376,10 +377,15 @@ def render_frame(height, width, focal, pose, model_coarse, model_fine, options, 
                                 encode_direction_fn=encode_direction_fn, scene_config=scene_config)
 
 
-_installed = {}
+_installed = {}   # module -> {attribute name: original object} for everything install() rebound
 
 
-def install(train_utils_module, nerf_helpers_module=None, train_nerf_module=None, differentiable=False):
+def _rebind(module, name, new):
+    _installed.setdefault(module, {}).setdefault(name, getattr(module, name))
+    setattr(module, name, new)
+
+
+def install(train_utils_module, nerf_helpers_module=None, train_nerf_module=None, differentiable=False, precision=None):
     """Rebind the reference's seams: `train_utils.run_one_iter_of_nerf` (which
     `eval_nerf` resolves through module globals at call time, train_utils.py:311) and, optionally,
     `nerf_helpers.get_ray_bundle`.  Under autograd the original functions keep running.
@@ -388,26 +394,40 @@ def install(train_utils_module, nerf_helpers_module=None, train_nerf_module=None
     train_nerf.py:13, resolved in train_nerf's globals at train_nerf.py:860).  With `differentiable=True` a
     grad-enabled call then goes to `nvsr_b200.autograd.run_one_iter_of_nerf` (hand-written backward of the gather
     and compositing stages) instead of the reference's function; unsupported configurations raise, there is no
-    silent fallback.  Default: training stays on the reference's own autograd path."""
-    orig = train_utils_module.run_one_iter_of_nerf
-    if getattr(orig, "_nvsr_b200", False):
-        return
+    silent fallback.  Default: training stays on the reference's own autograd path.
 
-    def run_one_iter_of_nerf_b200(*args, **kwargs):
-        if torch.is_grad_enabled():
-            if differentiable:
-                from . import autograd
-                return autograd.run_one_iter_of_nerf(*args, **kwargs)
-            return orig(*args, **kwargs)
-        return run_one_iter_of_nerf(*args, **kwargs)
+    `precision`: 'fp32' | 'fp16' | 'bf16' selects the arithmetic of every later call (same as set_precision); the
+    mode in force is logged once here, because the 16-bit modes are a stated-tolerance contract, not the 1e-3 one
+    (DESIGN.md §2).  Calling install() again updates the options of the existing wrapper (and rebinds whatever
+    modules the second call names); `uninstall()` restores every name any install() call rebound."""
+    if precision is not None:
+        set_precision(precision)
+    cur = train_utils_module.run_one_iter_of_nerf
+    if getattr(cur, "_nvsr_b200", False):
+        wrapper = cur
+        wrapper._options["differentiable"] = bool(differentiable)
+    else:
+        orig = cur
+        options = {"differentiable": bool(differentiable)}
 
-    run_one_iter_of_nerf_b200._nvsr_b200 = True
-    _installed[train_utils_module] = orig
-    train_utils_module.run_one_iter_of_nerf = run_one_iter_of_nerf_b200
-    if train_nerf_module is not None and getattr(train_nerf_module, "run_one_iter_of_nerf", None) is orig:
-        _installed[train_nerf_module] = orig
-        train_nerf_module.run_one_iter_of_nerf = run_one_iter_of_nerf_b200
-    if nerf_helpers_module is not None:
+        def run_one_iter_of_nerf_b200(*args, **kwargs):
+            if torch.is_grad_enabled():
+                if options["differentiable"]:
+                    from . import autograd
+                    return autograd.run_one_iter_of_nerf(*args, **kwargs)
+                return orig(*args, **kwargs)
+            return run_one_iter_of_nerf(*args, **kwargs)
+
+        run_one_iter_of_nerf_b200._nvsr_b200 = True
+        run_one_iter_of_nerf_b200._options = options
+        run_one_iter_of_nerf_b200._orig = orig
+        wrapper = run_one_iter_of_nerf_b200
+        _rebind(train_utils_module, "run_one_iter_of_nerf", wrapper)
+    if train_nerf_module is not None:
+        bound = getattr(train_nerf_module, "run_one_iter_of_nerf", None)
+        if bound is wrapper._orig:
+            _rebind(train_nerf_module, "run_one_iter_of_nerf", wrapper)
+    if nerf_helpers_module is not None and not getattr(nerf_helpers_module.get_ray_bundle, "_nvsr_b200", False):
         orig_grb = nerf_helpers_module.get_ray_bundle
 
         def get_ray_bundle_b200(height, width, focal_length, tform_cam2world, padding_size=0, downsampling_offset=0):
@@ -415,10 +435,31 @@ def install(train_utils_module, nerf_helpers_module=None, train_nerf_module=None
                 return orig_grb(height, width, focal_length, tform_cam2world, padding_size, downsampling_offset)
             return ops.get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size, downsampling_offset)
 
-        nerf_helpers_module.get_ray_bundle = get_ray_bundle_b200
+        get_ray_bundle_b200._nvsr_b200 = True
+        _rebind(nerf_helpers_module, "get_ray_bundle", get_ray_bundle_b200)
+    import logging
+    logging.getLogger("nvsr_b200").info(
+        "nvsr_b200 installed: precision=%s (%s), differentiable=%s", get_precision(),
+        "1e-3 parity contract" if get_precision() == "fp32" else "16-bit operands, stated tolerance - see DESIGN.md section 2",
+        wrapper._options["differentiable"])
+    return wrapper
 
 
-def uninstall(train_utils_module):
-    orig = _installed.pop(train_utils_module, None)
-    if orig is not None:
-        train_utils_module.run_one_iter_of_nerf = orig
+def uninstall(train_utils_module=None):
+    """Restore every name install() rebound — in `train_utils_module` and in every other module (train_nerf,
+    nerf_helpers) an install() call touched — and drop the packed-scene caches."""
+    for module, names in list(_installed.items()):
+        for name, orig in names.items():
+            setattr(module, name, orig)
+        del _installed[module]
+    clear_caches()
+
+
+def clear_caches():
+    """Drop every packed image this module and `scene` hold (planes, decoder weights, per-(model, scene) passes).
+    Call it after writing a plane or weight through `.data` (which does not bump the tensor's version counter, so the
+    identity+version cache keys cannot see it) and to release the device memory of scenes no longer rendered."""
+    _pass_cache.store.clear()
+    _t_vals_cache.clear()
+    scene._plane_cache.store.clear()
+    scene._decoder_cache.store.clear()

@@ -320,9 +320,8 @@ class _Cache:
         hit = self.store.get(id(obj))
         if hit is not None and hit[0]() is obj and hit[1] == sig:
             return hit[2]
-        if len(self.store) > 64:  # drop entries whose owners died
-            for k in [k for k, v in self.store.items() if v[0]() is None]:
-                del self.store[k]
+        for k in [k for k, v in self.store.items() if v[0]() is None]:  # entries whose owners died
+            del self.store[k]
         val = make()
         self.store[id(obj)] = (weakref.ref(obj), sig, val)
         return val
@@ -333,8 +332,11 @@ _decoder_cache = _Cache()
 
 
 def clear_caches():
-    _plane_cache.store.clear()
-    _decoder_cache.store.clear()
+    """Drop every packed plane / decoder image AND the per-(model, scene) pass objects of the render module that own
+    them (`render.clear_caches`).  Needed after in-place writes through `.data` — they do not bump `_version`, which
+    the cache keys rely on — and to release the device memory of scenes that are no longer rendered."""
+    from . import render
+    render.clear_caches()
 
 
 def _should_sr(model, d):
@@ -368,8 +370,8 @@ def check_supported_planes_model(model):
         bad.append("num_density_planes != 3")
     if getattr(model, "plane_interp", "bilinear") != "bilinear" or not getattr(model, "align_corners", True):
         bad.append("plane_interp/align_corners")
-    if getattr(model, "proj_combination", "avg") != "avg":
-        bad.append("proj_combination != 'avg'")
+    if getattr(model, "proj_combination", "avg") not in ("avg", "sum"):
+        bad.append("proj_combination not in ('avg', 'sum')")
     if getattr(model, "viewdir_proj_combination", "concat_pos") != "concat_pos":
         bad.append("viewdir_proj_combination != 'concat_pos'")
     if getattr(model, "rgb_dec_input", "projections") != "projections" or not getattr(model, "use_viewdirs", True):
@@ -409,7 +411,8 @@ def pack_scene_planes(model, scene_id, dtype):
     rots = model.coord_projector.rot_mats_NON_LEARNED
     proj = [rots[d].detach().float().cpu()[:, 1:].tolist() for d in range(3)]
     return ops.PackedPlanes(packed, dtype, lo[:3].tolist(), rng[:3].tolist(), proj, vplane,
-                            (float(lo[3]), float(rng[3]), float(lo[4]), float(rng[4])))
+                            (float(lo[3]), float(rng[3]), float(lo[4]), float(rng[4])),
+                            combine=getattr(model, "proj_combination", "avg"))
 
 
 class PackedPlanesDecoder:

@@ -360,6 +360,8 @@ def predict_and_render_radiance(ray_batch, model_coarse, model_fine, options, sc
                                           u=randoms.get("u"), return_all=True)
         z_samples = z_samples.detach()
         z_vals, _ = torch.sort(torch.cat((z_vals, z_samples), dim=-1), dim=-1)
+        if "z_fine" in randoms:   # test hook (not in the reference): teacher-forced fine depths, e.g. the CUDA path's
+            z_vals = randoms["z_fine"].to(ro)
         pts = ro[..., None, :] + rd[..., None, :] * z_vals[..., :, None]
         rf = run_network(model_fine, pts, ray_batch, cfg.chunksize, embed, embeddirs, scene_id, mip, z_vals)
         rgb_f, disp_f, acc_f, w_f, depth_f = volume_render_radiance_field(

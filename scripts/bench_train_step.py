@@ -28,6 +28,7 @@ from nvsr_b200 import autograd as A, ops, scene  # noqa: E402
 def torch_planes_forward(model, sid, ro, rd, z, vd):
     """TwoDimPlanesModel.forward with stock torch ops (models.py:381-421)."""
     n, S = z.shape
+    model.set_cur_scene_id(sid)
     box = model.box_coords[sid].to(ro)
     pts = (ro[:, None, :] + rd[:, None, :] * z[..., None]).reshape(-1, 3)
     el = torch.atan2(vd[:, 2], torch.sqrt((vd[:, :2] ** 2).sum(-1)))

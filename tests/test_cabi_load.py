@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.lib_path())
     for s in declared_symbols():
         assert hasattr(raw, s), s
-    assert lib.nvsr_abi_version() == 2
+    assert lib.nvsr_abi_version() == 3
     assert lib.nvsr_status_string(0) == b"ok"
     assert b"invalid" in lib.nvsr_status_string(-1)
 
@@ -40,7 +40,7 @@ def test_struct_sizes_match_c_layout(tmp_path):
     import subprocess
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
-    pairs = [("nvsr_layer_t", _lib.Layer, "head_ch"), ("nvsr_planes_t", _lib.Planes, "proj"),
+    pairs = [("nvsr_layer_t", _lib.Layer, "head_ch"), ("nvsr_planes_t", _lib.Planes, "combine"),
              ("nvsr_sampler_t", _lib.Sampler, "z_in"), ("nvsr_mlp_t", _lib.Mlp, "row_order"),
              ("nvsr_composite_t", _lib.Composite, "z_merged")]
     src = "#include <stdio.h>\n#include <stddef.h>\n#include \"nvsr.h\"\nint main(void){\n"

@@ -87,3 +87,45 @@ def test_install_training_seam(monkeypatch):
         nvsr_b200.uninstall(tu)
         nvsr_b200.uninstall(tn)
         assert tu.run_one_iter_of_nerf is ref_run and tn.run_one_iter_of_nerf is ref_run
+
+
+def test_reinstall_updates_options_and_uninstall_restores_everything(monkeypatch):
+    """A second install() is not a silent no-op: it updates the wrapper's options and rebinds the modules it names;
+    uninstall() restores every name any install() call touched."""
+    from nvsr_b200 import autograd
+    tu, nh, calls = _fake_reference_modules()
+    tn = types.ModuleType("train_nerf")
+    tn.run_one_iter_of_nerf = tu.run_one_iter_of_nerf
+    ref_run, ref_grb = tu.run_one_iter_of_nerf, nh.get_ray_bundle
+    monkeypatch.setattr(autograd, "run_one_iter_of_nerf", lambda *a, **k: ("b200_autograd",) * 9)
+    nvsr_b200.install(tu)                                           # plain install first
+    with torch.enable_grad():
+        assert tu.run_one_iter_of_nerf(1)[0] == "ref"
+    assert nh.get_ray_bundle is ref_grb and tn.run_one_iter_of_nerf is ref_run
+    nvsr_b200.install(tu, nh, train_nerf_module=tn, differentiable=True)   # second call: takes effect
+    assert tn.run_one_iter_of_nerf is tu.run_one_iter_of_nerf is not ref_run
+    assert nh.get_ray_bundle is not ref_grb
+    with torch.enable_grad():
+        assert tn.run_one_iter_of_nerf(1)[0] == "b200_autograd"
+    nvsr_b200.uninstall(tu)
+    assert tu.run_one_iter_of_nerf is ref_run and tn.run_one_iter_of_nerf is ref_run and nh.get_ray_bundle is ref_grb
+
+
+def test_install_sets_and_logs_precision(caplog):
+    import logging
+    tu, nh, _ = _fake_reference_modules()
+    before = nvsr_b200.get_precision()
+    with caplog.at_level(logging.INFO, logger="nvsr_b200"):
+        nvsr_b200.install(tu, precision="fp32")
+    assert nvsr_b200.get_precision() == "fp32"
+    assert any("precision=fp32" in r.getMessage() for r in caplog.records)
+    nvsr_b200.uninstall(tu)
+    nvsr_b200.set_precision(before)
+
+
+def test_clear_caches_reaches_the_pass_cache():
+    from nvsr_b200 import scene
+    render._pass_cache.store[123] = ("x",)
+    scene._plane_cache.store[5] = ("y",)
+    scene.clear_caches()
+    assert not render._pass_cache.store and not scene._plane_cache.store and not scene._decoder_cache.store
