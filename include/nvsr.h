@@ -275,6 +275,53 @@ int32_t nvsr_dir_encoding(const float* dirs, int64_t n_rays, int32_t n_freqs, in
                           float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Convenience: the whole coarse -> fine pipeline of predict_and_render_radiance (train_utils.py:71-182) for one batch
+ * of PREPARED rays (nvsr_prepare_rays) of a tri-plane scene, with one host call and no allocation: the stage entry
+ * points above, in the order the reference runs them, out of a caller-owned workspace of nvsr_workspace_bytes() bytes
+ * (256-byte aligned).  Every sample goes through both decoders (the sparse colour path is a host-side optimisation of
+ * the Python shim).  Results are bit-identical to issuing the stage calls one by one.
+ */
+typedef struct nvsr_decoder {
+  nvsr_layer_t density[NVSR_MAX_LAYERS];  /* density_dec + fc_alpha head on the last layer (models.py:393-404) */
+  int32_t n_density;
+  nvsr_layer_t rgb[NVSR_MAX_LAYERS];      /* rgb_dec over the 3C position columns + fc_rgb head; rgb[0].row_bias is set by the call */
+  int32_t n_rgb;
+  const float* view_w;                    /* the per-ray (view feature) columns of rgb_dec[0].weight: [n_out, C], row stride view_ldw */
+  int32_t view_ldw;
+  const float* view_b;                    /* rgb_dec[0].bias [n_out] */
+} nvsr_decoder_t;
+
+typedef struct nvsr_render {
+  int32_t precision;                      /* NVSR_F32 | NVSR_BF16 | NVSR_F16: selects gather layout and decoder kernel */
+  int64_t n_rays;
+  int32_t n_coarse, n_fine;               /* n_fine == 0: coarse pass only */
+  const float *ro, *rd, *viewdirs;        /* [n,3] each, as nvsr_prepare_rays returns them */
+  float near_, far_;
+  int32_t lindisp, white_bkgd;
+  const float* t_vals;                    /* [n_coarse] torch.linspace(0,1,n_coarse) */
+  const float* t_rand;                    /* [n,n_coarse] stratified jitter or NULL */
+  const float* u;                         /* [n_fine] (u_per_ray == 0) or [n,n_fine] */
+  int32_t u_per_ray;
+  const float *noise_c, *noise_f;         /* [n,n_coarse] / [n,n_coarse+n_fine], already scaled, or NULL */
+  const nvsr_planes_t* planes_coarse;
+  const nvsr_planes_t* planes_fine;       /* may equal planes_coarse; same channel count */
+  const float* vplane_coarse;             /* channels-last fp32 view plane [vrh][vrw][C] */
+  const float* vplane_fine;               /* == vplane_coarse when the models share it */
+  int32_t vrh, vrw;
+  float az_lo, az_rng, el_lo, el_rng;
+  const nvsr_decoder_t* dec_coarse;
+  const nvsr_decoder_t* dec_fine;
+  float *rgb_c, *disp_c, *acc_c, *depth_c; /* [n,3], [n], [n], [n] */
+  float *rgb_f, *disp_f, *acc_f, *depth_f; /* fine maps (n_fine > 0) */
+  void* workspace;
+  int64_t workspace_bytes;
+} nvsr_render_t;
+
+/* bytes of device workspace nvsr_render_rays needs for this request (-1: invalid request) */
+int64_t nvsr_workspace_bytes(const nvsr_render_t* request);
+int32_t nvsr_render_rays(const nvsr_render_t* request, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * BACKWARD of the memory-bound stages (the reference differentiates
  * run_one_iter_of_nerf with autograd, train_nerf.py:860-916 — mse on rgb_coarse / rgb_fine, loss.backward(),
  * PlanesOptimizer.step()).  The decoder between them stays with the caller's autograd in this version

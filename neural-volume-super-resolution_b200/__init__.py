@@ -16,11 +16,22 @@ from .render import (eval_nerf, get_precision, install, render_frame, run_one_it
                      set_ray_chunk, set_sparse_rgb, uninstall)
 
 
+from .ops import cast_rays  # noqa: F401,E402  (mip.cast_rays, mip.py:9-18)
+from .render import planes_model_forward  # noqa: F401,E402  (TwoDimPlanesModel.forward(x[n,6]) -> [n,4], models.py:381-421)
+
+
 class IntegratedPositionalEncoding:
-    """Handle with the reference's constructor (mip.py:155-161).  The encoding itself is fused with
-    cast_rays into one kernel (`ops.ipe`), which `run_one_iter_of_nerf` calls when it is given this
-    object (or the reference's own module — only `.max_freq` is read) as `encode_position_fn`."""
+    """Drop-in for mip.IntegratedPositionalEncoding (mip.py:154-199): same constructor, and calling it with the
+    reference's `(means, covs)` tuple returns the `[..., 6*(multires-1)]` encoding (`nvsr_ipe_encode`).  Inside
+    `run_one_iter_of_nerf` the encoding is fused with cast_rays into one kernel (`ops.ipe`); the render path only reads
+    `.max_freq` of whatever object it is given as `encode_position_fn` (this one or the reference's own module)."""
 
     def __init__(self, input_dims=3, multires=10, include_input=False):
         self.out_dims = input_dims * 2 * (multires - 1)
         self.max_freq = multires - 1
+
+    def __call__(self, x_coord):
+        means, covs = x_coord
+        return ops.ipe_encode(means, covs, self.max_freq)
+
+    forward = __call__

@@ -294,6 +294,8 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
                 u = torch.rand([n, Nf + 1])
             z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf + 1, det=(cfg.perturb == 0.0), u=u)
             z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
+            if "z_fine" in randoms:     # test hook: teacher-forced merged depths
+                z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
         rf_f = radiance(model_fine, z_f)
         rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background,
                                              noise_of("noise_f", z_f.shape[1] - 1), mip=True)
@@ -371,6 +373,8 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
                 u = torch.rand([n, Nf])
             z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf, det=(cfg.perturb == 0.0), u=u)
             z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
+            if "z_fine" in randoms:     # test hook: teacher-forced merged depths
+                z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
         rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd)
         rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background, noise_of("noise_f", Nc + Nf))
     return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, None, None, None

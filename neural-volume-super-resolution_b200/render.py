@@ -352,6 +352,33 @@ def run_one_iter_of_nerf(H, W, focal, model_coarse, model_fine, batch_rays, opti
             cat(outs_f, "rgb"), cat(outs_f, "disp"), cat(outs_f, "acc"), None, None, None)
 
 
+def planes_model_forward(model, x, scene_id=None):
+    """Drop-in for `TwoDimPlanesModel.forward(x[n,6]) -> [n,4]` (models.py:381-421; what `run_network` calls as
+    `network_fn(batch)`, train_utils.py:56): x = (point xyz, view direction) per row, output `cat(rgb, alpha)` raw
+    (sigmoid / relu are applied by the compositing).  Same stage kernels as the fused path — gather, per-row view bias,
+    both decoder chains — in the precision of `set_precision()`; each point is evaluated as a one-sample ray
+    (origin = the point, direction 0), so the 16-bit tile layout carries 15 padding rows per point: a parity /
+    integration surface, not the fast path (`run_one_iter_of_nerf` never materialises x)."""
+    if torch.is_grad_enabled():
+        raise RuntimeError("nvsr_b200.planes_model_forward is forward-only: call it under torch.no_grad()")
+    if not x.is_cuda:
+        raise _lib.NvsrError("x must be a CUDA tensor: nvsr_b200 has no CPU path")
+    sid = scene_id if scene_id is not None else model.cur_id
+    pp = _planes_pass(model, sid, _state["precision"])
+    x = x.float()
+    n = x.shape[0]
+    pts, dirs = x[:, :3].contiguous(), x[:, 3:6].contiguous()
+    vfeat = ops.viewdir_gather(dirs, pp.planes)
+    zero_d = torch.zeros_like(pts)
+    z0 = torch.zeros((n, 1), dtype=torch.float32, device=x.device)
+    sparse, _state["sparse_rgb"] = _state["sparse_rgb"], False       # every row's colour is wanted here
+    try:
+        raw, _ = pp.radiance(pts, zero_d, vfeat, 0.0, 1.0, False, 1, z_in=z0)
+    finally:
+        _state["sparse_rgb"] = sparse
+    return ops.raw_to_nsc(raw, n, 1, pp.rows).reshape(n, 4).contiguous()
+
+
 def eval_nerf(height, width, focal_length, model_coarse, model_fine, ray_origins, ray_directions, options, scene_id,
               mode="validation", encode_position_fn=None, encode_direction_fn=None, scene_config={}):
     """Drop-in for train_utils.eval_nerf (train_utils.py:285-331): full-image synthesis; like the

@@ -131,9 +131,10 @@ def _skip(model, layer_num):  # models.py:203-207
 
 def planes_decode(model, pos, view):
     """Decoder half (models.py:393-421), eval mode => ensemble member '0'."""
-    assert model.proj_combination == "avg" and model.viewdir_proj_combination == "concat_pos"
+    assert model.proj_combination in ("avg", "sum") and model.viewdir_proj_combination == "concat_pos"
     assert model.rgb_dec_input == "projections" and model.use_viewdirs
-    mean = torch.stack(pos, 0).mean(0)
+    # combine_pos_planes (models.py:355-361)
+    mean = torch.stack(pos, 0).mean(0) if model.proj_combination == "avg" else torch.stack(pos, 0).sum(0)
     h = 1 * mean
     for i, lin in enumerate(model.density_dec["0"]):
         if _skip(model, i - 1):

@@ -1,5 +1,8 @@
-cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-echo "=== fp32 tests" ; timeout 900 python -m pytest tests -m gpu -q -k "not bf16 and not fp16 and not 16bit and not full" --maxfail=40 --tb=short -s -p no:cacheprovider > gpurun_out/r1_t_fp32.log 2>&1; echo "rc=$?"; grep -v "^E    +\|Warning" gpurun_out/r1_t_fp32.log | tail -50
-echo "=== 16-bit tests" ; timeout 900 python -m pytest tests -m gpu -q -k "bf16 or fp16 or 16bit or full" --maxfail=40 --tb=short -s -p no:cacheprovider > gpurun_out/r1_t_16.log 2>&1; echo "rc=$?"; grep -v "^E    +\|Warning" gpurun_out/r1_t_16.log | tail -70
-echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-echo "=== bench"; timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r1_bench.json 2> gpurun_out/r1_bench.err; echo "rc=$?"; tail -3 gpurun_out/r1_bench.err; cat gpurun_out/r1_bench.json
+#!/bin/bash
+# Full GPU test pass + smoke; the parity-chain figures go to gpurun_out/parity_chain.jsonl.
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out; rm -f gpurun_out/parity_chain.jsonl
+export NVSR_PARITY_REPORT=$GRAFT_REPO_ROOT/gpurun_out/parity_chain.jsonl
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=30 --tb=short -p no:cacheprovider -rA > gpurun_out/t_gpu.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|error" gpurun_out/t_gpu.log | tail -5; grep -E "^(FAILED|ERROR)" gpurun_out/t_gpu.log | head -40
+echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v Warning | tail -6
+echo "=== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json

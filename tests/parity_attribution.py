@@ -35,8 +35,8 @@ from oracle import nvsr_oracle as O
 # compared relative to the far bound) of rays without a last-sample step.  B_free: the same for the free-running fine maps.
 BOUNDS = {
     "fp32": dict(sigma=1e-3, logit=1e-4, B=1e-3, B_free=1e-3),
-    "fp16": dict(sigma=0.15, logit=2e-3, B=1e-2, B_free=3e-2),
-    "bf16": dict(sigma=1.0, logit=1.5e-2, B=6e-2, B_free=1.2e-1),
+    "fp16": dict(sigma=0.15, logit=2e-3, B=1e-2, B_free=5e-2),
+    "bf16": dict(sigma=1.0, logit=1.5e-2, B=6e-2, B_free=1.5e-1),
 }
 
 
@@ -56,6 +56,11 @@ def _oracle(c, randoms=None, trace=None):
         for m in (mc, mf):
             if hasattr(m, "box_coords"):
                 m.box_coords = {k: v.cpu() for k, v in m.box_coords.items()}
+            sr = getattr(m, "SR_model", None)          # stored / cached SR planes are plain tensors, not parameters
+            if sr is not None and hasattr(sr, "SR_planes"):
+                sr.SR_planes = {k: v.cpu() for k, v in sr.SR_planes.items()}
+                if hasattr(sr, "LR_planes"):
+                    sr.LR_planes = {k: v.cpu() for k, v in sr.LR_planes.items()}
     rnd = {k: v.cpu() for k, v in (randoms or {}).items()}
     enc, encd = c.get("enc"), c.get("encd")
     if c.get("kind") == "mip":
@@ -162,7 +167,7 @@ def check_chain(c, prec, out_g, tr_g, randoms=None):
     cfg = c["opt"].nerf.validation
     mip = c.get("kind") == "mip"
     far = float(c["scfg"].far)
-    randoms = dict(randoms or {})
+    randoms = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in (randoms or {}).items()}
     _, rd = _prep_rays(c)
     g = {k: v.detach().cpu() for k, v in tr_g.items()}
     out = [None if o is None else o.detach().cpu() for o in out_g[:6]]

@@ -19,8 +19,14 @@ CASES = {
 }
 
 
-def build_case(name, device="cpu"):
-    c = CASES[name]
+_DEFAULT = object()
+
+
+def build_case(name, device="cpu", rays=_DEFAULT):
+    """`rays`: how many rays of the frame to take (None = the whole frame); default = the case's own figure"""
+    c = dict(CASES[name])
+    if rays is not _DEFAULT:
+        c["rays"] = rays
     H, W = c["res"]
     enc = encd = None
     if c["kind"] == "planes":

@@ -41,7 +41,7 @@ def _fake_package(state):
     ops = types.SimpleNamespace(LAUNCHES={}, PROFILE=None)
     pkg = types.ModuleType("nvsr_b200")
     pkg.ops = ops
-    pkg.render = types.SimpleNamespace(_state={"ray_chunk": 327680, "sparse_rgb": True})
+    pkg.render = types.SimpleNamespace(_state={"ray_chunk": 327680, "sparse_rgb": True}, clear_caches=lambda: None)
     pkg.set_precision = lambda p: state.__setitem__("precision", p)
     pkg.set_ray_chunk = lambda n: None
     pkg.set_sparse_rgb = lambda on: state.__setitem__("sparse", bool(on))
@@ -64,8 +64,8 @@ def _fake_package(state):
         z3, z1 = torch.zeros(n, 3), torch.zeros(n)
         return (z3, z1, z1, z3, z1, z1, None, None, None)
 
-    pkg.render_frame = lambda H, W, focal, pose, mc, mf, opt, sid, scfg, row_range=None: frame((row_range[1] - row_range[0]) * W)
-    pkg.run_one_iter_of_nerf = lambda H, W, focal, mc, mf, batch, opt, sid, mode, scene_config=None: frame(batch.shape[1])
+    pkg.render_frame = lambda H, W, focal, pose, mc, mf, opt, sid, scfg, row_range=None, **kw: frame((row_range[1] - row_range[0]) * W)
+    pkg.run_one_iter_of_nerf = lambda H, W, focal, mc, mf, batch, opt, sid, mode, scene_config=None, **kw: frame(batch.shape[1])
     pkg.get_ray_bundle = lambda H, W, focal, pose, row_range=None: (torch.zeros(row_range[1] - row_range[0], W, 3),) * 2
     return pkg
 
@@ -99,9 +99,19 @@ def _patch_bench(setattr_, setitem, state, argv, elapsed_ms=10.0):
                              else real_empty(*a, **k))
     setattr_(bench, "torch", Proxy(torch, cuda=cuda, device=lambda *a, **k: torch.device("cpu"), empty=small))
     setattr_(bench, "ClockSampler", _Clock)
-    setattr_(bench, "build_scene", lambda dev: (None, None, "sid", torch.eye(4), 1111.0, None, None))
-    setattr_(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2000.0, "cores": 8, "sample": "fake"})
-    setattr_(bench, "RES", 16)
+    def fake_workload(name, dev):
+        spec = dict(bench.WORKLOADS[name], H=16, W=16)
+        w = bench.Workload(name, **spec)
+        w.mc = w.mf = w.opt = w.scfg = None
+        w.sid, w.pose, w.focal = "sid", torch.eye(4), 1111.0
+        if name == "cfg5":
+            w.sids = ["s%d" % i for i in range(8)]
+        return w
+
+    setattr_(bench, "build_workload", fake_workload)
+    setattr_(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2000.0, "evals_per_s": 512000.0, "ms_per_step": 5.0, "cores": 8,
+                                                    "cpu_model": "fake", "sample": "fake", "rays": 100})
+    setattr_(bench, "time_torch_gpu_frame", lambda w, dev, **k: {"ms_per_step": 2000.0, "value": 128.0, "unit": "rays/s"})
     setattr_(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     setattr_(sys, "argv", ["bench.py"] + argv)
     return pkg
@@ -117,13 +127,21 @@ def test_bench_line_contract(monkeypatch, capfd, flags, headline_sparse):
     assert len(out) == 1
     d = json.loads(out[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "kernels", "cpu_baseline"):
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "kernels", "cpu_baseline",
+              "configs", "precision_modes", "torch_gpu_baseline"):
         assert k in d, k
+    assert sorted(d["configs"]) == ["cfg1", "cfg2", "cfg3a", "cfg3b", "cfg4", "cfg5"]
+    assert all(c["value"] > 0 and c["ms_per_step"] > 0 for c in d["configs"].values())
+    assert d["configs"]["cfg5"]["frames_timed"] == 8 and d["configs"]["cfg2"]["note"] == "the headline of this line"
+    assert d["cpu_baseline"]["cfg1"]["value"] > 0
     assert d["config"]["sparse_rgb"] is headline_sparse and d["steps"] == 4 and d["n_gpus"] == 1
     assert d["per_step"] == {"median_ms": 10.0, "min_ms": 10.0, "max_ms": 10.0, "rank": 0}
     assert d["ms_per_step"] == pytest.approx(10.0 / 4)
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     fp32 = "fp32" in flags
+    assert (d["precision_modes"] is None) == fp32 and (d["torch_gpu_baseline"] is None) == fp32
+    if not fp32:
+        assert d["precision_modes"]["fp32"]["value"] > 0 and state["precision"] == "fp16"
     comp = "dense" if headline_sparse else "sparse"
     assert comp in d and (d[comp] is None) == fp32
     if not fp32:
@@ -180,8 +198,10 @@ def test_two_rank_bench_flow_issues_the_same_collectives_on_every_rank(tmp_path)
 def test_reference_arm_line_contract(monkeypatch, capfd):
     """`bench.py --impl reference`: rank 0 prints one line with impl / cpu_baseline / zero-byte e2e on the b200 arm's
     metric and unit; other ranks print nothing and return."""
-    monkeypatch.setattr(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2345.0, "ms_per_step": 982.0, "rays": 2304, "cores": 24,
-                                                               "sample": "fake lattice"})
+    monkeypatch.setattr(bench, "time_cpu_oracle", lambda **k: {"rays_per_s": 2345.0, "evals_per_s": 2345.0 * 256, "ms_per_step": 982.0,
+                                                               "rays": 2304, "cores": 24, "sample": "fake lattice",
+                                                               "workload": bench.WORKLOADS[k.get("config", "cfg2")]["workload"],
+                                                               "metric": "rays/s (800x800 render, 64 coarse + 128 fine samples/ray)"})
     for rank, expect in ((0, 1), (1, 0)):
         monkeypatch.setenv("RANK", str(rank))
         monkeypatch.setenv("WORLD_SIZE", "2")

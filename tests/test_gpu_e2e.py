@@ -16,35 +16,9 @@ from nvsr_b200 import ops, scene
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# stated tolerances (north_star): fp32-accumulate mode 1e-3 abs on rgb/acc/depth;
-# bf16 mode: planes, features, weights and hidden activations are rounded to bf16 (fp32 accumulate)
+# fp32 mode: the north-star bound, 1e-3 abs on rgb / acc / depth.  The 16-bit modes and every full-size case go through
+# the explained-outlier gate of tests/parity_attribution.py (test_gpu_parity_chain.py): max-norm bounds, no percentiles.
 FP32_TOL = 1e-3
-# 16-bit modes: (p95, mean) abs-error bounds on rgb/acc maps.  A max-norm bound is ill-posed here: the
-# reference's last interval is 1e10 long (volume_rendering_utils.py:20-27), so alpha_last is a STEP in
-# sigma_last at 0 and any rounding of sigma (0.3 abs in bf16, 0.05 in fp16, at |sigma| ~ 50) flips it on
-# the few rays where sigma_last ~ 0; the resampling adds its own discontinuities.  The small
-# golden scenes use 16 coarse samples (0.25-long intervals, ~1 with lindisp), which amplify sigma rounding.
-TOL16_SMALL = {"bf16": (4e-2, 1.5e-2), "fp16": (6e-3, 2.5e-3)}
-TOL16_FULL = {"bf16": (1.5e-2, 5e-3), "fp16": (3e-3, 1.2e-3)}   # config-2 sized sampling (64+128)
-
-
-def _stats16(out, ref):
-    st = {}
-    for k, v, r in zip(NAMES, out[:6], ref[:6]):
-        if r is None or v is None or "disp" in k:
-            # disp (unbounded, NaN where acc == 0) is covered by the fp32 tests: under 16-bit rounding
-            # a sigma crossing 0 legitimately changes its NaN pattern
-            continue
-        r = r if torch.is_tensor(r) else T(r)
-        d = (v.detach().cpu() - r).abs().reshape(r.shape[0], -1).max(-1)[0]   # per ray
-        st[k] = (float(d.quantile(0.95)), float(d.mean()), float(d.max()))
-    return st
-
-
-def _check16(tag, st, tol):
-    print(tag, {k: "p95 %.1e mean %.1e max %.1e" % v for k, v in st.items()})
-    for k, (p95, mean, mx) in st.items():
-        assert p95 <= tol[0] and mean <= tol[1], (tag, k, p95, mean, mx)
 FLIP_TOL = 0.25       # fine maps of rays whose resampling index legitimately flipped (see below)
 
 
@@ -100,7 +74,9 @@ def test_e2e_fp32_vs_reference_golden(name):
     if "inds" in tc:
         u = T(g["u"]) if "u" in g else torch.linspace(0.0, 1.0, tc["inds"].shape[1])
         flips = _flip_rays(tg, tc, int(g["num_fine"]), u)
-        assert float(flips.float().mean()) <= 0.25
+        # every flip was checked to sit within 2 ulp of a cdf edge; and they are rare per SAMPLE (a ray holds
+        # num_fine chances, so the per-ray share is much larger than the per-sample one)
+        assert float((tg["inds"].cpu() != tc["inds"]).float().mean()) <= 0.01
         assert torch.equal(tg["z_coarse"].cpu(), tc["z_coarse"])       # stratified depths: bit-exact
         H.assert_close(tg["weights_coarse"], tc["weights_coarse"], 1e-4, what="coarse weights")
     w_all = _errors(out, gold)
@@ -111,14 +87,6 @@ def test_e2e_fp32_vs_reference_golden(name):
         assert v <= FP32_TOL, (name, k, v)
     for k, v in w_all.items():
         assert v <= (FP32_TOL if "coarse" in k else FLIP_TOL), (name, k, v)
-
-
-@pytest.mark.parametrize("prec", ["bf16", "fp16"])
-@pytest.mark.parametrize("name", [n for n in E2E if "mip" not in n])
-def test_e2e_16bit_vs_reference_golden(name, prec):
-    nvsr_b200.set_precision(prec)
-    g, out = run_oracle_e2e(name, DEV, runner=nvsr_b200.run_one_iter_of_nerf)
-    _check16(f"{name} {prec}", _stats16(out, [g.get(k) for k in NAMES]), TOL16_SMALL[prec])
 
 
 def test_fine_pass_teacher_forced():
@@ -156,45 +124,37 @@ def test_trace_indices_bit_exact_given_same_weights():
 @pytest.mark.parametrize("channels,res", [(32, 96), (16, 40), (64, 64)])
 def test_other_plane_shapes_vs_oracle(channels, res):
     """Plane channel counts other than the reference default (48) take the run-time-chunk-count gather and other
-    decoder input widths (K = C and 3C); ragged ray / sample counts (37 x 37 rays, 24 + 40 samples) on top."""
-    import copy
+    decoder input widths (K = C and 3C); ragged ray / sample counts (37 x 37 rays, 24 + 40 samples) on top.  Every
+    precision mode goes through the explained-outlier gate (max-norm bounds, parity_attribution)."""
+    import parity_attribution as PA
     mc, mf, sid = scene.make_synthetic_scene(plane_res=res, view_res=12, channels=channels, seed=3, device=DEV)
     pose, focal = scene.blender_camera(37)
     opt, scfg = scene.render_options(24, 40), scene.scene_cfg()
     with torch.no_grad():
         ro, rd = nvsr_b200.get_ray_bundle(37, 37, focal, pose.to(DEV))
-        batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
-        tc = {}
-        ref = O.run_one_iter_of_nerf(37, 37, focal, copy.deepcopy(mc).cpu(), copy.deepcopy(mf).cpu(), batch.cpu(), opt,
-                                     sid, "validation", scene_config=scfg, trace=tc)
-        nvsr_b200.set_precision("fp32")
-        tg = {}
-        out = nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg,
-                                             trace=tg)
-        flips = _flip_rays(tg, tc, 40, torch.linspace(0.0, 1.0, 40))
-        assert torch.equal(tg["z_coarse"].cpu(), tc["z_coarse"])
-        for k, v in _errors(out, ref, ~flips).items():
-            if "coarse" in k:      # coarse maps: the 1e-3 contract everywhere
-                assert v <= FP32_TOL, (channels, k, v)
-        # fine maps: free-running resampling is ill-conditioned in the reference itself (see
-        # test_full_size_subset_vs_oracle): 1e-3 on >= 99 % of the rays, small mean, bounded max
-        for k, a, b in zip(NAMES, out[:6], ref[:6]):
-            if "fine" in k and "disp" not in k:
-                d = (a.cpu() - b).abs()
-                frac = float((d <= FP32_TOL).float().mean())
-                assert frac >= 0.99 and float(d.mean()) <= 5e-5 and float(d.max()) <= 2e-2, (channels, k, frac, float(d.mean()), float(d.max()))
-        for prec in ("fp16", "bf16"):
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    c = dict(H=37, W=37, focal=focal, mc=mc, mf=mf, sid=sid, opt=opt, scfg=scfg, batch=batch, enc=None, encd=None,
+             kind="planes")
+    try:
+        for prec in ("fp32", "fp16", "bf16"):
             nvsr_b200.set_precision(prec)
-            if channels > 48:
+            nvsr_b200.set_sparse_rgb(False)
+            if prec != "fp32" and channels > 48:
                 # 3C = 192 input columns: resident rgb weights + the two ring buffers exceed the 227 KB of shared
                 # memory of the tensor-core decoder — refused loudly (fp32 parity mode above still serves it)
-                with pytest.raises(nvsr_b200.NvsrError, match="resource"):
+                with torch.no_grad(), pytest.raises(nvsr_b200.NvsrError, match="resource"):
                     nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
                 torch.cuda.synchronize()
                 continue
-            o16 = nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
-            _check16(f"C={channels} {prec}", _stats16(o16, ref), TOL16_SMALL[prec])
-    nvsr_b200.set_precision("fp16")
+            tg = {}
+            with torch.no_grad():
+                out = nvsr_b200.run_one_iter_of_nerf(37, 37, focal, mc, mf, batch, opt, sid, "validation",
+                                                     scene_config=scfg, trace=tg)
+            rep = PA.check_chain(c, prec, out, tg)
+            print(f"C={channels} {prec}", {k: v for k, v in rep.items() if "unexplained" in k})
+    finally:
+        nvsr_b200.set_sparse_rgb(True)
+        nvsr_b200.set_precision("fp16")
 
 
 def test_multi_scene_shared_decoder():
@@ -304,48 +264,6 @@ def big_scene():
     return mc, mf, sid, pose.to(DEV), focal
 
 
-def test_full_size_subset_vs_oracle(big_scene):
-    """config-2 scene (R=200, 64+128): 1024 rays spread over the 800x800 frame vs the CPU oracle."""
-    mc, mf, sid, pose, focal = big_scene
-    opt, scfg = scene.render_options(64, 128), scene.scene_cfg()
-    ro, rd = nvsr_b200.get_ray_bundle(800, 800, focal, pose)
-    idx = torch.randperm(640000, generator=torch.Generator().manual_seed(0))[:1024].to(DEV)
-    batch = torch.stack([ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx]], 0)
-    import copy
-    mc_c, mf_c = copy.deepcopy(mc).cpu(), copy.deepcopy(mf).cpu()
-    with torch.no_grad():
-        tc = {}
-        ref = O.run_one_iter_of_nerf(800, 800, focal, mc_c, mf_c, batch.cpu(), opt, sid, "validation", scene_config=scfg,
-                                     trace=tc)
-        nvsr_b200.set_precision("fp32")
-        tg = {}
-        out = nvsr_b200.run_one_iter_of_nerf(800, 800, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg,
-                                             trace=tg)
-        flips = _flip_rays(tg, tc, 128, torch.linspace(0.0, 1.0, 128))
-        w_ok, w_all = _errors(out, ref, ~flips), _errors(out, ref)
-        print("full-size fp32: flip rays %d/1024" % int(flips.sum()), {k: "%.1e" % v for k, v in w_ok.items()},
-              "| incl. flips:", {k: "%.1e" % v for k, v in w_all.items() if "fine" in k})
-        # coarse maps: 1e-3 everywhere.  Fine maps: free-running resampling is ill-conditioned in the
-        # reference itself (a 2e-5 change of sigma moves the oracle's own fine maps by up to 4e-3 on
-        # this scene, DESIGN.md "conditioning"), so: 1e-3 on >= 99.5% of the rays, mean <= 2e-5, and the
-        # teacher-forced fine pass (test_fine_pass_teacher_forced) covers the fine kernels at 1e-4.
-        for k, v in w_all.items():
-            if "coarse" in k:
-                assert v <= FP32_TOL, ("fp32", k, v)
-        for k, a, b in zip(NAMES, out[:6], ref[:6]):
-            if "fine" in k and "disp" not in k:
-                d = (a.cpu() - b).abs()
-                frac = float((d <= FP32_TOL).float().mean())
-                assert frac >= 0.995 and float(d.mean()) <= 2e-5 and float(d.max()) <= 2e-2, (k, frac, float(d.mean()), float(d.max()))
-        assert float(flips.float().mean()) < 0.25
-        for prec in ("bf16", "fp16"):
-            nvsr_b200.set_precision(prec)
-            out = nvsr_b200.run_one_iter_of_nerf(800, 800, focal, mc, mf, batch, opt, sid, "validation", scene_config=scfg)
-            _check16(f"full-size {prec}", _stats16(out, ref), TOL16_FULL[prec])
-    acc = ref[5]
-    assert 0.02 < float((acc > 0.5).float().mean()) < 0.995   # the synthetic scene is not degenerate
-
-
 def test_full_frame_properties(big_scene):
     """800x800, 64+128 (BASELINE config 2): chunk-size invariance, row-band sharding == full frame,
     eval_nerf shape contract."""
@@ -367,3 +285,19 @@ def test_full_frame_properties(big_scene):
         assert torch.equal(full[0], again[0]) and torch.equal(full[3], again[3])
         band = nvsr_b200.render_frame(800, 800, focal, pose, mc, mf, opt, sid, scfg, row_range=(300, 400))
         assert torch.equal(band[3].reshape(100, 800, 3), full[3][300:400])
+
+
+def test_config1_whole_frame_call_surface():
+    """BASELINE configs[0] (100x100 view, 64 coarse samples, no fine pass) through eval_nerf: ray order bit-exact
+    against the oracle's get_ray_bundle, the reference's 9-tuple contract (fine slots None), finite image.  Its
+    parity — every map of the whole frame, every precision — is test_gpu_parity_chain.py::test_baseline_config_chain[cfg1]."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=0, device=DEV)
+    pose, focal = scene.blender_camera(100)
+    opt, scfg = scene.render_options(64, 0), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(100, 100, focal, pose.to(DEV))
+        ro_o, rd_o = O.get_ray_bundle(100, 100, focal, pose)
+        assert torch.equal(ro.cpu(), ro_o) and torch.equal(rd.cpu(), rd_o)
+        out = nvsr_b200.eval_nerf(100, 100, focal, mc, mf, ro, rd, opt, sid, scene_config=scfg)
+    assert out[0].shape == (100, 100, 3) and all(o is None for o in out[1:])
+    assert bool(torch.isfinite(out[0]).all())

@@ -1,11 +1,8 @@
-"""GPU parity of the §8f rows written at the end of round 1 — backward kernels (rank 1), frame sink (rank 4), plane store
-device staging (rank 3) — through the C-ABI.
-
-These kernels were written after the round's GPU budget was spent: their arithmetic is verified on the CPU (the
-kernels' own per-element source compiled for the host, tests/test_backward_bodies.py), but the CUDA launch path has
-never run.  The tests are therefore marked xfail(strict=False): an XPASS in the driver's GPU run is the first
-confirmation, an xfail shows what round 2 has to fix — neither hides the state of the forward path's tests.
-The file sorts last on purpose.
+"""GPU parity of the SURVEY §8f rows — backward kernels of the gather and compositing stages (rank 1), frame sink
+(rank 4), plane store device staging (rank 3) — through the C-ABI, against autograd of the oracle and against
+gradients produced by the reference's own training step (tests/golden/backward_planes_train.npz).  The kernels'
+per-element arithmetic is additionally verified on the CPU (tests/test_backward_bodies.py compiles the kernels' own
+source for the host), and tests/test_gpu_tests_dry_run.py runs these very test functions on the CPU with host stand-ins.
 """
 import numpy as np
 import pytest
@@ -16,8 +13,7 @@ import nvsr_b200
 from nvsr_b200 import autograd as A, ops, scene
 from oracle import nvsr_oracle as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),     # never-run device code must not be able to hang the suite
-              pytest.mark.xfail(strict=False, reason="8f rows: CPU-verified bodies, first GPU run (see module docstring)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda:0"
 
 
@@ -25,7 +21,8 @@ def _close(got, want, rel):
     got, want = got.detach().float().cpu(), want.detach().float().cpu()
     scale = float(want.abs().max()) + 1e-30
     err = float((got - want).abs().max())
-    assert err <= rel * scale, f"max abs err {err:.3e} vs scale {scale:.3e}"
+    # + 1e-7: fp32 summation-order noise of the atomics on gradients whose own scale is ~1e-6
+    assert err <= rel * scale + 1e-7, f"max abs err {err:.3e} vs scale {scale:.3e}"
 
 
 @pytest.mark.parametrize("white,noise_std,mip", [(False, 0.0, False), (True, 0.6, False), (True, 0.3, True)])
@@ -87,33 +84,59 @@ def test_gather_bwd_matches_oracle_autograd():
         _close(leaves[d].grad, want[d], 5e-5)      # atomics: summation order differs
 
 
-def test_train_step_gradients_match_reference_golden():
-    """The whole train-mode step through nvsr_b200.autograd.run_one_iter_of_nerf against the gradients the reference's
-    loss.backward() produced (tests/golden/backward_planes_train.npz)."""
+def _train_case():
     g = H.golden("backward_planes_train.npz")
     sid = str(g["scene_id"])
-    mc, mf = H.load_planes_scene(str(g["scene_file"]), sid, DEV)
-    opt, scfg, rnd = H.options_from(g), H.scene_cfg_from(g), H.randoms_from(g, DEV)
-    batch = torch.stack([H.T(g["ro"]).reshape(-1, 3), H.T(g["rd"]).reshape(-1, 3)], 0).to(DEV)
-    target = H.T(g["target"], DEV)
+    opt, scfg = H.options_from(g), H.scene_cfg_from(g)
+    batch = torch.stack([H.T(g["ro"]).reshape(-1, 3), H.T(g["rd"]).reshape(-1, 3)], 0)
+    return g, sid, opt, scfg, batch
+
+
+def _named_params(mc, mf):
     named = {"plane__" + k: p for k, p in mc.planes_.items()}
     for prefix, m in (("coarse__", mc), ("fine__", mf)):
         for k, p in m.named_parameters():
             if "planes_" not in k and "rot_mats" not in k:
                 named[prefix + k.replace(".", "__")] = p
-    out = A.run_one_iter_of_nerf(int(g["H"]), int(g["W"]), float(g["focal"]), mc, mf, batch, opt, sid, "train",
-                                 scene_config=scfg, randoms=rnd)
-    loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
-    loss.backward()
-    # forward agreement CPU reference vs GPU: the decoder runs on cuBLAS fp32 there (another summation order)
-    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-4
-    H.assert_close(out[0], g["rgb_coarse"], 2e-4, what="rgb_coarse")
-    for k in [k[len("grad__"):] for k in g if k.startswith("grad__")]:
-        assert named[k].grad is not None, k
-        # end to end the hierarchical resampling is ill-conditioned in the reference itself (DESIGN.md §2: a 2e-5 change
-        # of sigma moves the fine maps by up to 4e-3), and the fine pass contributes to most gradients — the tight
-        # gradient checks are the stage tests above (5e-5 / 2e-4); here: same gradient to a few percent of its scale
-        _close(named[k].grad, torch.from_numpy(g["grad__" + k]), 3e-2)
+    return named
+
+
+def test_train_step_gradients_match_reference_golden():
+    """The whole train-mode step through nvsr_b200.autograd.run_one_iter_of_nerf against the gradients the reference's
+    loss.backward() produced (tests/golden/backward_planes_train.npz).
+
+    Free-running, the hierarchical resampling is ill-conditioned in the reference itself (an index flip within 2 ulp of a
+    cdf edge moves a fine sample by a bin — parity_attribution (i)), so the TIGHT gate is teacher-forced: the fine pass
+    runs at the merged depths the ORACLE's forward produced (which reproduces the reference's golden step to 1e-6 on
+    the CPU, tests/test_backward_bodies.py), and every gradient must then agree with the reference's to 1e-3 of its
+    scale.  The free-running step is checked as well, with the conditioning-limited tolerance."""
+    g, sid, opt, scfg, batch = _train_case()
+    target = H.T(g["target"], DEV)
+    rnd = H.randoms_from(g, DEV)
+    # oracle forward on the CPU: the merged depths of the reference's step
+    mc_o, mf_o = H.load_planes_scene(str(g["scene_file"]), sid, "cpu")
+    tc = {}
+    with torch.no_grad():
+        O.run_one_iter_of_nerf(int(g["H"]), int(g["W"]), float(g["focal"]), mc_o, mf_o, batch, opt, sid, "train",
+                               scene_config=scfg, randoms=H.randoms_from(g), trace=tc)
+    for forced, tol in ((True, 1e-3), (False, 3e-2)):
+        mc, mf = H.load_planes_scene(str(g["scene_file"]), sid, DEV)
+        named = _named_params(mc, mf)
+        r = dict(rnd, z_fine=tc["z_fine"].to(DEV)) if forced else dict(rnd)
+        out = A.run_one_iter_of_nerf(int(g["H"]), int(g["W"]), float(g["focal"]), mc, mf, batch.to(DEV), opt, sid, "train",
+                                     scene_config=scfg, randoms=r)
+        loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
+        loss.backward()
+        # forward agreement CPU reference vs GPU: the decoder runs on cuBLAS fp32 there (another summation order)
+        assert abs(float(loss.detach()) - float(g["loss"])) <= (2e-5 if forced else 1e-4)
+        H.assert_close(out[0], g["rgb_coarse"], 2e-4, what="rgb_coarse")
+        worst = 0.0
+        for k in [k[len("grad__"):] for k in g if k.startswith("grad__")]:
+            assert named[k].grad is not None, k
+            want = torch.from_numpy(g["grad__" + k])
+            worst = max(worst, float((named[k].grad.cpu() - want).abs().max()) / (float(want.abs().max()) + 1e-30))
+            _close(named[k].grad, want, tol)
+        print("train step vs reference gradients (%s): worst relative error %.2e" % ("teacher-forced" if forced else "free-running", worst))
 
 
 def test_gather_bwd_full_batch_mass_conservation():
@@ -154,19 +177,22 @@ def test_mip_train_step_gradients_match_oracle_autograd():
            "noise_c": torch.randn(n, Nc, generator=gen), "noise_f": torch.randn(n, Nc + Nf + 1, generator=gen)}
     target = torch.rand(n, 3, generator=gen)
     Hh, Ww, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    tc = {}
     out_o = O.run_one_iter_of_nerf(Hh, Ww, f, mc, mf, batch, opt, sid, "train",
                                    encode_position_fn=lambda m: O.integrated_pos_enc(m[0], m[1], 7),
-                                   encode_direction_fn=lambda x: O.positional_encoding(x, 4, True), scene_config=scfg, randoms=rnd)
+                                   encode_direction_fn=lambda x: O.positional_encoding(x, 4, True), scene_config=scfg, randoms=rnd,
+                                   trace=tc)
     (((out_o[0] - target) ** 2).mean() + ((out_o[3] - target) ** 2).mean()).backward()
     out_g = A.run_one_iter_of_nerf(Hh, Ww, f, mc_g, mf_g, batch.to(DEV), opt, sid, "train",
                                    encode_position_fn=nvsr_b200.IntegratedPositionalEncoding(3, 7), encode_direction_fn=object(),
-                                   scene_config=scfg, randoms={k: v.to(DEV) for k, v in rnd.items()})
+                                   scene_config=scfg,
+                                   randoms=dict({k: v.to(DEV) for k, v in rnd.items()}, z_fine=tc["z_fine"].detach().to(DEV)))
     (((out_g[0] - target.to(DEV)) ** 2).mean() + ((out_g[3] - target.to(DEV)) ** 2).mean()).backward()
     H.assert_close(out_g[0], out_o[0].detach(), 2e-4, what="rgb_coarse")
     for (k, a), b in zip(list(mc_g.named_parameters()) + list(mf_g.named_parameters()), list(mc.parameters()) + list(mf.parameters())):
         assert (a.grad is None) == (b.grad is None), k
         if b.grad is not None and float(b.grad.abs().max()) > 0:
-            _close(a.grad, b.grad, 3e-2)      # see the planes test: conditioning of the resampling
+            _close(a.grad, b.grad, 1e-3)      # teacher-forced fine depths (see the planes test)
 
 
 def test_frozen_decoder_coarse_pass_on_the_forward_kernels():
@@ -197,8 +223,7 @@ def test_frozen_decoder_coarse_pass_on_the_forward_kernels():
     assert any(p.grad is not None for p in mf.rgb_dec.parameters())
 
 
-# ---- the other §8f rows written at the end of round 1 (frame sink, plane store): kept here so that a fault in
-# never-run device code cannot disturb the forward path's tests, which sort before this file
+# ---- the other §8f rows: frame sink (rank 4), plane store staging (rank 3)
 def test_gpu_frame_sink_matches_write_image(tmp_path):
     from nvsr_b200 import frames
     from test_frames import reference_u8
@@ -240,32 +265,3 @@ def test_gpu_attach_overlaps_and_renders(tmp_path):
         want_dtype = nvsr_b200.NVSR_F32 if d == 3 else nvsr_b200.NVSR_F16
         assert want_dtype in hit[2]
         assert torch.equal(hit[2][want_dtype], ops.pack_plane(params[k], want_dtype))
-
-
-# ---- BASELINE.json config 1 at its exact size (the reference's own CPU-runnable case): written with the rows above, so it
-# shares their xfail hedge although it only drives the forward kernels the earlier files already verify
-def test_config1_100x100_coarse_only_vs_oracle():
-    """configs[0]: synthetic Blender-shaped scene, 100x100 view, 64 coarse samples per ray, no fine pass — the whole frame
-    against the CPU oracle (fp32 mode: 1e-3 abs on every map, disp NaN pattern identical; fp16 mode: stated p95 / mean)."""
-    import copy
-    mc, mf, sid = scene.make_synthetic_scene(plane_res=200, view_res=32, seed=0, device=DEV)
-    pose, focal = scene.blender_camera(100)
-    opt, scfg = scene.render_options(64, 0), scene.scene_cfg()
-    prec = nvsr_b200.get_precision()
-    try:
-        with torch.no_grad():
-            ro, rd = nvsr_b200.get_ray_bundle(100, 100, focal, pose.to(DEV))
-            ro_o, rd_o = O.get_ray_bundle(100, 100, focal, pose)
-            assert torch.equal(ro.cpu(), ro_o) and torch.equal(rd.cpu(), rd_o)                  # ray order bit-exact
-            ref = O.eval_nerf(100, 100, focal, copy.deepcopy(mc).cpu(), copy.deepcopy(mf).cpu(), ro_o, rd_o, opt, sid,
-                              scene_config=scfg)
-            nvsr_b200.set_precision("fp32")
-            out = nvsr_b200.eval_nerf(100, 100, focal, mc, mf, ro, rd, opt, sid, scene_config=scfg)
-            assert out[3] is None and ref[3] is None and out[0].shape == (100, 100, 3)
-            H.assert_close(out[0], ref[0], 1e-3, what="rgb_coarse fp32")
-            nvsr_b200.set_precision("fp16")
-            out16 = nvsr_b200.eval_nerf(100, 100, focal, mc, mf, ro, rd, opt, sid, scene_config=scfg)
-            d = (out16[0].cpu() - ref[0]).abs().flatten()
-            assert float(d.quantile(0.95)) <= 3e-3 and float(d.mean()) <= 1.2e-3
-    finally:
-        nvsr_b200.set_precision(prec)

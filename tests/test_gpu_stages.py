@@ -60,9 +60,23 @@ def test_pack_plane_layouts(dtype, tdt, shape):
     torch.manual_seed(11)
     c, rh, rw = shape
     plane = torch.randn(1, c, rh, rw) * 3
-    plane[0, 0, 0, 0] = 1e6     # beyond fp16: saturates to the largest finite value instead of inf
+    plane[0, 0, 0, 0] = 1e6     # beyond fp16
     plane[0, 1, 0, 0] = -1e6
-    out = ops.pack_plane(plane.to(DEV), dtype).cpu()
+    if dtype == NVSR_F16:
+        # the host wrapper refuses a plane that would saturate (silently wrong values otherwise) ...
+        with pytest.raises(nvsr_b200.NvsrError, match="fp16 range"):
+            ops.pack_plane(plane.to(DEV), dtype)
+        # ... and the kernel itself saturates to the largest finite value instead of producing inf
+        import ctypes as C
+        from nvsr_b200 import _lib
+        p_dev = plane.to(DEV).contiguous()
+        raw_out = torch.empty((rh, c // 8, rw, 2, 8), dtype=tdt, device=DEV)
+        st = _lib.load().nvsr_pack_plane(C.c_void_p(p_dev.data_ptr()), c, rh, rw, C.c_void_p(raw_out.data_ptr()), dtype,
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert st == 0
+        out = raw_out.cpu()
+    else:
+        out = ops.pack_plane(plane.to(DEV), dtype).cpu()
     if dtype == NVSR_F32:
         assert out.shape == (rh, rw, c)
         assert torch.equal(out, plane[0].permute(1, 2, 0).contiguous())
@@ -387,3 +401,76 @@ def test_invalid_arguments_fail_loudly():
         ops.composite(torch.zeros(4, 64, device=DEV), torch.zeros(1, 2000, device=DEV), torch.zeros(1, 3, device=DEV), 2000)
     with pytest.raises(nvsr_b200.NvsrError):
         ops.pack_weight16(torch.zeros(128, 48, device=DEV), k_pad=40)
+
+
+# ---- the same-signature stage drop-ins SURVEY.md 8(b) lists -----------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_planes_model_forward_dropin(prec):
+    """`nvsr_b200.planes_model_forward(model, x[n,6]) -> [n,4]` == TwoDimPlanesModel.forward (models.py:381-421) on the
+    reference-generated stage golden: fp32 within the golden's own tolerance, 16-bit modes within the per-mode raw
+    bounds of the parity gate."""
+    import nvsr_b200
+    import parity_attribution as PA
+    g = golden("stage_planes_forward.npz")
+    sid = str(g["scene_id"])
+    mc, _ = H.load_planes_scene("scene_planes_small.npz", sid, DEV)
+    mc.set_cur_scene_id(sid)
+    nvsr_b200.set_precision(prec)
+    try:
+        with torch.no_grad():
+            out = nvsr_b200.planes_model_forward(mc, T(g["x6"], DEV))
+    finally:
+        nvsr_b200.set_precision("fp16")
+    want = T(g["out"])
+    assert out.shape == want.shape
+    bd = PA.BOUNDS[prec]
+    d = (out.cpu() - want).abs()
+    assert float(d[:, 3].max()) <= bd["sigma"] and float(d[:, :3].max()) <= bd["logit"], (float(d[:, 3].max()), float(d[:, :3].max()))
+
+
+def test_proj_combination_sum():
+    """proj_combination='sum' (models.py:355-357): density features = sum of the three projections, in every mode."""
+    import copy
+    import nvsr_b200
+    import parity_attribution as PA
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=40, view_res=12, seed=5, device=DEV)
+    mc.proj_combination = "sum"
+    mc.set_cur_scene_id(sid)
+    g = torch.Generator().manual_seed(2)
+    x6 = torch.cat([torch.rand(777, 3, generator=g) * 2.4 - 1.2, torch.nn.functional.normalize(torch.randn(777, 3, generator=g), dim=-1)], -1)
+    mo = copy.deepcopy(mc).cpu()
+    with torch.no_grad():
+        want = O.planes_model_forward(mo, x6)
+        for prec in ("fp32", "fp16", "bf16"):
+            nvsr_b200.set_precision(prec)
+            out = nvsr_b200.planes_model_forward(mc, x6.to(DEV)).cpu()
+            bd = PA.BOUNDS[prec]
+            # sigma of a 'sum' model is ~3x the 'avg' one's scale: bound relative to that
+            d = (out - want).abs()
+            assert float(d[:, 3].max()) <= 3 * bd["sigma"] and float(d[:, :3].max()) <= bd["logit"], (prec, float(d[:, 3].max()))
+    nvsr_b200.set_precision("fp16")
+    mc.proj_combination = "avg"
+    with torch.no_grad():
+        nvsr_b200.set_precision("fp32")
+        avg = nvsr_b200.planes_model_forward(mc, x6.to(DEV)).cpu()
+        nvsr_b200.set_precision("fp16")
+    assert float((avg[:, 3] - want[:, 3]).abs().max()) > 1e-2      # the switch really changes the density input
+
+
+def test_cast_rays_and_ipe_dropins():
+    """mip.cast_rays (mip.py:9-18) and IntegratedPositionalEncoding.forward((means, covs)) (mip.py:164-191) with the
+    reference's own tensors at the boundary, against the reference-generated stage golden."""
+    import nvsr_b200
+    g = golden("stage_ipe.npz")
+    z, ro, rd = T(g["z"], DEV), T(g["ro"], DEV), T(g["rd"], DEV)
+    n = z.shape[0]
+    radius = float(g["radius"])
+    for radii in (radius, torch.full((n, 1), radius, device=DEV)):       # scalar, or the reference's constant column
+        means, covs = nvsr_b200.cast_rays(z, ro, rd, radii, None)
+        H.assert_close(means, g["means"], 2e-6, what="means")
+        H.assert_close(covs, g["covs"], 1e-7, 1e-5, what="covs")
+    enc = nvsr_b200.IntegratedPositionalEncoding(3, 7)
+    assert enc.max_freq == 6 and enc.out_dims == 36
+    out = enc((T(g["means"], DEV), T(g["covs"], DEV)))
+    H.assert_close(out, g["enc"], 5e-6, what="ipe((means, covs))")
+    assert out.shape == tuple(g["enc"].shape)

@@ -1,4 +1,4 @@
-"""Dry run of the never-run GPU tests of tests/test_gpu_zz_next_rows.py on the CPU: the SAME test functions, with the device
+"""Dry run of the GPU tests of tests/test_gpu_next_rows.py on the CPU: the SAME test functions, with the device
 set to "cpu", the C-ABI calls replaced by the host stand-ins of tests/host_ops.py (the kernels' own bodies built for
 the host), entered right behind the entry points' CUDA-only guards.  What this checks is the tests themselves — their plumbing, shapes and
 tolerances — so that their first run on a B200 measures the kernels and not a typo in a test."""
@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import host_ops as HO
-import test_gpu_zz_next_rows as T
+import test_gpu_next_rows as T
 from nvsr_b200 import ops
 
 

@@ -1,6 +1,6 @@
 """Plane store: the reference's `.par` scene files, read and written with its safe_saving /
 safe_loading protocol (nerf_helpers.py:19-67, models.py:612-678), host staging, and the torch.distributed broadcast.
-Host logic only — the device staging (`to_device` / `attach`) needs a GPU: tests/test_gpu_zz_next_rows.py."""
+Host logic only — the device staging (`to_device` / `attach`) needs a GPU: tests/test_gpu_next_rows.py."""
 import json
 import os
 import shutil
