@@ -108,6 +108,62 @@ class Composite(C.Structure):
     ]
 
 
+class Decoder(C.Structure):
+    _fields_ = [
+        ("density", Layer * MAX_LAYERS),
+        ("n_density", c_i32),
+        ("rgb", Layer * MAX_LAYERS),
+        ("n_rgb", c_i32),
+        ("view_w", c_p),
+        ("view_ldw", c_i32),
+        ("view_b", c_p),
+    ]
+
+
+class Render(C.Structure):
+    _fields_ = [
+        ("precision", c_i32),
+        ("n_rays", c_i64),
+        ("n_coarse", c_i32),
+        ("n_fine", c_i32),
+        ("ro", c_p),
+        ("rd", c_p),
+        ("viewdirs", c_p),
+        ("near_", c_f),
+        ("far_", c_f),
+        ("lindisp", c_i32),
+        ("white_bkgd", c_i32),
+        ("t_vals", c_p),
+        ("t_rand", c_p),
+        ("u", c_p),
+        ("u_per_ray", c_i32),
+        ("noise_c", c_p),
+        ("noise_f", c_p),
+        ("planes_coarse", C.POINTER(Planes)),
+        ("planes_fine", C.POINTER(Planes)),
+        ("vplane_coarse", c_p),
+        ("vplane_fine", c_p),
+        ("vrh", c_i32),
+        ("vrw", c_i32),
+        ("az_lo", c_f),
+        ("az_rng", c_f),
+        ("el_lo", c_f),
+        ("el_rng", c_f),
+        ("dec_coarse", C.POINTER(Decoder)),
+        ("dec_fine", C.POINTER(Decoder)),
+        ("rgb_c", c_p),
+        ("disp_c", c_p),
+        ("acc_c", c_p),
+        ("depth_c", c_p),
+        ("rgb_f", c_p),
+        ("disp_f", c_p),
+        ("acc_f", c_p),
+        ("depth_f", c_p),
+        ("workspace", c_p),
+        ("workspace_bytes", c_i64),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/nvsr.h declares
 SIGNATURES = {
     "nvsr_abi_version": (c_i32, []),
@@ -128,6 +184,8 @@ SIGNATURES = {
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),
     "nvsr_dir_encoding": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_p]),
+    "nvsr_workspace_bytes": (c_i64, [C.POINTER(Render)]),
+    "nvsr_render_rays": (c_i32, [C.POINTER(Render), c_p]),
     "nvsr_cast_rays": (c_i32, [c_p, c_p, c_p, c_p, c_f, c_i64, c_i32, c_p, c_p, c_p]),
     "nvsr_ipe_encode": (c_i32, [c_p, c_p, c_i64, c_i32, c_p, c_p]),
     "nvsr_sample_gather_bwd": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_p, c_p, C.POINTER(c_p), c_p]),

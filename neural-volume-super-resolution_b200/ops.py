@@ -452,6 +452,104 @@ def composite(raw, z, rd, n_samples, noise=None, white_background=False, mip=Fal
     return out
 
 
+def _fill_layers(dst, layers):
+    for i, ly in enumerate(layers):
+        c = dst[i]
+        c.w = ly.w.data_ptr()
+        c.bias = 0 if ly.bias is None else ly.bias.data_ptr()
+        c.row_bias = 0
+        c.head_w = 0 if ly.head_w is None else ly.head_w.data_ptr()
+        c.head_b = 0 if ly.head_b is None else ly.head_b.data_ptr()
+        c.k, c.n_out, c.relu = ly.k, ly.n_out, int(bool(ly.relu))
+        c.head_n = 0 if ly.head_w is None else ly.head_w.shape[0]
+        c.head_ch = ly.head_ch
+
+
+def decoder_struct(dec):
+    """nvsr_decoder_t of a scene.PackedPlanesDecoder (the per-ray bias of rgb[0] is produced inside nvsr_render_rays)"""
+    d = _lib.Decoder()
+    _fill_layers(d.density, dec.density)
+    d.n_density = len(dec.density)
+    _fill_layers(d.rgb, dec.rgb)
+    d.n_rgb = len(dec.rgb)
+    vw = dec.view_w
+    if vw.dtype != torch.float32 or vw.stride(1) != 1:
+        raise _lib.NvsrError("decoder view weights must be fp32 with unit column stride")
+    d.view_w, d.view_ldw, d.view_b = vw.data_ptr(), vw.stride(0), dec.view_b.data_ptr()
+    return d
+
+
+_workspaces = {}   # (device, bytes rounded up) -> uint8 tensor, reused by every later frame of the same shape
+
+
+def _workspace(nbytes, device):
+    key = (str(device), (nbytes + (1 << 20) - 1) >> 20)
+    ws = _workspaces.get(key)
+    if ws is None:
+        for k in [k for k in _workspaces if k[0] == key[0] and k[1] < key[1]]:     # keep only the largest per device
+            del _workspaces[k]
+        big = [v for k, v in _workspaces.items() if k[0] == key[0] and k[1] >= key[1]]
+        ws = big[0] if big else torch.empty((key[1] << 20,), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def render_rays(ro, rd, viewdirs, near, far, packed_c, dec_c, packed_f, dec_f, precision, n_coarse, n_fine, t_vals, u=None,
+                t_rand=None, noise_c=None, noise_f=None, lindisp=False, white_background=False):
+    """nvsr_render_rays: coarse -> fine for one batch of prepared rays with ONE host call out of a cached workspace
+    (no per-frame allocation besides the eight result maps).  Returns (coarse dict, fine dict or None) with rgb / disp /
+    acc / depth, bit-identical to issuing the stage calls one by one."""
+    lib = _lib.load()
+    n = ro.shape[0]
+    dev = ro.device
+    r = _lib.Render()
+    r.precision, r.n_rays, r.n_coarse, r.n_fine = precision, n, int(n_coarse), int(n_fine)
+    r.ro, r.rd, r.viewdirs = ro.data_ptr(), rd.data_ptr(), viewdirs.data_ptr()
+    r.near_, r.far_, r.lindisp, r.white_bkgd = float(near), float(far), int(bool(lindisp)), int(bool(white_background))
+    keep = [_f32c(t_vals)]
+    r.t_vals = keep[0].data_ptr()
+    for name, t in (("t_rand", t_rand), ("u", u), ("noise_c", noise_c), ("noise_f", noise_f)):
+        if t is not None:
+            t = _f32c(t)
+            keep.append(t)
+            setattr(r, name, t.data_ptr())
+    r.u_per_ray = int(u is not None and u.dim() == 2)
+    pc = packed_c.cstruct()
+    pf = pc if (packed_f is None or packed_f is packed_c) else packed_f.cstruct()
+    dc = decoder_struct(dec_c)
+    df = dc if (dec_f is None or dec_f is dec_c) else decoder_struct(dec_f)
+    r.planes_coarse, r.planes_fine = C.pointer(pc), C.pointer(pf)
+    r.dec_coarse, r.dec_fine = C.pointer(dc), C.pointer(df)
+    vp_c = packed_c.vplane
+    vp_f = vp_c if packed_f is None else packed_f.vplane
+    r.vplane_coarse, r.vplane_fine = vp_c.data_ptr(), vp_f.data_ptr()
+    r.vrh, r.vrw = vp_c.shape[0], vp_c.shape[1]
+    r.az_lo, r.az_rng, r.el_lo, r.el_rng = packed_c.view_lo_rng
+
+    def maps():
+        return {"rgb": torch.empty((n, 3), dtype=torch.float32, device=dev), "disp": torch.empty((n,), dtype=torch.float32, device=dev),
+                "acc": torch.empty((n,), dtype=torch.float32, device=dev), "depth": torch.empty((n,), dtype=torch.float32, device=dev)}
+
+    co = maps()
+    r.rgb_c, r.disp_c, r.acc_c, r.depth_c = (co[k].data_ptr() for k in ("rgb", "disp", "acc", "depth"))
+    fo = None
+    if n_fine > 0:
+        fo = maps()
+        r.rgb_f, r.disp_f, r.acc_f, r.depth_f = (fo[k].data_ptr() for k in ("rgb", "disp", "acc", "depth"))
+    need = lib.nvsr_workspace_bytes(C.byref(r))
+    if need < 0:
+        raise _lib.NvsrError("nvsr_workspace_bytes: invalid render request")
+    ws = _workspace(int(need), dev)
+    r.workspace, r.workspace_bytes = ws.data_ptr(), ws.numel()
+    evals = n * (n_coarse + ((n_coarse + n_fine) if n_fine > 0 else 0))
+    LAUNCHES["nvsr_render_rays(stage launches)"] = LAUNCHES.get("nvsr_render_rays(stage launches)", 0) + \
+        (6 if n_fine == 0 else (11 if vp_f is vp_c else 12))
+    with torch.cuda.device(dev):
+        st = lib.nvsr_render_rays(C.byref(r), _stream())
+    _lib.check(st, "nvsr_render_rays")
+    return co, fo
+
+
 def raw_to_planar(radiance_field):
     """[N,S,4] (reference layout, train_utils.py:57-60) -> planar [4, N*S]."""
     n, s, _ = radiance_field.shape

@@ -35,6 +35,10 @@ _state = {
     # every other sample has alpha = 0 and weight exactly 0, so its colour cannot reach any map (exact, not a
     # tolerance: volume_rendering_utils.py:29-44).  NVSR_SPARSE_RGB=0 evaluates every sample.
     "sparse_rgb": os.environ.get("NVSR_SPARSE_RGB", "1") != "0",
+    # dense frames (every sample through both decoders) go through ONE C call per chunk, nvsr_render_rays, working out
+    # of a cached workspace (no per-frame allocation); NVSR_ONE_CALL=0 issues the same stage calls from Python instead
+    # (bit-identical maps; what the sparse colour path, traces and bench.py's per-kernel event timing use anyway)
+    "one_call": os.environ.get("NVSR_ONE_CALL", "1") != "0",
 }
 
 
@@ -90,7 +94,8 @@ def _planes_pass(model, scene_id, precision):
     """Cached _PlanesPass: rebuilt only when a plane tensor or a decoder weight changed."""
     model.set_cur_scene_id(scene_id)
     srcs = [scene._source_plane(model, d) for d in range(4)]
-    sig = tuple((id(t),) + scene._Cache.key_of(t) for t in srcs) + _params_sig(model)
+    sig = tuple((id(t),) + scene._Cache.key_of(t) for t in srcs) + _params_sig(model) + \
+        (getattr(model, "proj_combination", "avg"),)
     per_key = _pass_cache.get(model, sig, dict)
     key = (scene_id, precision)
     hit = per_key.get(key)
@@ -174,11 +179,23 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace, coa
     n = ro.shape[0]
     dev = ro.device
     Nc, Nf = cfg.num_coarse, cfg.num_fine
-    vfeat = ops.viewdir_gather(vd, pc.planes)
     t_rand = randoms.get("t_rand") if cfg.perturb else None
     if cfg.perturb and t_rand is None:
         t_rand = torch.rand([n, Nc]).to(dev)  # CPU RNG like train_utils.py:108
     noise_c = _noise(randoms.get("noise_c"), cfg, n, Nc, dev)
+    sparse_on = _state["sparse_rgb"] and pc.precision != NVSR_F32
+    if (_state["one_call"] and trace is None and not coarse_only and not sparse_on and "z_fine" not in randoms
+            and ops.PROFILE is None and (Nf == 0 or pf is not None)):
+        u = None
+        if Nf > 0:
+            u = randoms.get("u")
+            if u is None:
+                u = _t_vals(Nf, dev) if cfg.perturb == 0.0 else torch.rand([n, Nf]).to(dev)
+        noise_f = _noise(randoms.get("noise_f"), cfg, n, Nc + Nf, dev) if Nf > 0 else None
+        return ops.render_rays(ro, rd, vd, near, far, pc.planes, pc.dec, pf.planes if pf else None, pf.dec if pf else None,
+                               pc.precision, Nc, Nf, _t_vals(Nc, dev), u=u, t_rand=t_rand, noise_c=noise_c, noise_f=noise_f,
+                               lindisp=cfg.lindisp, white_background=cfg.white_background)
+    vfeat = ops.viewdir_gather(vd, pc.planes)
     raw, z = pc.radiance(ro, rd, vfeat, near, far, cfg.lindisp, Nc, t_vals=_t_vals(Nc, dev), t_rand=t_rand, noise=noise_c)
     u = None
     if Nf > 0:

@@ -21,6 +21,13 @@ WANT = [
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+    # L1 data-pipe wavefronts (what bounds the gather: DESIGN.md 4.2 quotes wavefronts per load from these)
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_lg.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__inst_executed_per_warp.ratio", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 
 
@@ -37,6 +44,15 @@ def main():
         for w in WANT:
             if w in idx:
                 print(f"  {w:72s} {r[idx[w]]:>18s} {units[idx[w]]}")
+        # derived: wavefronts per global-load request (1 = every lane of a request inside one 128-byte line)
+        try:
+            wf = float(r[idx["l1tex__data_pipe_lsu_wavefronts_mem_lg.sum"]].replace(",", ""))
+            rq = float(r[idx["l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]].replace(",", "")) + \
+                float(r[idx["l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"]].replace(",", ""))
+            if rq > 0:
+                print(f"  {'derived: L1 wavefronts per global ld/st request':72s} {wf / rq:18.2f}")
+        except (KeyError, ValueError):
+            pass
         stalls = sorted(((float(r[idx[h]].replace(',', '') or 0), h) for h in extra), reverse=True)[:8]
         for v, h in stalls:
             print(f"  stall {h[len('smsp__average_'):-len('_per_issue_active.ratio')]:64s} {v:10.2f}")

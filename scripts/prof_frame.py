@@ -22,18 +22,19 @@ def main():
     ap.add_argument("--rows", type=int, default=bench.RES, help="render only the first ROWS image rows")
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--ray-chunk", type=int, default=0)
+    ap.add_argument("--sparse", action="store_true", help="profile the sparse colour path (default: every sample dense)")
+    ap.add_argument("--config", default="cfg2")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     nvsr_b200.set_precision(args.precision)
     if args.ray_chunk:
         nvsr_b200.set_ray_chunk(args.ray_chunk)
-    mc, mf, sid, pose, focal, opt, scfg = bench.build_scene(dev)
-    pose = pose.to(dev)
+    nvsr_b200.set_sparse_rgb(args.sparse)
+    w = bench.build_workload(args.config, dev)
     with torch.no_grad():
         for _ in range(args.frames):
-            out = nvsr_b200.render_frame(bench.RES, bench.RES, focal, pose, mc, mf, opt, sid, scfg,
-                                         row_range=(0, args.rows))
+            out = w.render(nvsr_b200, 0, min(args.rows, w.H))
     torch.cuda.synchronize()
     print("rgb_fine mean", float(out[3].mean()), "acc_fine mean", float(out[5].mean()))
 

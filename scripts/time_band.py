@@ -6,7 +6,8 @@ sys.path.insert(0, ROOT)
 import bench, nvsr_b200
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-mc, mf, sid, pose, focal, opt, scfg = bench.build_scene(dev)
+_w = bench.build_workload('cfg2', dev)
+mc, mf, sid, pose, focal, opt, scfg = _w.mc, _w.mf, _w.sid, _w.pose, _w.focal, _w.opt, _w.scfg
 pose = pose.to(dev)
 for rows in (800, 400, 200, 100):
     with torch.no_grad():

@@ -301,3 +301,43 @@ def test_config1_whole_frame_call_surface():
         out = nvsr_b200.eval_nerf(100, 100, focal, mc, mf, ro, rd, opt, sid, scene_config=scfg)
     assert out[0].shape == (100, 100, 3) and all(o is None for o in out[1:])
     assert bool(torch.isfinite(out[0]).all())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("kw", [dict(), dict(noise_std=0.7, white_background=True, perturb=True), dict(lindisp=True)])
+def test_one_call_render_rays_equals_staged_calls(prec, kw):
+    """nvsr_render_rays (the C-ABI convenience entry: coarse -> fine with one host call out of a cached workspace) gives
+    bit-identical maps to the same stage entry points issued one by one from Python — ragged ray count, jitter, noise,
+    white background, lindisp, SR planes on the fine pass, and the coarse-only case."""
+    from nvsr_b200 import render
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=32, view_res=8, seed=12, device=DEV, sr_scale=2)
+    pose, focal = scene.blender_camera(41)
+    n = 41 * 41 - 5
+    g = torch.Generator().manual_seed(3)
+    rnd = {"noise_c": torch.randn(n, 48, generator=g), "noise_f": torch.randn(n, 48 + 72, generator=g),
+           "t_rand": torch.rand(n, 48, generator=g), "u": torch.rand(n, 72, generator=g)}
+    if not kw.get("perturb"):
+        rnd.pop("t_rand"), rnd.pop("u")
+    nvsr_b200.set_precision(prec)
+    nvsr_b200.set_sparse_rgb(False)
+    try:
+        with torch.no_grad():
+            ro, rd = nvsr_b200.get_ray_bundle(41, 41, focal, pose.to(DEV))
+            batch = torch.stack([ro.reshape(-1, 3)[:n], rd.reshape(-1, 3)[:n]], 0)
+            for nf in (72, 0):
+                opt, scfg = scene.render_options(48, nf, **kw), scene.scene_cfg()
+                outs = []
+                for one in (True, False):
+                    render._state["one_call"] = one
+                    outs.append(nvsr_b200.run_one_iter_of_nerf(41, 41, focal, mc, mf, batch, opt, sid, "validation",
+                                                               scene_config=scfg, randoms=dict(rnd)))
+                    torch.cuda.synchronize()
+                for k, a, b in zip(NAMES, outs[0][:6], outs[1][:6]):
+                    if b is None:
+                        assert a is None
+                        continue
+                    assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a, 7.0), torch.nan_to_num(b, 7.0)), (k, nf)
+    finally:
+        render._state["one_call"] = True
+        nvsr_b200.set_sparse_rgb(True)
+        nvsr_b200.set_precision("fp16")

@@ -21,8 +21,9 @@ def _close(got, want, rel):
     got, want = got.detach().float().cpu(), want.detach().float().cpu()
     scale = float(want.abs().max()) + 1e-30
     err = float((got - want).abs().max())
-    # + 1e-7: fp32 summation-order noise of the atomics on gradients whose own scale is ~1e-6
-    assert err <= rel * scale + 1e-7, f"max abs err {err:.3e} vs scale {scale:.3e}"
+    # + 1e-6: fp32 summation-order noise (atomics, cuBLAS vs ATen) on gradients whose own scale is ~1e-5 (the large
+    # ones are O(1e-2 .. 1))
+    assert err <= rel * scale + 1e-6, f"max abs err {err:.3e} vs scale {scale:.3e}"
 
 
 @pytest.mark.parametrize("white,noise_std,mip", [(False, 0.0, False), (True, 0.6, False), (True, 0.3, True)])
