@@ -358,6 +358,22 @@ int32_t nvsr_composite_bwd(const float* radiance_field, const float* z, const fl
                            float* d_radiance_field, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Plane super-resolution, last step: PlanesSR.forward (models.py:884-926) ends with
+ *   out = inner_model(pad(LR))[..., crop:-crop, crop:-crop] + F.interpolate(LR, scale_factor, 'bilinear', align_corners)
+ * then caches `out` on the CPU (:925) and re-uploads it on every call (:893).  This entry fuses everything after the
+ * conv chain and writes the plane DIRECTLY in the layout the gather reads, device-resident:
+ *   diff        : conv-chain output, channels-last — element (y, x, c) at diff[y*row_stride + x*px_stride + c]
+ *                 (strides in elements; dtype NVSR_F32 | NVSR_BF16 | NVSR_F16); `crop` = PlanesSR.HR_overpadding
+ *   lr_nchw     : the LR plane [channels][rh][rw] fp32 as stored in planes_ (models.py:436-439)
+ *   packed      : nvsr_pack_plane image of the [rh*scale][rw*scale] SR plane (packed_dtype NVSR_F32: channels-last fp32;
+ *                 NVSR_BF16 | NVSR_F16: x-pair records, 32-byte aligned), or NULL
+ *   nchw_out    : optional fp32 [channels][rh*scale][rw*scale] copy for the reference's own consumers, or NULL
+ * Bilinear weights follow ATen's upsample_bilinear2d (area_pixel_compute_source_index). */
+int32_t nvsr_sr_finalize(const void* diff, int32_t diff_dtype, int64_t diff_row_stride, int64_t diff_px_stride,
+                         int32_t crop, const float* lr_nchw, int32_t channels, int32_t rh, int32_t rw, int32_t scale,
+                         int32_t align_corners, void* packed, int32_t packed_dtype, float* nchw_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Frame sink: write_image's conversion (train_nerf.py:270,273:
  * np.array(255*torch.clamp(im,0,1).cpu()).astype(np.uint8)) done on the device, so the device->host copy carries one
  * byte per channel.  rgb: n_elems fp32 values (a frame [H,W,3] flat, or any map); out: n_elems bytes, 4-byte aligned

@@ -184,6 +184,7 @@ SIGNATURES = {
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),
     "nvsr_dir_encoding": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_p]),
+    "nvsr_sr_finalize": (c_i32, [c_p, c_i32, c_i64, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
     "nvsr_workspace_bytes": (c_i64, [C.POINTER(Render)]),
     "nvsr_render_rays": (c_i32, [C.POINTER(Render), c_p]),
     "nvsr_cast_rays": (c_i32, [c_p, c_p, c_p, c_p, c_f, c_i64, c_i32, c_p, c_p, c_p]),

@@ -70,6 +70,17 @@ struct TcArgs {
   uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total;
 };
 
+#ifdef NVSR_TC_TIMING
+// Debug build only (scripts/ab_build.sh timing -DNVSR_TC_TIMING): per-warp cycle sums of the phases of a layer step in
+// CTA 0 — [warp][0] wait for the accumulator, [1] epilogue body, [2] arrive (+ MMA issue on the last warp),
+// [3] rest of the step (tile loads, head write-out), [4] layer steps counted, [5] steps in which this warp was the issuer,
+// [6] cycles of those issues.  Read back with nvsr_debug_tc_timing().
+__device__ unsigned long long g_tc_timing[16][8];
+#define TC_T(var) const long long var = clock64()
+#else
+#define TC_T(var)
+#endif
+
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -427,6 +438,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     (void)done_cnt, (void)bar_done;
     const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
     uint32_t ph_acc = 0, ph_rb = 0;
+#ifdef NVSR_TC_TIMING
+    unsigned long long t_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     // MMAs of layer l of the slot's tile number `use` (whole warp; one elected lane issues).
     //   layer 0: A = feature tile in smem (SS form); l > 0: A = activations in TMEM (TS form).
@@ -448,10 +462,16 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         if (l == 0) {
           for (int ks = 0; ks < ksteps; ++ks)
             umma_ss(d_base, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+#ifdef NVSR_TC_EXP_NOBIAS
+          if (kFixed) umma_ss(d_base, adesc0, bdesc0, idesc, 1u);
+#endif
         } else if (kFixed) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+#ifdef NVSR_TC_EXP_NOBIAS
+          umma_ts(d_base, d_base + kSlotAOff, bdesc0, idesc, 1u);   // stands for the bias K-step
+#endif
         } else {
           for (int ks = 0; ks < ksteps; ++ks)
             umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
@@ -490,7 +510,13 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #endif
       }
       last_in = __shfl_sync(0xffffffffu, last_in, 0);
+#ifdef NVSR_TC_TIMING
+      const long long ti0 = clock64();
+#endif
       if (last_in && issue_next) issue_layer(nl, nuse);
+#ifdef NVSR_TC_TIMING
+      if (last_in && issue_next) t_sum[5] += 1, t_sum[6] += clock64() - ti0;
+#endif
     };
 
     // source of the bias rows of `layer` for this thread: mode 1 = smem pointer, 2 = global pointer
@@ -574,14 +600,21 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           mbar_wait(bar_rb_full, ph_rb);
           ph_rb ^= 1;
         }
+        TC_T(tt0);
         mbar_wait(bar_acc_full, ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
+        TC_T(tt1);
 #ifndef NVSR_TC_OLD_EPI
         if constexpr (kFixed) {
           // fixed chains: bias rows always come from shared memory (mode 1)
+#ifdef NVSR_TC_EXP_NOBIAS   // timing experiment only (wrong numerics): what the bias pre-store costs
+          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, false, bsrc);
+          else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, false, bsrc);
+#else
           if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, n_next > 0, bsrc);
           else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, true, bsrc);
+#endif
         } else
 #endif
         {
@@ -594,7 +627,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
                             bias ? mode : 0, bsrc + c);
           }
         }
+        TC_T(tt2);
         arrive_then_issue(n_next > 0, nl, last ? use + 1 : use);
+        TC_T(tt3);
         // layer 0's MMAs have completed: the slot's ring buffer (and, since all 8 warps finished reading
         // them before those MMAs were issued, its staged bias rows) may take the slot's next tile.  Issued
         // after the arrival: the warp would only be waiting for layer 1's accumulator now.
@@ -614,8 +649,15 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
               if (h < head_n) a.raw[(int64_t)(ly.head_ch + h) * a.raw_stride + row] = hv[h] + __ldg(ly.head_b + h);
           }
         }
+#ifdef NVSR_TC_TIMING
+        t_sum[0] += tt1 - tt0, t_sum[1] += tt2 - tt1, t_sum[2] += tt3 - tt2, t_sum[3] += clock64() - tt3, t_sum[4] += 1;
+#endif
       }
     }
+#ifdef NVSR_TC_TIMING
+    if (blockIdx.x == 0 && lane == 0)
+      for (int i = 0; i < 8; ++i) g_tc_timing[warp][i] = t_sum[i];
+#endif
   }
 
   // ---- teardown ----
@@ -722,3 +764,9 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
 }
 
 }  // namespace nvsr
+
+#ifdef NVSR_TC_TIMING
+extern "C" int32_t nvsr_debug_tc_timing(unsigned long long* host_out /* [16][8] */) {
+  return (int32_t)cudaMemcpyFromSymbol(host_out, nvsr::g_tc_timing, sizeof(unsigned long long) * 16 * 8);
+}
+#endif

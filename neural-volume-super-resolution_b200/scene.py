@@ -165,6 +165,81 @@ class PlaneUpsampler(nn.Module):
         return self.SR_planes[plane_name]
 
 
+class _ResidualBlock(nn.Module):
+    """state-compatible with models._Residual_Block (models.py:773-789): conv-relu-conv, x0.1, + (cropped) identity"""
+
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.conv1 = nn.Conv2d(hidden_size, hidden_size, 3, bias=False)
+        self.conv2 = nn.Conv2d(hidden_size, hidden_size, 3, bias=False)
+
+
+class EDSRNet(nn.Module):
+    """State-compatible stand-in of models.EDSR (models.py:792-822) as PlanesSR builds it (padding=0: 'valid' 3x3
+    convolutions on a replicate-padded input, no biases, no receptive-field bound): conv_input, `n_blocks` residual
+    blocks, conv_mid, log2(scale) x [conv hidden -> 4 hidden, PixelShuffle(2)], conv_output.  Holds parameters only —
+    the forward pass of the render path is nvsr_b200.sr.PlaneSuperResolver."""
+
+    def __init__(self, in_channels, out_channels, hidden_size, n_blocks, scale_factor):
+        super().__init__()
+        self.conv_input = nn.Conv2d(in_channels, hidden_size, 3, bias=False)
+        self.residual = nn.Sequential(*[_ResidualBlock(hidden_size) for _ in range(n_blocks)])
+        self.conv_mid = nn.Conv2d(hidden_size, hidden_size, 3, bias=False)
+        ups = []
+        for _ in range(int(round(math.log2(scale_factor)))):
+            ups += [nn.Conv2d(hidden_size, hidden_size * 4, 3, bias=False), nn.PixelShuffle(2)]
+        self.upscale = nn.Sequential(*ups)
+        self.conv_output = nn.Conv2d(hidden_size, out_channels, 3, bias=False)
+        # receptive-field bookkeeping of models.py:796-803 (every conv is 3x3 here): padding in LR pixels
+        rp, rf = 0.0, 1.0
+        rp += rf            # conv_input
+        rp += rf * 2 * n_blocks
+        rp += rf            # conv_mid
+        for _ in range(int(round(math.log2(scale_factor)))):
+            rp += rf
+            rf /= 2
+        rp += rf            # conv_output
+        self.required_padding = rp
+
+
+class PlanesSRModel(nn.Module):
+    """State-compatible stand-in of models.PlanesSR (models.py:824-926): `inner_model` (EDSR), scale factor, LR /
+    SR plane dictionaries, the padding bookkeeping of :840-842 and the weight initialisation of :843-850.  Calling it
+    runs the device-resident super-resolution of nvsr_b200.sr (no CPU cache, no per-call re-upload)."""
+
+    def __init__(self, scale_factor=4, in_channels=48, out_channels=48, hidden_size=256, n_blocks=32, plane_interp="bilinear",
+                 weight_gain=1.0):
+        super().__init__()
+        self.scale_factor = scale_factor
+        self.plane_interp = plane_interp
+        self.align_corners = True
+        self.inner_model = EDSRNet(in_channels, out_channels, hidden_size, n_blocks, scale_factor)
+        rp = self.inner_model.required_padding
+        self.HR_overpadding = int(rp * scale_factor)
+        self.inner_model.required_padding = int(math.ceil(rp))
+        self.HR_overpadding = self.inner_model.required_padding * scale_factor - self.HR_overpadding
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n) / 10 * weight_gain)
+        self.LR_planes, self.SR_planes, self.residual_planes = {}, {}, {}
+
+    def set_LR_plane(self, plane, id, save_interpolated=False):
+        self.LR_planes[id] = plane
+
+    def clear_SR_planes(self, all_planes=False):
+        self.SR_planes = {}
+        if all_planes:
+            self.LR_planes, self.residual_planes = {}, {}
+
+    @torch.no_grad()
+    def forward(self, plane_name):
+        from . import sr
+        if plane_name not in self.SR_planes:
+            self.SR_planes[plane_name] = sr.resolver_of(self).super_resolve(plane_name, want_nchw=True)[1]
+        return self.SR_planes[plane_name]
+
+
 class MipMLP(nn.Module):
     """Stand-in of FlexibleNeRFModel as train_nerf.py:342-348 builds it for the mip baseline
     (models.py:14-108 with defaults num_layers=4, hidden=128, skip=4, use_viewdirs)."""
@@ -213,11 +288,14 @@ def shape_density(model, target_std=15.0, shift=-12.0, feat_std=0.5, n_draws=409
 
 
 def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device="cpu", scene_id=None,
-                         plane_std=0.5, density_std=10.0, density_shift=-10.0, sr_scale=None):
+                         plane_std=0.5, density_std=10.0, density_shift=-10.0, sr_scale=None, sr_hidden=256, sr_blocks=32,
+                         sr_weight_gain=6.0):
     """Synthetic Blender-shaped scene: seeded coarse+fine decoders, then planes.
 
-    With `sr_scale`, planes are stored at plane_res under an LR id, and the FINE model reads
-    `PlaneUpsampler` output (plane_res*sr_scale) while the coarse model reads the LR planes
+    With `sr_scale`, planes are stored at plane_res under an LR id, and the FINE model reads the output of a
+    `PlanesSRModel` — the reference's PlanesSR + EDSR architecture (config/TrainModels.yml:174-184: hidden 256,
+    32 residual blocks), random-init with the reference's own initialiser scaled by `sr_weight_gain` so that the SR
+    residual is a visible fraction of the plane — at plane_res*sr_scale, while the coarse model reads the LR planes
     (apply_2_coarse: False, config/TrainModels.yml:166) — BASELINE config 3a."""
     torch.manual_seed(seed)
     np.random.seed(seed)
@@ -248,11 +326,11 @@ def make_synthetic_scene(plane_res=200, view_res=32, channels=48, seed=0, device
     coarse.to(device)
     fine.to(device)
     if sr_scale:
-        sr = PlaneUpsampler(channels, sr_scale).to(device).eval()
+        sr = PlanesSRModel(sr_scale, channels, channels, sr_hidden, sr_blocks, weight_gain=sr_weight_gain).to(device).eval()
+        fine.assign_SR_model(sr)
         for d in range(3):
             n = get_plane_name(stored_sid, d)
-            sr.set_LR_plane(planes[n].detach(), n)
-        fine.assign_SR_model(sr)
+            sr.set_LR_plane(fine.planes_[n].detach(), n)
     return coarse, fine, sid
 
 
@@ -354,6 +432,10 @@ def _source_plane(model, d):
     `model.planes()` returns a fresh tensor each time; here the cached tensor itself is used as the
     cache key, making the SR plane device-resident after the first frame."""
     sr = d < 3 and _should_sr(model, d)
+    if sr and _native_sr(model):
+        # device-resident SR (nvsr_b200.sr): the SR plane is a function of the LR plane and the SR weights — the LR
+        # plane is the identity the caches key on, the SR weights are part of the model's parameter signature
+        return _lr_plane_of(model, d)[1]
     if sr and hasattr(model.SR_model, "SR_planes"):
         name = model.scene_coupler.scene_with_saved_plane(get_plane_name(model.cur_id, d), plane_not_scene=True)
         if name not in model.SR_model.SR_planes:
@@ -361,6 +443,22 @@ def _source_plane(model, d):
         if name in model.SR_model.SR_planes:
             return model.SR_model.SR_planes[name]
     return model.planes(d, super_resolve=sr)
+
+
+def _native_sr(model):
+    from . import sr
+    return hasattr(model, "SR_model") and sr.is_sr_model(model.SR_model)
+
+
+def _lr_plane_of(model, d):
+    """(stored plane name, LR plane tensor) the SR model super-resolves for dimension d of the current scene; registers
+    it with the SR model like TwoDimPlanesModel.assign_LR_planes (models.py:426-434) if that has not happened"""
+    name = model.scene_coupler.scene_with_saved_plane(get_plane_name(model.cur_id, d), plane_not_scene=True)
+    lr_planes = model.SR_model.LR_planes
+    if name not in lr_planes:
+        model.SR_model.set_LR_plane(model.raw_plane(name, detach=True) if hasattr(model, "raw_plane") else model.planes_[name],
+                                    id=name, save_interpolated=False)
+    return name, lr_planes[name]
 
 
 def check_supported_planes_model(model):
@@ -401,6 +499,12 @@ def pack_scene_planes(model, scene_id, dtype):
     model.set_cur_scene_id(scene_id)
     packed = []
     for d in range(3):
+        if _should_sr(model, d) and _native_sr(model):
+            # SR inference on the device, written by nvsr_sr_finalize directly as the gather's image (nvsr_b200.sr)
+            from . import sr
+            name, _ = _lr_plane_of(model, d)
+            packed.append(sr.resolver_of(model.SR_model).super_resolve(name, dtype)[0])
+            continue
         src = _source_plane(model, d)
         packed.append(_packed_plane(src, dtype))
     vsrc = _source_plane(model, 3)

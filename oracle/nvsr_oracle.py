@@ -86,12 +86,54 @@ def plane_name(scene_id, d):  # models.py:110-113
     return "_D%d" % d if scene_id is None else "sc%s_D%d" % (scene_id, d)
 
 
+# f2  models.py:773-822 (EDSR with padding=0) and :884-926 (PlanesSR.forward, full plane, eval mode)
+def edsr_forward(net, x):
+    out = F.conv2d(x, net.conv_input.weight)
+    for blk in net.residual:
+        m = 2 * (blk.conv1.kernel_size[0] // 2)               # _Residual_Block.margins (models.py:776)
+        ident = out[..., m:-m, m:-m] if m else out
+        y = F.conv2d(F.relu(F.conv2d(out, blk.conv1.weight)), blk.conv2.weight)
+        y = y * 0.1                                           # output *= 0.1
+        out = torch.add(y, ident)
+    out = F.conv2d(out, net.conv_mid.weight)
+    for m in net.upscale:
+        out = F.pixel_shuffle(out, 2) if isinstance(m, torch.nn.PixelShuffle) else F.conv2d(out, m.weight)
+    return F.conv2d(out, net.conv_output.weight)
+
+
+def planes_sr_forward(sr, name):
+    """PlanesSR.forward(plane_name) (models.py:884-926) for a full plane in eval mode, on the device of the LR plane."""
+    lr = sr.LR_planes[name].detach()
+    x = 1 * lr
+    if hasattr(sr, "planes_mean_NON_LEARNED"):
+        x = (x - sr.planes_mean_NON_LEARNED.to(x)) / sr.planes_std_NON_LEARNED.to(x)
+    pad = int(sr.inner_model.required_padding)
+    x = F.pad(x, pad=(pad, pad, pad, pad), mode="replicate")
+    crop = int(sr.HR_overpadding)
+    diff = edsr_forward(sr.inner_model, x)
+    if crop > 0:
+        diff = diff[..., crop:-crop, crop:-crop]
+    resid = F.interpolate(lr, scale_factor=sr.scale_factor, mode=sr.plane_interp, align_corners=sr.align_corners)
+    return torch.add(diff, resid)
+
+
 def _plane_tensor(model, d, super_resolve):
     """models.py:270-284 (`planes`) without the hard-coded .cuda()."""
     name = plane_name(model.cur_id, d)
     coupler = model.scene_coupler
     saved = coupler.scene_with_saved_plane(name, plane_not_scene=True)
     if super_resolve:
+        sr = model.SR_model
+        if hasattr(sr, "inner_model") and hasattr(sr.inner_model, "conv_input"):   # an EDSR-based PlanesSR: restated above
+            if saved not in sr.LR_planes:
+                sr.set_LR_plane(model.raw_plane(saved, False, detach=True), id=saved, save_interpolated=False)
+            cache = sr.__dict__.setdefault("_oracle_sr_cache", {})
+            lrp = sr.LR_planes[saved]
+            key = (saved, lrp.data_ptr(), lrp._version, str(lrp.device))
+            if key not in cache:
+                with torch.no_grad():
+                    cache[key] = planes_sr_forward(sr, saved)
+            return cache[key]
         return model.SR_model(saved)
     return model.raw_plane(saved, coupler.should_downsample(name), detach=False)
 

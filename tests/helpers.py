@@ -135,3 +135,22 @@ def check_resampling(inds_gpu, zs_gpu, inds_ref, zs_ref, cdf_ref, bins_ref, u, w
     bad = d > tol
     assert not bool(bad.any()), f"{what}: z_samples off by {float((d - tol).max()):.3e} beyond the conditioning bound"
     return mism
+
+
+def load_sr_model(golden_name, device="cpu"):
+    """The stand-in PlanesSRModel loaded with the EDSR weights of an SR golden (tests/golden/make_golden_sr.py) and its LR
+    planes registered -> (sr model, golden dict, {plane name: SR plane of the reference})."""
+    g = golden(golden_name)
+    sr = scene.PlanesSRModel(int(g["scale"]), int(g["channels"]), int(g["channels"]), int(g["hidden"]), int(g["n_blocks"]))
+    sd = {k[len("w__"):].replace("__", "."): T(v) for k, v in g.items() if k.startswith("w__")}
+    for k in [k for k in sd if k.startswith("planes_mean_NON_LEARNED") or k.startswith("planes_std_NON_LEARNED")]:
+        setattr(sr, k, torch.nn.Parameter(sd.pop(k), requires_grad=False))
+    missing, unexpected = sr.load_state_dict(sd, strict=False)
+    assert not [m for m in missing if "NON_LEARNED" not in m] and not unexpected, (missing, unexpected)
+    sr = sr.to(device).eval()
+    want = {}
+    for k, v in g.items():
+        if k.startswith("lr__"):
+            sr.set_LR_plane(T(v, device), k[len("lr__"):])
+            want[k[len("lr__"):]] = T(g["sr__" + k[len("lr__"):]])
+    return sr, g, want

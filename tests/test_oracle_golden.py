@@ -132,3 +132,15 @@ def test_e2e(name):
         # disp = 1/(depth/acc) amplifies last-ulp differences when depth/acc is tiny: relative tolerance
         H.assert_close(v, g[k], 5e-6, 1e-4 if "disp" in k else 1e-5, what=f"{name}:{k}")
     assert out[6] is None and out[7] is None and out[8] is None
+
+
+@pytest.mark.parametrize("name", ["sr_small.npz", "sr_x2_norm.npz", "sr_ragged.npz"])
+def test_planes_sr_forward_vs_reference(name):
+    """The oracle's restatement of PlanesSR.forward + EDSR (models.py:773-822, 884-926) against planes super-resolved by
+    the reference's own classes (tests/golden/make_golden_sr.py)."""
+    sr, g, planes = H.load_sr_model(name)
+    assert int(sr.inner_model.required_padding) == int(g["required_padding"]) and int(sr.HR_overpadding) == int(g["hr_overpadding"])
+    with torch.no_grad():
+        for pname, want in planes.items():
+            got = O.planes_sr_forward(sr, pname)
+            H.assert_close(got, want, 2e-6, 1e-5, what=pname)
