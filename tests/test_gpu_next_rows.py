@@ -17,13 +17,13 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda:0"
 
 
-def _close(got, want, rel):
+def _close(got, want, rel, what=""):
     got, want = got.detach().float().cpu(), want.detach().float().cpu()
     scale = float(want.abs().max()) + 1e-30
     err = float((got - want).abs().max())
-    # + 1e-6: fp32 summation-order noise (atomics, cuBLAS vs ATen) on gradients whose own scale is ~1e-5 (the large
-    # ones are O(1e-2 .. 1))
-    assert err <= rel * scale + 1e-6, f"max abs err {err:.3e} vs scale {scale:.3e}"
+    # + 1e-7: fp32 summation-order noise (atomics, cuBLAS vs ATen) on gradients whose own scale is ~1e-6 (the view
+    # plane's; the large ones are O(1e-2 .. 1))
+    assert err <= rel * scale + 1e-7, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
 
 
 @pytest.mark.parametrize("white,noise_std,mip", [(False, 0.0, False), (True, 0.6, False), (True, 0.3, True)])
@@ -102,32 +102,82 @@ def _named_params(mc, mf):
     return named
 
 
-def test_train_step_gradients_match_reference_golden():
+class _ReluTap:
+    """Record / teacher-force the hidden layers' ReLU masks of a training step.
+
+    A ReLU whose pre-activation is within fp32 summation noise of 0 is a discontinuity of the GRADIENT: cuBLAS and
+    ATen's CPU GEMM sum in different orders, the unit lands on the other side, and the row's whole delta through that
+    unit appears / disappears (observed on a B200: unit 104 of the fine rgb layer 3 in one row moves rgb_dec gradients
+    of scale 5e-5 by 1e-5, everything not downstream of it agrees to 1e-6).  `record` taps the oracle's F.relu calls on
+    [rows,128] tensors; `force` replaces torch.relu in the product path by `h * recorded mask` and lists every entry
+    where the product's own mask disagrees, with its |pre-activation|."""
+
+    def __init__(self):
+        self.masks, self.flips, self.i = [], [], 0
+
+    def record(self, monkeypatch):
+        import torch.nn.functional as F
+        orig = F.relu
+
+        def tap(h, *a, **k):
+            if h.dim() == 2 and h.shape[-1] == 128:
+                self.masks.append((h > 0).clone())
+            return orig(h, *a, **k)
+        monkeypatch.setattr(F, "relu", tap)
+
+    def force(self, monkeypatch, on=True):
+        orig = torch.relu
+        self.i, self.flips = 0, []
+
+        def forced(h):
+            if not (h.dim() == 2 and h.shape[-1] == 128):
+                return orig(h)
+            m = self.masks[self.i].to(h.device)
+            self.i += 1
+            bad = (h > 0) != m
+            if bool(bad.any()):
+                self.flips += [float(v) for v in h.detach()[bad].abs().cpu()]
+            return h * m if on else orig(h)
+        monkeypatch.setattr(torch, "relu", forced)
+
+
+def test_train_step_gradients_match_reference_golden(monkeypatch):
     """The whole train-mode step through nvsr_b200.autograd.run_one_iter_of_nerf against the gradients the reference's
     loss.backward() produced (tests/golden/backward_planes_train.npz).
 
-    Free-running, the hierarchical resampling is ill-conditioned in the reference itself (an index flip within 2 ulp of a
-    cdf edge moves a fine sample by a bin — parity_attribution (i)), so the TIGHT gate is teacher-forced: the fine pass
-    runs at the merged depths the ORACLE's forward produced (which reproduces the reference's golden step to 1e-6 on
-    the CPU, tests/test_backward_bodies.py), and every gradient must then agree with the reference's to 1e-3 of its
-    scale.  The free-running step is checked as well, with the conditioning-limited tolerance."""
+    Two discontinuities of the reference's own step are teacher-forced for the TIGHT gate (1e-3 of every gradient's
+    scale): (a) the hierarchical resampling (an index flip within 2 ulp of a cdf edge moves a fine sample by a bin —
+    parity_attribution (i)): the fine pass runs at the merged depths the ORACLE's forward produced (which reproduces the
+    reference's golden step to 1e-6 on the CPU, tests/test_backward_bodies.py); (b) hidden ReLUs whose pre-activation
+    is within summation noise of 0 (`_ReluTap`): the masks of the oracle's forward are applied, and every entry where the
+    product's own mask differs must have |pre-activation| < 1e-5 — at most a handful per step.  The free-running step
+    (own masks, own resampling) is checked as well, with the conditioning-limited tolerance."""
     g, sid, opt, scfg, batch = _train_case()
     target = H.T(g["target"], DEV)
     rnd = H.randoms_from(g, DEV)
-    # oracle forward on the CPU: the merged depths of the reference's step
+    # oracle forward on the CPU: the merged depths and the ReLU masks of the reference's step
     mc_o, mf_o = H.load_planes_scene(str(g["scene_file"]), sid, "cpu")
-    tc = {}
-    with torch.no_grad():
+    tc, tap = {}, _ReluTap()
+    with monkeypatch.context() as mp, torch.no_grad():
+        tap.record(mp)
         O.run_one_iter_of_nerf(int(g["H"]), int(g["W"]), float(g["focal"]), mc_o, mf_o, batch, opt, sid, "train",
                                scene_config=scfg, randoms=H.randoms_from(g), trace=tc)
-    for forced, tol in ((True, 1e-3), (False, 3e-2)):
+    assert len(tap.masks) == 16          # 2 models x (4 density + 4 rgb) hidden layers
+    for forced, tol in ((True, 1e-3), (False, 5e-2)):
         mc, mf = H.load_planes_scene(str(g["scene_file"]), sid, DEV)
         named = _named_params(mc, mf)
         r = dict(rnd, z_fine=tc["z_fine"].to(DEV)) if forced else dict(rnd)
-        out = A.run_one_iter_of_nerf(int(g["H"]), int(g["W"]), float(g["focal"]), mc, mf, batch.to(DEV), opt, sid, "train",
-                                     scene_config=scfg, randoms=r)
-        loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
-        loss.backward()
+        with monkeypatch.context() as mp:
+            tap.force(mp, on=forced)
+            out = A.run_one_iter_of_nerf(int(g["H"]), int(g["W"]), float(g["focal"]), mc, mf, batch.to(DEV), opt, sid, "train",
+                                         scene_config=scfg, randoms=r)
+            loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
+            loss.backward()
+        if forced:
+            assert tap.i == 16
+            # every disagreement of the product's own masks is a pre-activation within summation noise of zero
+            assert len(tap.flips) <= 8 and all(v < 1e-5 for v in tap.flips), tap.flips
+            print("relu mask disagreements (|pre-activation|):", tap.flips)
         # forward agreement CPU reference vs GPU: the decoder runs on cuBLAS fp32 there (another summation order)
         assert abs(float(loss.detach()) - float(g["loss"])) <= (2e-5 if forced else 1e-4)
         H.assert_close(out[0], g["rgb_coarse"], 2e-4, what="rgb_coarse")
@@ -136,7 +186,7 @@ def test_train_step_gradients_match_reference_golden():
             assert named[k].grad is not None, k
             want = torch.from_numpy(g["grad__" + k])
             worst = max(worst, float((named[k].grad.cpu() - want).abs().max()) / (float(want.abs().max()) + 1e-30))
-            _close(named[k].grad, want, tol)
+            _close(named[k].grad, want, tol, what=k)
         print("train step vs reference gradients (%s): worst relative error %.2e" % ("teacher-forced" if forced else "free-running", worst))
 
 

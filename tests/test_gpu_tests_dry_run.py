@@ -41,8 +41,8 @@ def test_dry_gather_bwd(cpu_as_device):
     T.test_gather_bwd_matches_oracle_autograd()
 
 
-def test_dry_train_step_golden(cpu_as_device):
-    T.test_train_step_gradients_match_reference_golden()
+def test_dry_train_step_golden(cpu_as_device, monkeypatch):
+    T.test_train_step_gradients_match_reference_golden(monkeypatch)
 
 
 def test_dry_mip_train_step(cpu_as_device):
