@@ -7,10 +7,13 @@
 // producer warp and no MMA-issuer warp:
 //   epilogue (all 16 warps, 8 per slot): warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and columns
 //       [64h, 64h+64): tcgen05.ld the accumulator, ReLU + saturate + 16-bit pack in ONE F2FP per
-//       pair, tcgen05.st the packed row into the slot's A region, and tcgen05.st the NEXT layer's
-//       bias (smem broadcast rows, or the staged per-ray rows) into the accumulator columns just
-//       read — every MMA ACCUMULATES, so no bias add is ever executed.  Output heads (128 -> 1 / 3)
-//       are fp32 dot products on the CUDA cores over the UNROUNDED last activations.
+//       pair, tcgen05.st the packed row into the slot's A region.  No bias add is ever executed:
+//       in the two tri-plane chains a layer's bias is ONE extra K = 16 MMA step (constant "ones"
+//       pattern in TMEM x a 4 KB image of the biases split into three 16-bit terms, see kPatCol);
+//       only the PER-RAY bias of the rgb chain's first layer (and every bias of the generic chain)
+//       is pre-stored with tcgen05.st into the accumulator columns just read, and the MMAs
+//       accumulate onto it.  Output heads (128 -> 1 / 3) are fp32 dot products on the CUDA cores
+//       over the UNROUNDED last activations.
 //   MMA issue: the LAST of a slot's 8 warps to finish a layer (shared-memory arrival counter) issues
 //       the next layer's tcgen05.mma itself from one elected lane — layer 0: A = feature tile in smem
 //       (SS form); hidden layers: A = previous activations in TMEM (TS form); B = resident weights
@@ -23,7 +26,7 @@
 //
 // TMEM map (512 columns allocated): slot s -> D_s = [192 s, 192 s + 128) fp32 accumulator,
 // A_s = [192 s + 128, 192 s + 192): 128 rows x 128 16-bit activations, two per 32-bit column
-// (row = lane, K pair k/2 = column: the TS-form A layout).
+// (row = lane, K pair k/2 = column: the TS-form A layout); [384, 416): the four bias "ones" patterns.
 //
 // smem operand layout (layer-0 A and every B): K-major, no-swizzle canonical UMMA layout with
 // 8x16-byte core matrices, stored [K/8][rows][8 x 16 bit]: LBO (K-chunk stride) = rows*16 B,
@@ -41,6 +44,13 @@ constexpr int kRbPitch = 132;       // floats per staged row (528 B: conflict-fr
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kSlotCols = 192;  // D (128 fp32 columns) + A (64 columns of packed 16-bit pairs)
 constexpr uint32_t kSlotAOff = 128;
+// Fixed chains: a layer's bias enters as ONE extra K = 16 MMA step instead of being pre-stored into the accumulator
+// (tcgen05.st of 128 fp32 columns per row and layer, the largest single item of the epilogue): A = a constant
+// "ones" pattern in TMEM (shared by both slots), B = a 4 KB image holding every layer's bias split into three 16-bit
+// terms (hi + mid + lo: exact to 2^-30 relative in fp16, 2^-24 in bf16 — below the fp32 accumulator's own rounding).
+// Layer l uses K rows 4l .. 4l+2 of the image; pattern l has ones in exactly those K positions.
+constexpr uint32_t kPatCol = 2 * kSlotCols;   // TMEM columns [384, 416): 4 patterns x 8 columns (16 K values each)
+constexpr uint32_t kBiasImgBytes = 2u * 128u * 16u;   // [2 K-chunks][128 n][8] 16-bit
 
 struct TcLayer {
   const void* w;          // global 16-bit image
@@ -67,7 +77,7 @@ struct TcArgs {
   int rb_layer;           // layer with a per-ray bias (-1: none)
   int rb_staged;          // 1: the producer stages the tile's bias rows in smem (BLOCKED order)
   // smem carve-up (byte offsets from the 1024-aligned base)
-  uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total;
+  uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total, bimg_off;
 };
 
 #ifdef NVSR_TC_TIMING
@@ -391,10 +401,49 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       }
     }
   }
+  if constexpr (kFixed) {
+    // bias image: K row 4l + t of column n = term t of layer l's bias[n] (hi, mid, lo); K rows 4l + 3 stay zero
+    uint16_t* bimg = reinterpret_cast<uint16_t*>(smem + a.bimg_off);
+    for (int i = threadIdx.x; i < LC * 128; i += kTcThreads) {
+      const int l = i >> 7, n = i & 127;
+      float rem = a.layer[l].bias ? __ldg(a.layer[l].bias + n) : 0.f;
+      uint16_t term[4];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const uint32_t pk = pack16x2<F16>(rem, 0.f);
+        term[t] = (uint16_t)(pk & 0xffffu);
+        rem -= unpack16x2<F16>(pk).x;
+      }
+      term[3] = 0;
+      const int k0 = 4 * l;   // chunk k0 / 8, position k0 % 8 within the 16-byte group
+      *reinterpret_cast<uint2*>(bimg + ((k0 >> 3) * 128 + n) * 8 + (k0 & 7)) =
+          make_uint2((uint32_t)term[0] | ((uint32_t)term[1] << 16), (uint32_t)term[2] | ((uint32_t)term[3] << 16));
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (kFixed) {
+    // "ones" patterns: pattern l = columns [kPatCol + 8l, +8) of every row, ones at K = 4l, 4l+1, 4l+2
+    if (warp < 4) {
+      const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+      uint32_t pat[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pat[j] = 0u;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        pat[8 * l + 2 * l] = one | (one << 16);   // K = 4l (low half), 4l + 1 (high half)
+        pat[8 * l + 2 * l + 1] = one;             // K = 4l + 2
+      }
+      tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + kPatCol, pat);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   // Loads of one tile into slot s: the feature tile image and, when staged, the bias rows of its 8 rays
   // (consecutive rows of row_bias in the BLOCKED order).  Issuing a bulk copy costs its thread well over a
@@ -459,19 +508,24 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       }
       tc_fence_after();
       if (elect_one()) {
-        if (l == 0) {
+        if constexpr (kFixed) {
+          // bias as a K step (see kPatCol); a layer whose bias is per ray (RB0, layer 0) keeps the pre-stored
+          // accumulator, every other layer starts from a clean accumulator (first MMA overwrites)
+          const bool kstep_bias = !(RB0 != 0 && l == 0);
+          if (l == 0) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_ss(d_base, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc,
+                      (ks > 0 || !kstep_bias) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, ks > 0 ? 1u : 0u);
+          }
+          if (kstep_bias)
+            umma_ts(d_base, tmem_base + kPatCol + 8u * (uint32_t)l, umma_desc(smem_u32(smem + a.bimg_off), 2048u, 128u), idesc, 1u);
+        } else if (l == 0) {
           for (int ks = 0; ks < ksteps; ++ks)
             umma_ss(d_base, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
-#ifdef NVSR_TC_EXP_NOBIAS
-          if (kFixed) umma_ss(d_base, adesc0, bdesc0, idesc, 1u);
-#endif
-        } else if (kFixed) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
-#ifdef NVSR_TC_EXP_NOBIAS
-          umma_ts(d_base, d_base + kSlotAOff, bdesc0, idesc, 1u);   // stands for the bias K-step
-#endif
         } else {
           for (int ks = 0; ks < ksteps; ++ks)
             umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
@@ -559,12 +613,14 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         mbar_wait(bar_rb_full, ph_rb);
         ph_rb ^= 1;
       }
-      int mode;
-      const float* bsrc = bias_src(0, first, &mode);
-      const int n0 = kFixed ? 128 : a.layer[0].n;
-      float dummy[4];
-      for (int c = 0; c < 64; c += 32)
-        if (col0 + c < n0) epi_pass<F16>(d_tmem + (uint32_t)c, 0u, false, false, false, 0, nullptr, dummy, mode, bsrc + c);
+      if (!kFixed || RB0 != 0) {
+        int mode;
+        const float* bsrc = bias_src(0, first, &mode);
+        const int n0 = kFixed ? 128 : a.layer[0].n;
+        float dummy[4];
+        for (int c = 0; c < 64; c += 32)
+          if (col0 + c < n0) epi_pass<F16>(d_tmem + (uint32_t)c, 0u, false, false, false, 0, nullptr, dummy, mode, bsrc + c);
+      }
       arrive_then_issue(true, 0, 0u);
     }
 
@@ -594,7 +650,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         const int n_next = (last && !next_valid) ? 0 : (kFixed ? 128 : a.layer[nl].n);
         const bool nl_rb = n_next > 0 && nl == rb_layer && rb_staged;
         int mode = 0;
-        const float* bsrc = n_next > 0 ? bias_src(nl, last ? next_tile : tile, &mode) : nullptr;
+        const float* bsrc = (n_next > 0 && (!kFixed || (RB0 != 0 && last))) ? bias_src(nl, last ? next_tile : tile, &mode) : nullptr;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         if (nl_rb) {
           mbar_wait(bar_rb_full, ph_rb);
@@ -608,13 +664,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #ifndef NVSR_TC_OLD_EPI
         if constexpr (kFixed) {
           // fixed chains: bias rows always come from shared memory (mode 1)
-#ifdef NVSR_TC_EXP_NOBIAS   // timing experiment only (wrong numerics): what the bias pre-store costs
-          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, false, bsrc);
+          // (hidden-layer biases ride in the MMA: only the per-ray layer-0 bias of the next tile is pre-stored)
+          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, RB0 != 0 && n_next > 0, bsrc);
           else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, false, bsrc);
-#else
-          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, n_next > 0, bsrc);
-          else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, true, bsrc);
-#endif
         } else
 #endif
         {
@@ -720,6 +772,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
     off += 2u * kRbRowsMax * kRbPitch * 4u;
   }
   a.bias_off = off, off += (uint32_t)m->n_layers * 128u * 4u;
+  a.bimg_off = off, off += kBiasImgBytes;   // bias image of the fixed chains (16-byte aligned: every size above is a multiple of 16)
   a.headw_off = off, off += kTcMaxHeadRows * 128u * 4u;
   a.hpart_off = off, off += 2u * 128u * 4u * 4u;
   a.bar_off = off, off += BAR_COUNT * 8u + 16u;  // barriers, then {tmem base, arrival counter x2}

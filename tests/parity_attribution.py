@@ -24,7 +24,9 @@ every ray that exceeds a bound to (i) or (ii) constructively — anything else f
   L4 free-running     maps vs the oracle's own free-running fine maps.  fp32: a ray above B must have merged depths that
                       differ from the oracle's (then L2 has explained them) or a last-sample step.  16-bit modes: the
                       coarse weights legitimately differ by the mode's rounding, which moves every resampled depth
-                      continuously — rays without a step are bounded by B_free (stated per mode), rays with one by L3.
+                      continuously — rays without a flip or step are bounded by B_free (stated per mode) except for at
+                      most 0.5 % of the rays (near-empty bins amplify a depth by 1/denom), each of which must be
+                      reproduced by the oracle's own fine network at the implementation's depths to within L3's bound.
 """
 import torch
 
@@ -244,10 +246,23 @@ def check_chain(c, prec, out_g, tr_g, randoms=None):
         flip_rays = flips.any(-1)
         report["free_flip_rays"] = int(flip_rays.sum())
         plain = ~step_free & ~flip_rays
-        report["free_unexplained_rays"] = int(plain.sum())
-        report["free_unexplained_max"] = float(err_free[plain].max()) if plain.any() else 0.0
-        bad = plain & (err_free > B_free)
-        assert not bool(bad.any()), (f"L4 {prec}: {int(bad.sum())} rays without a last-sample step exceed B_free "
-                                     f"{B_free}: max {float(err_free[plain].max()):.3e}")
+        # A ray without a flip or step still runs its fine pass at depths that moved CONTINUOUSLY with the cdf, and a depth
+        # inside a near-empty bin is amplified by 1/denom (nerf_helpers.py:696-699): B_free states how far that normally
+        # goes.  A ray above B_free is attributed constructively: the ORACLE's own fine network evaluated at the
+        # implementation's merged depths (the L3 run) must reproduce the excess — i.e. the reference algorithm itself
+        # moves that far when handed these depths, and what remains is within the teacher-forced bound B of L3.
+        maps_tf = _maps_of(tf["raw_fine"], g["z_fine"], rd, cfg, mip, randoms.get("noise_f"))
+        self_sens = _map_err(maps_tf, maps_of, far)
+        B_tf = bd["B"] * _interval_scale(g["z_fine"], rd, mip)
+        moved = plain & (err_free > B_free)
+        report["free_depth_sensitivity_rays"] = int(moved.sum())
+        unexpl = plain & ~moved
+        report["free_unexplained_rays"] = int(unexpl.sum())
+        report["free_unexplained_max"] = float(err_free[unexpl].max()) if unexpl.any() else 0.0
+        bad = moved & (err_free > self_sens + B_tf)
+        assert not bool(bad.any()), (f"L4 {prec}: {int(bad.sum())} rays without a flip or last-sample step exceed B_free "
+                                     f"{B_free} by more than the oracle's own sensitivity to the depths: max "
+                                     f"{float((err_free - self_sens)[moved].max()):.3e} vs {B_tf}")
+        assert int(moved.sum()) <= max(2, n // 200), f"L4 {prec}: {int(moved.sum())} of {n} rays above B_free {B_free}"
         report["free_max_incl_explained"] = float(err_free.max())
     return report
