@@ -358,6 +358,43 @@ int32_t nvsr_composite_bwd(const float* radiance_field, const float* z, const fl
                            float* d_radiance_field, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Decoder training path on the tensor cores: forward that keeps what the backward needs, data
+ * gradient chain, weight gradients — the reference's loss.backward() through models.py:393-421 (train_nerf.py:860-916).
+ * fp16 operands, fp32 accumulation; every delta carries the caller's power-of-two loss `scale`.
+ * All images are 16-bit "tile images" [tile][channels/8][128 rows][8] in the BLOCKED row order of the gather.
+ *
+ * nvsr_mlp_chain_train: nvsr_mlp_chain for one of the two tri-plane chains (4 layers x 128, NVSR_F16, NVSR_ROWS_BLOCKED) that
+ *   also stores act_out[l] = image of layer l's post-ReLU 16-bit output x_{l+1} (128 channels), l = 0..3.
+ * nvsr_mlp_dgrad: g[3] = (d_raw . head_w) * [x_4 > 0];  g[l-1] = (g[l] . W_l) * [x_l > 0];  d_x0 = g[0] . W_0 (fp32, unscaled,
+ *   ray-major rows [n_rays * n_samples][k0]); w[l] are the FORWARD weight images (read MN-major: no transposed copies);
+ *   dout_img receives the scaled head gradient as a 16-column image.  d_raw of padding rows must be 0.
+ * nvsr_mlp_wgrad: dw[m][n] += inv_scale * sum_rows a_img[r][m] * b_img[r][n] (a: 128 channels, b: n_b channels, n_b % 16 == 0),
+ *   db[m] += inv_scale * sum_rows a_img[r][m] (db may be NULL).  dw / db are ACCUMULATED into (fp32 atomics): zero them first.
+ *   Layer l: a = g[l], b = x_l (l = 0: the feature image);  head: a = x_4, b = dout_img, n_b = 16 (dw = head weight grad^T).
+ * nvsr_ray_sum: out[ray][128] = inv_scale * sum over the ray's samples of a 128-channel image (per-ray bias gradients). */
+typedef struct nvsr_dgrad {
+  const void* w[4];      /* forward weight images of layers 0..3 (nvsr_pack_weight16, NVSR_F16) */
+  int32_t k0;            /* input width of layer 0 (multiple of 16, <= 256) */
+  const float* head_w;   /* [head_n][128] fp32 */
+  int32_t head_n, head_ch;
+  const float* d_raw;    /* planar [4][raw_stride], BLOCKED rows */
+  int64_t raw_stride;
+  float scale;
+  const void* act[4];    /* x_1..x_4 images written by nvsr_mlp_chain_train */
+  void* g[4];            /* out: delta images g_0..g_3 */
+  void* dout_img;        /* out: [tiles][2][128][8] */
+  float* d_x0;           /* out: [n_rays * n_samples][k0] fp32 */
+  int64_t n_rays;
+  int32_t n_samples;
+} nvsr_dgrad_t;
+
+int32_t nvsr_mlp_chain_train(const nvsr_mlp_t* mlp, void* const* act_out, void* stream);
+int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* args, void* stream);
+int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t n_b, int64_t n_tiles, float inv_scale, float* dw,
+                       int64_t ldw, float* db, void* stream);
+int32_t nvsr_ray_sum(const void* img, int64_t n_rays, int32_t n_samples, float inv_scale, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Plane super-resolution, last step: PlanesSR.forward (models.py:884-926) ends with
  *   out = inner_model(pad(LR))[..., crop:-crop, crop:-crop] + F.interpolate(LR, scale_factor, 'bilinear', align_corners)
  * then caches `out` on the CPU (:925) and re-uploads it on every call (:893).  This entry fuses everything after the

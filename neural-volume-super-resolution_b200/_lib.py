@@ -82,6 +82,25 @@ class Mlp(C.Structure):
     ]
 
 
+class Dgrad(C.Structure):
+    _fields_ = [
+        ("w", c_p * 4),
+        ("k0", c_i32),
+        ("head_w", c_p),
+        ("head_n", c_i32),
+        ("head_ch", c_i32),
+        ("d_raw", c_p),
+        ("raw_stride", c_i64),
+        ("scale", c_f),
+        ("act", c_p * 4),
+        ("g", c_p * 4),
+        ("dout_img", c_p),
+        ("d_x0", c_p),
+        ("n_rays", c_i64),
+        ("n_samples", c_i32),
+    ]
+
+
 class Composite(C.Structure):
     _fields_ = [
         ("n_rays", c_i64),
@@ -180,6 +199,10 @@ SIGNATURES = {
     "nvsr_viewdir_gather": (c_i32, [c_p, c_i64, c_p, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p]),
     "nvsr_row_bias": (c_i32, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p]),
     "nvsr_mlp_chain": (c_i32, [C.POINTER(Mlp), c_p]),
+    "nvsr_mlp_chain_train": (c_i32, [C.POINTER(Mlp), C.POINTER(c_p), c_p]),
+    "nvsr_mlp_dgrad": (c_i32, [C.POINTER(Dgrad), c_p]),
+    "nvsr_mlp_wgrad": (c_i32, [c_p, c_p, c_i32, c_i64, c_f, c_p, c_i64, c_p, c_p]),
+    "nvsr_ray_sum": (c_i32, [c_p, c_i64, c_i32, c_f, c_p, c_p]),
     "nvsr_composite": (c_i32, [C.POINTER(Composite), c_p]),
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),

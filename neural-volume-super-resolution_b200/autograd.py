@@ -20,7 +20,24 @@ from . import _lib, ops
 from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
 
 
-_state = {"fast_frozen_coarse": False}
+_state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0}
+
+
+def set_decoder(mode):
+    """'tc' (default): the tri-plane decoder of the differentiable path — forward, data gradient and weight gradients —
+    runs on this package's tcgen05 kernels (fp16 operands, fp32 accumulation, loss-scaled deltas: csrc/train_tc.cu) and
+    the gather writes its 16-bit tile images.  'fp32': the model's own nn.Linear layers under torch autograd on fp32
+    features — the parity mode of the training path (gradients within 1e-3 of the reference's, tests/golden)."""
+    if mode not in ("tc", "fp32"):
+        raise ValueError("decoder mode must be 'tc' or 'fp32'")
+    _state["decoder"] = mode
+
+
+def set_loss_scale(scale):
+    """Power-of-two factor folded into the fp16 deltas of the 'tc' decoder backward (default 2**10; the weight and plane
+    gradients are returned unscaled).  scripts/studies/backward_precision.py: without it the deltas of an mse over
+    thousands of rays underflow fp16 (18 % gradient error); 2**10 .. 2**16 give 6e-4."""
+    _state["loss_scale"] = float(scale)
 
 
 def set_fast_frozen_coarse(on):
@@ -139,6 +156,126 @@ class _VolumeRender(torch.autograd.Function):
         return d_rf, None, None, None, None, None
 
 
+def _packed16(plane_nchw):
+    """fp16 x-pair image of a plane (the forward path's gather layout), cached per (tensor, version)"""
+    from . import scene
+    per = scene._plane_cache.get(plane_nchw, scene._Cache.key_of(plane_nchw), dict)
+    if "autograd_f16" not in per:
+        per["autograd_f16"] = ops.pack_plane(plane_nchw, ops.NVSR_F16)
+    return per["autograd_f16"]
+
+
+class PlanesRadianceTC(torch.autograd.Function):
+    """TwoDimPlanesModel.forward (models.py:381-421) for n rays x S samples entirely on this package's kernels, forward
+    AND backward: 16-bit tile-image gather -> training forward of both decoder chains on tcgen05 (activation images
+    kept) | backward: data-gradient chains and weight gradients on tcgen05 (forward operand images read MN-major),
+    plane gradients by the scatter kernels.  Inputs: 4 planes, then (weight, bias) of density_dec x4, fc_alpha,
+    rgb_dec x4, fc_rgb (20 tensors), then ro, rd, z, viewdirs, geometry.  Output radiance_field [n, S, 4]."""
+
+    @staticmethod
+    def forward(ctx, p0, p1, p2, pv, *rest):
+        params, (ro, rd, z, vd, geom) = rest[:20], rest[20:]
+        dW, dB = params[0:8:2], params[1:8:2]
+        aW, aB = params[8], params[9]
+        cW, cB = params[10:18:2], params[11:18:2]
+        rW, rB = params[18], params[19]
+        n, S = z.shape
+        C3 = 3 * p0.shape[1]
+        F16 = ops.NVSR_F16
+        packed = ops.PackedPlanes([_packed16(p) for p in (p0, p1, p2)], F16, geom.box_lo, geom.box_rng, geom.proj,
+                                  _cl_image(pv), geom.view_lo_rng, combine=geom.combine)
+        feat_p, feat_m, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, ops.FEAT_TILE_F16, z_in=z)
+        vfeat = ops.viewdir_gather(vd, packed)
+        rb = ops.row_bias(vfeat, cW[0].detach()[:, C3:], cB[0])
+        f = lambda t: t.detach().float().contiguous()
+        wd = [ops.pack_weight16(w, dtype=F16) for w in dW]
+        wc = [ops.pack_weight16(cW[0].detach()[:, :C3], dtype=F16)] + [ops.pack_weight16(w, dtype=F16) for w in cW[1:]]
+        Ld = [ops.ChainLayer(wd[i], f(dB[i]), dW[i].shape[1], 128, True, head_w=f(aW) if i == 3 else None,
+                             head_b=f(aB) if i == 3 else None, head_ch=3) for i in range(4)]
+        Lc = [ops.ChainLayer(wc[i], None if i == 0 else f(cB[i]), C3 if i == 0 else 128, 128, True,
+                             row_bias=rb if i == 0 else None, head_w=f(rW) if i == 3 else None,
+                             head_b=f(rB) if i == 3 else None, head_ch=0) for i in range(4)]
+        rows = ops.rows_padded(n, S, ops.ROWS_BLOCKED)
+        raw = ops.raw_buffer(n, S, ops.ROWS_BLOCKED, ro.device)
+        acts_d = ops.mlp_chain_train(feat_m, Ld, rows, raw, S, n)
+        acts_c = ops.mlp_chain_train(feat_p, Lc, rows, raw, S, n)
+        ctx.save_for_backward(ro, rd, z, vd, vfeat, feat_p, feat_m, *acts_d, *acts_c, *wd, *wc, aW, rW, cW[0])
+        ctx.geom, ctx.shapes = geom, [tuple(p.shape) for p in (p0, p1, p2, pv)]
+        ctx.scale = _state["loss_scale"]
+        ctx.set_materialize_grads(False)
+        return ops.raw_to_nsc(raw, n, S, ops.ROWS_BLOCKED).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_rf):
+        t = ctx.saved_tensors
+        ro, rd, z, vd, vfeat, feat_p, feat_m = t[:7]
+        acts_d, acts_c, wd, wc = t[7:11], t[11:15], t[15:19], t[19:23]
+        aW, rW, cW0 = t[23:26]
+        n, S = z.shape
+        dev = ro.device
+        Cc = ctx.shapes[0][1]
+        C3 = 3 * Cc
+        if d_rf is None:
+            return (None,) * (4 + 20 + 5)
+        scale, inv = ctx.scale, 1.0 / ctx.scale
+        d_rf = d_rf.float()
+        d_raw = ops.nsc_to_planar_blocked(d_rf, n, S)
+        z0 = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        grads = []
+        # ---- density chain: data gradient, then the weight gradients on the same images
+        g, dout, d_fm = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S)
+        dens = []
+        for l in range(4):
+            k = Cc if l == 0 else 128
+            dw, db = z0(128, k), z0(128)
+            ops.mlp_wgrad(g[l], feat_m if l == 0 else acts_d[l - 1], k, inv, dw, db)
+            dens += [dw, db]
+        dwh = z0(128, 16)
+        ops.mlp_wgrad(acts_d[3], dout, 16, inv, dwh)
+        dens += [dwh[:, :1].t().contiguous(), d_rf[..., 3].sum().reshape(1)]
+        # ---- rgb chain (its first layer's view-feature columns are a per-ray bias in the forward)
+        g, dout, d_fp = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S)
+        col = []
+        g0_ray = ops.ray_sum(g[0], n, S, inv)                        # [n, 128]: sum over the ray's samples of g_0
+        for l in range(4):
+            k = C3 if l == 0 else 128
+            dw, db = z0(128, k), z0(128)
+            ops.mlp_wgrad(g[l], feat_p if l == 0 else acts_c[l - 1], k, inv, dw, db)
+            if l == 0:
+                dw = torch.cat([dw, g0_ray.t() @ vfeat], 1)         # [128, 3C + C]
+            col += [dw, db]
+        dwh = z0(128, 16)
+        ops.mlp_wgrad(acts_c[3], dout, 16, inv, dwh)
+        col += [dwh[:, :3].t().contiguous(), d_rf[..., :3].sum((0, 1))]
+        d_v = g0_ray @ cW0.detach()[:, C3:].float()                  # [n, C]
+        # ---- planes
+        acc = [z0(s[-2], s[-1], s[-3]) for s in ctx.shapes[:3]]
+        shell = ops.PackedPlanes(acc, NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, None, ctx.geom.view_lo_rng)
+        if ctx.geom.combine == "sum":
+            d_fm = d_fm * 3.0
+        ops.sample_gather_bwd(ro, rd, z, shell, d_fp, d_fm, acc)
+        sv = ctx.shapes[3]
+        vacc = z0(sv[-2], sv[-1], sv[-3])
+        vshell = ops.PackedPlanes([vacc, vacc, vacc], NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, vacc,
+                                  ctx.geom.view_lo_rng)
+        ops.viewdir_gather_bwd(vd, vshell, d_v, vacc)
+        pg = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc + [vacc], ctx.shapes)]
+        needs = ctx.needs_input_grad
+        out = pg + dens + col + [None] * 5
+        return tuple(o if (o is None or needs[i]) else None for i, o in enumerate(out))
+
+
+def _tc_supported(model):
+    try:
+        d, c = list(model.density_dec["0"]), list(model.rgb_dec["0"])
+    except (KeyError, AttributeError, TypeError):
+        return False
+    C = next(iter(model.planes_.values())).shape[1] if len(model.planes_) else 0
+    ok = len(d) == 4 and len(c) == 4 and all(l.out_features == 128 and l.bias is not None for l in d + c)
+    return ok and C % 16 == 0 and d[0].in_features == C and c[0].in_features == 4 * C and 3 * C <= 144 \
+        and model.fc_alpha["0"].out_features == 1 and model.fc_rgb["0"].out_features == 3
+
+
 def _render(radiance_field, depth_values, ray_directions, noise_std, white_background, noise, mip=False):
     nz = None
     if noise_std > 0.0:
@@ -176,6 +313,13 @@ def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
     # view-direction plane is never super-resolved (models.py:312-326)
     planes = [model.planes(d, super_resolve=scene._should_sr(model, d)) for d in range(3)] + [model.planes(3, super_resolve=False)]
     n, S = z.shape
+    if _state["decoder"] == "tc" and _tc_supported(model) and geom.combine in ("avg", "sum"):
+        params = []
+        for seq in (model.density_dec["0"], [model.fc_alpha["0"]], model.rgb_dec["0"], [model.fc_rgb["0"]]):
+            for lin in seq:
+                params += [lin.weight, lin.bias]
+        return PlanesRadianceTC.apply(planes[0], planes[1], planes[2], planes[3], *params, ro.contiguous(), rd.contiguous(),
+                                      z.contiguous(), viewdirs.contiguous(), geom)
     feat_p, feat_m = TriPlaneGather.apply(planes[0], planes[1], planes[2], ro, rd, z, geom)
     vfeat = ViewdirGather.apply(planes[3], viewdirs, geom)
     h = feat_m
@@ -375,6 +519,8 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
             z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
             if "z_fine" in randoms:     # test hook: teacher-forced merged depths
                 z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
+            if isinstance(randoms.get("trace"), dict):
+                randoms["trace"]["z_fine"] = z_f
         rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd)
         rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background, noise_of("noise_f", Nc + Nf))
     return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, None, None, None

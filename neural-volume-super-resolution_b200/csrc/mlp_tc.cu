@@ -78,6 +78,9 @@ struct TcArgs {
   int rb_staged;          // 1: the producer stages the tile's bias rows in smem (BLOCKED order)
   // smem carve-up (byte offsets from the 1024-aligned base)
   uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total, bimg_off;
+  // training forward (TRAIN kernels): act[l] = tile images [tile][16][128][8] of layer l's post-ReLU 16-bit output —
+  // exactly the values the next layer's MMA reads (the last layer's: the head input rounded to 16 bit)
+  uint8_t* act[4];
 };
 
 #ifdef NVSR_TC_TIMING
@@ -303,9 +306,16 @@ __device__ __forceinline__ void head_dot32(uint32_t (&v)[32], const float* hw, f
 // Epilogue of one layer of a FIXED chain for one thread (= one row, this warp's 64 columns): both
 // 32-column accumulator loads are issued back to back and waited for once, so the second load's latency
 // hides behind the first group's pack/store.  ReLU always; HN > 0: last layer (heads, no A operand).
+// act (training forward only, else nullptr): this thread's 16-byte slot of the warp's first 8-column chunk in the
+// layer's activation tile image; chunk c of the warp's 64 columns lies c * 128 slots further
+__device__ __forceinline__ void store_act16(uint4* act, int chunk0, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) act[(chunk0 + c) * 128] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
 template <bool F16, int HN>
 __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, const float* hw, float (&hacc)[4],
-                                          bool bias, const float* bsrc) {
+                                          bool bias, const float* bsrc, uint4* act = nullptr) {
   if constexpr (HN == 0) {
     uint32_t v0[32], v1[32];
     tmem_ld32(d_addr, v0);
@@ -315,9 +325,11 @@ __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, cons
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
     tmem_st16(a_addr, pk);
+    if (act) store_act16(act, 0, pk);
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
     tmem_st16(a_addr + 16u, pk);
+    if (act) store_act16(act, 4, pk);
     if (bias) {
       load_bias32(bsrc, v0);
       tmem_st32(d_addr, v0);
@@ -332,11 +344,23 @@ __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, cons
     tmem_ld32(d_addr + 32u, v1);
     tmem_ld_wait();
     head_dot32<HN>(v0, hw, hacc);
+    if (act) {   // v0 holds the ReLU'd activations now
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, false>(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+      store_act16(act, 0, pk);
+    }
     if (bias) {
       load_bias32(bsrc, v0);
       tmem_st32(d_addr, v0);
     }
     head_dot32<HN>(v1, hw + 32, hacc);
+    if (act) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, false>(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+      store_act16(act, 4, pk);
+    }
     if (bias) {
       load_bias32(bsrc + 32, v1);
       tmem_st32(d_addr + 32u, v1);
@@ -347,7 +371,7 @@ __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, cons
 // LC > 0: "uniform" chain known at compile time — LC layers, all 128 wide with ReLU, one head of HN
 // rows on the last layer, per-ray bias on layer 0 iff RB0 (staged rows, BLOCKED order).  Both decoders
 // of the tri-plane model are of this shape (LC = 4).  LC == 0: generic chain described at run time.
-template <bool F16, int LC, int HN, int RB0>
+template <bool F16, int LC, int HN, int RB0, bool TRAIN = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool kFixed = LC > 0;
@@ -665,8 +689,11 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         if constexpr (kFixed) {
           // fixed chains: bias rows always come from shared memory (mode 1)
           // (hidden-layer biases ride in the MMA: only the per-ray layer-0 bias of the next tile is pre-stored)
-          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, RB0 != 0 && n_next > 0, bsrc);
-          else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, false, bsrc);
+          uint4* act = nullptr;
+          if constexpr (TRAIN)
+            act = reinterpret_cast<uint4*>(a.act[l] + tile * (int64_t)(kTileRows * 128 * 2)) + (col0 >> 3) * 128 + r;
+          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, RB0 != 0 && n_next > 0, bsrc, act);
+          else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, false, bsrc, act);
         } else
 #endif
         {
@@ -721,8 +748,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   }
 }
 
-int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
+int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out) {
   TcArgs a;
+  for (int l = 0; l < 4; ++l) a.act[l] = act_out ? (uint8_t*)act_out[l] : nullptr;
   a.n_layers = m->n_layers;
   a.rb_layer = -1;
   uint32_t off = 0;
@@ -796,7 +824,15 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st) {
   void (*kernel)(TcArgs) = nullptr;
   // compile-time specialisations: the two decoders of the tri-plane model
   const bool rb_ok = a.rb_layer < 0 || a.rb_staged;
-  if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 1 && a.rb_layer < 0)
+  if (act_out) {
+    // training forward: the two fp16 tri-plane chains only, dense BLOCKED rows
+    for (int l = 0; l < 4; ++l)
+      if (!act_out[l] || !aligned16(act_out[l])) return NVSR_ERR_INVALID_ARG;
+    if (!(uniform && m->n_layers == 4 && f16 && !sparse && m->row_order == NVSR_ROWS_BLOCKED)) return NVSR_ERR_UNSUPPORTED;
+    if (lastL.head_n == 1 && a.rb_layer < 0) kernel = mlp_chain_tc_kernel<true, 4, 1, 0, true>;
+    else if (lastL.head_n == 3 && a.rb_layer == 0 && a.rb_staged) kernel = mlp_chain_tc_kernel<true, 4, 3, 1, true>;
+    else return NVSR_ERR_UNSUPPORTED;
+  } else if (uniform && m->n_layers == 4 && rb_ok && lastL.head_n == 1 && a.rb_layer < 0)
     kernel = f16 ? mlp_chain_tc_kernel<true, 4, 1, 0> : mlp_chain_tc_kernel<false, 4, 1, 0>;
   else if (uniform && m->n_layers == 4 && lastL.head_n == 3 && a.rb_layer == 0 && sparse)
     kernel = f16 ? mlp_chain_tc_kernel<true, 4, 3, 2> : mlp_chain_tc_kernel<false, 4, 3, 2>;

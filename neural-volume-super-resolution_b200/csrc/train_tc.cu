@@ -1,0 +1,450 @@
+// Backward of the decoder MLP on the tensor cores (the reference's loss.backward() through
+// models.py:393-421, train_nerf.py:860-916).  Everything works on the FORWARD's operand images — no transposed
+// packing, no activation transposes (both descriptor claims verified on a B200 by scripts/ubench/umma_wgrad.cu):
+//
+//   forward (training)   mlp_chain_tc_kernel<..., TRAIN> (mlp_tc.cu): the inference chain that additionally stores every
+//                        layer's post-ReLU 16-bit activation tile image x_1 .. x_4 — the next MMA's exact operand.
+//   dgrad_chain_kernel   per 128-row tile: g_3 = (d_out . W_head) * [x_4 > 0] on the CUDA cores, then per layer
+//                        l = 3, 2, 1:  g_{l-1} = (g_l . W_l) * [x_l > 0]  as ONE tcgen05.mma K-loop with A = g_l in TMEM
+//                        (TS form, the forward's activation layout) and B = the forward weight image of W_l read
+//                        MN-major (8 consecutive k_in in 16 B, LBO 128 B, SBO n_out * 16 B); finally d_x0 = g_0 . W_0
+//                        written fp32 row-major for nvsr_sample_gather_bwd.  Every g_l is also stored as a 16-bit tile
+//                        image (the weight gradient's operand).  Deltas carry a power-of-two loss scale (fp16 deltas of
+//                        an mse over thousands of rays underflow otherwise: scripts/studies/backward_precision.py).
+//   wgrad_kernel         dW_l[n_out][k_in] = sum over rows g_l[r][n_out] * x_l[r][k_in]: persistent streaming kernel,
+//                        both operands are tile images read MN-major (K = the 128 rows of a tile), the accumulator
+//                        stays in TMEM over the CTA's whole slice of tiles; the bias gradient rides along as one more
+//                        N = 16 block against a resident image of ones; partials are reduced with fp32 atomics.
+//   ray_sum_kernel       per-ray sum over the samples of a delta image (the per-ray view-feature columns of the rgb
+//                        chain's first layer are a per-ray bias in the forward: their gradients are tiny per-ray GEMMs).
+#include "common.cuh"
+
+namespace nvsr {
+
+namespace {
+
+constexpr int kDgThreads = 256;          // 8 warps: quad = warp & 3 (TMEM lane quadrant), half = warp >> 2 (columns)
+constexpr uint32_t kDgTmemCols = 512;    // D: [0, 256), A: [256, 320)
+constexpr uint32_t kDgAOff = 256;
+constexpr uint32_t kActTileBytes = kTileRows * 128 * 2;
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+// kind::f16, fp16 x fp16 -> fp32, M = 128, N = n; a_mn / b_mn: the operand is MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t idesc_f16(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct DgradArgs {
+  const uint8_t* w[4];   // forward weight images W_0 .. W_3, fp16 [k/8][128][8]
+  int k0;                // input width of layer 0 (multiple of 16, <= 256): N of the last product
+  const float* head_w;   // [head_n][128] fp32
+  int head_n, head_ch;
+  const float* d_raw;    // planar [4][raw_stride], BLOCKED rows: gradient w.r.t. the chain's raw outputs
+  int64_t raw_stride;
+  float scale;           // loss scale folded into every delta; d_x0 is written unscaled
+  const uint8_t* act[4]; // x_1 .. x_4 images of the training forward
+  uint8_t* g[4];         // out: g_0 .. g_3 images (scaled)
+  uint8_t* dout_img;     // out: [tiles][2][128][8] image of the scaled head gradient (columns head_n.. are zero)
+  float* d_x0;           // out: fp32 [n_rays * S][k0], ray-major rows
+  int64_t n_tiles, n_rays;
+  int S, tiles_per_blk;
+};
+
+// this thread's mask words: the 64 activations of row r, columns [col0, col0 + 64), eight per 16-byte group
+__device__ __forceinline__ void load_mask64(const uint8_t* act_tile, int col0, int r, uint4 (&m)[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(act_tile) + (col0 >> 3) * 128 + r;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = __ldg(p + j * 128);
+}
+// activations are post-ReLU (>= +0): "positive" == any non-sign bit set
+__device__ __forceinline__ bool act_pos(const uint4& m, int e) {
+  const uint32_t w = e < 2 ? m.x : (e < 4 ? m.y : (e < 6 ? m.z : m.w));
+  return ((e & 1) ? (w >> 16) : (w & 0xffffu)) & 0x7fffu;
+}
+// pack 64 fp32 deltas (already masked) to fp16 pairs, hand them to the next MMA (TMEM A region) and to the image
+__device__ __forceinline__ void emit_delta64(const float (&d)[64], uint32_t a_addr, uint8_t* g_tile, int col0, int r) {
+  uint32_t pk[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) pk[j] = pack16x2<true>(d[2 * j], d[2 * j + 1]);
+  tmem_st32(a_addr, pk);
+  uint4* p = reinterpret_cast<uint4*>(g_tile) + (col0 >> 3) * 128 + r;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j * 128] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+
+__global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid_constant__ DgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_headw[4 * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int r = quad * 32 + lane, col0 = half * 64;
+  // smem: W_3 | W_2 | W_1 (32 KB each) | W_0 (k0 * 256 B)
+  const uint32_t w_hidden = 128u * 128u * 2u, w0_bytes = (uint32_t)a.k0 * 256u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1), mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kDgTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 4 * 128; i += kDgThreads) s_headw[i] = (i >> 7) < a.head_n ? __ldg(a.head_w + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0 && blockIdx.x < a.n_tiles) {
+    mbar_arrive_expect_tx(&bar_w, 3u * w_hidden + w0_bytes);
+    for (int l = 3; l >= 1; --l) bulk_g2s(smem + (3 - l) * w_hidden, a.w[l], w_hidden, &bar_w);
+    bulk_g2s(smem + 3 * w_hidden, a.w[0], w0_bytes, &bar_w);
+  }
+  const uint32_t d_tmem = tmem + ((uint32_t)(quad * 32) << 16);                   // this warp's lanes, column 0 of D
+  const uint32_t a_tmem = d_tmem + kDgAOff + (uint32_t)(col0 >> 1);               // its 32 columns of the A region
+  uint32_t ph = 0;
+  bool w_ready = false;
+
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    // ---- g_3 = (d_out . W_head) * [x_4 > 0], on the CUDA cores ----
+    {
+      float dv[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        dv[h] = h < a.head_n ? __ldg(a.d_raw + (int64_t)(a.head_ch + h) * a.raw_stride + tile * kTileRows + r) * a.scale : 0.f;
+      uint4 m[8];
+      load_mask64(a.act[3] + tile * (int64_t)kActTileBytes, col0, r, m);
+      float d[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float v = dv[0] * s_headw[col0 + c];
+#pragma unroll
+        for (int h = 1; h < 4; ++h) v = fmaf(dv[h], s_headw[h * 128 + col0 + c], v);
+        d[c] = act_pos(m[c >> 3], c & 7) ? v : 0.f;
+      }
+      emit_delta64(d, a_tmem, a.g[3] + tile * (int64_t)kActTileBytes, col0, r);
+      if (half == 0) {   // the head gradient as a 16-column image (the head weight gradient's B operand)
+        uint4* p = reinterpret_cast<uint4*>(a.dout_img + tile * (int64_t)(2 * kTileRows * 16)) + r;
+        p[0] = make_uint4(pack16x2<true>(dv[0], dv[1]), pack16x2<true>(dv[2], dv[3]), 0u, 0u);
+        p[128] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    // ---- g_{l-1} = (g_l . W_l) * [x_l > 0] for l = 3, 2, 1; then d_x0 = g_0 . W_0 ----
+#pragma unroll 1
+    for (int l = 3; l >= 0; --l) {
+      const int n = l > 0 ? 128 : a.k0;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncthreads();   // every thread's g_l is in TMEM (and the previous accumulator has been read)
+      if (warp == 0) {
+        if (!w_ready) mbar_wait(&bar_w, 0);
+        tc_fence_after();
+        if (elect_one()) {
+          // B = forward weight image [k_in/8][128 n_out][8] read MN-major: N = k_in, K = n_out
+          const uint64_t b0 = smem_desc(smem_u32(smem + (3 - l) * w_hidden), 128u, 2048u);
+          const uint32_t idesc = idesc_f16(n, false, true);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ts(tmem, tmem + kDgAOff + (uint32_t)ks * 8u, b0 + (uint64_t)(ks * 16), idesc, ks ? 1u : 0u);
+          umma_commit(&bar_mma);
+        }
+        __syncwarp();
+      }
+      w_ready = true;
+      // the mask of the layer below does not depend on the accumulator: fetch it while the MMAs run
+      uint4 m[8];
+      if (l > 0) load_mask64(a.act[l - 1] + tile * (int64_t)kActTileBytes, col0, r, m);
+      mbar_wait(&bar_mma, ph);
+      ph ^= 1;
+      tc_fence_after();
+      if (l > 0) {
+        float d[64];
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(d_tmem + (uint32_t)col0, v0);
+          tmem_ld32(d_tmem + (uint32_t)col0 + 32u, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            d[c] = act_pos(m[c >> 3], c & 7) ? __uint_as_float(v0[c]) : 0.f;
+            d[32 + c] = act_pos(m[4 + (c >> 3)], c & 7) ? __uint_as_float(v1[c]) : 0.f;
+          }
+        }
+        emit_delta64(d, a_tmem, a.g[l - 1] + tile * (int64_t)kActTileBytes, col0, r);
+      } else {
+        // d_x0: 16-column units split over the two column halves; fp32, unscaled, ray-major rows
+        const int units = a.k0 >> 4, u_half = (units + 1) >> 1;
+        const int u0 = half == 0 ? 0 : u_half, u1 = half == 0 ? u_half : units;
+        const int64_t blk = tile / a.tiles_per_blk;
+        const int s = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
+        const int64_t ray = blk * kBlkRays + (r & 7);
+        const bool valid = ray < a.n_rays && s < a.S;
+        const float inv = 1.0f / a.scale;
+        float* out = a.d_x0 + (valid ? (ray * a.S + s) * (int64_t)a.k0 : 0);
+        for (int u = u0; u < u1; ++u) {
+          uint32_t v[16];
+          tmem_ld16(d_tmem + (uint32_t)(u * 16), v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(out + u * 16 + 4 * j) =
+                  make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                              __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+          }
+        }
+      }
+    }
+    // the last accumulator has been read by everyone before the next tile's first MMA: the __syncthreads at the top
+    // of the next layer loop orders it (tcgen05.ld completes at tmem_ld_wait)
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kDgTmemCols) : "memory");
+  }
+}
+
+// ---- weight gradient ------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 128;
+constexpr int kWgStages = 3;
+
+// dW[m][n] += inv_scale * sum over the tiles' rows of A[r][m] * B[r][n]  (A: 128 channels, B: n_b channels, both tile
+// images), db[m] += inv_scale * sum over rows of A[r][m] (optional).  One warp loads and issues, four read out.
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, int n_b, int64_t n_tiles, float inv_scale,
+             float* __restrict__ dw, int64_t ldw, float* __restrict__ db) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[kWgStages], empty[kWgStages], done;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t a_bytes = kActTileBytes, b_bytes = (uint32_t)kTileRows * (uint32_t)n_b * 2u, st_bytes = a_bytes + b_bytes;
+  uint8_t* ones = smem + kWgStages * st_bytes;   // [2][128][8] fp16 1.0
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+    mbar_init(&done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * kTileRows * 8 / 2; i += kWgThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0 && my_tiles > 0) {
+    auto load = [&](int64_t t) {
+      const int s = (int)(t % kWgStages);
+      const int64_t tile = blockIdx.x + t * gridDim.x;
+      mbar_arrive_expect_tx(&full[s], st_bytes);
+      bulk_g2s(smem + s * st_bytes, a_img + tile * a_bytes, a_bytes, &full[s]);
+      bulk_g2s(smem + s * st_bytes + a_bytes, b_img + tile * (int64_t)b_bytes, b_bytes, &full[s]);
+    };
+    for (int64_t t = 0; t < kWgStages && t < my_tiles; ++t) load(t);
+    // both operands MN-major: 8 consecutive MN (channels) in 16 B, the next 8 rows (K) 128 B further (LBO), the next 8
+    // channels 128 rows * 16 B further (SBO); 16 rows per MMA = + 256 B
+    const uint32_t idesc = idesc_f16(n_b, true, true), idesc1 = idesc_f16(16, true, true);
+    const uint64_t o0 = smem_desc(smem_u32(ones), 128u, 2048u);
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int s = (int)(t % kWgStages);
+      const uint32_t par = (uint32_t)((t / kWgStages) & 1);
+      mbar_wait(&full[s], par);
+      tc_fence_after();
+      const uint64_t a0 = smem_desc(smem_u32(smem + s * st_bytes), 128u, 2048u);
+      const uint64_t b0 = smem_desc(smem_u32(smem + s * st_bytes + a_bytes), 128u, 2048u);
+#pragma unroll
+      for (int ks = 0; ks < kTileRows / 16; ++ks) {
+        umma_ss(tmem, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, (t | ks) ? 1u : 0u);
+        if (db) umma_ss(tmem + 256u, a0 + (uint64_t)(ks * 16), o0 + (uint64_t)(ks * 16), idesc1, (t | ks) ? 1u : 0u);
+      }
+      umma_commit(&empty[s]);   // arrives when the MMAs above have finished reading stage s
+      // refill the stage of the PREVIOUS tile (its MMAs have had this tile's issue time to finish): the issuer never
+      // waits for the MMAs it has just issued
+      if (t >= 1 && t - 1 + kWgStages < my_tiles) {
+        mbar_wait(&empty[(t - 1) % kWgStages], (uint32_t)(((t - 1) / kWgStages) & 1));
+        load(t - 1 + kWgStages);
+      }
+    }
+    umma_commit(&done);
+  }
+  __syncwarp();
+  if (my_tiles > 0) {
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    // warp w reads TMEM lanes 32w .. 32w+31 = output rows m; 16 columns (n) at a time
+    const int m = warp * 32 + lane;
+    for (int c0 = 0; c0 < n_b; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(dw + (int64_t)m * ldw + c0 + j, __uint_as_float(v[j]) * inv_scale);
+    }
+    if (db) {
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + 256u, v);
+      tmem_ld_wait();
+      atomicAdd(db + m, __uint_as_float(v[0]) * inv_scale);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// out[ray][c] = inv_scale * sum over the ray's samples of img[row(ray, s)][c]; one thread per (ray, 8-channel chunk)
+__global__ void __launch_bounds__(256)
+ray_sum_kernel(const uint8_t* __restrict__ img, int64_t n_rays, int S, int tiles_per_blk, float inv_scale, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rays * 16) return;
+  const int64_t ray = idx >> 4;
+  const int j = (int)(idx & 15);
+  const int64_t blk = ray / kBlkRays;
+  const int rr = (int)(ray - blk * kBlkRays);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < S; ++s) {
+    const int64_t tile = blk * tiles_per_blk + s / kBlkSamples;
+    const int row = (s % kBlkSamples) * kBlkRays + rr;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + tile * (int64_t)kActTileBytes) + j * 128 + row);
+    const float2 f0 = unpack16x2<true>(v.x), f1 = unpack16x2<true>(v.y), f2 = unpack16x2<true>(v.z), f3 = unpack16x2<true>(v.w);
+    acc[0] += f0.x, acc[1] += f0.y, acc[2] += f1.x, acc[3] += f1.y, acc[4] += f2.x, acc[5] += f2.y, acc[6] += f3.x, acc[7] += f3.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[ray * 128 + j * 8 + e] = acc[e] * inv_scale;
+}
+
+}  // namespace
+
+int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out);
+
+}  // namespace nvsr
+
+using namespace nvsr;
+
+extern "C" int32_t nvsr_mlp_chain_train(const nvsr_mlp_t* m, void* const* act_out, void* stream) {
+  NVSR_CHECK_ARG(m && act_out && m->n_layers == 4 && m->precision == NVSR_F16);
+  NVSR_CHECK_ARG(m->in && m->raw && m->rows >= 0 && m->raw_stride >= m->rows);
+  if (m->rows == 0) return NVSR_OK;
+  return launch_mlp_tc(m, (cudaStream_t)stream, act_out);
+}
+
+extern "C" int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* d, void* stream) {
+  NVSR_CHECK_ARG(d && d->k0 > 0 && (d->k0 % 16) == 0 && d->k0 <= 256 && d->head_n >= 1 && d->head_n <= 4);
+  NVSR_CHECK_ARG(d->head_ch >= 0 && d->head_ch + d->head_n <= 4 && d->head_w && d->d_raw && d->dout_img && d->d_x0);
+  NVSR_CHECK_ARG(d->n_rays > 0 && d->n_samples > 0 && d->scale > 0.f);
+  DgradArgs a;
+  for (int l = 0; l < 4; ++l) {
+    NVSR_CHECK_ARG(d->w[l] && d->act[l] && d->g[l]);
+    if (!aligned16(d->w[l]) || !aligned16(d->act[l]) || !aligned16(d->g[l])) return NVSR_ERR_ALIGNMENT;
+    a.w[l] = (const uint8_t*)d->w[l], a.act[l] = (const uint8_t*)d->act[l], a.g[l] = (uint8_t*)d->g[l];
+  }
+  if (!aligned16(d->dout_img) || !aligned16(d->d_x0)) return NVSR_ERR_ALIGNMENT;
+  a.k0 = d->k0, a.head_w = d->head_w, a.head_n = d->head_n, a.head_ch = d->head_ch;
+  a.d_raw = d->d_raw, a.raw_stride = d->raw_stride, a.scale = d->scale;
+  a.dout_img = (uint8_t*)d->dout_img, a.d_x0 = d->d_x0;
+  a.n_rays = d->n_rays, a.S = d->n_samples, a.tiles_per_blk = tiles_per_block(d->n_samples);
+  a.n_tiles = ceil_div64(d->n_rays, kBlkRays) * a.tiles_per_blk;
+  NVSR_CHECK_ARG(d->raw_stride >= a.n_tiles * kTileRows);
+  const uint32_t smem_bytes = 3u * 128u * 128u * 2u + (uint32_t)d->k0 * 256u;
+  cudaError_t e = cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return (int32_t)e;
+  const int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
+  dgrad_chain_kernel<<<(unsigned)grid, kDgThreads, smem_bytes, (cudaStream_t)stream>>>(a);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t n_b, int64_t n_tiles, float inv_scale,
+                                  float* dw, int64_t ldw, float* db, void* stream) {
+  NVSR_CHECK_ARG(a_img && b_img && dw && n_b >= 16 && (n_b % 16) == 0 && n_b <= 256 && ldw >= n_b && n_tiles >= 0);
+  if (!aligned16(a_img) || !aligned16(b_img)) return NVSR_ERR_ALIGNMENT;
+  if (n_tiles == 0) return NVSR_OK;
+  const uint32_t smem_bytes = kWgStages * (kActTileBytes + (uint32_t)kTileRows * (uint32_t)n_b * 2u) + 2u * kTileRows * 16u;
+  if (smem_bytes > 227u * 1024u) return NVSR_ERR_RESOURCE;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return (int32_t)e;
+  const int64_t grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  wgrad_kernel<<<(unsigned)grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>((const uint8_t*)a_img, (const uint8_t*)b_img, n_b,
+                                                                                  n_tiles, inv_scale, dw, ldw, db);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_ray_sum(const void* img, int64_t n_rays, int32_t n_samples, float inv_scale, float* out, void* stream) {
+  NVSR_CHECK_ARG(img && out && n_rays >= 0 && n_samples > 0);
+  if (n_rays == 0) return NVSR_OK;
+  const int64_t threads = n_rays * 16;
+  ray_sum_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img, n_rays, n_samples,
+                                                                                       tiles_per_block(n_samples), inv_scale, out);
+  NVSR_RETURN_LAST_ERROR();
+}

@@ -359,17 +359,10 @@ class ChainLayer:
         self.row_bias, self.head_w, self.head_b, self.head_ch = row_bias, head_w, head_b, head_ch
 
 
-def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, row_order=ROWS_RAY_MAJOR,
-              row_ids=None, row_count=None):
-    """Evaluate one decoder chain (models.py:393-421 / :85-108) over `rows` rows into planar raw [4,stride].
-    `rows` counts the rows of the input buffer (padded rows included for ROWS_BLOCKED).  With `row_ids` /
-    `row_count` (sparse colour path) input row i stands for BLOCKED row row_ids[i] and row_count[0] rows are
-    evaluated; `rows` is then the capacity of the input buffer."""
-    lib = _lib.load()
+def _mlp_struct(inp, layers, rows, raw, precision, samples_per_ray, n_rays, row_order, row_ids=None, row_count=None):
     m = _lib.Mlp()
     m.precision = precision
     m.n_layers = len(layers)
-    keep = []
     for i, ly in enumerate(layers):
         c = m.layer[i]
         c.w = ly.w.data_ptr()
@@ -380,7 +373,6 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, ro
         c.k, c.n_out, c.relu = ly.k, ly.n_out, int(bool(ly.relu))
         c.head_n = 0 if ly.head_w is None else ly.head_w.shape[0]
         c.head_ch = ly.head_ch
-        keep.append(ly)
     m.in_ = inp.data_ptr()
     m.rows = rows
     m.samples_per_ray = samples_per_ray
@@ -390,15 +382,103 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, ro
     m.row_order = row_order
     m.row_ids = 0 if row_ids is None else row_ids.data_ptr()
     m.row_count = 0 if row_count is None else row_count.data_ptr()
+    # true MACs x2 only (no padding): layers + heads
+    fpr = 2 * sum(ly.k * ly.n_out + (0 if ly.head_w is None else ly.head_w.shape[0] * ly.n_out) for ly in layers)
+    bpr = layers[0].k * (4 if precision == NVSR_F32 else 2) + 4 * sum(
+        0 if ly.head_w is None else ly.head_w.shape[0] for ly in layers)
+    return m, fpr, bpr
+
+
+def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, row_order=ROWS_RAY_MAJOR,
+              row_ids=None, row_count=None):
+    """Evaluate one decoder chain (models.py:393-421 / :85-108) over `rows` rows into planar raw [4,stride].
+    `rows` counts the rows of the input buffer (padded rows included for ROWS_BLOCKED).  With `row_ids` /
+    `row_count` (sparse colour path) input row i stands for BLOCKED row row_ids[i] and row_count[0] rows are
+    evaluated; `rows` is then the capacity of the input buffer."""
+    lib = _lib.load()
+    m, fpr, bpr = _mlp_struct(inp, layers, rows, raw, precision, samples_per_ray, n_rays, row_order, row_ids, row_count)
     with torch.cuda.device(raw.device):
-        # true MACs x2 only (no padding): layers + heads; `count` (sparse): rows actually evaluated, on the device
-        fpr = 2 * sum(ly.k * ly.n_out + (0 if ly.head_w is None else ly.head_w.shape[0] * ly.n_out) for ly in layers)
-        bpr = layers[0].k * (4 if precision == NVSR_F32 else 2) + 4 * sum(
-            0 if ly.head_w is None else ly.head_w.shape[0] for ly in layers)
+        # `count` (sparse): rows actually evaluated, on the device
         st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows, count=row_count,
                    flops_per_row=fpr, bytes_per_row=bpr, flops=rows * fpr, bytes=rows * bpr)
     _lib.check(st, "nvsr_mlp_chain")
     return raw
+
+
+# ---- decoder training path on the tensor cores (SURVEY.md §8f rank 1; csrc/train_tc.cu) ------------------------
+ACT_TILE_ELEMS = TILE_ROWS * 128
+
+
+def mlp_chain_train(inp, layers, rows, raw, samples_per_ray, n_rays):
+    """`mlp_chain` (fp16, BLOCKED rows, one of the two tri-plane chains) that also returns the four activation images
+    x_1..x_4 [tiles,16,128,8] fp16 the backward needs."""
+    lib = _lib.load()
+    m, fpr, bpr = _mlp_struct(inp, layers, rows, raw, NVSR_F16, samples_per_ray, n_rays, ROWS_BLOCKED)
+    tiles = rows // TILE_ROWS
+    acts = [torch.empty((tiles, 16, TILE_ROWS, 8), dtype=torch.float16, device=raw.device) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[a.data_ptr() for a in acts])
+    with torch.cuda.device(raw.device):
+        st = _call("nvsr_mlp_chain_train", lib.nvsr_mlp_chain_train, C.byref(m), ptrs, _stream(), rows=rows,
+                   flops=rows * fpr, bytes=rows * (bpr + 4 * 256))
+    _lib.check(st, "nvsr_mlp_chain_train")
+    return acts
+
+
+def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples):
+    """Data-gradient chain of one tri-plane decoder chain.  w_imgs: the 4 forward weight images (fp16); head_w [h,128]
+    fp32; d_raw planar [4,stride] (BLOCKED rows, padding rows 0); acts: x_1..x_4 images.
+    -> (g images g_0..g_3, d_out image [tiles,2,128,8], d_x0 fp32 [n_rays*n_samples, k0])."""
+    lib = _lib.load()
+    dev = d_raw.device
+    tiles = rows_padded(n_rays, n_samples, ROWS_BLOCKED) // TILE_ROWS
+    g = [torch.empty((tiles, 16, TILE_ROWS, 8), dtype=torch.float16, device=dev) for _ in range(4)]
+    dout = torch.empty((tiles, 2, TILE_ROWS, 8), dtype=torch.float16, device=dev)
+    d_x0 = torch.empty((n_rays * n_samples, k0), dtype=torch.float32, device=dev)
+    head_w = _f32c(head_w.detach())
+    a = _lib.Dgrad()
+    for l in range(4):
+        a.w[l], a.act[l], a.g[l] = w_imgs[l].data_ptr(), acts[l].data_ptr(), g[l].data_ptr()
+    a.k0, a.head_w, a.head_n, a.head_ch = k0, head_w.data_ptr(), head_w.shape[0], head_ch
+    a.d_raw, a.raw_stride, a.scale = d_raw.data_ptr(), d_raw.stride(0), float(scale)
+    a.dout_img, a.d_x0, a.n_rays, a.n_samples = dout.data_ptr(), d_x0.data_ptr(), n_rays, n_samples
+    with torch.cuda.device(dev):
+        rows = tiles * TILE_ROWS
+        st = _call("nvsr_mlp_dgrad", lib.nvsr_mlp_dgrad, C.byref(a), _stream(), rows=rows,
+                   flops=rows * 2 * (3 * 128 * 128 + k0 * 128 + head_w.shape[0] * 128), bytes=rows * (8 * 256 + 4 * k0 + 16))
+    _lib.check(st, "nvsr_mlp_dgrad")
+    return g, dout, d_x0
+
+
+def mlp_wgrad(a_img, b_img, n_b, inv_scale, dw, db=None):
+    """dw[128, n_b] += inv_scale * a^T b over every row of the two tile images; db[128] += inv_scale * column sums of a."""
+    lib = _lib.load()
+    tiles = a_img.shape[0]
+    assert b_img.shape[0] == tiles and dw.dtype == torch.float32 and dw.stride(1) == 1
+    with torch.cuda.device(dw.device):
+        st = _call("nvsr_mlp_wgrad", lib.nvsr_mlp_wgrad, _ptr(a_img), _ptr(b_img), n_b, tiles, float(inv_scale), _ptr(dw),
+                   dw.stride(0), _ptr(db), _stream(), rows=tiles * TILE_ROWS, flops=tiles * TILE_ROWS * 2 * 128 * n_b,
+                   bytes=tiles * TILE_ROWS * 2 * (128 + n_b))
+    _lib.check(st, "nvsr_mlp_wgrad")
+    return dw
+
+
+def ray_sum(img, n_rays, n_samples, inv_scale=1.0):
+    """[n_rays, 128] fp32 = inv_scale * per-ray sum over the samples of a 128-channel tile image (BLOCKED rows)."""
+    lib = _lib.load()
+    out = torch.empty((n_rays, 128), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        st = _call("nvsr_ray_sum", lib.nvsr_ray_sum, _ptr(img), n_rays, n_samples, float(inv_scale), _ptr(out), _stream())
+    _lib.check(st, "nvsr_ray_sum")
+    return out
+
+
+def nsc_to_planar_blocked(x, n_rays, n_samples):
+    """[N, S, 4] -> planar [4, stride] in the BLOCKED row order, padding rows 0 (inverse of raw_to_nsc)."""
+    nb, ts = -(-n_rays // BLK_RAYS), -(-n_samples // BLK_SAMPLES)
+    buf = torch.zeros((nb * BLK_RAYS, ts * BLK_SAMPLES, 4), dtype=torch.float32, device=x.device)
+    buf[:n_rays, :n_samples] = x
+    r = buf.reshape(nb, BLK_RAYS, ts, BLK_SAMPLES, 4).permute(4, 0, 2, 3, 1)     # [ch, block, sblock, s%16, ray%8]
+    return r.reshape(4, nb * ts * TILE_ROWS).contiguous()
 
 
 # ---------------------------------------------------------------------------------------------

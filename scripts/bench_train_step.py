@@ -4,7 +4,8 @@
 One step = the reference's train iteration on the render path (train_nerf.py:860-905): 4 096 rays
 (config/TrainModels.yml:8), 64 coarse + 128 fine samples with perturbation, mse on rgb_coarse + rgb_fine, backward to
 the tri-planes and both decoders.  Two arms, same scene, same rays, same random draws:
-  nvsr   nvsr_b200.autograd.run_one_iter_of_nerf (gather / compositing forward+backward kernels, decoder on torch)
+  nvsr   nvsr_b200.autograd.run_one_iter_of_nerf: gather / compositing forward+backward kernels and the decoder's forward,
+         data gradient and weight gradients on tcgen05 ('tc', default); also timed in its fp32 parity mode (decoder on torch)
   torch  the same step written with stock PyTorch ops on the GPU (F.grid_sample, nn.Linear, cumprod, searchsorted) —
          what the reference's own code executes on a CUDA device
 Prints one JSON object with ms per step (CUDA events, after warm-up), the gradient agreement between the arms and the
@@ -139,11 +140,20 @@ def main():
         return e0.elapsed_time(e1) / args.steps
 
     res = {"rays": args.rays, "samples": [Nc, Nf], "plane_res": args.plane_res}
+    A.set_decoder("tc")          # decoder forward + backward on tcgen05 (the default of the differentiable path)
     res["nvsr_ms"] = timed(nvsr_arm)
     g_n = [None if p.grad is None else p.grad.clone() for p in params]
+    A.set_decoder("fp32")        # fp32 parity mode: gather / compositing kernels + the model's nn.Linear under torch autograd
+    res["nvsr_fp32_mode_ms"] = timed(nvsr_arm)
+    g_f = [None if p.grad is None else p.grad.clone() for p in params]
+    A.set_decoder("tc")
     res["torch_ms"] = timed(torch_arm)
     g_t = [None if p.grad is None else p.grad.clone() for p in params]
-    res["max_rel_grad_diff"] = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g_n, g_t) if a is not None and b is not None)
+
+    def rel_l2(x, y):
+        return max(float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)) for a, b in zip(x, y) if a is not None and b is not None)
+    res["max_rel_l2_grad_diff_tc_vs_torch"] = rel_l2(g_n, g_t)
+    res["max_rel_l2_grad_diff_fp32_mode_vs_torch"] = rel_l2(g_f, g_t)
     ops.PROFILE = []
     zero(), nvsr_arm()
     torch.cuda.synchronize()

@@ -9,6 +9,7 @@ from oracle import nvsr_oracle as O
 import test_gpu_next_rows as T
 
 DEV = "cuda:0"
+A.set_decoder("fp32")
 g, sid, opt, scfg, batch = T._train_case()
 target = H.T(g["target"], DEV)
 rnd = H.randoms_from(g, DEV)
