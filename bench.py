@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS),
                     help="BASELINE.json config that is the headline workload (default: cfg2, the one the metric is quoted on)")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32", "fp16-split"])
     ap.add_argument("--ray-chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
@@ -547,6 +547,11 @@ def main():
             nvsr_b200.set_precision("fp32")
             frame_device()
             ms32 = timed(frame_device, 2)
+            ms_split = None
+            if args.config != "cfg3b":
+                nvsr_b200.set_precision("fp16-split")
+                frame_device()
+                ms_split = timed(frame_device, 3)
             nvsr_b200.set_precision(args.precision)
             precision_modes = {
                 args.precision: {"ms_per_step": ms_dev, "value": wl.rays / (ms_dev * 1e-3), "unit": "rays/s",
@@ -554,6 +559,12 @@ def main():
                                              "(DESIGN.md section 2)"},
                 "fp32": {"ms_per_step": ms32, "value": wl.rays / (ms32 * 1e-3), "unit": "rays/s", "frames_timed": 2,
                          "contract": "SIMT fp32 decoder, fp32 planes and features: the 1e-3 parity mode"}}
+            if ms_split is not None:
+                precision_modes["fp16-split"] = {
+                    "ms_per_step": ms_split, "value": wl.rays / (ms_split * 1e-3), "unit": "rays/s", "frames_timed": 3,
+                    "contract": "tcgen05 decoder; the density chain with split fp16 operands (3 MMA passes per layer) on "
+                                "fp32-gathered features, the colour chain in fp16: meets the 1e-3 map contract "
+                                "(tests/parity_attribution.py, mode 'fp16-split')"}
             if args.config == "cfg2":
                 torch_gpu = time_torch_gpu_frame(wl, dev)
     agg = {}
@@ -626,7 +637,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "per_step": per_step.get("device"),   # rank 0's own per-frame median / min / max over the timed steps
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate", "fp32": "f32"}[args.precision],
+            "dtype": {"fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate", "fp32": "f32",
+                      "fp16-split": "f16 operands (density chain: split hi+lo, 3 passes), f32 accumulate"}[args.precision],
             "data": "synthetic",
             "config": {"workload": wl.workload, "what": wl.desc, "rays_per_step": rays,
                        "planes": "3x48x200^2 + 48x32^2" if args.config != "cfg3b" else None,

@@ -358,6 +358,18 @@ int32_t nvsr_composite_bwd(const float* radiance_field, const float* z, const fl
                            float* d_radiance_field, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Decoder chain on the tensor cores at fp32-grade accuracy ('fp16-split' precision mode): one tri-plane chain
+ * (k0 -> 128 x4 -> head_n, ReLU) with every operand split into two fp16 terms and three tcgen05.mma passes per layer
+ * (hi.hi + lo.hi + hi.lo, fp32 accumulation; csrc/mlp_split.cu).  feat: fp32 row-major features [n_rays * n_samples][k0]
+ * in RAY-MAJOR rows (the fp32 gather; nvsr_sample_gather with NVSR_FEAT_ROWMAJOR_F32 and feat_p = NULL writes only the
+ * combined features); w_hi[l] / w_lo[l]: nvsr_pack_weight16(NVSR_F16) images of W and of W - fp16(W); bias[l]: fp32 [128].
+ * Heads are written into planar raw[head_ch ..][raw_stride] in the BLOCKED row order, like nvsr_mlp_chain. */
+int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const void* const* w_hi, const void* const* w_lo,
+                             const float* const* bias, const float* head_w, const float* head_b, int32_t head_n,
+                             int32_t head_ch, int64_t n_rays, int32_t n_samples, float* raw, int64_t raw_stride,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Decoder training path on the tensor cores: forward that keeps what the backward needs, data
  * gradient chain, weight gradients — the reference's loss.backward() through models.py:393-421 (train_nerf.py:860-916).
  * fp16 operands, fp32 accumulation; every delta carries the caller's power-of-two loss `scale`.

@@ -199,6 +199,8 @@ SIGNATURES = {
     "nvsr_viewdir_gather": (c_i32, [c_p, c_i64, c_p, c_i32, c_i32, c_i32, c_f, c_f, c_f, c_f, c_p, c_p]),
     "nvsr_row_bias": (c_i32, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p]),
     "nvsr_mlp_chain": (c_i32, [C.POINTER(Mlp), c_p]),
+    "nvsr_mlp_chain_split": (c_i32, [c_p, c_i32, C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_p), c_p, c_p, c_i32, c_i32, c_i64, c_i32,
+                                     c_p, c_i64, c_p]),
     "nvsr_mlp_chain_train": (c_i32, [C.POINTER(Mlp), C.POINTER(c_p), c_p]),
     "nvsr_mlp_dgrad": (c_i32, [C.POINTER(Dgrad), c_p]),
     "nvsr_mlp_wgrad": (c_i32, [c_p, c_p, c_i32, c_i64, c_f, c_p, c_i64, c_p, c_p]),

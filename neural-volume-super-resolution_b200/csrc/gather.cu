@@ -106,7 +106,7 @@ gather_rowmajor_f32(SamplerArgs a, PlaneArgs p, float* __restrict__ featP, float
     o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.y, b[d].w00), __fmul_rn(v01.y, b[d].w01)), __fmul_rn(v10.y, b[d].w10)), __fmul_rn(v11.y, b[d].w11));
     o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.z, b[d].w00), __fmul_rn(v01.z, b[d].w01)), __fmul_rn(v10.z, b[d].w10)), __fmul_rn(v11.z, b[d].w11));
     o.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.w, b[d].w00), __fmul_rn(v01.w, b[d].w01)), __fmul_rn(v10.w, b[d].w10)), __fmul_rn(v11.w, b[d].w11));
-    *reinterpret_cast<float4*>(featP + row * (3 * p.C) + d * p.C + ch) = o;
+    if (featP) *reinterpret_cast<float4*>(featP + row * (3 * p.C) + d * p.C + ch) = o;
     m.x = __fadd_rn(m.x, o.x), m.y = __fadd_rn(m.y, o.y), m.z = __fadd_rn(m.z, o.z), m.w = __fadd_rn(m.w, o.w);
   }
   // combine_pos_planes('avg'): stack(...).mean(0) = sum / 3; 'sum': the sum itself
@@ -393,7 +393,7 @@ using namespace nvsr;
 
 extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes_t* pl, int32_t feat_layout,
                                       void* feat_p, void* feat_m, float* z_out, void* stream) {
-  NVSR_CHECK_ARG(s && pl && feat_m && (feat_p || feat_layout != NVSR_FEAT_ROWMAJOR_F32));
+  NVSR_CHECK_ARG(s && pl && feat_m);   // feat_p == NULL: only the combined features are written
   NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd);
   NVSR_CHECK_ARG(s->z_in || s->t_vals);
   NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64);

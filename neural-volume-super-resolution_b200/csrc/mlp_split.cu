@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) chain_split_kernel(const __grid
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[4 * 128];
-  __shared__ float s_headw[4 * 128];
-  __shared__ float s_hpart[128 * 4];
+  __shared__ __align__(16) float s_bias[4 * 128];
+  __shared__ __align__(16) float s_headw[4 * 128];
+  __shared__ __align__(16) float s_hpart[128 * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int r = quad * 32 + lane, col0 = half * 64;

@@ -235,7 +235,7 @@ def feature_buffers(n_rays, n_samples, channels, layout, device, density_only=Fa
     if density_only and layout != FEAT_ROWMAJOR_F32:
         return (None, torch.empty((rows // TILE_ROWS, channels // 8, TILE_ROWS, 8), dtype=LAYOUT_DTYPE[layout], device=device))
     if layout == FEAT_ROWMAJOR_F32:
-        return (torch.empty((rows, 3 * channels), dtype=torch.float32, device=device),
+        return (None if density_only else torch.empty((rows, 3 * channels), dtype=torch.float32, device=device),
                 torch.empty((rows, channels), dtype=torch.float32, device=device))
     tiles = rows // TILE_ROWS
     dt = LAYOUT_DTYPE[layout]
@@ -402,6 +402,23 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, ro
         st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows, count=row_count,
                    flops_per_row=fpr, bytes_per_row=bpr, flops=rows * fpr, bytes=rows * bpr)
     _lib.check(st, "nvsr_mlp_chain")
+    return raw
+
+
+def mlp_chain_split(feat, w_hi, w_lo, biases, head_w, head_b, head_ch, n_rays, n_samples, raw):
+    """One tri-plane decoder chain with split fp16 operands (three tcgen05 passes per layer: fp32-grade accuracy).
+    feat: fp32 [n_rays*n_samples, k0] ray-major; w_hi / w_lo: lists of 4 fp16 weight images; raw: BLOCKED planar buffer."""
+    lib = _lib.load()
+    k0 = feat.shape[1]
+    P = C.c_void_p * 4
+    wh, wl, bs = P(*[w.data_ptr() for w in w_hi]), P(*[w.data_ptr() for w in w_lo]), P(*[b.data_ptr() for b in biases])
+    rows = n_rays * n_samples
+    with torch.cuda.device(raw.device):
+        fpr = 2 * (k0 * 128 + 3 * 128 * 128 + head_w.shape[0] * 128)
+        st = _call("nvsr_mlp_chain_split", lib.nvsr_mlp_chain_split, _ptr(feat), k0, wh, wl, bs, _ptr(head_w), _ptr(head_b),
+                   head_w.shape[0], head_ch, n_rays, n_samples, _ptr(raw), raw.stride(0), _stream(), rows=rows,
+                   flops_per_row=fpr, flops=rows * fpr, bytes=rows * (4 * k0 + 4 * head_w.shape[0]))
+    _lib.check(st, "nvsr_mlp_chain_split")
     return raw
 
 

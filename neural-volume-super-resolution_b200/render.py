@@ -22,9 +22,13 @@ import torch
 from . import _lib, ops, scene
 from ._lib import NVSR_BF16, NVSR_F16, NVSR_F32
 
-_PRECISION = {"bf16": NVSR_BF16, "fp16": NVSR_F16, "fp32": NVSR_F32}
+_PRECISION = {"bf16": NVSR_BF16, "fp16": NVSR_F16, "fp32": NVSR_F32, "fp16-split": NVSR_F16}
 _state = {
     "precision": _PRECISION[os.environ.get("NVSR_PRECISION", "fp16")],
+    # 'fp16-split': fp16 everywhere except the DENSITY chain, which runs on the tensor cores with every operand split
+    # into two fp16 terms (three MMA passes per layer, csrc/mlp_split.cu) on fp32-gathered features: the 16-bit modes'
+    # map error is sigma's (the colour logits are 3e-5 off), so this mode meets the 1e-3 contract on tcgen05
+    "split_density": os.environ.get("NVSR_PRECISION", "fp16") == "fp16-split",
     # rays per chunk of the frame loop.  The reference chunks for memory (131 072 points per network call,
     # train_utils.py:228-234); here a chunk only bounds the temporaries (384 B of features per sample row),
     # and 180 GB of HBM take half a frame at once: fewer, longer launches (measured -2.8 % per frame against
@@ -45,12 +49,17 @@ _state = {
 def set_precision(name):
     """'bf16' / 'fp16': tcgen05 decoder with 16-bit planes/features/weights/activations and fp32
     accumulation (same tensor-core rate; fp16 rounds 8x finer, bf16 has fp32's range);
-    'fp32': SIMT fp32 everywhere — the 1e-3 parity contract."""
+    'fp32': SIMT fp32 everywhere — the 1e-3 parity contract;
+    'fp16-split': the fp16 mode with the density chain on split operands (tcgen05, three passes per layer, fp32
+    features): meets the 1e-3 contract at tensor-core speed (tri-plane model; the mip model runs plain fp16)."""
     _state["precision"] = _PRECISION[name]
+    _state["split_density"] = name == "fp16-split"
 
 
 def get_precision():
-    return {v: k for k, v in _PRECISION.items()}[_state["precision"]]
+    if _state["split_density"]:
+        return "fp16-split"
+    return {NVSR_BF16: "bf16", NVSR_F16: "fp16", NVSR_F32: "fp32"}[_state["precision"]]
 
 
 def set_ray_chunk(n):
@@ -97,11 +106,12 @@ def _planes_pass(model, scene_id, precision):
     sig = tuple((id(t),) + scene._Cache.key_of(t) for t in srcs) + _params_sig(model) + \
         (getattr(model, "proj_combination", "avg"),)
     per_key = _pass_cache.get(model, sig, dict)
-    key = (scene_id, precision)
+    split = _state["split_density"] and precision == NVSR_F16
+    key = (scene_id, precision, split)
     hit = per_key.get(key)
     # the source planes are held weakly: a recycled id()/data_ptr() of a dead tensor must not match
     if hit is None or any(r() is not t for r, t in zip(hit[0], srcs)):
-        hit = ([weakref.ref(t) for t in srcs], _PlanesPass(model, scene_id, precision))
+        hit = ([weakref.ref(t) for t in srcs], _PlanesPass(model, scene_id, precision, split))
         per_key[key] = hit
     return hit[1]
 
@@ -116,13 +126,17 @@ def _mip_pass(model, precision):
 class _PlanesPass:
     """Everything one (model, scene) pair needs on the device, packed once and cached."""
 
-    def __init__(self, model, scene_id, precision):
+    def __init__(self, model, scene_id, precision, split=False):
         scene.check_supported_planes_model(model)
         self.precision = precision
         self.layout = ops.FEAT_LAYOUT[precision]
         self.rows = ops.LAYOUT_ROWS[self.layout]
         self.planes = scene.pack_scene_planes(model, scene_id, precision)
         self.dec = scene.pack_planes_decoder(model, precision)
+        self.split = None
+        if split:   # 'fp16-split': fp32 planes for the density features + split weights of the density chain
+            self.planes32 = scene.pack_scene_planes(model, scene_id, NVSR_F32)
+            self.split = self.dec.density_split(model)
 
     # The sparse colour path pays while few samples are lit (15 % on the bench scene); on a volume that is dense
     # almost everywhere the second gather would cost more than the skipped rgb rows save.  The lit fraction of the
@@ -161,7 +175,11 @@ class _PlanesPass:
                                       t_rand=t_rand, lindisp=lindisp, density_only=sparse)
         rbias = ops.row_bias(vfeat, self.dec.view_w, self.dec.view_b)
         raw = ops.raw_buffer(n, S, self.rows, ro.device)
-        ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n, self.rows)
+        if self.split is not None:
+            _, fm32, _ = ops.sample_gather(ro, rd, near, far, self.planes32, ops.FEAT_ROWMAJOR_F32, z_in=z, density_only=True)
+            ops.mlp_chain_split(fm32, *self.split, 3, n, S, raw)
+        else:
+            ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n, self.rows)
         if sparse:
             keep, count = ops.keep_rows(raw, n, S, noise)
             fp = ops.sample_gather_rows(ro, rd, self.planes, self.layout, z, keep, count)
@@ -185,7 +203,7 @@ def _render_planes_chunk(pc, pf, ro, rd, vd, near, far, cfg, randoms, trace, coa
     noise_c = _noise(randoms.get("noise_c"), cfg, n, Nc, dev)
     sparse_on = _state["sparse_rgb"] and pc.precision != NVSR_F32
     if (_state["one_call"] and trace is None and not coarse_only and not sparse_on and "z_fine" not in randoms
-            and ops.PROFILE is None and (Nf == 0 or pf is not None)):
+            and ops.PROFILE is None and (Nf == 0 or pf is not None) and pc.split is None):
         u = None
         if Nf > 0:
             u = randoms.get("u")

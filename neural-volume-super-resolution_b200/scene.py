@@ -551,6 +551,22 @@ class PackedPlanesDecoder:
                                            head_w=f(fr.weight) if last else None,
                                            head_b=f(fr.bias) if last else None, head_ch=0))
 
+    def density_split(self, model):
+        """(w_hi, w_lo, biases, head_w, head_b) of the density chain for nvsr_mlp_chain_split: W = fp16(W) + fp16(W - fp16(W))"""
+        if not hasattr(self, "_split"):
+            dd, fa = list(model.density_dec["0"]), model.fc_alpha["0"]
+            if len(dd) != 4 or any(l.out_features != 128 for l in dd):
+                raise NotImplementedError("nvsr_b200: the 'fp16-split' mode serves the 4 x 128 density chain")
+            w_hi, w_lo = [], []
+            for lin in dd:
+                w = lin.weight.detach().float()
+                hi = w.half().float()
+                w_hi.append(ops.pack_weight16(hi, dtype=NVSR_F16))
+                w_lo.append(ops.pack_weight16(w - hi, dtype=NVSR_F16))
+            f = lambda t: t.detach().float().contiguous()
+            self._split = (w_hi, w_lo, [f(l.bias) for l in dd], f(fa.weight), f(fa.bias))
+        return self._split
+
     def rgb_chain(self, row_bias):
         first = self.rgb[0]
         l0 = ops.ChainLayer(first.w, None, first.k, first.n_out, True, row_bias=row_bias,

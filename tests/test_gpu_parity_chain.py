@@ -20,7 +20,7 @@ from test_oracle_golden import E2E
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-PRECISIONS = ("fp32", "fp16", "bf16")
+PRECISIONS = ("fp32", "fp16", "bf16", "fp16-split")
 # more rays than the dumps used while the gate was developed: the oracle renders 1 000 rays of config 2 per second
 RAYS = {"big": 3072, "cfg1": None, "cfg4": 512, "mipbig": 2048}
 
@@ -61,6 +61,8 @@ def full_case(request):
 @pytest.mark.parametrize("prec", PRECISIONS)
 def test_baseline_config_chain(full_case, prec):
     """BASELINE configs at their own sampling density: every link of the chain in every precision mode."""
+    if prec == "fp16-split" and full_case.get("kind") == "mip":
+        pytest.skip("'fp16-split' splits the tri-plane density chain; the mip model runs plain fp16 in that mode")
     out, tr = _render(full_case, prec)
     rep = PA.check_chain(full_case, prec, out, tr)
     _report(full_case["name"], prec, rep)
@@ -89,6 +91,8 @@ def test_golden_chain(name, prec):
     """Every reference-generated golden scene — including the mip/IPE model on the tcgen05 generic chain — through the
     same gate, in every precision mode."""
     c = golden_case(name, DEV)
+    if prec == "fp16-split" and c.get("kind") == "mip":
+        pytest.skip("'fp16-split' splits the tri-plane density chain; the mip model runs plain fp16 in that mode")
     out, tr = _render(c, prec)
     rep = PA.check_chain(c, prec, out, tr, c["randoms"])
     _report(name, prec, rep)
