@@ -75,43 +75,60 @@ __device__ __forceinline__ void sample_corners(const SamplerArgs& a, const Plane
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32 parity kernel: one thread per (row, 4-channel chunk)
+// fp32 parity kernel: one thread per (row, CPT consecutive 4-channel chunks).  CPT = 4 (C % 16 == 0) computes the row's
+// depth / point / footprints once per 16 channels instead of once per 4 — the per-element arithmetic is the same.
+template <int CPT>
 __global__ void __launch_bounds__(256)
 gather_rowmajor_f32(SamplerArgs a, PlaneArgs p, float* __restrict__ featP, float* __restrict__ featM,
                     float* __restrict__ z_out) {
-  const int chunks = p.C / 4;
+  const int chunks = p.C / (4 * CPT);
   int64_t rows = a.n_rays * a.S;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * chunks) return;
   int64_t row = idx / chunks;
-  int ch = (int)(idx % chunks) * 4;
+  const int ch0 = (int)(idx % chunks) * 4 * CPT;
   int64_t ray = row / a.S;
   int s = (int)(row % a.S);
   float z = sample_depth(a, ray, s);
-  if (z_out && ch == 0) z_out[row] = z;
+  if (z_out && ch0 == 0) z_out[row] = z;
   Bilin b[3];
   sample_corners(a, p, ray, z, b);
-  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 m[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) m[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const float* pl = (const float*)p.plane[d];
     int rw = p.rw[d];
-    const float4 v00 = __ldg(reinterpret_cast<const float4*>(pl + ((int64_t)b[d].y0 * rw + b[d].x0) * p.C + ch));
-    const float4 v01 = __ldg(reinterpret_cast<const float4*>(pl + ((int64_t)b[d].y0 * rw + b[d].x1) * p.C + ch));
-    const float4 v10 = __ldg(reinterpret_cast<const float4*>(pl + ((int64_t)b[d].y1 * rw + b[d].x0) * p.C + ch));
-    const float4 v11 = __ldg(reinterpret_cast<const float4*>(pl + ((int64_t)b[d].y1 * rw + b[d].x1) * p.C + ch));
-    float4 o;
-    // ATen order: nw*w + ne*w + sw*w + se*w, unfused
-    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.x, b[d].w00), __fmul_rn(v01.x, b[d].w01)), __fmul_rn(v10.x, b[d].w10)), __fmul_rn(v11.x, b[d].w11));
-    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.y, b[d].w00), __fmul_rn(v01.y, b[d].w01)), __fmul_rn(v10.y, b[d].w10)), __fmul_rn(v11.y, b[d].w11));
-    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.z, b[d].w00), __fmul_rn(v01.z, b[d].w01)), __fmul_rn(v10.z, b[d].w10)), __fmul_rn(v11.z, b[d].w11));
-    o.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00.w, b[d].w00), __fmul_rn(v01.w, b[d].w01)), __fmul_rn(v10.w, b[d].w10)), __fmul_rn(v11.w, b[d].w11));
-    if (featP) *reinterpret_cast<float4*>(featP + row * (3 * p.C) + d * p.C + ch) = o;
-    m.x = __fadd_rn(m.x, o.x), m.y = __fadd_rn(m.y, o.y), m.z = __fadd_rn(m.z, o.z), m.w = __fadd_rn(m.w, o.w);
+    const float* p00 = pl + ((int64_t)b[d].y0 * rw + b[d].x0) * p.C + ch0;
+    const float* p01 = pl + ((int64_t)b[d].y0 * rw + b[d].x1) * p.C + ch0;
+    const float* p10 = pl + ((int64_t)b[d].y1 * rw + b[d].x0) * p.C + ch0;
+    const float* p11 = pl + ((int64_t)b[d].y1 * rw + b[d].x1) * p.C + ch0;
+    float4 v00[CPT], v01[CPT], v10[CPT], v11[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      v00[c] = __ldg(reinterpret_cast<const float4*>(p00) + c), v01[c] = __ldg(reinterpret_cast<const float4*>(p01) + c);
+      v10[c] = __ldg(reinterpret_cast<const float4*>(p10) + c), v11[c] = __ldg(reinterpret_cast<const float4*>(p11) + c);
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      float4 o;
+      // ATen order: nw*w + ne*w + sw*w + se*w, unfused
+      o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00[c].x, b[d].w00), __fmul_rn(v01[c].x, b[d].w01)), __fmul_rn(v10[c].x, b[d].w10)), __fmul_rn(v11[c].x, b[d].w11));
+      o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00[c].y, b[d].w00), __fmul_rn(v01[c].y, b[d].w01)), __fmul_rn(v10[c].y, b[d].w10)), __fmul_rn(v11[c].y, b[d].w11));
+      o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00[c].z, b[d].w00), __fmul_rn(v01[c].z, b[d].w01)), __fmul_rn(v10[c].z, b[d].w10)), __fmul_rn(v11[c].z, b[d].w11));
+      o.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00[c].w, b[d].w00), __fmul_rn(v01[c].w, b[d].w01)), __fmul_rn(v10[c].w, b[d].w10)), __fmul_rn(v11[c].w, b[d].w11));
+      if (featP) *reinterpret_cast<float4*>(featP + row * (3 * p.C) + d * p.C + ch0 + 4 * c) = o;
+      m[c].x = __fadd_rn(m[c].x, o.x), m[c].y = __fadd_rn(m[c].y, o.y), m[c].z = __fadd_rn(m[c].z, o.z), m[c].w = __fadd_rn(m[c].w, o.w);
+    }
   }
   // combine_pos_planes('avg'): stack(...).mean(0) = sum / 3; 'sum': the sum itself
-  if (!p.combine_sum) m.x = __fdiv_rn(m.x, 3.f), m.y = __fdiv_rn(m.y, 3.f), m.z = __fdiv_rn(m.z, 3.f), m.w = __fdiv_rn(m.w, 3.f);
-  *reinterpret_cast<float4*>(featM + row * p.C + ch) = m;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    if (!p.combine_sum)
+      m[c].x = __fdiv_rn(m[c].x, 3.f), m[c].y = __fdiv_rn(m[c].y, 3.f), m[c].z = __fdiv_rn(m[c].z, 3.f), m[c].w = __fdiv_rn(m[c].w, 3.f);
+    *reinterpret_cast<float4*>(featM + row * p.C + ch0 + 4 * c) = m[c];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,10 +436,14 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
 
   if (feat_layout == NVSR_FEAT_ROWMAJOR_F32) {
     if (pl->dtype != NVSR_F32) return NVSR_ERR_UNSUPPORTED;
-    int64_t total = rows * (p.C / 4);
+    // CPT = 4 (coordinates once per 16 channels) measured SLOWER on B200 (11.8 vs 9.4 ms per mean-only fine-pass launch:
+    // 64-byte strides between the lanes of a store instruction); kept as a template parameter for the record
+    const bool wide = false;
+    int64_t total = rows * (p.C / (wide ? 16 : 4));
     int64_t blocks = ceil_div64(total, 256);
     NVSR_CHECK_ARG(blocks < (int64_t)1 << 31);
-    gather_rowmajor_f32<<<(unsigned)blocks, 256, 0, st>>>(a, p, (float*)feat_p, (float*)feat_m, z_out);
+    if (wide) gather_rowmajor_f32<4><<<(unsigned)blocks, 256, 0, st>>>(a, p, (float*)feat_p, (float*)feat_m, z_out);
+    else gather_rowmajor_f32<1><<<(unsigned)blocks, 256, 0, st>>>(a, p, (float*)feat_p, (float*)feat_m, z_out);
     NVSR_RETURN_LAST_ERROR();
   }
   if (feat_layout == NVSR_FEAT_TILE_BF16 || feat_layout == NVSR_FEAT_TILE_F16) {

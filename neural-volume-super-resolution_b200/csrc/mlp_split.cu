@@ -5,7 +5,7 @@
 // 16-bit mode's map error comes from sigma alone (the colour logits are 3e-5 off, sigma 7e-2), so splitting the density
 // chain (43 % of the decoder FLOPs, x3) brings the maps inside the 1e-3 contract at ~1/30 of the SIMT fp32 mode's cost.
 //
-// One 128-row tile at a time per CTA (one CTA per SM, 8 warps: TMEM lane quadrant x column half):
+// One CTA per SM, two 128-row tiles in flight (8 epilogue warps: TMEM lane quadrant x column half, + 1 issuer warp):
 //   features : fp32 row-major [n_rays * S][k0] (the fp32 gather), split by the threads and stored straight into TMEM
 //              (A_hi / A_lo, the TS-form operand layout) — there is no shared-memory input ring, which is what lets BOTH
 //              weight images of all four layers (221 KB for 48 -> 128 x4) stay resident in shared memory;
@@ -18,8 +18,9 @@ namespace nvsr {
 
 namespace {
 
-constexpr int kSpThreads = 256;
-constexpr uint32_t kSpTmemCols = 256;   // D [0,128) | A_hi [128,192) | A_lo [192,256)
+constexpr int kSpThreads = 288;         // 8 epilogue warps (TMEM lane quadrant x column half) + 1 issuer warp
+constexpr uint32_t kSpTmemCols = 512;   // slot s: D [256 s, +128) | A_hi [256 s + 128, +64) | A_lo [256 s + 192, +64)
+constexpr uint32_t kSpSlotCols = 256;
 constexpr uint32_t kSpAhi = 128, kSpAlo = 192;
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -107,21 +108,24 @@ struct SplitArgs {
   int S, tiles_per_blk;
 };
 
+// Two tiles ("slots") are in flight per CTA: while the eight epilogue warps work on one slot's accumulator, the tensor core
+// runs the other slot's 3 x K/16 MMAs.  Warp 8 is the issuer: it waits for the slot's eight "operands written" arrivals,
+// issues the layer's MMAs from one elected lane and commits them to the slot's mbarrier; the epilogue warps wait on that.
+template <int K0C>   // k0 / 16
 __global__ void __launch_bounds__(kSpThreads, 1) chain_split_kernel(const __grid_constant__ SplitArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint64_t bar_w, bar_mma[2], bar_ready[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[4 * 128];
   __shared__ __align__(16) float s_headw[4 * 128];
-  __shared__ __align__(16) float s_hpart[128 * 4];
+  __shared__ __align__(16) float s_hpart[2 * 128 * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = warp & 3, half = warp >> 2;
-  const int r = quad * 32 + lane, col0 = half * 64;
-  const uint32_t w0_bytes = (uint32_t)a.k0 * 256u, wh_bytes = 128u * 256u;
-  const uint32_t w_all = w0_bytes + 3u * wh_bytes;   // one copy (hi or lo) of the four images
+  constexpr uint32_t w0_bytes = (uint32_t)K0C * 16u * 256u, wh_bytes = 128u * 256u;
+  constexpr uint32_t w_all = w0_bytes + 3u * wh_bytes;   // one copy (hi or lo) of the four images
   auto w_off = [&](int l) { return l == 0 ? 0u : w0_bytes + (uint32_t)(l - 1) * wh_bytes; };
   if (threadIdx.x == 0) {
-    mbar_init(&bar_w, 1), mbar_init(&bar_mma, 1);
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&bar_mma[s], 1), mbar_init(&bar_ready[s], 8);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -136,121 +140,175 @@ __global__ void __launch_bounds__(kSpThreads, 1) chain_split_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bar_w, 2u * w_all);
-    for (int l = 0; l < 4; ++l) {
-      const uint32_t nb = l == 0 ? w0_bytes : wh_bytes;
-      bulk_g2s(smem + w_off(l), a.w_hi[l], nb, &bar_w);
-      bulk_g2s(smem + w_all + w_off(l), a.w_lo[l], nb, &bar_w);
-    }
-  }
-  const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
-  const uint32_t d_tmem = lane_base + (uint32_t)col0;                   // this thread's 64 accumulator columns
-  const uint32_t ahi_tmem = lane_base + kSpAhi, alo_tmem = lane_base + kSpAlo;
-  uint32_t ph = 0;
-  bool w_ready = false;
+  // tiles of this CTA: blockIdx.x + j * gridDim.x; slot = j & 1
+  const int64_t my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  auto prestore_bias = [&](int l) {
-    uint32_t v[32];
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + l * 128 + col0 + 32 * g + 4 * j);
-        v[4 * j] = __float_as_uint(b4.x), v[4 * j + 1] = __float_as_uint(b4.y);
-        v[4 * j + 2] = __float_as_uint(b4.z), v[4 * j + 3] = __float_as_uint(b4.w);
+  if (warp == 8) {
+    // ================= issuer =================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_arrive_expect_tx(&bar_w, 2u * w_all);
+      for (int l = 0; l < 4; ++l) {
+        const uint32_t nb = l == 0 ? w0_bytes : wh_bytes;
+        bulk_g2s(smem + w_off(l), a.w_hi[l], nb, &bar_w);
+        bulk_g2s(smem + w_all + w_off(l), a.w_lo[l], nb, &bar_w);
       }
-      tmem_st32(d_tmem + 32u * g, v);
     }
-  };
+    if (my_tiles > 0) mbar_wait(&bar_w, 0);
+    const uint32_t idesc = idesc_f16_kmajor(128);
+    uint32_t ph[2] = {0u, 0u};
+    // order of the steps: (pair p, layer l, slot s) for l = 0..3, s = 0..1 — the same order the epilogue warps follow
+    for (int64_t p = 0; 2 * p < my_tiles; ++p) {
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (2 * p + s >= my_tiles) continue;
+          mbar_wait(&bar_ready[s], ph[s]);
+          ph[s] ^= 1u;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d = tmem + (uint32_t)s * kSpSlotCols;
+            const uint64_t bh = smem_desc(smem_u32(smem + w_off(l)), 2048u, 128u);
+            const uint64_t bl = smem_desc(smem_u32(smem + w_all + w_off(l)), 2048u, 128u);
+            if (l == 0) {
+#pragma unroll
+              for (int ks = 0; ks < K0C; ++ks) {   // + 2 K-chunks (2 * 2048 B) per step of 16
+                umma_ts(d, d + kSpAhi + (uint32_t)ks * 8u, bh + (uint64_t)(ks * 256), idesc, 1u);
+                umma_ts(d, d + kSpAlo + (uint32_t)ks * 8u, bh + (uint64_t)(ks * 256), idesc, 1u);
+                umma_ts(d, d + kSpAhi + (uint32_t)ks * 8u, bl + (uint64_t)(ks * 256), idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                umma_ts(d, d + kSpAhi + (uint32_t)ks * 8u, bh + (uint64_t)(ks * 256), idesc, 1u);
+                umma_ts(d, d + kSpAlo + (uint32_t)ks * 8u, bh + (uint64_t)(ks * 256), idesc, 1u);
+                umma_ts(d, d + kSpAhi + (uint32_t)ks * 8u, bl + (uint64_t)(ks * 256), idesc, 1u);
+              }
+            }
+            umma_commit(&bar_mma[s]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane, col0 = half * 64;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t ph[2] = {0u, 0u};
 
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // ---- features -> A_hi (column half 0 warps) / A_lo (half 1 warps); bias of layer 0 -> D ----
-    {
+    auto prestore_bias = [&](uint32_t d_tmem, int l) {
+      uint32_t v[32];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + l * 128 + col0 + 32 * g + 4 * j);
+          v[4 * j] = __float_as_uint(b4.x), v[4 * j + 1] = __float_as_uint(b4.y);
+          v[4 * j + 2] = __float_as_uint(b4.z), v[4 * j + 3] = __float_as_uint(b4.w);
+        }
+        tmem_st32(d_tmem + 32u * g, v);
+      }
+    };
+    auto arrive_ready = [&](int s) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ready[s]);
+    };
+    // features of `tile` -> A_hi (column-half 0 warps) / A_lo (half 1 warps) of slot s, bias of layer 0 -> D_s
+    auto load_tile = [&](int s, int64_t tile) {
+      const uint32_t sb = lane_base + (uint32_t)s * kSpSlotCols;
       const int64_t blk = tile / a.tiles_per_blk;
-      const int s = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
+      const int smp = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
       const int64_t ray = blk * kBlkRays + (r & 7);
-      const bool valid = ray < a.n_rays && s < a.S;
-      const float4* src = reinterpret_cast<const float4*>(a.feat + (valid ? (ray * a.S + s) * (int64_t)a.k0 : 0));
-      for (int c = 0; c < a.k0 / 16; ++c) {   // 16 features = 8 TMEM columns per step
+      const bool valid = ray < a.n_rays && smp < a.S;
+      const float4* src = reinterpret_cast<const float4*>(a.feat + (valid ? (ray * a.S + smp) * (int64_t)(K0C * 16) : 0));
+      float4 f[K0C * 4];
+#pragma unroll
+      for (int j = 0; j < K0C * 4; ++j) f[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < K0C; ++c) {   // 16 features = 8 TMEM columns per step
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 f = valid ? __ldg(src + c * 4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          split2(f.x, f.y, &hi[2 * j], &lo[2 * j]);
-          split2(f.z, f.w, &hi[2 * j + 1], &lo[2 * j + 1]);
+          split2(f[c * 4 + j].x, f[c * 4 + j].y, &hi[2 * j], &lo[2 * j]);
+          split2(f[c * 4 + j].z, f[c * 4 + j].w, &hi[2 * j + 1], &lo[2 * j + 1]);
         }
-        if (half == 0) tmem_st8(ahi_tmem + (uint32_t)(c * 8), hi);
-        else tmem_st8(alo_tmem + (uint32_t)(c * 8), lo);
+        if (half == 0) tmem_st8(sb + kSpAhi + (uint32_t)(c * 8), hi);
+        else tmem_st8(sb + kSpAlo + (uint32_t)(c * 8), lo);
       }
-      prestore_bias(0);
-    }
+      prestore_bias(sb + (uint32_t)col0, 0);
+    };
+
+    // prologue: the first tile of each slot
+    for (int s = 0; s < 2; ++s)
+      if (s < my_tiles) {
+        load_tile(s, blockIdx.x + (int64_t)s * gridDim.x);
+        arrive_ready(s);
+      }
+    for (int64_t p = 0; 2 * p < my_tiles; ++p) {
 #pragma unroll 1
-    for (int l = 0; l < 4; ++l) {
-      tmem_st_wait();
-      tc_fence_before();
-      __syncthreads();   // operands and bias of layer l are in TMEM; the previous accumulator has been read
-      if (warp == 0) {
-        if (!w_ready) mbar_wait(&bar_w, 0);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t idesc = idesc_f16_kmajor(128);
-          const uint64_t bh = smem_desc(smem_u32(smem + w_off(l)), 2048u, 128u);
-          const uint64_t bl = smem_desc(smem_u32(smem + w_all + w_off(l)), 2048u, 128u);
-          const int ksteps = (l == 0 ? a.k0 : 128) >> 4;
-          for (int ks = 0; ks < ksteps; ++ks) {   // + 2 K-chunks (2 * 2048 B) per step of 16
-            umma_ts(tmem, tmem + kSpAhi + (uint32_t)ks * 8u, bh + (uint64_t)(ks * 256), idesc, 1u);
-            umma_ts(tmem, tmem + kSpAlo + (uint32_t)ks * 8u, bh + (uint64_t)(ks * 256), idesc, 1u);
-            umma_ts(tmem, tmem + kSpAhi + (uint32_t)ks * 8u, bl + (uint64_t)(ks * 256), idesc, 1u);
-          }
-          umma_commit(&bar_mma);
-        }
-        __syncwarp();
-      }
-      w_ready = true;
-      mbar_wait(&bar_mma, ph);
-      ph ^= 1;
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld32(d_tmem, v0);
-      tmem_ld32(d_tmem + 32u, v1);
-      tmem_ld_wait();
-      if (l < 3) {
-        uint32_t hi[16], lo[16];
+      for (int l = 0; l < 4; ++l) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          split2(fmaxf(__uint_as_float(v0[2 * j]), 0.f), fmaxf(__uint_as_float(v0[2 * j + 1]), 0.f), &hi[j], &lo[j]);
-        tmem_st16(ahi_tmem + (uint32_t)(col0 >> 1), hi);
-        tmem_st16(alo_tmem + (uint32_t)(col0 >> 1), lo);
+        for (int s = 0; s < 2; ++s) {
+          const int64_t j = 2 * p + s;
+          if (j >= my_tiles) continue;
+          const int64_t tile = blockIdx.x + j * gridDim.x;
+          const uint32_t sb = lane_base + (uint32_t)s * kSpSlotCols;
+          const uint32_t d_tmem = sb + (uint32_t)col0;
+          mbar_wait(&bar_mma[s], ph[s]);
+          ph[s] ^= 1u;
+          tc_fence_after();
+          uint32_t v0[32], v1[32];
+          tmem_ld32(d_tmem, v0);
+          tmem_ld32(d_tmem + 32u, v1);
+          tmem_ld_wait();
+          if (l < 3) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          split2(fmaxf(__uint_as_float(v1[2 * j]), 0.f), fmaxf(__uint_as_float(v1[2 * j + 1]), 0.f), &hi[j], &lo[j]);
-        tmem_st16(ahi_tmem + (uint32_t)(col0 >> 1) + 16u, hi);
-        tmem_st16(alo_tmem + (uint32_t)(col0 >> 1) + 16u, lo);
-        prestore_bias(l + 1);
-      } else {
-        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < 16; ++q)
+              split2(fmaxf(__uint_as_float(v0[2 * q]), 0.f), fmaxf(__uint_as_float(v0[2 * q + 1]), 0.f), &hi[q], &lo[q]);
+            tmem_st16(sb + kSpAhi + (uint32_t)(col0 >> 1), hi);
+            tmem_st16(sb + kSpAlo + (uint32_t)(col0 >> 1), lo);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (h < a.head_n) {
-            float acc = 0.f;
+            for (int q = 0; q < 16; ++q)
+              split2(fmaxf(__uint_as_float(v1[2 * q]), 0.f), fmaxf(__uint_as_float(v1[2 * q + 1]), 0.f), &hi[q], &lo[q]);
+            tmem_st16(sb + kSpAhi + (uint32_t)(col0 >> 1) + 16u, hi);
+            tmem_st16(sb + kSpAlo + (uint32_t)(col0 >> 1) + 16u, lo);
+            prestore_bias(d_tmem, l + 1);
+            arrive_ready(s);
+          } else {
+            float hacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              acc = fmaf(fmaxf(__uint_as_float(v0[c]), 0.f), s_headw[h * 128 + col0 + c], acc);
-              acc = fmaf(fmaxf(__uint_as_float(v1[c]), 0.f), s_headw[h * 128 + col0 + 32 + c], acc);
+            for (int h = 0; h < 4; ++h) {
+              if (h < a.head_n) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  acc = fmaf(fmaxf(__uint_as_float(v0[c]), 0.f), s_headw[h * 128 + col0 + c], acc);
+                  acc = fmaf(fmaxf(__uint_as_float(v1[c]), 0.f), s_headw[h * 128 + col0 + 32 + c], acc);
+                }
+                hacc[h] = acc;
+              }
             }
-            hacc[h] = acc;
+            // the accumulator has been read: hand the slot its next tile first, so its layer-0 MMAs run under the rest
+            if (j + 2 < my_tiles) {
+              load_tile(s, blockIdx.x + (j + 2) * gridDim.x);
+              arrive_ready(s);
+            }
+            float* hp = s_hpart + (s * 128 + r) * 4;
+            if (half == 1) *reinterpret_cast<float4*>(hp) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+            named_bar_sync(1 + s * 4 + quad, 64);   // the two warps sharing this slot and lane quadrant
+            if (half == 0) {
+              const float4 o = *reinterpret_cast<const float4*>(hp);
+              const float hv[4] = {hacc[0] + o.x, hacc[1] + o.y, hacc[2] + o.z, hacc[3] + o.w};
+              for (int h = 0; h < a.head_n; ++h)
+                a.raw[(int64_t)(a.head_ch + h) * a.raw_stride + tile * kTileRows + r] = hv[h] + __ldg(a.head_b + h);
+            }
           }
         }
-        if (half == 1) *reinterpret_cast<float4*>(s_hpart + r * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
-        __syncthreads();
-        if (half == 0) {
-          const float4 o = *reinterpret_cast<const float4*>(s_hpart + r * 4);
-          const float hv[4] = {hacc[0] + o.x, hacc[1] + o.y, hacc[2] + o.z, hacc[3] + o.w};
-          for (int h = 0; h < a.head_n; ++h)
-            a.raw[(int64_t)(a.head_ch + h) * a.raw_stride + tile * kTileRows + r] = hv[h] + __ldg(a.head_b + h);
-        }
-        __syncthreads();   // s_hpart is free again
       }
     }
   }
@@ -272,7 +330,7 @@ extern "C" int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const voi
                                         int32_t head_ch, int64_t n_rays, int32_t n_samples, float* raw, int64_t raw_stride,
                                         void* stream) {
   NVSR_CHECK_ARG(feat && w_hi && w_lo && bias && head_w && head_b && raw && n_rays >= 0 && n_samples > 0);
-  NVSR_CHECK_ARG(k0 >= 16 && (k0 % 16) == 0 && k0 <= 128 && head_n >= 1 && head_n <= 4 && head_ch >= 0 && head_ch + head_n <= 4);
+  NVSR_CHECK_ARG(k0 >= 16 && (k0 % 16) == 0 && k0 <= 64 && head_n >= 1 && head_n <= 4 && head_ch >= 0 && head_ch + head_n <= 4);
   if (n_rays == 0) return NVSR_OK;
   SplitArgs a;
   for (int l = 0; l < 4; ++l) {
@@ -287,10 +345,18 @@ extern "C" int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const voi
   a.n_tiles = ceil_div64(n_rays, kBlkRays) * a.tiles_per_blk;
   NVSR_CHECK_ARG(raw_stride >= a.n_tiles * kTileRows);
   const uint32_t smem_bytes = 2u * ((uint32_t)k0 * 256u + 3u * 128u * 256u);
-  if (smem_bytes + 8192u > 227u * 1024u) return NVSR_ERR_RESOURCE;
-  cudaError_t e = cudaFuncSetAttribute(chain_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (smem_bytes + 9728u > 227u * 1024u) return NVSR_ERR_RESOURCE;   // + the kernel's static shared memory
+  void (*kernel)(SplitArgs) = nullptr;
+  switch (k0 / 16) {
+    case 1: kernel = chain_split_kernel<1>; break;
+    case 2: kernel = chain_split_kernel<2>; break;
+    case 3: kernel = chain_split_kernel<3>; break;
+    case 4: kernel = chain_split_kernel<4>; break;
+    default: return NVSR_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
   const int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
-  chain_split_kernel<<<(unsigned)grid, kSpThreads, smem_bytes, (cudaStream_t)stream>>>(a);
+  kernel<<<(unsigned)grid, kSpThreads, smem_bytes, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();
 }

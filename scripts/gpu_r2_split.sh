@@ -1,8 +1,4 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-echo "=== split parity"; timeout 900 python -m pytest tests/test_gpu_parity_chain.py -m gpu -q --tb=short -k "split" -rA 2>&1 | grep -E "passed|failed|Error|assert|^\{|FAILED|SKIPPED" | cut -c1-900 | tail -30
-echo "=== bench (precision modes)"; timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_split.json 2> gpurun_out/bench_split.err; tail -3 gpurun_out/bench_split.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_split.json').read().strip().splitlines()[-1])
-print(d['ms_per_step'], json.dumps(d['precision_modes'], indent=0)[:1200])
-PY
+echo "=== split parity + fp32 gather users"; timeout 1200 python -m pytest tests/test_gpu_parity_chain.py tests/test_gpu_stages.py tests/test_gpu_e2e.py -m gpu -q --tb=short -k "split or fp32 or planes_forward or gather" 2>&1 | grep -E "passed|failed|Error|assert|FAILED" | cut -c1-300 | tail -12
+bash scripts/gpu_r2_split_bench.sh
