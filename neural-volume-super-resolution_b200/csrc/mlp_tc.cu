@@ -51,6 +51,15 @@ constexpr uint32_t kSlotAOff = 128;
 // Layer l uses K rows 4l .. 4l+2 of the image; pattern l has ones in exactly those K positions.
 constexpr uint32_t kPatCol = 2 * kSlotCols;   // TMEM columns [384, 416): 4 patterns x 8 columns (16 K values each)
 constexpr uint32_t kBiasImgBytes = 2u * 128u * 16u;   // [2 K-chunks][128 n][8] 16-bit
+// rgb chain (3 outputs): the head runs on the tensor core too — one N = 16 MMA group per tile over the 16-bit last
+// activations (A region) against a [128 K][16 N] image of the head weights split hi + lo (rows 0-2 / 3-5), into 16
+// spare TMEM columns per slot; it is issued together with the slot's next layer-0 MMAs and read back (8 columns per row)
+// under them.  This takes ~1 500 of the head epilogue's ~1 850 cycles off the slot's critical path (measured with
+// -DNVSR_TC_TIMING).  The head weights stay exact to 2^-22; the activations enter rounded to 16 bit (colour logits
+// ~1e-4 instead of 3e-5 off).  The density head (sigma carries the mode's whole map error) stays an fp32 dot product over
+// the unrounded activations.
+constexpr uint32_t kHeadCol = kPatCol + 32u;          // TMEM columns [416, 432) slot 0, [432, 448) slot 1
+constexpr uint32_t kHeadImgBytes = 16u * 16u * 16u;   // [16 K-chunks][16 n][8] 16-bit
 
 struct TcLayer {
   const void* w;          // global 16-bit image
@@ -77,7 +86,7 @@ struct TcArgs {
   int rb_layer;           // layer with a per-ray bias (-1: none)
   int rb_staged;          // 1: the producer stages the tile's bias rows in smem (BLOCKED order)
   // smem carve-up (byte offsets from the 1024-aligned base)
-  uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total, bimg_off;
+  uint32_t in_off[2], rb_off[2], bias_off, headw_off, hpart_off, bar_off, w_bytes_total, bimg_off, himg_off;
   // training forward (TRAIN kernels): act[l] = tile images [tile][16][128][8] of layer l's post-ReLU 16-bit output —
   // exactly the values the next layer's MMA reads (the last layer's: the head input rounded to 16 bit)
   uint8_t* act[4];
@@ -88,7 +97,7 @@ struct TcArgs {
 // CTA 0 — [warp][0] wait for the accumulator, [1] epilogue body, [2] arrive (+ MMA issue on the last warp),
 // [3] rest of the step (tile loads, head write-out), [4] layer steps counted, [5] steps in which this warp was the issuer,
 // [6] cycles of those issues.  Read back with nvsr_debug_tc_timing().
-__device__ unsigned long long g_tc_timing[16][8];
+__device__ unsigned long long g_tc_timing[16][4][8];   // [warp][layer & 3][phase]
 #define TC_T(var) const long long var = clock64()
 #else
 #define TC_T(var)
@@ -158,6 +167,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 32 lanes x 16 consecutive 32-bit columns
@@ -375,6 +390,7 @@ template <bool F16, int LC, int HN, int RB0, bool TRAIN = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr bool kFixed = LC > 0;
+  constexpr bool kHeadTC = kFixed && HN == 3;   // rgb chain: head on the tensor core (see kHeadCol)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
@@ -399,8 +415,8 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   if (threadIdx.x == 0) {
     mbar_init(&bars[BAR_W], 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[BAR_IN_FULL + s], kTcEpiWarpsPerSlot);
-      mbar_init(&bars[BAR_RB_FULL + s], kTcEpiWarpsPerSlot);
+      mbar_init(&bars[BAR_IN_FULL + s], rb_staged ? 4 : kTcEpiWarpsPerSlot);   // arrivals per tile: see issue_tile_loads
+      mbar_init(&bars[BAR_RB_FULL + s], 4);
       mbar_init(&bars[BAR_ACC_FULL + s], 1);
       mbar_init(&bars[BAR_DONE + s], kTcEpiWarpsPerSlot);
     }
@@ -409,21 +425,41 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   // biases / head weights -> smem (tiny, read by every epilogue thread for every tile)
-  for (int i = threadIdx.x; i < L * 128; i += kTcThreads) {
-    int l = i >> 7, n = i & 127;
-    const TcLayer& ly = a.layer[l];
-    sbias[i] = (n < ly.n && ly.bias) ? __ldg(ly.bias + n) : 0.f;
+  if constexpr (!kFixed) {
+    for (int i = threadIdx.x; i < L * 128; i += kTcThreads) {
+      int l = i >> 7, n = i & 127;
+      const TcLayer& ly = a.layer[l];
+      sbias[i] = (n < ly.n && ly.bias) ? __ldg(ly.bias + n) : 0.f;
+    }
   }
-  for (int i = threadIdx.x; i < kTcMaxHeadRows * 128; i += kTcThreads) sheadw[i] = 0.f;
-  __syncthreads();
-  for (int l = 0; l < L; ++l) {
-    const TcLayer& ly = a.layer[l];
-    if (ly.head_w) {
-      for (int i = threadIdx.x; i < ly.head_n * ly.n; i += kTcThreads) {
-        int h = i / ly.n, n = i - h * ly.n;
-        sheadw[(ly.head_row + h) * 128 + n] = __ldg(ly.head_w + i);
+  if constexpr (!kHeadTC) {
+    for (int i = threadIdx.x; i < kTcMaxHeadRows * 128; i += kTcThreads) sheadw[i] = 0.f;
+    __syncthreads();
+    for (int l = 0; l < L; ++l) {
+      const TcLayer& ly = a.layer[l];
+      if (ly.head_w) {
+        for (int i = threadIdx.x; i < ly.head_n * ly.n; i += kTcThreads) {
+          int h = i / ly.n, n = i - h * ly.n;
+          sheadw[(ly.head_row + h) * 128 + n] = __ldg(ly.head_w + i);
+        }
       }
     }
+  } else {
+    // head weight image [16 K-chunks][16 n][8]: n = h holds fp16(W_head[h][k]), n = 3 + h the remainder, n >= 6 zero
+    uint32_t* himg32 = reinterpret_cast<uint32_t*>(smem + a.himg_off);
+    for (int i = threadIdx.x; i < (int)(kHeadImgBytes / 4); i += kTcThreads) himg32[i] = 0u;
+    __syncthreads();
+    uint16_t* himg = reinterpret_cast<uint16_t*>(smem + a.himg_off);
+    const TcLayer& lh = a.layer[LC - 1];
+    for (int i = threadIdx.x; i < 3 * 128; i += kTcThreads) {
+      const int h = i >> 7, k = i & 127;
+      const float w = __ldg(lh.head_w + h * 128 + k);
+      const uint32_t hi = pack16x2<F16>(w, 0.f);
+      const uint32_t lo = pack16x2<F16>(w - unpack16x2<F16>(hi).x, 0.f);
+      himg[((k >> 3) * 16 + h) * 8 + (k & 7)] = (uint16_t)(hi & 0xffffu);
+      himg[((k >> 3) * 16 + 3 + h) * 8 + (k & 7)] = (uint16_t)(lo & 0xffffu);
+    }
+    fence_proxy_async_smem();
   }
   if constexpr (kFixed) {
     // bias image: K row 4l + t of column n = term t of layer l's bias[n] (hi, mid, lo); K rows 4l + 3 stay zero
@@ -471,21 +507,33 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 
   // Loads of one tile into slot s: the feature tile image and, when staged, the bias rows of its 8 rays
   // (consecutive rows of row_bias in the BLOCKED order).  Issuing a bulk copy costs its thread well over a
-  // hundred cycles, so the work is spread: lane 0 of EACH of the slot's 8 warps copies one eighth of the
-  // image and one bias row (wi = warp index within the slot); both barriers count 8 arrivals.
+  // hundred cycles, so the work is spread over lane 0 of the slot's 8 warps (wi = warp index within the slot).
   auto issue_tile_loads = [&](int s, int64_t tile, int wi) {
-    const uint32_t piece = a.in_bytes / kTcEpiWarpsPerSlot;  // K * 32 bytes: a multiple of 16
-    mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], piece);
-    bulk_g2s(smem + a.in_off[s] + wi * piece, a.in + tile * (int64_t)a.in_bytes + wi * piece, piece, &bars[BAR_IN_FULL + s]);
-    if (rb_staged) {
+    if (!rb_staged) {
+      const uint32_t piece = a.in_bytes / kTcEpiWarpsPerSlot;  // K * 32 bytes: a multiple of 16
+      mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], piece);
+      bulk_g2s(smem + a.in_off[s] + wi * piece, a.in + tile * (int64_t)a.in_bytes + wi * piece, piece, &bars[BAR_IN_FULL + s]);
+      return;
+    }
+    // staged per-ray bias rows: warps 0-3 copy a quarter of the image each, warps 4-7 two bias rows each — one
+    // arrival and at most two copies per warp (measured: with image piece + bias row on EVERY warp the loads cost each
+    // warp ~1 100 cycles after the layer-0 arrival, more than layer 1's MMAs hide)
+    if (wi < 4) {
+      const uint32_t piece = a.in_bytes / 4;   // K * 64 bytes
+      mbar_arrive_expect_tx(&bars[BAR_IN_FULL + s], piece);
+      bulk_g2s(smem + a.in_off[s] + wi * piece, a.in + tile * (int64_t)a.in_bytes + wi * piece, piece, &bars[BAR_IN_FULL + s]);
+    } else {
       const TcLayer& rl = a.layer[rb_layer];
-      int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays;
-      if (ray0 + wi < a.n_rays) {
-        mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], (uint32_t)(rl.n * 4));
-        float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]);
-        bulk_g2s(dst + wi * kRbPitch, rl.row_bias + (ray0 + wi) * rl.n, (uint32_t)(rl.n * 4), &bars[BAR_RB_FULL + s]);
-      } else {
+      const int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays + 2 * (wi - 4);
+      const uint32_t row_bytes = (uint32_t)(rl.n * 4);
+      const int n_rows = ray0 + 1 < a.n_rays ? 2 : (ray0 < a.n_rays ? 1 : 0);
+      if (n_rows == 0) {
         mbar_arrive(&bars[BAR_RB_FULL + s]);
+      } else {
+        mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], row_bytes * (uint32_t)n_rows);
+        float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]) + 2 * (wi - 4) * kRbPitch;
+        for (int k = 0; k < n_rows; ++k)
+          bulk_g2s(dst + k * kRbPitch, rl.row_bias + (ray0 + k) * rl.n, row_bytes, &bars[BAR_RB_FULL + s]);
       }
     }
   };
@@ -512,13 +560,31 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
     uint32_t ph_acc = 0, ph_rb = 0;
 #ifdef NVSR_TC_TIMING
-    unsigned long long t_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long t_sum[4][8] = {};
+    int t_layer = 0;
 #endif
 
     // MMAs of layer l of the slot's tile number `use` (whole warp; one elected lane issues).
     //   layer 0: A = feature tile in smem (SS form); l > 0: A = activations in TMEM (TS form).
     // Every MMA accumulates onto the bias the epilogue pre-loaded into D_s.
-    auto issue_layer = [&](int l, uint32_t use) {
+    // the rgb head of the tile whose last activations sit in the slot's A region: 8 K steps of an N = 16 MMA
+    auto issue_head_mmas = [&]() {
+      const uint32_t d_head = tmem_base + kHeadCol + 16u * (uint32_t)s;
+      const uint64_t hdesc = umma_desc(smem_u32(smem + a.himg_off), 256u, 128u);   // LBO = 16 n * 16 B, + 2 chunks per K step
+      const uint32_t idesc16 = umma_idesc_16(16, F16);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_ts(d_head, d_base + kSlotAOff + (uint32_t)ks * 8u, hdesc + (uint64_t)(ks * 32), idesc16, ks > 0 ? 1u : 0u);
+    };
+    auto issue_head_only = [&]() {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_head_mmas();
+        umma_commit(bar_acc_full);
+      }
+      __syncwarp();
+    };
+    auto issue_layer = [&](int l, uint32_t use, bool with_head = false) {
       const TcLayer& ly = a.layer[l];
       const int n = kFixed ? 128 : ly.n;
       const uint32_t idesc = umma_idesc_16(n, F16);
@@ -532,6 +598,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       }
       tc_fence_after();
       if (elect_one()) {
+        if constexpr (kHeadTC) {
+          if (with_head) issue_head_mmas();
+        }
         if constexpr (kFixed) {
           // bias as a K step (see kPatCol); a layer whose bias is per ray (RB0, layer 0) keeps the pre-stored
           // accumulator, every other layer starts from a clean accumulator (first MMA overwrites)
@@ -560,7 +629,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     };
     // This warp's TMEM writes for the next accumulation are done: count it; the slot's 8th arrival
     // issues the MMAs of (layer nl, tile number nuse) — no issuer warp, no wake-up hop.
-    auto arrive_then_issue = [&](bool issue_next, int nl, uint32_t nuse) {
+    auto arrive_then_issue = [&](bool issue_next, int nl, uint32_t nuse, bool head = false) {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -591,9 +660,10 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #ifdef NVSR_TC_TIMING
       const long long ti0 = clock64();
 #endif
-      if (last_in && issue_next) issue_layer(nl, nuse);
+      if (last_in && issue_next) issue_layer(nl, nuse, head);
+      else if (last_in && head) issue_head_only();
 #ifdef NVSR_TC_TIMING
-      if (last_in && issue_next) t_sum[5] += 1, t_sum[6] += clock64() - ti0;
+      if (last_in && issue_next) t_sum[t_layer][5] += 1, t_sum[t_layer][6] += clock64() - ti0;
 #endif
     };
 
@@ -619,6 +689,22 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       if (ray >= a.n_rays) ray = a.n_rays - 1;
       *mode = 2;
       return ly.row_bias + ray * ly.n + col0;
+    };
+
+    // tensor-core head read-back of `tile` (kHeadTC): this thread's row, columns hi 0-2 + lo 3-5 of the slot's head block
+    auto write_tc_head = [&](int64_t tile) {
+      uint32_t hv[8];
+      tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + kHeadCol + 16u * (uint32_t)s, hv);
+      tmem_ld_wait();
+      const TcLayer& lh = a.layer[L - 1];
+      int64_t row = tile * kTileRows + r;
+      if (row < rows) {
+        if (a.row_ids) row = __ldg(a.row_ids + row);  // sparse list: write the row the entry stands for
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+          a.raw[(int64_t)(lh.head_ch + h) * a.raw_stride + row] =
+              __uint_as_float(hv[h]) + __uint_as_float(hv[3 + h]) + __ldg(lh.head_b + h);
+      }
     };
 
     // prologue: weights (once per CTA) and the first tile's loads, then D_s <- its layer-0 bias
@@ -692,7 +778,12 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           uint4* act = nullptr;
           if constexpr (TRAIN)
             act = reinterpret_cast<uint4*>(a.act[l] + tile * (int64_t)(kTileRows * 128 * 2)) + (col0 >> 3) * 128 + r;
-          if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, RB0 != 0 && n_next > 0, bsrc, act);
+          if constexpr (kHeadTC) {
+            // layer 0 of a later tile: the previous tile's head (issued with this layer's MMAs) is complete too —
+            // 4 of the slot's warps read it back (8 columns per row: hi 0-2 + lo 3-5) and write the heads out
+            if (l == 0 && use > 0 && half == 0) write_tc_head(tile - 2 * G);
+            epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, last && RB0 != 0 && n_next > 0, bsrc, act);
+          } else if (last) epi_fixed<F16, HN>(d_tmem, a_tmem, hw, hacc, RB0 != 0 && n_next > 0, bsrc, act);
           else epi_fixed<F16, 0>(d_tmem, a_tmem, hw, hacc, false, bsrc, act);
         } else
 #endif
@@ -706,15 +797,18 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
                             bias ? mode : 0, bsrc + c);
           }
         }
+#ifdef NVSR_TC_TIMING
+        t_layer = l & 3;
+#endif
         TC_T(tt2);
-        arrive_then_issue(n_next > 0, nl, last ? use + 1 : use);
+        arrive_then_issue(n_next > 0, nl, last ? use + 1 : use, kHeadTC && last);
         TC_T(tt3);
         // layer 0's MMAs have completed: the slot's ring buffer (and, since all 8 warps finished reading
         // them before those MMAs were issued, its staged bias rows) may take the slot's next tile.  Issued
         // after the arrival: the warp would only be waiting for layer 1's accumulator now.
         if (l == 0 && next_valid && lane == 0) issue_tile_loads(s, next_tile, wi);
 
-        if (head_n > 0) {
+        if (!kHeadTC && head_n > 0) {
           // combine the two column halves of a row: half 1 -> smem -> half 0
           if (half == 1) *reinterpret_cast<float4*>(hp) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
           named_bar_sync(1 + s * 4 + quad, 64);  // the two warps sharing this slot and lane quadrant
@@ -729,13 +823,24 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           }
         }
 #ifdef NVSR_TC_TIMING
-        t_sum[0] += tt1 - tt0, t_sum[1] += tt2 - tt1, t_sum[2] += tt3 - tt2, t_sum[3] += clock64() - tt3, t_sum[4] += 1;
+        t_sum[l & 3][0] += tt1 - tt0, t_sum[l & 3][1] += tt2 - tt1, t_sum[l & 3][2] += tt3 - tt2, t_sum[l & 3][3] += clock64() - tt3, t_sum[l & 3][4] += 1;
 #endif
+      }
+    }
+    if constexpr (kHeadTC) {
+      // drain: the head of the slot's last tile was committed alone
+      if (first < n_tiles) {
+        const int64_t last_tile = first + ((n_tiles - 1 - first) / (2 * G)) * (2 * G);
+        mbar_wait(bar_acc_full, ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after();
+        if (half == 0) write_tc_head(last_tile);
       }
     }
 #ifdef NVSR_TC_TIMING
     if (blockIdx.x == 0 && lane == 0)
-      for (int i = 0; i < 8; ++i) g_tc_timing[warp][i] = t_sum[i];
+      for (int l = 0; l < 4; ++l)
+        for (int i = 0; i < 8; ++i) g_tc_timing[warp][l][i] = t_sum[l][i];
 #endif
   }
 
@@ -799,10 +904,16 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out
     a.rb_off[1] = off + kRbRowsMax * kRbPitch * 4u;
     off += 2u * kRbRowsMax * kRbPitch * 4u;
   }
-  a.bias_off = off, off += (uint32_t)m->n_layers * 128u * 4u;
-  a.bimg_off = off, off += kBiasImgBytes;   // bias image of the fixed chains (16-byte aligned: every size above is a multiple of 16)
-  a.headw_off = off, off += kTcMaxHeadRows * 128u * 4u;
-  a.hpart_off = off, off += 2u * 128u * 4u * 4u;
+  // which specialisation will run (decided below with the same predicates): the fixed chains keep their biases in an
+  // image, the rgb one also its head weights — they do not need the fp32 tables / the half-combining scratch
+  const bool fixed_any = uniform && m->n_layers == 4 && (lastL.head_n == 1 ? a.rb_layer < 0 : (lastL.head_n == 3 && a.rb_layer == 0)) &&
+                         (a.rb_layer < 0 || a.rb_staged || sparse);
+  const bool fixed_rgb = fixed_any && lastL.head_n == 3;
+  a.bias_off = off, off += fixed_any ? 0u : (uint32_t)m->n_layers * 128u * 4u;
+  a.bimg_off = off, off += fixed_any ? kBiasImgBytes : 0u;   // (16-byte aligned: every size above is a multiple of 16)
+  a.himg_off = off, off += fixed_rgb ? kHeadImgBytes : 0u;
+  a.headw_off = off, off += fixed_rgb ? 0u : kTcMaxHeadRows * 128u * 4u;
+  a.hpart_off = off, off += fixed_rgb ? 0u : 2u * 128u * 4u * 4u;
   a.bar_off = off, off += BAR_COUNT * 8u + 16u;  // barriers, then {tmem base, arrival counter x2}
   const uint32_t smem_bytes = off;
   if (smem_bytes > 227u * 1024u) return NVSR_ERR_RESOURCE;
@@ -855,7 +966,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out
 }  // namespace nvsr
 
 #ifdef NVSR_TC_TIMING
-extern "C" int32_t nvsr_debug_tc_timing(unsigned long long* host_out /* [16][8] */) {
-  return (int32_t)cudaMemcpyFromSymbol(host_out, nvsr::g_tc_timing, sizeof(unsigned long long) * 16 * 8);
+extern "C" int32_t nvsr_debug_tc_timing(unsigned long long* host_out /* [16][4][8] */) {
+  return (int32_t)cudaMemcpyFromSymbol(host_out, nvsr::g_tc_timing, sizeof(unsigned long long) * 16 * 4 * 8);
 }
 #endif

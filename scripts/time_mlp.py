@@ -30,15 +30,16 @@ for which in ("density", "rgb"):
     ms = e0.elapsed_time(e1) / int(os.environ.get("REPS", "10"))
     fl = 2 * rows * (55424 if which == "density" else 74112 - 48 * 128)
     print(f"NVSR_DBG={os.environ.get('NVSR_DBG','0'):>3s} {which:8s} {ms:7.3f} ms  {fl/ms/1e9:7.1f} TFLOP/s  cycles/tile {ms*1e-3*1.965e9/(tiles/148):7.0f}")
-    # debug build with -DNVSR_TC_TIMING: per-warp phase cycle sums of CTA 0
+    # debug build with -DNVSR_TC_TIMING: per-warp, per-layer phase cycle sums of CTA 0
     import ctypes as C
     lib = nvsr_b200._lib.load()
     if hasattr(lib, "nvsr_debug_tc_timing"):
-        buf = (C.c_ulonglong * 128)()
+        buf = (C.c_ulonglong * 512)()
         lib.nvsr_debug_tc_timing(buf)
-        print(f"  {which}: per-warp average cycles per layer step (CTA 0): wait_acc / epilogue / arrive(+issue) / rest | issuer share, cycles per issue")
-        for w in range(16):
-            t = [buf[w * 8 + i] for i in range(8)]
-            n_ = max(t[4], 1)
-            print(f"   warp {w:2d} slot {w >> 3} half {(w & 7) >> 2} quad {w & 3}: {t[0] / n_:7.0f} {t[1] / n_:7.0f} {t[2] / n_:7.0f} {t[3] / n_:7.0f} | "
-                  f"{t[5] / n_:5.2f} {t[6] / max(t[5], 1):7.0f}   (steps {t[4]})")
+        print(f"  {which}: average cycles per layer step (CTA 0, mean over the 8 warps of slot 0 half 0 / half 1): wait_acc / epilogue / arrive(+issue) / rest | cycles per issue")
+        for l in range(4):
+            for half in (0, 1):
+                ws = [w for w in range(8) if ((w & 7) >> 2) == half]
+                t = [sum(buf[(w * 4 + l) * 8 + i] for w in ws) for i in range(8)]
+                n_ = max(t[4], 1)
+                print(f"   layer {l} half {half}: {t[0] / n_:7.0f} {t[1] / n_:7.0f} {t[2] / n_:7.0f} {t[3] / n_:7.0f} | sum {sum(t[:4]) / n_:7.0f} | issue {t[6] / max(t[5], 1):7.0f} (x{t[5]})")
