@@ -54,10 +54,12 @@ constexpr uint32_t kBiasImgBytes = 2u * 128u * 16u;   // [2 K-chunks][128 n][8] 
 // rgb chain (3 outputs): the head runs on the tensor core too — one N = 16 MMA group per tile over the 16-bit last
 // activations (A region) against a [128 K][16 N] image of the head weights split hi + lo (rows 0-2 / 3-5), into 16
 // spare TMEM columns per slot; it is issued together with the slot's next layer-0 MMAs and read back (8 columns per row)
-// under them.  This takes ~1 500 of the head epilogue's ~1 850 cycles off the slot's critical path (measured with
-// -DNVSR_TC_TIMING).  The head weights stay exact to 2^-22; the activations enter rounded to 16 bit (colour logits
-// ~1e-4 instead of 3e-5 off).  The density head (sigma carries the mode's whole map error) stays an fp32 dot product over
-// the unrounded activations.
+// under them.  This takes the head dot products, the half-combining through shared memory and its named barrier off the
+// slot's critical path (~1 500 of the head epilogue's ~1 850 cycles, measured with -DNVSR_TC_TIMING): rgb chain 1 065 ->
+// 1 216 TFLOP/s alone.  The head weights stay exact to 2^-22; the activations enter rounded to 16 bit: colour logits
+// 3.9e-5 instead of 3.0e-5 off in fp16.  The DENSITY head stays an fp32 dot product over the unrounded activations: tried
+// on the tensor core as well — sigma error +50-70 % (0.073 -> 0.126 fp16, 0.55 -> 1.05 bf16: sigma's head weights are
+// large) for 2 % of the density chain; rejected.  The generic chain (mip decoder) keeps the fp32 head too.
 constexpr uint32_t kHeadCol = kPatCol + 32u;          // TMEM columns [416, 432) slot 0, [432, 448) slot 1
 constexpr uint32_t kHeadImgBytes = 16u * 16u * 16u;   // [16 K-chunks][16 n][8] 16-bit
 
@@ -451,7 +453,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     __syncthreads();
     uint16_t* himg = reinterpret_cast<uint16_t*>(smem + a.himg_off);
     const TcLayer& lh = a.layer[LC - 1];
-    for (int i = threadIdx.x; i < 3 * 128; i += kTcThreads) {
+    for (int i = threadIdx.x; i < HN * 128; i += kTcThreads) {
       const int h = i >> 7, k = i & 127;
       const float w = __ldg(lh.head_w + h * 128 + k);
       const uint32_t hi = pack16x2<F16>(w, 0.f);
@@ -701,7 +703,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       if (row < rows) {
         if (a.row_ids) row = __ldg(a.row_ids + row);  // sparse list: write the row the entry stands for
 #pragma unroll
-        for (int h = 0; h < 3; ++h)
+        for (int h = 0; h < (HN > 0 ? HN : 1); ++h)
           a.raw[(int64_t)(lh.head_ch + h) * a.raw_stride + row] =
               __uint_as_float(hv[h]) + __uint_as_float(hv[3 + h]) + __ldg(lh.head_b + h);
       }
@@ -908,9 +910,9 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out
   // image, the rgb one also its head weights — they do not need the fp32 tables / the half-combining scratch
   const bool fixed_any = uniform && m->n_layers == 4 && (lastL.head_n == 1 ? a.rb_layer < 0 : (lastL.head_n == 3 && a.rb_layer == 0)) &&
                          (a.rb_layer < 0 || a.rb_staged || sparse);
-  const bool fixed_rgb = fixed_any && lastL.head_n == 3;
   a.bias_off = off, off += fixed_any ? 0u : (uint32_t)m->n_layers * 128u * 4u;
   a.bimg_off = off, off += fixed_any ? kBiasImgBytes : 0u;   // (16-byte aligned: every size above is a multiple of 16)
+  const bool fixed_rgb = fixed_any && lastL.head_n == 3;
   a.himg_off = off, off += fixed_rgb ? kHeadImgBytes : 0u;
   a.headw_off = off, off += fixed_rgb ? 0u : kTcMaxHeadRows * 128u * 4u;
   a.hpart_off = off, off += fixed_rgb ? 0u : 2u * 128u * 4u * 4u;
