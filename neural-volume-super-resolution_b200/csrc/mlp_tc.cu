@@ -60,7 +60,8 @@ constexpr uint32_t kBiasImgBytes = 2u * 128u * 16u;   // [2 K-chunks][128 n][8] 
 // 3.9e-5 instead of 3.0e-5 off in fp16.  The DENSITY head stays an fp32 dot product over the unrounded activations: tried
 // on the tensor core as well — sigma error +50-70 % (0.073 -> 0.126 fp16, 0.55 -> 1.05 bf16: sigma's head weights are
 // large) for 2 % of the density chain; rejected.  The generic chain (mip decoder) keeps the fp32 head too.
-constexpr uint32_t kHeadCol = kPatCol + 32u;          // TMEM columns [416, 432) slot 0, [432, 448) slot 1
+constexpr uint32_t kHeadCol = kPatCol + 32u;          // TMEM columns [416, 432) slot 0, [432, 448) slot 1 (fixed chains;
+                                                      // the generic chains' eight 2-term patterns fill [384, 448))
 constexpr uint32_t kHeadImgBytes = 16u * 16u * 16u;   // [16 K-chunks][16 n][8] 16-bit
 
 struct TcLayer {
@@ -427,13 +428,6 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   // biases / head weights -> smem (tiny, read by every epilogue thread for every tile)
-  if constexpr (!kFixed) {
-    for (int i = threadIdx.x; i < L * 128; i += kTcThreads) {
-      int l = i >> 7, n = i & 127;
-      const TcLayer& ly = a.layer[l];
-      sbias[i] = (n < ly.n && ly.bias) ? __ldg(ly.bias + n) : 0.f;
-    }
-  }
   if constexpr (!kHeadTC) {
     for (int i = threadIdx.x; i < kTcMaxHeadRows * 128; i += kTcThreads) sheadw[i] = 0.f;
     __syncthreads();
@@ -482,11 +476,46 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           make_uint2((uint32_t)term[0] | ((uint32_t)term[1] << 16), (uint32_t)term[2] | ((uint32_t)term[3] << 16));
     }
     fence_proxy_async_smem();
+  } else {
+    // generic chains (up to 8 layers): K rows 2l, 2l + 1 of column n = hi, lo of layer l's bias[n] (exact to 2^-22 in
+    // fp16, 2^-16 in bf16 — far below the operand rounding); a layer with a per-ray bias keeps the pre-stored accumulator
+    uint32_t* bimg32 = reinterpret_cast<uint32_t*>(smem + a.bimg_off);
+    for (int i = threadIdx.x; i < (int)(kBiasImgBytes / 4); i += kTcThreads) bimg32[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * 128; i += kTcThreads) {
+      const int l = i >> 7, n = i & 127;
+      const TcLayer& ly = a.layer[l];
+      const float b = (n < ly.n && ly.bias) ? __ldg(ly.bias + n) : 0.f;
+      const uint32_t hi = pack16x2<F16>(b, 0.f);
+      const uint32_t lo = pack16x2<F16>(b - unpack16x2<F16>(hi).x, 0.f);
+      const int k0 = 2 * l;
+      bimg32[(((k0 >> 3) * 128 + n) * 8 + (k0 & 7)) >> 1] = (hi & 0xffffu) | (lo << 16);
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (!kFixed) {
+    // "ones" patterns of the generic chains: pattern l = columns [kPatCol + 8l, +8), ones at K = 2l, 2l + 1
+    if (warp < 4) {
+      const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t pat[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pat[j] = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pat[8 * q + (4 * g + q)] = one | (one << 16);
+        tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + kPatCol + 32u * g, pat);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if constexpr (kFixed) {
     // "ones" patterns: pattern l = columns [kPatCol + 8l, +8) of every row, ones at K = 4l, 4l+1, 4l+2
     if (warp < 4) {
@@ -618,12 +647,18 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           }
           if (kstep_bias)
             umma_ts(d_base, tmem_base + kPatCol + 8u * (uint32_t)l, umma_desc(smem_u32(smem + a.bimg_off), 2048u, 128u), idesc, 1u);
-        } else if (l == 0) {
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_ss(d_base, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
         } else {
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc, 1u);
+          const bool kstep_bias = l != rb_layer;   // a per-ray bias was pre-stored into the accumulator
+          if (l == 0) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_ss(d_base, adesc0 + (uint64_t)(ks * 256), bdesc0 + (uint64_t)(ks * b_step), idesc, (ks > 0 || !kstep_bias) ? 1u : 0u);
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_ts(d_base, d_base + kSlotAOff + (uint32_t)ks * 8u, bdesc0 + (uint64_t)(ks * b_step), idesc,
+                      (ks > 0 || !kstep_bias) ? 1u : 0u);
+          }
+          if (kstep_bias)
+            umma_ts(d_base, tmem_base + kPatCol + 8u * (uint32_t)l, umma_desc(smem_u32(smem + a.bimg_off), 2048u, 128u), idesc, 1u);
         }
         umma_commit(bar_acc_full);
       }
@@ -725,7 +760,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         mbar_wait(bar_rb_full, ph_rb);
         ph_rb ^= 1;
       }
-      if (!kFixed || RB0 != 0) {
+      if (kFixed ? RB0 != 0 : rb_layer == 0) {
         int mode;
         const float* bsrc = bias_src(0, first, &mode);
         const int n0 = kFixed ? 128 : a.layer[0].n;
@@ -762,7 +797,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         const int n_next = (last && !next_valid) ? 0 : (kFixed ? 128 : a.layer[nl].n);
         const bool nl_rb = n_next > 0 && nl == rb_layer && rb_staged;
         int mode = 0;
-        const float* bsrc = (n_next > 0 && (!kFixed || (RB0 != 0 && last))) ? bias_src(nl, last ? next_tile : tile, &mode) : nullptr;
+        const float* bsrc = (n_next > 0 && (kFixed ? (RB0 != 0 && last) : nl == rb_layer)) ? bias_src(nl, last ? next_tile : tile, &mode) : nullptr;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         if (nl_rb) {
           mbar_wait(bar_rb_full, ph_rb);
@@ -793,7 +828,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
 #pragma unroll
           for (int c = 0; c < 64; c += 32) {
             const bool read = col0 + c < n_cur;
-            const bool bias = col0 + c < n_next;
+            const bool bias = col0 + c < n_next && nl == rb_layer;   // every other bias rides in the MMA
             if (read || bias)
               epi_pass<F16>(d_tmem + (uint32_t)c, a_tmem + (uint32_t)(c >> 1), read, !last, relu, head_n, hw + c, hacc,
                             bias ? mode : 0, bsrc + c);
@@ -910,8 +945,8 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out
   // image, the rgb one also its head weights — they do not need the fp32 tables / the half-combining scratch
   const bool fixed_any = uniform && m->n_layers == 4 && (lastL.head_n == 1 ? a.rb_layer < 0 : (lastL.head_n == 3 && a.rb_layer == 0)) &&
                          (a.rb_layer < 0 || a.rb_staged || sparse);
-  a.bias_off = off, off += fixed_any ? 0u : (uint32_t)m->n_layers * 128u * 4u;
-  a.bimg_off = off, off += fixed_any ? kBiasImgBytes : 0u;   // (16-byte aligned: every size above is a multiple of 16)
+  a.bias_off = off;                                          // (fp32 bias table: no longer used, every bias is in the image)
+  a.bimg_off = off, off += kBiasImgBytes;                    // (16-byte aligned: every size above is a multiple of 16)
   const bool fixed_rgb = fixed_any && lastL.head_n == 3;
   a.himg_off = off, off += fixed_rgb ? kHeadImgBytes : 0u;
   a.headw_off = off, off += fixed_rgb ? 0u : kTcMaxHeadRows * 128u * 4u;
