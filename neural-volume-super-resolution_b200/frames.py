@@ -11,6 +11,7 @@ Frame sink:
   encode_png              (imageio.imwrite in the reference) stdlib-only PNG writer: zlib + crc32
   FrameSink               converts on the device, copies one byte per channel into pinned host buffers on a side stream
                           (double-buffered, no host synchronisation per frame), hands finished frames to a writer
+  AviWriter               (imageio.mimwrite, train_nerf.py:273) stdlib AVI container: uncompressed or MJPEG (Pillow) frames
 There is no CPU path for the conversion: `to_uint8` refuses CPU tensors.
 """
 import struct
@@ -236,3 +237,128 @@ def png_writer(directory, pattern="%d.png"):
             f.write(encode_png(arr))
 
     return write
+
+
+class AviWriter:
+    """Video sink for FrameSink: the reference assembles evaluation frames into a video with `imageio.mimwrite`
+    (train_nerf.py:273; needs ffmpeg, absent here).  This writes an AVI (RIFF) file with the standard library alone:
+    `codec='raw'` stores uncompressed bottom-up BGR frames ('DIB '), `codec='mjpg'` stores one JPEG per frame (needs
+    Pillow for the JPEG encoder; plays in any player).  Frames must arrive in order (FrameSink delivers them so).
+
+        with AviWriter("orbit.avi", fps=30, codec="mjpg") as w:
+            sink = FrameSink(writer=w); ...; sink.flush()
+    """
+
+    def __init__(self, path, fps=30, codec="raw", quality=92):
+        if codec not in ("raw", "mjpg"):
+            raise ValueError("codec must be 'raw' or 'mjpg'")
+        self.path, self.fps, self.codec, self.quality = path, int(fps), codec, int(quality)
+        self._f = open(path, "wb")
+        self._index = []          # (offset relative to 'movi', size)
+        self._shape = None
+        self._next = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _header(self, n_frames, movi_bytes, idx_bytes):
+        h, w = self._shape
+        fourcc = b"MJPG" if self.codec == "mjpg" else b"\x00\x00\x00\x00"
+        handler = b"MJPG" if self.codec == "mjpg" else b"DIB "
+        frame_bytes = max((s for _, s in self._index), default=w * h * 3)
+        avih = struct.pack("<14I", 1000000 // self.fps, frame_bytes * self.fps, 0, 0x10, n_frames, 0, 1, frame_bytes, w, h,
+                           0, 0, 0, 0)
+        strh = struct.pack("<4s4sIHHIIIIIIIIhhhh", b"vids", handler, 0, 0, 0, 0, 1, self.fps, 0, n_frames, frame_bytes,
+                           0xFFFFFFFF, 0, 0, 0, w, h)
+        strf = struct.pack("<IiiHH4sIiiII", 40, w, h, 1, 24, fourcc, w * h * 3, 0, 0, 0, 0)
+        strl = b"LIST" + struct.pack("<I", 4 + 8 + len(strh) + 8 + len(strf)) + b"strl" + \
+            b"strh" + struct.pack("<I", len(strh)) + strh + b"strf" + struct.pack("<I", len(strf)) + strf
+        hdrl = b"LIST" + struct.pack("<I", 4 + 8 + len(avih) + len(strl)) + b"hdrl" + b"avih" + struct.pack("<I", len(avih)) + avih + strl
+        movi_head = b"LIST" + struct.pack("<I", 4 + movi_bytes) + b"movi"
+        riff_size = 4 + len(hdrl) + len(movi_head) + movi_bytes + idx_bytes
+        return b"RIFF" + struct.pack("<I", riff_size) + b"AVI " + hdrl + movi_head
+
+    def __call__(self, index, arr):
+        if index != self._next:
+            raise ValueError(f"AviWriter: frame {index} out of order (expected {self._next})")
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[2] != 3:
+            raise ValueError("AviWriter takes uint8 [H,W,3] frames")
+        if self._shape is None:
+            self._shape = arr.shape[:2]
+            self._hdr_len = len(self._header(0, 0, 0))
+            self._f.write(b"\0" * self._hdr_len)       # patched in close()
+            self._movi = 0
+        elif arr.shape[:2] != self._shape:
+            raise ValueError("AviWriter: frame size changed")
+        if self.codec == "mjpg":
+            import io
+            from PIL import Image
+            buf = io.BytesIO()
+            Image.fromarray(arr).save(buf, format="JPEG", quality=self.quality)
+            data, tag = buf.getvalue(), b"00dc"
+        else:
+            h, w = self._shape
+            pad = (-(w * 3)) % 4
+            rows = arr[::-1, :, ::-1]                    # bottom-up, BGR
+            data = rows.tobytes() if pad == 0 else b"".join(r.tobytes() + b"\0" * pad for r in rows)
+            tag = b"00db"
+        chunk = tag + struct.pack("<I", len(data)) + data + (b"\0" if len(data) & 1 else b"")
+        self._index.append((4 + self._movi, len(data)))
+        self._f.write(chunk)
+        self._movi += len(chunk)
+        self._next += 1
+
+    def close(self):
+        if self._f is None:
+            return
+        if self._shape is not None:
+            tag = b"00dc" if self.codec == "mjpg" else b"00db"
+            idx = b"".join(tag + struct.pack("<III", 0x10, off, size) for off, size in self._index)
+            idx1 = b"idx1" + struct.pack("<I", len(idx)) + idx
+            self._f.write(idx1)
+            self._f.seek(0)
+            head = self._header(len(self._index), self._movi, len(idx1))
+            assert len(head) == self._hdr_len
+            self._f.write(head)
+        self._f.close()
+        self._f = None
+
+
+def read_avi_frames(path):
+    """Minimal reader of AviWriter's files (tests, round trips): -> (fps, list of uint8 [H,W,3] frames)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    assert data[:4] == b"RIFF" and data[8:12] == b"AVI "
+    pos, frames, fps, wh, mjpg = 12, [], None, None, False
+    end = 8 + struct.unpack("<I", data[4:8])[0]
+
+    def walk(p, stop):
+        nonlocal fps, wh, mjpg
+        while p + 8 <= stop:
+            tag, n = data[p:p + 4], struct.unpack("<I", data[p + 4:p + 8])[0]
+            body = data[p + 8:p + 8 + n]
+            if tag == b"LIST":
+                walk(p + 12, p + 8 + n)
+            elif tag == b"avih":
+                fps = round(1e6 / struct.unpack("<I", body[:4])[0])
+                wh = struct.unpack("<II", body[32:40])
+            elif tag == b"strf":
+                mjpg = body[16:20] == b"MJPG"
+            elif tag in (b"00db", b"00dc"):
+                w, h = wh
+                if tag == b"00dc":
+                    import io
+                    from PIL import Image
+                    frames.append(np.asarray(Image.open(io.BytesIO(body)).convert("RGB")))
+                else:
+                    stride = (w * 3 + 3) // 4 * 4
+                    a = np.frombuffer(body, np.uint8).reshape(h, stride)[:, :w * 3].reshape(h, w, 3)
+                    frames.append(a[::-1, :, ::-1].copy())
+            p += 8 + n + (n & 1)
+
+    walk(pos, end)
+    return fps, frames
