@@ -24,6 +24,7 @@ from nvsr_b200 import autograd as A, ops  # noqa: E402
 
 for name, fn in HO.standins(HO.build_hostcheck()).items():
     setattr(ops, name, fn)
+A.set_decoder("fp32")     # the fp32 parity mode of the differentiable path (the tcgen05 decoder has no host stand-in)
 out = {}
 
 
