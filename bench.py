@@ -261,7 +261,8 @@ def run_reference(args, rank, guard):
     if rank != 0:
         return
     # each step = a bounded ray sample of the workload's frame (cfg1: the whole 100x100 frame, it is the CPU-sized config)
-    n_side = None if args.config == "cfg1" else 48
+    # (64 x 64 = 4 096 rays: ~1.7 s per pass on the box's 16 cores, so the driver's 20 + 5 steps end within a minute)
+    n_side = None if args.config == "cfg1" else 64
     r = time_cpu_oracle(n_side=n_side, steps=max(1, args.steps), warmup=min(args.warmup, 1), config=args.config)
     line = {
         "impl": "reference", "metric": r["metric"], "value": r["rays_per_s"],
