@@ -100,7 +100,7 @@ struct TcArgs {
 // CTA 0 — [warp][0] wait for the accumulator, [1] epilogue body, [2] arrive (+ MMA issue on the last warp),
 // [3] rest of the step (tile loads, head write-out), [4] layer steps counted, [5] steps in which this warp was the issuer,
 // [6] cycles of those issues.  Read back with nvsr_debug_tc_timing().
-__device__ unsigned long long g_tc_timing[16][4][8];   // [warp][layer & 3][phase]
+__device__ unsigned long long g_tc_timing[16][8][8];   // [warp][layer & 7][phase]
 #define TC_T(var) const long long var = clock64()
 #else
 #define TC_T(var)
@@ -386,6 +386,77 @@ __device__ __forceinline__ void epi_fixed(uint32_t d_addr, uint32_t a_addr, cons
   }
 }
 
+// Epilogue of one layer of a GENERIC chain for one thread (= one row, this warp's 64 columns; layer widths are multiples
+// of 64, so a warp owns either all 64 or none): the fixed chains' structure — both 32-column accumulator loads issued back
+// to back and waited for once — with the layer's shape as run-time (warp-uniform) flags.  Measured on the mip decoder
+// (-DNVSR_TC_TIMING): the 32-columns-at-a-time version cost ~1 040 cycles per hidden layer against ~220 in the fixed chains.
+template <bool F16>
+__device__ __forceinline__ void epi_pass64(uint32_t d_addr, uint32_t a_addr, bool read, bool pack, bool relu, int head_n,
+                                           const float* hw, float (&hacc)[4], int bias_mode, const float* bsrc) {
+  uint32_t v0[32], v1[32];
+  if (read) {
+    tmem_ld32(d_addr, v0);
+    tmem_ld32(d_addr + 32u, v1);
+    tmem_ld_wait();
+    if (pack) {
+      uint32_t pk[16];
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+        tmem_st16(a_addr, pk);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, true>(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+        tmem_st16(a_addr + 16u, pk);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, false>(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+        tmem_st16(a_addr, pk);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_act<F16, false>(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+        tmem_st16(a_addr + 16u, pk);
+      }
+    }
+    if (head_n > 0) {
+      if (relu) {   // head_dot32 applies the ReLU in place
+        if (head_n == 1) head_dot32<1>(v0, hw, hacc), head_dot32<1>(v1, hw + 32, hacc);
+        else if (head_n == 3) head_dot32<3>(v0, hw, hacc), head_dot32<3>(v1, hw + 32, hacc);
+        else head_dot32<4>(v0, hw, hacc), head_dot32<4>(v1, hw + 32, hacc);   // rows >= head_n of the table are zero
+      } else {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (h < head_n) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              acc = fmaf(__uint_as_float(v0[j]), hw[h * 128 + j], acc);
+              acc = fmaf(__uint_as_float(v1[j]), hw[h * 128 + 32 + j], acc);
+            }
+            hacc[h] += acc;
+          }
+        }
+      }
+    }
+  }
+  if (bias_mode == 1) {
+    load_bias32(bsrc, v0);
+    tmem_st32(d_addr, v0);
+    load_bias32(bsrc + 32, v1);
+    tmem_st32(d_addr + 32u, v1);
+  } else if (bias_mode == 2) {
+    const float4* g = reinterpret_cast<const float4*>(bsrc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = __ldg(g + j), c4 = __ldg(g + 8 + j);
+      v0[4 * j + 0] = __float_as_uint(b4.x), v0[4 * j + 1] = __float_as_uint(b4.y);
+      v0[4 * j + 2] = __float_as_uint(b4.z), v0[4 * j + 3] = __float_as_uint(b4.w);
+      v1[4 * j + 0] = __float_as_uint(c4.x), v1[4 * j + 1] = __float_as_uint(c4.y);
+      v1[4 * j + 2] = __float_as_uint(c4.z), v1[4 * j + 3] = __float_as_uint(c4.w);
+    }
+    tmem_st32(d_addr, v0);
+    tmem_st32(d_addr + 32u, v1);
+  }
+}
+
 // LC > 0: "uniform" chain known at compile time — LC layers, all 128 wide with ReLU, one head of HN
 // rows on the last layer, per-ray bias on layer 0 iff RB0 (staged rows, BLOCKED order).  Both decoders
 // of the tri-plane model are of this shape (LC = 4).  LC == 0: generic chain described at run time.
@@ -591,7 +662,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     const uint64_t adesc0 = umma_desc(smem_u32(smem + a.in_off[s]), 2048u, 128u);
     uint32_t ph_acc = 0, ph_rb = 0;
 #ifdef NVSR_TC_TIMING
-    unsigned long long t_sum[4][8] = {};
+    unsigned long long t_sum[8][8] = {};
     int t_layer = 0;
 #endif
 
@@ -825,17 +896,12 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
         } else
 #endif
         {
-#pragma unroll
-          for (int c = 0; c < 64; c += 32) {
-            const bool read = col0 + c < n_cur;
-            const bool bias = col0 + c < n_next && nl == rb_layer;   // every other bias rides in the MMA
-            if (read || bias)
-              epi_pass<F16>(d_tmem + (uint32_t)c, a_tmem + (uint32_t)(c >> 1), read, !last, relu, head_n, hw + c, hacc,
-                            bias ? mode : 0, bsrc + c);
-          }
+          const bool read = col0 < n_cur;
+          const bool bias = col0 < n_next && nl == rb_layer;   // every other bias rides in the MMA
+          if (read || bias) epi_pass64<F16>(d_tmem, a_tmem, read, !last, relu, head_n, hw, hacc, bias ? mode : 0, bsrc);
         }
 #ifdef NVSR_TC_TIMING
-        t_layer = l & 3;
+        t_layer = l & 7;
 #endif
         TC_T(tt2);
         arrive_then_issue(n_next > 0, nl, last ? use + 1 : use, kHeadTC && last);
@@ -860,7 +926,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
           }
         }
 #ifdef NVSR_TC_TIMING
-        t_sum[l & 3][0] += tt1 - tt0, t_sum[l & 3][1] += tt2 - tt1, t_sum[l & 3][2] += tt3 - tt2, t_sum[l & 3][3] += clock64() - tt3, t_sum[l & 3][4] += 1;
+        t_sum[l & 7][0] += tt1 - tt0, t_sum[l & 7][1] += tt2 - tt1, t_sum[l & 7][2] += tt3 - tt2, t_sum[l & 7][3] += clock64() - tt3, t_sum[l & 7][4] += 1;
 #endif
       }
     }
@@ -876,7 +942,7 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
     }
 #ifdef NVSR_TC_TIMING
     if (blockIdx.x == 0 && lane == 0)
-      for (int l = 0; l < 4; ++l)
+      for (int l = 0; l < 8; ++l)
         for (int i = 0; i < 8; ++i) g_tc_timing[warp][l][i] = t_sum[l][i];
 #endif
   }
@@ -1003,7 +1069,7 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out
 }  // namespace nvsr
 
 #ifdef NVSR_TC_TIMING
-extern "C" int32_t nvsr_debug_tc_timing(unsigned long long* host_out /* [16][4][8] */) {
-  return (int32_t)cudaMemcpyFromSymbol(host_out, nvsr::g_tc_timing, sizeof(unsigned long long) * 16 * 4 * 8);
+extern "C" int32_t nvsr_debug_tc_timing(unsigned long long* host_out /* [16][8][8] */) {
+  return (int32_t)cudaMemcpyFromSymbol(host_out, nvsr::g_tc_timing, sizeof(unsigned long long) * 16 * 8 * 8);
 }
 #endif
