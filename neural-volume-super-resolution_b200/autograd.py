@@ -222,32 +222,38 @@ class PlanesRadianceTC(torch.autograd.Function):
         d_raw = ops.nsc_to_planar_blocked(d_rf, n, S)
         z0 = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
         grads = []
+        needs = ctx.needs_input_grad
+        # decoder frozen (the phase in which only the SR model / the planes train, train_nerf.py:560): no weight gradients
+        want_w = any(needs[4:24])
         # ---- density chain: data gradient, then the weight gradients on the same images
         g, dout, d_fm = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S)
-        dens = []
-        for l in range(4):
-            k = Cc if l == 0 else 128
-            dw, db = z0(128, k), z0(128)
-            ops.mlp_wgrad(g[l], feat_m if l == 0 else acts_d[l - 1], k, inv, dw, db)
-            dens += [dw, db]
-        dwh = z0(128, 16)
-        ops.mlp_wgrad(acts_d[3], dout, 16, inv, dwh)
-        dens += [dwh[:, :1].t().contiguous(), d_rf[..., 3].sum().reshape(1)]
+        dens = [None] * 10
+        if want_w:
+            dens = []
+            for l in range(4):
+                k = Cc if l == 0 else 128
+                dw, db = z0(128, k), z0(128)
+                ops.mlp_wgrad(g[l], feat_m if l == 0 else acts_d[l - 1], k, inv, dw, db)
+                dens += [dw, db]
+            dwh = z0(128, 16)
+            ops.mlp_wgrad(acts_d[3], dout, 16, inv, dwh)
+            dens += [dwh[:, :1].t().contiguous(), d_rf[..., 3].sum().reshape(1)]
         # ---- rgb chain (its first layer's view-feature columns are a per-ray bias in the forward)
         g, dout, d_fp = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S)
-        col = []
-        g0_ray = ops.ray_sum(g[0], n, S, inv)                        # [n, 128]: sum over the ray's samples of g_0
-        for l in range(4):
-            k = C3 if l == 0 else 128
-            dw, db = z0(128, k), z0(128)
-            ops.mlp_wgrad(g[l], feat_p if l == 0 else acts_c[l - 1], k, inv, dw, db)
-            if l == 0:
-                dw = torch.cat([dw, g0_ray.t() @ vfeat], 1)         # [128, 3C + C]
-            col += [dw, db]
-        dwh = z0(128, 16)
-        ops.mlp_wgrad(acts_c[3], dout, 16, inv, dwh)
-        col += [dwh[:, :3].t().contiguous(), d_rf[..., :3].sum((0, 1))]
-        d_v = g0_ray @ cW0.detach()[:, C3:].float()                  # [n, C]
+        col = [None] * 10
+        g0_ray = ops.ray_sum(g[0], n, S, inv) if (want_w or needs[3]) else None    # [n, 128]: per-ray sum of g_0
+        if want_w:
+            col = []
+            for l in range(4):
+                k = C3 if l == 0 else 128
+                dw, db = z0(128, k), z0(128)
+                ops.mlp_wgrad(g[l], feat_p if l == 0 else acts_c[l - 1], k, inv, dw, db)
+                if l == 0:
+                    dw = torch.cat([dw, g0_ray.t() @ vfeat], 1)         # [128, 3C + C]
+                col += [dw, db]
+            dwh = z0(128, 16)
+            ops.mlp_wgrad(acts_c[3], dout, 16, inv, dwh)
+            col += [dwh[:, :3].t().contiguous(), d_rf[..., :3].sum((0, 1))]
         # ---- planes
         acc = [z0(s[-2], s[-1], s[-3]) for s in ctx.shapes[:3]]
         shell = ops.PackedPlanes(acc, NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, None, ctx.geom.view_lo_rng)
@@ -255,12 +261,15 @@ class PlanesRadianceTC(torch.autograd.Function):
             d_fm = d_fm * 3.0
         ops.sample_gather_bwd(ro, rd, z, shell, d_fp, d_fm, acc)
         sv = ctx.shapes[3]
-        vacc = z0(sv[-2], sv[-1], sv[-3])
-        vshell = ops.PackedPlanes([vacc, vacc, vacc], NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, vacc,
-                                  ctx.geom.view_lo_rng)
-        ops.viewdir_gather_bwd(vd, vshell, d_v, vacc)
-        pg = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc + [vacc], ctx.shapes)]
-        needs = ctx.needs_input_grad
+        vgrad = None
+        if needs[3]:
+            d_v = g0_ray @ cW0.detach()[:, C3:].float()                  # [n, C]
+            vacc = z0(sv[-2], sv[-1], sv[-3])
+            vshell = ops.PackedPlanes([vacc, vacc, vacc], NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, vacc,
+                                      ctx.geom.view_lo_rng)
+            ops.viewdir_gather_bwd(vd, vshell, d_v, vacc)
+            vgrad = vacc.permute(2, 0, 1).reshape(sv)
+        pg = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc, ctx.shapes[:3])] + [vgrad]
         out = pg + dens + col + [None] * 5
         return tuple(o if (o is None or needs[i]) else None for i, o in enumerate(out))
 

@@ -286,3 +286,32 @@ def test_training_with_tc_decoder_tracks_fp32_mode():
     print({k: (v if not isinstance(v, dict) else {a: b for a, b in v.items() if a != "curve"}) for k, v in r.items()})
     assert r["tc"]["last"] < 0.8 * r["tc"]["first"] and r["fp32"]["last"] < 0.8 * r["fp32"]["first"]
     assert 0.85 <= r["last_loss_ratio_tc_over_fp32"] <= 1.15, r["last_loss_ratio_tc_over_fp32"]
+
+
+def test_frozen_decoder_step_gives_the_same_plane_gradients():
+    """The phase in which only planes / the SR model train (decoder frozen, train_nerf.py:560): PlanesRadianceTC skips the
+    weight-gradient kernels; the plane gradients are the ones of the unfrozen step, bit for bit."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=48, view_res=12, seed=5, device=DEV)
+    for m in (mc, mf):
+        m.train()
+    Hh = Ww = 24
+    pose, focal = scene.blender_camera(Hh)
+    opt, scfg = scene.render_options(32, 32, perturb=True), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(Hh, Ww, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    n = batch.shape[1]
+    g = torch.Generator().manual_seed(1)
+    rnd = dict(t_rand=torch.rand(n, 32, generator=g), u=torch.rand(n, 32, generator=g))
+    target = torch.rand(n, 3, generator=g).to(DEV)
+    _, _, g_all = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, Hh, Ww, focal)
+    for m in (mc, mf):
+        for k, p in m.named_parameters():
+            if "planes_" not in k:
+                p.requires_grad_(False)
+    ops.LAUNCHES.clear()
+    _, _, g_frozen = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, Hh, Ww, focal)
+    assert ops.LAUNCHES.get("nvsr_mlp_wgrad", 0) == 0 and ops.LAUNCHES.get("nvsr_mlp_dgrad", 0) == 4
+    assert set(g_frozen) == {k for k in g_all if "planes_" in k}
+    for k in g_frozen:
+        assert torch.equal(g_frozen[k], g_all[k]) or float((g_frozen[k] - g_all[k]).abs().max()) <= 1e-6 * float(g_all[k].abs().max()), k
