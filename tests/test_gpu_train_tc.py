@@ -221,7 +221,8 @@ def _compare(gtc, gref, what):
     return worst
 
 
-def test_train_step_tc_vs_same_rounding_and_fp32_mode(monkeypatch):
+@pytest.mark.parametrize("res,nc,nf", [(32, 64, 128), (19, 24, 40)])
+def test_train_step_tc_vs_same_rounding_and_fp32_mode(monkeypatch, res, nc, nf):
     """One training step (1 024 rays, 64 + 128 samples, perturbation, density noise, white background) with the decoder
     forward + backward on tcgen05, fine depths teacher-forced, against
       (a) the SAME step differentiated by torch autograd through a stock-PyTorch restatement with the same 16-bit
@@ -236,16 +237,16 @@ def test_train_step_tc_vs_same_rounding_and_fp32_mode(monkeypatch):
     mc, mf, sid = scene.make_synthetic_scene(plane_res=64, view_res=16, seed=0, device=DEV)
     for m in (mc, mf):
         m.train()
-    Hh = Ww = 32
+    Hh = Ww = res          # (19 x 19 = 361 rays with 24 + 40 samples: padding rays and padding samples in the tiles)
     pose, focal = scene.blender_camera(Hh)
-    opt, scfg = scene.render_options(64, 128, perturb=True, white_background=True, noise_std=0.2), scene.scene_cfg()
+    opt, scfg = scene.render_options(nc, nf, perturb=True, white_background=True, noise_std=0.2), scene.scene_cfg()
     with torch.no_grad():
         ro, rd = nvsr_b200.get_ray_bundle(Hh, Ww, focal, pose.to(DEV))
     batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
     n = batch.shape[1]
     g = torch.Generator().manual_seed(3)
-    rnd = dict(t_rand=torch.rand(n, 64, generator=g), u=torch.rand(n, 128, generator=g),
-               noise_c=torch.randn(n, 64, generator=g), noise_f=torch.randn(n, 192, generator=g))
+    rnd = dict(t_rand=torch.rand(n, nc, generator=g), u=torch.rand(n, nf, generator=g),
+               noise_c=torch.randn(n, nc, generator=g), noise_f=torch.randn(n, nc + nf, generator=g))
     target = torch.rand(n, 3, generator=g).to(DEV)
     try:
         tr = {}
