@@ -55,8 +55,27 @@ class Geometry:
     def __init__(self, box_lo, box_rng, proj, view_lo_rng, combine="avg"):
         self.box_lo, self.box_rng, self.proj, self.view_lo_rng, self.combine = box_lo, box_rng, proj, view_lo_rng, combine
 
+    _cache = {}
+
     @classmethod
     def of_model(cls, model, scene_id):
+        """Cached per (model, scene, box tensor, its version): reading the box and the projection matrices is a
+        device -> host copy, i.e. a host synchronisation — once per scene, not once per training step."""
+        import weakref
+        box_t = model.box_coords[scene_id]
+        key = (id(model), scene_id)
+        hit = cls._cache.get(key)
+        sig = (box_t.data_ptr(), box_t._version, getattr(model, "proj_combination", "avg"))
+        if hit is not None and hit[0]() is model and hit[1] == sig:
+            return hit[2]
+        geom = cls._build(model, scene_id)
+        if len(cls._cache) > 256:
+            cls._cache.clear()
+        cls._cache[key] = (weakref.ref(model), sig, geom)
+        return geom
+
+    @classmethod
+    def _build(cls, model, scene_id):
         box = model.box_coords[scene_id].detach().double().cpu()
         lo, rng = box[0].float(), (box[1] - box[0]).float()
         rots = model.coord_projector.rot_mats_NON_LEARNED
@@ -156,12 +175,16 @@ class _VolumeRender(torch.autograd.Function):
         return d_rf, None, None, None, None, None
 
 
+# fp16 range of the planes / weights packed by the training forward: checked without a host synchronisation
+_range_check = ops.DeferredRangeCheck()
+
+
 def _packed16(plane_nchw):
     """fp16 x-pair image of a plane (the forward path's gather layout), cached per (tensor, version)"""
     from . import scene
     per = scene._plane_cache.get(plane_nchw, scene._Cache.key_of(plane_nchw), dict)
     if "autograd_f16" not in per:
-        per["autograd_f16"] = ops.pack_plane(plane_nchw, ops.NVSR_F16)
+        per["autograd_f16"] = ops.pack_plane(plane_nchw, ops.NVSR_F16, range_check=_range_check)
     return per["autograd_f16"]
 
 
@@ -188,8 +211,10 @@ class PlanesRadianceTC(torch.autograd.Function):
         vfeat = ops.viewdir_gather(vd, packed)
         rb = ops.row_bias(vfeat, cW[0].detach()[:, C3:], cB[0])
         f = lambda t: t.detach().float().contiguous()
-        wd = [ops.pack_weight16(w, dtype=F16) for w in dW]
-        wc = [ops.pack_weight16(cW[0].detach()[:, :C3], dtype=F16)] + [ops.pack_weight16(w, dtype=F16) for w in cW[1:]]
+        wd = [ops.pack_weight16(w, dtype=F16, range_check=_range_check) for w in dW]
+        wc = [ops.pack_weight16(cW[0].detach()[:, :C3], dtype=F16, range_check=_range_check)] + \
+            [ops.pack_weight16(w, dtype=F16, range_check=_range_check) for w in cW[1:]]
+        _range_check.commit()
         Ld = [ops.ChainLayer(wd[i], f(dB[i]), dW[i].shape[1], 128, True, head_w=f(aW) if i == 3 else None,
                              head_b=f(aB) if i == 3 else None, head_ch=3) for i in range(4)]
         Lc = [ops.ChainLayer(wc[i], None if i == 0 else f(cB[i]), C3 if i == 0 else 128, 128, True,
@@ -220,7 +245,19 @@ class PlanesRadianceTC(torch.autograd.Function):
         scale, inv = ctx.scale, 1.0 / ctx.scale
         d_rf = d_rf.float()
         d_raw = ops.nsc_to_planar_blocked(d_rf, n, S)
-        z0 = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        # every accumulator of the two chains' weight gradients comes out of ONE zero-filled buffer (one memset per pass)
+        pool = torch.zeros((2 * (128 * (Cc + C3 + 6 * 128 + 2 * 16) + 8 * 128),), dtype=torch.float32, device=dev)
+        cursor = [0]
+
+        def z0(*shape):
+            k = 1
+            for d in shape:
+                k *= d
+            if cursor[0] + k > pool.numel():
+                return torch.zeros(shape, dtype=torch.float32, device=dev)
+            v = pool[cursor[0]:cursor[0] + k].view(shape)
+            cursor[0] += (k + 3) // 4 * 4       # keep every view 16-byte aligned
+            return v
         grads = []
         needs = ctx.needs_input_grad
         # decoder frozen (the phase in which only the SR model / the planes train, train_nerf.py:560): no weight gradients

@@ -46,8 +46,34 @@ def raw_to_nsc(raw, n_rays, n_samples, row_order):
     return r[:n_rays, :n_samples]
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """the current stream of the current device as a raw handle.  torch.cuda.current_stream() costs ~20 us of Python
+    per call (device-index bookkeeping); the training step makes ~60 kernel calls, so the raw accessor is used when the
+    build has it."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _OnDevice:
+    """`with _OnDevice(d)` only when d is not already the current device (the guard costs ~10 us per call)."""
+    __slots__ = ("guard",)
+
+    def __init__(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.guard = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
 
 
 def _ptr(t):
@@ -113,7 +139,7 @@ def get_ray_bundle(height, width, focal_length, tform_cam2world, padding_size=0,
     dev = tform_cam2world.device
     ro = torch.empty((r1 - r0, wp, 3), dtype=torch.float32, device=dev)
     rd = torch.empty_like(ro)
-    with torch.cuda.device(dev):
+    with _OnDevice(dev):
         st = _call("nvsr_ray_bundle", lib.nvsr_ray_bundle_dev, height, width, fx, fy, _ptr(c2w), padding_size,
                    float(downsampling_offset), r0, r1, _ptr(ro), _ptr(rd), _stream())
     _lib.check(st, "nvsr_ray_bundle_dev")
@@ -134,7 +160,7 @@ def prepare_rays(ray_origins, ray_directions, use_ndc=False, height=0, width=0, 
     vd = torch.empty_like(rd) if want_viewdirs else None
     if isinstance(focal, (list, tuple)):
         raise _lib.NvsrError("ndc_rays needs a scalar focal (as in the reference)")
-    with torch.cuda.device(ro.device):
+    with _OnDevice(ro.device):
         st = _call("nvsr_prepare_rays", lib.nvsr_prepare_rays, _ptr(ro), _ptr(rd), n, int(bool(use_ndc)), int(height), int(width), float(focal),
                                    float(ndc_near), _ptr(ro_o), _ptr(rd_o), _ptr(vd), _stream())
     _lib.check(st, "nvsr_prepare_rays")
@@ -153,14 +179,60 @@ def _check_f16_range(t, what):
                              "use set_precision('bf16') (fp32 range) or 'fp32' for this scene")
 
 
-def pack_plane(plane_nchw, dtype=NVSR_F32):
+class DeferredRangeCheck:
+    """fp16 range check WITHOUT a host synchronisation, for paths that re-pack every step (training): the maximum of the
+    tensors packed in one step is reduced on the device and copied to pinned memory asynchronously; the NEXT step (or
+    `flush()`) reads it and raises — one step late, but loudly, and the step itself never waits for the GPU."""
+
+    def __init__(self):
+        self.pending = None      # (pinned host tensor, event, description)
+        self.cur = []
+
+    def add(self, t, what):
+        self.cur.append((t.detach().abs().max(), what))
+
+    def commit(self):
+        self.poll()
+        if not self.cur:
+            return
+        m = torch.stack([v.float() for v, _ in self.cur]).max()
+        what = ", ".join(sorted({w for _, w in self.cur}))
+        self.cur = []
+        if self.pending is None:         # at most one check in flight; a step whose check is skipped is covered by the next
+            host = torch.empty((), dtype=torch.float32).pin_memory()
+            host.copy_(m, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.pending = (host, ev, what)
+
+    def poll(self, wait=False):
+        if self.pending is None:
+            return
+        host, ev, what = self.pending
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            self.pending = None
+            if float(host) > F16_MAX:
+                raise _lib.NvsrError(f"{what}: |value| exceeded the fp16 range ({F16_MAX:g}) in the previous step; values "
+                                     "saturated silently - use the fp32 decoder mode for this model")
+
+    def flush(self):
+        self.poll(wait=True)
+
+
+def pack_plane(plane_nchw, dtype=NVSR_F32, range_check=None):
     """[1,C,Rh,Rw] fp32 (models.py:436-439) -> device plane image: fp32 channels-last [Rh,Rw,C], or 16-bit
-    x-pair records [Rh,C/8,Rw,2,8] (nvsr.h: 8-channel chunk of a texel followed by its right neighbour's)."""
+    x-pair records [Rh,C/8,Rw,2,8] (nvsr.h: 8-channel chunk of a texel followed by its right neighbour's).
+    `range_check`: a DeferredRangeCheck to use instead of the synchronous fp16 range check."""
     lib = _lib.load()
     p = _f32c(plane_nchw.detach())
     _require_cuda(p, "plane")
     if dtype == NVSR_F16:
-        _check_f16_range(p, "pack_plane")
+        if range_check is None:
+            _check_f16_range(p, "pack_plane")
+        else:
+            range_check.add(p, "pack_plane")
     if p.dim() == 4:
         assert p.shape[0] == 1
         p = p[0]
@@ -171,27 +243,31 @@ def pack_plane(plane_nchw, dtype=NVSR_F32):
         if c % 8:
             raise ValueError("16-bit planes need a channel count that is a multiple of 8")
         out = torch.empty((rh, c // 8, rw, 2, 8), dtype=TORCH_DTYPE[dtype], device=p.device)
-    with torch.cuda.device(p.device):
+    with _OnDevice(p.device):
         st = _call("nvsr_pack_plane", lib.nvsr_pack_plane, _ptr(p), c, rh, rw, _ptr(out), dtype, _stream())
     _lib.check(st, "nvsr_pack_plane")
     return out
 
 
-def pack_weight16(weight, k_pad=None, dtype=NVSR_BF16):
-    """nn.Linear weight [n_out,k] (may be a column-slice view) -> UMMA image [k_pad/8, n_out, 8] bf16|fp16."""
+def pack_weight16(weight, k_pad=None, dtype=NVSR_BF16, range_check=None):
+    """nn.Linear weight [n_out,k] (may be a column-slice view) -> UMMA image [k_pad/8, n_out, 8] bf16|fp16.
+    `range_check`: a DeferredRangeCheck to use instead of the synchronous fp16 range check."""
     lib = _lib.load()
     w = weight.detach()
     _require_cuda(w, "weight")
     if w.dtype != torch.float32 or w.stride(1) != 1:
         w = w.float().contiguous()
     if dtype == NVSR_F16:
-        _check_f16_range(w, "pack_weight16")
+        if range_check is None:
+            _check_f16_range(w, "pack_weight16")
+        else:
+            range_check.add(w, "pack_weight16")
     n_out, k = w.shape
     ldw = w.stride(0)
     if k_pad is None:
         k_pad = (k + 15) // 16 * 16
     out = torch.empty((k_pad // 8, n_out, 8), dtype=TORCH_DTYPE[dtype], device=w.device)
-    with torch.cuda.device(w.device):
+    with _OnDevice(w.device):
         st = _call("nvsr_pack_weight16", lib.nvsr_pack_weight16, _ptr(w), n_out, k, ldw, k_pad, _ptr(out), dtype, _stream())
     _lib.check(st, "nvsr_pack_weight16")
     return out
@@ -270,7 +346,7 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
     s.t_rand = 0 if t_rand is None else t_rand.data_ptr()
     s.z_in = 0 if z_in is None else z_in.data_ptr()
     pl = packed.cstruct()
-    with torch.cuda.device(ro.device):
+    with _OnDevice(ro.device):
         st = _call("nvsr_sample_gather", lib.nvsr_sample_gather, C.byref(s), C.byref(pl), layout, _ptr(feat_p),
                    _ptr(feat_m), _ptr(z_out), _stream(),
                    # algorithmic HBM bytes: feature write 4C*e per row + z (4 B) + rays (24 B/ray)
@@ -289,7 +365,7 @@ def keep_rows(raw, n_rays, n_samples, noise=None):
     keep = torch.empty((rows,), dtype=torch.int32, device=raw.device)
     count = torch.zeros((1,), dtype=torch.int32, device=raw.device)
     noise = None if noise is None else _f32c(noise)
-    with torch.cuda.device(raw.device):
+    with _OnDevice(raw.device):
         st = _call("nvsr_keep_rows", lib.nvsr_keep_rows, _ptr(raw[3]), _ptr(noise), n_rays, n_samples, _ptr(keep),
                    _ptr(count), _stream(), bytes=rows * 4, rows=rows)
     _lib.check(st, "nvsr_keep_rows")
@@ -310,7 +386,7 @@ def sample_gather_rows(ro, rd, packed, layout, z, keep, count, out=None):
     s.near_, s.far_, s.lindisp = 0.0, 1.0, 0
     s.t_vals, s.t_rand, s.z_in = 0, 0, z.data_ptr()
     pl = packed.cstruct()
-    with torch.cuda.device(ro.device):
+    with _OnDevice(ro.device):
         st = _call("nvsr_sample_gather_rows", lib.nvsr_sample_gather_rows, C.byref(s), C.byref(pl), layout, _ptr(keep),
                    _ptr(count), max_rows, _ptr(out), _stream(), count=count, bytes_per_row=3 * packed.channels * 2)
     _lib.check(st, "nvsr_sample_gather_rows")
@@ -325,7 +401,7 @@ def viewdir_gather(viewdirs, packed):
     vp = packed.vplane
     out = torch.empty((n, vp.shape[-1]), dtype=torch.float32, device=vd.device)
     az_lo, az_rng, el_lo, el_rng = packed.view_lo_rng
-    with torch.cuda.device(vd.device):
+    with _OnDevice(vd.device):
         st = _call("nvsr_viewdir_gather", lib.nvsr_viewdir_gather, _ptr(vd), n, _ptr(vp), vp.shape[0], vp.shape[1], vp.shape[2], az_lo, az_rng,
                                      el_lo, el_rng, _ptr(out), _stream())
     _lib.check(st, "nvsr_viewdir_gather")
@@ -344,7 +420,7 @@ def row_bias(vin, weight_cols, bias):
     assert w.shape[1] == k
     b = None if bias is None else _f32c(bias.detach())
     out = torch.empty((n, n_out), dtype=torch.float32, device=vin.device)
-    with torch.cuda.device(vin.device):
+    with _OnDevice(vin.device):
         st = _call("nvsr_row_bias", lib.nvsr_row_bias, _ptr(vin), n, k, _ptr(w), w.stride(0), _ptr(b), n_out, _ptr(out), _stream())
     _lib.check(st, "nvsr_row_bias")
     return out
@@ -397,7 +473,7 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, ro
     evaluated; `rows` is then the capacity of the input buffer."""
     lib = _lib.load()
     m, fpr, bpr = _mlp_struct(inp, layers, rows, raw, precision, samples_per_ray, n_rays, row_order, row_ids, row_count)
-    with torch.cuda.device(raw.device):
+    with _OnDevice(raw.device):
         # `count` (sparse): rows actually evaluated, on the device
         st = _call("nvsr_mlp_chain", lib.nvsr_mlp_chain, C.byref(m), _stream(), rows=rows, count=row_count,
                    flops_per_row=fpr, bytes_per_row=bpr, flops=rows * fpr, bytes=rows * bpr)
@@ -413,7 +489,7 @@ def mlp_chain_split(feat, w_hi, w_lo, biases, head_w, head_b, head_ch, n_rays, n
     P = C.c_void_p * 4
     wh, wl, bs = P(*[w.data_ptr() for w in w_hi]), P(*[w.data_ptr() for w in w_lo]), P(*[b.data_ptr() for b in biases])
     rows = n_rays * n_samples
-    with torch.cuda.device(raw.device):
+    with _OnDevice(raw.device):
         fpr = 2 * (k0 * 128 + 3 * 128 * 128 + head_w.shape[0] * 128)
         st = _call("nvsr_mlp_chain_split", lib.nvsr_mlp_chain_split, _ptr(feat), k0, wh, wl, bs, _ptr(head_w), _ptr(head_b),
                    head_w.shape[0], head_ch, n_rays, n_samples, _ptr(raw), raw.stride(0), _stream(), rows=rows,
@@ -434,7 +510,7 @@ def mlp_chain_train(inp, layers, rows, raw, samples_per_ray, n_rays):
     tiles = rows // TILE_ROWS
     acts = [torch.empty((tiles, 16, TILE_ROWS, 8), dtype=torch.float16, device=raw.device) for _ in range(4)]
     ptrs = (C.c_void_p * 4)(*[a.data_ptr() for a in acts])
-    with torch.cuda.device(raw.device):
+    with _OnDevice(raw.device):
         st = _call("nvsr_mlp_chain_train", lib.nvsr_mlp_chain_train, C.byref(m), ptrs, _stream(), rows=rows,
                    flops=rows * fpr, bytes=rows * (bpr + 4 * 256))
     _lib.check(st, "nvsr_mlp_chain_train")
@@ -458,7 +534,7 @@ def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples
     a.k0, a.head_w, a.head_n, a.head_ch = k0, head_w.data_ptr(), head_w.shape[0], head_ch
     a.d_raw, a.raw_stride, a.scale = d_raw.data_ptr(), d_raw.stride(0), float(scale)
     a.dout_img, a.d_x0, a.n_rays, a.n_samples = dout.data_ptr(), d_x0.data_ptr(), n_rays, n_samples
-    with torch.cuda.device(dev):
+    with _OnDevice(dev):
         rows = tiles * TILE_ROWS
         st = _call("nvsr_mlp_dgrad", lib.nvsr_mlp_dgrad, C.byref(a), _stream(), rows=rows,
                    flops=rows * 2 * (3 * 128 * 128 + k0 * 128 + head_w.shape[0] * 128), bytes=rows * (8 * 256 + 4 * k0 + 16))
@@ -471,7 +547,7 @@ def mlp_wgrad(a_img, b_img, n_b, inv_scale, dw, db=None):
     lib = _lib.load()
     tiles = a_img.shape[0]
     assert b_img.shape[0] == tiles and dw.dtype == torch.float32 and dw.stride(1) == 1
-    with torch.cuda.device(dw.device):
+    with _OnDevice(dw.device):
         st = _call("nvsr_mlp_wgrad", lib.nvsr_mlp_wgrad, _ptr(a_img), _ptr(b_img), n_b, tiles, float(inv_scale), _ptr(dw),
                    dw.stride(0), _ptr(db), _stream(), rows=tiles * TILE_ROWS, flops=tiles * TILE_ROWS * 2 * 128 * n_b,
                    bytes=tiles * TILE_ROWS * 2 * (128 + n_b))
@@ -483,7 +559,7 @@ def ray_sum(img, n_rays, n_samples, inv_scale=1.0):
     """[n_rays, 128] fp32 = inv_scale * per-ray sum over the samples of a 128-channel tile image (BLOCKED rows)."""
     lib = _lib.load()
     out = torch.empty((n_rays, 128), dtype=torch.float32, device=img.device)
-    with torch.cuda.device(img.device):
+    with _OnDevice(img.device):
         st = _call("nvsr_ray_sum", lib.nvsr_ray_sum, _ptr(img), n_rays, n_samples, float(inv_scale), _ptr(out), _stream())
     _lib.check(st, "nvsr_ray_sum")
     return out
@@ -541,7 +617,7 @@ def composite(raw, z, rd, n_samples, noise=None, white_background=False, mip=Fal
         if want_samples:
             out["z_samples"] = torch.empty((n, n_fine), dtype=torch.float32, device=dev)
             c.z_samples = out["z_samples"].data_ptr()
-    with torch.cuda.device(dev):
+    with _OnDevice(dev):
         st = _call("nvsr_composite", lib.nvsr_composite, C.byref(c), _stream(), rows=n * n_samples,
                    # per sample 16 B raw + 4 B z; per ray 12 B rd + 24 B out; coarse pass: merged depths written
                    bytes=n * n_samples * 20 + n * 36 + (n * (n_samples + n_fine) * 4 if n_fine > 0 else 0))
@@ -641,7 +717,7 @@ def render_rays(ro, rd, viewdirs, near, far, packed_c, dec_c, packed_f, dec_f, p
     evals = n * (n_coarse + ((n_coarse + n_fine) if n_fine > 0 else 0))
     LAUNCHES["nvsr_render_rays(stage launches)"] = LAUNCHES.get("nvsr_render_rays(stage launches)", 0) + \
         (6 if n_fine == 0 else (11 if vp_f is vp_c else 12))
-    with torch.cuda.device(dev):
+    with _OnDevice(dev):
         st = lib.nvsr_render_rays(C.byref(r), _stream())
     _lib.check(st, "nvsr_render_rays")
     return co, fo
@@ -689,7 +765,7 @@ def sample_pdf(bins, weights, num_samples, det=False, u=None, cdf=None, return_a
     inds = torch.empty((n, num_samples), dtype=torch.int64, device=dev)
     samples = torch.empty((n, num_samples), dtype=torch.float32, device=dev)
     cdf_out = torch.empty((n, nb), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _OnDevice(dev):
         st = _call("nvsr_sample_pdf", lib.nvsr_sample_pdf, _ptr(bins), _ptr(w), _ptr(cdf), n, nb, _ptr(u), int(u.dim() == 2), num_samples,
                                  _ptr(inds), _ptr(samples), _ptr(cdf_out), _stream())
     _lib.check(st, "nvsr_sample_pdf")
@@ -713,7 +789,7 @@ def ipe(z_edges, ro, rd, radius, n_freqs, layout=FEAT_ROWMAJOR_F32, k_pad=None):
         k_pad = k_pad or (6 * n_freqs + 15) // 16 * 16
         tiles = (n * S + TILE_ROWS - 1) // TILE_ROWS
         out = torch.empty((tiles, k_pad // 8, TILE_ROWS, 8), dtype=LAYOUT_DTYPE[layout], device=dev)
-    with torch.cuda.device(dev):
+    with _OnDevice(dev):
         st = _call("nvsr_ipe", lib.nvsr_ipe, _ptr(z), _ptr(_f32c(ro)), _ptr(_f32c(rd)), n, S, float(radius), n_freqs, layout, k_pad,
                           _ptr(out), _stream())
     _lib.check(st, "nvsr_ipe")
@@ -742,7 +818,7 @@ def cast_rays(t_vals, origins, directions, radii, ray_shape=None):
         rad = float(radii)
     means = torch.empty((n, S, 3), dtype=torch.float32, device=z.device)
     covs = torch.empty_like(means)
-    with torch.cuda.device(z.device):
+    with _OnDevice(z.device):
         st = _call("nvsr_cast_rays", lib.nvsr_cast_rays, _ptr(z), _ptr(ro), _ptr(rd), _ptr(rad_t), rad, n, S, _ptr(means),
                    _ptr(covs), _stream())
     _lib.check(st, "nvsr_cast_rays")
@@ -758,7 +834,7 @@ def ipe_encode(means, covs, n_freqs):
         raise _lib.NvsrError("ipe_encode: means and covs must both be [..., 3]")
     rows = m.numel() // 3
     out = torch.empty(tuple(m.shape[:-1]) + (6 * n_freqs,), dtype=torch.float32, device=m.device)
-    with torch.cuda.device(m.device):
+    with _OnDevice(m.device):
         st = _call("nvsr_ipe_encode", lib.nvsr_ipe_encode, _ptr(m), _ptr(c), rows, int(n_freqs), _ptr(out), _stream())
     _lib.check(st, "nvsr_ipe_encode")
     return out
@@ -770,7 +846,7 @@ def dir_encoding(dirs, n_freqs, include_input=True):
     d = _f32c(dirs)
     n = d.shape[0]
     out = torch.empty((n, (3 if include_input else 0) + 6 * n_freqs), dtype=torch.float32, device=d.device)
-    with torch.cuda.device(d.device):
+    with _OnDevice(d.device):
         st = _call("nvsr_dir_encoding", lib.nvsr_dir_encoding, _ptr(d), n, n_freqs, int(bool(include_input)), _ptr(out), _stream())
     _lib.check(st, "nvsr_dir_encoding")
     return out
@@ -808,7 +884,7 @@ def sample_gather_bwd(ro, rd, z, packed, d_feat_p, d_feat_m, d_planes=None):
     s.n_rays, s.n_samples = n, S
     s.ro, s.rd, s.z_in = ro.data_ptr(), rd.data_ptr(), z.data_ptr()
     ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in d_planes])
-    with torch.cuda.device(ro.device):
+    with _OnDevice(ro.device):
         st = _call("nvsr_sample_gather_bwd", lib.nvsr_sample_gather_bwd, C.byref(s), C.byref(pl), _ptr(gp), _ptr(gm), ptrs,
                    _stream(), rows=n * S, bytes=n * S * (4 * Cc * 4 + 4))
     _lib.check(st, "nvsr_sample_gather_bwd")
@@ -825,7 +901,7 @@ def viewdir_gather_bwd(viewdirs, packed, d_vfeat, d_vplane=None):
     if d_vplane is None:
         d_vplane = torch.zeros((rh, rw, Cc), dtype=torch.float32, device=vd.device)
     az_lo, az_rng, el_lo, el_rng = packed.view_lo_rng
-    with torch.cuda.device(vd.device):
+    with _OnDevice(vd.device):
         st = _call("nvsr_viewdir_gather_bwd", lib.nvsr_viewdir_gather_bwd, _ptr(vd), n, rh, rw, Cc, az_lo, az_rng, el_lo,
                    el_rng, _ptr(g), _ptr(d_vplane), _stream())
     _lib.check(st, "nvsr_viewdir_gather_bwd")
@@ -844,7 +920,7 @@ def composite_bwd(radiance_field, depth_values, ray_directions, d_rgb, d_acc=Non
         raise _lib.NvsrError("composite_bwd: depth_values must be [N,S] ([N,S+1] interval edges for mip)")
     out = torch.empty_like(rf)
     args = [None if t is None else _f32c(t) for t in (noise, d_rgb, d_acc, d_depth, d_weights)]
-    with torch.cuda.device(rf.device):
+    with _OnDevice(rf.device):
         st = _call("nvsr_composite_bwd", lib.nvsr_composite_bwd, _ptr(rf), _ptr(z), _ptr(rd), _ptr(args[0]), n, S,
                    int(bool(white_background)), int(bool(mip)), _ptr(args[1]), _ptr(args[2]), _ptr(args[3]), _ptr(args[4]),
                    _ptr(out), _stream(), rows=n * S, bytes=n * S * 36 + n * 24)
