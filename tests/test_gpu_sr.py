@@ -47,7 +47,7 @@ def test_sr_plane_is_cached_per_plane_version():
     assert c is not a and not torch.equal(c, a)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16", "fp16-split"])
 def test_render_with_native_sr_vs_oracle(prec):
     """BASELINE config 3a's structure at test size: the fine model reads planes super-resolved by an EDSR-shaped SR
     model (x2, hidden 32, 2 blocks) on the device; the coarse model reads the LR planes.  Whole chain through the
