@@ -100,6 +100,9 @@ int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int
  * [k_pad/8][n_out][8], zero-padded for k <= kk < k_pad.  k_pad % 16 == 0. */
 int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
                            void* dst, int32_t dst_dtype, void* stream);
+/* `count` weights in one call (same arguments as nvsr_pack_weight16, as arrays) */
+int32_t nvsr_pack_weights16(int32_t count, const float* const* w, const int32_t* n_out, const int32_t* k, const int32_t* ldw,
+                            const int32_t* k_pad, void* const* dst, int32_t dst_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a4 + a5  stratified sampler (train_utils.py:95-111) fused with the tri-plane bilinear gather of
@@ -405,6 +408,12 @@ int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* args, void* stream);
 int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t n_b, int64_t n_tiles, float inv_scale, float* dw,
                        int64_t ldw, float* db, void* stream);
 int32_t nvsr_ray_sum(const void* img, int64_t n_rays, int32_t n_samples, float inv_scale, float* out, void* stream);
+/* all five weight gradients of one chain in one call (the host side of a training step is call-bound): layers 0..3
+ * (a = g[l], b = x0_img for l = 0 with k0 channels, else act[l-1]; db[l] bias gradients) and the head (a = act[3],
+ * b = dout_img, dw_head [128][16]).  Same accumulation contract as nvsr_mlp_wgrad. */
+int32_t nvsr_mlp_wgrad_chain(const void* const* g, const void* x0_img, int32_t k0, const void* const* act,
+                             const void* dout_img, int64_t n_tiles, float inv_scale, float* const* dw, const int64_t* ldw,
+                             float* const* db, float* dw_head, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Plane super-resolution, last step: PlanesSR.forward (models.py:884-926) ends with

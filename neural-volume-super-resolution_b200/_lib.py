@@ -205,6 +205,10 @@ SIGNATURES = {
     "nvsr_mlp_dgrad": (c_i32, [C.POINTER(Dgrad), c_p]),
     "nvsr_mlp_wgrad": (c_i32, [c_p, c_p, c_i32, c_i64, c_f, c_p, c_i64, c_p, c_p]),
     "nvsr_ray_sum": (c_i32, [c_p, c_i64, c_i32, c_f, c_p, c_p]),
+    "nvsr_mlp_wgrad_chain": (c_i32, [C.POINTER(c_p), c_p, c_i32, C.POINTER(c_p), c_p, c_i64, c_f, C.POINTER(c_p), C.POINTER(c_i64),
+                                     C.POINTER(c_p), c_p, c_p]),
+    "nvsr_pack_weights16": (c_i32, [c_i32, C.POINTER(c_p), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32),
+                                    C.POINTER(c_p), c_i32, c_p]),
     "nvsr_composite": (c_i32, [C.POINTER(Composite), c_p]),
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),

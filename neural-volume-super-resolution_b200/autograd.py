@@ -211,9 +211,8 @@ class PlanesRadianceTC(torch.autograd.Function):
         vfeat = ops.viewdir_gather(vd, packed)
         rb = ops.row_bias(vfeat, cW[0].detach()[:, C3:], cB[0])
         f = lambda t: t.detach().float().contiguous()
-        wd = [ops.pack_weight16(w, dtype=F16, range_check=_range_check) for w in dW]
-        wc = [ops.pack_weight16(cW[0].detach()[:, :C3], dtype=F16, range_check=_range_check)] + \
-            [ops.pack_weight16(w, dtype=F16, range_check=_range_check) for w in cW[1:]]
+        packed_w = ops.pack_weights16(list(dW) + [cW[0].detach()[:, :C3]] + list(cW[1:]), F16, range_check=_range_check)
+        wd, wc = packed_w[:4], packed_w[4:]
         _range_check.commit()
         Ld = [ops.ChainLayer(wd[i], f(dB[i]), dW[i].shape[1], 128, True, head_w=f(aW) if i == 3 else None,
                              head_b=f(aB) if i == 3 else None, head_ch=3) for i in range(4)]
@@ -266,31 +265,18 @@ class PlanesRadianceTC(torch.autograd.Function):
         g, dout, d_fm = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S)
         dens = [None] * 10
         if want_w:
-            dens = []
-            for l in range(4):
-                k = Cc if l == 0 else 128
-                dw, db = z0(128, k), z0(128)
-                ops.mlp_wgrad(g[l], feat_m if l == 0 else acts_d[l - 1], k, inv, dw, db)
-                dens += [dw, db]
-            dwh = z0(128, 16)
-            ops.mlp_wgrad(acts_d[3], dout, 16, inv, dwh)
-            dens += [dwh[:, :1].t().contiguous(), d_rf[..., 3].sum().reshape(1)]
+            dws, dbs, dwh = [z0(128, Cc if l == 0 else 128) for l in range(4)], [z0(128) for _ in range(4)], z0(128, 16)
+            ops.mlp_wgrad_chain(g, feat_m, Cc, acts_d, dout, inv, dws, dbs, dwh)
+            dens = [t for pair in zip(dws, dbs) for t in pair] + [dwh[:, :1].t().contiguous(), d_rf[..., 3].sum().reshape(1)]
         # ---- rgb chain (its first layer's view-feature columns are a per-ray bias in the forward)
         g, dout, d_fp = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S)
         col = [None] * 10
         g0_ray = ops.ray_sum(g[0], n, S, inv) if (want_w or needs[3]) else None    # [n, 128]: per-ray sum of g_0
         if want_w:
-            col = []
-            for l in range(4):
-                k = C3 if l == 0 else 128
-                dw, db = z0(128, k), z0(128)
-                ops.mlp_wgrad(g[l], feat_p if l == 0 else acts_c[l - 1], k, inv, dw, db)
-                if l == 0:
-                    dw = torch.cat([dw, g0_ray.t() @ vfeat], 1)         # [128, 3C + C]
-                col += [dw, db]
-            dwh = z0(128, 16)
-            ops.mlp_wgrad(acts_c[3], dout, 16, inv, dwh)
-            col += [dwh[:, :3].t().contiguous(), d_rf[..., :3].sum((0, 1))]
+            dws, dbs, dwh = [z0(128, C3 if l == 0 else 128) for l in range(4)], [z0(128) for _ in range(4)], z0(128, 16)
+            ops.mlp_wgrad_chain(g, feat_p, C3, acts_c, dout, inv, dws, dbs, dwh)
+            dws[0] = torch.cat([dws[0], g0_ray.t() @ vfeat], 1)         # [128, 3C + C]
+            col = [t for pair in zip(dws, dbs) for t in pair] + [dwh[:, :3].t().contiguous(), d_rf[..., :3].sum((0, 1))]
         # ---- planes
         acc = [z0(s[-2], s[-1], s[-3]) for s in ctx.shapes[:3]]
         shell = ops.PackedPlanes(acc, NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, None, ctx.geom.view_lo_rng)
@@ -447,7 +433,8 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
     n_dir = (model_coarse.dim_dir - 3) // 6
     if model_coarse.dim_xyz != 6 * n_freqs:
         raise _lib.NvsrError("IPE width does not match the model's dim_xyz")
-    t = torch.linspace(0.0, 1.0, Nc + 1).to(dev)
+    from .render import _t_vals
+    t = _t_vals(Nc + 1, dev)       # cached per (n, device): an upload from pageable memory synchronises the host
     z = near * (1.0 - t) + far * t if not cfg.lindisp else 1.0 / (1.0 / near * (1.0 - t) + 1.0 / far * t)
     z = z.expand(n, Nc + 1)
     if cfg.perturb:
@@ -515,7 +502,8 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
 
     def coarse_depths():
         # stratified depths (train_utils.py:95-109); data, not parameters: no gradient
-        t_vals = torch.linspace(0.0, 1.0, Nc).to(dev)
+        from .render import _t_vals
+        t_vals = _t_vals(Nc, dev)  # cached per (n, device): an upload from pageable memory synchronises the host
         if not cfg.lindisp:
             z = near * (1.0 - t_vals) + far * t_vals
         else:

@@ -372,6 +372,17 @@ extern "C" int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, 
   NVSR_RETURN_LAST_ERROR();
 }
 
+extern "C" int32_t nvsr_pack_weights16(int32_t count, const float* const* w, const int32_t* n_out, const int32_t* k,
+                                       const int32_t* ldw, const int32_t* k_pad, void* const* dst, int32_t dst_dtype,
+                                       void* stream) {
+  NVSR_CHECK_ARG(count >= 0 && (count == 0 || (w && n_out && k && ldw && k_pad && dst)));
+  for (int32_t i = 0; i < count; ++i) {
+    int32_t st = nvsr_pack_weight16(w[i], n_out[i], k[i], ldw[i], k_pad[i], dst[i], dst_dtype, stream);
+    if (st != NVSR_OK) return st;
+  }
+  return NVSR_OK;
+}
+
 extern "C" int32_t nvsr_viewdir_gather(const float* viewdirs, int64_t n_rays, const float* vplane, int32_t rh,
                                        int32_t rw, int32_t channels, float az_lo, float az_rng, float el_lo,
                                        float el_rng, float* vfeat, void* stream) {

@@ -440,6 +440,17 @@ extern "C" int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t 
   NVSR_RETURN_LAST_ERROR();
 }
 
+extern "C" int32_t nvsr_mlp_wgrad_chain(const void* const* g, const void* x0_img, int32_t k0, const void* const* act,
+                                        const void* dout_img, int64_t n_tiles, float inv_scale, float* const* dw,
+                                        const int64_t* ldw, float* const* db, float* dw_head, void* stream) {
+  NVSR_CHECK_ARG(g && x0_img && act && dout_img && dw && ldw && db && dw_head);
+  for (int l = 0; l < 4; ++l) {
+    int32_t st = nvsr_mlp_wgrad(g[l], l == 0 ? x0_img : act[l - 1], l == 0 ? k0 : 128, n_tiles, inv_scale, dw[l], ldw[l], db[l], stream);
+    if (st != NVSR_OK) return st;
+  }
+  return nvsr_mlp_wgrad(act[3], dout_img, 16, n_tiles, inv_scale, dw_head, 16, nullptr, stream);
+}
+
 extern "C" int32_t nvsr_ray_sum(const void* img, int64_t n_rays, int32_t n_samples, float inv_scale, float* out, void* stream) {
   NVSR_CHECK_ARG(img && out && n_rays >= 0 && n_samples > 0);
   if (n_rays == 0) return NVSR_OK;

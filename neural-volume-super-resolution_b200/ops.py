@@ -555,6 +555,47 @@ def mlp_wgrad(a_img, b_img, n_b, inv_scale, dw, db=None):
     return dw
 
 
+def mlp_wgrad_chain(g, x0_img, k0, acts, dout, inv_scale, dws, dbs, dw_head):
+    """the five weight gradients of one chain in ONE C call (nvsr_mlp_wgrad_chain): layers 0..3 into dws[l] [128, k] /
+    dbs[l] [128], the head into dw_head [128, 16]; all accumulated into (zero them first)."""
+    lib = _lib.load()
+    tiles = g[0].shape[0]
+    P = C.c_void_p * 4
+    with _OnDevice(dw_head.device):
+        st = _call("nvsr_mlp_wgrad_chain", lib.nvsr_mlp_wgrad_chain, P(*[t.data_ptr() for t in g]), _ptr(x0_img), k0,
+                   P(*[t.data_ptr() for t in acts]), _ptr(dout), tiles, float(inv_scale), P(*[t.data_ptr() for t in dws]),
+                   (C.c_int64 * 4)(*[t.stride(0) for t in dws]), P(*[t.data_ptr() for t in dbs]), _ptr(dw_head), _stream(),
+                   rows=tiles * TILE_ROWS, flops=tiles * TILE_ROWS * 2 * 128 * (k0 + 3 * 128 + 16),
+                   bytes=tiles * TILE_ROWS * 2 * (9 * 128 + k0 + 16))
+    _lib.check(st, "nvsr_mlp_wgrad_chain")
+
+
+def pack_weights16(weights, dtype=NVSR_F16, range_check=None):
+    """several nn.Linear weights [n_out, k] (column-slice views allowed) -> UMMA images, ONE C call"""
+    lib = _lib.load()
+    ws, outs = [], []
+    for w in weights:
+        w = w.detach()
+        _require_cuda(w, "weight")
+        if w.dtype != torch.float32 or w.stride(1) != 1:
+            w = w.float().contiguous()
+        if dtype == NVSR_F16:
+            if range_check is None:
+                _check_f16_range(w, "pack_weights16")
+            else:
+                range_check.add(w, "pack_weights16")
+        ws.append(w)
+        outs.append(torch.empty(((w.shape[1] + 15) // 16 * 2, w.shape[0], 8), dtype=TORCH_DTYPE[dtype], device=w.device))
+    n = len(ws)
+    I = C.c_int32 * n
+    with _OnDevice(ws[0].device):
+        st = _call("nvsr_pack_weights16", lib.nvsr_pack_weights16, n, (C.c_void_p * n)(*[w.data_ptr() for w in ws]),
+                   I(*[w.shape[0] for w in ws]), I(*[w.shape[1] for w in ws]), I(*[w.stride(0) for w in ws]),
+                   I(*[(w.shape[1] + 15) // 16 * 16 for w in ws]), (C.c_void_p * n)(*[o.data_ptr() for o in outs]), dtype, _stream())
+    _lib.check(st, "nvsr_pack_weights16")
+    return outs
+
+
 def ray_sum(img, n_rays, n_samples, inv_scale=1.0):
     """[n_rays, 128] fp32 = inv_scale * per-ray sum over the samples of a 128-channel tile image (BLOCKED rows)."""
     lib = _lib.load()
