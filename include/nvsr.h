@@ -389,7 +389,7 @@ int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const void* const* w
  * nvsr_ray_sum: out[ray][128] = inv_scale * sum over the ray's samples of a 128-channel image (per-ray bias gradients). */
 typedef struct nvsr_dgrad {
   const void* w[4];      /* forward weight images of layers 0..3 (nvsr_pack_weight16, NVSR_F16) */
-  int32_t k0;            /* input width of layer 0 (multiple of 16, <= 256) */
+  int32_t k0;            /* input width of layer 0 (multiple of 16, <= 192) */
   const float* head_w;   /* [head_n][128] fp32 */
   int32_t head_n, head_ch;
   const float* d_raw;    /* planar [4][raw_stride], BLOCKED rows */

@@ -23,9 +23,10 @@ namespace nvsr {
 
 namespace {
 
-constexpr int kDgThreads = 256;          // 8 warps: quad = warp & 3 (TMEM lane quadrant), half = warp >> 2 (columns)
-constexpr uint32_t kDgTmemCols = 512;    // D: [0, 256), A: [256, 320)
-constexpr uint32_t kDgAOff = 256;
+constexpr int kDgThreads = 288;          // 8 epilogue warps (quad = warp & 3: TMEM lane quadrant, half = warp >> 2: columns) + issuer
+constexpr uint32_t kDgTmemCols = 512;    // slot s: D [256 s, +192) | A [256 s + 192, +64)
+constexpr uint32_t kDgSlotCols = 256;
+constexpr uint32_t kDgAOff = 192;
 constexpr uint32_t kActTileBytes = kTileRows * 128 * 2;
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -134,18 +135,19 @@ __device__ __forceinline__ void emit_delta64(const float (&d)[64], uint32_t a_ad
   for (int j = 0; j < 8; ++j) p[j * 128] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
 }
 
+// Two tiles ("slots") in flight per CTA: 8 epilogue warps (TMEM lane quadrant x column half) + warp 8 as the MMA issuer.
+// While the epilogue warps mask / pack / store one slot's deltas, the tensor core runs the other slot's K loop.
 __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid_constant__ DgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint64_t bar_w, bar_mma[2], bar_ready[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_headw[4 * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = warp & 3, half = warp >> 2;
-  const int r = quad * 32 + lane, col0 = half * 64;
   // smem: W_3 | W_2 | W_1 (32 KB each) | W_0 (k0 * 256 B)
   const uint32_t w_hidden = 128u * 128u * 2u, w0_bytes = (uint32_t)a.k0 * 256u;
   if (threadIdx.x == 0) {
-    mbar_init(&bar_w, 1), mbar_init(&bar_mma, 1);
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&bar_mma[s], 1), mbar_init(&bar_ready[s], 8);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -157,19 +159,55 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (threadIdx.x == 0 && blockIdx.x < a.n_tiles) {
-    mbar_arrive_expect_tx(&bar_w, 3u * w_hidden + w0_bytes);
-    for (int l = 3; l >= 1; --l) bulk_g2s(smem + (3 - l) * w_hidden, a.w[l], w_hidden, &bar_w);
-    bulk_g2s(smem + 3 * w_hidden, a.w[0], w0_bytes, &bar_w);
-  }
-  const uint32_t d_tmem = tmem + ((uint32_t)(quad * 32) << 16);                   // this warp's lanes, column 0 of D
-  const uint32_t a_tmem = d_tmem + kDgAOff + (uint32_t)(col0 >> 1);               // its 32 columns of the A region
-  uint32_t ph = 0;
-  bool w_ready = false;
+  const int64_t my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // ---- g_3 = (d_out . W_head) * [x_4 > 0], on the CUDA cores ----
-    {
+  if (warp == 8) {
+    // ================= issuer =================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_arrive_expect_tx(&bar_w, 3u * w_hidden + w0_bytes);
+      for (int l = 3; l >= 1; --l) bulk_g2s(smem + (3 - l) * w_hidden, a.w[l], w_hidden, &bar_w);
+      bulk_g2s(smem + 3 * w_hidden, a.w[0], w0_bytes, &bar_w);
+    }
+    if (my_tiles > 0) mbar_wait(&bar_w, 0);
+    uint32_t ph[2] = {0u, 0u};
+    for (int64_t p = 0; 2 * p < my_tiles; ++p) {
+#pragma unroll 1
+      for (int l = 3; l >= 0; --l) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (2 * p + s >= my_tiles) continue;
+          mbar_wait(&bar_ready[s], ph[s]);
+          ph[s] ^= 1u;
+          tc_fence_after();
+          if (elect_one()) {
+            // B = forward weight image [k_in/8][128 n_out][8] read MN-major: N = k_in, K = n_out
+            const uint32_t d = tmem + (uint32_t)s * kDgSlotCols;
+            const uint64_t b0 = smem_desc(smem_u32(smem + (3 - l) * w_hidden), 128u, 2048u);
+            const uint32_t idesc = idesc_f16(l > 0 ? 128 : a.k0, false, true);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_ts(d, d + kDgAOff + (uint32_t)ks * 8u, b0 + (uint64_t)(ks * 16), idesc, ks ? 1u : 0u);
+            umma_commit(&bar_mma[s]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane, col0 = half * 64;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t ph[2] = {0u, 0u};
+    auto arrive_ready = [&](int s) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ready[s]);
+    };
+    // g_3 = (d_out . W_head) * [x_4 > 0] of `tile` on the CUDA cores -> slot s's A region + the g[3] / d_out images
+    auto prep_tile = [&](int s, int64_t tile) {
+      const uint32_t a_tmem = lane_base + (uint32_t)s * kDgSlotCols + kDgAOff + (uint32_t)(col0 >> 1);
       float dv[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h)
@@ -186,80 +224,79 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
       }
       emit_delta64(d, a_tmem, a.g[3] + tile * (int64_t)kActTileBytes, col0, r);
       if (half == 0) {   // the head gradient as a 16-column image (the head weight gradient's B operand)
-        uint4* p = reinterpret_cast<uint4*>(a.dout_img + tile * (int64_t)(2 * kTileRows * 16)) + r;
-        p[0] = make_uint4(pack16x2<true>(dv[0], dv[1]), pack16x2<true>(dv[2], dv[3]), 0u, 0u);
-        p[128] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* pimg = reinterpret_cast<uint4*>(a.dout_img + tile * (int64_t)(2 * kTileRows * 16)) + r;
+        pimg[0] = make_uint4(pack16x2<true>(dv[0], dv[1]), pack16x2<true>(dv[2], dv[3]), 0u, 0u);
+        pimg[128] = make_uint4(0u, 0u, 0u, 0u);
       }
-    }
-    // ---- g_{l-1} = (g_l . W_l) * [x_l > 0] for l = 3, 2, 1; then d_x0 = g_0 . W_0 ----
+    };
+
+    for (int s = 0; s < 2; ++s)
+      if (s < my_tiles) {
+        prep_tile(s, blockIdx.x + (int64_t)s * gridDim.x);
+        arrive_ready(s);
+      }
+    for (int64_t p = 0; 2 * p < my_tiles; ++p) {
 #pragma unroll 1
-    for (int l = 3; l >= 0; --l) {
-      const int n = l > 0 ? 128 : a.k0;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncthreads();   // every thread's g_l is in TMEM (and the previous accumulator has been read)
-      if (warp == 0) {
-        if (!w_ready) mbar_wait(&bar_w, 0);
-        tc_fence_after();
-        if (elect_one()) {
-          // B = forward weight image [k_in/8][128 n_out][8] read MN-major: N = k_in, K = n_out
-          const uint64_t b0 = smem_desc(smem_u32(smem + (3 - l) * w_hidden), 128u, 2048u);
-          const uint32_t idesc = idesc_f16(n, false, true);
+      for (int l = 3; l >= 0; --l) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ts(tmem, tmem + kDgAOff + (uint32_t)ks * 8u, b0 + (uint64_t)(ks * 16), idesc, ks ? 1u : 0u);
-          umma_commit(&bar_mma);
-        }
-        __syncwarp();
-      }
-      w_ready = true;
-      // the mask of the layer below does not depend on the accumulator: fetch it while the MMAs run
-      uint4 m[8];
-      if (l > 0) load_mask64(a.act[l - 1] + tile * (int64_t)kActTileBytes, col0, r, m);
-      mbar_wait(&bar_mma, ph);
-      ph ^= 1;
-      tc_fence_after();
-      if (l > 0) {
-        float d[64];
-        {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(d_tmem + (uint32_t)col0, v0);
-          tmem_ld32(d_tmem + (uint32_t)col0 + 32u, v1);
-          tmem_ld_wait();
+        for (int s = 0; s < 2; ++s) {
+          const int64_t j = 2 * p + s;
+          if (j >= my_tiles) continue;
+          const int64_t tile = blockIdx.x + j * gridDim.x;
+          const uint32_t d_tmem = lane_base + (uint32_t)s * kDgSlotCols;
+          const uint32_t a_tmem = d_tmem + kDgAOff + (uint32_t)(col0 >> 1);
+          // the mask of the layer below does not depend on the accumulator: fetch it while the MMAs run
+          uint4 m[8];
+          if (l > 0) load_mask64(a.act[l - 1] + tile * (int64_t)kActTileBytes, col0, r, m);
+          mbar_wait(&bar_mma[s], ph[s]);
+          ph[s] ^= 1u;
+          tc_fence_after();
+          if (l > 0) {
+            float d[64];
+            {
+              uint32_t v0[32], v1[32];
+              tmem_ld32(d_tmem + (uint32_t)col0, v0);
+              tmem_ld32(d_tmem + (uint32_t)col0 + 32u, v1);
+              tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            d[c] = act_pos(m[c >> 3], c & 7) ? __uint_as_float(v0[c]) : 0.f;
-            d[32 + c] = act_pos(m[4 + (c >> 3)], c & 7) ? __uint_as_float(v1[c]) : 0.f;
-          }
-        }
-        emit_delta64(d, a_tmem, a.g[l - 1] + tile * (int64_t)kActTileBytes, col0, r);
-      } else {
-        // d_x0: 16-column units split over the two column halves; fp32, unscaled, ray-major rows
-        const int units = a.k0 >> 4, u_half = (units + 1) >> 1;
-        const int u0 = half == 0 ? 0 : u_half, u1 = half == 0 ? u_half : units;
-        const int64_t blk = tile / a.tiles_per_blk;
-        const int s = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
-        const int64_t ray = blk * kBlkRays + (r & 7);
-        const bool valid = ray < a.n_rays && s < a.S;
-        const float inv = 1.0f / a.scale;
-        float* out = a.d_x0 + (valid ? (ray * a.S + s) * (int64_t)a.k0 : 0);
-        for (int u = u0; u < u1; ++u) {
-          uint32_t v[16];
-          tmem_ld16(d_tmem + (uint32_t)(u * 16), v);
-          tmem_ld_wait();
-          if (valid) {
+              for (int c = 0; c < 32; ++c) {
+                d[c] = act_pos(m[c >> 3], c & 7) ? __uint_as_float(v0[c]) : 0.f;
+                d[32 + c] = act_pos(m[4 + (c >> 3)], c & 7) ? __uint_as_float(v1[c]) : 0.f;
+              }
+            }
+            emit_delta64(d, a_tmem, a.g[l - 1] + tile * (int64_t)kActTileBytes, col0, r);
+            arrive_ready(s);
+          } else {
+            // d_x0: 16-column units split over the two column halves; fp32, unscaled, ray-major rows
+            const int units = a.k0 >> 4, u_half = (units + 1) >> 1;
+            const int u0 = half == 0 ? 0 : u_half, u1 = half == 0 ? u_half : units;
+            const int64_t blk = tile / a.tiles_per_blk;
+            const int smp = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
+            const int64_t ray = blk * kBlkRays + (r & 7);
+            const bool valid = ray < a.n_rays && smp < a.S;
+            const float inv = 1.0f / a.scale;
+            float* out = a.d_x0 + (valid ? (ray * a.S + smp) * (int64_t)a.k0 : 0);
+            for (int u = u0; u < u1; ++u) {
+              uint32_t v[16];
+              tmem_ld16(d_tmem + (uint32_t)(u * 16), v);
+              tmem_ld_wait();
+              if (valid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(out + u * 16 + 4 * j) =
-                  make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
-                              __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(out + u * 16 + 4 * q) =
+                      make_float4(__uint_as_float(v[4 * q]) * inv, __uint_as_float(v[4 * q + 1]) * inv,
+                                  __uint_as_float(v[4 * q + 2]) * inv, __uint_as_float(v[4 * q + 3]) * inv);
+              }
+            }
+            // the slot's accumulator and A region are free: its next tile's g_3 goes in
+            if (j + 2 < my_tiles) {
+              prep_tile(s, blockIdx.x + (j + 2) * gridDim.x);
+              arrive_ready(s);
+            }
           }
         }
       }
     }
-    // the last accumulator has been read by everyone before the next tile's first MMA: the __syncthreads at the top
-    // of the next layer loop orders it (tcgen05.ld completes at tmem_ld_wait)
-    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
@@ -401,7 +438,7 @@ extern "C" int32_t nvsr_mlp_chain_train(const nvsr_mlp_t* m, void* const* act_ou
 }
 
 extern "C" int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* d, void* stream) {
-  NVSR_CHECK_ARG(d && d->k0 > 0 && (d->k0 % 16) == 0 && d->k0 <= 256 && d->head_n >= 1 && d->head_n <= 4);
+  NVSR_CHECK_ARG(d && d->k0 > 0 && (d->k0 % 16) == 0 && d->k0 <= 192 && d->head_n >= 1 && d->head_n <= 4);
   NVSR_CHECK_ARG(d->head_ch >= 0 && d->head_ch + d->head_n <= 4 && d->head_w && d->d_raw && d->dout_img && d->d_x0);
   NVSR_CHECK_ARG(d->n_rays > 0 && d->n_samples > 0 && d->scale > 0.f);
   DgradArgs a;
