@@ -188,7 +188,7 @@ def test_multi_scene_shared_decoder():
     nvsr_b200.set_precision("fp16")
 
 
-@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp16", "bf16", "fp16-split"])
 @pytest.mark.parametrize("kw", [dict(), dict(noise_std=1.0, white_background=True), dict(perturb=True)])
 def test_sparse_rgb_equals_dense(prec, kw):
     """The sparse colour path (rgb decoder only where sigma + noise > 0) is EXACT: a sample with alpha = 0 has
