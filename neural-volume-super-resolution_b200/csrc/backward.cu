@@ -65,6 +65,107 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                          g_w ? g_w + ray * S : nullptr, d_raw + ray * S * 4);
 }
 
+
+// Warp-per-ray variant for S <= 32 * kCbM samples (a training batch is 4 096 rays: one thread per ray leaves most SMs
+// idle and walks 2 x S dependent steps).  Lane l owns samples [l * m, (l + 1) * m): the transmittance is a lane-local
+// running product on top of an exclusive warp scan of the lanes' products, the suffix sum of dL/dw_k * w_k a lane-local
+// running sum on top of a reverse exclusive scan — the same formulas as composite_bwd_ray (backward_bodies.h), another
+// association order of the fp32 products / sums (the GPU tests compare both with autograd of the oracle).
+constexpr int kCbM = 8;
+
+__global__ void __launch_bounds__(128)
+composite_bwd_warp_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rd,
+                          const float* __restrict__ noise, int64_t n, int S, int white, int mip,
+                          const float* __restrict__ g_rgb, const float* __restrict__ g_acc,
+                          const float* __restrict__ g_depth, const float* __restrict__ g_w, float* __restrict__ d_raw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= n) return;
+  const float dx = rd[ray * 3 + 0], dy = rd[ray * 3 + 1], dz = rd[ray * 3 + 2];
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const int Z = S + (mip ? 1 : 0);
+  const float* zr = z + ray * Z;
+  const float4* rr = reinterpret_cast<const float4*>(raw) + ray * S;
+  float4* out = reinterpret_cast<float4*>(d_raw) + ray * S;
+  const int m = (S + 31) >> 5;
+  const int i0 = lane * m;
+  const float gr = g_rgb[ray * 3 + 0], gg = g_rgb[ray * 3 + 1], gb = g_rgb[ray * 3 + 2];
+  const float gsum = white ? gr + gg + gb : 0.f;
+  const float ga = g_acc ? g_acc[ray] : 0.f, gd = g_depth ? g_depth[ray] : 0.f;
+
+  float q[kCbM], a_[kCbM], e_[kCbM], dist_[kCbM], dwv[kCbM];
+  float4 rw[kCbM];
+  bool pos[kCbM];
+  float prod = 1.f;
+#pragma unroll
+  for (int j = 0; j < kCbM; ++j) {
+    const int i = i0 + j;
+    q[j] = 1.f, a_[j] = 0.f, e_[j] = 1.f, dist_[j] = 0.f, dwv[j] = 0.f, pos[j] = false;
+    rw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < m && i < S) {
+      rw[j] = __ldg(rr + i);
+      float dist = (i + 1 < S || mip) ? __fsub_rn(zr[i + 1], zr[i]) : 1e10f;
+      dist = __fmul_rn(dist, nrm);
+      const float pre = rw[j].w + (noise ? noise[ray * S + i] : 0.f);
+      const float sg = pre > 0.f ? pre : 0.f;
+      const float e = expf(-__fmul_rn(sg, dist));
+      const float a = __fsub_rn(1.f, e);
+      pos[j] = pre > 0.f, dist_[j] = dist, e_[j] = e, a_[j] = a;
+      q[j] = __fadd_rn(__fsub_rn(1.f, a), 1e-10f);
+      prod *= q[j];
+    }
+  }
+  // exclusive scan of the lanes' products -> transmittance at the lane's first sample
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= up;
+  }
+  float T = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T = 1.f;
+  // forward sweep: T_i, w_i, dL/dw_i, the colour gradients; lane total of dL/dw * w
+  float Ti[kCbM], wv[kCbM];
+  float lane_sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kCbM; ++j) {
+    const int i = i0 + j;
+    Ti[j] = T, wv[j] = 0.f;
+    if (j < m && i < S) {
+      const float w = a_[j] * T;
+      wv[j] = w;
+      const float t = mip ? 0.5f * (zr[i] + zr[i + 1]) : zr[i];
+      float dw = ga + gd * t + (g_w ? g_w[ray * S + i] : 0.f) - gsum;
+      const float c0 = 1.f / (1.f + expf(-rw[j].x)), c1 = 1.f / (1.f + expf(-rw[j].y)), c2 = 1.f / (1.f + expf(-rw[j].z));
+      dw += gr * c0 + gg * c1 + gb * c2;
+      dwv[j] = dw;
+      rw[j].x = w * gr * c0 * (1.f - c0), rw[j].y = w * gg * c1 * (1.f - c1), rw[j].z = w * gb * c2 * (1.f - c2);
+      lane_sum += dw * w;
+      T *= q[j];
+    }
+  }
+  // reverse exclusive scan of the lane totals -> sum over every later lane's samples
+  float rincl = lane_sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float dn = __shfl_down_sync(0xffffffffu, rincl, o);
+    if (lane + o < 32) rincl += dn;
+  }
+  float suffix = __shfl_down_sync(0xffffffffu, rincl, 1);
+  if (lane == 31) suffix = 0.f;
+  // backward sweep within the lane
+#pragma unroll
+  for (int j = kCbM - 1; j >= 0; --j) {
+    const int i = i0 + j;
+    if (j < m && i < S) {
+      const float da = dwv[j] * Ti[j] - suffix / q[j];
+      rw[j].w = pos[j] ? da * dist_[j] * e_[j] : 0.f;
+      suffix += dwv[j] * wv[j];
+      out[i] = rw[j];
+    }
+  }
+}
+
 }  // namespace nvsr
 
 using namespace nvsr;
@@ -112,8 +213,13 @@ extern "C" int32_t nvsr_composite_bwd(const float* radiance_field, const float* 
                                       const float* d_weights, float* d_radiance_field, void* stream) {
   NVSR_CHECK_ARG(radiance_field && z && rd && d_rgb && d_radiance_field && n_rays >= 0 && n_samples > 0);
   if (n_rays == 0) return NVSR_OK;
-  composite_bwd_kernel<<<(unsigned)ceil_div64(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
-      radiance_field, z, rd, noise, n_rays, n_samples, white_bkgd, mip, d_rgb, d_acc, d_depth, d_weights,
-      d_radiance_field);
+  if (n_samples <= 32 * kCbM && aligned16(radiance_field) && aligned16(d_radiance_field))
+    composite_bwd_warp_kernel<<<(unsigned)ceil_div64(n_rays, 4), 128, 0, (cudaStream_t)stream>>>(
+        radiance_field, z, rd, noise, n_rays, n_samples, white_bkgd, mip, d_rgb, d_acc, d_depth, d_weights,
+        d_radiance_field);
+  else
+    composite_bwd_kernel<<<(unsigned)ceil_div64(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+        radiance_field, z, rd, noise, n_rays, n_samples, white_bkgd, mip, d_rgb, d_acc, d_depth, d_weights,
+        d_radiance_field);
   NVSR_RETURN_LAST_ERROR();
 }
