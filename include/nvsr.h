@@ -401,6 +401,13 @@ typedef struct nvsr_dgrad {
   float* d_x0;           /* out: [n_rays * n_samples][k0] fp32 */
   int64_t n_rays;
   int32_t n_samples;
+  const int32_t* row_count; /* NULL, or row-list mode (below): device count of listed rows; g / dout_img / d_x0 come out
+                             * LIST-ordered (d_x0 [tiles*128][k0]) and only the tiles the list fills are visited */
+  const int32_t* row_ids;   /* row-list mode: NULL = act / d_raw are LIST-ordered already (nvsr_compact_rows); else they
+                             * are the forward's BLOCKED buffers, read through the list, and the kernel writes ... */
+  void* act_list[4];        /* ... the listed rows of x_1..x_4 here in LIST order (out; the weight gradients' operands) */
+  const void* x0_img;       /* optional (both or neither): the forward's k0-channel feature image and ... */
+  void* x0_list;            /* ... its listed rows in LIST order (out) */
 } nvsr_dgrad_t;
 
 int32_t nvsr_mlp_chain_train(const nvsr_mlp_t* mlp, void* const* act_out, void* stream);
@@ -414,6 +421,34 @@ int32_t nvsr_ray_sum(const void* img, int64_t n_rays, int32_t n_samples, float i
 int32_t nvsr_mlp_wgrad_chain(const void* const* g, const void* x0_img, int32_t k0, const void* const* act,
                              const void* dout_img, int64_t n_tiles, float inv_scale, float* const* dw, const int64_t* ldw,
                              float* const* db, float* dw_head, void* stream);
+
+/* Row-list ("sparse") backward.  A sample whose raw gradient is identically zero — alpha = 0 because sigma + noise <= 0
+ * (volume_rendering_utils.py:29-44), or transmittance 0 — adds nothing to any weight or plane gradient, so the
+ * backward chains need only the other rows; on a trained scene that is 10-20 % of the samples.  Results equal the
+ * dense backward's up to the order of the fp32 sums.
+ * nvsr_nonzero_rows: row_ids[0..count) = BLOCKED row ids r < n_rows with d_raw[h][r] != 0 for some h (NaN counts as
+ *   non-zero); order unspecified; count (device int32) is reset first.  row_ids needs n_rows entries.
+ * nvsr_compact_rows: copies the listed rows of n_img tile images (channels[k] each, multiple of 8) and of the four d_raw
+ *   planes into dense tiles in LIST order; the tail of the last tile is zero-filled (it then contributes nothing to
+ *   nvsr_mlp_wgrad_chain_rows).  max_tiles: capacity of the outputs in 128-row tiles; out_stride >= max_tiles * 128.
+ * nvsr_mlp_dgrad with row_count + row_ids set gathers the listed rows itself (no separate compaction pass) and emits the
+ *   LIST-ordered activation / feature images the weight gradients read; the list's tail rows are zero-filled there too.
+ * nvsr_mlp_dgrad with row_count set / nvsr_mlp_wgrad_chain_rows / nvsr_ray_sum_rows / nvsr_sample_gather_bwd_rows: the
+ *   dense entries over the LIST-ordered images, reading the row count on the device (no host synchronisation).
+ *   nvsr_ray_sum_rows ACCUMULATES into out [n_rays][128] (zero it first). */
+int32_t nvsr_nonzero_rows(const float* d_raw, int64_t raw_stride, int64_t n_rows, int32_t* row_ids, int32_t* count,
+                          void* stream);
+int32_t nvsr_compact_rows(const void* const* src, void* const* dst, const int32_t* channels, int32_t n_img,
+                          const float* d_raw, int64_t raw_stride, float* d_raw_out, int64_t out_stride,
+                          const int32_t* row_ids, const int32_t* count, int64_t max_tiles, void* stream);
+int32_t nvsr_mlp_wgrad_chain_rows(const void* const* g, const void* x0_img, int32_t k0, const void* const* act,
+                                  const void* dout_img, int64_t n_tiles, const int32_t* row_count, float inv_scale,
+                                  float* const* dw, const int64_t* ldw, float* const* db, float* dw_head, void* stream);
+int32_t nvsr_ray_sum_rows(const void* img, const int32_t* row_ids, const int32_t* count, int64_t max_rows,
+                          int32_t n_samples, float inv_scale, float* out, void* stream);
+int32_t nvsr_sample_gather_bwd_rows(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes, const float* d_feat_p,
+                                    const float* d_feat_m, const int32_t* row_ids, const int32_t* count, int64_t max_rows,
+                                    float* const d_plane[3], void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Plane super-resolution, last step: PlanesSR.forward (models.py:884-926) ends with

@@ -98,6 +98,11 @@ class Dgrad(C.Structure):
         ("d_x0", c_p),
         ("n_rays", c_i64),
         ("n_samples", c_i32),
+        ("row_count", c_p),
+        ("row_ids", c_p),
+        ("act_list", c_p * 4),
+        ("x0_img", c_p),
+        ("x0_list", c_p),
     ]
 
 
@@ -207,6 +212,14 @@ SIGNATURES = {
     "nvsr_ray_sum": (c_i32, [c_p, c_i64, c_i32, c_f, c_p, c_p]),
     "nvsr_mlp_wgrad_chain": (c_i32, [C.POINTER(c_p), c_p, c_i32, C.POINTER(c_p), c_p, c_i64, c_f, C.POINTER(c_p), C.POINTER(c_i64),
                                      C.POINTER(c_p), c_p, c_p]),
+    "nvsr_nonzero_rows": (c_i32, [c_p, c_i64, c_i64, c_p, c_p, c_p]),
+    "nvsr_compact_rows": (c_i32, [C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_i32), c_i32, c_p, c_i64, c_p, c_i64, c_p, c_p,
+                                  c_i64, c_p]),
+    "nvsr_mlp_wgrad_chain_rows": (c_i32, [C.POINTER(c_p), c_p, c_i32, C.POINTER(c_p), c_p, c_i64, c_p, c_f, C.POINTER(c_p),
+                                          C.POINTER(c_i64), C.POINTER(c_p), c_p, c_p]),
+    "nvsr_ray_sum_rows": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_p, c_p]),
+    "nvsr_sample_gather_bwd_rows": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_p, c_p, c_p, c_p, c_i64, C.POINTER(c_p),
+                                            c_p]),
     "nvsr_pack_weights16": (c_i32, [c_i32, C.POINTER(c_p), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32),
                                     C.POINTER(c_p), c_i32, c_p]),
     "nvsr_composite": (c_i32, [C.POINTER(Composite), c_p]),

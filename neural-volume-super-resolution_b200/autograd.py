@@ -20,7 +20,15 @@ from . import _lib, ops
 from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
 
 
-_state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0}
+_state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0, "sparse_backward": True}
+
+
+def set_sparse_backward(flag):
+    """True (default): the 'tc' decoder's backward runs over the samples whose raw gradient is not identically zero
+    only (row list built on the device from d_raw: csrc/train_tc.cu nonzero_rows / compact_rows) — the others have
+    alpha = 0 or transmittance 0 and add nothing to any gradient.  False: every sample goes through the backward chains.
+    The two give the same gradients up to the order of the fp32 sums."""
+    _state["sparse_backward"] = bool(flag)
 
 
 def set_decoder(mode):
@@ -244,6 +252,12 @@ class PlanesRadianceTC(torch.autograd.Function):
         scale, inv = ctx.scale, 1.0 / ctx.scale
         d_rf = d_rf.float()
         d_raw = ops.nsc_to_planar_blocked(d_rf, n, S)
+        rows = ids = count = None
+        if _state["sparse_backward"]:
+            # the rows that carry a gradient: the data-gradient chains gather them through the list and leave
+            # LIST-ordered copies of the forward's images for the weight gradients
+            ids, count = ops.nonzero_rows(d_raw)
+            rows = (ids, count)
         # every accumulator of the two chains' weight gradients comes out of ONE zero-filled buffer (one memset per pass)
         pool = torch.zeros((2 * (128 * (Cc + C3 + 6 * 128 + 2 * 16) + 8 * 128),), dtype=torch.float32, device=dev)
         cursor = [0]
@@ -262,19 +276,29 @@ class PlanesRadianceTC(torch.autograd.Function):
         # decoder frozen (the phase in which only the SR model / the planes train, train_nerf.py:560): no weight gradients
         want_w = any(needs[4:24])
         # ---- density chain: data gradient, then the weight gradients on the same images
-        g, dout, d_fm = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S)
+        if rows is None:
+            g, dout, d_fm = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S)
+        else:
+            g, dout, d_fm, acts_d, feat_m = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S, row_count=count, row_ids=ids,
+                                                          x0_img=feat_m if want_w else None)
         dens = [None] * 10
         if want_w:
             dws, dbs, dwh = [z0(128, Cc if l == 0 else 128) for l in range(4)], [z0(128) for _ in range(4)], z0(128, 16)
-            ops.mlp_wgrad_chain(g, feat_m, Cc, acts_d, dout, inv, dws, dbs, dwh)
+            ops.mlp_wgrad_chain(g, feat_m, Cc, acts_d, dout, inv, dws, dbs, dwh, row_count=count)
             dens = [t for pair in zip(dws, dbs) for t in pair] + [dwh[:, :1].t().contiguous(), d_rf[..., 3].sum().reshape(1)]
         # ---- rgb chain (its first layer's view-feature columns are a per-ray bias in the forward)
-        g, dout, d_fp = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S)
+        if rows is None:
+            g, dout, d_fp = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S)
+        else:
+            g, dout, d_fp, acts_c, feat_p = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S, row_count=count, row_ids=ids,
+                                                          x0_img=feat_p if want_w else None)
         col = [None] * 10
-        g0_ray = ops.ray_sum(g[0], n, S, inv) if (want_w or needs[3]) else None    # [n, 128]: per-ray sum of g_0
+        g0_ray = None                                                              # [n, 128]: per-ray sum of g_0
+        if want_w or needs[3]:
+            g0_ray = ops.ray_sum(g[0], n, S, inv) if rows is None else ops.ray_sum_rows(g[0], ids, count, n, S, inv, out=z0(n, 128))
         if want_w:
             dws, dbs, dwh = [z0(128, C3 if l == 0 else 128) for l in range(4)], [z0(128) for _ in range(4)], z0(128, 16)
-            ops.mlp_wgrad_chain(g, feat_p, C3, acts_c, dout, inv, dws, dbs, dwh)
+            ops.mlp_wgrad_chain(g, feat_p, C3, acts_c, dout, inv, dws, dbs, dwh, row_count=count)
             dws[0] = torch.cat([dws[0], g0_ray.t() @ vfeat], 1)         # [128, 3C + C]
             col = [t for pair in zip(dws, dbs) for t in pair] + [dwh[:, :3].t().contiguous(), d_rf[..., :3].sum((0, 1))]
         # ---- planes
@@ -282,7 +306,7 @@ class PlanesRadianceTC(torch.autograd.Function):
         shell = ops.PackedPlanes(acc, NVSR_F32, ctx.geom.box_lo, ctx.geom.box_rng, ctx.geom.proj, None, ctx.geom.view_lo_rng)
         if ctx.geom.combine == "sum":
             d_fm = d_fm * 3.0
-        ops.sample_gather_bwd(ro, rd, z, shell, d_fp, d_fm, acc)
+        ops.sample_gather_bwd(ro, rd, z, shell, d_fp, d_fm, acc, rows=rows)
         sv = ctx.shapes[3]
         vgrad = None
         if needs[3]:
@@ -295,6 +319,41 @@ class PlanesRadianceTC(torch.autograd.Function):
         pg = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc, ctx.shapes[:3])] + [vgrad]
         out = pg + dens + col + [None] * 5
         return tuple(o if (o is None or needs[i]) else None for i, o in enumerate(out))
+
+
+class GraphedStep:
+    """One whole training step — forward, backward and (if `step_fn` does it) the optimizer update — captured into a CUDA
+    graph and replayed: the step is ~40 kernel launches of a few microseconds each plus torch glue, so eagerly it is
+    bound by the host's enqueue time, not by the GPU (scripts/bench_train_step.py).  The path has no host
+    synchronisation and takes every size from the tensors' shapes (the sparse backward reads its row count on the
+    device), which is what makes it capturable.
+
+    step_fn(): runs the step reading its inputs (ray batch, targets, random draws — CUDA tensors; draw them inside with
+    `.uniform_()` / `.normal_()` or `copy_` into them between replays) from tensors the caller keeps alive, and
+    returns whatever should be readable after a replay (e.g. the loss tensor).  Gradients: step_fn must start with
+    `optimizer.zero_grad(set_to_none=True)` (or `p.grad = None`), so that the capture allocates them in the graph's pool
+    and a replay overwrites instead of accumulating on top of the warm-up steps' gradients.
+    Use `capturable=True` optimizers.  `check_every`: replays between host reads of the fp16 range flag."""
+
+    def __init__(self, step_fn, warmup=3, check_every=256):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step_fn()
+        torch.cuda.current_stream().wait_stream(side)
+        _range_check.flush()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = step_fn()
+        self.replays, self.check_every = 0, check_every
+
+    def __call__(self):
+        self.graph.replay()
+        self.replays += 1
+        if self.check_every and self.replays % self.check_every == 0:
+            _range_check.check_graph()
+        return self.result
 
 
 def _tc_supported(model):

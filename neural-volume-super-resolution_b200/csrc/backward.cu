@@ -24,6 +24,8 @@ struct GatherBwdArgs {
   const float* d_feat_p;
   const float* d_feat_m;
   float* d_plane[3];
+  const int32_t* ids;     // row-list mode: d_feat rows are in LIST order, ids[i] = BLOCKED row id of list row i
+  const int32_t* count;
 };
 
 // one thread per (row, 4-channel chunk): consecutive threads hold consecutive channel chunks of one row, so the
@@ -37,6 +39,21 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(GatherBwdArgs a) {
   int ch = (int)(idx % chunks) * 4;
   int64_t ray = row / a.S;
   bwd::gather_bwd_row(a.g, a.ro, a.rd, a.z[row], ray, row, ch, a.d_feat_p, a.d_feat_m, a.d_plane);
+}
+
+// row-list variant (the sparse training backward): list row i carries the gradient of BLOCKED row ids[i]
+__global__ void __launch_bounds__(256) gather_bwd_rows_kernel(GatherBwdArgs a) {
+  const int chunks = a.g.C / 4;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = idx / chunks;
+  if (i >= __ldg(a.count)) return;
+  int ch = (int)(idx % chunks) * 4;
+  const int32_t rid = __ldg(a.ids + i);
+  int64_t ray;
+  int s;
+  blocked_decode(rid / kTileRows, rid % kTileRows, tiles_per_block(a.S), &ray, &s);
+  if (ray >= a.n_rays || s >= a.S) return;
+  bwd::gather_bwd_row(a.g, a.ro, a.rd, a.z[ray * a.S + s], ray, i, ch, a.d_feat_p, a.d_feat_m, a.d_plane);
 }
 
 __global__ void __launch_bounds__(256)
@@ -170,8 +187,9 @@ composite_bwd_warp_kernel(const float* __restrict__ raw, const float* __restrict
 
 using namespace nvsr;
 
-extern "C" int32_t nvsr_sample_gather_bwd(const nvsr_sampler_t* s, const nvsr_planes_t* pl, const float* d_feat_p,
-                                          const float* d_feat_m, float* const d_plane[3], void* stream) {
+static int32_t gather_bwd_launch(const nvsr_sampler_t* s, const nvsr_planes_t* pl, const float* d_feat_p,
+                                 const float* d_feat_m, const int32_t* row_ids, const int32_t* count, int64_t max_rows,
+                                 float* const d_plane[3], void* stream) {
   NVSR_CHECK_ARG(s && pl && d_plane && (d_feat_p || d_feat_m));
   NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd && s->z_in);
   NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 4 == 0);
@@ -188,10 +206,26 @@ extern "C" int32_t nvsr_sample_gather_bwd(const nvsr_sampler_t* s, const nvsr_pl
   a.n_rays = s->n_rays, a.S = s->n_samples;
   a.ro = s->ro, a.rd = s->rd, a.z = s->z_in;
   a.d_feat_p = d_feat_p, a.d_feat_m = d_feat_m;
-  int64_t total = a.n_rays * a.S * (a.g.C / 4);
+  a.ids = row_ids, a.count = count;
+  int64_t total = (row_ids ? max_rows : a.n_rays * a.S) * (a.g.C / 4);
   if (total == 0) return NVSR_OK;
-  gather_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  if (row_ids)
+    gather_bwd_rows_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  else
+    gather_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_sample_gather_bwd(const nvsr_sampler_t* s, const nvsr_planes_t* pl, const float* d_feat_p,
+                                          const float* d_feat_m, float* const d_plane[3], void* stream) {
+  return gather_bwd_launch(s, pl, d_feat_p, d_feat_m, nullptr, nullptr, 0, d_plane, stream);
+}
+
+extern "C" int32_t nvsr_sample_gather_bwd_rows(const nvsr_sampler_t* s, const nvsr_planes_t* pl, const float* d_feat_p,
+                                               const float* d_feat_m, const int32_t* row_ids, const int32_t* count,
+                                               int64_t max_rows, float* const d_plane[3], void* stream) {
+  NVSR_CHECK_ARG(row_ids && count && max_rows >= 0);
+  return gather_bwd_launch(s, pl, d_feat_p, d_feat_m, row_ids, count, max_rows, d_plane, stream);
 }
 
 extern "C" int32_t nvsr_viewdir_gather_bwd(const float* viewdirs, int64_t n_rays, int32_t rh, int32_t rw,

@@ -111,13 +111,30 @@ struct DgradArgs {
   float* d_x0;           // out: fp32 [n_rays * S][k0], ray-major rows
   int64_t n_tiles, n_rays;
   int S, tiles_per_blk;
+  const int32_t* row_count;   // row-list mode (device count of listed rows): g / dout_img / d_x0 come out in LIST order
+  const int32_t* row_ids;     // with row_count: act / d_raw / x0 are the forward's BLOCKED buffers, read through the list,
+  uint8_t* act_c[4];          //   and their listed rows are written out in LIST order for the weight gradients
+  const uint8_t* x0;          //   (act_c: x_1..x_4, x0_c: the k0-channel feature image).  NULL: act / d_raw are
+  uint8_t* x0_c;              //   LIST-ordered already (nvsr_compact_rows)
 };
 
-// this thread's mask words: the 64 activations of row r, columns [col0, col0 + 64), eight per 16-byte group
-__device__ __forceinline__ void load_mask64(const uint8_t* act_tile, int col0, int r, uint4 (&m)[8]) {
-  const uint4* p = reinterpret_cast<const uint4*>(act_tile) + (col0 >> 3) * 128 + r;
+// this thread's mask words: the 64 activations of image row `src` (< 0: a zero row), columns [col0, col0 + 64), eight per
+// 16-byte group; `copy` (row-list mode): the same words go to row r of tile `tile` of the LIST-ordered image
+__device__ __forceinline__ void load_mask64(const uint8_t* img, int64_t src, int col0, uint4 (&m)[8], uint8_t* copy,
+                                            int64_t tile, int r) {
+  if (src >= 0) {
+    const uint4* p = reinterpret_cast<const uint4*>(img + (src >> 7) * (int64_t)kActTileBytes) + (col0 >> 3) * 128 + (src & 127);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = __ldg(p + j * 128);
+    for (int j = 0; j < 8; ++j) m[j] = __ldg(p + j * 128);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (copy) {
+    uint4* q = reinterpret_cast<uint4*>(copy + tile * (int64_t)kActTileBytes) + (col0 >> 3) * 128 + r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j * 128] = m[j];
+  }
 }
 // activations are post-ReLU (>= +0): "positive" == any non-sign bit set
 __device__ __forceinline__ bool act_pos(const uint4& m, int e) {
@@ -159,7 +176,13 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const int64_t my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  int64_t n_tiles = a.n_tiles, listed_rows = 0;
+  if (a.row_count) {
+    listed_rows = (int64_t)__ldg(a.row_count);
+    const int64_t listed = (listed_rows + kTileRows - 1) / kTileRows;
+    n_tiles = listed < n_tiles ? listed : n_tiles;
+  }
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 8) {
     // ================= issuer =================
@@ -206,14 +229,28 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
       if (lane == 0) mbar_arrive(&bar_ready[s]);
     };
     // g_3 = (d_out . W_head) * [x_4 > 0] of `tile` on the CUDA cores -> slot s's A region + the g[3] / d_out images
+    // the buffer row that feeds row r of `tile`: itself, or (row-list mode) the listed BLOCKED row; -1 = the list's zero tail
+    auto src_row = [&](int64_t tile) -> int64_t {
+      const int64_t i = tile * kTileRows + r;
+      if (!a.row_ids) return i;
+      return i < listed_rows ? (int64_t)__ldg(a.row_ids + i) : -1;
+    };
     auto prep_tile = [&](int s, int64_t tile) {
       const uint32_t a_tmem = lane_base + (uint32_t)s * kDgSlotCols + kDgAOff + (uint32_t)(col0 >> 1);
+      const int64_t src = src_row(tile);
       float dv[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h)
-        dv[h] = h < a.head_n ? __ldg(a.d_raw + (int64_t)(a.head_ch + h) * a.raw_stride + tile * kTileRows + r) * a.scale : 0.f;
+        dv[h] = (h < a.head_n && src >= 0) ? __ldg(a.d_raw + (int64_t)(a.head_ch + h) * a.raw_stride + src) * a.scale : 0.f;
       uint4 m[8];
-      load_mask64(a.act[3] + tile * (int64_t)kActTileBytes, col0, r, m);
+      load_mask64(a.act[3], src, col0, m, a.row_ids ? a.act_c[3] : nullptr, tile, r);
+      if (a.row_ids && a.x0_c) {   // the feature image's listed rows, for the layer-0 weight gradient
+        const int chunks = a.k0 >> 3, c_half = (chunks + 1) >> 1;
+        const int c0 = half == 0 ? 0 : c_half, c1 = half == 0 ? c_half : chunks;
+        const uint4* px = reinterpret_cast<const uint4*>(a.x0) + (src >= 0 ? (src >> 7) * chunks * kTileRows + (src & 127) : 0);
+        uint4* qx = reinterpret_cast<uint4*>(a.x0_c) + tile * chunks * kTileRows + r;
+        for (int c = c0; c < c1; ++c) qx[c * kTileRows] = src >= 0 ? __ldg(px + c * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
+      }
       float d[64];
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
@@ -247,7 +284,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
           const uint32_t a_tmem = d_tmem + kDgAOff + (uint32_t)(col0 >> 1);
           // the mask of the layer below does not depend on the accumulator: fetch it while the MMAs run
           uint4 m[8];
-          if (l > 0) load_mask64(a.act[l - 1] + tile * (int64_t)kActTileBytes, col0, r, m);
+          if (l > 0) load_mask64(a.act[l - 1], src_row(tile), col0, m, a.row_ids ? a.act_c[l - 1] : nullptr, tile, r);
           mbar_wait(&bar_mma[s], ph[s]);
           ph[s] ^= 1u;
           tc_fence_after();
@@ -273,9 +310,10 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
             const int64_t blk = tile / a.tiles_per_blk;
             const int smp = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
             const int64_t ray = blk * kBlkRays + (r & 7);
-            const bool valid = ray < a.n_rays && smp < a.S;
+            // row-list mode: row i of the list -> d_x0 row i (the list's zero-padded tail rows come out as zeros)
+            const bool valid = a.row_count ? true : (ray < a.n_rays && smp < a.S);
             const float inv = 1.0f / a.scale;
-            float* out = a.d_x0 + (valid ? (ray * a.S + smp) * (int64_t)a.k0 : 0);
+            float* out = a.d_x0 + (a.row_count ? (tile * kTileRows + r) * (int64_t)a.k0 : (valid ? (ray * a.S + smp) * (int64_t)a.k0 : 0));
             for (int u = u0; u < u1; ++u) {
               uint32_t v[16];
               tmem_ld16(d_tmem + (uint32_t)(u * 16), v);
@@ -312,9 +350,36 @@ constexpr int kWgStages = 3;
 
 // dW[m][n] += inv_scale * sum over the tiles' rows of A[r][m] * B[r][n]  (A: 128 channels, B: n_b channels, both tile
 // images), db[m] += inv_scale * sum over rows of A[r][m] (optional).  One warp loads and issues, four read out.
-__global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, int n_b, int64_t n_tiles, float inv_scale,
-             float* __restrict__ dw, int64_t ldw, float* __restrict__ db) {
+// up to five products per launch (blockIdx.y): the weight gradients of one chain are independent, and with a short row
+// list each needs only a few CTAs, so they run side by side instead of one launch after the other
+struct WgradProblem {
+  const uint8_t* a_img;
+  const uint8_t* b_img;
+  int n_b;
+  float* dw;
+  int64_t ldw;
+  float* db;
+};
+struct WgradArgs {
+  WgradProblem p[5];
+  int64_t n_tiles;
+  const int32_t* row_count;
+  int min_tiles;
+  float inv_scale;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradArgs args) {
+  const WgradProblem& pr = args.p[blockIdx.y];
+  const uint8_t* __restrict__ a_img = pr.a_img;
+  const uint8_t* __restrict__ b_img = pr.b_img;
+  const int n_b = pr.n_b;
+  float* __restrict__ dw = pr.dw;
+  const int64_t ldw = pr.ldw;
+  float* __restrict__ db = pr.db;
+  int64_t n_tiles = args.n_tiles;
+  const int32_t* __restrict__ row_count = args.row_count;
+  const int min_tiles = args.min_tiles;
+  const float inv_scale = args.inv_scale;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kWgStages], empty[kWgStages], done;
   __shared__ uint32_t tmem_slot;
@@ -336,12 +401,20 @@ wgrad_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_im
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (row_count) {   // row-list mode: only the tiles the list fills (its tail rows are zero in both images)
+    const int64_t listed = ((int64_t)__ldg(row_count) + kTileRows - 1) / kTileRows;
+    n_tiles = listed < n_tiles ? listed : n_tiles;
+  }
+  // every participating CTA ends with 128 x n_b atomics into the same accumulator: with few tiles (a short row list)
+  // fewer CTAs take part, at least `min_tiles` tiles each
+  int64_t ctas = n_tiles / min_tiles;
+  ctas = ctas < 1 ? 1 : (ctas > (int64_t)gridDim.x ? (int64_t)gridDim.x : ctas);
+  const int64_t my_tiles = blockIdx.x < ctas && blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + ctas - 1) / ctas : 0;
 
   if (threadIdx.x == 0 && my_tiles > 0) {
     auto load = [&](int64_t t) {
       const int s = (int)(t % kWgStages);
-      const int64_t tile = blockIdx.x + t * gridDim.x;
+      const int64_t tile = blockIdx.x + t * ctas;
       mbar_arrive_expect_tx(&full[s], st_bytes);
       bulk_g2s(smem + s * st_bytes, a_img + tile * a_bytes, a_bytes, &full[s]);
       bulk_g2s(smem + s * st_bytes + a_bytes, b_img + tile * (int64_t)b_bytes, b_bytes, &full[s]);
@@ -422,6 +495,113 @@ ray_sum_kernel(const uint8_t* __restrict__ img, int64_t n_rays, int S, int tiles
   for (int e = 0; e < 8; ++e) out[ray * 128 + j * 8 + e] = acc[e] * inv_scale;
 }
 
+
+// ---- row-list ("sparse") backward ---------------------------------------------------------------------------------
+// A sample whose raw gradient is identically zero (alpha = 0: sigma + noise <= 0, or transmittance 0) contributes
+// nothing to any weight / plane gradient: the backward chains need only the other rows.  nonzero_rows_kernel lists them
+// (BLOCKED row ids, order unspecified), compact_rows_kernel copies those rows of the forward's images and of d_raw into
+// dense tiles in list order (tail of the last tile zero-filled, so it adds nothing to the weight gradients).
+__global__ void __launch_bounds__(256)
+nonzero_rows_kernel(const float* __restrict__ d_raw, int64_t stride, int64_t n_rows, int32_t* __restrict__ ids,
+                    int32_t* __restrict__ count) {
+  __shared__ int warp_cnt[8];
+  __shared__ int block_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * 1024; base < n_rows; base += (int64_t)gridDim.x * 1024) {
+    unsigned m[4];
+    bool k[4];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t row = base + j * 256 + threadIdx.x;
+      k[j] = false;
+      if (row < n_rows) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) k[j] = k[j] || !(__ldg(d_raw + h * stride + row) == 0.f);   // NaN is kept
+      }
+      m[j] = __ballot_sync(0xffffffffu, k[j]);
+      mine += __popc(m[j]);
+    }
+    if (lane == 0) warp_cnt[wid] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int c = warp_cnt[w];
+        warp_cnt[w] = tot;
+        tot += c;
+      }
+      block_base = tot ? atomicAdd(count, tot) : 0;
+    }
+    __syncthreads();
+    int off = block_base + warp_cnt[wid];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (k[j]) ids[off + __popc(m[j] & ((1u << lane) - 1u))] = (int32_t)(base + j * 256 + threadIdx.x);
+      off += __popc(m[j]);
+    }
+    __syncthreads();
+  }
+}
+
+struct CompactArgs {
+  const uint8_t* src[12];
+  uint8_t* dst[12];
+  int chunks[12];     // 16-byte chunks per row (channels / 8)
+  int n_img;
+  const float* d_raw;      // planar [4][raw_stride]
+  float* d_raw_out;        // planar [4][out_stride]
+  int64_t raw_stride, out_stride;
+  const int32_t* ids;
+  const int32_t* count;
+};
+
+// grid (tiles, n_img + 1): block (t, k) fills tile t of image k (k == n_img: the four d_raw planes)
+__global__ void __launch_bounds__(kTileRows) compact_rows_kernel(const __grid_constant__ CompactArgs a) {
+  const int n = __ldg(a.count);
+  const int64_t tile = blockIdx.x;
+  if (tile * kTileRows >= n) return;
+  const int r = threadIdx.x, k = blockIdx.y;
+  const int64_t i = tile * kTileRows + r;
+  const bool live = i < n;
+  const int64_t rid = live ? __ldg(a.ids + i) : 0;
+  if (k == a.n_img) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) a.d_raw_out[h * a.out_stride + i] = live ? __ldg(a.d_raw + h * a.raw_stride + rid) : 0.f;
+    return;
+  }
+  const int chunks = a.chunks[k];
+  const uint4* src = reinterpret_cast<const uint4*>(a.src[k]) + (rid >> 7) * chunks * kTileRows + (rid & 127);
+  uint4* dst = reinterpret_cast<uint4*>(a.dst[k]) + tile * chunks * kTileRows + r;
+  int c = 0;
+  for (; c + 4 <= chunks; c += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = live ? __ldg(src + (c + q) * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[(c + q) * kTileRows] = v[q];
+  }
+  for (; c < chunks; ++c) dst[c * kTileRows] = live ? __ldg(src + c * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// per-ray sums of a LIST-ordered 128-channel image: out[ray(ids[i])][c] += inv_scale * img[i][c]  (out zeroed by the caller)
+__global__ void __launch_bounds__(256)
+ray_sum_rows_kernel(const uint8_t* __restrict__ img, const int32_t* __restrict__ ids, const int32_t* __restrict__ count,
+                    int tiles_per_blk, float inv_scale, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = idx >> 4;
+  if (i >= __ldg(count)) return;
+  const int j = (int)(idx & 15);
+  const int32_t rid = __ldg(ids + i);
+  const int64_t ray = (int64_t)((rid >> 7) / tiles_per_blk) * kBlkRays + (rid & (kBlkRays - 1));
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (i >> 7) * (int64_t)kActTileBytes) + j * 128 + (i & 127));
+  const float2 f0 = unpack16x2<true>(v.x), f1 = unpack16x2<true>(v.y), f2 = unpack16x2<true>(v.z), f3 = unpack16x2<true>(v.w);
+  float4* o = reinterpret_cast<float4*>(out + ray * 128 + j * 8);
+  atomicAdd(o, make_float4(f0.x * inv_scale, f0.y * inv_scale, f1.x * inv_scale, f1.y * inv_scale));
+  atomicAdd(o + 1, make_float4(f2.x * inv_scale, f2.y * inv_scale, f3.x * inv_scale, f3.y * inv_scale));
+}
+
 }  // namespace
 
 int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out);
@@ -453,6 +633,19 @@ extern "C" int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* d, void* stream) {
   a.dout_img = (uint8_t*)d->dout_img, a.d_x0 = d->d_x0;
   a.n_rays = d->n_rays, a.S = d->n_samples, a.tiles_per_blk = tiles_per_block(d->n_samples);
   a.n_tiles = ceil_div64(d->n_rays, kBlkRays) * a.tiles_per_blk;
+  a.row_count = d->row_count, a.row_ids = d->row_count ? d->row_ids : nullptr;
+  a.x0 = nullptr, a.x0_c = nullptr;
+  for (int l = 0; l < 4; ++l) a.act_c[l] = nullptr;
+  if (a.row_ids) {
+    for (int l = 0; l < 4; ++l) {
+      NVSR_CHECK_ARG(d->act_list[l]);
+      if (!aligned16(d->act_list[l])) return NVSR_ERR_ALIGNMENT;
+      a.act_c[l] = (uint8_t*)d->act_list[l];
+    }
+    NVSR_CHECK_ARG((d->x0_img == nullptr) == (d->x0_list == nullptr));
+    if (!aligned16(d->x0_img) || !aligned16(d->x0_list)) return NVSR_ERR_ALIGNMENT;
+    a.x0 = (const uint8_t*)d->x0_img, a.x0_c = (uint8_t*)d->x0_list;
+  }
   NVSR_CHECK_ARG(d->raw_stride >= a.n_tiles * kTileRows);
   const uint32_t smem_bytes = 3u * 128u * 128u * 2u + (uint32_t)d->k0 * 256u;
   cudaError_t e = cudaFuncSetAttribute(dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -462,30 +655,94 @@ extern "C" int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* d, void* stream) {
   NVSR_RETURN_LAST_ERROR();
 }
 
-extern "C" int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t n_b, int64_t n_tiles, float inv_scale,
-                                  float* dw, int64_t ldw, float* db, void* stream) {
-  NVSR_CHECK_ARG(a_img && b_img && dw && n_b >= 16 && (n_b % 16) == 0 && n_b <= 256 && ldw >= n_b && n_tiles >= 0);
-  if (!aligned16(a_img) || !aligned16(b_img)) return NVSR_ERR_ALIGNMENT;
+constexpr int kWgMinTiles = 16;   // tiles per participating CTA before another CTA joins (A/B on B200: 1: 0.93, 8: 0.70, 16: 0.66 ms)
+
+// n products (<= 5) of one chain in one launch
+static int32_t wgrad_launch(const WgradProblem* pr, int n, int64_t n_tiles, const int32_t* row_count, float inv_scale,
+                            void* stream) {
+  NVSR_CHECK_ARG(n >= 1 && n <= 5 && n_tiles >= 0);
+  WgradArgs a;
+  uint32_t smem_bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    const WgradProblem& q = pr[i];
+    NVSR_CHECK_ARG(q.a_img && q.b_img && q.dw && q.n_b >= 16 && (q.n_b % 16) == 0 && q.n_b <= 256 && q.ldw >= q.n_b);
+    if (!aligned16(q.a_img) || !aligned16(q.b_img)) return NVSR_ERR_ALIGNMENT;
+    const uint32_t need = kWgStages * (kActTileBytes + (uint32_t)kTileRows * (uint32_t)q.n_b * 2u) + 2u * kTileRows * 16u;
+    smem_bytes = need > smem_bytes ? need : smem_bytes;
+    a.p[i] = q;
+  }
   if (n_tiles == 0) return NVSR_OK;
-  const uint32_t smem_bytes = kWgStages * (kActTileBytes + (uint32_t)kTileRows * (uint32_t)n_b * 2u) + 2u * kTileRows * 16u;
   if (smem_bytes > 227u * 1024u) return NVSR_ERR_RESOURCE;
+  a.n_tiles = n_tiles, a.row_count = row_count, a.min_tiles = kWgMinTiles, a.inv_scale = inv_scale;
   cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int32_t)e;
   const int64_t grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  wgrad_kernel<<<(unsigned)grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>((const uint8_t*)a_img, (const uint8_t*)b_img, n_b,
-                                                                                  n_tiles, inv_scale, dw, ldw, db);
+  wgrad_kernel<<<dim3((unsigned)grid, (unsigned)n), kWgThreads, smem_bytes, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t n_b, int64_t n_tiles, float inv_scale,
+                                  float* dw, int64_t ldw, float* db, void* stream) {
+  const WgradProblem q{(const uint8_t*)a_img, (const uint8_t*)b_img, n_b, dw, ldw, db};
+  return wgrad_launch(&q, 1, n_tiles, nullptr, inv_scale, stream);
+}
+
+extern "C" int32_t nvsr_mlp_wgrad_chain_rows(const void* const* g, const void* x0_img, int32_t k0, const void* const* act,
+                                             const void* dout_img, int64_t n_tiles, const int32_t* row_count,
+                                             float inv_scale, float* const* dw, const int64_t* ldw, float* const* db,
+                                             float* dw_head, void* stream) {
+  NVSR_CHECK_ARG(g && x0_img && act && dout_img && dw && ldw && db && dw_head);
+  WgradProblem q[5];
+  for (int l = 0; l < 4; ++l)
+    q[l] = WgradProblem{(const uint8_t*)g[l], (const uint8_t*)(l == 0 ? x0_img : act[l - 1]), l == 0 ? k0 : 128, dw[l], ldw[l], db[l]};
+  q[4] = WgradProblem{(const uint8_t*)act[3], (const uint8_t*)dout_img, 16, dw_head, 16, nullptr};
+  return wgrad_launch(q, 5, n_tiles, row_count, inv_scale, stream);
 }
 
 extern "C" int32_t nvsr_mlp_wgrad_chain(const void* const* g, const void* x0_img, int32_t k0, const void* const* act,
                                         const void* dout_img, int64_t n_tiles, float inv_scale, float* const* dw,
                                         const int64_t* ldw, float* const* db, float* dw_head, void* stream) {
-  NVSR_CHECK_ARG(g && x0_img && act && dout_img && dw && ldw && db && dw_head);
-  for (int l = 0; l < 4; ++l) {
-    int32_t st = nvsr_mlp_wgrad(g[l], l == 0 ? x0_img : act[l - 1], l == 0 ? k0 : 128, n_tiles, inv_scale, dw[l], ldw[l], db[l], stream);
-    if (st != NVSR_OK) return st;
+  return nvsr_mlp_wgrad_chain_rows(g, x0_img, k0, act, dout_img, n_tiles, nullptr, inv_scale, dw, ldw, db, dw_head, stream);
+}
+
+extern "C" int32_t nvsr_nonzero_rows(const float* d_raw, int64_t raw_stride, int64_t n_rows, int32_t* row_ids, int32_t* count,
+                                     void* stream) {
+  NVSR_CHECK_ARG(d_raw && row_ids && count && n_rows >= 0 && raw_stride >= n_rows && n_rows < ((int64_t)1 << 31));
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int32_t)e;
+  if (n_rows == 0) return NVSR_OK;
+  int64_t blocks = ceil_div64(n_rows, 1024);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  nonzero_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_raw, raw_stride, n_rows, row_ids, count);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_compact_rows(const void* const* src, void* const* dst, const int32_t* channels, int32_t n_img,
+                                     const float* d_raw, int64_t raw_stride, float* d_raw_out, int64_t out_stride,
+                                     const int32_t* row_ids, const int32_t* count, int64_t max_tiles, void* stream) {
+  NVSR_CHECK_ARG(src && dst && channels && n_img >= 0 && n_img <= 12 && d_raw && d_raw_out && row_ids && count);
+  NVSR_CHECK_ARG(max_tiles >= 0 && max_tiles <= 0x7fffffff && out_stride >= max_tiles * kTileRows);
+  if (max_tiles == 0) return NVSR_OK;
+  CompactArgs a;
+  for (int k = 0; k < n_img; ++k) {
+    NVSR_CHECK_ARG(src[k] && dst[k] && channels[k] > 0 && channels[k] % 8 == 0);
+    if (!aligned16(src[k]) || !aligned16(dst[k])) return NVSR_ERR_ALIGNMENT;
+    a.src[k] = (const uint8_t*)src[k], a.dst[k] = (uint8_t*)dst[k], a.chunks[k] = channels[k] / 8;
   }
-  return nvsr_mlp_wgrad(act[3], dout_img, 16, n_tiles, inv_scale, dw_head, 16, nullptr, stream);
+  a.n_img = n_img, a.d_raw = d_raw, a.d_raw_out = d_raw_out, a.raw_stride = raw_stride, a.out_stride = out_stride;
+  a.ids = row_ids, a.count = count;
+  compact_rows_kernel<<<dim3((unsigned)max_tiles, (unsigned)(n_img + 1)), kTileRows, 0, (cudaStream_t)stream>>>(a);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_ray_sum_rows(const void* img, const int32_t* row_ids, const int32_t* count, int64_t max_rows,
+                                     int32_t n_samples, float inv_scale, float* out, void* stream) {
+  NVSR_CHECK_ARG(img && row_ids && count && out && max_rows >= 0 && n_samples > 0);
+  if (!aligned16(img) || !aligned16(out)) return NVSR_ERR_ALIGNMENT;
+  if (max_rows == 0) return NVSR_OK;
+  ray_sum_rows_kernel<<<(unsigned)ceil_div64(max_rows * 16, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)img, row_ids, count, tiles_per_block(n_samples), inv_scale, out);
+  NVSR_RETURN_LAST_ERROR();
 }
 
 extern "C" int32_t nvsr_ray_sum(const void* img, int64_t n_rays, int32_t n_samples, float inv_scale, float* out, void* stream) {

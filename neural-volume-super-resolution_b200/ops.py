@@ -187,11 +187,24 @@ class DeferredRangeCheck:
     def __init__(self):
         self.pending = None      # (pinned host tensor, event, description)
         self.cur = []
+        self.graph_max = None    # running maximum kept on the device by steps replayed from a CUDA graph
+        self.graph_what = ""
 
     def add(self, t, what):
         self.cur.append((t.detach().abs().max(), what))
 
     def commit(self):
+        if torch.cuda.is_current_stream_capturing():
+            # a step being captured into a CUDA graph: no events, no host copies — fold the maximum into a device scalar
+            # that `check_graph()` reads between replays
+            if self.cur:
+                m = torch.stack([v.float() for v, _ in self.cur]).max()
+                self.graph_what = ", ".join(sorted({w for _, w in self.cur}))
+                self.cur = []
+                if self.graph_max is None:
+                    self.graph_max = torch.zeros_like(m)
+                self.graph_max.copy_(torch.maximum(self.graph_max, m))
+            return
         self.poll()
         if not self.cur:
             return
@@ -219,6 +232,12 @@ class DeferredRangeCheck:
 
     def flush(self):
         self.poll(wait=True)
+
+    def check_graph(self):
+        """host read (synchronises) of the maximum accumulated by graph replays; raises like `poll`"""
+        if self.graph_max is not None and float(self.graph_max) > F16_MAX:
+            raise _lib.NvsrError(f"{self.graph_what}: |value| exceeded the fp16 range ({F16_MAX:g}) in a replayed step; values "
+                                 "saturated silently - use the fp32 decoder mode for this model")
 
 
 def pack_plane(plane_nchw, dtype=NVSR_F32, range_check=None):
@@ -517,16 +536,20 @@ def mlp_chain_train(inp, layers, rows, raw, samples_per_ray, n_rays):
     return acts
 
 
-def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples):
+def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples, row_count=None, row_ids=None, x0_img=None):
     """Data-gradient chain of one tri-plane decoder chain.  w_imgs: the 4 forward weight images (fp16); head_w [h,128]
     fp32; d_raw planar [4,stride] (BLOCKED rows, padding rows 0); acts: x_1..x_4 images.
-    -> (g images g_0..g_3, d_out image [tiles,2,128,8], d_x0 fp32 [n_rays*n_samples, k0])."""
+    -> (g images g_0..g_3, d_out image [tiles,2,128,8], d_x0 fp32 [n_rays*n_samples, k0]).
+    row_count (device int32 [1]): row-list mode — the outputs are LIST-ordered (d_x0 [tiles*128, k0]) and only the tiles
+    the list fills are touched.  Without row_ids, d_raw / acts are the LIST-ordered copies of `compact_rows`; with
+    row_ids (+ x0_img, the feature image) they are the forward's own buffers, gathered through the list by the kernel,
+    which then also returns the LIST-ordered x_1..x_4 and feature images: (g, d_out, d_x0, acts_list, x0_list)."""
     lib = _lib.load()
     dev = d_raw.device
     tiles = rows_padded(n_rays, n_samples, ROWS_BLOCKED) // TILE_ROWS
     g = [torch.empty((tiles, 16, TILE_ROWS, 8), dtype=torch.float16, device=dev) for _ in range(4)]
     dout = torch.empty((tiles, 2, TILE_ROWS, 8), dtype=torch.float16, device=dev)
-    d_x0 = torch.empty((n_rays * n_samples, k0), dtype=torch.float32, device=dev)
+    d_x0 = torch.empty((n_rays * n_samples if row_count is None else tiles * TILE_ROWS, k0), dtype=torch.float32, device=dev)
     head_w = _f32c(head_w.detach())
     a = _lib.Dgrad()
     for l in range(4):
@@ -534,11 +557,23 @@ def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples
     a.k0, a.head_w, a.head_n, a.head_ch = k0, head_w.data_ptr(), head_w.shape[0], head_ch
     a.d_raw, a.raw_stride, a.scale = d_raw.data_ptr(), d_raw.stride(0), float(scale)
     a.dout_img, a.d_x0, a.n_rays, a.n_samples = dout.data_ptr(), d_x0.data_ptr(), n_rays, n_samples
+    a.row_count = _ptr(row_count)
+    acts_list = x0_list = None
+    if row_ids is not None:
+        acts_list = [torch.empty_like(t) for t in acts]
+        a.row_ids = row_ids.data_ptr()
+        for l in range(4):
+            a.act_list[l] = acts_list[l].data_ptr()
+        if x0_img is not None:
+            x0_list = torch.empty_like(x0_img)
+            a.x0_img, a.x0_list = x0_img.data_ptr(), x0_list.data_ptr()
     with _OnDevice(dev):
         rows = tiles * TILE_ROWS
         st = _call("nvsr_mlp_dgrad", lib.nvsr_mlp_dgrad, C.byref(a), _stream(), rows=rows,
                    flops=rows * 2 * (3 * 128 * 128 + k0 * 128 + head_w.shape[0] * 128), bytes=rows * (8 * 256 + 4 * k0 + 16))
     _lib.check(st, "nvsr_mlp_dgrad")
+    if row_ids is not None:
+        return g, dout, d_x0, acts_list, x0_list
     return g, dout, d_x0
 
 
@@ -555,15 +590,17 @@ def mlp_wgrad(a_img, b_img, n_b, inv_scale, dw, db=None):
     return dw
 
 
-def mlp_wgrad_chain(g, x0_img, k0, acts, dout, inv_scale, dws, dbs, dw_head):
-    """the five weight gradients of one chain in ONE C call (nvsr_mlp_wgrad_chain): layers 0..3 into dws[l] [128, k] /
-    dbs[l] [128], the head into dw_head [128, 16]; all accumulated into (zero them first)."""
+def mlp_wgrad_chain(g, x0_img, k0, acts, dout, inv_scale, dws, dbs, dw_head, row_count=None):
+    """the five weight gradients of one chain in ONE C call (nvsr_mlp_wgrad_chain[_rows]): layers 0..3 into dws[l]
+    [128, k] / dbs[l] [128], the head into dw_head [128, 16]; all accumulated into (zero them first).
+    row_count (device int32 [1]): the images are LIST-ordered (`compact_rows`); only the listed tiles are read."""
     lib = _lib.load()
     tiles = g[0].shape[0]
     P = C.c_void_p * 4
     with _OnDevice(dw_head.device):
-        st = _call("nvsr_mlp_wgrad_chain", lib.nvsr_mlp_wgrad_chain, P(*[t.data_ptr() for t in g]), _ptr(x0_img), k0,
-                   P(*[t.data_ptr() for t in acts]), _ptr(dout), tiles, float(inv_scale), P(*[t.data_ptr() for t in dws]),
+        st = _call("nvsr_mlp_wgrad_chain", lib.nvsr_mlp_wgrad_chain_rows, P(*[t.data_ptr() for t in g]), _ptr(x0_img), k0,
+                   P(*[t.data_ptr() for t in acts]), _ptr(dout), tiles, _ptr(row_count), float(inv_scale),
+                   P(*[t.data_ptr() for t in dws]),
                    (C.c_int64 * 4)(*[t.stride(0) for t in dws]), P(*[t.data_ptr() for t in dbs]), _ptr(dw_head), _stream(),
                    rows=tiles * TILE_ROWS, flops=tiles * TILE_ROWS * 2 * 128 * (k0 + 3 * 128 + 16),
                    bytes=tiles * TILE_ROWS * 2 * (9 * 128 + k0 + 16))
@@ -603,6 +640,50 @@ def ray_sum(img, n_rays, n_samples, inv_scale=1.0):
     with _OnDevice(img.device):
         st = _call("nvsr_ray_sum", lib.nvsr_ray_sum, _ptr(img), n_rays, n_samples, float(inv_scale), _ptr(out), _stream())
     _lib.check(st, "nvsr_ray_sum")
+    return out
+
+
+def nonzero_rows(d_raw):
+    """BLOCKED row ids whose raw gradient (planar [4, stride]) is not identically zero -> (row_ids int32 [stride],
+    count int32 [1]) on the device, order unspecified (nvsr_nonzero_rows)."""
+    lib = _lib.load()
+    rows = d_raw.shape[1]
+    ids = torch.empty((rows,), dtype=torch.int32, device=d_raw.device)
+    count = torch.empty((1,), dtype=torch.int32, device=d_raw.device)
+    with _OnDevice(d_raw.device):
+        st = _call("nvsr_nonzero_rows", lib.nvsr_nonzero_rows, _ptr(d_raw), d_raw.stride(0), rows, _ptr(ids), _ptr(count),
+                   _stream(), rows=rows, bytes=rows * 16)
+    _lib.check(st, "nvsr_nonzero_rows")
+    return ids, count
+
+
+def compact_rows(images, d_raw, ids, count):
+    """The listed rows of tile images [tiles, C/8, 128, 8] (16-bit) and of d_raw [4, stride], packed densely in LIST
+    order (nvsr_compact_rows; the last tile's tail is zero-filled).  -> (list of compact images, compact d_raw); tiles
+    past the list are left uninitialised."""
+    lib = _lib.load()
+    tiles = d_raw.shape[1] // TILE_ROWS
+    out = [torch.empty_like(t) for t in images]
+    d_out = torch.empty_like(d_raw)
+    k = len(images)
+    P = C.c_void_p * k
+    with _OnDevice(d_raw.device):
+        st = _call("nvsr_compact_rows", lib.nvsr_compact_rows, P(*[t.data_ptr() for t in images]), P(*[t.data_ptr() for t in out]),
+                   (C.c_int32 * k)(*[t.shape[1] * 8 for t in images]), k, _ptr(d_raw), d_raw.stride(0), _ptr(d_out),
+                   d_out.stride(0), _ptr(ids), _ptr(count), tiles, _stream(), rows=tiles * TILE_ROWS)
+    _lib.check(st, "nvsr_compact_rows")
+    return out, d_out
+
+
+def ray_sum_rows(img, ids, count, n_rays, n_samples, inv_scale=1.0, out=None):
+    """per-ray sums of a LIST-ordered 128-channel image -> [n_rays, 128] fp32 (accumulated into `out` when given)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.zeros((n_rays, 128), dtype=torch.float32, device=img.device)
+    with _OnDevice(img.device):
+        st = _call("nvsr_ray_sum_rows", lib.nvsr_ray_sum_rows, _ptr(img), _ptr(ids), _ptr(count), ids.numel(), n_samples,
+                   float(inv_scale), _ptr(out), _stream())
+    _lib.check(st, "nvsr_ray_sum_rows")
     return out
 
 
@@ -904,11 +985,13 @@ def mip_radius(scene_id):
 
 # ---------------------------------------------------------------------------------------------
 # backward of the memory-bound stages (include/nvsr.h "BACKWARD")
-def sample_gather_bwd(ro, rd, z, packed, d_feat_p, d_feat_m, d_planes=None):
+def sample_gather_bwd(ro, rd, z, packed, d_feat_p, d_feat_m, d_planes=None, rows=None):
     """Scatter-add of the row-major fp32 feature gradients into channels-last plane gradients [Rh,Rw,C] (x3).
 
     `packed` supplies the geometry (box, projections, plane sizes); its plane images are not read.  `d_planes`
-    (list of 3 tensors) are accumulated into when given, else allocated zeroed.  Returns the list."""
+    (list of 3 tensors) are accumulated into when given, else allocated zeroed.  Returns the list.
+    rows=(row_ids, count): the feature gradients are LIST-ordered ([len(row_ids), .]), row i belongs to BLOCKED row
+    row_ids[i] (nvsr_sample_gather_bwd_rows)."""
     lib = _lib.load()
     ro, rd, z = _f32c(ro), _f32c(rd), _f32c(z)
     _require_cuda(ro, "ray_origins")
@@ -919,15 +1002,20 @@ def sample_gather_bwd(ro, rd, z, packed, d_feat_p, d_feat_m, d_planes=None):
         d_planes = [torch.zeros((pl.rh[d], pl.rw[d], Cc), dtype=torch.float32, device=ro.device) for d in range(3)]
     gp = None if d_feat_p is None else _f32c(d_feat_p)
     gm = None if d_feat_m is None else _f32c(d_feat_m)
-    if gp is not None and tuple(gp.shape) != (n * S, 3 * Cc) or gm is not None and tuple(gm.shape) != (n * S, Cc):
-        raise _lib.NvsrError("sample_gather_bwd: feature gradients must be [n*S, 3C] / [n*S, C]")
+    nrow = n * S if rows is None else rows[0].numel()
+    if gp is not None and tuple(gp.shape) != (nrow, 3 * Cc) or gm is not None and tuple(gm.shape) != (nrow, Cc):
+        raise _lib.NvsrError("sample_gather_bwd: feature gradients must be [rows, 3C] / [rows, C]")
     s = _lib.Sampler()
     s.n_rays, s.n_samples = n, S
     s.ro, s.rd, s.z_in = ro.data_ptr(), rd.data_ptr(), z.data_ptr()
     ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in d_planes])
     with _OnDevice(ro.device):
-        st = _call("nvsr_sample_gather_bwd", lib.nvsr_sample_gather_bwd, C.byref(s), C.byref(pl), _ptr(gp), _ptr(gm), ptrs,
-                   _stream(), rows=n * S, bytes=n * S * (4 * Cc * 4 + 4))
+        if rows is None:
+            st = _call("nvsr_sample_gather_bwd", lib.nvsr_sample_gather_bwd, C.byref(s), C.byref(pl), _ptr(gp), _ptr(gm), ptrs,
+                       _stream(), rows=n * S, bytes=n * S * (4 * Cc * 4 + 4))
+        else:
+            st = _call("nvsr_sample_gather_bwd", lib.nvsr_sample_gather_bwd_rows, C.byref(s), C.byref(pl), _ptr(gp), _ptr(gm),
+                       _ptr(rows[0]), _ptr(rows[1]), nrow, ptrs, _stream(), rows=nrow)
     _lib.check(st, "nvsr_sample_gather_bwd")
     return d_planes
 

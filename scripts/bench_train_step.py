@@ -84,6 +84,19 @@ def torch_step(mc, mf, sid, ro, rd, vd, z, u, white):
     return rgb_c, rgb_f
 
 
+def timed_replay(graphed, args):
+    for _ in range(args.warmup):
+        graphed()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graphed()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / args.steps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=4096)
@@ -143,6 +156,13 @@ def main():
     A.set_decoder("tc")          # decoder forward + backward on tcgen05 (the default of the differentiable path)
     res["nvsr_ms"] = timed(nvsr_arm)
     g_n = [None if p.grad is None else p.grad.clone() for p in params]
+    # the same step captured once into a CUDA graph and replayed (autograd.GraphedStep): no host enqueue cost
+    graphed = A.GraphedStep(lambda: (zero(), nvsr_arm()))   # .grad set to None inside: the capture allocates the gradients
+    res["nvsr_graph_ms"] = timed_replay(graphed, args)
+    g_g = [None if p.grad is None else p.grad.clone() for p in params]
+    A.set_sparse_backward(False)
+    res["nvsr_dense_backward_ms"] = timed(nvsr_arm)
+    A.set_sparse_backward(True)
     A.set_decoder("fp32")        # fp32 parity mode: gather / compositing kernels + the model's nn.Linear under torch autograd
     res["nvsr_fp32_mode_ms"] = timed(nvsr_arm)
     g_f = [None if p.grad is None else p.grad.clone() for p in params]
@@ -152,6 +172,7 @@ def main():
 
     def rel_l2(x, y):
         return max(float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)) for a, b in zip(x, y) if a is not None and b is not None)
+    res["max_rel_l2_grad_diff_graph_vs_eager"] = rel_l2(g_g, g_n)
     res["max_rel_l2_grad_diff_tc_vs_torch"] = rel_l2(g_n, g_t)
     res["max_rel_l2_grad_diff_fp32_mode_vs_torch"] = rel_l2(g_f, g_t)
     ops.PROFILE = []

@@ -129,6 +129,51 @@ def test_dgrad_chain_vs_torch(k0, head_n, head_ch):
     assert float((d_x0 - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-12
 
 
+@pytest.mark.parametrize("k0,head_n,head_ch,frac", [(48, 1, 3, 0.25), (144, 3, 0, 0.6), (32, 1, 3, 0.004)])
+def test_dgrad_row_list_equals_dense_rows(k0, head_n, head_ch, frac):
+    """nvsr_mlp_dgrad in row-list mode (row_ids): every listed row gets bit for bit the deltas / d_x0 of the dense pass,
+    the LIST-ordered activation / feature images are the listed rows of the forward's images, the list tail is zero;
+    and the weight gradients over the list equal the dense ones to the order of the fp32 sums."""
+    n, S = 61, 40
+    W, B, hw, hb, x0, rows = _chain(4, k0, head_n, n_rays=n, S=S)
+    rb = (torch.randn(n, 128, generator=torch.Generator().manual_seed(6)) * 0.5).to(DEV).contiguous() if head_n == 3 else None
+    wimg, L = _layers(W, B, hw, hb, head_ch, rb)
+    raw = ops.raw_buffer(n, S, ops.ROWS_BLOCKED, DEV).zero_()
+    x0_img = rows_to_img(x0)
+    acts = ops.mlp_chain_train(x0_img, L, rows, raw, S, n)
+    g = torch.Generator().manual_seed(10)
+    d_rf = torch.zeros(n, S, 4)
+    d_rf[..., head_ch:head_ch + head_n] = torch.randn(n, S, head_n, generator=g) * 1e-4 * (torch.rand(n, S, 1, generator=g) < frac)
+    d_raw = ops.nsc_to_planar_blocked(d_rf.to(DEV), n, S)
+    scale = 1024.0
+    gd, doutd, dxd = ops.mlp_dgrad(wimg, k0, hw, head_ch, d_raw, scale, acts, n, S)
+    ids, count = ops.nonzero_rows(d_raw)
+    gl, doutl, dxl, acts_l, x0_l = ops.mlp_dgrad(wimg, k0, hw, head_ch, d_raw, scale, acts, n, S, row_count=count, row_ids=ids,
+                                                 x0_img=x0_img)
+    k = int(count)
+    assert 0 < k < n * S
+    kp = -(-k // 128) * 128
+    sel = ids[:k].long()
+    for l in range(4):
+        assert torch.equal(img_to_rows(gl[l])[:k], img_to_rows(gd[l])[sel]), l
+        assert not img_to_rows(gl[l])[k:kp].any()
+        assert torch.equal(img_to_rows(acts_l[l])[:k], img_to_rows(acts[l])[sel]) and not img_to_rows(acts_l[l])[k:kp].any()
+    assert torch.equal(img_to_rows(x0_l)[:k], x0[sel]) and not img_to_rows(x0_l)[k:kp].any()
+    assert torch.equal(img_to_rows(doutl)[:k], img_to_rows(doutd)[sel])
+    ts = -(-S // 16)
+    ray, smp = (sel // 128 // ts) * 8 + (sel % 8), (sel // 128 % ts) * 16 + (sel % 128) // 8
+    assert torch.equal(dxl[:k], dxd[ray * S + smp]) and not dxl[k:kp].any()
+    # weight gradients: the list's products == the dense products
+    def wgrads(gi, x0i, ai, do, rc):
+        dws = [torch.zeros(128, k0 if l == 0 else 128, device=DEV) for l in range(4)]
+        dbs = [torch.zeros(128, device=DEV) for _ in range(4)]
+        dwh = torch.zeros(128, 16, device=DEV)
+        ops.mlp_wgrad_chain(gi, x0i, k0, ai, do, 1.0 / scale, dws, dbs, dwh, row_count=rc)
+        return dws + dbs + [dwh]
+    for a, b in zip(wgrads(gl, x0_l, acts_l, doutl, count), wgrads(gd, x0_img, acts, doutd, None)):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
+
+
 @pytest.mark.parametrize("n_b", [16, 48, 128, 144])
 def test_wgrad_and_ray_sum_vs_torch(n_b):
     g = torch.Generator().manual_seed(n_b)
@@ -316,3 +361,150 @@ def test_frozen_decoder_step_gives_the_same_plane_gradients():
     assert set(g_frozen) == {k for k in g_all if "planes_" in k}
     for k in g_frozen:
         assert torch.equal(g_frozen[k], g_all[k]) or float((g_frozen[k] - g_all[k]).abs().max()) <= 1e-6 * float(g_all[k].abs().max()), k
+
+
+# ---- row-list ("sparse") backward: csrc/train_tc.cu nonzero_rows / compact_rows / *_rows ----------------------------
+@pytest.mark.parametrize("n_rays,S,frac", [(64, 40, 0.2), (19, 24, 0.9), (40, 64, 0.0)])
+def test_row_list_stages_vs_torch(n_rays, S, frac):
+    """nonzero_rows lists exactly the rows with a non-zero raw gradient; compact_rows moves those rows of tile images and
+    of d_raw to list order (tail of the last tile zero); ray_sum_rows adds the list rows to their rays."""
+    g = torch.Generator().manual_seed(n_rays + S)
+    rows = ops.rows_padded(n_rays, S, ops.ROWS_BLOCKED)
+    d_rf = torch.randn(n_rays, S, 4, generator=g) * (torch.rand(n_rays, S, 1, generator=g) < frac)
+    d_rf[0, 0, 2] = float("nan") if frac > 0 else 0.0          # NaN rows are listed
+    d_raw = ops.nsc_to_planar_blocked(d_rf.to(DEV), n_rays, S)
+    ids, count = ops.nonzero_rows(d_raw)
+    k = int(count)
+    want = torch.nonzero(((d_raw != 0) | d_raw.isnan()).any(0)).flatten()
+    assert k == want.numel()
+    got = ids[:k].long().sort().values
+    assert torch.equal(got, want)
+    imgs = [torch.randn(rows, c, generator=g).half().to(DEV) for c in (32, 128, 96)]
+    timgs = [rows_to_img(x.float()) for x in imgs]
+    cimgs, c_raw = ops.compact_rows(timgs, d_raw, ids, count)
+    kp = -(-k // 128) * 128
+    sel = ids[:k].long()
+    for x, ci in zip(imgs, cimgs):
+        r = img_to_rows(ci)
+        assert torch.equal(r[:k], x[sel].float())
+        assert not r[k:kp].any()
+    assert torch.equal(c_raw[:, :k].nan_to_num(7.0), d_raw[:, sel].nan_to_num(7.0)) and not c_raw[:, k:kp].any()
+    # ray sums of the 128-channel image in list order
+    out = ops.ray_sum_rows(cimgs[1], ids, count, n_rays, S, 0.5)
+    tile, r = sel // 128, sel % 128
+    ray = (tile // (-(-S // ops.BLK_SAMPLES))) * ops.BLK_RAYS + (r % ops.BLK_RAYS)
+    ref = torch.zeros(n_rays, 128, dtype=torch.float64, device=DEV).index_add_(0, ray, imgs[1][sel].double() * 0.5)
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("res,nc,nf,white,noise", [(32, 64, 128, True, 0.2), (19, 24, 40, False, 0.0)])
+def test_row_list_backward_equals_dense_backward(res, nc, nf, white, noise):
+    """The default backward of the 'tc' decoder visits only the samples with a non-zero raw gradient.  Same step, same
+    draws, with the row list on and off: every gradient agrees to the order of the fp32 sums (the per-row arithmetic
+    is the same kernels on the same operands), and the list is a strict subset of the samples."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=64, view_res=16, seed=0, device=DEV)
+    for m in (mc, mf):
+        m.train()
+    pose, focal = scene.blender_camera(res)
+    opt, scfg = scene.render_options(nc, nf, perturb=True, white_background=white, noise_std=noise), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(res, res, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    n = batch.shape[1]
+    g = torch.Generator().manual_seed(11)
+    rnd = dict(t_rand=torch.rand(n, nc, generator=g), u=torch.rand(n, nf, generator=g))
+    if noise:
+        rnd.update(noise_c=torch.randn(n, nc, generator=g), noise_f=torch.randn(n, nc + nf, generator=g))
+    target = torch.rand(n, 3, generator=g).to(DEV)
+    try:
+        A.set_sparse_backward(False)
+        ops.LAUNCHES.clear()
+        l_d, _, g_dense = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        assert ops.LAUNCHES.get("nvsr_nonzero_rows", 0) == 0
+        A.set_sparse_backward(True)
+        ops.LAUNCHES.clear()
+        l_s, _, g_rows = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        assert ops.LAUNCHES.get("nvsr_nonzero_rows", 0) == 2
+    finally:
+        A.set_sparse_backward(True)
+    assert l_d == l_s and set(g_dense) == set(g_rows)
+    for k in g_dense:
+        a, b = g_rows[k].double(), g_dense[k].double()
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, (k, float((a - b).abs().max()), float(b.abs().max()))
+
+
+def test_row_list_backward_with_no_gradient_rows():
+    """an all-zero upstream gradient: the list is empty, no tile is visited, every gradient is exactly zero"""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=32, view_res=8, seed=2, device=DEV)
+    pose, focal = scene.blender_camera(16)
+    opt, scfg = scene.render_options(24, 24, perturb=False), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(16, 16, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    for m in (mc, mf):
+        m.train()
+        for p in m.parameters():
+            p.grad = None
+    out = A.run_one_iter_of_nerf(16, 16, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg, randoms={})
+    ((out[0] * 0.0).sum() + (out[3] * 0.0).sum()).backward()
+    gs = [p.grad for m in (mc, mf) for p in m.parameters() if p.grad is not None]
+    assert gs and all(not bool(x.any()) for x in gs)
+
+
+def test_graphed_train_step_matches_eager_step():
+    """autograd.GraphedStep: the whole step (forward, sparse backward, SGD update) captured into a CUDA graph; replays
+    with new ray batches give the same losses and the same parameters as the eager loop from the same start (plain SGD:
+    an Adam update divides by |gradient| and turns the fp32 summation-order noise of near-zero entries into +-lr)."""
+    import copy
+    mc0, mf0, sid = scene.make_synthetic_scene(plane_res=48, view_res=12, seed=4, device=DEV)
+    res, nc, nf, n = 32, 32, 32, 512
+    pose, focal = scene.blender_camera(res)
+    opt, scfg = scene.render_options(nc, nf, perturb=True), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(res, res, focal, pose.to(DEV))
+    rays = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    g = torch.Generator().manual_seed(2)
+    steps = 6
+    picks = [torch.randperm(res * res, generator=g)[:n].to(DEV) for _ in range(steps)]
+    targets = [torch.rand(n, 3, generator=g).to(DEV) for _ in range(steps)]
+    draws = [dict(t_rand=torch.rand(n, nc, generator=g).to(DEV), u=torch.rand(n, nf, generator=g).to(DEV)) for _ in range(steps)]
+
+    def run(graphed):
+        mc, mf = copy.deepcopy(mc0), copy.deepcopy(mf0)
+        for m in (mc, mf):
+            m.train()
+        params = list({id(p): p for m in (mc, mf) for p in m.parameters() if p.requires_grad}.values())
+        optim = torch.optim.SGD(params, lr=0.2)
+        batch, target = rays[:, picks[0]].clone(), targets[0].clone()
+        rnd = {k: v.clone() for k, v in draws[0].items()}
+        snapshot = [p.detach().clone() for p in params]
+
+        def step():
+            optim.zero_grad(set_to_none=True)
+            out = A.run_one_iter_of_nerf(res, res, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg, randoms=rnd)
+            loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
+            loss.backward()
+            optim.step()
+            return loss
+        fn = step
+        if graphed:
+            fn = A.GraphedStep(step, warmup=2)
+            # the warm-up and the capture ran real updates: restart from the snapshot
+            with torch.no_grad():
+                for p, s0 in zip(params, snapshot):
+                    p.copy_(s0)
+        losses = []
+        for i in range(steps):
+            batch.copy_(rays[:, picks[i]]), target.copy_(targets[i])
+            for k in rnd:
+                rnd[k].copy_(draws[i][k])
+            losses.append(float(fn().detach()))
+        return losses, [p.detach().clone() for p in params], snapshot
+
+    le, pe, p0 = run(False)
+    lg, pg, _ = run(True)
+    assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(le, lg)), (le, lg)
+    moved = max(float((a - s0).abs().max()) for a, s0 in zip(pe, p0))
+    assert moved > 1e-4          # the six updates did something
+    for a, b, s0 in zip(pe, pg, p0):
+        assert float((a - b).abs().max()) <= 1e-3 * float((a - s0).abs().max()) + 1e-7
