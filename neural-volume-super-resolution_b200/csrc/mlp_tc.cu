@@ -629,11 +629,15 @@ mlp_chain_tc_kernel(const __grid_constant__ TcArgs a) {
       const int64_t ray0 = (tile / a.tiles_per_blk) * kBlkRays + 2 * (wi - 4);
       const uint32_t row_bytes = (uint32_t)(rl.n * 4);
       const int n_rows = ray0 + 1 < a.n_rays ? 2 : (ray0 < a.n_rays ? 1 : 0);
+      float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]) + 2 * (wi - 4) * kRbPitch;
+      // padding rays of the last ray block: a zero bias row, so that their (unused) activations stay finite — the dense
+      // weight gradient multiplies them by a zero delta, and 0 x Inf would poison the sum
+      for (int k = n_rows; k < 2; ++k)
+        for (int i = 0; i < rl.n; i += 4) *reinterpret_cast<float4*>(dst + k * kRbPitch + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n_rows == 0) {
         mbar_arrive(&bars[BAR_RB_FULL + s]);
       } else {
         mbar_arrive_expect_tx(&bars[BAR_RB_FULL + s], row_bytes * (uint32_t)n_rows);
-        float* dst = reinterpret_cast<float*>(smem + a.rb_off[s]) + 2 * (wi - 4) * kRbPitch;
         for (int k = 0; k < n_rows; ++k)
           bulk_g2s(dst + k * kRbPitch, rl.row_bias + (ray0 + k) * rl.n, row_bytes, &bars[BAR_RB_FULL + s]);
       }
