@@ -100,9 +100,11 @@ int32_t nvsr_pack_plane(const float* src_nchw, int32_t channels, int32_t rh, int
  * [k_pad/8][n_out][8], zero-padded for k <= kk < k_pad.  k_pad % 16 == 0. */
 int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, int32_t ldw, int32_t k_pad,
                            void* dst, int32_t dst_dtype, void* stream);
-/* `count` weights in one call (same arguments as nvsr_pack_weight16, as arrays) */
+/* `count` weights in one call and one launch per 8 (same arguments as nvsr_pack_weight16, as arrays).  absmax (device
+ * fp32, may be NULL): max(*absmax, max |w| of everything packed) is left there (atomic on the bit pattern: start it at
+ * 0; a NaN weight leaves a NaN) — the fp16 range check of a step that re-packs its weights, without a host read. */
 int32_t nvsr_pack_weights16(int32_t count, const float* const* w, const int32_t* n_out, const int32_t* k, const int32_t* ldw,
-                            const int32_t* k_pad, void* const* dst, int32_t dst_dtype, void* stream);
+                            const int32_t* k_pad, void* const* dst, int32_t dst_dtype, float* absmax, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a4 + a5  stratified sampler (train_utils.py:95-111) fused with the tri-plane bilinear gather of

@@ -221,7 +221,7 @@ SIGNATURES = {
     "nvsr_sample_gather_bwd_rows": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), c_p, c_p, c_p, c_p, c_i64, C.POINTER(c_p),
                                             c_p]),
     "nvsr_pack_weights16": (c_i32, [c_i32, C.POINTER(c_p), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32),
-                                    C.POINTER(c_p), c_i32, c_p]),
+                                    C.POINTER(c_p), c_i32, c_p, c_p]),
     "nvsr_composite": (c_i32, [C.POINTER(Composite), c_p]),
     "nvsr_sample_pdf": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "nvsr_ipe": (c_i32, [c_p, c_p, c_p, c_i64, c_i32, c_f, c_i32, c_i32, c_i32, c_p, c_p]),

@@ -145,6 +145,40 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int n_out, int k
   dst[idx] = OutT(v);
 }
 
+// up to 8 weights in one launch (blockIdx.y = which); optionally the maximum |w| of everything packed is folded into
+// *absmax (non-negative floats order like their bit patterns; a NaN compares above +Inf) — the fp16 range check of a
+// training step without separate reduction kernels
+struct PackWeightsArgs {
+  const float* w[8];
+  void* dst[8];
+  int n_out[8], k[8], ldw[8], k_pad[8];
+  float* absmax;
+};
+template <typename OutT>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackWeightsArgs a) {
+  const int i = blockIdx.y;
+  const int n_out = a.n_out[i], k = a.k[i], k_pad = a.k_pad[i];
+  const float* __restrict__ w = a.w[i];
+  OutT* __restrict__ dst = reinterpret_cast<OutT*>(a.dst[i]);
+  const int total = n_out * k_pad;
+  float m = 0.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int e = idx & 7;
+    const int n = (idx >> 3) % n_out;
+    const int kk = ((idx >> 3) / n_out) * 8 + e;
+    const float v = kk < k ? w[(int64_t)n * a.ldw[i] + kk] : 0.f;
+    dst[idx] = OutT(v);
+    const float av = fabsf(v);
+    m = (av > m || av != av) ? av : m;
+  }
+  if (a.absmax) {
+    int bits = __float_as_int(m) & 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+    if ((threadIdx.x & 31) == 0 && bits > 0) atomicMax(reinterpret_cast<int*>(a.absmax), bits);
+  }
+}
+
 // a5 (view half): one thread per (ray, 4-channel chunk)
 __global__ void viewdir_gather_kernel(const float* __restrict__ viewdirs, int64_t n, const float* __restrict__ vplane,
                                       int rh, int rw, int C, float az_lo, float az_rng, float el_lo, float el_rng,
@@ -374,13 +408,26 @@ extern "C" int32_t nvsr_pack_weight16(const float* w, int32_t n_out, int32_t k, 
 
 extern "C" int32_t nvsr_pack_weights16(int32_t count, const float* const* w, const int32_t* n_out, const int32_t* k,
                                        const int32_t* ldw, const int32_t* k_pad, void* const* dst, int32_t dst_dtype,
-                                       void* stream) {
+                                       float* absmax, void* stream) {
   NVSR_CHECK_ARG(count >= 0 && (count == 0 || (w && n_out && k && ldw && k_pad && dst)));
-  for (int32_t i = 0; i < count; ++i) {
-    int32_t st = nvsr_pack_weight16(w[i], n_out[i], k[i], ldw[i], k_pad[i], dst[i], dst_dtype, stream);
-    if (st != NVSR_OK) return st;
+  NVSR_CHECK_ARG(dst_dtype == NVSR_BF16 || dst_dtype == NVSR_F16);
+  for (int32_t base = 0; base < count; base += 8) {
+    PackWeightsArgs a;
+    const int n = count - base < 8 ? count - base : 8;
+    int max_total = 0;
+    for (int i = 0; i < n; ++i) {
+      const int j = base + i;
+      NVSR_CHECK_ARG(w[j] && dst[j] && n_out[j] > 0 && k[j] > 0 && ldw[j] >= k[j] && k_pad[j] >= k[j] && (k_pad[j] % 16) == 0);
+      a.w[i] = w[j], a.dst[i] = dst[j], a.n_out[i] = n_out[j], a.k[i] = k[j], a.ldw[i] = ldw[j], a.k_pad[i] = k_pad[j];
+      const int total = n_out[j] * k_pad[j];
+      max_total = total > max_total ? total : max_total;
+    }
+    a.absmax = absmax;
+    const dim3 grid((unsigned)((max_total + 255) / 256), (unsigned)n);
+    if (dst_dtype == NVSR_BF16) pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else pack_weights_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   }
-  return NVSR_OK;
+  NVSR_RETURN_LAST_ERROR();
 }
 
 extern "C" int32_t nvsr_viewdir_gather(const float* viewdirs, int64_t n_rays, const float* vplane, int32_t rh,

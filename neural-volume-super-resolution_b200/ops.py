@@ -189,6 +189,17 @@ class DeferredRangeCheck:
         self.cur = []
         self.graph_max = None    # running maximum kept on the device by steps replayed from a CUDA graph
         self.graph_what = ""
+        self.dev = {}            # device -> fp32 scalar the pack kernels fold max |value| into (`absmax` arguments)
+        self.dev_used = []
+
+    def device_max(self, device, what):
+        """the device scalar a C entry with an `absmax` argument accumulates into; counts as an `add` of this step"""
+        device = torch.device(device)
+        t = self.dev.get(device)
+        if t is None:
+            t = self.dev[device] = torch.zeros((), dtype=torch.float32, device=device)
+        self.dev_used.append((t, what))
+        return t
 
     def add(self, t, what):
         self.cur.append((t.detach().abs().max(), what))
@@ -196,7 +207,10 @@ class DeferredRangeCheck:
     def commit(self):
         if torch.cuda.is_current_stream_capturing():
             # a step being captured into a CUDA graph: no events, no host copies — fold the maximum into a device scalar
-            # that `check_graph()` reads between replays
+            # that `check_graph()` reads between replays (the pack kernels' own accumulators just keep accumulating)
+            if self.dev_used:
+                self.graph_what = ", ".join(sorted({w for _, w in self.dev_used} | ({self.graph_what} if self.graph_what else set())))
+                self.dev_used = []
             if self.cur:
                 m = torch.stack([v.float() for v, _ in self.cur]).max()
                 self.graph_what = ", ".join(sorted({w for _, w in self.cur}))
@@ -206,17 +220,20 @@ class DeferredRangeCheck:
                 self.graph_max.copy_(torch.maximum(self.graph_max, m))
             return
         self.poll()
-        if not self.cur:
+        if not self.cur and not self.dev_used:
             return
-        m = torch.stack([v.float() for v, _ in self.cur]).max()
-        what = ", ".join(sorted({w for _, w in self.cur}))
-        self.cur = []
+        vals = [v.float() for v, _ in self.cur] + [t for t, _ in {id(t): (t, w) for t, w in self.dev_used}.values()]
+        m = vals[0] if len(vals) == 1 else torch.stack(vals).max()
+        what = ", ".join(sorted({w for _, w in self.cur} | {w for _, w in self.dev_used}))
+        used, self.cur, self.dev_used = self.dev_used, [], []
         if self.pending is None:         # at most one check in flight; a step whose check is skipped is covered by the next
             host = torch.empty((), dtype=torch.float32).pin_memory()
             host.copy_(m, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             self.pending = (host, ev, what)
+            for t in {id(t): t for t, _ in used}.values():
+                t.zero_()        # a skipped copy leaves the accumulator running: the next check still sees its maximum
 
     def poll(self, wait=False):
         if self.pending is None:
@@ -226,7 +243,7 @@ class DeferredRangeCheck:
             ev.synchronize()
         if ev.query():
             self.pending = None
-            if float(host) > F16_MAX:
+            if not (float(host) <= F16_MAX):
                 raise _lib.NvsrError(f"{what}: |value| exceeded the fp16 range ({F16_MAX:g}) in the previous step; values "
                                      "saturated silently - use the fp32 decoder mode for this model")
 
@@ -235,7 +252,8 @@ class DeferredRangeCheck:
 
     def check_graph(self):
         """host read (synchronises) of the maximum accumulated by graph replays; raises like `poll`"""
-        if self.graph_max is not None and float(self.graph_max) > F16_MAX:
+        vals = ([self.graph_max] if self.graph_max is not None else []) + list(self.dev.values())
+        if any(not (float(v) <= F16_MAX) for v in vals):
             raise _lib.NvsrError(f"{self.graph_what}: |value| exceeded the fp16 range ({F16_MAX:g}) in a replayed step; values "
                                  "saturated silently - use the fp32 decoder mode for this model")
 
@@ -616,19 +634,19 @@ def pack_weights16(weights, dtype=NVSR_F16, range_check=None):
         _require_cuda(w, "weight")
         if w.dtype != torch.float32 or w.stride(1) != 1:
             w = w.float().contiguous()
-        if dtype == NVSR_F16:
-            if range_check is None:
-                _check_f16_range(w, "pack_weights16")
-            else:
-                range_check.add(w, "pack_weights16")
+        if dtype == NVSR_F16 and range_check is None:
+            _check_f16_range(w, "pack_weights16")
         ws.append(w)
         outs.append(torch.empty(((w.shape[1] + 15) // 16 * 2, w.shape[0], 8), dtype=TORCH_DTYPE[dtype], device=w.device))
     n = len(ws)
     I = C.c_int32 * n
+    # the deferred range check rides in the pack kernel (one atomic max per warp) instead of an abs().max() per weight
+    absmax = range_check.device_max(ws[0].device, "pack_weights16") if (dtype == NVSR_F16 and range_check is not None) else None
     with _OnDevice(ws[0].device):
         st = _call("nvsr_pack_weights16", lib.nvsr_pack_weights16, n, (C.c_void_p * n)(*[w.data_ptr() for w in ws]),
                    I(*[w.shape[0] for w in ws]), I(*[w.shape[1] for w in ws]), I(*[w.stride(0) for w in ws]),
-                   I(*[(w.shape[1] + 15) // 16 * 16 for w in ws]), (C.c_void_p * n)(*[o.data_ptr() for o in outs]), dtype, _stream())
+                   I(*[(w.shape[1] + 15) // 16 * 16 for w in ws]), (C.c_void_p * n)(*[o.data_ptr() for o in outs]), dtype,
+                   _ptr(absmax), _stream())
     _lib.check(st, "nvsr_pack_weights16")
     return outs
 

@@ -508,3 +508,34 @@ def test_graphed_train_step_matches_eager_step():
     assert moved > 1e-4          # the six updates did something
     for a, b, s0 in zip(pe, pg, p0):
         assert float((a - b).abs().max()) <= 1e-3 * float((a - s0).abs().max()) + 1e-7
+
+
+def test_pack_weights16_one_launch_and_deferred_range_check():
+    """nvsr_pack_weights16: every image equals nvsr_pack_weight16's, one launch for the lot, and the maximum |w| lands in
+    the device scalar of the deferred fp16 range check — which raises one step late (or at flush) without any host read
+    inside the step."""
+    g = torch.Generator().manual_seed(0)
+    big = torch.randn(128, 160, generator=g).to(DEV)
+    ws = [torch.randn(128, 48, generator=g).to(DEV), big[:, :144], torch.randn(128, 128, generator=g).to(DEV) * 3.0,
+          torch.randn(3, 128, generator=g).to(DEV)]
+    rc = ops.DeferredRangeCheck()
+    ops.LAUNCHES.clear()
+    imgs = ops.pack_weights16(ws, NVSR_F16, range_check=rc)
+    assert ops.LAUNCHES.get("nvsr_pack_weights16") == 1
+    for w, im in zip(ws, imgs):
+        assert torch.equal(im, ops.pack_weight16(w.contiguous(), dtype=NVSR_F16))
+    want = max(float(w.abs().max()) for w in ws)
+    assert float(rc.dev[torch.device(DEV)]) == want
+    rc.commit()
+    rc.flush()                                   # in range: silent
+    assert float(rc.dev[torch.device(DEV)]) == 0.0
+    ws[2][5, 7] = 1.0e5
+    ops.pack_weights16(ws, NVSR_F16, range_check=rc)
+    rc.commit()
+    with pytest.raises(nvsr_b200.NvsrError, match="fp16 range"):
+        rc.flush()
+    ws[2][5, 7] = float("nan")
+    ops.pack_weights16(ws, NVSR_F16, range_check=rc)
+    rc.commit()
+    with pytest.raises(nvsr_b200.NvsrError, match="fp16 range"):
+        rc.flush()
