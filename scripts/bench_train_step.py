@@ -103,6 +103,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--plane-res", type=int, default=200)
+    ap.add_argument("--no-torch", action="store_true", help="only the eager 'tc' arm (for a profiler's launch list)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     mc, mf, sid = scene.make_synthetic_scene(plane_res=args.plane_res, view_res=32, seed=0, device=dev)
@@ -155,6 +156,9 @@ def main():
     res = {"rays": args.rays, "samples": [Nc, Nf], "plane_res": args.plane_res}
     A.set_decoder("tc")          # decoder forward + backward on tcgen05 (the default of the differentiable path)
     res["nvsr_ms"] = timed(nvsr_arm)
+    if args.no_torch:
+        print(json.dumps(res))
+        return
     g_n = [None if p.grad is None else p.grad.clone() for p in params]
     # the same step captured once into a CUDA graph and replayed (autograd.GraphedStep): no host enqueue cost
     graphed = A.GraphedStep(lambda: (zero(), nvsr_arm()))   # .grad set to None inside: the capture allocates the gradients
