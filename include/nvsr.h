@@ -410,8 +410,12 @@ typedef struct nvsr_dgrad {
   void* act_list[4];        /* ... the listed rows of x_1..x_4 here in LIST order (out; the weight gradients' operands) */
   const void* x0_img;       /* optional (both or neither): the forward's k0-channel feature image and ... */
   void* x0_list;            /* ... its listed rows in LIST order (out) */
+  int32_t acts_listed;      /* with row_ids: 1 = act is LIST-ordered already (nvsr_mlp_chain_train over the same list);
+                             * only d_raw is read through the list and act_list / x0_list are not written */
 } nvsr_dgrad_t;
 
+/* mlp->row_ids / row_count (the rgb chain only): the sparse colour path of the forward — input row i stands for BLOCKED
+ * row row_ids[i], the heads go to that row of raw, and act_out comes out in LIST order. */
 int32_t nvsr_mlp_chain_train(const nvsr_mlp_t* mlp, void* const* act_out, void* stream);
 int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* args, void* stream);
 int32_t nvsr_mlp_wgrad(const void* a_img, const void* b_img, int32_t n_b, int64_t n_tiles, float inv_scale, float* dw,

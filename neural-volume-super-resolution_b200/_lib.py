@@ -103,6 +103,7 @@ class Dgrad(C.Structure):
         ("act_list", c_p * 4),
         ("x0_img", c_p),
         ("x0_list", c_p),
+        ("acts_listed", c_i32),
     ]
 
 

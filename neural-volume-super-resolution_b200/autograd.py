@@ -20,7 +20,8 @@ from . import _lib, ops
 from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
 
 
-_state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0, "sparse_backward": True}
+_state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0, "sparse_backward": True, "sparse_forward": True}
+_DENSE = "dense"     # planes_model_forward's default for sigma_noise: the caller does not say what the compositing will add
 
 
 def set_sparse_backward(flag):
@@ -29,6 +30,14 @@ def set_sparse_backward(flag):
     alpha = 0 or transmittance 0 and add nothing to any gradient.  False: every sample goes through the backward chains.
     The two give the same gradients up to the order of the fp32 sums."""
     _state["sparse_backward"] = bool(flag)
+
+
+def set_sparse_forward(flag):
+    """True (default): when the caller of `planes_model_forward` tells it the density noise the compositing will add
+    (`run_one_iter_of_nerf` does), the 'tc' decoder's rgb chain runs — forward and backward — over the samples with
+    relu(sigma + noise) > 0 only, exactly as the inference path's sparse colour path does; the other samples have weight
+    exactly 0 (volume_rendering_utils.py:29-44), their rgb is returned as 0.  Needs the row-list backward."""
+    _state["sparse_forward"] = bool(flag)
 
 
 def set_decoder(mode):
@@ -205,7 +214,8 @@ class PlanesRadianceTC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, p0, p1, p2, pv, *rest):
-        params, (ro, rd, z, vd, geom) = rest[:20], rest[20:]
+        params, (ro, rd, z, vd, geom, sigma_noise) = rest[:20], rest[20:]
+        sparse_fwd = sigma_noise is not _DENSE and _state["sparse_forward"] and _state["sparse_backward"]
         dW, dB = params[0:8:2], params[1:8:2]
         aW, aB = params[8], params[9]
         cW, cB = params[10:18:2], params[11:18:2]
@@ -215,7 +225,7 @@ class PlanesRadianceTC(torch.autograd.Function):
         F16 = ops.NVSR_F16
         packed = ops.PackedPlanes([_packed16(p) for p in (p0, p1, p2)], F16, geom.box_lo, geom.box_rng, geom.proj,
                                   _cl_image(pv), geom.view_lo_rng, combine=geom.combine)
-        feat_p, feat_m, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, ops.FEAT_TILE_F16, z_in=z)
+        feat_p, feat_m, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, ops.FEAT_TILE_F16, z_in=z, density_only=sparse_fwd)
         vfeat = ops.viewdir_gather(vd, packed)
         rb = ops.row_bias(vfeat, cW[0].detach()[:, C3:], cB[0])
         f = lambda t: t.detach().float().contiguous()
@@ -230,8 +240,19 @@ class PlanesRadianceTC(torch.autograd.Function):
         rows = ops.rows_padded(n, S, ops.ROWS_BLOCKED)
         raw = ops.raw_buffer(n, S, ops.ROWS_BLOCKED, ro.device)
         acts_d = ops.mlp_chain_train(feat_m, Ld, rows, raw, S, n)
-        acts_c = ops.mlp_chain_train(feat_p, Lc, rows, raw, S, n)
-        ctx.save_for_backward(ro, rd, z, vd, vfeat, feat_p, feat_m, *acts_d, *acts_c, *wd, *wc, aW, rW, cW[0])
+        keep = count = None
+        if sparse_fwd:
+            # sparse colour path: only the samples whose density (+ the noise the compositing adds) is positive can
+            # reach the maps; their 3-plane features are gathered and decoded in LIST order, the others' rgb stays 0
+            raw[:3].zero_()
+            keep, count = ops.keep_rows(raw, n, S, sigma_noise)
+            feat_p = ops.sample_gather_rows(ro, rd, packed, ops.FEAT_TILE_F16, z, keep, count)
+            acts_c = ops.mlp_chain_train(feat_p, Lc, rows, raw, S, n, row_ids=keep, row_count=count)
+        else:
+            acts_c = ops.mlp_chain_train(feat_p, Lc, rows, raw, S, n)
+        ctx.fwd_list = sparse_fwd
+        extra = (keep, count) if sparse_fwd else ()
+        ctx.save_for_backward(ro, rd, z, vd, vfeat, feat_p, feat_m, *acts_d, *acts_c, *wd, *wc, aW, rW, cW[0], *extra)
         ctx.geom, ctx.shapes = geom, [tuple(p.shape) for p in (p0, p1, p2, pv)]
         ctx.scale = _state["loss_scale"]
         ctx.set_materialize_grads(False)
@@ -248,12 +269,17 @@ class PlanesRadianceTC(torch.autograd.Function):
         Cc = ctx.shapes[0][1]
         C3 = 3 * Cc
         if d_rf is None:
-            return (None,) * (4 + 20 + 5)
+            return (None,) * (4 + 20 + 6)
         scale, inv = ctx.scale, 1.0 / ctx.scale
         d_rf = d_rf.float()
         d_raw = ops.nsc_to_planar_blocked(d_rf, n, S)
         rows = ids = count = None
-        if _state["sparse_backward"]:
+        if ctx.fwd_list:
+            # the forward's own list (sigma + noise > 0): a superset of the rows with a non-zero raw gradient, and the
+            # order the rgb chain's images are already in
+            ids, count = t[26], t[27]
+            rows = (ids, count)
+        elif _state["sparse_backward"]:
             # the rows that carry a gradient: the data-gradient chains gather them through the list and leave
             # LIST-ordered copies of the forward's images for the weight gradients
             ids, count = ops.nonzero_rows(d_raw)
@@ -289,6 +315,9 @@ class PlanesRadianceTC(torch.autograd.Function):
         # ---- rgb chain (its first layer's view-feature columns are a per-ray bias in the forward)
         if rows is None:
             g, dout, d_fp = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S)
+        elif ctx.fwd_list:
+            g, dout, d_fp, _, _ = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S, row_count=count, row_ids=ids,
+                                                acts_listed=True)
         else:
             g, dout, d_fp, acts_c, feat_p = ops.mlp_dgrad(wc, C3, rW, 0, d_raw, scale, acts_c, n, S, row_count=count, row_ids=ids,
                                                           x0_img=feat_p if want_w else None)
@@ -317,7 +346,7 @@ class PlanesRadianceTC(torch.autograd.Function):
             ops.viewdir_gather_bwd(vd, vshell, d_v, vacc)
             vgrad = vacc.permute(2, 0, 1).reshape(sv)
         pg = [a.permute(2, 0, 1).reshape(s) for a, s in zip(acc, ctx.shapes[:3])] + [vgrad]
-        out = pg + dens + col + [None] * 5
+        out = pg + dens + col + [None] * 6
         return tuple(o if (o is None or needs[i]) else None for i, o in enumerate(out))
 
 
@@ -367,9 +396,9 @@ def _tc_supported(model):
         and model.fc_alpha["0"].out_features == 1 and model.fc_rgb["0"].out_features == 3
 
 
-def _render(radiance_field, depth_values, ray_directions, noise_std, white_background, noise, mip=False):
-    nz = None
-    if noise_std > 0.0:
+def _render(radiance_field, depth_values, ray_directions, noise_std, white_background, noise, mip=False, nz=None):
+    """nz: the density noise ALREADY scaled by the std (what `planes_model_forward(sigma_noise=)` was given)"""
+    if nz is None and noise_std > 0.0:
         if noise is None:
             noise = torch.randn(radiance_field[..., 3].shape)
         nz = (noise * noise_std).to(radiance_field).contiguous()
@@ -387,10 +416,14 @@ def volume_render_radiance_field(radiance_field, depth_values, ray_directions, r
     return _render(radiance_field, depth_values, ray_directions, radiance_field_noise_std, white_background, noise, mip_nerf)
 
 
-def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
+def planes_model_forward(model, scene_id, ro, rd, z, viewdirs, sigma_noise=_DENSE):
     """TwoDimPlanesModel.forward (models.py:381-421) for the points ro + rd*z of n rays x S samples with the gather
     done by the Functions above and the decoder by the model's own nn.Linear layers under torch autograd.
     Returns radiance_field [n,S,4].  Gradients reach the model's planes_ parameters and decoder weights.
+    sigma_noise (the 'tc' decoder only): what the compositing will add to the density before its relu — None (nothing) or
+    the [n,S] noise already scaled by radiance_field_noise_std.  When given, the rgb chain runs over the samples with
+    relu(sigma + noise) > 0 only (`set_sparse_forward`) and the rgb of the others — weight exactly 0 in
+    volume_render_radiance_field — is returned as 0 instead of the decoder's value.  Default: every sample is decoded.
     Not reproduced: the region-of-interest SR of a TRAINING SR model (models.py:277-280 crops the SR input to the
     footprint of the batch; here the whole plane is super-resolved, which differs near the crop borders)."""
     from . import scene
@@ -409,8 +442,10 @@ def planes_model_forward(model, scene_id, ro, rd, z, viewdirs):
         for seq in (model.density_dec["0"], [model.fc_alpha["0"]], model.rgb_dec["0"], [model.fc_rgb["0"]]):
             for lin in seq:
                 params += [lin.weight, lin.bias]
+        if sigma_noise is not _DENSE and sigma_noise is not None:
+            sigma_noise = sigma_noise.to(device=ro.device, dtype=torch.float32).contiguous()
         return PlanesRadianceTC.apply(planes[0], planes[1], planes[2], planes[3], *params, ro.contiguous(), rd.contiguous(),
-                                      z.contiguous(), viewdirs.contiguous(), geom)
+                                      z.contiguous(), viewdirs.contiguous(), geom, sigma_noise)
     feat_p, feat_m = TriPlaneGather.apply(planes[0], planes[1], planes[2], ro, rd, z, geom)
     vfeat = ViewdirGather.apply(planes[3], viewdirs, geom)
     h = feat_m
@@ -506,9 +541,11 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
     std = float(cfg.radiance_field_noise_std)
 
     def noise_of(name, S):
+        """the density noise of one pass, scaled by the std, on the device (volume_rendering_utils.py:30-35)"""
         if std <= 0.0:
             return None
-        return randoms[name] if name in randoms else torch.randn((n, S))
+        nse = randoms[name] if name in randoms else torch.randn((n, S))     # the reference draws on the CPU
+        return (nse * std).to(device=dev, dtype=torch.float32).contiguous()
 
     def radiance(model, z_edges):
         S = z_edges.shape[1] - 1
@@ -519,7 +556,7 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
 
     with _coarse_context(model_coarse):
         rf = radiance(model_coarse, z)
-        rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc), mip=True)
+        rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, 0.0, cfg.white_background, None, mip=True, nz=noise_of("noise_c", Nc))
     rgb_f = disp_f = acc_f = None
     if Nf > 0:
         with torch.no_grad():
@@ -533,8 +570,8 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
             if "z_fine" in randoms:     # test hook: teacher-forced merged depths
                 z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
         rf_f = radiance(model_fine, z_f)
-        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background,
-                                             noise_of("noise_f", z_f.shape[1] - 1), mip=True)
+        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, 0.0, cfg.white_background, None, mip=True,
+                                             nz=noise_of("noise_f", z_f.shape[1] - 1))
     return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, None, None, None
 
 
@@ -578,9 +615,11 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
     std = float(cfg.radiance_field_noise_std)
 
     def noise_of(name, S):
+        """the density noise of one pass, scaled by the std, on the device (volume_rendering_utils.py:30-35)"""
         if std <= 0.0:
             return None
-        return randoms[name] if name in randoms else torch.randn((n, S))
+        nse = randoms[name] if name in randoms else torch.randn((n, S))     # the reference draws on the CPU
+        return (nse * std).to(device=dev, dtype=torch.float32).contiguous()
 
     z_f = None
     if _state["fast_frozen_coarse"] and getattr(model_coarse, "optional_no_grad", None) is torch.no_grad:
@@ -596,12 +635,14 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
     else:
         z = coarse_depths()
         with _coarse_context(model_coarse):
-            rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd)
-            rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, std, cfg.white_background, noise_of("noise_c", Nc))
+            nz = noise_of("noise_c", Nc)
+            rf = planes_model_forward(model_coarse, scene_id, ro, rd, z, vd, sigma_noise=nz)
+            rgb_c, disp_c, acc_c, weights, _ = _render(rf, z, rd, 0.0, cfg.white_background, None, nz=nz)
     rgb_f = disp_f = acc_f = None
     if Nf > 0 and z_f is not None:
-        rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd)
-        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background, noise_of("noise_f", Nc + Nf))
+        nz = noise_of("noise_f", Nc + Nf)
+        rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd, sigma_noise=nz)
+        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, 0.0, cfg.white_background, None, nz=nz)
     elif Nf > 0:
         with torch.no_grad():    # z_samples.detach() (train_utils.py:153)
             mid = 0.5 * (z[..., 1:] + z[..., :-1])
@@ -614,6 +655,7 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
                 z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
             if isinstance(randoms.get("trace"), dict):
                 randoms["trace"]["z_fine"] = z_f
-        rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd)
-        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, std, cfg.white_background, noise_of("noise_f", Nc + Nf))
+        nz = noise_of("noise_f", Nc + Nf)
+        rf_f = planes_model_forward(model_fine, scene_id, ro, rd, z_f, vd, sigma_noise=nz)
+        rgb_f, disp_f, acc_f, _, _ = _render(rf_f, z_f, rd, 0.0, cfg.white_background, None, nz=nz)
     return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, None, None, None

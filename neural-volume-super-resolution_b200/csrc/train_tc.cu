@@ -116,6 +116,8 @@ struct DgradArgs {
   uint8_t* act_c[4];          //   and their listed rows are written out in LIST order for the weight gradients
   const uint8_t* x0;          //   (act_c: x_1..x_4, x0_c: the k0-channel feature image).  NULL: act / d_raw are
   uint8_t* x0_c;              //   LIST-ordered already (nvsr_compact_rows)
+  int acts_listed;            // with row_ids: only d_raw is read through the list, act is LIST-ordered already (the sparse
+                              //   training forward wrote it so); no copies are written
 };
 
 // this thread's mask words: the 64 activations of image row `src` (< 0: a zero row), columns [col0, col0 + 64), eight per
@@ -235,6 +237,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
       if (!a.row_ids) return i;
       return i < listed_rows ? (int64_t)__ldg(a.row_ids + i) : -1;
     };
+    const bool copy_acts = a.row_ids && !a.acts_listed;
+    // the row of the activation images that belongs to list row (tile, r) whose buffer row is `src`
+    auto act_row = [&](int64_t tile, int64_t src) -> int64_t {
+      return (a.acts_listed && src >= 0) ? tile * kTileRows + r : src;
+    };
     auto prep_tile = [&](int s, int64_t tile) {
       const uint32_t a_tmem = lane_base + (uint32_t)s * kDgSlotCols + kDgAOff + (uint32_t)(col0 >> 1);
       const int64_t src = src_row(tile);
@@ -243,8 +250,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
       for (int h = 0; h < 4; ++h)
         dv[h] = (h < a.head_n && src >= 0) ? __ldg(a.d_raw + (int64_t)(a.head_ch + h) * a.raw_stride + src) * a.scale : 0.f;
       uint4 m[8];
-      load_mask64(a.act[3], src, col0, m, a.row_ids ? a.act_c[3] : nullptr, tile, r);
-      if (a.row_ids && a.x0_c) {   // the feature image's listed rows, for the layer-0 weight gradient
+      load_mask64(a.act[3], act_row(tile, src), col0, m, copy_acts ? a.act_c[3] : nullptr, tile, r);
+      if (copy_acts && a.x0_c) {   // the feature image's listed rows, for the layer-0 weight gradient
         const int chunks = a.k0 >> 3, c_half = (chunks + 1) >> 1;
         const int c0 = half == 0 ? 0 : c_half, c1 = half == 0 ? c_half : chunks;
         const uint4* px = reinterpret_cast<const uint4*>(a.x0) + (src >= 0 ? (src >> 7) * chunks * kTileRows + (src & 127) : 0);
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) dgrad_chain_kernel(const __grid
           const uint32_t a_tmem = d_tmem + kDgAOff + (uint32_t)(col0 >> 1);
           // the mask of the layer below does not depend on the accumulator: fetch it while the MMAs run
           uint4 m[8];
-          if (l > 0) load_mask64(a.act[l - 1], src_row(tile), col0, m, a.row_ids ? a.act_c[l - 1] : nullptr, tile, r);
+          if (l > 0) load_mask64(a.act[l - 1], act_row(tile, src_row(tile)), col0, m, copy_acts ? a.act_c[l - 1] : nullptr, tile, r);
           mbar_wait(&bar_mma[s], ph[s]);
           ph[s] ^= 1u;
           tc_fence_after();
@@ -635,8 +642,9 @@ extern "C" int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* d, void* stream) {
   a.n_tiles = ceil_div64(d->n_rays, kBlkRays) * a.tiles_per_blk;
   a.row_count = d->row_count, a.row_ids = d->row_count ? d->row_ids : nullptr;
   a.x0 = nullptr, a.x0_c = nullptr;
+  a.acts_listed = (a.row_ids && d->acts_listed) ? 1 : 0;
   for (int l = 0; l < 4; ++l) a.act_c[l] = nullptr;
-  if (a.row_ids) {
+  if (a.row_ids && !a.acts_listed) {
     for (int l = 0; l < 4; ++l) {
       NVSR_CHECK_ARG(d->act_list[l]);
       if (!aligned16(d->act_list[l])) return NVSR_ERR_ALIGNMENT;

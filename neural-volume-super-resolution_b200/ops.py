@@ -539,11 +539,12 @@ def mlp_chain_split(feat, w_hi, w_lo, biases, head_w, head_b, head_ch, n_rays, n
 ACT_TILE_ELEMS = TILE_ROWS * 128
 
 
-def mlp_chain_train(inp, layers, rows, raw, samples_per_ray, n_rays):
+def mlp_chain_train(inp, layers, rows, raw, samples_per_ray, n_rays, row_ids=None, row_count=None):
     """`mlp_chain` (fp16, BLOCKED rows, one of the two tri-plane chains) that also returns the four activation images
-    x_1..x_4 [tiles,16,128,8] fp16 the backward needs."""
+    x_1..x_4 [tiles,16,128,8] fp16 the backward needs.  row_ids / row_count (rgb chain): the sparse colour path — `inp`
+    and the returned images are in LIST order, the heads go to the listed rows of `raw`."""
     lib = _lib.load()
-    m, fpr, bpr = _mlp_struct(inp, layers, rows, raw, NVSR_F16, samples_per_ray, n_rays, ROWS_BLOCKED)
+    m, fpr, bpr = _mlp_struct(inp, layers, rows, raw, NVSR_F16, samples_per_ray, n_rays, ROWS_BLOCKED, row_ids, row_count)
     tiles = rows // TILE_ROWS
     acts = [torch.empty((tiles, 16, TILE_ROWS, 8), dtype=torch.float16, device=raw.device) for _ in range(4)]
     ptrs = (C.c_void_p * 4)(*[a.data_ptr() for a in acts])
@@ -554,14 +555,17 @@ def mlp_chain_train(inp, layers, rows, raw, samples_per_ray, n_rays):
     return acts
 
 
-def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples, row_count=None, row_ids=None, x0_img=None):
+def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples, row_count=None, row_ids=None, x0_img=None,
+              acts_listed=False):
     """Data-gradient chain of one tri-plane decoder chain.  w_imgs: the 4 forward weight images (fp16); head_w [h,128]
     fp32; d_raw planar [4,stride] (BLOCKED rows, padding rows 0); acts: x_1..x_4 images.
     -> (g images g_0..g_3, d_out image [tiles,2,128,8], d_x0 fp32 [n_rays*n_samples, k0]).
     row_count (device int32 [1]): row-list mode — the outputs are LIST-ordered (d_x0 [tiles*128, k0]) and only the tiles
     the list fills are touched.  Without row_ids, d_raw / acts are the LIST-ordered copies of `compact_rows`; with
     row_ids (+ x0_img, the feature image) they are the forward's own buffers, gathered through the list by the kernel,
-    which then also returns the LIST-ordered x_1..x_4 and feature images: (g, d_out, d_x0, acts_list, x0_list)."""
+    which then also returns the LIST-ordered x_1..x_4 and feature images: (g, d_out, d_x0, acts_list, x0_list).
+    acts_listed (with row_ids): `acts` are LIST-ordered already (the sparse training forward over the same list) — only
+    d_raw is read through the list; acts_list / x0_list come back as None."""
     lib = _lib.load()
     dev = d_raw.device
     tiles = rows_padded(n_rays, n_samples, ROWS_BLOCKED) // TILE_ROWS
@@ -577,7 +581,9 @@ def mlp_dgrad(w_imgs, k0, head_w, head_ch, d_raw, scale, acts, n_rays, n_samples
     a.dout_img, a.d_x0, a.n_rays, a.n_samples = dout.data_ptr(), d_x0.data_ptr(), n_rays, n_samples
     a.row_count = _ptr(row_count)
     acts_list = x0_list = None
-    if row_ids is not None:
+    if row_ids is not None and acts_listed:
+        a.row_ids, a.acts_listed = row_ids.data_ptr(), 1
+    elif row_ids is not None:
         acts_list = [torch.empty_like(t) for t in acts]
         a.row_ids = row_ids.data_ptr()
         for l in range(4):

@@ -1,4 +1,4 @@
 # compute-sanitizer memcheck over the row-list ("sparse") training backward kernels and the fused weight-gradient launch
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_train_tc.py -m gpu -q -x -k "row_list or dgrad or wgrad or frozen" -p no:cacheprovider > gpurun_out/sanitize_rows_memcheck.log 2>&1; echo "memcheck rc=$?"
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_train_tc.py -m gpu -q -x -k "row_list or dgrad or wgrad or frozen or sparse_training or pack_weights" -p no:cacheprovider > gpurun_out/sanitize_rows_memcheck.log 2>&1; echo "memcheck rc=$?"
 grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" gpurun_out/sanitize_rows_memcheck.log | tail -6

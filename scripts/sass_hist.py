@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "neural-volume-super-resolution_b200", "libnvsr_b200.so")
 WANT = ["mlp_chain_tc_kernelILb1ELi4ELi1ELi0ELb0", "mlp_chain_tc_kernelILb1ELi4ELi3ELi1ELb0", "mlp_chain_tc_kernelILb1ELi4ELi3ELi1ELb1",
         "mlp_chain_tc_kernelILb1ELin6", "gather_tile_16ILb1ELi6", "gather_rows_16ILb1ELi6", "composite_kernelILb1ELb1",
-        "composite_kernelILb0ELb0", "dgrad_chain_kernel", "wgrad_kernel", "sr_finalize_kernelILb1"]
+        "composite_kernelILb0ELb0", "composite_bwd_warp_kernel", "dgrad_chain_kernel", "wgrad_kernel", "nonzero_rows_kernel",
+        "ray_sum_rows_kernel", "gather_bwd_rows_kernel", "pack_weights_kernelI6__half", "sr_finalize_kernelILb1"]
 
 
 def main():

@@ -43,7 +43,7 @@ def test_struct_sizes_match_c_layout(tmp_path):
     pairs = [("nvsr_layer_t", _lib.Layer, "head_ch"), ("nvsr_planes_t", _lib.Planes, "combine"),
              ("nvsr_sampler_t", _lib.Sampler, "z_in"), ("nvsr_mlp_t", _lib.Mlp, "row_order"),
              ("nvsr_composite_t", _lib.Composite, "z_merged"), ("nvsr_decoder_t", _lib.Decoder, "view_b"),
-             ("nvsr_render_t", _lib.Render, "workspace_bytes"), ("nvsr_dgrad_t", _lib.Dgrad, "x0_list")]
+             ("nvsr_render_t", _lib.Render, "workspace_bytes"), ("nvsr_dgrad_t", _lib.Dgrad, "acts_listed")]
     src = "#include <stdio.h>\n#include <stddef.h>\n#include \"nvsr.h\"\nint main(void){\n"
     for cname, _, last in pairs:
         src += f'printf("%zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));\n'

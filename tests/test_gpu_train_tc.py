@@ -226,7 +226,7 @@ def _q(t):
     return t + (t.half().float() - t).detach()
 
 
-def _emulated_planes_forward(model, scene_id, ro, rd, z, viewdirs):
+def _emulated_planes_forward(model, scene_id, ro, rd, z, viewdirs, sigma_noise=None):
     """`autograd.planes_model_forward` in stock PyTorch ops with the tcgen05 path's rounding points: fp16 planes, fp16
     features, fp16 weights, fp16 hidden activations (straight-through), fp32 accumulation, fp32 biases, heads on the
     unrounded last activations, the rgb chain's view columns as an fp32 per-ray bias."""
@@ -417,6 +417,7 @@ def test_row_list_backward_equals_dense_backward(res, nc, nf, white, noise):
         rnd.update(noise_c=torch.randn(n, nc, generator=g), noise_f=torch.randn(n, nc + nf, generator=g))
     target = torch.rand(n, 3, generator=g).to(DEV)
     try:
+        A.set_sparse_forward(False)      # (the sparse forward brings its own list: tested below)
         A.set_sparse_backward(False)
         ops.LAUNCHES.clear()
         l_d, _, g_dense = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
@@ -427,6 +428,7 @@ def test_row_list_backward_equals_dense_backward(res, nc, nf, white, noise):
         assert ops.LAUNCHES.get("nvsr_nonzero_rows", 0) == 2
     finally:
         A.set_sparse_backward(True)
+        A.set_sparse_forward(True)
     assert l_d == l_s and set(g_dense) == set(g_rows)
     for k in g_dense:
         a, b = g_rows[k].double(), g_dense[k].double()
@@ -539,3 +541,43 @@ def test_pack_weights16_one_launch_and_deferred_range_check():
     rc.commit()
     with pytest.raises(nvsr_b200.NvsrError, match="fp16 range"):
         rc.flush()
+
+
+@pytest.mark.parametrize("res,nc,nf,white,noise", [(32, 64, 128, True, 0.2), (19, 24, 40, False, 0.0)])
+def test_sparse_training_forward_equals_dense_forward(res, nc, nf, white, noise):
+    """`set_sparse_forward` (default on): the rgb chain of the training forward runs over the samples with
+    relu(sigma + noise) > 0 only.  Same step with it off: bit-identical maps and loss (a dropped sample has weight exactly
+    0), gradients equal to the order of the fp32 sums; the rgb chain sees a strict subset of the rows."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=64, view_res=16, seed=0, device=DEV)
+    for m in (mc, mf):
+        m.train()
+    pose, focal = scene.blender_camera(res)
+    opt, scfg = scene.render_options(nc, nf, perturb=True, white_background=white, noise_std=noise), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(res, res, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    n = batch.shape[1]
+    g = torch.Generator().manual_seed(12)
+    rnd = dict(t_rand=torch.rand(n, nc, generator=g), u=torch.rand(n, nf, generator=g))
+    if noise:
+        rnd.update(noise_c=torch.randn(n, nc, generator=g), noise_f=torch.randn(n, nc + nf, generator=g))
+    target = torch.rand(n, 3, generator=g).to(DEV)
+    try:
+        A.set_sparse_forward(False)
+        ops.LAUNCHES.clear()
+        l_d, o_d, g_d = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        assert ops.LAUNCHES.get("nvsr_keep_rows", 0) == 0 and ops.LAUNCHES.get("nvsr_nonzero_rows", 0) == 2
+        A.set_sparse_forward(True)
+        ops.LAUNCHES.clear()
+        l_s, o_s, g_s = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        assert ops.LAUNCHES.get("nvsr_keep_rows", 0) == 2 and ops.LAUNCHES.get("nvsr_nonzero_rows", 0) == 0
+        assert ops.LAUNCHES.get("nvsr_sample_gather_rows", 0) == 2
+    finally:
+        A.set_sparse_forward(True)
+    assert l_d == l_s
+    for k in (0, 2, 3, 5):
+        assert torch.equal(o_d[k], o_s[k]), k
+    assert set(g_d) == set(g_s)
+    for k in g_d:
+        a, b = g_s[k].double(), g_d[k].double()
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, (k, float((a - b).abs().max()), float(b.abs().max()))
