@@ -21,6 +21,7 @@ from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
 
 
 _state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0, "sparse_backward": True, "sparse_forward": True}
+_state["device_rng"] = False
 _DENSE = "dense"     # planes_model_forward's default for sigma_noise: the caller does not say what the compositing will add
 
 
@@ -30,6 +31,21 @@ def set_sparse_backward(flag):
     alpha = 0 or transmittance 0 and add nothing to any gradient.  False: every sample goes through the backward chains.
     The two give the same gradients up to the order of the fp32 sums."""
     _state["sparse_backward"] = bool(flag)
+
+
+def set_device_rng(flag):
+    """False (default): the stratified offsets, the inverse-CDF u and the density noise are drawn like the reference
+    draws them — `torch.rand` / `torch.randn` on the CPU (train_utils.py:108, nerf_helpers.py:683,
+    volume_rendering_utils.py:32), so the same torch seed gives the reference's numbers — and uploaded (a pageable copy
+    that synchronises the host with the device, ~3 MB per 4 096-ray step).  True: drawn on the device from torch's CUDA
+    generator: same distributions, another stream of numbers, no upload, and the step stays capturable into a CUDA graph
+    (`GraphedStep`) without the caller providing `randoms`."""
+    _state["device_rng"] = bool(flag)
+
+
+def _rand(shape, device, normal=False):
+    dev = device if _state["device_rng"] else None
+    return (torch.randn if normal else torch.rand)(tuple(shape), device=dev)
 
 
 def set_sparse_forward(flag):
@@ -400,7 +416,7 @@ def _render(radiance_field, depth_values, ray_directions, noise_std, white_backg
     """nz: the density noise ALREADY scaled by the std (what `planes_model_forward(sigma_noise=)` was given)"""
     if nz is None and noise_std > 0.0:
         if noise is None:
-            noise = torch.randn(radiance_field[..., 3].shape)
+            noise = _rand(radiance_field[..., 3].shape, radiance_field.device, normal=True)
         nz = (noise * noise_std).to(radiance_field).contiguous()
     return _VolumeRender.apply(radiance_field.float().contiguous(), depth_values.float().contiguous(),
                                ray_directions.float().contiguous(), nz, white_background, mip)
@@ -534,7 +550,7 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
     if cfg.perturb:
         mids = 0.5 * (z[..., 1:] + z[..., :-1])
         upper, lower = torch.cat((mids, z[..., -1:]), -1), torch.cat((z[..., :1], mids), -1)
-        t_rand = randoms["t_rand"] if "t_rand" in randoms else torch.rand((n, Nc + 1))
+        t_rand = randoms["t_rand"] if "t_rand" in randoms else _rand((n, Nc + 1), dev)
         z = lower + (upper - lower) * t_rand.to(device=dev, dtype=torch.float32)
     z = z.contiguous()
     denc = ops.dir_encoding(vd, n_dir, True)
@@ -544,7 +560,7 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
         """the density noise of one pass, scaled by the std, on the device (volume_rendering_utils.py:30-35)"""
         if std <= 0.0:
             return None
-        nse = randoms[name] if name in randoms else torch.randn((n, S))     # the reference draws on the CPU
+        nse = randoms[name] if name in randoms else _rand((n, S), dev, normal=True)     # the reference draws on the CPU
         return (nse * std).to(device=dev, dtype=torch.float32).contiguous()
 
     def radiance(model, z_edges):
@@ -564,7 +580,7 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
             mid = 0.5 * (mid[..., 1:] + mid[..., :-1])
             u = randoms.get("u")
             if u is None and cfg.perturb != 0.0:
-                u = torch.rand([n, Nf + 1])
+                u = _rand([n, Nf + 1], dev)
             z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf + 1, det=(cfg.perturb == 0.0), u=u)
             z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
             if "z_fine" in randoms:     # test hook: teacher-forced merged depths
@@ -593,7 +609,7 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
         return _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scene_id, n_freqs, randoms)
 
     def draw(name, shape):
-        t = randoms[name] if name in randoms else torch.rand(shape)     # the reference draws on the CPU
+        t = randoms[name] if name in randoms else _rand(shape, dev)     # the reference draws on the CPU
         return t.to(device=dev, dtype=torch.float32)
 
     def coarse_depths():
@@ -618,7 +634,7 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
         """the density noise of one pass, scaled by the std, on the device (volume_rendering_utils.py:30-35)"""
         if std <= 0.0:
             return None
-        nse = randoms[name] if name in randoms else torch.randn((n, S))     # the reference draws on the CPU
+        nse = randoms[name] if name in randoms else _rand((n, S), dev, normal=True)     # the reference draws on the CPU
         return (nse * std).to(device=dev, dtype=torch.float32).contiguous()
 
     z_f = None
@@ -648,7 +664,7 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
             mid = 0.5 * (z[..., 1:] + z[..., :-1])
             u = randoms.get("u")
             if u is None and cfg.perturb != 0.0:
-                u = torch.rand([n, Nf])
+                u = _rand([n, Nf], dev)
             z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf, det=(cfg.perturb == 0.0), u=u)
             z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
             if "z_fine" in randoms:     # test hook: teacher-forced merged depths

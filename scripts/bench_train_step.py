@@ -167,6 +167,14 @@ def main():
     A.set_sparse_backward(False)
     res["nvsr_dense_backward_ms"] = timed(nvsr_arm)
     A.set_sparse_backward(True)
+    # the drop-in flow (no `randoms` from the caller): draws on the CPU like the reference + upload, or on the device
+    def dropin_arm():
+        out = A.run_one_iter_of_nerf(800, 800, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg)
+        (F.mse_loss(out[0], target) + F.mse_loss(out[3], target)).backward()
+    res["nvsr_cpu_rng_ms"] = timed(dropin_arm)
+    A.set_device_rng(True)
+    res["nvsr_device_rng_ms"] = timed(dropin_arm)
+    A.set_device_rng(False)
     A.set_decoder("fp32")        # fp32 parity mode: gather / compositing kernels + the model's nn.Linear under torch autograd
     res["nvsr_fp32_mode_ms"] = timed(nvsr_arm)
     g_f = [None if p.grad is None else p.grad.clone() for p in params]

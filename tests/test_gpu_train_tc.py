@@ -581,3 +581,41 @@ def test_sparse_training_forward_equals_dense_forward(res, nc, nf, white, noise)
     for k in g_d:
         a, b = g_s[k].double(), g_d[k].double()
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, (k, float((a - b).abs().max()), float(b.abs().max()))
+
+
+def test_device_rng_step_needs_no_randoms_and_is_capturable():
+    """`set_device_rng(True)`: the random draws come from torch's CUDA generator, so a step without caller-provided
+    `randoms` has no host upload, captures into a CUDA graph, and every replay draws new numbers."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=48, view_res=12, seed=6, device=DEV)
+    for m in (mc, mf):
+        m.train()
+    res, nc, nf = 24, 32, 32
+    pose, focal = scene.blender_camera(res)
+    opt, scfg = scene.render_options(nc, nf, perturb=True, noise_std=0.1), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(res, res, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    target = torch.rand(batch.shape[1], 3, generator=torch.Generator().manual_seed(0)).to(DEV)
+    params = [p for m in (mc, mf) for p in m.parameters()]
+
+    def step():
+        for p in params:
+            p.grad = None
+        out = A.run_one_iter_of_nerf(res, res, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg)
+        loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
+        loss.backward()
+        return loss
+    A.set_device_rng(True)
+    try:
+        torch.manual_seed(1)
+        a = float(step().detach())
+        torch.manual_seed(1)
+        b = float(step().detach())
+        assert a == b                                    # torch's CUDA generator: seedable like the CPU one
+        graphed = A.GraphedStep(step, warmup=2)
+        losses = [float(graphed().detach()) for _ in range(4)]
+        assert len(set(losses)) == 4, losses             # new draws in every replay
+        assert all(abs(x - a) < 0.05 * abs(a) + 0.05 for x in losses)
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in params if p.requires_grad)
+    finally:
+        A.set_device_rng(False)
