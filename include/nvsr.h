@@ -456,6 +456,12 @@ int32_t nvsr_sample_gather_bwd_rows(const nvsr_sampler_t* sampler, const nvsr_pl
                                     const float* d_feat_m, const int32_t* row_ids, const int32_t* count, int64_t max_rows,
                                     float* const d_plane[3], void* stream);
 
+/* out[ray][0 .. sa+sb) = sort(cat(a[ray][0..sa), b[ray][0..sb))) ascending — the merge of the coarse depths with the
+ * inverse-CDF samples (train_utils.py:144-156) when those are not sorted (training with perturbation).  One warp per
+ * ray, bitonic network in registers; sa + sb <= 512 (NVSR_ERR_UNSUPPORTED beyond).  Values are moved, never changed;
+ * NaNs sort last (torch.sort). */
+int32_t nvsr_sort_cat(const float* a, int32_t sa, const float* b, int32_t sb, int64_t n_rays, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Plane super-resolution, last step: PlanesSR.forward (models.py:884-926) ends with
  *   out = inner_model(pad(LR))[..., crop:-crop, crop:-crop] + F.interpolate(LR, scale_factor, 'bilinear', align_corners)

@@ -582,7 +582,7 @@ def _run_one_iter_mip(model_coarse, model_fine, ro, rd, vd, near, far, cfg, scen
             if u is None and cfg.perturb != 0.0:
                 u = _rand([n, Nf + 1], dev)
             z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf + 1, det=(cfg.perturb == 0.0), u=u)
-            z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
+            z_f = ops.sort_cat(z, z_samples)
             if "z_fine" in randoms:     # test hook: teacher-forced merged depths
                 z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
         rf_f = radiance(model_fine, z_f)
@@ -666,7 +666,7 @@ def _run_one_iter(H, W, focal, model_coarse, model_fine, batch_rays, options, sc
             if u is None and cfg.perturb != 0.0:
                 u = _rand([n, Nf], dev)
             z_samples = ops.sample_pdf(mid, weights[..., 1:-1], Nf, det=(cfg.perturb == 0.0), u=u)
-            z_f = torch.sort(torch.cat((z, z_samples), -1), -1).values.contiguous()
+            z_f = ops.sort_cat(z, z_samples)
             if "z_fine" in randoms:     # test hook: teacher-forced merged depths
                 z_f = randoms["z_fine"].to(device=dev, dtype=torch.float32).contiguous()
             if isinstance(randoms.get("trace"), dict):

@@ -488,6 +488,66 @@ sample_pdf_kernel(const float* __restrict__ bins_g, const float* __restrict__ w_
   }
 }
 
+
+// out[ray] = sort(cat(a[ray], b[ray])) ascending (train_utils.py:144-156: the merged depths of the fine pass when the
+// inverse-CDF samples are NOT sorted, i.e. with perturbation; the det=True frame path rank-merges inside composite_kernel).
+// One warp per ray, a bitonic network over 32 * M keys held in registers: element e = reg * 32 + lane, so strides < 32
+// are lane exchanges (SHFL.BFLY) and strides >= 32 are register exchanges.  Keys are the order-preserving unsigned image
+// of the floats (total order; a NaN sorts last like torch.sort), padding = 0xffffffff.
+template <int M>
+__global__ void __launch_bounds__(128) sort_cat_kernel(const float* __restrict__ a, int sa, const float* __restrict__ b, int sb,
+                                                       int64_t n_rays, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const int S = sa + sb;
+  uint32_t v[M];
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+    const int e = r * 32 + lane;
+    uint32_t key = 0xffffffffu;
+    if (e < S) {
+      const uint32_t bits = __float_as_uint(e < sa ? __ldg(a + ray * sa + e) : __ldg(b + ray * sb + (e - sa)));
+      key = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+    }
+    v[r] = key;
+  }
+#pragma unroll
+  for (int k = 2; k <= 32 * M; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j >= 32) {
+        const int rj = j >> 5;
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+          if ((r & rj) == 0) {
+            const bool up = (((r * 32) & k) == 0);   // k >= 64 here: the block direction depends on the register index only
+            const uint32_t lo = min(v[r], v[r | rj]), hi = max(v[r], v[r | rj]);
+            v[r] = up ? lo : hi;
+            v[r | rj] = up ? hi : lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+          const int e = r * 32 + lane;
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool up = ((e & k) == 0), lower = ((lane & j) == 0);
+          v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+    const int e = r * 32 + lane;
+    if (e < S) {
+      const uint32_t key = v[r];
+      out[ray * S + e] = __uint_as_float(key ^ ((key >> 31) ? 0x80000000u : 0xffffffffu));
+    }
+  }
+}
+
 template <typename K>
 static int32_t pick_warps(K kernel, size_t floats_per_warp, int max_warps, int* warps_out, size_t* smem_out) {
   size_t per_warp = floats_per_warp * sizeof(float);
@@ -552,5 +612,19 @@ extern "C" int32_t nvsr_sample_pdf(const float* bins, const float* weights, cons
   if (blocks > max_blocks) blocks = max_blocks;
   sample_pdf_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(
       bins, weights, cdf_in, n_rays, n_bins, u, u_per_ray, n_samples, inds, samples, cdf_out, warps);
+  NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_sort_cat(const float* a, int32_t sa, const float* b, int32_t sb, int64_t n_rays, float* out, void* stream) {
+  NVSR_CHECK_ARG(out && sa >= 0 && sb >= 0 && sa + sb > 0 && n_rays >= 0 && (a || sa == 0) && (b || sb == 0));
+  if (sa + sb > 512) return NVSR_ERR_UNSUPPORTED;
+  if (n_rays == 0) return NVSR_OK;
+  const unsigned blocks = (unsigned)ceil_div64(n_rays, 4);
+  const int S = sa + sb;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S <= 64) sort_cat_kernel<2><<<blocks, 128, 0, st>>>(a, sa, b, sb, n_rays, out);
+  else if (S <= 128) sort_cat_kernel<4><<<blocks, 128, 0, st>>>(a, sa, b, sb, n_rays, out);
+  else if (S <= 256) sort_cat_kernel<8><<<blocks, 128, 0, st>>>(a, sa, b, sb, n_rays, out);
+  else sort_cat_kernel<16><<<blocks, 128, 0, st>>>(a, sa, b, sb, n_rays, out);
   NVSR_RETURN_LAST_ERROR();
 }

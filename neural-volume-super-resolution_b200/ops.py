@@ -667,6 +667,23 @@ def ray_sum(img, n_rays, n_samples, inv_scale=1.0):
     return out
 
 
+def sort_cat(a, b):
+    """sort(cat((a, b), -1), -1).values for [n, Sa] / [n, Sb] fp32 depths (train_utils.py:144-156) in one launch
+    (nvsr_sort_cat, Sa + Sb <= 512; longer rows go through torch.sort on the device)."""
+    a, b = _f32c(a), _f32c(b, a.device)
+    _require_cuda(a, "depths")
+    n, sa = a.shape
+    sb = b.shape[1]
+    if sa + sb > 512:
+        return torch.sort(torch.cat((a, b), -1), -1).values.contiguous()
+    lib = _lib.load()
+    out = torch.empty((n, sa + sb), dtype=torch.float32, device=a.device)
+    with _OnDevice(a.device):
+        st = _call("nvsr_sort_cat", lib.nvsr_sort_cat, _ptr(a), sa, _ptr(b), sb, n, _ptr(out), _stream(), rows=n * (sa + sb))
+    _lib.check(st, "nvsr_sort_cat")
+    return out
+
+
 def nonzero_rows(d_raw):
     """BLOCKED row ids whose raw gradient (planar [4, stride]) is not identically zero -> (row_ids int32 [stride],
     count int32 [1]) on the device, order unspecified (nvsr_nonzero_rows)."""

@@ -474,3 +474,24 @@ def test_cast_rays_and_ipe_dropins():
     out = enc((T(g["means"], DEV), T(g["covs"], DEV)))
     H.assert_close(out, g["enc"], 5e-6, what="ipe((means, covs))")
     assert out.shape == tuple(g["enc"].shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sa,sb,n", [(64, 128, 1000), (24, 40, 37), (1, 0, 5), (128, 256, 129), (65, 130, 64), (200, 312, 9)])
+def test_sort_cat_equals_torch_sort(sa, sb, n):
+    """nvsr_sort_cat == torch.sort(torch.cat((a, b), -1), -1).values bit for bit (train_utils.py:144-156), including
+    duplicates, negative values, infinities and a NaN (sorted last)."""
+    g = torch.Generator().manual_seed(sa * 1000 + sb)
+    a = torch.sort(2.0 + 4.0 * torch.rand(n, sa, generator=g), -1).values
+    b = 2.0 + 4.0 * torch.rand(n, sb, generator=g)
+    if sb:
+        b[:, : sb // 3] = a[:, :1]                     # duplicates of a coarse depth
+        b[0, -1] = float("inf")
+        if n > 2:
+            b[1, 0], b[2, 0] = -3.5, float("nan")
+    a, b = a.to(DEV), b.to(DEV)
+    got = ops.sort_cat(a, b)
+    want = torch.sort(torch.cat((a, b), -1), -1).values
+    assert got.shape == want.shape
+    assert torch.equal(got.nan_to_num(nan=123.0), want.nan_to_num(nan=123.0))
+    assert torch.equal(got.isnan(), want.isnan())
