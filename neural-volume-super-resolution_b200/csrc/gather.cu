@@ -224,10 +224,17 @@ __device__ __forceinline__ void texel_fma(unsigned long long acc[4], const uint4
 // contiguous bytes, so the stores go straight to global, fully coalesced.  CH_T > 0 fixes the chunk
 // count at compile time (6 for the reference's 48-channel planes): the chunk loop is fully unrolled
 // and the loads of the next chunk are in flight while one is interpolated.
-template <bool F16, int CH_T>
-__global__ void __launch_bounds__(kGatherThreads, NVSR_GATHER_MINB)
+// HILO (the fp16-split precision mode): every plane comes as TWO fp16 x-pair images, hi = fp16(p) and lo = fp16(p - hi),
+// so hi + lo carries ~22 bits of the fp32 plane.  featP (the colour chain's fp16 operand) is interpolated from hi alone,
+// exactly as without HILO; the combined features are interpolated from hi + lo in fp32 and written as an fp32 tile image
+// [tiles][C/4][128 rows][4] (featM32) — what the split density chain splits into its own hi / lo operands.
+struct LoPlanes {
+  const void* plane[3];
+};
+template <bool F16, int CH_T, bool HILO = false>
+__global__ void __launch_bounds__(kGatherThreads, HILO ? 4 : NVSR_GATHER_MINB)
 gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t* __restrict__ featM,
-               float* __restrict__ z_out, int64_t n_tiles) {
+               float* __restrict__ z_out, int64_t n_tiles, LoPlanes lo = LoPlanes{}, float* __restrict__ featM32 = nullptr) {
   const int CH = CH_T > 0 ? CH_T : p.C / 8;  // 16-byte chunks per plane texel (6 for C=48)
   const uint32_t p_bytes = 3u * CH * 2048u;  // 128 rows * 3C * 2 B
   const uint32_t m_bytes = (uint32_t)CH * 2048u;
@@ -238,6 +245,9 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
   const XPair* const pl0 = reinterpret_cast<const XPair*>(p.plane[0]);
   const XPair* const pl1 = reinterpret_cast<const XPair*>(p.plane[1]);
   const XPair* const pl2 = reinterpret_cast<const XPair*>(p.plane[2]);
+  const XPair* const lo0 = reinterpret_cast<const XPair*>(lo.plane[0]);
+  const XPair* const lo1 = reinterpret_cast<const XPair*>(lo.plane[1]);
+  const XPair* const lo2 = reinterpret_cast<const XPair*>(lo.plane[2]);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- per-row sample position -> 3 planes' footprints (registers) ----
@@ -260,6 +270,9 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
     uint8_t* gM = featM + tile * (int64_t)m_bytes + (uint32_t)r * 16u;
     const XPair* rowT[3] = {pl0 + f[0].top, pl1 + f[1].top, pl2 + f[2].top};
     const XPair* rowB[3] = {pl0 + f[0].bot, pl1 + f[1].bot, pl2 + f[2].bot};
+    const XPair* loT[3] = {lo0 + f[0].top, lo1 + f[1].top, lo2 + f[2].top};
+    const XPair* loB[3] = {lo0 + f[0].bot, lo1 + f[1].bot, lo2 + f[2].bot};
+    uint8_t* gM32 = HILO ? reinterpret_cast<uint8_t*>(featM32) + tile * (int64_t)(2u * m_bytes) + (uint32_t)r * 16u : nullptr;
     // ---- channel chunks ----
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -274,17 +287,37 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
         texel_fma<F16, false>(acc, vt.r, f[d].w01);
         texel_fma<F16, false>(acc, vb.l, f[d].w10);
         texel_fma<F16, false>(acc, vb.r, f[d].w11);
+        if (featP) {  // featP == NULL: density features only
+          uint4 o;
+          o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
+          o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
+          st_stream16(gP + (uint32_t)(d * CH + c) * 2048u, o);
+        }
+        if constexpr (HILO) {   // the low halves of the same four texels, on top of the high halves' sum
+          const XPair wt = ldg256(loT[d] + c * p.rw[d]);
+          const XPair wb = ldg256(loB[d] + c * p.rw[d]);
+          texel_fma<F16, false>(acc, wt.l, f[d].w00);
+          texel_fma<F16, false>(acc, wt.r, f[d].w01);
+          texel_fma<F16, false>(acc, wb.l, f[d].w10);
+          texel_fma<F16, false>(acc, wb.r, f[d].w11);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) mean[e] = d == 0 ? acc[e] : add_f32x2(mean[e], acc[e]);
-        uint4 o;
-        o.x = pack16_pair<F16>(acc[0]), o.y = pack16_pair<F16>(acc[1]);
-        o.z = pack16_pair<F16>(acc[2]), o.w = pack16_pair<F16>(acc[3]);
-        if (featP) st_stream16(gP + (uint32_t)(d * CH + c) * 2048u, o);  // featP == NULL: density features only
       }
-      uint4 o;
-      o.x = pack16_pair<F16>(mul_f32x2(mean[0], third)), o.y = pack16_pair<F16>(mul_f32x2(mean[1], third));
-      o.z = pack16_pair<F16>(mul_f32x2(mean[2], third)), o.w = pack16_pair<F16>(mul_f32x2(mean[3], third));
-      st_stream16(gM + (uint32_t)c * 2048u, o);
+      if constexpr (HILO) {
+        uint4 o0, o1;   // 8 fp32 channels = two 16-byte groups of the fp32 tile image
+        const unsigned long long m0 = mul_f32x2(mean[0], third), m1 = mul_f32x2(mean[1], third);
+        const unsigned long long m2 = mul_f32x2(mean[2], third), m3 = mul_f32x2(mean[3], third);
+        o0.x = (uint32_t)m0, o0.y = (uint32_t)(m0 >> 32), o0.z = (uint32_t)m1, o0.w = (uint32_t)(m1 >> 32);
+        o1.x = (uint32_t)m2, o1.y = (uint32_t)(m2 >> 32), o1.z = (uint32_t)m3, o1.w = (uint32_t)(m3 >> 32);
+        st_stream16(gM32 + (uint32_t)(2 * c) * 2048u, o0);
+        st_stream16(gM32 + (uint32_t)(2 * c + 1) * 2048u, o1);
+      } else {
+        uint4 o;
+        o.x = pack16_pair<F16>(mul_f32x2(mean[0], third)), o.y = pack16_pair<F16>(mul_f32x2(mean[1], third));
+        o.z = pack16_pair<F16>(mul_f32x2(mean[2], third)), o.w = pack16_pair<F16>(mul_f32x2(mean[3], third));
+        st_stream16(gM + (uint32_t)c * 2048u, o);
+      }
     }
   }
 }
@@ -455,10 +488,42 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
     int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
     int64_t grid = (int64_t)kNumSMs * NVSR_GATHER_MINB * 4;  // a few waves of the resident CTAs per SM, grid-stride beyond
     if (grid > n_tiles) grid = n_tiles;
-    kernel<<<(unsigned)grid, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_tiles);
+    kernel<<<(unsigned)grid, kGatherThreads, 0, st>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m, z_out, n_tiles, LoPlanes{}, nullptr);
     NVSR_RETURN_LAST_ERROR();
   }
   return NVSR_ERR_UNSUPPORTED;
+}
+
+extern "C" int32_t nvsr_sample_gather_hilo(const nvsr_sampler_t* s, const nvsr_planes_t* pl, const void* const lo_plane[3],
+                                           void* feat_p, float* feat_m32, float* z_out, void* stream) {
+  NVSR_CHECK_ARG(s && pl && lo_plane && feat_m32);
+  NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd && (s->z_in || s->t_vals));
+  NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64 && (pl->combine == 0 || pl->combine == 1));
+  if (pl->dtype != NVSR_F16) return NVSR_ERR_UNSUPPORTED;
+  LoPlanes lo;
+  for (int d = 0; d < 3; ++d) {
+    NVSR_CHECK_ARG(pl->plane[d] && lo_plane[d] && pl->rh[d] > 0 && pl->rw[d] > 0);
+    if ((reinterpret_cast<uintptr_t>(pl->plane[d]) & 31u) != 0 || (reinterpret_cast<uintptr_t>(lo_plane[d]) & 31u) != 0)
+      return NVSR_ERR_ALIGNMENT;
+    lo.plane[d] = lo_plane[d];
+  }
+  if ((feat_p && !aligned16(feat_p)) || !aligned16(feat_m32)) return NVSR_ERR_ALIGNMENT;
+  if (s->n_rays == 0) return NVSR_OK;
+  SamplerArgs a{s->n_rays, s->n_samples, s->ro, s->rd, s->near_, s->far_, s->lindisp, s->t_vals, s->t_rand, s->z_in};
+  PlaneArgs p;
+  for (int d = 0; d < 3; ++d) {
+    p.plane[d] = pl->plane[d], p.rh[d] = pl->rh[d], p.rw[d] = pl->rw[d];
+    p.lo[d] = pl->box_lo[d], p.rng[d] = pl->box_rng[d];
+    for (int j = 0; j < 6; ++j) p.proj[d][j] = pl->proj[d][j];
+  }
+  p.C = pl->channels;
+  p.combine_sum = pl->combine == 1;
+  auto kernel = pl->channels == 48 ? gather_tile_16<true, 6, true> : gather_tile_16<true, 0, true>;
+  int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
+  int64_t grid = (int64_t)kNumSMs * 4 * 4;
+  if (grid > n_tiles) grid = n_tiles;
+  kernel<<<(unsigned)grid, kGatherThreads, 0, (cudaStream_t)stream>>>(a, p, (uint8_t*)feat_p, nullptr, z_out, n_tiles, lo, feat_m32);
+  NVSR_RETURN_LAST_ERROR();
 }
 
 extern "C" int32_t nvsr_keep_rows(const float* sigma, const float* noise, int64_t n_rays, int32_t n_samples,

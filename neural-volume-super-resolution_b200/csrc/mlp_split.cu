@@ -94,7 +94,8 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t* hi, uint32_t*
 }
 
 struct SplitArgs {
-  const float* feat;          // [n_rays * S][k0] fp32, ray-major rows
+  const float* feat;          // [n_rays * S][k0] fp32, ray-major rows; or (feat_tiled) the fp32 tile image
+  int feat_tiled;             //   [tiles][k0/4][128 rows][4] in BLOCKED rows that nvsr_sample_gather_hilo writes
   int k0;
   const uint8_t* w_hi[4];     // fp16 images [k/8][128][8]
   const uint8_t* w_lo[4];
@@ -224,10 +225,16 @@ __global__ void __launch_bounds__(kSpThreads, 1) chain_split_kernel(const __grid
       const int smp = (int)(tile - blk * a.tiles_per_blk) * kBlkSamples + (r >> 3);
       const int64_t ray = blk * kBlkRays + (r & 7);
       const bool valid = ray < a.n_rays && smp < a.S;
-      const float4* src = reinterpret_cast<const float4*>(a.feat + (valid ? (ray * a.S + smp) * (int64_t)(K0C * 16) : 0));
       float4 f[K0C * 4];
+      if (a.feat_tiled) {   // group j of row r: 16 bytes, a warp's 32 rows contiguous (padding rows are zero in the image)
+        const float4* src = reinterpret_cast<const float4*>(a.feat) + tile * (int64_t)(K0C * 4 * kTileRows) + r;
 #pragma unroll
-      for (int j = 0; j < K0C * 4; ++j) f[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < K0C * 4; ++j) f[j] = __ldg(src + j * kTileRows);
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(a.feat + (valid ? (ray * a.S + smp) * (int64_t)(K0C * 16) : 0));
+#pragma unroll
+        for (int j = 0; j < K0C * 4; ++j) f[j] = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int c = 0; c < K0C; ++c) {   // 16 features = 8 TMEM columns per step
         uint32_t hi[8], lo[8];
@@ -325,10 +332,10 @@ __global__ void __launch_bounds__(kSpThreads, 1) chain_split_kernel(const __grid
 
 using namespace nvsr;
 
-extern "C" int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const void* const* w_hi, const void* const* w_lo,
-                                        const float* const* bias, const float* head_w, const float* head_b, int32_t head_n,
-                                        int32_t head_ch, int64_t n_rays, int32_t n_samples, float* raw, int64_t raw_stride,
-                                        void* stream) {
+static int32_t split_launch(const float* feat, int32_t tiled, int32_t k0, const void* const* w_hi, const void* const* w_lo,
+                            const float* const* bias, const float* head_w, const float* head_b, int32_t head_n,
+                            int32_t head_ch, int64_t n_rays, int32_t n_samples, float* raw, int64_t raw_stride,
+                            void* stream) {
   NVSR_CHECK_ARG(feat && w_hi && w_lo && bias && head_w && head_b && raw && n_rays >= 0 && n_samples > 0);
   NVSR_CHECK_ARG(k0 >= 16 && (k0 % 16) == 0 && k0 <= 64 && head_n >= 1 && head_n <= 4 && head_ch >= 0 && head_ch + head_n <= 4);
   if (n_rays == 0) return NVSR_OK;
@@ -339,7 +346,7 @@ extern "C" int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const voi
     a.w_hi[l] = (const uint8_t*)w_hi[l], a.w_lo[l] = (const uint8_t*)w_lo[l], a.bias[l] = bias[l];
   }
   if (!aligned16(feat)) return NVSR_ERR_ALIGNMENT;
-  a.feat = feat, a.k0 = k0, a.head_w = head_w, a.head_b = head_b, a.head_n = head_n, a.head_ch = head_ch;
+  a.feat = feat, a.feat_tiled = tiled, a.k0 = k0, a.head_w = head_w, a.head_b = head_b, a.head_n = head_n, a.head_ch = head_ch;
   a.raw = raw, a.raw_stride = raw_stride, a.n_rays = n_rays, a.S = n_samples;
   a.tiles_per_blk = tiles_per_block(n_samples);
   a.n_tiles = ceil_div64(n_rays, kBlkRays) * a.tiles_per_blk;
@@ -359,4 +366,19 @@ extern "C" int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const voi
   const int64_t grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
   kernel<<<(unsigned)grid, kSpThreads, smem_bytes, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();
+}
+
+extern "C" int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const void* const* w_hi, const void* const* w_lo,
+                                        const float* const* bias, const float* head_w, const float* head_b, int32_t head_n,
+                                        int32_t head_ch, int64_t n_rays, int32_t n_samples, float* raw, int64_t raw_stride,
+                                        void* stream) {
+  return split_launch(feat, 0, k0, w_hi, w_lo, bias, head_w, head_b, head_n, head_ch, n_rays, n_samples, raw, raw_stride, stream);
+}
+
+extern "C" int32_t nvsr_mlp_chain_split_tiled(const float* feat_tiles, int32_t k0, const void* const* w_hi,
+                                              const void* const* w_lo, const float* const* bias, const float* head_w,
+                                              const float* head_b, int32_t head_n, int32_t head_ch, int64_t n_rays,
+                                              int32_t n_samples, float* raw, int64_t raw_stride, void* stream) {
+  return split_launch(feat_tiles, 1, k0, w_hi, w_lo, bias, head_w, head_b, head_n, head_ch, n_rays, n_samples, raw, raw_stride,
+                      stream);
 }

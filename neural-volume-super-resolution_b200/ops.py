@@ -393,6 +393,41 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
     return feat_p, feat_m, (z_out if z_in is None else z_in)
 
 
+def sample_gather_hilo(ro, rd, near, far, packed, lo_planes, t_vals=None, z_in=None, t_rand=None, lindisp=False,
+                       n_samples=None, density_only=False):
+    """The fp16-split mode's gather (nvsr_sample_gather_hilo): `packed` holds the fp16 x-pair images of fp16(p),
+    `lo_planes` those of p - fp16(p).  Returns (featP fp16 tile image or None, featM32 fp32 tile image
+    [tiles, C/4, 128, 4] interpolated from hi + lo, z [n,S])."""
+    lib = _lib.load()
+    n = ro.shape[0]
+    if z_in is not None:
+        S = z_in.shape[1]
+        z_in = _f32c(z_in)
+    else:
+        S = t_vals.numel() if n_samples is None else n_samples
+        t_vals = _f32c(t_vals)
+    rows = rows_padded(n, S, ROWS_BLOCKED)
+    tiles, Cc = rows // TILE_ROWS, packed.channels
+    feat_p = None if density_only else torch.empty((tiles, 3 * Cc // 8, TILE_ROWS, 8), dtype=torch.float16, device=ro.device)
+    feat_m = torch.empty((tiles, Cc // 4, TILE_ROWS, 4), dtype=torch.float32, device=ro.device)
+    z_out = torch.empty((n, S), dtype=torch.float32, device=ro.device) if z_in is None else None
+    s = _lib.Sampler()
+    s.n_rays, s.n_samples = n, S
+    s.ro, s.rd = ro.data_ptr(), rd.data_ptr()
+    s.near_, s.far_, s.lindisp = float(near), float(far), int(bool(lindisp))
+    s.t_vals = 0 if t_vals is None else t_vals.data_ptr()
+    s.t_rand = 0 if t_rand is None else t_rand.data_ptr()
+    s.z_in = 0 if z_in is None else z_in.data_ptr()
+    pl = packed.cstruct()
+    lo = (C.c_void_p * 3)(*[t.data_ptr() for t in lo_planes])
+    with _OnDevice(ro.device):
+        st = _call("nvsr_sample_gather", lib.nvsr_sample_gather_hilo, C.byref(s), C.byref(pl), lo, _ptr(feat_p), _ptr(feat_m),
+                   _ptr(z_out), _stream(), rows=n * S,
+                   bytes=n * S * ((0 if feat_p is None else 3) * Cc * 2 + Cc * 4 + 4) + n * 24)
+    _lib.check(st, "nvsr_sample_gather_hilo")
+    return feat_p, feat_m, (z_out if z_in is None else z_in)
+
+
 def keep_rows(raw, n_rays, n_samples, noise=None):
     """Rows of a BLOCKED raw buffer that can contribute to the maps: sigma (+ noise) > 0 (or NaN) — every other
     sample has alpha = 0 and weight exactly 0 (volume_rendering_utils.py:29-44).  Returns (row_ids int32
@@ -520,15 +555,18 @@ def mlp_chain(inp, layers, rows, raw, precision, samples_per_ray=1, n_rays=1, ro
 
 def mlp_chain_split(feat, w_hi, w_lo, biases, head_w, head_b, head_ch, n_rays, n_samples, raw):
     """One tri-plane decoder chain with split fp16 operands (three tcgen05 passes per layer: fp32-grade accuracy).
-    feat: fp32 [n_rays*n_samples, k0] ray-major; w_hi / w_lo: lists of 4 fp16 weight images; raw: BLOCKED planar buffer."""
+    feat: fp32 [n_rays*n_samples, k0] ray-major, or the fp32 tile image [tiles, k0/4, 128, 4] of `sample_gather_hilo`;
+    w_hi / w_lo: lists of 4 fp16 weight images; raw: BLOCKED planar buffer."""
     lib = _lib.load()
-    k0 = feat.shape[1]
+    tiled = feat.dim() == 4
+    k0 = feat.shape[1] * 4 if tiled else feat.shape[1]
     P = C.c_void_p * 4
     wh, wl, bs = P(*[w.data_ptr() for w in w_hi]), P(*[w.data_ptr() for w in w_lo]), P(*[b.data_ptr() for b in biases])
     rows = n_rays * n_samples
     with _OnDevice(raw.device):
         fpr = 2 * (k0 * 128 + 3 * 128 * 128 + head_w.shape[0] * 128)
-        st = _call("nvsr_mlp_chain_split", lib.nvsr_mlp_chain_split, _ptr(feat), k0, wh, wl, bs, _ptr(head_w), _ptr(head_b),
+        st = _call("nvsr_mlp_chain_split", lib.nvsr_mlp_chain_split_tiled if tiled else lib.nvsr_mlp_chain_split, _ptr(feat), k0,
+                   wh, wl, bs, _ptr(head_w), _ptr(head_b),
                    head_w.shape[0], head_ch, n_rays, n_samples, _ptr(raw), raw.stride(0), _stream(), rows=rows,
                    flops_per_row=fpr, flops=rows * fpr, bytes=rows * (4 * k0 + 4 * head_w.shape[0]))
     _lib.check(st, "nvsr_mlp_chain_split")

@@ -131,12 +131,13 @@ class _PlanesPass:
         self.precision = precision
         self.layout = ops.FEAT_LAYOUT[precision]
         self.rows = ops.LAYOUT_ROWS[self.layout]
-        self.planes = scene.pack_scene_planes(model, scene_id, precision)
         self.dec = scene.pack_planes_decoder(model, precision)
         self.split = None
-        if split:   # 'fp16-split': fp32 planes for the density features + split weights of the density chain
-            self.planes32 = scene.pack_scene_planes(model, scene_id, NVSR_F32)
+        if split:   # 'fp16-split': the planes as fp16 hi + lo halves (density features) + split weights of the density chain
+            self.planes, self.planes_lo = scene.pack_scene_planes_hilo(model, scene_id)
             self.split = self.dec.density_split(model)
+        else:
+            self.planes = scene.pack_scene_planes(model, scene_id, precision)
 
     # The sparse colour path pays while few samples are lit (15 % on the bench scene); on a volume that is dense
     # almost everywhere the second gather would cost more than the skipped rgb rows save.  The lit fraction of the
@@ -171,14 +172,17 @@ class _PlanesPass:
         n = ro.shape[0]
         rows = ops.rows_padded(n, S, self.rows)
         sparse = _state["sparse_rgb"] and self.precision != NVSR_F32 and self._sparse_pays()
-        fp, fm, z = ops.sample_gather(ro, rd, near, far, self.planes, self.layout, t_vals=t_vals, z_in=z_in,
-                                      t_rand=t_rand, lindisp=lindisp, density_only=sparse)
         rbias = ops.row_bias(vfeat, self.dec.view_w, self.dec.view_b)
         raw = ops.raw_buffer(n, S, self.rows, ro.device)
         if self.split is not None:
-            _, fm32, _ = ops.sample_gather(ro, rd, near, far, self.planes32, ops.FEAT_ROWMAJOR_F32, z_in=z, density_only=True)
+            # one gather for both chains: fp16 3-plane features from the planes' high halves, fp32 combined features from
+            # hi + lo (an fp32 tile image the split chain reads directly)
+            fp, fm32, z = ops.sample_gather_hilo(ro, rd, near, far, self.planes, self.planes_lo, t_vals=t_vals, z_in=z_in,
+                                                 t_rand=t_rand, lindisp=lindisp, density_only=sparse)
             ops.mlp_chain_split(fm32, *self.split, 3, n, S, raw)
         else:
+            fp, fm, z = ops.sample_gather(ro, rd, near, far, self.planes, self.layout, t_vals=t_vals, z_in=z_in,
+                                          t_rand=t_rand, lindisp=lindisp, density_only=sparse)
             ops.mlp_chain(fm, self.dec.density, rows, raw, self.precision, S, n, self.rows)
         if sparse:
             keep, count = ops.keep_rows(raw, n, S, noise)

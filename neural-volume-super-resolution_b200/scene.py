@@ -519,6 +519,21 @@ def pack_scene_planes(model, scene_id, dtype):
                             combine=getattr(model, "proj_combination", "avg"))
 
 
+def pack_scene_planes_hilo(model, scene_id):
+    """The fp16-split mode's planes: (PackedPlanes of the fp16 x-pair images of fp16(p), list of the three images of
+    p - fp16(p)), both cut from the SAME fp32 planes (an SR plane is evaluated in fp32 once), so that hi + lo carries ~22
+    bits of every texel — what nvsr_sample_gather_hilo interpolates the combined features from."""
+    base = pack_scene_planes(model, scene_id, NVSR_F32)          # fp32 channels-last [Rh,Rw,C]
+    hi, lo = [], []
+    for img in base.planes:
+        src = img.permute(2, 0, 1)[None].contiguous()              # NCHW, as nvsr_pack_plane reads it
+        hi.append(ops.pack_plane(src, ops.NVSR_F16))
+        lo.append(ops.pack_plane((src - src.half().float()).contiguous(), ops.NVSR_F16))
+    packed = ops.PackedPlanes(hi, ops.NVSR_F16, base.box_lo, base.box_rng, base.proj, base.vplane, base.view_lo_rng,
+                              combine=base.combine)
+    return packed, lo
+
+
 class PackedPlanesDecoder:
     """Decoder chains of one TwoDimPlanesModel instance, in fp32 (SIMT) or bf16 (tcgen05) form."""
 

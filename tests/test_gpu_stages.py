@@ -495,3 +495,36 @@ def test_sort_cat_equals_torch_sort(sa, sb, n):
     assert got.shape == want.shape
     assert torch.equal(got.nan_to_num(nan=123.0), want.nan_to_num(nan=123.0))
     assert torch.equal(got.isnan(), want.isnan())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels,n,S", [(48, 61, 40), (32, 64, 64)])
+def test_sample_gather_hilo_vs_fp32_gather(channels, n, S):
+    """nvsr_sample_gather_hilo (the fp16-split mode's gather): featP is the 16-bit gather's featP bit for bit; the fp32
+    tile image of the combined features, interpolated from the planes' hi + lo fp16 halves, equals the fp32 gather's
+    combined features to a few 1e-7 of the feature scale (hi + lo carries ~22 bits of each texel); padding rows are 0."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=40, view_res=8, channels=channels, seed=9, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    ro = (torch.randn(n, 3, generator=g) * 0.3).to(DEV)
+    rd = torch.randn(n, 3, generator=g).to(DEV)
+    z = torch.sort(0.2 + 2.5 * torch.rand(n, S, generator=g), -1).values.to(DEV)
+    p32 = scene.pack_scene_planes(mf, sid, NVSR_F32)
+    p16, lo = scene.pack_scene_planes_hilo(mf, sid)
+    fp, fm32, z2 = ops.sample_gather_hilo(ro, rd, 0.0, 1.0, p16, lo, z_in=z)
+    fp_ref, _, _ = ops.sample_gather(ro, rd, 0.0, 1.0, p16, FEAT_TILE_F16, z_in=z)
+    assert torch.equal(fp, fp_ref) and z2 is z or torch.equal(z2, z)
+    _, fm_ref, _ = ops.sample_gather(ro, rd, 0.0, 1.0, p32, FEAT_ROWMAJOR_F32, z_in=z, density_only=True)   # [n*S, C] ray-major
+    t, c4, r, e = fm32.shape
+    rows = fm32.permute(0, 2, 1, 3).reshape(t * r, c4 * e)                     # BLOCKED rows
+    ts = -(-S // 16)
+    i = torch.arange(t * r, device=DEV)
+    ray, smp = (i // 128 // ts) * 8 + (i % 8), (i // 128 % ts) * 16 + (i % 128) // 8
+    valid = (ray < n) & (smp < S)
+    got = rows[valid]
+    want = fm_ref[(ray * S + smp)[valid]]
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-6 * scale, (float((got - want).abs().max()), scale)
+    assert not rows[~valid].any()
+    # density-only form
+    fp0, fm0, _ = ops.sample_gather_hilo(ro, rd, 0.0, 1.0, p16, lo, z_in=z, density_only=True)
+    assert fp0 is None and torch.equal(fm0, fm32)
