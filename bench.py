@@ -586,7 +586,7 @@ def main():
                 precision_modes["fp16-split"] = {
                     "ms_per_step": ms_split, "value": wl.rays / (ms_split * 1e-3), "unit": "rays/s", "frames_timed": 3,
                     "contract": "tcgen05 decoder; the density chain with split fp16 operands (3 MMA passes per layer) on "
-                                "fp32-gathered features, the colour chain in fp16: meets the 1e-3 map contract "
+                                "features interpolated in fp32 from the planes as fp16 hi + lo halves, the colour chain in fp16: meets the 1e-3 map contract "
                                 "(tests/parity_attribution.py, mode 'fp16-split')"}
             if args.config == "cfg2":
                 torch_gpu = time_torch_gpu_frame(wl, dev)

@@ -26,7 +26,7 @@ _PRECISION = {"bf16": NVSR_BF16, "fp16": NVSR_F16, "fp32": NVSR_F32, "fp16-split
 _state = {
     "precision": _PRECISION[os.environ.get("NVSR_PRECISION", "fp16")],
     # 'fp16-split': fp16 everywhere except the DENSITY chain, which runs on the tensor cores with every operand split
-    # into two fp16 terms (three MMA passes per layer, csrc/mlp_split.cu) on fp32-gathered features: the 16-bit modes'
+    # into two fp16 terms (three MMA passes per layer, csrc/mlp_split.cu) on features interpolated in fp32 from the planes stored as fp16 hi + lo halves: the 16-bit modes'
     # map error is sigma's (the colour logits are 3e-5 off), so this mode meets the 1e-3 contract on tcgen05
     "split_density": os.environ.get("NVSR_PRECISION", "fp16") == "fp16-split",
     # rays per chunk of the frame loop.  The reference chunks for memory (131 072 points per network call,
