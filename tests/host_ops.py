@@ -102,7 +102,10 @@ def standins(hc):
     def dir_encoding(dirs, n_freqs, include_input=True):
         return O.positional_encoding(dirs, n_freqs, include_input)
 
-    return dict(pack_plane=pack_plane, sample_gather=sample_gather, sample_gather_bwd=sample_gather_bwd,
+    def sort_cat(a, b):
+        return torch.sort(torch.cat((a, b), -1), -1).values.contiguous()
+
+    return dict(sort_cat=sort_cat, pack_plane=pack_plane, sample_gather=sample_gather, sample_gather_bwd=sample_gather_bwd,
                 viewdir_gather=viewdir_gather, viewdir_gather_bwd=viewdir_gather_bwd, composite=composite,
                 composite_bwd=composite_bwd, prepare_rays=prepare_rays, sample_pdf=sample_pdf, ipe=ipe,
                 dir_encoding=dir_encoding)
