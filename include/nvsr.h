@@ -449,6 +449,7 @@ int32_t nvsr_mlp_wgrad_chain(const void* const* g, const void* x0_img, int32_t k
  * nvsr_compact_rows: copies the listed rows of n_img tile images (channels[k] each, multiple of 8) and of the four d_raw
  *   planes into dense tiles in LIST order; the tail of the last tile is zero-filled (it then contributes nothing to
  *   nvsr_mlp_wgrad_chain_rows).  max_tiles: capacity of the outputs in 128-row tiles; out_stride >= max_tiles * 128.
+ *   d_raw / d_raw_out may both be NULL (images only).
  * nvsr_mlp_dgrad with row_count + row_ids set gathers the listed rows itself (no separate compaction pass) and emits the
  *   LIST-ordered activation / feature images the weight gradients read; the list's tail rows are zero-filled there too.
  * nvsr_mlp_dgrad with row_count set / nvsr_mlp_wgrad_chain_rows / nvsr_ray_sum_rows / nvsr_sample_gather_bwd_rows: the

@@ -221,6 +221,15 @@ def _packed16(plane_nchw):
     return per["autograd_f16"]
 
 
+def _with_head_ch(layer, ch):
+    """a copy of a ChainLayer whose head (if any) writes channel `ch`"""
+    import copy
+    l = copy.copy(layer)
+    if getattr(l, "head_w", None) is not None:
+        l.head_ch = ch
+    return l
+
+
 class PlanesRadianceTC(torch.autograd.Function):
     """TwoDimPlanesModel.forward (models.py:381-421) for n rays x S samples entirely on this package's kernels, forward
     AND backward: 16-bit tile-image gather -> training forward of both decoder chains on tcgen05 (activation images
@@ -255,16 +264,22 @@ class PlanesRadianceTC(torch.autograd.Function):
                              head_b=f(rB) if i == 3 else None, head_ch=0) for i in range(4)]
         rows = ops.rows_padded(n, S, ops.ROWS_BLOCKED)
         raw = ops.raw_buffer(n, S, ops.ROWS_BLOCKED, ro.device)
-        acts_d = ops.mlp_chain_train(feat_m, Ld, rows, raw, S, n)
         keep = count = None
         if sparse_fwd:
-            # sparse colour path: only the samples whose density (+ the noise the compositing adds) is positive can
-            # reach the maps; their 3-plane features are gathered and decoded in LIST order, the others' rgb stays 0
+            # sparse path: the density chain runs on every sample WITHOUT storing activations (the inference kernel); only
+            # the samples whose density (+ the noise the compositing adds) is positive can reach the maps or carry a
+            # gradient, so only they are decoded by the training kernels — density again (its activations, ~1/6 of the
+            # rows instead of 1 KB per row for all of them) and colour — in LIST order; the others' rgb stays 0
+            ops.mlp_chain(feat_m, Ld, rows, raw, F16, S, n, ops.ROWS_BLOCKED)
             raw[:3].zero_()
             keep, count = ops.keep_rows(raw, n, S, sigma_noise)
+            (feat_m,), _ = ops.compact_rows([feat_m], None, keep, count)
+            scratch = torch.empty_like(raw[3:4])      # the list pass recomputes the listed sigmas: kept out of `raw`
+            acts_d = ops.mlp_chain_train(feat_m, [_with_head_ch(l, 0) for l in Ld], rows, scratch, S, n, row_ids=keep, row_count=count)
             feat_p = ops.sample_gather_rows(ro, rd, packed, ops.FEAT_TILE_F16, z, keep, count)
             acts_c = ops.mlp_chain_train(feat_p, Lc, rows, raw, S, n, row_ids=keep, row_count=count)
         else:
+            acts_d = ops.mlp_chain_train(feat_m, Ld, rows, raw, S, n)
             acts_c = ops.mlp_chain_train(feat_p, Lc, rows, raw, S, n)
         ctx.fwd_list = sparse_fwd
         extra = (keep, count) if sparse_fwd else ()
@@ -322,6 +337,9 @@ class PlanesRadianceTC(torch.autograd.Function):
         # ---- density chain: data gradient, then the weight gradients on the same images
         if rows is None:
             g, dout, d_fm = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S)
+        elif ctx.fwd_list:
+            g, dout, d_fm, _, _ = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S, row_count=count, row_ids=ids,
+                                                acts_listed=True)
         else:
             g, dout, d_fm, acts_d, feat_m = ops.mlp_dgrad(wd, Cc, aW, 3, d_raw, scale, acts_d, n, S, row_count=count, row_ids=ids,
                                                           x0_img=feat_m if want_w else None)

@@ -1043,12 +1043,12 @@ int32_t launch_mlp_tc(const nvsr_mlp_t* m, cudaStream_t st, void* const* act_out
   // compile-time specialisations: the two decoders of the tri-plane model
   const bool rb_ok = a.rb_layer < 0 || a.rb_staged;
   if (act_out) {
-    // training forward: the two fp16 tri-plane chains only, BLOCKED rows; the rgb chain also over a row list (sparse
-    // colour path: the activation images then come out in LIST order)
+    // training forward: the two fp16 tri-plane chains only, BLOCKED rows, dense or over a row list (sparse path: input
+    // and activation images in LIST order, heads to the listed rows)
     for (int l = 0; l < 4; ++l)
       if (!act_out[l] || !aligned16(act_out[l])) return NVSR_ERR_INVALID_ARG;
     if (!(uniform && m->n_layers == 4 && f16 && m->row_order == NVSR_ROWS_BLOCKED)) return NVSR_ERR_UNSUPPORTED;
-    if (lastL.head_n == 1 && a.rb_layer < 0 && !sparse) kernel = mlp_chain_tc_kernel<true, 4, 1, 0, true>;
+    if (lastL.head_n == 1 && a.rb_layer < 0) kernel = mlp_chain_tc_kernel<true, 4, 1, 0, true>;   // dense or over a row list
     else if (lastL.head_n == 3 && a.rb_layer == 0 && sparse) kernel = mlp_chain_tc_kernel<true, 4, 3, 2, true>;
     else if (lastL.head_n == 3 && a.rb_layer == 0 && a.rb_staged) kernel = mlp_chain_tc_kernel<true, 4, 3, 1, true>;
     else return NVSR_ERR_UNSUPPORTED;

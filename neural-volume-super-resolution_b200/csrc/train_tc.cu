@@ -728,8 +728,8 @@ extern "C" int32_t nvsr_nonzero_rows(const float* d_raw, int64_t raw_stride, int
 extern "C" int32_t nvsr_compact_rows(const void* const* src, void* const* dst, const int32_t* channels, int32_t n_img,
                                      const float* d_raw, int64_t raw_stride, float* d_raw_out, int64_t out_stride,
                                      const int32_t* row_ids, const int32_t* count, int64_t max_tiles, void* stream) {
-  NVSR_CHECK_ARG(src && dst && channels && n_img >= 0 && n_img <= 12 && d_raw && d_raw_out && row_ids && count);
-  NVSR_CHECK_ARG(max_tiles >= 0 && max_tiles <= 0x7fffffff && out_stride >= max_tiles * kTileRows);
+  NVSR_CHECK_ARG(src && dst && channels && n_img >= 0 && n_img <= 12 && row_ids && count && ((d_raw == nullptr) == (d_raw_out == nullptr)));
+  NVSR_CHECK_ARG(max_tiles >= 0 && max_tiles <= 0x7fffffff && (!d_raw || out_stride >= max_tiles * kTileRows));
   if (max_tiles == 0) return NVSR_OK;
   CompactArgs a;
   for (int k = 0; k < n_img; ++k) {
@@ -739,7 +739,7 @@ extern "C" int32_t nvsr_compact_rows(const void* const* src, void* const* dst, c
   }
   a.n_img = n_img, a.d_raw = d_raw, a.d_raw_out = d_raw_out, a.raw_stride = raw_stride, a.out_stride = out_stride;
   a.ids = row_ids, a.count = count;
-  compact_rows_kernel<<<dim3((unsigned)max_tiles, (unsigned)(n_img + 1)), kTileRows, 0, (cudaStream_t)stream>>>(a);
+  compact_rows_kernel<<<dim3((unsigned)max_tiles, (unsigned)(n_img + (d_raw ? 1 : 0))), kTileRows, 0, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();
 }
 

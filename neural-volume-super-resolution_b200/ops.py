@@ -737,19 +737,20 @@ def nonzero_rows(d_raw):
 
 
 def compact_rows(images, d_raw, ids, count):
-    """The listed rows of tile images [tiles, C/8, 128, 8] (16-bit) and of d_raw [4, stride], packed densely in LIST
-    order (nvsr_compact_rows; the last tile's tail is zero-filled).  -> (list of compact images, compact d_raw); tiles
-    past the list are left uninitialised."""
+    """The listed rows of tile images [tiles, C/8, 128, 8] (16-bit) and (unless None) of d_raw [4, stride], packed densely
+    in LIST order (nvsr_compact_rows; the last tile's tail is zero-filled).  -> (list of compact images, compact d_raw or
+    None); tiles past the list are left uninitialised."""
     lib = _lib.load()
-    tiles = d_raw.shape[1] // TILE_ROWS
+    tiles = images[0].shape[0] if d_raw is None else d_raw.shape[1] // TILE_ROWS
     out = [torch.empty_like(t) for t in images]
-    d_out = torch.empty_like(d_raw)
+    d_out = None if d_raw is None else torch.empty_like(d_raw)
     k = len(images)
     P = C.c_void_p * k
-    with _OnDevice(d_raw.device):
+    with _OnDevice(images[0].device):
         st = _call("nvsr_compact_rows", lib.nvsr_compact_rows, P(*[t.data_ptr() for t in images]), P(*[t.data_ptr() for t in out]),
-                   (C.c_int32 * k)(*[t.shape[1] * 8 for t in images]), k, _ptr(d_raw), d_raw.stride(0), _ptr(d_out),
-                   d_out.stride(0), _ptr(ids), _ptr(count), tiles, _stream(), rows=tiles * TILE_ROWS)
+                   (C.c_int32 * k)(*[t.shape[1] * 8 for t in images]), k, _ptr(d_raw), 0 if d_raw is None else d_raw.stride(0),
+                   _ptr(d_out), 0 if d_out is None else d_out.stride(0), _ptr(ids), _ptr(count), tiles, _stream(),
+                   rows=tiles * TILE_ROWS)
     _lib.check(st, "nvsr_compact_rows")
     return out, d_out
 
