@@ -459,12 +459,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     tc_fence_after();
     // warp w reads TMEM lanes 32w .. 32w+31 = output rows m; 16 columns (n) at a time
     const int m = warp * 32 + lane;
+    // 128-bit vector reductions (RED.E.ADD.F32x4) when the accumulator rows are 16-byte aligned: the partial sums of all
+    // participating CTAs meet in 128 x n_b addresses, and the L2's reduction rate — not the streaming — bounds a launch
+    // over a short row list (4x fewer operations: 0.30 -> see DESIGN 4.6)
+    const bool vec = ((reinterpret_cast<uintptr_t>(dw) | (uintptr_t)(ldw * 4)) & 15u) == 0;
     for (int c0 = 0; c0 < n_b; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
+      float* row = dw + (int64_t)m * ldw + c0;
+      if (vec) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(dw + (int64_t)m * ldw + c0 + j, __uint_as_float(v[j]) * inv_scale);
+        for (int q = 0; q < 4; ++q)
+          atomicAdd(reinterpret_cast<float4*>(row) + q,
+                    make_float4(__uint_as_float(v[4 * q]) * inv_scale, __uint_as_float(v[4 * q + 1]) * inv_scale,
+                                __uint_as_float(v[4 * q + 2]) * inv_scale, __uint_as_float(v[4 * q + 3]) * inv_scale));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(row + j, __uint_as_float(v[j]) * inv_scale);
+      }
     }
     if (db) {
       uint32_t v[16];
@@ -663,7 +676,7 @@ extern "C" int32_t nvsr_mlp_dgrad(const nvsr_dgrad_t* d, void* stream) {
   NVSR_RETURN_LAST_ERROR();
 }
 
-constexpr int kWgMinTiles = 16;   // tiles per participating CTA before another CTA joins (A/B on B200: 1: 0.93, 8: 0.70, 16: 0.66 ms)
+constexpr int kWgMinTiles = 16;   // tiles per participating CTA before another CTA joins (A/B on B200, scalar reductions: 1: 0.93, 8: 0.70, 16: 0.66 ms; with vector reductions 8 and 16 measure the same)
 
 // n products (<= 5) of one chain in one launch
 static int32_t wgrad_launch(const WgradProblem* pr, int n, int64_t n_tiles, const int32_t* row_count, float inv_scale,
