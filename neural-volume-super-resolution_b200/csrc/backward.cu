@@ -44,16 +44,19 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(GatherBwdArgs a) {
 // row-list variant (the sparse training backward): list row i carries the gradient of BLOCKED row ids[i]
 __global__ void __launch_bounds__(256) gather_bwd_rows_kernel(GatherBwdArgs a) {
   const int chunks = a.g.C / 4;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t i = idx / chunks;
-  if (i >= __ldg(a.count)) return;
-  int ch = (int)(idx % chunks) * 4;
-  const int32_t rid = __ldg(a.ids + i);
-  int64_t ray;
-  int s;
-  blocked_decode(rid / kTileRows, rid % kTileRows, tiles_per_block(a.S), &ray, &s);
-  if (ray >= a.n_rays || s >= a.S) return;
-  bwd::gather_bwd_row(a.g, a.ro, a.rd, a.z[ray * a.S + s], ray, i, ch, a.d_feat_p, a.d_feat_m, a.d_plane);
+  const int TS = tiles_per_block(a.S);
+  // grid-stride over the listed rows (device-side count): no blocks that only exit
+  const int64_t total = (int64_t)__ldg(a.count) * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / chunks;
+    const int ch = (int)(idx % chunks) * 4;
+    const int32_t rid = __ldg(a.ids + i);
+    int64_t ray;
+    int s;
+    blocked_decode(rid / kTileRows, rid % kTileRows, TS, &ray, &s);
+    if (ray >= a.n_rays || s >= a.S) continue;
+    bwd::gather_bwd_row(a.g, a.ro, a.rd, a.z[ray * a.S + s], ray, i, ch, a.d_feat_p, a.d_feat_m, a.d_plane);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -209,8 +212,11 @@ static int32_t gather_bwd_launch(const nvsr_sampler_t* s, const nvsr_planes_t* p
   a.ids = row_ids, a.count = count;
   int64_t total = (row_ids ? max_rows : a.n_rays * a.S) * (a.g.C / 4);
   if (total == 0) return NVSR_OK;
-  if (row_ids)
-    gather_bwd_rows_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  if (row_ids) {
+    int64_t blocks = ceil_div64(total, 256);
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    gather_bwd_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  }
   else
     gather_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();

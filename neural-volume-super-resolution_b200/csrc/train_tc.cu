@@ -580,46 +580,49 @@ struct CompactArgs {
 // grid (tiles, n_img + 1): block (t, k) fills tile t of image k (k == n_img: the four d_raw planes)
 __global__ void __launch_bounds__(kTileRows) compact_rows_kernel(const __grid_constant__ CompactArgs a) {
   const int n = __ldg(a.count);
-  const int64_t tile = blockIdx.x;
-  if (tile * kTileRows >= n) return;
   const int r = threadIdx.x, k = blockIdx.y;
-  const int64_t i = tile * kTileRows + r;
-  const bool live = i < n;
-  const int64_t rid = live ? __ldg(a.ids + i) : 0;
-  if (k == a.n_img) {
+  for (int64_t tile = blockIdx.x; tile * kTileRows < n; tile += gridDim.x) {   // the listed tiles only (device-side count)
+    const int64_t i = tile * kTileRows + r;
+    const bool live = i < n;
+    const int64_t rid = live ? __ldg(a.ids + i) : 0;
+    if (k == a.n_img) {
 #pragma unroll
-    for (int h = 0; h < 4; ++h) a.d_raw_out[h * a.out_stride + i] = live ? __ldg(a.d_raw + h * a.raw_stride + rid) : 0.f;
-    return;
+      for (int h = 0; h < 4; ++h) a.d_raw_out[h * a.out_stride + i] = live ? __ldg(a.d_raw + h * a.raw_stride + rid) : 0.f;
+      continue;
+    }
+    const int chunks = a.chunks[k];
+    const uint4* src = reinterpret_cast<const uint4*>(a.src[k]) + (rid >> 7) * chunks * kTileRows + (rid & 127);
+    uint4* dst = reinterpret_cast<uint4*>(a.dst[k]) + tile * chunks * kTileRows + r;
+    int c = 0;
+    for (; c + 4 <= chunks; c += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = live ? __ldg(src + (c + q) * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[(c + q) * kTileRows] = v[q];
+    }
+    for (; c < chunks; ++c) dst[c * kTileRows] = live ? __ldg(src + c * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
   }
-  const int chunks = a.chunks[k];
-  const uint4* src = reinterpret_cast<const uint4*>(a.src[k]) + (rid >> 7) * chunks * kTileRows + (rid & 127);
-  uint4* dst = reinterpret_cast<uint4*>(a.dst[k]) + tile * chunks * kTileRows + r;
-  int c = 0;
-  for (; c + 4 <= chunks; c += 4) {
-    uint4 v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = live ? __ldg(src + (c + q) * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) dst[(c + q) * kTileRows] = v[q];
-  }
-  for (; c < chunks; ++c) dst[c * kTileRows] = live ? __ldg(src + c * kTileRows) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 // per-ray sums of a LIST-ordered 128-channel image: out[ray(ids[i])][c] += inv_scale * img[i][c]  (out zeroed by the caller)
 __global__ void __launch_bounds__(256)
 ray_sum_rows_kernel(const uint8_t* __restrict__ img, const int32_t* __restrict__ ids, const int32_t* __restrict__ count,
                     int tiles_per_blk, float inv_scale, float* __restrict__ out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = idx >> 4;
-  if (i >= __ldg(count)) return;
-  const int j = (int)(idx & 15);
-  const int32_t rid = __ldg(ids + i);
-  const int64_t ray = (int64_t)((rid >> 7) / tiles_per_blk) * kBlkRays + (rid & (kBlkRays - 1));
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (i >> 7) * (int64_t)kActTileBytes) + j * 128 + (i & 127));
-  const float2 f0 = unpack16x2<true>(v.x), f1 = unpack16x2<true>(v.y), f2 = unpack16x2<true>(v.z), f3 = unpack16x2<true>(v.w);
-  float4* o = reinterpret_cast<float4*>(out + ray * 128 + j * 8);
-  atomicAdd(o, make_float4(f0.x * inv_scale, f0.y * inv_scale, f1.x * inv_scale, f1.y * inv_scale));
-  atomicAdd(o + 1, make_float4(f2.x * inv_scale, f2.y * inv_scale, f3.x * inv_scale, f3.y * inv_scale));
+  // grid-stride over the listed rows only: the list length is known on the device, a grid sized for the capacity would
+  // be mostly blocks that exit at once (65 536 of them for 1 M rows: ~20 us of pure block scheduling)
+  const int64_t total = (int64_t)__ldg(count) * 16;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx >> 4;
+    const int j = (int)(idx & 15);
+    const int32_t rid = __ldg(ids + i);
+    const int64_t ray = (int64_t)((rid >> 7) / tiles_per_blk) * kBlkRays + (rid & (kBlkRays - 1));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (i >> 7) * (int64_t)kActTileBytes) + j * 128 + (i & 127));
+    const float2 f0 = unpack16x2<true>(v.x), f1 = unpack16x2<true>(v.y), f2 = unpack16x2<true>(v.z), f3 = unpack16x2<true>(v.w);
+    float4* o = reinterpret_cast<float4*>(out + ray * 128 + j * 8);
+    atomicAdd(o, make_float4(f0.x * inv_scale, f0.y * inv_scale, f1.x * inv_scale, f1.y * inv_scale));
+    atomicAdd(o + 1, make_float4(f2.x * inv_scale, f2.y * inv_scale, f3.x * inv_scale, f3.y * inv_scale));
+  }
 }
 
 }  // namespace
@@ -752,7 +755,8 @@ extern "C" int32_t nvsr_compact_rows(const void* const* src, void* const* dst, c
   }
   a.n_img = n_img, a.d_raw = d_raw, a.d_raw_out = d_raw_out, a.raw_stride = raw_stride, a.out_stride = out_stride;
   a.ids = row_ids, a.count = count;
-  compact_rows_kernel<<<dim3((unsigned)max_tiles, (unsigned)(n_img + (d_raw ? 1 : 0))), kTileRows, 0, (cudaStream_t)stream>>>(a);
+  const int64_t gx = max_tiles < (int64_t)kNumSMs * 8 ? max_tiles : (int64_t)kNumSMs * 8;
+  compact_rows_kernel<<<dim3((unsigned)gx, (unsigned)(n_img + (d_raw ? 1 : 0))), kTileRows, 0, (cudaStream_t)stream>>>(a);
   NVSR_RETURN_LAST_ERROR();
 }
 
@@ -761,7 +765,9 @@ extern "C" int32_t nvsr_ray_sum_rows(const void* img, const int32_t* row_ids, co
   NVSR_CHECK_ARG(img && row_ids && count && out && max_rows >= 0 && n_samples > 0);
   if (!aligned16(img) || !aligned16(out)) return NVSR_ERR_ALIGNMENT;
   if (max_rows == 0) return NVSR_OK;
-  ray_sum_rows_kernel<<<(unsigned)ceil_div64(max_rows * 16, 256), 256, 0, (cudaStream_t)stream>>>(
+  int64_t blocks = ceil_div64(max_rows * 16, 256);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  ray_sum_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const uint8_t*)img, row_ids, count, tiles_per_block(n_samples), inv_scale, out);
   NVSR_RETURN_LAST_ERROR();
 }
