@@ -17,6 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "--threads", "0",          # the .cu files compile in parallel (one nvcc invocation, all host cores)
 ]
 
 
