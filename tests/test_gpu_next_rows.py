@@ -41,9 +41,11 @@ def test_composite_bwd_matches_oracle_autograd(white, noise_std, mip):
     noise = torch.randn(n, S, generator=g) if noise_std > 0 else None
     g_rgb, g_acc, g_depth, g_w = (torch.randn(n, 3, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g),
                                   torch.randn(n, S, generator=g))
-    # the gradient truth is autograd of the oracle evaluated in float64 on the same fp32 inputs: the fp32 CPU autograd of
-    # cumprod differs between host CPUs at the 1e-5 level on rays whose transmittance underflows (one box measured 4.6e-5
-    # where others measure 7e-8), which is the oracle's conditioning, not the kernel's
+    # the gradient truth is autograd of the oracle evaluated in float64 on the same fp32 inputs.  With the fp32 oracle this
+    # comparison depended on the host: twice, on one GPU box, the oracle's own fp32 gradient came out different (max
+    # 0.45549175 instead of 0.45549244 everywhere else) and the check missed by 4.6e-5, where the same kernels measure
+    # 7e-8 on other boxes — the fp32 CPU autograd of cumprod over near-zero transmittances is the ill-conditioned part,
+    # not the kernel.  float64 takes the host's fp32 kernels out of the reference.
     D = torch.float64
     raw_o = raw.to(D).requires_grad_(True)
     rgb, _, acc, w, depth = O.volume_render_radiance_field(raw_o, z.to(D), rd.to(D), noise_std, white, mip_nerf=mip,
