@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NVSR_ABI_VERSION 3
+#define NVSR_ABI_VERSION 4
 
 #define NVSR_OK 0
 #define NVSR_ERR_INVALID_ARG (-1)

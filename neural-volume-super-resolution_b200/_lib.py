@@ -274,7 +274,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.nvsr_abi_version() != 3:
+    if lib.nvsr_abi_version() != 4:
         raise NvsrError("libnvsr_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.lib_path())
     for s in declared_symbols():
         assert hasattr(raw, s), s
-    assert lib.nvsr_abi_version() == 3
+    assert lib.nvsr_abi_version() == 4
     assert lib.nvsr_status_string(0) == b"ok"
     assert b"invalid" in lib.nvsr_status_string(-1)
 
