@@ -416,6 +416,10 @@ class GraphedStep:
     def __call__(self):
         self.graph.replay()
         self.replays += 1
+        # the replay may have updated parameters (an optimizer step inside the graph) without any `_version` moving:
+        # every packed-plane / packed-weight cache entry made before it is stale from here on
+        from . import scene
+        scene.bump_generation()
         if self.check_every and self.replays % self.check_every == 0:
             _range_check.check_graph()
         return self.result

@@ -96,7 +96,7 @@ _pass_cache = scene._Cache()
 
 
 def _params_sig(model):
-    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+    return tuple((p.data_ptr(), p._version) for p in model.parameters()) + (scene._GENERATION[0],)
 
 
 def _planes_pass(model, scene_id, precision):

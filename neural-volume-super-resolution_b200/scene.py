@@ -380,6 +380,15 @@ def blender_camera(width, theta=30.0, phi=-30.0, radius=4.0, camera_angle_x=0.69
 
 # --------------------------------------------------------------------------------------------------
 # packers
+# Bumped whenever parameters may have changed WITHOUT their `_version` moving — a CUDA-graph replay that contains the
+# optimizer update (autograd.GraphedStep) runs no Python, so no version counter ticks.  Part of every cache signature.
+_GENERATION = [0]
+
+
+def bump_generation():
+    _GENERATION[0] += 1
+
+
 class _Cache:
     """Identity + version cache.  Entries hold a WEAK reference to the object they were made from:
     `id()`/`data_ptr()` alone can be recycled by a new object after the old one died, which would
@@ -391,7 +400,7 @@ class _Cache:
 
     @staticmethod
     def key_of(t):
-        return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+        return (t.data_ptr(), t._version, tuple(t.shape), str(t.device), _GENERATION[0])
 
     def get(self, obj, sig, make):
         import weakref
@@ -592,7 +601,7 @@ class PackedPlanesDecoder:
 def pack_planes_decoder(model, precision):
     params = list(model.density_dec["0"].parameters()) + list(model.rgb_dec["0"].parameters()) + \
         list(model.fc_alpha["0"].parameters()) + list(model.fc_rgb["0"].parameters())
-    sig = tuple((p.data_ptr(), p._version) for p in params)
+    sig = tuple((p.data_ptr(), p._version) for p in params) + (_GENERATION[0],)
     per_prec = _decoder_cache.get(model, sig, dict)
     if precision not in per_prec:
         per_prec[precision] = PackedPlanesDecoder(model, precision)
@@ -647,7 +656,7 @@ class PackedMipDecoder:
 
 def pack_mip_decoder(model, precision):
     params = list(model.parameters())
-    sig = tuple((p.data_ptr(), p._version) for p in params)
+    sig = tuple((p.data_ptr(), p._version) for p in params) + (_GENERATION[0],)
     per_prec = _decoder_cache.get(model, sig, dict)
     if precision not in per_prec:
         per_prec[precision] = PackedMipDecoder(model, precision)

@@ -72,7 +72,9 @@ class PlaneSuperResolver:
             raise NotImplementedError("nvsr_b200.sr: pre-interpolated residual planes (save_interpolated) are not supported")
 
     def _signature(self, sr, lr):
-        return (id(lr), lr.data_ptr(), lr._version) + tuple((p.data_ptr(), p._version) for p in sr.inner_model.parameters())
+        from . import scene
+        return (id(lr), lr.data_ptr(), lr._version, scene._GENERATION[0]) + \
+            tuple((p.data_ptr(), p._version) for p in sr.inner_model.parameters())
 
     @torch.no_grad()
     def super_resolve(self, plane_name, packed_dtype=None, want_nchw=False, compute_dtype=None):

@@ -619,3 +619,51 @@ def test_device_rng_step_needs_no_randoms_and_is_capturable():
         assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in params if p.requires_grad)
     finally:
         A.set_device_rng(False)
+
+
+def test_render_after_graphed_training_sees_the_updated_parameters():
+    """An optimizer step inside a replayed CUDA graph changes planes and weights without moving any `_version` counter —
+    the signature the packed-plane / packed-weight caches key on.  GraphedStep bumps the caches' generation after every
+    replay: a render after graphed training equals the render after `clear_caches()` bit for bit (and is not the
+    pre-training image the caches held)."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=48, view_res=12, seed=8, device=DEV)
+    res, nc, nf = 32, 32, 32
+    pose, focal = scene.blender_camera(res)
+    opt, scfg = scene.render_options(nc, nf, perturb=True), scene.scene_cfg()
+    vopt = scene.render_options(nc, nf)
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(res, res, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0).contiguous()
+    n = batch.shape[1]
+    g = torch.Generator().manual_seed(4)
+    rnd = dict(t_rand=torch.rand(n, nc, generator=g).to(DEV), u=torch.rand(n, nf, generator=g).to(DEV))
+    target = torch.rand(n, 3, generator=g).to(DEV)
+
+    def render():
+        with torch.no_grad():
+            out = nvsr_b200.run_one_iter_of_nerf(res, res, focal, mc, mf, batch, vopt, sid, "validation", scene_config=scfg)
+        return out[3].clone()
+    before = render()
+    for m in (mc, mf):
+        m.train()
+    params = list({id(p): p for m in (mc, mf) for p in m.parameters() if p.requires_grad}.values())
+    optim = torch.optim.SGD(params, lr=0.5)
+
+    def step():
+        optim.zero_grad(set_to_none=True)
+        out = A.run_one_iter_of_nerf(res, res, focal, mc, mf, batch, opt, sid, "train", scene_config=scfg, randoms=rnd)
+        loss = torch.nn.functional.mse_loss(out[0], target) + torch.nn.functional.mse_loss(out[3], target)
+        loss.backward()
+        optim.step()
+        return loss
+    graphed = A.GraphedStep(step, warmup=1)
+    for _ in range(2):
+        graphed()
+    mid = render()                                     # caches now hold the scene as of replay 2 (versions as captured)
+    for _ in range(4):
+        graphed()                                      # ... and these move the parameters with no version tick
+    after = render()
+    scene.clear_caches()
+    fresh = render()
+    assert torch.equal(after, fresh)
+    assert float((after - mid).abs().max()) > 1e-4 and float((mid - before).abs().max()) > 1e-4
