@@ -377,10 +377,11 @@ int32_t nvsr_mlp_chain_split(const float* feat, int32_t k0, const void* const* w
  * NVSR_FEAT_TILE_F16) reading every plane as TWO fp16 x-pair images — planes->plane[d] = pack(fp16(p)), lo_plane[d] =
  * pack(fp16(p - fp16(p))) — in one pass: feat_p (may be NULL) is the colour chain's fp16 tile image, interpolated from the
  * high halves exactly as nvsr_sample_gather does; feat_m32 is the combined feature interpolated from hi + lo in fp32, as
- * an fp32 tile image [tiles][channels/4][128 rows][4] in BLOCKED rows (padding rows zero).
+ * an fp32 tile image [tiles][channels/4][128 rows][4] in BLOCKED rows (padding rows zero); feat_m16 (may be NULL): the
+ * same combined feature rounded to fp16, as the plain gather's featM tile image.
  * nvsr_mlp_chain_split_tiled: nvsr_mlp_chain_split reading that image (k0 = channels). */
 int32_t nvsr_sample_gather_hilo(const nvsr_sampler_t* sampler, const nvsr_planes_t* planes, const void* const lo_plane[3],
-                                void* feat_p, float* feat_m32, float* z_out, void* stream);
+                                void* feat_p, float* feat_m32, void* feat_m16, float* z_out, void* stream);
 int32_t nvsr_mlp_chain_split_tiled(const float* feat_tiles, int32_t k0, const void* const* w_hi, const void* const* w_lo,
                                    const float* const* bias, const float* head_w, const float* head_b, int32_t head_n,
                                    int32_t head_ch, int64_t n_rays, int32_t n_samples, float* raw, int64_t raw_stride,

@@ -213,7 +213,7 @@ SIGNATURES = {
     "nvsr_ray_sum": (c_i32, [c_p, c_i64, c_i32, c_f, c_p, c_p]),
     "nvsr_mlp_wgrad_chain": (c_i32, [C.POINTER(c_p), c_p, c_i32, C.POINTER(c_p), c_p, c_i64, c_f, C.POINTER(c_p), C.POINTER(c_i64),
                                      C.POINTER(c_p), c_p, c_p]),
-    "nvsr_sample_gather_hilo": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), C.POINTER(c_p), c_p, c_p, c_p, c_p]),
+    "nvsr_sample_gather_hilo": (c_i32, [C.POINTER(Sampler), C.POINTER(Planes), C.POINTER(c_p), c_p, c_p, c_p, c_p, c_p]),
     "nvsr_mlp_chain_split_tiled": (c_i32, [c_p, c_i32, C.POINTER(c_p), C.POINTER(c_p), C.POINTER(c_p), c_p, c_p, c_i32, c_i32, c_i64,
                                            c_i32, c_p, c_i64, c_p]),
     "nvsr_sort_cat": (c_i32, [c_p, c_i32, c_p, c_i32, c_i64, c_p, c_p]),

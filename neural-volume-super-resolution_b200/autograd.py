@@ -22,6 +22,7 @@ from .ops import NVSR_F32, FEAT_ROWMAJOR_F32
 
 _state = {"fast_frozen_coarse": False, "decoder": "tc", "loss_scale": 1024.0, "sparse_backward": True, "sparse_forward": True}
 _state["device_rng"] = False
+_state["precise_density"] = False
 _DENSE = "dense"     # planes_model_forward's default for sigma_noise: the caller does not say what the compositing will add
 
 
@@ -46,6 +47,26 @@ def set_device_rng(flag):
 def _rand(shape, device, normal=False):
     dev = device if _state["device_rng"] else None
     return (torch.randn if normal else torch.rand)(tuple(shape), device=dev)
+
+
+def set_precise_density(flag):
+    """False (default).  True: the density of the 'tc' training forward — what decides which samples are lit and what
+    every compositing weight is — comes from the split-operand chain on features interpolated from the planes' fp16 hi + lo
+    halves (the 'fp16-split' inference mode's kernels, fp32-grade sigma) instead of the fp16 chain; activations and
+    gradients stay on the fp16 training kernels.  The fp16 forward moves sigma by up to ~0.1, which flips
+    relu(sigma + noise) on ~0.5 % of the samples and is the whole 6-8 % plane-gradient difference to the fp32 mode
+    (DESIGN 2.3); this removes the flips for ~0.4 ms per 4 096-ray step.  Needs the sparse forward."""
+    _state["precise_density"] = bool(flag)
+
+
+def _packed16_lo(plane_nchw):
+    """fp16 x-pair image of p - fp16(p), cached like `_packed16`"""
+    from . import scene
+    per = scene._plane_cache.get(plane_nchw, scene._Cache.key_of(plane_nchw), dict)
+    if "autograd_f16_lo" not in per:
+        p = plane_nchw.detach().float()
+        per["autograd_f16_lo"] = ops.pack_plane((p - p.half().float()).contiguous(), ops.NVSR_F16, range_check=_range_check)
+    return per["autograd_f16_lo"]
 
 
 def set_sparse_forward(flag):
@@ -250,7 +271,14 @@ class PlanesRadianceTC(torch.autograd.Function):
         F16 = ops.NVSR_F16
         packed = ops.PackedPlanes([_packed16(p) for p in (p0, p1, p2)], F16, geom.box_lo, geom.box_rng, geom.proj,
                                   _cl_image(pv), geom.view_lo_rng, combine=geom.combine)
-        feat_p, feat_m, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, ops.FEAT_TILE_F16, z_in=z, density_only=sparse_fwd)
+        precise = sparse_fwd and _state["precise_density"]
+        fm32 = None
+        if precise:
+            _, fm32, feat_m, _ = ops.sample_gather_hilo(ro, rd, 0.0, 1.0, packed, [_packed16_lo(p) for p in (p0, p1, p2)], z_in=z,
+                                                        density_only=True, want_m16=True)
+            feat_p = None
+        else:
+            feat_p, feat_m, _ = ops.sample_gather(ro, rd, 0.0, 1.0, packed, ops.FEAT_TILE_F16, z_in=z, density_only=sparse_fwd)
         vfeat = ops.viewdir_gather(vd, packed)
         rb = ops.row_bias(vfeat, cW[0].detach()[:, C3:], cB[0])
         f = lambda t: t.detach().float().contiguous()
@@ -270,7 +298,12 @@ class PlanesRadianceTC(torch.autograd.Function):
             # the samples whose density (+ the noise the compositing adds) is positive can reach the maps or carry a
             # gradient, so only they are decoded by the training kernels — density again (its activations, ~1/6 of the
             # rows instead of 1 KB per row for all of them) and colour — in LIST order; the others' rgb stays 0
-            ops.mlp_chain(feat_m, Ld, rows, raw, F16, S, n, ops.ROWS_BLOCKED)
+            if precise:
+                # sigma at fp32 grade: split-operand chain (3 MMA passes per layer) on the hi + lo features
+                lo_w = ops.pack_weights16([w.detach().float() - w.detach().half().float() for w in dW], F16, range_check=_range_check)
+                ops.mlp_chain_split(fm32, wd, lo_w, [f(b) for b in dB], f(aW), f(aB), 3, n, S, raw)
+            else:
+                ops.mlp_chain(feat_m, Ld, rows, raw, F16, S, n, ops.ROWS_BLOCKED)
             raw[:3].zero_()
             keep, count = ops.keep_rows(raw, n, S, sigma_noise)
             (feat_m,), _ = ops.compact_rows([feat_m], None, keep, count)

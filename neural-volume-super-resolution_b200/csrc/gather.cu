@@ -312,6 +312,11 @@ gather_tile_16(SamplerArgs a, PlaneArgs p, uint8_t* __restrict__ featP, uint8_t*
         o1.x = (uint32_t)m2, o1.y = (uint32_t)(m2 >> 32), o1.z = (uint32_t)m3, o1.w = (uint32_t)(m3 >> 32);
         st_stream16(gM32 + (uint32_t)(2 * c) * 2048u, o0);
         st_stream16(gM32 + (uint32_t)(2 * c + 1) * 2048u, o1);
+        if (featM) {   // optionally the same combined features rounded to fp16 (the training decoder's operand image)
+          uint4 o;
+          o.x = pack16_pair<F16>(m0), o.y = pack16_pair<F16>(m1), o.z = pack16_pair<F16>(m2), o.w = pack16_pair<F16>(m3);
+          st_stream16(gM + (uint32_t)c * 2048u, o);
+        }
       } else {
         uint4 o;
         o.x = pack16_pair<F16>(mul_f32x2(mean[0], third)), o.y = pack16_pair<F16>(mul_f32x2(mean[1], third));
@@ -495,7 +500,7 @@ extern "C" int32_t nvsr_sample_gather(const nvsr_sampler_t* s, const nvsr_planes
 }
 
 extern "C" int32_t nvsr_sample_gather_hilo(const nvsr_sampler_t* s, const nvsr_planes_t* pl, const void* const lo_plane[3],
-                                           void* feat_p, float* feat_m32, float* z_out, void* stream) {
+                                           void* feat_p, float* feat_m32, void* feat_m16, float* z_out, void* stream) {
   NVSR_CHECK_ARG(s && pl && lo_plane && feat_m32);
   NVSR_CHECK_ARG(s->n_rays >= 0 && s->n_samples > 0 && s->ro && s->rd && (s->z_in || s->t_vals));
   NVSR_CHECK_ARG(pl->channels > 0 && pl->channels % 8 == 0 && pl->channels <= 64 && (pl->combine == 0 || pl->combine == 1));
@@ -507,7 +512,7 @@ extern "C" int32_t nvsr_sample_gather_hilo(const nvsr_sampler_t* s, const nvsr_p
       return NVSR_ERR_ALIGNMENT;
     lo.plane[d] = lo_plane[d];
   }
-  if ((feat_p && !aligned16(feat_p)) || !aligned16(feat_m32)) return NVSR_ERR_ALIGNMENT;
+  if ((feat_p && !aligned16(feat_p)) || !aligned16(feat_m32) || (feat_m16 && !aligned16(feat_m16))) return NVSR_ERR_ALIGNMENT;
   if (s->n_rays == 0) return NVSR_OK;
   SamplerArgs a{s->n_rays, s->n_samples, s->ro, s->rd, s->near_, s->far_, s->lindisp, s->t_vals, s->t_rand, s->z_in};
   PlaneArgs p;
@@ -522,7 +527,7 @@ extern "C" int32_t nvsr_sample_gather_hilo(const nvsr_sampler_t* s, const nvsr_p
   int64_t n_tiles = rows_padded(s->n_rays, s->n_samples, NVSR_ROWS_BLOCKED) / kTileRows;
   int64_t grid = (int64_t)kNumSMs * 4 * 4;
   if (grid > n_tiles) grid = n_tiles;
-  kernel<<<(unsigned)grid, kGatherThreads, 0, (cudaStream_t)stream>>>(a, p, (uint8_t*)feat_p, nullptr, z_out, n_tiles, lo, feat_m32);
+  kernel<<<(unsigned)grid, kGatherThreads, 0, (cudaStream_t)stream>>>(a, p, (uint8_t*)feat_p, (uint8_t*)feat_m16, z_out, n_tiles, lo, feat_m32);
   NVSR_RETURN_LAST_ERROR();
 }
 

@@ -394,10 +394,11 @@ def sample_gather(ro, rd, near, far, packed, layout, t_vals=None, z_in=None, t_r
 
 
 def sample_gather_hilo(ro, rd, near, far, packed, lo_planes, t_vals=None, z_in=None, t_rand=None, lindisp=False,
-                       n_samples=None, density_only=False):
+                       n_samples=None, density_only=False, want_m16=False):
     """The fp16-split mode's gather (nvsr_sample_gather_hilo): `packed` holds the fp16 x-pair images of fp16(p),
     `lo_planes` those of p - fp16(p).  Returns (featP fp16 tile image or None, featM32 fp32 tile image
-    [tiles, C/4, 128, 4] interpolated from hi + lo, z [n,S])."""
+    [tiles, C/4, 128, 4] interpolated from hi + lo, z [n,S]); with want_m16 a 4-tuple whose third entry is the combined
+    feature as an fp16 tile image [tiles, C/8, 128, 8] as well."""
     lib = _lib.load()
     n = ro.shape[0]
     if z_in is not None:
@@ -410,6 +411,7 @@ def sample_gather_hilo(ro, rd, near, far, packed, lo_planes, t_vals=None, z_in=N
     tiles, Cc = rows // TILE_ROWS, packed.channels
     feat_p = None if density_only else torch.empty((tiles, 3 * Cc // 8, TILE_ROWS, 8), dtype=torch.float16, device=ro.device)
     feat_m = torch.empty((tiles, Cc // 4, TILE_ROWS, 4), dtype=torch.float32, device=ro.device)
+    feat_m16 = torch.empty((tiles, Cc // 8, TILE_ROWS, 8), dtype=torch.float16, device=ro.device) if want_m16 else None
     z_out = torch.empty((n, S), dtype=torch.float32, device=ro.device) if z_in is None else None
     s = _lib.Sampler()
     s.n_rays, s.n_samples = n, S
@@ -422,9 +424,11 @@ def sample_gather_hilo(ro, rd, near, far, packed, lo_planes, t_vals=None, z_in=N
     lo = (C.c_void_p * 3)(*[t.data_ptr() for t in lo_planes])
     with _OnDevice(ro.device):
         st = _call("nvsr_sample_gather", lib.nvsr_sample_gather_hilo, C.byref(s), C.byref(pl), lo, _ptr(feat_p), _ptr(feat_m),
-                   _ptr(z_out), _stream(), rows=n * S,
+                   _ptr(feat_m16), _ptr(z_out), _stream(), rows=n * S,
                    bytes=n * S * ((0 if feat_p is None else 3) * Cc * 2 + Cc * 4 + 4) + n * 24)
     _lib.check(st, "nvsr_sample_gather_hilo")
+    if want_m16:
+        return feat_p, feat_m, feat_m16, (z_out if z_in is None else z_in)
     return feat_p, feat_m, (z_out if z_in is None else z_in)
 
 

@@ -184,6 +184,14 @@ def main():
 
     def rel_l2(x, y):
         return max(float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)) for a, b in zip(x, y) if a is not None and b is not None)
+    # 'tc' with the fp32-grade density forward (set_precise_density): gradients against the same stock-PyTorch step
+    A.set_precise_density(True)
+    res["nvsr_precise_density_ms"] = timed(nvsr_arm)
+    g_p = [None if p.grad is None else p.grad.clone() for p in params]
+    graphed_p = A.GraphedStep(lambda: (zero(), nvsr_arm()))
+    res["nvsr_precise_density_graph_ms"] = timed_replay(graphed_p, args)
+    A.set_precise_density(False)
+    res["max_rel_l2_grad_diff_tc_precise_vs_torch"] = rel_l2(g_p, g_t)
     res["max_rel_l2_grad_diff_graph_vs_eager"] = rel_l2(g_g, g_n)
     res["max_rel_l2_grad_diff_tc_vs_torch"] = rel_l2(g_n, g_t)
     res["max_rel_l2_grad_diff_fp32_mode_vs_torch"] = rel_l2(g_f, g_t)

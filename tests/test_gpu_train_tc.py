@@ -667,3 +667,42 @@ def test_render_after_graphed_training_sees_the_updated_parameters():
     fresh = render()
     assert torch.equal(after, fresh)
     assert float((after - mid).abs().max()) > 1e-4 and float((mid - before).abs().max()) > 1e-4
+
+
+def test_precise_density_forward_closes_most_of_the_gap_to_the_fp32_mode():
+    """`set_precise_density(True)`: sigma of the training forward from the split-operand chain (fp32 grade).  Free-running
+    step with density noise against the fp32 parity mode: the rendered maps come within 1e-3 (the fp16 forward: several
+    1e-3) and the worst plane-gradient deviation drops well below the plain 'tc' step's, whose excess is the
+    relu(sigma + noise) flips of the fp16 sigma."""
+    mc, mf, sid = scene.make_synthetic_scene(plane_res=64, view_res=16, seed=0, device=DEV)
+    for m in (mc, mf):
+        m.train()
+    res, nc, nf = 32, 64, 128
+    pose, focal = scene.blender_camera(res)
+    opt, scfg = scene.render_options(nc, nf, perturb=True, white_background=True, noise_std=0.2), scene.scene_cfg()
+    with torch.no_grad():
+        ro, rd = nvsr_b200.get_ray_bundle(res, res, focal, pose.to(DEV))
+    batch = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+    n = batch.shape[1]
+    g = torch.Generator().manual_seed(3)
+    rnd = dict(t_rand=torch.rand(n, nc, generator=g), u=torch.rand(n, nf, generator=g),
+               noise_c=torch.randn(n, nc, generator=g), noise_f=torch.randn(n, nc + nf, generator=g))
+    target = torch.rand(n, 3, generator=g).to(DEV)
+    try:
+        _, o32, g32 = _step("fp32", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        _, otc, gtc = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        A.set_precise_density(True)
+        ops.LAUNCHES.clear()
+        _, opr, gpr = _step("tc", mc, mf, sid, batch, opt, scfg, rnd, target, res, res, focal)
+        assert ops.LAUNCHES.get("nvsr_mlp_chain_split", 0) == 2
+    finally:
+        A.set_precise_density(False)
+        A.set_decoder("tc")
+
+    def worst(ga):
+        return max(float((ga[k].double() - g32[k].double()).norm() / (g32[k].double().norm() + 1e-30)) for k in g32 if "planes_" in k)
+    e_tc, e_pr = float((otc[0] - o32[0]).abs().max()), float((opr[0] - o32[0]).abs().max())
+    w_tc, w_pr = worst(gtc), worst(gpr)
+    print("coarse map error tc %.2e precise %.2e | worst plane-gradient rel L2 tc %.3f precise %.3f" % (e_tc, e_pr, w_tc, w_pr))
+    assert e_pr <= 1e-3 and e_pr < 0.5 * e_tc
+    assert w_pr < 0.7 * w_tc
