@@ -25,8 +25,10 @@ fine samples (hierarchical sample_pdf) -> rgb/disp/acc, coarse and fine.
   --config cfgN : make another BASELINE.json config the headline workload (default cfg2, the one the metric is quoted on).
           The default line also carries a `configs` block — every BASELINE config at FULL size, 1 warm-up + 3 timed frames
           each, same event timing and sharding — plus, at N = 1: `precision_modes` (the frame in the fp32 1e-3-parity
-          mode), `torch_gpu_baseline` (informative: the reference's op sequence in stock PyTorch on this GPU) and the CPU
-          baselines BASELINE.md §4 asks for (cfg1 exactly: 100x100, 64+0, 1 + 3 frames, median).
+          mode), `torch_gpu_baseline` (informative: the reference's op sequence in stock PyTorch on this GPU), `train_step`
+          (informative, SURVEY §8f-1: the 4 096-ray training iteration of the same path — ours eager / replayed from a CUDA
+          graph / stock PyTorch) and the CPU baselines BASELINE.md §4 asks for (cfg1 exactly: 100x100, 64+0, 1 + 3 frames,
+          median).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -638,6 +640,21 @@ def main():
                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
                     "peak_source": pk["src"], "share_of_step": mlp_ms / total_ms}
 
+    train_step = None
+    if rank == 0 and world == 1 and not args.no_extras and args.config == "cfg2" and args.precision == "fp16":
+        # SURVEY section 8f rank 1 (informative, not the metric): the training iteration of the same path, ours vs stock PyTorch
+        try:
+            import argparse as _ap
+            import importlib.util as _iu
+            _spec = _iu.spec_from_file_location("bench_train_step", os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                                 "scripts", "bench_train_step.py"))
+            _mod = _iu.module_from_spec(_spec)
+            _spec.loader.exec_module(_mod)
+            train_step = _mod.measure(_ap.Namespace(rays=4096, steps=10, warmup=3, plane_res=200, no_torch=False, quick=True))
+        except Exception as e:   # the block is informative: never lose the bench line to it
+            train_step = {"error": repr(e)[:300]}
+        finally:
+            torch.cuda.empty_cache()
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -681,6 +698,7 @@ def main():
             "configs": configs,
             "precision_modes": precision_modes,
             "torch_gpu_baseline": torch_gpu,
+            "train_step": train_step,
         }
         guard.emit(json.dumps(line))
     if world > 1:

@@ -97,15 +97,23 @@ def timed_replay(graphed, args):
     return e0.elapsed_time(e1) / args.steps
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--plane-res", type=int, default=200)
     ap.add_argument("--no-torch", action="store_true", help="only the eager 'tc' arm (for a profiler's launch list)")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    ap.add_argument("--quick", action="store_true",
+                    help="only the eager / graphed 'tc' arms and the stock-PyTorch arm (bench.py's `train_step` block)")
+    args = ap.parse_args(argv)
+    res = measure(args)
+    print(json.dumps(res))
+    return res
+
+
+def measure(args):
+    dev = torch.device("cuda", torch.cuda.current_device())
     mc, mf, sid = scene.make_synthetic_scene(plane_res=args.plane_res, view_res=32, seed=0, device=dev)
     for m in (mc, mf):
         m.box_coords = {k: v.to(dev) for k, v in m.box_coords.items()}
@@ -157,13 +165,22 @@ def main():
     A.set_decoder("tc")          # decoder forward + backward on tcgen05 (the default of the differentiable path)
     res["nvsr_ms"] = timed(nvsr_arm)
     if args.no_torch:
-        print(json.dumps(res))
-        return
+        return res
     g_n = [None if p.grad is None else p.grad.clone() for p in params]
     # the same step captured once into a CUDA graph and replayed (autograd.GraphedStep): no host enqueue cost
     graphed = A.GraphedStep(lambda: (zero(), nvsr_arm()))   # .grad set to None inside: the capture allocates the gradients
     res["nvsr_graph_ms"] = timed_replay(graphed, args)
     g_g = [None if p.grad is None else p.grad.clone() for p in params]
+    if getattr(args, "quick", False):
+        res["torch_ms"] = timed(torch_arm)
+        g_t = [None if p.grad is None else p.grad.clone() for p in params]
+        res["max_rel_l2_grad_diff_tc_vs_torch"] = max(float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+                                                      for a, b in zip(g_n, g_t) if a is not None and b is not None)
+        res["what"] = ("one training iteration of the render path (train_nerf.py:860-905): 4 096 rays, 64 + 128 samples with "
+                       "perturbation, mse on both passes, backward to planes and decoders; nvsr = nvsr_b200.autograd (tcgen05 "
+                       "decoder forward + backward), graph = the same step replayed from a CUDA graph, torch = stock PyTorch "
+                       "ops on the same GPU")
+        return res
     A.set_sparse_backward(False)
     res["nvsr_dense_backward_ms"] = timed(nvsr_arm)
     A.set_sparse_backward(True)
@@ -205,7 +222,7 @@ def main():
         d[0] += 1
         d[1] += a.elapsed_time(b)
     res["kernels_ms"] = {k: {"launches": v[0], "total_ms": v[1]} for k, v in agg.items()}
-    print(json.dumps(res))
+    return res
 
 
 if __name__ == "__main__":
